@@ -1,0 +1,824 @@
+// libdppo_b200.so — C-ABI entry points (include/dppo_b200.h) and host-side orchestration.
+#include "common.cuh"
+#include "simt_kernels.cuh"
+#include "sample_cluster.cuh"
+#include "tc_path.cuh"
+#include <stdarg.h>
+#include <dlfcn.h>
+#include <cmath>
+
+// ------------------------------------------------------------------ error plumbing
+static thread_local char g_err[1024] = "";
+void dppo_set_error(const char* fmt, ...) {
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+}
+extern "C" const char* dppo_last_error(void) { return g_err; }
+extern "C" int dppo_abi_version(void) { return DPPO_ABI_VERSION; }
+extern "C" size_t dppo_cfg_size(void) { return sizeof(dppo_cfg); }
+
+#define KLAUNCH(h) do { (h)->launches++; } while (0)
+#define KCHECK() do { cudaError_t _e = cudaGetLastError(); if (_e != cudaSuccess) { \
+    dppo_set_error("kernel launch failed at %s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(_e)); return -3; } } while (0)
+
+extern "C" void dppo_cfg_default(dppo_cfg* c) {
+    memset(c, 0, sizeof(*c));
+    c->obs_dim = 11; c->action_dim = 3; c->horizon_steps = 4; c->cond_steps = 1;
+    c->denoising_steps = 20; c->ft_denoising_steps = 10; c->time_dim = 16;
+    c->actor_hidden = 512; c->critic_hidden = 256;
+    c->actor_act = DPPO_ACT_RELU; c->critic_act = DPPO_ACT_MISH;
+    c->precision = DPPO_PREC_FP32;
+    c->denoised_clip_value = 1.0f; c->randn_clip_value = 3.0f; c->final_action_clip_value = -1.f;
+    c->min_sampling_denoising_std = 0.1f; c->min_logprob_denoising_std = 0.1f;
+    c->gamma_denoising = 0.99f; c->clip_ploss_coef = 0.01f; c->clip_ploss_coef_base = 0.01f; c->clip_ploss_coef_rate = 3.f;
+    c->clip_vloss_coef = -1.f; c->norm_adv = 1; c->reward_horizon = 4; c->vf_coef = 0.5f;
+    c->logprob_clip_lo = -5.f; c->logprob_clip_hi = 2.f;
+    c->adam_beta1 = 0.9f; c->adam_beta2 = 0.999f; c->adam_eps = 1e-7f;
+    c->weight_decay = 0.004f; c->pretrain_weight_decay = 1e-6f;
+}
+
+// ------------------------------------------------------------------ schedule (sampling.py:7-17, diffusion.py:58-73)
+extern "C" int dppo_ddpm_schedule(int T, float* out) {
+    if (T < 1 || T > 1024 || !out) DPPO_FAIL(-1, "dppo_ddpm_schedule: bad arguments (T=%d)", T);
+    const double s = 0.008;
+    const int steps = T + 1;
+    std::vector<double> acp(steps);
+    for (int i = 0; i < steps; ++i) {
+        // np.linspace(0, steps, steps)[i] = i * steps/(steps-1)
+        double x = (double)i * ((double)steps / (double)(steps - 1));
+        if (i == steps - 1) x = (double)steps;
+        double c = cos(((x / steps) + s) / (1 + s) * M_PI * 0.5);
+        acp[i] = c * c;
+    }
+    double a0 = acp[0];
+    for (int i = 0; i < steps; ++i) acp[i] /= a0;
+    std::vector<float> betas(T), alphas(T), cum(T), cumprev(T);
+    for (int i = 0; i < T; ++i) {
+        double b = 1.0 - acp[i + 1] / acp[i];
+        if (b < 0) b = 0; if (b > 0.999) b = 0.999;
+        betas[i] = (float)b;
+        alphas[i] = 1.0f - betas[i];
+    }
+    float acc = 1.0f;
+    for (int i = 0; i < T; ++i) { acc = acc * alphas[i]; cum[i] = acc; cumprev[i] = i ? cum[i - 1] : 1.0f; }
+    for (int i = 0; i < T; ++i) {
+        float one_m = 1.0f - cum[i];
+        out[SCH_BETAS * T + i] = betas[i];
+        out[SCH_ACP * T + i] = cum[i];
+        out[SCH_SQRT_ACP * T + i] = sqrtf(cum[i]);
+        out[SCH_SQRT_1M_ACP * T + i] = sqrtf(one_m);
+        float recip = 1.0f / cum[i];
+        out[SCH_SQRT_RECIP * T + i] = sqrtf(recip);
+        out[SCH_SQRT_RECIPM1 * T + i] = sqrtf(recip - 1.0f);
+        float var = (betas[i] * (1.0f - cumprev[i])) / one_m;
+        out[SCH_LOGVAR * T + i] = logf(fmaxf(var, 1e-20f));
+        out[SCH_COEF1 * T + i] = (betas[i] * sqrtf(cumprev[i])) / one_m;
+        out[SCH_COEF2 * T + i] = ((1.0f - cumprev[i]) * sqrtf(alphas[i])) / one_m;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------ geometry
+static int make_geom(const dppo_cfg* c, Geom* g) {
+    if (c->obs_dim < 1 || c->action_dim < 1 || c->horizon_steps < 1 || c->cond_steps < 1) return -1;
+    if (c->denoising_steps < 1 || c->denoising_steps > 255 || c->ft_denoising_steps < 0 || c->ft_denoising_steps > c->denoising_steps) return -1;
+    if (c->time_dim < 4 || (c->time_dim & 1) || c->time_dim > 64) return -1;
+    if (c->actor_hidden < 16 || c->actor_hidden > 1024 || c->critic_hidden < 16 || c->critic_hidden > 1024) return -1;
+    if ((c->actor_hidden % 4) || (c->critic_hidden % 4)) return -1;
+    g->Do = c->obs_dim * c->cond_steps; g->A = c->action_dim * c->horizon_steps;
+    g->T = c->denoising_steps; g->K = c->ft_denoising_steps; g->td = c->time_dim;
+    g->H = c->actor_hidden; g->Hc = c->critic_hidden;
+    g->Din = g->A + g->td + g->Do;
+    g->KP = round_up(g->A + g->Do, 4); g->KPc = round_up(g->Do, 4);
+    size_t o = 0; const size_t td = g->td, H = g->H, A = g->A, Hc = g->Hc;
+    g->ao.tw1 = o; o += td * 2 * td; g->ao.tb1 = o; o += 2 * td;
+    g->ao.tw2 = o; o += 2 * td * td; g->ao.tb2 = o; o += td;
+    g->ao.win = o; o += (size_t)g->Din * H; g->ao.bin = o; o += H;
+    g->ao.w1 = o; o += H * H; g->ao.b1 = o; o += H;
+    g->ao.w2 = o; o += H * H; g->ao.b2 = o; o += H;
+    g->ao.w3 = o; o += H * A; g->ao.b3 = o; o += A;
+    g->ao.n = o;
+    o = 0;
+    g->co.win = o; o += (size_t)g->Do * Hc; g->co.bin = o; o += Hc;
+    g->co.w1 = o; o += Hc * Hc; g->co.b1 = o; o += Hc;
+    g->co.w2 = o; o += Hc * Hc; g->co.b2 = o; o += Hc;
+    g->co.w3 = o; o += Hc; g->co.b3 = o; o += 1;
+    g->co.n = o;
+    return 0;
+}
+extern "C" size_t dppo_num_params(const dppo_cfg* cfg, int net) {
+    Geom g; if (!cfg || make_geom(cfg, &g)) return 0;
+    return net == DPPO_NET_CRITIC ? g.co.n : g.ao.n;
+}
+
+// ------------------------------------------------------------------ workspace
+int ws_reserve(dppo_handle* h, size_t bytes, cudaStream_t s) {
+    h->ws.used = 0;
+    if (bytes <= h->ws.cap) return 0;
+    if (h->ws.base) { CUDA_TRY(cudaStreamSynchronize(s)); CUDA_TRY(cudaDeviceSynchronize()); CUDA_TRY(cudaFree(h->ws.base)); h->ws.base = nullptr; h->ws.cap = 0; }
+    size_t cap = bytes + (bytes >> 3) + (1 << 20);
+    CUDA_TRY(cudaMalloc(&h->ws.base, cap));
+    h->ws.cap = cap;
+    return 0;
+}
+
+static inline bool al16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
+
+// ------------------------------------------------------------------ SGEMM dispatch
+static int gemm(dppo_handle* h, cudaStream_t s, bool a_km, bool b_nk, GemmP p, int splits = 1) {
+    if (p.M <= 0 || p.N <= 0) return 0;
+    const int BN = p.N <= 32 ? 32 : 128;
+    if (splits < 1) splits = 1;
+    int kchunk = round_up((p.K + splits - 1) / splits, 16);
+    if (kchunk < 16) kchunk = 16;
+    splits = (p.K + kchunk - 1) / kchunk; if (splits < 1) splits = 1;
+    p.kchunk = kchunk;
+    if (splits == 1) p.cstride = 0;
+    p.vecA = a_km ? (p.lda % 4 == 0 && p.M % 4 == 0 && al16(p.A)) : (p.lda % 4 == 0 && p.K % 4 == 0 && al16(p.A));
+    p.vecB = b_nk ? (p.ldb % 4 == 0 && p.K % 4 == 0 && al16(p.B)) : (p.ldb % 4 == 0 && p.N % 4 == 0 && al16(p.B));
+    p.vecC = (p.ldc % 4 == 0 && al16(p.C) && p.cstride % 4 == 0);
+    dim3 grid((p.N + BN - 1) / BN, (p.M + 127) / 128, splits);
+#define SG(AK, BK_, BNV) sgemm_kernel<AK, BK_, BNV><<<grid, 256, 0, s>>>(p)
+    if (BN == 128) {
+        if (!a_km && !b_nk) SG(false, false, 128); else if (!a_km && b_nk) SG(false, true, 128);
+        else if (a_km && !b_nk) SG(true, false, 128); else SG(true, true, 128);
+    } else {
+        if (!a_km && !b_nk) SG(false, false, 32); else if (!a_km && b_nk) SG(false, true, 32);
+        else if (a_km && !b_nk) SG(true, false, 32); else SG(true, true, 32);
+    }
+#undef SG
+    KLAUNCH(h); KCHECK();
+    return splits;
+}
+static GemmP gp(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int K) {
+    GemmP p; memset(&p, 0, sizeof(p));
+    p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.tconst = 0;
+    return p;
+}
+static inline int nblk(size_t n, int b) { return (int)((n + b - 1) / b); }
+
+// ------------------------------------------------------------------ derived tables
+static int prep_net(dppo_handle* h, int net, cudaStream_t s) {
+    const Geom& g = h->g;
+    if (net == DPPO_NET_CRITIC) {
+        pack_w0_kernel<<<nblk((size_t)g.KPc * g.Hc, 256), 256, 0, s>>>(h->net_w[net] + g.co.win, 0, 0, g.Do, g.KPc, g.Hc, h->ad[net].w0p);
+        KLAUNCH(h); KCHECK();
+    } else {
+        ActorDerived& d = h->ad[net];
+        int threads = g.H < 64 ? 64 : (g.H > 512 ? 512 : round_up(g.H, 32));
+        if (threads < 2 * g.td) threads = round_up(2 * g.td, 32);
+        actor_prep_kernel<<<g.T, threads, 4 * g.td * sizeof(float), s>>>(h->net_w[net], g.ao, g.A, g.td, g.H, d.sinemb, d.thpre, d.temb, d.bt);
+        KLAUNCH(h); KCHECK();
+        pack_w0_kernel<<<nblk((size_t)g.KP * g.H, 256), 256, 0, s>>>(h->net_w[net] + g.ao.win, g.A, g.td, g.Do, g.KP, g.H, d.w0p);
+        KLAUNCH(h); KCHECK();
+    }
+    return tc_refresh_net(h, net, s);
+}
+
+// ------------------------------------------------------------------ create / destroy
+extern "C" int dppo_create(const dppo_cfg* cfg, int device, dppo_handle** out) {
+    if (!cfg || !out) DPPO_FAIL(-1, "dppo_create: null argument");
+    Geom g;
+    if (make_geom(cfg, &g)) DPPO_FAIL(-1, "dppo_create: invalid configuration");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) DPPO_FAIL(-4, "dppo_create: no CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) DPPO_FAIL(-1, "dppo_create: device %d out of range (%d devices)", device, ndev);
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop; CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) DPPO_FAIL(-4, "dppo_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+    dppo_handle* h = new dppo_handle();
+    h->cfg = *cfg; h->device = device; h->g = g; h->sm_count = prop.multiProcessorCount;
+    const size_t nA = g.ao.n, nC = g.co.n;
+    const size_t total = 3 * nA + nC;
+    CUDA_TRY(cudaMalloc(&h->params, total * sizeof(float)));
+    CUDA_TRY(cudaMemset(h->params, 0, total * sizeof(float)));
+    h->net_w[DPPO_NET_ACTOR] = h->params; h->net_n[DPPO_NET_ACTOR] = nA;
+    h->net_w[DPPO_NET_ACTOR_FT] = h->params + nA; h->net_n[DPPO_NET_ACTOR_FT] = nA;
+    h->net_w[DPPO_NET_CRITIC] = h->params + 2 * nA; h->net_n[DPPO_NET_CRITIC] = nC;
+    h->net_w[DPPO_NET_ACTOR_EMA] = h->params + 2 * nA + nC; h->net_n[DPPO_NET_ACTOR_EMA] = nA;
+    for (int net = 0; net < 4; ++net) {
+        ActorDerived& d = h->ad[net];
+        memset(&d, 0, sizeof(d));
+        if (net == DPPO_NET_CRITIC) { CUDA_TRY(cudaMalloc(&d.w0p, (size_t)g.KPc * g.Hc * sizeof(float))); continue; }
+        CUDA_TRY(cudaMalloc(&d.sinemb, (size_t)g.T * g.td * sizeof(float)));
+        CUDA_TRY(cudaMalloc(&d.thpre, (size_t)g.T * 2 * g.td * sizeof(float)));
+        CUDA_TRY(cudaMalloc(&d.temb, (size_t)g.T * g.td * sizeof(float)));
+        CUDA_TRY(cudaMalloc(&d.bt, (size_t)g.T * g.H * sizeof(float)));
+        CUDA_TRY(cudaMalloc(&d.w0p, (size_t)g.KP * g.H * sizeof(float)));
+    }
+    DPPO_TRY(dppo_ddpm_schedule(g.T, h->sched_host));
+    CUDA_TRY(cudaMalloc(&h->sched, SCH_ROWS * g.T * sizeof(float)));
+    CUDA_TRY(cudaMemcpy(h->sched, h->sched_host, SCH_ROWS * g.T * sizeof(float), cudaMemcpyHostToDevice));
+    size_t on[2] = {nA, nA + nC};
+    for (int i = 0; i < 2; ++i) {
+        h->opt[i].n = on[i]; h->opt[i].step = 0;
+        CUDA_TRY(cudaMalloc(&h->opt[i].m, on[i] * sizeof(float))); CUDA_TRY(cudaMemset(h->opt[i].m, 0, on[i] * sizeof(float)));
+        CUDA_TRY(cudaMalloc(&h->opt[i].v, on[i] * sizeof(float))); CUDA_TRY(cudaMemset(h->opt[i].v, 0, on[i] * sizeof(float)));
+    }
+    CUDA_TRY(cudaMalloc(&h->grads, (nA + nC + 16) * sizeof(float)));
+    CUDA_TRY(cudaMemset(h->grads, 0, (nA + nC + 16) * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&h->scalars, 64 * sizeof(float)));
+    CUDA_TRY(cudaMemset(h->scalars, 0, 64 * sizeof(float)));
+    int r = tc_init(h);
+    if (r) { dppo_destroy(h); return r; }
+    for (int net = 0; net < 4; ++net) { r = prep_net(h, net, 0); if (r) { dppo_destroy(h); return r; } }
+    CUDA_TRY(cudaDeviceSynchronize());
+    *out = h;
+    return 0;
+}
+extern "C" void dppo_destroy(dppo_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    tc_destroy(h);
+    if (h->comm) {
+        void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+        if (lib) { typedef int (*fn_t)(void*); fn_t f = (fn_t)dlsym(lib, "ncclCommDestroy"); if (f) f(h->comm); }
+    }
+    cudaFree(h->params); cudaFree(h->sched); cudaFree(h->grads); cudaFree(h->scalars);
+    for (int i = 0; i < 2; ++i) { cudaFree(h->opt[i].m); cudaFree(h->opt[i].v); }
+    for (int net = 0; net < 4; ++net) { ActorDerived& d = h->ad[net]; cudaFree(d.sinemb); cudaFree(d.thpre); cudaFree(d.temb); cudaFree(d.bt); cudaFree(d.w0p); }
+    if (h->ws.base) cudaFree(h->ws.base);
+    if (h->pin) cudaFreeHost(h->pin);
+    if (h->dstage) cudaFree(h->dstage);
+    delete h;
+}
+
+#define ENTER(h) do { if (!(h)) DPPO_FAIL(-1, "null handle"); CUDA_TRY(cudaSetDevice((h)->device)); } while (0)
+
+extern "C" int dppo_set_weights(dppo_handle* h, int net, const float* src, size_t n, int is_device, dppo_stream_t st) {
+    ENTER(h); cudaStream_t s = (cudaStream_t)st;
+    if (net < 0 || net > 3 || !src) DPPO_FAIL(-1, "dppo_set_weights: bad net %d", net);
+    if (n != h->net_n[net]) DPPO_FAIL(-1, "dppo_set_weights: net %d has %zu parameters, got %zu", net, h->net_n[net], n);
+    CUDA_TRY(cudaMemcpyAsync(h->net_w[net], src, n * sizeof(float), is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+    if (!is_device) CUDA_TRY(cudaStreamSynchronize(s));
+    return prep_net(h, net, s);
+}
+extern "C" int dppo_get_weights(dppo_handle* h, int net, float* dst, size_t n, int is_device, dppo_stream_t st) {
+    ENTER(h); cudaStream_t s = (cudaStream_t)st;
+    if (net < 0 || net > 3 || !dst) DPPO_FAIL(-1, "dppo_get_weights: bad net %d", net);
+    if (n != h->net_n[net]) DPPO_FAIL(-1, "dppo_get_weights: net %d has %zu parameters, got %zu", net, h->net_n[net], n);
+    CUDA_TRY(cudaMemcpyAsync(dst, h->net_w[net], n * sizeof(float), is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+    if (!is_device) CUDA_TRY(cudaStreamSynchronize(s));
+    return 0;
+}
+extern "C" int dppo_set_opt_state(dppo_handle* h, int opt, const float* m, const float* v, size_t n, int64_t step, int is_device, dppo_stream_t st) {
+    ENTER(h); cudaStream_t s = (cudaStream_t)st;
+    if (opt < 0 || opt > 1 || n != h->opt[opt].n) DPPO_FAIL(-1, "dppo_set_opt_state: bad slot/size");
+    cudaMemcpyKind k = is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    if (m) CUDA_TRY(cudaMemcpyAsync(h->opt[opt].m, m, n * sizeof(float), k, s));
+    if (v) CUDA_TRY(cudaMemcpyAsync(h->opt[opt].v, v, n * sizeof(float), k, s));
+    h->opt[opt].step = step;
+    if (!is_device) CUDA_TRY(cudaStreamSynchronize(s));
+    return 0;
+}
+extern "C" int dppo_get_opt_state(dppo_handle* h, int opt, float* m, float* v, size_t n, int64_t* step, int is_device, dppo_stream_t st) {
+    ENTER(h); cudaStream_t s = (cudaStream_t)st;
+    if (opt < 0 || opt > 1 || n != h->opt[opt].n) DPPO_FAIL(-1, "dppo_get_opt_state: bad slot/size");
+    cudaMemcpyKind k = is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    if (m) CUDA_TRY(cudaMemcpyAsync(m, h->opt[opt].m, n * sizeof(float), k, s));
+    if (v) CUDA_TRY(cudaMemcpyAsync(v, h->opt[opt].v, n * sizeof(float), k, s));
+    if (step) *step = h->opt[opt].step;
+    if (!is_device) CUDA_TRY(cudaStreamSynchronize(s));
+    return 0;
+}
+extern "C" int dppo_set_ft_denoising_steps(dppo_handle* h, int K) {
+    if (!h) DPPO_FAIL(-1, "null handle");
+    if (K < 0 || K > h->g.T) DPPO_FAIL(-1, "dppo_set_ft_denoising_steps: K=%d outside [0,%d]", K, h->g.T);
+    h->g.K = K; h->cfg.ft_denoising_steps = K;
+    return 0;
+}
+extern "C" int64_t dppo_launch_count(dppo_handle* h) { return h ? h->launches : -1; }
+extern "C" int dppo_last_path(dppo_handle* h) { return h ? h->last_path : -1; }
+
+// ------------------------------------------------------------------ fp32 layer-by-layer forward
+struct FwdBufs { float *h0p, *u, *h1, *v, *out; };
+
+static size_t fwd_ws_bytes(int N, int KP, int H, int NO) {
+    return ws_bytes((size_t)N * KP, 4) + 3 * ws_bytes((size_t)N * H, 4) + ws_bytes((size_t)N * NO, 4);
+}
+static void fwd_take(dppo_handle* h, int N, int KP, int H, int NO, FwdBufs& b) {
+    b.h0p = ws_take<float>(h, (size_t)N * KP);
+    b.u = ws_take<float>(h, (size_t)N * H); b.h1 = ws_take<float>(h, (size_t)N * H); b.v = ws_take<float>(h, (size_t)N * H);
+    b.out = ws_take<float>(h, (size_t)N * NO);
+}
+// actor: out[N][A] = eps; x[N][A], obs row = r / obs_div; t from trow[] or tconst
+static int actor_fwd_fp32(dppo_handle* h, cudaStream_t s, int net, const float* x, const float* obs, int obs_div, int N,
+                          const int* trow, int tconst, FwdBufs& b) {
+    const Geom& g = h->g; const float* w = h->net_w[net]; const ActorDerived& d = h->ad[net];
+    const int act1 = h->cfg.actor_act + 1;
+    pack_h0_kernel<<<nblk((size_t)N * g.KP, 256), 256, 0, s>>>(x, obs, N, g.A, g.Do, g.KP, obs_div, b.h0p); KLAUNCH(h); KCHECK();
+    GemmP p = gp(b.h0p, g.KP, d.w0p, g.H, b.u, g.H, N, g.H, g.KP);
+    p.btab = d.bt; p.ldbt = g.H; p.trow = trow; p.tconst = tconst;
+    DPPO_TRY(gemm(h, s, false, false, p) < 0 ? -3 : 0);
+    p = gp(b.u, g.H, w + g.ao.w1, g.H, b.h1, g.H, N, g.H, g.H); p.aop = act1; p.bias = w + g.ao.b1;
+    DPPO_TRY(gemm(h, s, false, false, p) < 0 ? -3 : 0);
+    p = gp(b.h1, g.H, w + g.ao.w2, g.H, b.v, g.H, N, g.H, g.H); p.aop = act1; p.bias = w + g.ao.b2; p.add = b.u; p.ldadd = g.H;
+    DPPO_TRY(gemm(h, s, false, false, p) < 0 ? -3 : 0);
+    p = gp(b.v, g.H, w + g.ao.w3, g.A, b.out, g.A, N, g.A, g.H); p.bias = w + g.ao.b3;
+    DPPO_TRY(gemm(h, s, false, false, p) < 0 ? -3 : 0);
+    return 0;
+}
+static int critic_fwd_fp32(dppo_handle* h, cudaStream_t s, const float* obs, int N, FwdBufs& b) {
+    const Geom& g = h->g; const float* w = h->net_w[DPPO_NET_CRITIC]; const ActorDerived& d = h->ad[DPPO_NET_CRITIC];
+    const int act1 = h->cfg.critic_act + 1;
+    pack_h0_kernel<<<nblk((size_t)N * g.KPc, 256), 256, 0, s>>>(nullptr, obs, N, 0, g.Do, g.KPc, 1, b.h0p); KLAUNCH(h); KCHECK();
+    GemmP p = gp(b.h0p, g.KPc, d.w0p, g.Hc, b.u, g.Hc, N, g.Hc, g.KPc); p.bias = w + g.co.bin;
+    DPPO_TRY(gemm(h, s, false, false, p) < 0 ? -3 : 0);
+    p = gp(b.u, g.Hc, w + g.co.w1, g.Hc, b.h1, g.Hc, N, g.Hc, g.Hc); p.aop = act1; p.bias = w + g.co.b1;
+    DPPO_TRY(gemm(h, s, false, false, p) < 0 ? -3 : 0);
+    p = gp(b.h1, g.Hc, w + g.co.w2, g.Hc, b.v, g.Hc, N, g.Hc, g.Hc); p.aop = act1; p.bias = w + g.co.b2; p.add = b.u; p.ldadd = g.Hc;
+    DPPO_TRY(gemm(h, s, false, false, p) < 0 ? -3 : 0);
+    p = gp(b.v, g.Hc, w + g.co.w3, 1, b.out, 1, N, 1, g.Hc); p.bias = w + g.co.b3;
+    DPPO_TRY(gemm(h, s, false, false, p) < 0 ? -3 : 0);
+    return 0;
+}
+
+// ------------------------------------------------------------------ fp32 backward (shared by actor / critic)
+struct BwdBufs { float *dv, *dh1, *du, *part; size_t part_floats; };
+static size_t bwd_ws_bytes(const dppo_handle* h, int N, int KP, int H, int NO, int nseg) {
+    size_t colpart = (size_t)320 * (size_t)nseg * H;             // colsum partials
+    size_t gemm_part = (size_t)40 * (size_t)H * H;               // split-K partials
+    size_t pf = colpart > gemm_part ? colpart : gemm_part;
+    return 3 * ws_bytes((size_t)N * H, 4) + ws_bytes(pf, 4) + ws_bytes((size_t)nseg * H, 4) + ws_bytes((size_t)KP * H, 4);
+}
+static int colsum(dppo_handle* h, cudaStream_t s, const float* D, int ld, int N, int ncols, const int* seg, int nseg,
+                  float* part, float* out) {
+    int nb = (N + 127) / 128; if (nb > 320) nb = 320; if (nb < 1) nb = 1;
+    int rpb = (N + nb - 1) / nb; nb = (N + rpb - 1) / rpb;
+    size_t sm = (size_t)nseg * ncols * sizeof(float);
+    if (sm > 48 * 1024) {
+        if (sm > 200 * 1024) DPPO_FAIL(-1, "colsum: %d segments x %d columns does not fit in shared memory", nseg, ncols);
+        CUDA_TRY(cudaFuncSetAttribute(colsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    }
+    colsum_kernel<<<nb, 256, sm, s>>>(D, ld, N, ncols, seg, nseg, rpb, part); KLAUNCH(h); KCHECK();
+    size_t n = (size_t)nseg * ncols;
+    reduce_partials_kernel<<<nblk(n, 256), 256, 0, s>>>(part, nb, n, n, out, 1.f); KLAUNCH(h); KCHECK();
+    return 0;
+}
+// dW[M=in][N=out] = aop(X)[rows][in]^T @ D[rows][out], split over rows, deterministic reduce into out
+static int gemm_dw(dppo_handle* h, cudaStream_t s, const float* X, int ldx, int aop, const float* D, int ldd,
+                   int rows, int M, int N, float* part, float* out) {
+    int tiles = ((M + 127) / 128) * ((N + (N <= 32 ? 31 : 127)) / (N <= 32 ? 32 : 128));
+    int splits = (2 * h->sm_count + tiles - 1) / tiles;
+    if (splits > 40) splits = 40;
+    int maxs = (rows + 255) / 256; if (splits > maxs) splits = maxs; if (splits < 1) splits = 1;
+    GemmP p = gp(X, ldx, D, ldd, part, N, M, N, rows); p.aop = aop; p.cstride = (size_t)M * N;
+    int S = gemm(h, s, true, false, p, splits);
+    if (S < 0) return -3;
+    size_t n = (size_t)M * N;
+    reduce_partials_kernel<<<nblk(n, 256), 256, 0, s>>>(part, S, n, n, out, 1.f); KLAUNCH(h); KCHECK();
+    return 0;
+}
+// generic residual-MLP backward. dout [N][NO]; writes gradient of W1,b1,W2,b2,W3,b3 into gnet at the given
+// offsets, dW0p into dw0p [KP][H], and per-segment column sums of du into Gseg [nseg][H].
+static int mlp_bwd_fp32(dppo_handle* h, cudaStream_t s, const float* w, size_t ow1, size_t ob1, size_t ow2, size_t ob2,
+                        size_t ow3, size_t ob3, int act1, const FwdBufs& f, const float* dout, int N, int KP, int H, int NO,
+                        const int* seg, int nseg, BwdBufs& b, float* gnet, float* dw0p, float* Gseg) {
+    // dv = dout @ W3^T
+    GemmP p = gp(dout, NO, w + ow3, NO, b.dv, H, N, H, NO);
+    DPPO_TRY(gemm(h, s, false, true, p) < 0 ? -3 : 0);
+    // dh1 = (dv @ W2^T) * act'(h1)
+    p = gp(b.dv, H, w + ow2, H, b.dh1, H, N, H, H); p.mask = f.h1; p.ldm = H; p.mask_act = act1;
+    DPPO_TRY(gemm(h, s, false, true, p) < 0 ? -3 : 0);
+    // du = (dh1 @ W1^T) * act'(u) + dv
+    p = gp(b.dh1, H, w + ow1, H, b.du, H, N, H, H); p.mask = f.u; p.ldm = H; p.mask_act = act1; p.add = b.dv; p.ldadd = H;
+    DPPO_TRY(gemm(h, s, false, true, p) < 0 ? -3 : 0);
+    // weight gradients
+    DPPO_TRY(gemm_dw(h, s, f.v, H, 0, dout, NO, N, H, NO, b.part, gnet + ow3));
+    DPPO_TRY(gemm_dw(h, s, f.h1, H, act1, b.dv, H, N, H, H, b.part, gnet + ow2));
+    DPPO_TRY(gemm_dw(h, s, f.u, H, act1, b.dh1, H, N, H, H, b.part, gnet + ow1));
+    DPPO_TRY(gemm_dw(h, s, f.h0p, KP, 0, b.du, H, N, KP, H, b.part, dw0p));
+    // bias gradients
+    DPPO_TRY(colsum(h, s, dout, NO, N, NO, nullptr, 1, b.part, gnet + ob3));
+    DPPO_TRY(colsum(h, s, b.dv, H, N, H, nullptr, 1, b.part, gnet + ob2));
+    DPPO_TRY(colsum(h, s, b.dh1, H, N, H, nullptr, 1, b.part, gnet + ob1));
+    DPPO_TRY(colsum(h, s, b.du, H, N, H, seg, nseg, b.part, Gseg));
+    return 0;
+}
+static void bwd_take(dppo_handle* h, int N, int KP, int H, int nseg, BwdBufs& b, float** Gseg, float** dw0p) {
+    b.dv = ws_take<float>(h, (size_t)N * H); b.dh1 = ws_take<float>(h, (size_t)N * H); b.du = ws_take<float>(h, (size_t)N * H);
+    size_t colpart = (size_t)320 * (size_t)nseg * H, gemm_part = (size_t)40 * (size_t)H * H;
+    b.part_floats = colpart > gemm_part ? colpart : gemm_part;
+    b.part = ws_take<float>(h, b.part_floats);
+    *Gseg = ws_take<float>(h, (size_t)nseg * H);
+    *dw0p = ws_take<float>(h, (size_t)KP * H);
+}
+static int actor_bwd_fp32(dppo_handle* h, cudaStream_t s, int net, const FwdBufs& f, const float* deps, int N, const int* trow,
+                          BwdBufs& b, float* Gseg, float* dw0p, float* gnet) {
+    const Geom& g = h->g; const float* w = h->net_w[net]; const ActorDerived& d = h->ad[net];
+    DPPO_TRY(mlp_bwd_fp32(h, s, w, g.ao.w1, g.ao.b1, g.ao.w2, g.ao.b2, g.ao.w3, g.ao.b3, h->cfg.actor_act + 1, f, deps, N,
+                          g.KP, g.H, g.A, trow, g.T, b, gnet, dw0p, Gseg));
+    size_t sm = (size_t)(g.T * g.td * 3) * sizeof(float);
+    time_backward_kernel<<<1, 512, sm, s>>>(w, g.ao, g.A, g.td, g.H, g.T, Gseg, d.sinemb, d.thpre, d.temb, gnet); KLAUNCH(h); KCHECK();
+    unpack_dw0_kernel<<<nblk((size_t)(g.A + g.Do) * g.H, 256), 256, 0, s>>>(dw0p, g.A, g.td, g.Do, g.H, gnet + g.ao.win); KLAUNCH(h); KCHECK();
+    return 0;
+}
+static int critic_bwd_fp32(dppo_handle* h, cudaStream_t s, const FwdBufs& f, const float* dval, int N,
+                           BwdBufs& b, float* Gseg, float* dw0p, float* gnet) {
+    const Geom& g = h->g; const float* w = h->net_w[DPPO_NET_CRITIC];
+    DPPO_TRY(mlp_bwd_fp32(h, s, w, g.co.w1, g.co.b1, g.co.w2, g.co.b2, g.co.w3, g.co.b3, h->cfg.critic_act + 1, f, dval, N,
+                          g.KPc, g.Hc, 1, nullptr, 1, b, gnet, dw0p, Gseg));
+    CUDA_TRY(cudaMemcpyAsync(gnet + g.co.bin, Gseg, g.Hc * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    unpack_dw0_kernel<<<nblk((size_t)g.Do * g.Hc, 256), 256, 0, s>>>(dw0p, 0, 0, g.Do, g.Hc, gnet + g.co.win); KLAUNCH(h); KCHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------ forward-only entry points
+static const int ROW_CHUNK = 1 << 18;
+
+extern "C" int dppo_actor_forward(dppo_handle* h, int net, const float* x, const int32_t* t, const float* obs,
+                                  int N, float* eps, dppo_stream_t st) {
+    ENTER(h); cudaStream_t s = (cudaStream_t)st; const Geom& g = h->g;
+    if (net < 0 || net > 3 || net == DPPO_NET_CRITIC || !x || !t || !obs || !eps || N < 0) DPPO_FAIL(-1, "dppo_actor_forward: bad arguments");
+    for (int r0 = 0; r0 < N; r0 += ROW_CHUNK) {
+        int n = N - r0 < ROW_CHUNK ? N - r0 : ROW_CHUNK;
+        if (tc_eligible(h, n)) { DPPO_TRY(tc_actor_forward(h, s, net, x + (size_t)r0 * g.A, obs + (size_t)r0 * g.Do, 1, n, t + r0, 0, eps + (size_t)r0 * g.A)); continue; }
+        DPPO_TRY(ws_reserve(h, fwd_ws_bytes(n, g.KP, g.H, g.A), s));
+        FwdBufs b; fwd_take(h, n, g.KP, g.H, g.A, b);
+        DPPO_TRY(actor_fwd_fp32(h, s, net, x + (size_t)r0 * g.A, obs + (size_t)r0 * g.Do, 1, n, t + r0, 0, b));
+        CUDA_TRY(cudaMemcpyAsync(eps + (size_t)r0 * g.A, b.out, (size_t)n * g.A * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    }
+    return 0;
+}
+extern "C" int dppo_value(dppo_handle* h, const float* obs, int N, float* v, dppo_stream_t st) {
+    ENTER(h); cudaStream_t s = (cudaStream_t)st; const Geom& g = h->g;
+    if (!obs || !v || N < 0) DPPO_FAIL(-1, "dppo_value: bad arguments");
+    for (int r0 = 0; r0 < N; r0 += ROW_CHUNK) {
+        int n = N - r0 < ROW_CHUNK ? N - r0 : ROW_CHUNK;
+        DPPO_TRY(ws_reserve(h, fwd_ws_bytes(n, g.KPc, g.Hc, 1), s));
+        FwdBufs b; fwd_take(h, n, g.KPc, g.Hc, 1, b);
+        DPPO_TRY(critic_fwd_fp32(h, s, obs + (size_t)r0 * g.Do, n, b));
+        CUDA_TRY(cudaMemcpyAsync(v + r0, b.out, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    }
+    return 0;
+}
+
+static int logprobs_impl(dppo_handle* h, cudaStream_t s, const float* obs, const float* prev, const float* nxt,
+                         const float* chains, const int* inds, int N, int use_base, float* logp) {
+    const Geom& g = h->g;
+    if (g.K < 1) DPPO_FAIL(-1, "log-probs need ft_denoising_steps >= 1");
+    const int net = use_base ? DPPO_NET_ACTOR : DPPO_NET_ACTOR_FT;   // t < K for every row (diffusion_vpg.py:165-180)
+    // chains mode processes whole chains per chunk (row = b*K + k)
+    const int chunk_rows = chains ? (ROW_CHUNK / g.K) * g.K : ROW_CHUNK;
+    for (int r0 = 0; r0 < N; r0 += chunk_rows) {
+        int n = N - r0 < chunk_rows ? N - r0 : chunk_rows;
+        size_t need = fwd_ws_bytes(n, g.KP, g.H, g.A) + ws_bytes(n, 4) + ws_bytes((size_t)n * g.A, 4);
+        DPPO_TRY(ws_reserve(h, need, s));
+        FwdBufs b; fwd_take(h, n, g.KP, g.H, g.A, b);
+        int* trow = ws_take<int>(h, n);
+        float* pv = ws_take<float>(h, (size_t)n * g.A);
+        const float* xin; const float* ob; int obs_div;
+        const float* ch = nullptr;
+        if (chains) {
+            ch = chains + (size_t)(r0 / g.K) * (g.K + 1) * g.A;
+            make_trow_kernel<<<nblk(n, 256), 256, 0, s>>>(nullptr, n, g.K, 1, trow); KLAUNCH(h); KCHECK();
+            chains_prev_kernel<<<nblk((size_t)n * g.A, 256), 256, 0, s>>>(ch, n, g.A, g.K, pv); KLAUNCH(h); KCHECK();
+            xin = pv; ob = obs + (size_t)(r0 / g.K) * g.Do; obs_div = g.K;
+        } else {
+            make_trow_kernel<<<nblk(n, 256), 256, 0, s>>>(inds + r0, n, g.K, 0, trow); KLAUNCH(h); KCHECK();
+            xin = prev + (size_t)r0 * g.A; ob = obs + (size_t)r0 * g.Do; obs_div = 1;
+        }
+        const float* epsp;
+        if (tc_eligible(h, n)) { DPPO_TRY(tc_actor_forward(h, s, net, xin, ob, obs_div, n, trow, 0, b.out)); epsp = b.out; }
+        else { DPPO_TRY(actor_fwd_fp32(h, s, net, xin, ob, obs_div, n, trow, 0, b)); epsp = b.out; }
+        logprob_kernel<<<nblk((size_t)n * g.A, 256), 256, 0, s>>>(chains ? nullptr : prev + (size_t)r0 * g.A,
+            chains ? nullptr : nxt + (size_t)r0 * g.A, ch, epsp, trow, n, g.A, g.K, h->sched, g.T,
+            h->cfg.denoised_clip_value, h->cfg.min_logprob_denoising_std, logp + (size_t)r0 * g.A);
+        KLAUNCH(h); KCHECK();
+    }
+    return 0;
+}
+extern "C" int dppo_logprobs(dppo_handle* h, const float* obs, const float* chains, int B, int use_base_policy,
+                             float* logp, dppo_stream_t st) {
+    ENTER(h);
+    if (!obs || !chains || !logp || B < 0) DPPO_FAIL(-1, "dppo_logprobs: bad arguments");
+    if ((int64_t)B * h->g.K > 2000000000LL) DPPO_FAIL(-1, "dppo_logprobs: too many rows");
+    return logprobs_impl(h, (cudaStream_t)st, obs, nullptr, nullptr, chains, nullptr, B * h->g.K, use_base_policy, logp);
+}
+extern "C" int dppo_logprobs_subsample(dppo_handle* h, const float* obs, const float* chains_prev, const float* chains_next,
+                                       const int32_t* denoising_inds, int N, int use_base_policy, float* logp, dppo_stream_t st) {
+    ENTER(h);
+    if (!obs || !chains_prev || !chains_next || !denoising_inds || !logp || N < 0) DPPO_FAIL(-1, "dppo_logprobs_subsample: bad arguments");
+    return logprobs_impl(h, (cudaStream_t)st, obs, chains_prev, chains_next, nullptr, denoising_inds, N, use_base_policy, logp);
+}
+
+// ------------------------------------------------------------------ sampling
+template <int AP, int R>
+static int launch_cluster(dppo_handle* h, cudaStream_t s, ClusterSampleP& p, int B, bool probe_only, int* max_clusters) {
+    auto kern = sample_cluster_kernel<AP, R>;
+    size_t smem = cluster_sample_smem_floats<AP, R>() * sizeof(float);
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CS_C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1; cfg.blockDim = dim3(CS_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cfg.gridDim = dim3(CS_C * 8);
+    int nc = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveClusters(&nc, kern, &cfg));
+    if (max_clusters) *max_clusters = nc;
+    if (probe_only) return 0;
+    if (nc < 1) DPPO_FAIL(-5, "cluster sampler: no 16-CTA cluster can be resident");
+    p.nchunks = (B + R - 1) / R;
+    int ncl = p.nchunks < nc ? p.nchunks : nc;
+    cfg.gridDim = dim3(CS_C * ncl);
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, (const ClusterSampleP)p));
+    KLAUNCH(h);
+    return 0;
+}
+template <int AP>
+static int cluster_dispatch(dppo_handle* h, cudaStream_t s, ClusterSampleP& p, int B) {
+    int nc = h->cluster_max;
+    if (nc < 0) {
+        DPPO_TRY((launch_cluster<AP, 8>(h, s, p, B, true, &nc)));
+        h->cluster_max = nc;
+    }
+    if (nc < 1) DPPO_FAIL(-5, "cluster sampler unavailable on this device");
+    int per = (B + nc - 1) / nc;
+    if (per <= 2) return launch_cluster<AP, 2>(h, s, p, B, false, nullptr);
+    if (per <= 4) return launch_cluster<AP, 4>(h, s, p, B, false, nullptr);
+    if (per <= 6) return launch_cluster<AP, 6>(h, s, p, B, false, nullptr);
+    return launch_cluster<AP, 8>(h, s, p, B, false, nullptr);
+}
+
+static int sample_layered_fp32(dppo_handle* h, cudaStream_t s, const float* obs, int B, int use_base, SampleHyper hp,
+                               uint64_t seed, uint64_t offset, int64_t row_offset, const float* xT, const float* noise,
+                               float* actions, float* chains, bool tensor) {
+    const Geom& g = h->g;
+    size_t need = fwd_ws_bytes(B, g.KP, g.H, g.A) + ws_bytes((size_t)B * g.A, 4);
+    DPPO_TRY(ws_reserve(h, need, s));
+    FwdBufs b; fwd_take(h, B, g.KP, g.H, g.A, b);
+    float* x = ws_take<float>(h, (size_t)B * g.A);
+    sample_init_kernel<<<nblk((size_t)B * g.A, 256), 256, 0, s>>>(x, xT, B, g.A, seed, offset, row_offset, chains, g.K, g.K == g.T);
+    KLAUNCH(h); KCHECK();
+    for (int i = 0; i < g.T; ++i) {
+        const int t = g.T - 1 - i;
+        const int net = (t < g.K && !use_base) ? DPPO_NET_ACTOR_FT : DPPO_NET_ACTOR;
+        if (tensor) DPPO_TRY(tc_actor_forward(h, s, net, x, obs, 1, B, nullptr, t, b.out));
+        else DPPO_TRY(actor_fwd_fp32(h, s, net, x, obs, 1, B, nullptr, t, b));
+        sample_update_kernel<<<nblk((size_t)B * g.A, 256), 256, 0, s>>>(x, b.out, noise, B, g.A, t, i, h->sched, g.T, hp,
+            seed, offset, row_offset, chains, g.K, t <= g.K ? g.K - t : -1, actions);
+        KLAUNCH(h); KCHECK();
+    }
+    return 0;
+}
+
+extern "C" int dppo_sample(dppo_handle* h, const float* obs, int B, int deterministic, int use_base_policy,
+                           float min_sampling_std, uint64_t seed, uint64_t offset, int64_t row_offset,
+                           const float* xT, const float* noise, float* actions, float* chains, dppo_stream_t st) {
+    ENTER(h); cudaStream_t s = (cudaStream_t)st; const Geom& g = h->g;
+    if (!obs || !actions || B < 0) DPPO_FAIL(-1, "dppo_sample: bad arguments");
+    if (B == 0) return 0;
+    SampleHyper hp;
+    hp.dcv = h->cfg.denoised_clip_value; hp.rcv = h->cfg.randn_clip_value; hp.facv = h->cfg.final_action_clip_value;
+    hp.min_std = min_sampling_std >= 0.f ? min_sampling_std : h->cfg.min_sampling_denoising_std;
+    hp.deterministic = deterministic;
+    const bool tensor = tc_eligible(h, B);
+    const bool cluster_shape = (g.H == CS_H && g.A <= 32 && h->cfg.actor_act == DPPO_ACT_RELU && h->force_path != 2);
+    // the persistent cluster kernel wins while the chain is latency bound; beyond that rows are
+    // plentiful enough for real GEMM tiles
+    const int cluster_limit = h->cfg.precision == DPPO_PREC_BF16 ? 1024 : 4096;
+    if (cluster_shape && !tensor && (B <= cluster_limit || h->force_path == 1) && h->cluster_max != 0) {
+        ClusterSampleP p; memset(&p, 0, sizeof(p));
+        p.w[0] = h->net_w[DPPO_NET_ACTOR]; p.w[1] = h->net_w[DPPO_NET_ACTOR_FT];
+        p.bt[0] = h->ad[DPPO_NET_ACTOR].bt; p.bt[1] = h->ad[DPPO_NET_ACTOR_FT].bt;
+        p.o = g.ao; p.obs = obs; p.xT = xT; p.noise = noise; p.actions = actions; p.chains = chains; p.sch = h->sched;
+        p.B = B; p.A = g.A; p.Do = g.Do; p.T = g.T; p.K = g.K; p.td = g.td; p.use_base_policy = use_base_policy;
+        p.hp = hp; p.seed = seed; p.offset = offset; p.row_offset = row_offset;
+        int r = g.A <= 12 ? cluster_dispatch<12>(h, s, p, B) : (g.A <= 24 ? cluster_dispatch<24>(h, s, p, B) : cluster_dispatch<32>(h, s, p, B));
+        if (r == 0) { h->last_path = 1; return 0; }
+        if (h->force_path == 1) return r;
+        h->cluster_max = 0;   // not launchable here: remember and fall through to the layered path
+        (void)cudaGetLastError();
+    }
+    h->last_path = tensor ? 3 : 2;
+    return sample_layered_fp32(h, s, obs, B, use_base_policy, hp, seed, offset, row_offset, xT, noise, actions, chains, tensor);
+}
+
+static int stage_reserve(dppo_handle* h, size_t bytes) {
+    if (bytes <= h->dstage_cap) return 0;
+    if (h->dstage) { CUDA_TRY(cudaDeviceSynchronize()); CUDA_TRY(cudaFree(h->dstage)); h->dstage = nullptr; h->dstage_cap = 0; }
+    size_t cap = bytes + (bytes >> 2) + 4096;
+    CUDA_TRY(cudaMalloc(&h->dstage, cap));
+    h->dstage_cap = cap;
+    return 0;
+}
+static inline size_t a256(size_t b) { return (b + 255) / 256 * 256; }
+
+extern "C" int dppo_sample_host(dppo_handle* h, const float* obs, int B, int deterministic, int use_base_policy,
+                                float min_sampling_std, uint64_t seed, uint64_t offset, int64_t row_offset,
+                                const float* xT, const float* noise, float* actions, float* chains, dppo_stream_t st) {
+    ENTER(h); cudaStream_t s = (cudaStream_t)st; const Geom& g = h->g;
+    if (!obs || !actions || B < 0) DPPO_FAIL(-1, "dppo_sample_host: bad arguments");
+    if (B == 0) return 0;
+    size_t b_obs = a256((size_t)B * g.Do * 4), b_x = a256((size_t)B * g.A * 4), b_nz = a256((size_t)g.T * B * g.A * 4);
+    size_t b_ch = a256((size_t)B * (g.K + 1) * g.A * 4);
+    DPPO_TRY(stage_reserve(h, b_obs + 2 * b_x + b_nz + b_ch));
+    char* p = h->dstage;
+    float* d_obs = (float*)p; p += b_obs;
+    float* d_xT = (float*)p; p += b_x;
+    float* d_act = (float*)p; p += b_x;
+    float* d_nz = (float*)p; p += b_nz;
+    float* d_ch = (float*)p;
+    CUDA_TRY(cudaMemcpyAsync(d_obs, obs, (size_t)B * g.Do * 4, cudaMemcpyHostToDevice, s));
+    if (xT) CUDA_TRY(cudaMemcpyAsync(d_xT, xT, (size_t)B * g.A * 4, cudaMemcpyHostToDevice, s));
+    if (noise) CUDA_TRY(cudaMemcpyAsync(d_nz, noise, (size_t)g.T * B * g.A * 4, cudaMemcpyHostToDevice, s));
+    DPPO_TRY(dppo_sample(h, d_obs, B, deterministic, use_base_policy, min_sampling_std, seed, offset, row_offset,
+                         xT ? d_xT : nullptr, noise ? d_nz : nullptr, d_act, chains ? d_ch : nullptr, st));
+    CUDA_TRY(cudaMemcpyAsync(actions, d_act, (size_t)B * g.A * 4, cudaMemcpyDeviceToHost, s));
+    if (chains) CUDA_TRY(cudaMemcpyAsync(chains, d_ch, (size_t)B * (g.K + 1) * g.A * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return 0;
+}
+
+// ------------------------------------------------------------------ NCCL (dlopen)
+struct NcclUid { char internal[128]; };
+typedef int (*nccl_get_uid_t)(NcclUid*);
+typedef int (*nccl_init_rank_t)(void**, int, NcclUid, int);
+typedef int (*nccl_allreduce_t)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef const char* (*nccl_errstr_t)(int);
+static void* g_nccl = nullptr;
+static nccl_allreduce_t g_allreduce = nullptr;
+static int nccl_load() {
+    if (g_nccl) return 0;
+    g_nccl = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!g_nccl) DPPO_FAIL(-6, "dlopen(libnccl.so.2) failed: %s", dlerror());
+    g_allreduce = (nccl_allreduce_t)dlsym(g_nccl, "ncclAllReduce");
+    if (!g_allreduce) DPPO_FAIL(-6, "ncclAllReduce not found in libnccl.so.2");
+    return 0;
+}
+extern "C" int dppo_comm_unique_id(char* id128) {
+    if (!id128) DPPO_FAIL(-1, "dppo_comm_unique_id: null");
+    DPPO_TRY(nccl_load());
+    nccl_get_uid_t f = (nccl_get_uid_t)dlsym(g_nccl, "ncclGetUniqueId");
+    if (!f) DPPO_FAIL(-6, "ncclGetUniqueId not found");
+    NcclUid u; int r = f(&u);
+    if (r) DPPO_FAIL(-6, "ncclGetUniqueId failed (%d)", r);
+    memcpy(id128, u.internal, 128);
+    return 0;
+}
+extern "C" int dppo_comm_init(dppo_handle* h, const char* id128, int rank, int world) {
+    ENTER(h);
+    if (!id128 || world < 1 || rank < 0 || rank >= world) DPPO_FAIL(-1, "dppo_comm_init: bad arguments");
+    if (world == 1) { h->rank = 0; h->world = 1; return 0; }
+    DPPO_TRY(nccl_load());
+    nccl_init_rank_t f = (nccl_init_rank_t)dlsym(g_nccl, "ncclCommInitRank");
+    if (!f) DPPO_FAIL(-6, "ncclCommInitRank not found");
+    NcclUid u; memcpy(u.internal, id128, 128);
+    void* comm = nullptr;
+    int r = f(&comm, world, u, rank);
+    if (r) {
+        nccl_errstr_t es = (nccl_errstr_t)dlsym(g_nccl, "ncclGetErrorString");
+        DPPO_FAIL(-6, "ncclCommInitRank failed: %s", es ? es(r) : "?");
+    }
+    h->comm = comm; h->rank = rank; h->world = world;
+    return 0;
+}
+static int allreduce_sum(dppo_handle* h, float* buf, size_t n, cudaStream_t s) {
+    if (h->world <= 1) return 0;
+    if (!h->comm || !g_allreduce) DPPO_FAIL(-6, "all-reduce requested but no communicator attached");
+    int r = g_allreduce(buf, buf, n, 7 /*ncclFloat32*/, 0 /*ncclSum*/, h->comm, s);
+    if (r) DPPO_FAIL(-6, "ncclAllReduce failed (%d)", r);
+    return 0;
+}
+
+// ------------------------------------------------------------------ AdamW
+static int adam_apply(dppo_handle* h, cudaStream_t s, int opt, float* w, const float* g, size_t n, float lr, float wd) {
+    OptState& o = h->opt[opt];
+    o.step += 1;
+    const float b1 = h->cfg.adam_beta1, b2 = h->cfg.adam_beta2;
+    float b1p = powf(b1, (float)o.step), b2p = powf(b2, (float)o.step);
+    float alpha = lr * sqrtf(1.f - b2p) / (1.f - b1p);
+    adamw_kernel<<<nblk(n, 256), 256, 0, s>>>(w, g, o.m, o.v, n, lr, alpha, b1, b2, h->cfg.adam_eps, wd); KLAUNCH(h); KCHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------ PPO step
+extern "C" int dppo_ppo_step(dppo_handle* h, const float* obs, const float* prev, const float* nxt,
+                             const int32_t* inds, const float* returns, const float* oldvalues,
+                             const float* advantages, const float* oldlogp, int N, int64_t N_global,
+                             float adv_mean, float adv_std, float lr, int apply,
+                             float* metrics8, float* grads_out, dppo_stream_t st) {
+    ENTER(h); cudaStream_t s = (cudaStream_t)st; const Geom& g = h->g;
+    if (!obs || !prev || !nxt || !inds || !returns || !oldvalues || !advantages || !oldlogp || N < 1 || N_global < N)
+        DPPO_FAIL(-1, "dppo_ppo_step: bad arguments");
+    if (g.K < 1) DPPO_FAIL(-1, "dppo_ppo_step: ft_denoising_steps must be >= 1");
+    if (adv_std < 0.f && N_global != N) DPPO_FAIL(-1, "dppo_ppo_step: global advantage statistics are required when rows are sharded");
+    const size_t nA = g.ao.n, nC = g.co.n;
+    float* gr = h->grads;
+    if (tc_eligible(h, N)) {
+        DPPO_TRY(tc_ppo_step(h, s, obs, prev, nxt, inds, returns, oldvalues, advantages, oldlogp, N, N_global, adv_mean, adv_std));
+    } else {
+        const int nlb = nblk(N, 128);
+        size_t need = fwd_ws_bytes(N, g.KP, g.H, g.A) + fwd_ws_bytes(N, g.KPc, g.Hc, 1)
+                    + bwd_ws_bytes(h, N, g.KP, g.H, g.A, g.T) + bwd_ws_bytes(h, N, g.KPc, g.Hc, 1, 1)
+                    + ws_bytes(N, 4) + ws_bytes((size_t)N * g.A, 4) + ws_bytes(N, 4) + ws_bytes((size_t)nlb * 5, 8);
+        DPPO_TRY(ws_reserve(h, need, s));
+        FwdBufs fa, fc; fwd_take(h, N, g.KP, g.H, g.A, fa); fwd_take(h, N, g.KPc, g.Hc, 1, fc);
+        BwdBufs ba, bc; float *Ga, *Gc, *dw0a, *dw0c;
+        bwd_take(h, N, g.KP, g.H, g.T, ba, &Ga, &dw0a); bwd_take(h, N, g.KPc, g.Hc, 1, bc, &Gc, &dw0c);
+        int* trow = ws_take<int>(h, N);
+        float* deps = ws_take<float>(h, (size_t)N * g.A);
+        float* dval = ws_take<float>(h, N);
+        double* bsum = ws_take<double>(h, (size_t)nlb * 5);
+
+        make_trow_kernel<<<nblk(N, 256), 256, 0, s>>>(inds, N, g.K, 0, trow); KLAUNCH(h); KCHECK();
+        if (adv_std < 0.f) { adv_stats_kernel<<<1, 256, 0, s>>>(advantages, N, h->scalars); KLAUNCH(h); KCHECK(); }
+        else { set_scalars_kernel<<<1, 1, 0, s>>>(h->scalars, adv_mean, adv_std); KLAUNCH(h); KCHECK(); }
+        DPPO_TRY(actor_fwd_fp32(h, s, DPPO_NET_ACTOR_FT, prev, obs, 1, N, trow, 0, fa));
+        DPPO_TRY(critic_fwd_fp32(h, s, obs, N, fc));
+        PpoHyper hp;
+        hp.A = g.A; hp.Da = h->cfg.action_dim; hp.K = g.K; hp.T = g.T; hp.reward_horizon = h->cfg.reward_horizon; hp.norm_adv = h->cfg.norm_adv;
+        hp.dcv = h->cfg.denoised_clip_value; hp.min_lp_std = h->cfg.min_logprob_denoising_std;
+        hp.lp_lo = h->cfg.logprob_clip_lo; hp.lp_hi = h->cfg.logprob_clip_hi; hp.gamma_d = h->cfg.gamma_denoising;
+        hp.clip_coef = h->cfg.clip_ploss_coef; hp.clip_base = h->cfg.clip_ploss_coef_base; hp.clip_rate = h->cfg.clip_ploss_coef_rate;
+        hp.clip_v = h->cfg.clip_vloss_coef; hp.vf_coef = h->cfg.vf_coef; hp.inv_nglobal = 1.0f / (float)N_global;
+        ppo_loss_kernel<<<nlb, 128, 0, s>>>(prev, nxt, fa.out, inds, returns, oldvalues, advantages, oldlogp, fc.out,
+                                           h->scalars, h->sched, hp, N, deps, dval, bsum); KLAUNCH(h); KCHECK();
+        ppo_metrics_kernel<<<1, 256, 0, s>>>(bsum, nlb, hp.inv_nglobal, (float)((double)N / (double)N_global), gr + nA + nC); KLAUNCH(h); KCHECK();
+        DPPO_TRY(actor_bwd_fp32(h, s, DPPO_NET_ACTOR_FT, fa, deps, N, trow, ba, Ga, dw0a, gr));
+        DPPO_TRY(critic_bwd_fp32(h, s, fc, dval, N, bc, Gc, dw0c, gr + nA));
+    }
+    if (apply) {
+        DPPO_TRY(allreduce_sum(h, gr, nA + nC + 8, s));
+        // actor_ft and critic are contiguous in `params` and share one optimizer (train_ppo_diffusion_agent.py:354-356)
+        DPPO_TRY(adam_apply(h, s, DPPO_OPT_FINETUNE, h->net_w[DPPO_NET_ACTOR_FT], gr, nA + nC, lr, h->cfg.weight_decay));
+        DPPO_TRY(prep_net(h, DPPO_NET_ACTOR_FT, s));
+        DPPO_TRY(prep_net(h, DPPO_NET_CRITIC, s));
+    }
+    if (metrics8) CUDA_TRY(cudaMemcpyAsync(metrics8, gr + nA + nC, 8 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    if (grads_out) CUDA_TRY(cudaMemcpyAsync(grads_out, gr, (nA + nC) * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    return 0;
+}
+
+extern "C" int dppo_ppo_step_host(dppo_handle* h, const float* obs, const float* prev, const float* nxt,
+                                  const int32_t* inds, const float* returns, const float* oldvalues,
+                                  const float* advantages, const float* oldlogp, int N, int64_t N_global,
+                                  float adv_mean, float adv_std, float lr, int apply, float* metrics8_host, dppo_stream_t st) {
+    ENTER(h); cudaStream_t s = (cudaStream_t)st; const Geom& g = h->g;
+    if (N < 1) DPPO_FAIL(-1, "dppo_ppo_step_host: bad arguments");
+    size_t b_obs = a256((size_t)N * g.Do * 4), b_x = a256((size_t)N * g.A * 4), b_n = a256((size_t)N * 4);
+    DPPO_TRY(stage_reserve(h, b_obs + 3 * b_x + 4 * b_n + 256));
+    char* p = h->dstage;
+    float* d_obs = (float*)p; p += b_obs;
+    float* d_prev = (float*)p; p += b_x; float* d_next = (float*)p; p += b_x; float* d_olp = (float*)p; p += b_x;
+    int* d_inds = (int*)p; p += b_n; float* d_ret = (float*)p; p += b_n; float* d_val = (float*)p; p += b_n; float* d_adv = (float*)p; p += b_n;
+    float* d_met = (float*)p;
+    CUDA_TRY(cudaMemcpyAsync(d_obs, obs, (size_t)N * g.Do * 4, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(d_prev, prev, (size_t)N * g.A * 4, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(d_next, nxt, (size_t)N * g.A * 4, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(d_olp, oldlogp, (size_t)N * g.A * 4, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(d_inds, inds, (size_t)N * 4, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(d_ret, returns, (size_t)N * 4, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(d_val, oldvalues, (size_t)N * 4, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(d_adv, advantages, (size_t)N * 4, cudaMemcpyHostToDevice, s));
+    DPPO_TRY(dppo_ppo_step(h, d_obs, d_prev, d_next, d_inds, d_ret, d_val, d_adv, d_olp, N, N_global, adv_mean, adv_std, lr, apply,
+                           d_met, nullptr, st));
+    if (metrics8_host) CUDA_TRY(cudaMemcpyAsync(metrics8_host, d_met, 8 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return 0;
+}
+
+// ------------------------------------------------------------------ pre-train step
+extern "C" int dppo_pretrain_step(dppo_handle* h, const float* actions, const float* obs, int N, int64_t N_global,
+                                  int64_t row_offset, const int32_t* t_in, const float* noise_in,
+                                  uint64_t seed, uint64_t offset, float lr, int apply,
+                                  float* loss, float* grads_out, dppo_stream_t st) {
+    ENTER(h); cudaStream_t s = (cudaStream_t)st; const Geom& g = h->g;
+    if (!actions || !obs || N < 1 || N_global < N) DPPO_FAIL(-1, "dppo_pretrain_step: bad arguments");
+    const size_t nA = g.ao.n;
+    float* gr = h->grads;
+    const size_t ne = (size_t)N * g.A;
+    const int nlb = nblk(ne, 256);
+    size_t need = fwd_ws_bytes(N, g.KP, g.H, g.A) + bwd_ws_bytes(h, N, g.KP, g.H, g.A, g.T)
+                + ws_bytes(N, 4) + 3 * ws_bytes(ne, 4) + ws_bytes(nlb, 8);
+    DPPO_TRY(ws_reserve(h, need, s));
+    FwdBufs fa; fwd_take(h, N, g.KP, g.H, g.A, fa);
+    BwdBufs ba; float *Ga, *dw0a; bwd_take(h, N, g.KP, g.H, g.T, ba, &Ga, &dw0a);
+    int* trow = ws_take<int>(h, N);
+    float* noise = ws_take<float>(h, ne); float* xn = ws_take<float>(h, ne); float* deps = ws_take<float>(h, ne);
+    double* bsum = ws_take<double>(h, nlb);
+    pretrain_prep_kernel<<<nblk(ne, 256), 256, 0, s>>>(actions, t_in, noise_in, N, g.A, g.T, h->sched, seed, offset, row_offset, trow, noise, xn);
+    KLAUNCH(h); KCHECK();
+    if (tc_eligible(h, N)) DPPO_TRY(tc_actor_forward_keep(h, s, DPPO_NET_ACTOR, xn, obs, 1, N, trow, 0, fa));
+    else DPPO_TRY(actor_fwd_fp32(h, s, DPPO_NET_ACTOR, xn, obs, 1, N, trow, 0, fa));
+    mse_loss_kernel<<<nlb, 256, 0, s>>>(fa.out, noise, ne, 1.0f / ((float)N_global * (float)g.A), deps, bsum); KLAUNCH(h); KCHECK();
+    sum_blocks_kernel<<<1, 256, 0, s>>>(bsum, nlb, 1.0f / ((float)N_global * (float)g.A), gr + nA); KLAUNCH(h); KCHECK();
+    DPPO_TRY(actor_bwd_fp32(h, s, DPPO_NET_ACTOR, fa, deps, N, trow, ba, Ga, dw0a, gr));
+    if (apply) {
+        DPPO_TRY(allreduce_sum(h, gr, nA + 8, s));
+        DPPO_TRY(adam_apply(h, s, DPPO_OPT_PRETRAIN, h->net_w[DPPO_NET_ACTOR], gr, nA, lr, h->cfg.pretrain_weight_decay));
+        DPPO_TRY(prep_net(h, DPPO_NET_ACTOR, s));
+    }
+    if (loss) CUDA_TRY(cudaMemcpyAsync(loss, gr + nA, sizeof(float), cudaMemcpyDeviceToDevice, s));
+    if (grads_out) CUDA_TRY(cudaMemcpyAsync(grads_out, gr, nA * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    return 0;
+}
+extern "C" int dppo_ema_update(dppo_handle* h, float decay, dppo_stream_t st) {
+    ENTER(h); cudaStream_t s = (cudaStream_t)st;
+    size_t n = h->g.ao.n;
+    ema_kernel<<<nblk(n, 256), 256, 0, s>>>(h->net_w[DPPO_NET_ACTOR_EMA], h->net_w[DPPO_NET_ACTOR], n, decay); KLAUNCH(h); KCHECK();
+    return prep_net(h, DPPO_NET_ACTOR_EMA, s);
+}
+extern "C" int dppo_force_path(dppo_handle* h, int path) { if (!h) return -1; h->force_path = path; return 0; }

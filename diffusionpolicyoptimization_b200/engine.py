@@ -1,0 +1,238 @@
+"""Thin Python handle over the C ABI: torch only supplies device memory, streams and (for N>1)
+the rendezvous that carries the NCCL unique id.  All arithmetic runs in libdppo_b200.so."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    if isinstance(t, torch.Tensor):
+        return C.c_void_p(t.data_ptr())
+    if isinstance(t, np.ndarray):
+        return C.c_void_p(t.ctypes.data)
+    raise TypeError(type(t))
+
+
+def _as_dev(x, dev, dtype=torch.float32):
+    """Contiguous tensor of `dtype` on `dev` (no copy if it already is)."""
+    if isinstance(x, np.ndarray):
+        x = torch.from_numpy(np.ascontiguousarray(x))
+    return x.to(device=dev, dtype=dtype).contiguous()
+
+
+def _as_host(x, dtype=np.float32) -> np.ndarray:
+    if isinstance(x, torch.Tensor):
+        x = x.detach().cpu().numpy()
+    return np.ascontiguousarray(x, dtype=dtype)
+
+
+class Engine:
+    """One `dppo_handle` bound to one GPU (one per rank / process)."""
+
+    def __init__(self, cfg: L.DppoCfg, device: int = 0):
+        self.lib = L.load()
+        if not torch.cuda.is_available():
+            raise L.DppoError("no CUDA device visible: libdppo_b200 has no CPU fallback")
+        self.cfg = cfg
+        self.device_index = int(device)
+        self.dev = torch.device("cuda", self.device_index)
+        h = C.c_void_p()
+        L.check(self.lib.dppo_create(C.byref(cfg), self.device_index, C.byref(h)), "dppo_create")
+        self.h = h
+        self.Do = cfg.obs_dim * cfg.cond_steps
+        self.A = cfg.action_dim * cfg.horizon_steps
+        self.T = cfg.denoising_steps
+        self.n_actor = self.lib.dppo_num_params(C.byref(cfg), L.NET_ACTOR)
+        self.n_critic = self.lib.dppo_num_params(C.byref(cfg), L.NET_CRITIC)
+        self.rank, self.world = 0, 1
+
+    @property
+    def K(self):
+        return self.cfg.ft_denoising_steps
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.dppo_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+
+    # ---------------------------------------------------------------- weights / optimizer state
+    def num_params(self, net: int) -> int:
+        return self.n_critic if net == L.NET_CRITIC else self.n_actor
+
+    def set_weights(self, net: int, flat):
+        if isinstance(flat, torch.Tensor) and flat.is_cuda:
+            flat = flat.to(torch.float32).contiguous().reshape(-1)
+            L.check(self.lib.dppo_set_weights(self.h, net, _ptr(flat), flat.numel(), 1, self._stream()), "dppo_set_weights")
+        else:
+            a = _as_host(flat).reshape(-1)
+            L.check(self.lib.dppo_set_weights(self.h, net, _ptr(a), a.size, 0, self._stream()), "dppo_set_weights")
+
+    def get_weights(self, net: int) -> np.ndarray:
+        out = np.empty(self.num_params(net), np.float32)
+        L.check(self.lib.dppo_get_weights(self.h, net, _ptr(out), out.size, 0, self._stream()), "dppo_get_weights")
+        return out
+
+    def get_opt_state(self, opt: int):
+        n = self.n_actor if opt == L.OPT_PRETRAIN else self.n_actor + self.n_critic
+        m, v = np.empty(n, np.float32), np.empty(n, np.float32)
+        step = C.c_int64(0)
+        L.check(self.lib.dppo_get_opt_state(self.h, opt, _ptr(m), _ptr(v), n, C.byref(step), 0, self._stream()), "dppo_get_opt_state")
+        return m, v, int(step.value)
+
+    def set_opt_state(self, opt: int, m, v, step: int):
+        m, v = _as_host(m).reshape(-1), _as_host(v).reshape(-1)
+        L.check(self.lib.dppo_set_opt_state(self.h, opt, _ptr(m), _ptr(v), m.size, int(step), 0, self._stream()), "dppo_set_opt_state")
+
+    def set_ft_denoising_steps(self, K: int):
+        L.check(self.lib.dppo_set_ft_denoising_steps(self.h, int(K)), "dppo_set_ft_denoising_steps")
+        self.cfg.ft_denoising_steps = int(K)
+
+    # ---------------------------------------------------------------- forward-only
+    def actor_forward(self, net: int, x, t, obs) -> torch.Tensor:
+        x = _as_dev(x, self.dev).reshape(-1, self.A)
+        N = x.shape[0]
+        t = _as_dev(t, self.dev, torch.int32).reshape(N)
+        obs = _as_dev(obs, self.dev).reshape(N, self.Do)
+        eps = torch.empty(N, self.A, device=self.dev, dtype=torch.float32)
+        L.check(self.lib.dppo_actor_forward(self.h, net, _ptr(x), _ptr(t), _ptr(obs), N, _ptr(eps), self._stream()), "dppo_actor_forward")
+        return eps
+
+    def value(self, obs) -> torch.Tensor:
+        obs = _as_dev(obs, self.dev).reshape(-1, self.Do)
+        N = obs.shape[0]
+        v = torch.empty(N, device=self.dev, dtype=torch.float32)
+        L.check(self.lib.dppo_value(self.h, _ptr(obs), N, _ptr(v), self._stream()), "dppo_value")
+        return v
+
+    def sample(self, obs, deterministic=False, use_base_policy=False, min_sampling_std: float = -1.0,
+               seed: int = 0, offset: int = 0, row_offset: int = 0, x_T=None, noise=None,
+               return_chain=True) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+        """Device-resident call: obs is (moved to) a CUDA tensor; returns CUDA tensors."""
+        obs = _as_dev(obs, self.dev).reshape(-1, self.Do)
+        B = obs.shape[0]
+        x_T = None if x_T is None else _as_dev(x_T, self.dev).reshape(B, self.A)
+        noise = None if noise is None else _as_dev(noise, self.dev).reshape(self.T, B, self.A)
+        actions = torch.empty(B, self.A, device=self.dev, dtype=torch.float32)
+        chains = torch.empty(B, self.K + 1, self.A, device=self.dev, dtype=torch.float32) if return_chain else None
+        L.check(self.lib.dppo_sample(self.h, _ptr(obs), B, int(deterministic), int(use_base_policy), float(min_sampling_std),
+                                     int(seed), int(offset), int(row_offset), _ptr(x_T), _ptr(noise),
+                                     _ptr(actions), _ptr(chains), self._stream()), "dppo_sample")
+        return actions, chains
+
+    def sample_host(self, obs: np.ndarray, actions_out: np.ndarray, chains_out: Optional[np.ndarray],
+                    deterministic=False, use_base_policy=False, min_sampling_std: float = -1.0,
+                    seed: int = 0, offset: int = 0, row_offset: int = 0, x_T=None, noise=None):
+        """Host-buffer call (H2D + chain + D2H + sync inside the library).  Buffers should be pinned."""
+        B = obs.shape[0]
+        L.check(self.lib.dppo_sample_host(self.h, _ptr(obs), B, int(deterministic), int(use_base_policy), float(min_sampling_std),
+                                          int(seed), int(offset), int(row_offset), _ptr(x_T), _ptr(noise),
+                                          _ptr(actions_out), _ptr(chains_out), self._stream()), "dppo_sample_host")
+
+    def logprobs(self, obs, chains, use_base_policy=False) -> torch.Tensor:
+        obs = _as_dev(obs, self.dev).reshape(-1, self.Do)
+        B = obs.shape[0]
+        chains = _as_dev(chains, self.dev).reshape(B, self.K + 1, self.A)
+        logp = torch.empty(B * self.K, self.A, device=self.dev, dtype=torch.float32)
+        L.check(self.lib.dppo_logprobs(self.h, _ptr(obs), _ptr(chains), B, int(use_base_policy), _ptr(logp), self._stream()), "dppo_logprobs")
+        return logp
+
+    def logprobs_subsample(self, obs, prev, nxt, inds, use_base_policy=False) -> torch.Tensor:
+        obs = _as_dev(obs, self.dev).reshape(-1, self.Do)
+        N = obs.shape[0]
+        prev = _as_dev(prev, self.dev).reshape(N, self.A)
+        nxt = _as_dev(nxt, self.dev).reshape(N, self.A)
+        inds = _as_dev(inds, self.dev, torch.int32).reshape(N)
+        logp = torch.empty(N, self.A, device=self.dev, dtype=torch.float32)
+        L.check(self.lib.dppo_logprobs_subsample(self.h, _ptr(obs), _ptr(prev), _ptr(nxt), _ptr(inds), N, int(use_base_policy),
+                                                 _ptr(logp), self._stream()), "dppo_logprobs_subsample")
+        return logp
+
+    # ---------------------------------------------------------------- updates
+    def ppo_step(self, obs, prev, nxt, inds, returns, oldvalues, advantages, oldlogp, lr: float, apply=True,
+                 n_global: Optional[int] = None, adv_mean: float = 0.0, adv_std: float = -1.0, want_grads=False):
+        obs = _as_dev(obs, self.dev).reshape(-1, self.Do)
+        N = obs.shape[0]
+        prev = _as_dev(prev, self.dev).reshape(N, self.A)
+        nxt = _as_dev(nxt, self.dev).reshape(N, self.A)
+        inds = _as_dev(inds, self.dev, torch.int32).reshape(N)
+        returns = _as_dev(returns, self.dev).reshape(N)
+        oldvalues = _as_dev(oldvalues, self.dev).reshape(N)
+        advantages = _as_dev(advantages, self.dev).reshape(N)
+        oldlogp = _as_dev(oldlogp, self.dev).reshape(N, self.A)
+        metrics = torch.empty(8, device=self.dev, dtype=torch.float32)
+        grads = torch.empty(self.n_actor + self.n_critic, device=self.dev, dtype=torch.float32) if want_grads else None
+        L.check(self.lib.dppo_ppo_step(self.h, _ptr(obs), _ptr(prev), _ptr(nxt), _ptr(inds), _ptr(returns), _ptr(oldvalues),
+                                       _ptr(advantages), _ptr(oldlogp), N, int(n_global if n_global is not None else N),
+                                       float(adv_mean), float(adv_std), float(lr), int(apply),
+                                       _ptr(metrics), _ptr(grads), self._stream()), "dppo_ppo_step")
+        return (metrics, grads) if want_grads else metrics
+
+    def ppo_step_host(self, obs, prev, nxt, inds, returns, oldvalues, advantages, oldlogp, metrics_out: np.ndarray,
+                      lr: float, apply=True, n_global: Optional[int] = None, adv_mean: float = 0.0, adv_std: float = -1.0):
+        """All arguments are host (ideally pinned) contiguous arrays; metrics_out is host float32[8]."""
+        N = obs.shape[0]
+        L.check(self.lib.dppo_ppo_step_host(self.h, _ptr(obs), _ptr(prev), _ptr(nxt), _ptr(inds), _ptr(returns), _ptr(oldvalues),
+                                            _ptr(advantages), _ptr(oldlogp), N, int(n_global if n_global is not None else N),
+                                            float(adv_mean), float(adv_std), float(lr), int(apply),
+                                            _ptr(metrics_out), self._stream()), "dppo_ppo_step_host")
+
+    def pretrain_step(self, actions, obs, lr: float, apply=True, t=None, noise=None, seed: int = 0, offset: int = 0,
+                      n_global: Optional[int] = None, row_offset: int = 0, want_grads=False):
+        actions = _as_dev(actions, self.dev).reshape(-1, self.A)
+        N = actions.shape[0]
+        obs = _as_dev(obs, self.dev).reshape(N, self.Do)
+        t = None if t is None else _as_dev(t, self.dev, torch.int32).reshape(N)
+        noise = None if noise is None else _as_dev(noise, self.dev).reshape(N, self.A)
+        loss = torch.empty(1, device=self.dev, dtype=torch.float32)
+        grads = torch.empty(self.n_actor, device=self.dev, dtype=torch.float32) if want_grads else None
+        L.check(self.lib.dppo_pretrain_step(self.h, _ptr(actions), _ptr(obs), N, int(n_global if n_global is not None else N),
+                                            int(row_offset), _ptr(t), _ptr(noise), int(seed), int(offset), float(lr), int(apply),
+                                            _ptr(loss), _ptr(grads), self._stream()), "dppo_pretrain_step")
+        return (loss, grads) if want_grads else loss
+
+    def ema_update(self, decay: float):
+        L.check(self.lib.dppo_ema_update(self.h, float(decay), self._stream()), "dppo_ema_update")
+
+    # ---------------------------------------------------------------- multi-GPU
+    def init_comm(self, group=None):
+        """Attach an NCCL communicator spanning torch.distributed's (default) group.  torch only
+        carries the 128-byte unique id; the gradient all-reduce is issued by the library."""
+        import torch.distributed as dist
+        if not dist.is_initialized() or dist.get_world_size(group) == 1:
+            return
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        buf = (C.c_char * 128)()
+        if rank == 0:
+            L.check(self.lib.dppo_comm_unique_id(buf), "dppo_comm_unique_id")
+        obj = [bytes(buf.raw) if rank == 0 else None]
+        dist.broadcast_object_list(obj, src=0, group=group)
+        idb = C.create_string_buffer(obj[0], 128)
+        L.check(self.lib.dppo_comm_init(self.h, idb, rank, world), "dppo_comm_init")
+        self.rank, self.world = rank, world
+
+    # ---------------------------------------------------------------- introspection
+    def launch_count(self) -> int:
+        return int(self.lib.dppo_launch_count(self.h))
+
+    def last_path(self) -> int:
+        return int(self.lib.dppo_last_path(self.h))
+
+    def force_path(self, path: int):
+        self.lib.dppo_force_path(self.h, int(path))

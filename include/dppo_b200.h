@@ -1,0 +1,193 @@
+/*
+ * dppo_b200.h — C ABI of libdppo_b200.so: the B200-native (sm_100a) implementation of DPPO's
+ * data-parallel hot path (DDPM chain sampling + PPO log-prob update + eps-MSE pre-train step).
+ *
+ * The reference (jamesmshihua/DiffusionPolicyOptimization) has no FFI / plugin layer: its boundary
+ * is the Python object surface the agents call.  Each entry point below names the reference
+ * method(s) it replaces (file:line relative to the reference root).  TensorFlow's tape + optimizer
+ * cannot be kept (TF is not a dependency), so "loss -> gradient -> AdamW" is one entry point.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes.  Unless a parameter is documented as HOST, every
+ *     pointer is a DEVICE pointer owned by the caller, row-major contiguous fp32 (int32 indices).
+ *   - every call is asynchronous on the passed stream (a cudaStream_t cast to void*; NULL = the
+ *     legacy default stream) except the *_host convenience calls, which synchronise that stream.
+ *   - return value: 0 = OK, negative = error; dppo_last_error() returns a thread-local message.
+ *   - a handle is bound to one GPU and is not thread-safe: one handle per rank / process.
+ *   - there is no CPU fallback: without a usable CUDA device dppo_create fails.
+ *
+ * Shapes: Do = obs_dim*cond_steps, A = horizon_steps*action_dim, T = denoising_steps,
+ *         K = ft_denoising_steps, H = actor_hidden, Hc = critic_hidden.
+ */
+#ifndef DPPO_B200_H
+#define DPPO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DPPO_ABI_VERSION 1
+
+typedef struct dppo_handle dppo_handle;
+typedef void* dppo_stream_t; /* cudaStream_t */
+
+/* network ids for dppo_{set,get}_weights / dppo_actor_forward */
+enum { DPPO_NET_ACTOR = 0, DPPO_NET_ACTOR_FT = 1, DPPO_NET_CRITIC = 2, DPPO_NET_ACTOR_EMA = 3 };
+/* activation ids: model/common/mlp.py:6-14 (only the two any cfg uses) */
+enum { DPPO_ACT_RELU = 0, DPPO_ACT_MISH = 1 };
+/* arithmetic of the MLP GEMMs */
+enum {
+    DPPO_PREC_FP32 = 0, /* CUDA-core FFMA everywhere: the parity mode (1e-4 rel / 1e-3 abs)        */
+    DPPO_PREC_BF16 = 1  /* tcgen05 bf16 x bf16 -> fp32 for large row counts; fp32 master weights,
+                           fp32 epilogues; looser bound stated in DESIGN.md                         */
+};
+/* optimizer slots */
+enum { DPPO_OPT_PRETRAIN = 0 /* actor */, DPPO_OPT_FINETUNE = 1 /* actor_ft ++ critic */ };
+
+/* Hyper-parameters = cfg.model.* / cfg.train.* of cfg/gym/finetune/hopper-v2/ft_ppo_diffusion_mlp.yaml
+ * and cfg/gym/pretrain/hopper-medium-v2/pre_diffusion_mlp.yaml.  dppo_cfg_default() fills the
+ * hopper fine-tune values. */
+typedef struct dppo_cfg {
+    int32_t obs_dim, action_dim, horizon_steps, cond_steps;   /* yaml:16-22                        */
+    int32_t denoising_steps, ft_denoising_steps;              /* yaml:18-19                        */
+    int32_t time_dim;                                         /* mlp_diffusion.py:17  (16)         */
+    int32_t actor_hidden, critic_hidden;                      /* yaml:93,102 (512 / 256)           */
+    int32_t actor_act, critic_act;                            /* yaml:94,103 (ReLU / Mish)         */
+    int32_t precision;                                        /* DPPO_PREC_*                       */
+    float denoised_clip_value;      /* diffusion.py:28; < 0 = None                                 */
+    float randn_clip_value;         /* yaml:83                                                     */
+    float final_action_clip_value;  /* diffusion.py:30; < 0 = None                                 */
+    float min_sampling_denoising_std, min_logprob_denoising_std; /* yaml:84-85                    */
+    float gamma_denoising;          /* yaml:79                                                     */
+    float clip_ploss_coef, clip_ploss_coef_base, clip_ploss_coef_rate; /* yaml:80-82             */
+    float clip_vloss_coef;          /* diffusion_ppo.py:14; < 0 = None                             */
+    int32_t norm_adv;               /* diffusion_ppo.py:17                                         */
+    int32_t reward_horizon;         /* train_ppo_diffusion_agent.py:26 (= act_steps)               */
+    float vf_coef;                  /* yaml:71                                                     */
+    float logprob_clip_lo, logprob_clip_hi; /* diffusion_ppo.py:50-51 (-5, 2)                      */
+    /* keras.optimizers.AdamW (Keras 3 semantics; train_ppo_agent.py:45-49, pretrain/train_agent.py:129-132) */
+    float adam_beta1, adam_beta2, adam_eps;
+    float weight_decay;             /* fine-tune optimizer (Keras default 0.004: `decay=` kwarg is ignored) */
+    float pretrain_weight_decay;    /* pre_diffusion_mlp.yaml:29 (1e-6)                            */
+} dppo_cfg;
+
+int         dppo_abi_version(void);
+const char* dppo_last_error(void);
+void        dppo_cfg_default(dppo_cfg* cfg);
+size_t      dppo_cfg_size(void); /* sizeof(dppo_cfg), for binding sanity checks */
+
+/* DDPM constants — model/diffusion/sampling.py:7-17 + model/diffusion/diffusion.py:58-73.
+ * HOST call, no GPU needed.  out is HOST [9*T]: rows betas, alphas_cumprod, sqrt_alphas_cumprod,
+ * sqrt_one_minus_alphas_cumprod, sqrt_recip_alphas_cumprod, sqrt_recipm1_alphas_cumprod,
+ * ddpm_logvar_clipped, ddpm_mu_coef1, ddpm_mu_coef2. */
+int dppo_ddpm_schedule(int T, float* out);
+
+/* number of fp32 parameters of a network; flat order = Keras variable-creation order:
+ * actor  = [time Dense(2td) W[td,2td], b, time Dense(td) W[2td,td], b, input W[Din,H], b,
+ *           block.l1 W[H,H], b, block.l2 W[H,H], b, output W[H,A], b]   (mlp_diffusion.py:40-62, mlp.py:117-132,170-171)
+ * critic = [input W[Do,Hc], b, l1 W, b, l2 W, b, output W[Hc,1], b]       (critic.py:27-38)
+ * Dense kernels are stored [in, out]. */
+size_t dppo_num_params(const dppo_cfg* cfg, int net);
+
+/* PPODiffusion.__init__ / VPGDiffusion.__init__ / DiffusionModel.__init__
+ * (diffusion_ppo.py:8-30, diffusion_vpg.py:29-110, diffusion.py:19-100).  Weights start at zero. */
+int  dppo_create(const dppo_cfg* cfg, int device, dppo_handle** out);
+void dppo_destroy(dppo_handle* h);
+
+/* set_weights / get_weights / load_weights / save_weights (diffusion.py:204-208,
+ * finetune/train_agent.py:127-142).  `is_device` says whether src/dst is a device pointer;
+ * host transfers synchronise the stream. */
+int dppo_set_weights(dppo_handle* h, int net, const float* src, size_t n, int is_device, dppo_stream_t s);
+int dppo_get_weights(dppo_handle* h, int net, float* dst, size_t n, int is_device, dppo_stream_t s);
+/* AdamW moments + step counter of an optimizer slot (n = params covered by that slot). */
+int dppo_set_opt_state(dppo_handle* h, int opt, const float* m, const float* v, size_t n, int64_t step, int is_device, dppo_stream_t s);
+int dppo_get_opt_state(dppo_handle* h, int opt, float* m, float* v, size_t n, int64_t* step, int is_device, dppo_stream_t s);
+/* VPGDiffusion.step(): set the number of fine-tuned denoising steps (diffusion_vpg.py:114-142). */
+int dppo_set_ft_denoising_steps(dppo_handle* h, int K);
+
+/* DiffusionMLP.call (mlp_diffusion.py:65-90): eps[N,A] = net(x[N,A], t[N] int32, obs[N,Do]). */
+int dppo_actor_forward(dppo_handle* h, int net, const float* x, const int32_t* t, const float* obs,
+                       int N, float* eps, dppo_stream_t s);
+
+/* CriticObs.call (critic.py:40-54): v[N] = critic(obs[N,Do]). */
+int dppo_value(dppo_handle* h, const float* obs, int N, float* v, dppo_stream_t s);
+
+/* VPGDiffusion.call (diffusion_vpg.py:249-339): the whole T-step chain in one call.
+ *   obs[B,Do]; actions[B,A]; chains_or_null[B,K+1,A].
+ *   Noise: x_T_or_null[B,A] and noise_or_null[T,B,A] (row i = i-th loop iteration, t = T-1-i)
+ *   inject the Gaussian draws (parity mode); when NULL they are drawn in-kernel by Philox4x32-10
+ *   from (seed, offset, global row = row_offset + local row), so results do not depend on how
+ *   rows are sharded across GPUs.
+ *   min_sampling_std < 0 uses cfg.min_sampling_denoising_std. */
+int dppo_sample(dppo_handle* h, const float* obs, int B, int deterministic, int use_base_policy,
+                float min_sampling_std, uint64_t seed, uint64_t offset, int64_t row_offset,
+                const float* x_T_or_null, const float* noise_or_null,
+                float* actions, float* chains_or_null, dppo_stream_t s);
+/* Same call with HOST buffers (the reference caller passes NumPy and does np.array() on the result:
+ * train_ppo_diffusion_agent.py:111-132).  H2D + kernel + D2H + stream sync inside. */
+int dppo_sample_host(dppo_handle* h, const float* obs_host, int B, int deterministic, int use_base_policy,
+                     float min_sampling_std, uint64_t seed, uint64_t offset, int64_t row_offset,
+                     const float* x_T_host_or_null, const float* noise_host_or_null,
+                     float* actions_host, float* chains_host_or_null, dppo_stream_t s);
+
+/* VPGDiffusion.get_logprobs (diffusion_vpg.py:343-425): logp[B*K,A], row = b*K + k. */
+int dppo_logprobs(dppo_handle* h, const float* obs, const float* chains, int B, int use_base_policy,
+                  float* logp, dppo_stream_t s);
+/* VPGDiffusion.get_logprobs_subsample (diffusion_vpg.py:427-481): logp[N,A]. */
+int dppo_logprobs_subsample(dppo_handle* h, const float* obs, const float* chains_prev, const float* chains_next,
+                            const int32_t* denoising_inds, int N, int use_base_policy, float* logp, dppo_stream_t s);
+
+/* PPODiffusion.c_loss (diffusion_ppo.py:32-132) + tape.gradient + AdamW.apply_gradients
+ * (train_ppo_diffusion_agent.py:340-356) in one call, on this rank's N_local rows.
+ *   N_global   : rows of the whole (un-sharded) minibatch; all means divide by it.
+ *   adv_mean/adv_std : population mean / std of `advantages` over the GLOBAL minibatch
+ *                (diffusion_ppo.py:74-75); pass adv_std < 0 to have them computed on device from
+ *                the local rows (valid only when N_local == N_global).
+ *   apply      : 0 = loss + gradients only, 1 = also all-reduce (if a communicator is attached)
+ *                and take the AdamW step with learning rate lr.
+ *   metrics8   : DEVICE [8] = (pg_loss, entropy_loss, v_loss, clipfrac, approx_kl, ratio, bc_loss, eta)
+ *   grads_or_null : DEVICE [n_actor + n_critic] flat gradient (after the all-reduce when apply=1). */
+int dppo_ppo_step(dppo_handle* h, const float* obs, const float* chains_prev, const float* chains_next,
+                  const int32_t* denoising_inds, const float* returns, const float* oldvalues,
+                  const float* advantages, const float* oldlogprobs, int N_local, int64_t N_global,
+                  float adv_mean, float adv_std, float lr, int apply,
+                  float* metrics8, float* grads_or_null, dppo_stream_t s);
+/* Same with HOST buffers; metrics8_host is HOST [8].  Synchronises the stream. */
+int dppo_ppo_step_host(dppo_handle* h, const float* obs, const float* chains_prev, const float* chains_next,
+                       const int32_t* denoising_inds, const float* returns, const float* oldvalues,
+                       const float* advantages, const float* oldlogprobs, int N_local, int64_t N_global,
+                       float adv_mean, float adv_std, float lr, int apply, float* metrics8_host, dppo_stream_t s);
+
+/* DiffusionModel.c_loss / p_losses / q_sample (diffusion.py:179-202) + tape.gradient + AdamW
+ * (train_diffusion_agent.py:63-69) on net DPPO_NET_ACTOR.  t_or_null[N] int32 and
+ * noise_or_null[N,A] inject the draws at diffusion.py:183,187; NULL = Philox(seed, offset, row).
+ *   loss : DEVICE [1];  grads_or_null : DEVICE [n_actor]. */
+int dppo_pretrain_step(dppo_handle* h, const float* actions, const float* obs, int N_local, int64_t N_global,
+                       int64_t row_offset, const int32_t* t_or_null, const float* noise_or_null,
+                       uint64_t seed, uint64_t offset, float lr, int apply,
+                       float* loss, float* grads_or_null, dppo_stream_t s);
+/* EMA.update_model_average (pretrain/train_agent.py:53-58): ema <- decay*ema + (1-decay)*actor. */
+int dppo_ema_update(dppo_handle* h, float decay, dppo_stream_t s);
+
+/* Multi-GPU (absent in the reference): one handle per rank, weights replicated,
+ * rows sharded by the caller, ONE sum all-reduce of [grads ++ metric partial sums] per step.
+ * dppo_comm_unique_id fills HOST id[128] on rank 0; the caller broadcasts it (any transport) and
+ * every rank calls dppo_comm_init.  NCCL is loaded with dlopen("libnccl.so.2"). */
+int dppo_comm_unique_id(char* id128);
+int dppo_comm_init(dppo_handle* h, const char* id128, int rank, int world);
+
+/* Count of kernel launches issued by this handle since creation (bench `gpu_launches`). */
+int64_t dppo_launch_count(dppo_handle* h);
+/* Which sampler the last dppo_sample used: 1 = persistent cluster kernel (one launch, T steps on
+ * chip), 2 = layer-by-layer fp32, 3 = layer-by-layer tcgen05.  Test / bench introspection. */
+int dppo_last_path(dppo_handle* h);
+/* Test hook: 0 = automatic dispatch, 1 = force the cluster sampler, 2 = forbid it. */
+int dppo_force_path(dppo_handle* h, int path);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DPPO_B200_H */
