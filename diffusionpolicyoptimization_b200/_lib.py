@@ -23,7 +23,8 @@ EXPORTS = (
     "dppo_get_opt_state", "dppo_set_ft_denoising_steps", "dppo_actor_forward", "dppo_value",
     "dppo_sample", "dppo_sample_host", "dppo_logprobs", "dppo_logprobs_subsample", "dppo_ppo_step",
     "dppo_ppo_step_host", "dppo_pretrain_step", "dppo_ema_update", "dppo_comm_unique_id",
-    "dppo_comm_init", "dppo_launch_count", "dppo_last_path", "dppo_force_path",
+    "dppo_comm_init", "dppo_launch_count", "dppo_last_path", "dppo_force_path", "dppo_profile_enable",
+    "dppo_profile_read",
 )
 
 
@@ -93,6 +94,8 @@ def load():
         "dppo_launch_count": (i64, [vp]),
         "dppo_last_path": (C.c_int, [vp]),
         "dppo_force_path": (C.c_int, [vp, i32]),
+        "dppo_profile_enable": (C.c_int, [vp, i32]),
+        "dppo_profile_read": (C.c_int, [vp, C.POINTER(C.c_double), C.POINTER(i64), C.POINTER(C.c_double)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

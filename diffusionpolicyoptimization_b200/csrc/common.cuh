@@ -140,9 +140,17 @@ struct dppo_handle {
     int last_path = 0;    // sampler path of the last dppo_sample: 1 cluster, 2 layered fp32, 3 tensor
     int force_path = 0;   // test hook: 0 auto, 1 force cluster sampler, 2 forbid it
     struct TcState* tc = nullptr;   // tcgen05 path state (tc_path.cuh)
+    // live GEMM timing (dppo_profile_*): event pairs recorded around GEMM-class launches
+    int prof_on = 0;
+    std::vector<cudaEvent_t> prof_ev;   // pairs
+    size_t prof_used = 0;
+    double prof_flops = 0, prof_ms_acc = 0; int64_t prof_launches = 0;
 };
 
 int ws_reserve(dppo_handle* h, size_t bytes, cudaStream_t s);
+// profile bracket: call prof_begin before and prof_end after a GEMM-class launch
+void prof_begin(dppo_handle* h, cudaStream_t s);
+void prof_end(dppo_handle* h, cudaStream_t s, double flops);
 template <typename T> static inline T* ws_take(dppo_handle* h, size_t count) {
     size_t bytes = (count * sizeof(T) + 255) / 256 * 256;
     T* p = (T*)(h->ws.base + h->ws.used);

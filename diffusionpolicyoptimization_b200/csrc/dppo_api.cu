@@ -121,6 +121,42 @@ int ws_reserve(dppo_handle* h, size_t bytes, cudaStream_t s) {
     return 0;
 }
 
+// ------------------------------------------------------------------ live GEMM timing
+static int prof_flush(dppo_handle* h) {
+    for (size_t i = 0; i + 1 < h->prof_used; i += 2) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->prof_ev[i], h->prof_ev[i + 1]) == cudaSuccess) h->prof_ms_acc += ms;
+    }
+    h->prof_used = 0;
+    return 0;
+}
+void prof_begin(dppo_handle* h, cudaStream_t s) {
+    if (!h->prof_on) return;
+    if (h->prof_used + 2 > h->prof_ev.size()) {
+        if (h->prof_ev.size() >= 8192) { cudaDeviceSynchronize(); prof_flush(h); }
+        else for (int i = 0; i < 2; ++i) { cudaEvent_t e; cudaEventCreate(&e); h->prof_ev.push_back(e); }
+    }
+    cudaEventRecord(h->prof_ev[h->prof_used], s);
+}
+void prof_end(dppo_handle* h, cudaStream_t s, double flops) {
+    if (!h->prof_on) return;
+    cudaEventRecord(h->prof_ev[h->prof_used + 1], s);
+    h->prof_used += 2; h->prof_launches += 1; h->prof_flops += flops;
+}
+extern "C" int dppo_profile_enable(dppo_handle* h, int on) {
+    if (!h) DPPO_FAIL(-1, "null handle");
+    CUDA_TRY(cudaSetDevice(h->device)); CUDA_TRY(cudaDeviceSynchronize());
+    h->prof_used = 0; h->prof_flops = 0; h->prof_ms_acc = 0; h->prof_launches = 0; h->prof_on = on ? 1 : 0;
+    return 0;
+}
+extern "C" int dppo_profile_read(dppo_handle* h, double* ms, int64_t* launches, double* flops) {
+    if (!h) DPPO_FAIL(-1, "null handle");
+    CUDA_TRY(cudaSetDevice(h->device)); CUDA_TRY(cudaDeviceSynchronize());
+    prof_flush(h);
+    if (ms) *ms = h->prof_ms_acc; if (launches) *launches = h->prof_launches; if (flops) *flops = h->prof_flops;
+    return 0;
+}
+
 static inline bool al16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
 
 // ------------------------------------------------------------------ SGEMM dispatch
@@ -137,6 +173,7 @@ static int gemm(dppo_handle* h, cudaStream_t s, bool a_km, bool b_nk, GemmP p, i
     p.vecB = b_nk ? (p.ldb % 4 == 0 && p.K % 4 == 0 && al16(p.B)) : (p.ldb % 4 == 0 && p.N % 4 == 0 && al16(p.B));
     p.vecC = (p.ldc % 4 == 0 && al16(p.C) && p.cstride % 4 == 0);
     dim3 grid((p.N + BN - 1) / BN, (p.M + 127) / 128, splits);
+    prof_begin(h, s);
 #define SG(AK, BK_, BNV) sgemm_kernel<AK, BK_, BNV><<<grid, 256, 0, s>>>(p)
     if (BN == 128) {
         if (!a_km && !b_nk) SG(false, false, 128); else if (!a_km && b_nk) SG(false, true, 128);
@@ -146,6 +183,7 @@ static int gemm(dppo_handle* h, cudaStream_t s, bool a_km, bool b_nk, GemmP p, i
         else if (a_km && !b_nk) SG(true, false, 32); else SG(true, true, 32);
     }
 #undef SG
+    prof_end(h, s, 2.0 * (double)p.M * (double)p.N * (double)p.K);
     KLAUNCH(h); KCHECK();
     return splits;
 }
@@ -231,6 +269,7 @@ extern "C" void dppo_destroy(dppo_handle* h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     tc_destroy(h);
+    for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
     if (h->comm) {
         void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
         if (lib) { typedef int (*fn_t)(void*); fn_t f = (fn_t)dlsym(lib, "ncclCommDestroy"); if (f) f(h->comm); }

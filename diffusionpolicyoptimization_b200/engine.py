@@ -236,3 +236,12 @@ class Engine:
 
     def force_path(self, path: int):
         self.lib.dppo_force_path(self.h, int(path))
+
+    def profile_enable(self, on: bool = True):
+        L.check(self.lib.dppo_profile_enable(self.h, int(on)), "dppo_profile_enable")
+
+    def profile_read(self):
+        """-> (gemm_ms, gemm_launches, gemm_flops) accumulated since profile_enable(True)."""
+        ms, n, fl = C.c_double(0), C.c_int64(0), C.c_double(0)
+        L.check(self.lib.dppo_profile_read(self.h, C.byref(ms), C.byref(n), C.byref(fl)), "dppo_profile_read")
+        return float(ms.value), int(n.value), float(fl.value)

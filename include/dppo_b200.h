@@ -186,6 +186,12 @@ int64_t dppo_launch_count(dppo_handle* h);
 int dppo_last_path(dppo_handle* h);
 /* Test hook: 0 = automatic dispatch, 1 = force the cluster sampler, 2 = forbid it. */
 int dppo_force_path(dppo_handle* h, int path);
+/* Live kernel timing for the roofline: when enabled, every GEMM-class launch (the MLP layers and
+ * their gradients: >97% of the path's flops) is bracketed by CUDA events on the launching stream.
+ * dppo_profile_read synchronises the device and returns the accumulated device time, launch count
+ * and algorithmic flops (2*M*N*K per GEMM) since the last enable/reset. */
+int dppo_profile_enable(dppo_handle* h, int on);
+int dppo_profile_read(dppo_handle* h, double* gemm_ms, int64_t* gemm_launches, double* gemm_flops);
 
 #ifdef __cplusplus
 }
