@@ -861,3 +861,19 @@ extern "C" int dppo_ema_update(dppo_handle* h, float decay, dppo_stream_t st) {
     return prep_net(h, DPPO_NET_ACTOR_EMA, s);
 }
 extern "C" int dppo_force_path(dppo_handle* h, int path) { if (!h) return -1; h->force_path = path; return 0; }
+
+extern "C" int dppo_debug_tc_gemm(dppo_handle* h, const void* A, int a_mn, int64_t lda, const void* A2, int64_t lda2, int K2,
+                                  const void* B, int b_mn, int64_t ldb, int M, int N, int K, int splits,
+                                  const float* bias, int act, float* out_f32, void* out_bf16, dppo_stream_t st) {
+    ENTER(h); cudaStream_t s = (cudaStream_t)st;
+    tc::Gemm g; memset(&g, 0, sizeof(g));
+    g.A = tc::Operand{(const __nv_bfloat16*)A, a_mn != 0, M, K, lda};
+    if (A2) g.A2 = tc::Operand{(const __nv_bfloat16*)A2, a_mn != 0, M, K2, lda2};
+    g.B = tc::Operand{(const __nv_bfloat16*)B, b_mn != 0, N, K + (A2 ? K2 : 0), ldb};
+    g.M = M; g.N = N; g.splits = splits;
+    g.epi.M = M; g.epi.N = N; g.epi.bias = bias; g.epi.act = act;
+    g.epi.out_f32 = out_f32; g.epi.ld_f32 = N; g.epi.split_stride = (size_t)M * N;
+    g.epi.out_bf16 = (__nv_bfloat16*)out_bf16; g.epi.ld_bf16 = N;
+    int r = tc::launch(h, s, g);
+    return r < 0 ? r : 0;
+}

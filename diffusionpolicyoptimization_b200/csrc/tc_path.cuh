@@ -1,6 +1,7 @@
 // tcgen05 (bf16 x bf16 -> fp32, TMEM accumulators, TMA operand staging) path for large row counts.
 #pragma once
 #include "common.cuh"
+#include "tc_gemm.cuh"
 
 struct FwdBufs;
 struct TcState { int dummy; };

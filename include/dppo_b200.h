@@ -190,6 +190,13 @@ int dppo_force_path(dppo_handle* h, int path);
  * their gradients: >97% of the path's flops) is bracketed by CUDA events on the launching stream.
  * dppo_profile_read synchronises the device and returns the accumulated device time, launch count
  * and algorithmic flops (2*M*N*K per GEMM) since the last enable/reset. */
+/* Test hook: one tcgen05 GEMM  out[M,N] = act(A*B + bias)  on bf16 device operands.
+ * a_mn / b_mn = 0: operand is K-major (A stored [M][K], B stored [N][K]); 1: MN-major (A stored
+ * [K][M], B stored [K][N]).  A2 (optional, same major as A, K2 columns) is K-concatenated to A.
+ * out_f32 is [splits][M][N] partial sums (no bias/act when splits > 1); out_bf16 optional [M][N]. */
+int dppo_debug_tc_gemm(dppo_handle* h, const void* A, int a_mn, int64_t lda, const void* A2, int64_t lda2, int K2,
+                       const void* B, int b_mn, int64_t ldb, int M, int N, int K, int splits,
+                       const float* bias, int act, float* out_f32, void* out_bf16, dppo_stream_t s);
 int dppo_profile_enable(dppo_handle* h, int on);
 int dppo_profile_read(dppo_handle* h, double* gemm_ms, int64_t* gemm_launches, double* gemm_flops);
 
