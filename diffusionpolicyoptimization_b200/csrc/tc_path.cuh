@@ -1,25 +1,352 @@
-// tcgen05 (bf16 x bf16 -> fp32, TMEM accumulators, TMA operand staging) path for large row counts.
+// tcgen05 path (DPPO_PREC_BF16) for large row counts: every MLP layer and every gradient is one
+// tc::gemm_kernel launch (TMA-staged bf16 operands, fp32 accumulation in TMEM, fused epilogue).
+//
+// Data layout in HBM (all bf16 activations are row-major [rows][features]; nothing is transposed):
+//   h0   [N][KP0]   = [ x (A) | obs (Do) | onehot(t) (T) | 1 | 0.. ]          KP0 = roundup(A+Do+T+1, 64)
+//        The one-hot block turns the per-t layer-0 bias bt[t] (time-MLP output folded through W_in)
+//        into T extra rows of the layer-0 weight, so the time embedding costs no epilogue work in
+//        the forward pass and its gradient (per-t column sums of du) falls out of dW0 = h0^T du.
+//        The ones column does the same for the critic's input-layer bias gradient.
+//   a0,a1 [N][H]    post-activation outputs of layer 0 / block.l1 (operands of the next layer and of dW)
+//   pre0,pre1       pre-activation copies, only stored for Mish (ReLU masks come from a > 0)
+//   v    [N][H]     residual-block output  v = a1 W2 + b2 + u,  u = h0 W0 re-accumulated by K-concatenating
+//                   [a1 | h0] against [W2 ; W0] instead of storing and re-reading u
+//   eps  [N][A]     fp32 (feeds the fp32 loss kernels)
+//   dv, dh1, du     [N][H] bf16 gradients; deps / dvalue are padded to [N][64] bf16
+// Weights: fp32 masters stay in h->params; bf16 operand copies are rebuilt after every update:
+//   w2w0 [(H+KP0)][H] = [W2 ; W0 rows in h0 order]   (MN-major B of the forward layers, K-major B of dX)
+//   w1   [H][H],  w3t [32][H] = W3^T (zero padded),  w3p [H][64] = W3 (zero padded)
 #pragma once
 #include "common.cuh"
+#include "simt_kernels.cuh"
 #include "tc_gemm.cuh"
 
-struct FwdBufs;
-struct TcState { int dummy; };
+typedef __nv_bfloat16 bf16;
 
-static int tc_init(dppo_handle* h) { (void)h; return 0; }
-static void tc_destroy(dppo_handle* h) { (void)h; }
-static int tc_refresh_net(dppo_handle* h, int net, cudaStream_t s) { (void)h; (void)net; (void)s; return 0; }
-static bool tc_eligible(const dppo_handle* h, int rows) { (void)h; (void)rows; return false; }
+struct TcNetW {
+    bf16 *w2w0, *w1, *w3t, *w3p;
+    float* bias2;          // critic: b2 + b_in (the residual's input-layer bias rides with block.l2's)
+    int H;
+};
+struct TcState {
+    TcNetW net[4];
+    int KP0;
+};
+
+// ------------------------------------------------------------------ small kernels
+__global__ void tc_pack_actor_kernel(const float* __restrict__ w, ActorOff o, int A, int td, int Do, int T, int H, int KP0,
+                                     const float* __restrict__ bt, bf16* __restrict__ w2w0, bf16* __restrict__ w1,
+                                     bf16* __restrict__ w3t, bf16* __restrict__ w3p) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x, i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (size_t i = i0; i < (size_t)H * H; i += stride) { w2w0[i] = __float2bfloat16(w[o.w2 + i]); w1[i] = __float2bfloat16(w[o.w1 + i]); }
+    for (size_t i = i0; i < (size_t)KP0 * H; i += stride) {
+        int k = (int)(i / H), c = (int)(i % H);
+        float v = 0.f;
+        if (k < A) v = w[o.win + (size_t)k * H + c];
+        else if (k < A + Do) v = w[o.win + (size_t)(k + td) * H + c];
+        else if (k < A + Do + T) v = bt[(size_t)(k - A - Do) * H + c];
+        w2w0[(size_t)H * H + i] = __float2bfloat16(v);
+    }
+    for (size_t i = i0; i < (size_t)32 * H; i += stride) {
+        int a = (int)(i / H), k = (int)(i % H);
+        w3t[i] = __float2bfloat16(a < A ? w[o.w3 + (size_t)k * A + a] : 0.f);
+    }
+    for (size_t i = i0; i < (size_t)H * 64; i += stride) {
+        int k = (int)(i / 64), a = (int)(i % 64);
+        w3p[i] = __float2bfloat16(a < A ? w[o.w3 + (size_t)k * A + a] : 0.f);
+    }
+}
+__global__ void tc_pack_critic_kernel(const float* __restrict__ w, CriticOff o, int A, int Do, int Hc, int KP0,
+                                      bf16* __restrict__ w2w0, bf16* __restrict__ w1, bf16* __restrict__ w3t,
+                                      bf16* __restrict__ w3p, float* __restrict__ bias2) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x, i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (size_t i = i0; i < (size_t)Hc * Hc; i += stride) { w2w0[i] = __float2bfloat16(w[o.w2 + i]); w1[i] = __float2bfloat16(w[o.w1 + i]); }
+    for (size_t i = i0; i < (size_t)KP0 * Hc; i += stride) {
+        int k = (int)(i / Hc), c = (int)(i % Hc);
+        float v = (k >= A && k < A + Do) ? w[o.win + (size_t)(k - A) * Hc + c] : 0.f;
+        w2w0[(size_t)Hc * Hc + i] = __float2bfloat16(v);
+    }
+    for (size_t i = i0; i < (size_t)32 * Hc; i += stride) { int a = (int)(i / Hc), k = (int)(i % Hc); w3t[i] = __float2bfloat16(a == 0 ? w[o.w3 + k] : 0.f); }
+    for (size_t i = i0; i < (size_t)Hc * 64; i += stride) { int k = (int)(i / 64), a = (int)(i % 64); w3p[i] = __float2bfloat16(a == 0 ? w[o.w3 + k] : 0.f); }
+    for (size_t i = i0; i < (size_t)Hc; i += stride) bias2[i] = w[o.b2 + i] + w[o.bin + i];
+}
+// h0[r] = [x[r] | obs[r / obs_div] | onehot(t_r) | 1 | 0..]; one thread per 8 consecutive columns (16-byte store)
+__global__ void tc_pack_h0_kernel(const float* __restrict__ x, const float* __restrict__ obs, const int* __restrict__ trow, int tconst,
+                                  int N, int A, int Do, int T, int KP0, int obs_div, bf16* __restrict__ h0) {
+    const int g8 = KP0 / 8;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)N * g8) return;
+    const int r = (int)(i / g8), k0 = (int)(i % g8) * 8;
+    const int t = trow ? trow[r] : tconst;
+    __align__(16) bf16 o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int k = k0 + j;
+        float v = 0.f;
+        if (k < A) v = x[(size_t)r * A + k];
+        else if (k < A + Do) v = obs[(size_t)(r / obs_div) * Do + (k - A)];
+        else if (k < A + Do + T) v = (k - A - Do == t) ? 1.f : 0.f;
+        else if (k == A + Do + T) v = 1.f;
+        o[j] = __float2bfloat16(v);
+    }
+    *reinterpret_cast<uint4*>(h0 + (size_t)r * KP0 + k0) = *reinterpret_cast<const uint4*>(o);
+}
+// dst[r][0:64] (bf16) = [src[r][0:ncols] | 0..]
+__global__ void tc_pad64_kernel(const float* __restrict__ src, int N, int ncols, bf16* __restrict__ dst) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)N * 8) return;
+    const int r = (int)(i >> 3), k0 = (int)(i & 7) * 8;
+    __align__(16) bf16 o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = __float2bfloat16(k0 + j < ncols ? src[(size_t)r * ncols + k0 + j] : 0.f);
+    *reinterpret_cast<uint4*>(dst + (size_t)r * 64 + k0) = *reinterpret_cast<const uint4*>(o);
+}
+// column sums of a bf16 matrix D[N][ncols] (ncols even, ncols/2 <= 256): part[blk][ncols]
+__global__ void __launch_bounds__(256) tc_colsum_kernel(const bf16* __restrict__ D, int N, int ncols, int rows_per_block, float* __restrict__ part) {
+    __shared__ float2 red[256];
+    const int tpr = ncols / 2, groups = 256 / tpr;
+    const int cg = threadIdx.x % tpr, rg = threadIdx.x / tpr;
+    const int r0 = blockIdx.x * rows_per_block, r1 = min(N, r0 + rows_per_block);
+    float2 acc = make_float2(0.f, 0.f);
+    if (rg < groups) {
+        for (int r = r0 + rg; r < r1; r += groups) {
+            __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(D + (size_t)r * ncols + 2 * cg);
+            float2 f = __bfloat1622float2(v);
+            acc.x += f.x; acc.y += f.y;
+        }
+    }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.x < tpr) {
+        float2 s = red[threadIdx.x];
+        for (int g = 1; g < groups; ++g) { float2 o = red[g * tpr + threadIdx.x]; s.x += o.x; s.y += o.y; }
+        part[(size_t)blockIdx.x * ncols + 2 * threadIdx.x] = s.x;
+        part[(size_t)blockIdx.x * ncols + 2 * threadIdx.x + 1] = s.y;
+    }
+}
+// out[r][c] = sum_s part[s*stride + r*ld_in + c]   for r < rows, c < cols   (deterministic split-K reduction)
+__global__ void tc_reduce2d_kernel(const float* __restrict__ part, int S, size_t stride, int rows, int cols, int ld_in,
+                                   float* __restrict__ out, int ld_out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)rows * cols) return;
+    const int r = (int)(i / cols), c = (int)(i % cols);
+    float s = 0.f;
+    for (int k = 0; k < S; ++k) s += part[(size_t)k * stride + (size_t)r * ld_in + c];
+    out[(size_t)r * ld_out + c] = s;
+}
+
+// ------------------------------------------------------------------ state
+static int tc_init(dppo_handle* h) {
+    const Geom& g = h->g;
+    TcState* st = new TcState();
+    memset(st, 0, sizeof(*st));
+    h->tc = st;
+    st->KP0 = round_up(g.A + g.Do + g.T + 1, 64);
+    if ((g.H % 64) || (g.Hc % 64) || g.A > 32) return 0;    // shapes the tensor path does not cover: stays on FFMA
+    for (int net = 0; net < 4; ++net) {
+        TcNetW& w = st->net[net];
+        const int H = net == DPPO_NET_CRITIC ? g.Hc : g.H;
+        w.H = H;
+        CUDA_TRY(cudaMalloc(&w.w2w0, (size_t)(H + st->KP0) * H * sizeof(bf16)));
+        CUDA_TRY(cudaMalloc(&w.w1, (size_t)H * H * sizeof(bf16)));
+        CUDA_TRY(cudaMalloc(&w.w3t, (size_t)32 * H * sizeof(bf16)));
+        CUDA_TRY(cudaMalloc(&w.w3p, (size_t)H * 64 * sizeof(bf16)));
+        CUDA_TRY(cudaMalloc(&w.bias2, (size_t)H * sizeof(float)));
+    }
+    return 0;
+}
+static void tc_destroy(dppo_handle* h) {
+    if (!h->tc) return;
+    for (int net = 0; net < 4; ++net) {
+        TcNetW& w = h->tc->net[net];
+        cudaFree(w.w2w0); cudaFree(w.w1); cudaFree(w.w3t); cudaFree(w.w3p); cudaFree(w.bias2);
+    }
+    delete h->tc; h->tc = nullptr;
+}
+static bool tc_shapes_ok(const dppo_handle* h) { return h->tc && h->tc->net[0].w1 != nullptr; }
+static const int TC_MIN_ROWS = 2048;
+static bool tc_eligible(const dppo_handle* h, int rows) {
+    return h->cfg.precision == DPPO_PREC_BF16 && tc_shapes_ok(h) && rows >= TC_MIN_ROWS;
+}
+// rebuild the bf16 operand copies of one net (after set_weights / an optimizer step)
+static int tc_refresh_net(dppo_handle* h, int net, cudaStream_t s) {
+    if (h->cfg.precision != DPPO_PREC_BF16 || !tc_shapes_ok(h)) return 0;
+    const Geom& g = h->g; TcNetW& w = h->tc->net[net];
+    if (net == DPPO_NET_CRITIC)
+        tc_pack_critic_kernel<<<128, 256, 0, s>>>(h->net_w[net], g.co, g.A, g.Do, g.Hc, h->tc->KP0, w.w2w0, w.w1, w.w3t, w.w3p, w.bias2);
+    else
+        tc_pack_actor_kernel<<<256, 256, 0, s>>>(h->net_w[net], g.ao, g.A, g.td, g.Do, g.T, g.H, h->tc->KP0, h->ad[net].bt, w.w2w0, w.w1, w.w3t, w.w3p);
+    h->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) DPPO_FAIL(-3, "tc pack launch failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+#define TC_KCHECK(h) do { (h)->launches++; cudaError_t _e = cudaGetLastError(); if (_e != cudaSuccess) { \
+    dppo_set_error("kernel launch failed at %s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(_e)); return -3; } } while (0)
+static inline int tc_nblk(size_t n, int b) { return (int)((n + b - 1) / b); }
+
+// ------------------------------------------------------------------ GEMM helpers
+static tc::Operand opK(const bf16* p, int64_t mn, int64_t k, int64_t ld) { return tc::Operand{p, false, mn, k, ld}; }
+static tc::Operand opMN(const bf16* p, int64_t mn, int64_t k, int64_t ld) { return tc::Operand{p, true, mn, k, ld}; }
+static tc::Gemm gemm_of(tc::Operand A, tc::Operand B, int M, int N) {
+    tc::Gemm g; memset(&g, 0, sizeof(g));
+    g.A = A; g.B = B; g.M = M; g.N = N; g.splits = 1; g.epi.M = M; g.epi.N = N;
+    return g;
+}
+static int tc_run(dppo_handle* h, cudaStream_t s, const tc::Gemm& g) { int r = tc::launch(h, s, g); return r < 0 ? r : 0; }
+
+// one residual MLP (actor: ReLU, NO = A; critic: Mish, NO = 1) on N rows
+struct TcMlp {
+    const TcNetW* W; int H, NO, act1, KP0;
+    const float *b0, *b1, *b2, *b3;       // fp32 biases (b0 null for the actor: bt rides in W0's one-hot rows)
+    const bf16* h0;
+    bf16 *a0, *a1, *v, *pre0, *pre1;      // pre* only when act1 == 2
+    float* out;                            // [N][NO] fp32
+    bf16 *dv, *dh1, *du;                   // backward
+};
+static size_t tc_mlp_ws_bytes(int N, int H, bool mish, bool bwd) {
+    size_t one = ws_bytes((size_t)N * H, sizeof(bf16));
+    return one * (3 + (mish ? 2 : 0) + (bwd ? 3 : 0));
+}
+static void tc_mlp_take(dppo_handle* h, int N, TcMlp& m, bool bwd) {
+    const size_t n = (size_t)N * m.H;
+    m.a0 = ws_take<bf16>(h, n); m.a1 = ws_take<bf16>(h, n); m.v = ws_take<bf16>(h, n);
+    m.pre0 = m.pre1 = nullptr;
+    if (m.act1 == 2) { m.pre0 = ws_take<bf16>(h, n); m.pre1 = ws_take<bf16>(h, n); }
+    m.dv = m.dh1 = m.du = nullptr;
+    if (bwd) { m.dv = ws_take<bf16>(h, n); m.dh1 = ws_take<bf16>(h, n); m.du = ws_take<bf16>(h, n); }
+}
+static int tc_mlp_forward(dppo_handle* h, cudaStream_t s, const TcMlp& m, int N) {
+    const int H = m.H, KP0 = m.KP0; const TcNetW& W = *m.W;
+    // L0: a0 = act(h0 W0 (+ b0))
+    tc::Gemm g = gemm_of(opK(m.h0, N, KP0, KP0), opMN(W.w2w0 + (size_t)H * H, H, KP0, H), N, H);
+    g.epi.bias = m.b0; g.epi.act = m.act1; g.epi.out_bf16 = m.a0; g.epi.ld_bf16 = H; g.epi.out_pre = m.pre0; g.epi.ld_pre = H;
+    DPPO_TRY(tc_run(h, s, g));
+    // L1: a1 = act(a0 W1 + b1)
+    g = gemm_of(opK(m.a0, N, H, H), opMN(W.w1, H, H, H), N, H);
+    g.epi.bias = m.b1; g.epi.act = m.act1; g.epi.out_bf16 = m.a1; g.epi.ld_bf16 = H; g.epi.out_pre = m.pre1; g.epi.ld_pre = H;
+    DPPO_TRY(tc_run(h, s, g));
+    // L2 + residual: v = [a1 | h0] [W2 ; W0] + b2 (+ b0)
+    g = gemm_of(opK(m.a1, N, H, H), opMN(W.w2w0, H, H + KP0, H), N, H);
+    g.A2 = opK(m.h0, N, KP0, KP0);
+    g.epi.bias = m.b2; g.epi.out_bf16 = m.v; g.epi.ld_bf16 = H;
+    DPPO_TRY(tc_run(h, s, g));
+    // L3: out = v W3 + b3
+    g = gemm_of(opK(m.v, N, H, H), opK(W.w3t, 32, H, H), N, m.NO);
+    g.epi.bias = m.b3; g.epi.out_f32 = m.out; g.epi.ld_f32 = m.NO;
+    DPPO_TRY(tc_run(h, s, g));
+    return 0;
+}
+static int tc_splits_for(const dppo_handle* h, int M, int N, int rows) {
+    const int BN = N > 128 ? 256 : (N > 64 ? 128 : 64);
+    const int tiles = ((M + 127) / 128) * ((N + BN - 1) / BN);
+    int splits = h->sm_count / tiles; if (splits < 1) splits = 1;
+    const int kb = (rows + 63) / 64;
+    int maxs = kb / 4; if (maxs < 1) maxs = 1;          // at least 4 k-blocks of work per split
+    if (splits > maxs) splits = maxs;
+    if (splits > 64) splits = 64;
+    return splits;
+}
+// dW[M][ncols] = X^T D  (X [rows][M] bf16, D [rows][Nd] bf16), deterministic split-K over the rows
+static int tc_dw(dppo_handle* h, cudaStream_t s, const bf16* X, int M, const bf16* D, int Nd, int rows, float* part,
+                 float* out, int out_rows, int out_cols, int ld_out) {
+    tc::Gemm g = gemm_of(opMN(X, M, rows, M), opMN(D, Nd, rows, Nd), M, Nd);
+    g.splits = tc_splits_for(h, M, Nd, rows);
+    g.epi.out_f32 = part; g.epi.ld_f32 = Nd; g.epi.split_stride = (size_t)M * Nd;
+    int S = tc::launch(h, s, g);
+    if (S < 0) return S;
+    tc_reduce2d_kernel<<<tc_nblk((size_t)out_rows * out_cols, 256), 256, 0, s>>>(part, S, (size_t)M * Nd, out_rows, out_cols, Nd, out, ld_out);
+    TC_KCHECK(h);
+    return 0;
+}
+static int tc_colsum(dppo_handle* h, cudaStream_t s, const bf16* D, int N, int ncols, float* part, float* out) {
+    int nb = 2 * h->sm_count; if (nb > (N + 63) / 64) nb = (N + 63) / 64; if (nb < 1) nb = 1;
+    int rpb = (N + nb - 1) / nb; nb = (N + rpb - 1) / rpb;
+    tc_colsum_kernel<<<nb, 256, 0, s>>>(D, N, ncols, rpb, part); TC_KCHECK(h);
+    reduce_partials_kernel<<<tc_nblk(ncols, 256), 256, 0, s>>>(part, nb, (size_t)ncols, (size_t)ncols, out, 1.f); TC_KCHECK(h);
+    return 0;
+}
+static size_t tc_part_floats(const dppo_handle* h, int H) {
+    size_t a = (size_t)64 * H * 256, b = (size_t)2 * h->sm_count * H;     // generous: splits <= 64 on [H][<=256-wide share]
+    size_t c = (size_t)h->sm_count * 128 * 256;                            // one 128x256 fp32 tile per CTA
+    size_t m = a > b ? a : b;
+    return m > c ? m : c;
+}
+// backward of the residual MLP from doutb [N][64] (bf16, zero padded).  Writes gradients of W1,b1,W2,b2,W3 into gnet
+// at the given offsets and dW0 (in h0 row order) into dw0 [KP0][H].
+static int tc_mlp_backward(dppo_handle* h, cudaStream_t s, const TcMlp& m, const bf16* doutb, int N, float* part,
+                           float* gnet, size_t ow1, size_t ob1, size_t ow2, size_t ob2, size_t ow3, float* dw0) {
+    const int H = m.H, KP0 = m.KP0; const TcNetW& W = *m.W;
+    // dv = dout W3^T
+    tc::Gemm g = gemm_of(opK(doutb, N, 64, 64), opK(W.w3p, H, 64, 64), N, H);
+    g.epi.out_bf16 = m.dv; g.epi.ld_bf16 = H;
+    DPPO_TRY(tc_run(h, s, g));
+    // dh1 = (dv W2^T) * act'(h1)
+    g = gemm_of(opK(m.dv, N, H, H), opK(W.w2w0, H, H, H), N, H);
+    g.epi.mask = m.act1 == 2 ? m.pre1 : m.a1; g.epi.ldmask = H; g.epi.mask_mode = m.act1;
+    g.epi.out_bf16 = m.dh1; g.epi.ld_bf16 = H;
+    DPPO_TRY(tc_run(h, s, g));
+    // du = (dh1 W1^T) * act'(u) + dv
+    g = gemm_of(opK(m.dh1, N, H, H), opK(W.w1, H, H, H), N, H);
+    g.epi.mask = m.act1 == 2 ? m.pre0 : m.a0; g.epi.ldmask = H; g.epi.mask_mode = m.act1;
+    g.epi.add = m.dv; g.epi.ldadd = H; g.epi.out_bf16 = m.du; g.epi.ld_bf16 = H;
+    DPPO_TRY(tc_run(h, s, g));
+    // weight gradients
+    DPPO_TRY(tc_dw(h, s, m.v, H, doutb, 64, N, part, gnet + ow3, H, m.NO, m.NO));
+    DPPO_TRY(tc_dw(h, s, m.a1, H, m.dv, H, N, part, gnet + ow2, H, H, H));
+    DPPO_TRY(tc_dw(h, s, m.a0, H, m.dh1, H, N, part, gnet + ow1, H, H, H));
+    DPPO_TRY(tc_dw(h, s, m.h0, KP0, m.du, H, N, part, dw0, KP0, H, H));
+    // bias gradients of block.l1 / block.l2 (the input-layer bias comes out of dw0's constant rows)
+    DPPO_TRY(tc_colsum(h, s, m.dv, N, H, part, gnet + ob2));
+    DPPO_TRY(tc_colsum(h, s, m.dh1, N, H, part, gnet + ob1));
+    return 0;
+}
+
+static void tc_actor_mlp(const dppo_handle* h, int net, TcMlp& m) {
+    const Geom& g = h->g; const float* w = h->net_w[net];
+    m.W = &h->tc->net[net]; m.H = g.H; m.NO = g.A; m.act1 = h->cfg.actor_act + 1; m.KP0 = h->tc->KP0;
+    m.b0 = nullptr; m.b1 = w + g.ao.b1; m.b2 = w + g.ao.b2; m.b3 = w + g.ao.b3;
+}
+static void tc_critic_mlp(const dppo_handle* h, TcMlp& m) {
+    const Geom& g = h->g; const float* w = h->net_w[DPPO_NET_CRITIC];
+    m.W = &h->tc->net[DPPO_NET_CRITIC]; m.H = g.Hc; m.NO = 1; m.act1 = h->cfg.critic_act + 1; m.KP0 = h->tc->KP0;
+    m.b0 = w + g.co.bin; m.b1 = w + g.co.b1; m.b2 = m.W->bias2; m.b3 = w + g.co.b3;
+}
+
+// ------------------------------------------------------------------ forward-only: eps[N][A] = actor(x, t, obs)
 static int tc_actor_forward(dppo_handle* h, cudaStream_t s, int net, const float* x, const float* obs, int obs_div, int N,
                             const int* trow, int tconst, float* eps) {
-    DPPO_FAIL(-7, "tensor path not built");
+    const Geom& g = h->g; const int KP0 = h->tc->KP0;
+    // the caller may hold workspace pointers (eps, trow) below ws.used: only append
+    const size_t need = h->ws.used + ws_bytes((size_t)N * KP0, 2) + tc_mlp_ws_bytes(N, g.H, h->cfg.actor_act == DPPO_ACT_MISH, false);
+    if (need > h->ws.cap) DPPO_FAIL(-7, "tc_actor_forward: workspace too small (%zu > %zu)", need, h->ws.cap);
+    const size_t mark = h->ws.used;
+    TcMlp m; tc_actor_mlp(h, net, m);
+    bf16* h0 = ws_take<bf16>(h, (size_t)N * KP0);
+    tc_mlp_take(h, N, m, false);
+    m.h0 = h0; m.out = eps;
+    tc_pack_h0_kernel<<<tc_nblk((size_t)N * (KP0 / 8), 256), 256, 0, s>>>(x, obs, trow, tconst, N, g.A, g.Do, g.T, KP0, obs_div, h0);
+    TC_KCHECK(h);
+    int r = tc_mlp_forward(h, s, m, N);
+    h->ws.used = mark;
+    return r;
 }
-static int tc_actor_forward_keep(dppo_handle* h, cudaStream_t s, int net, const float* x, const float* obs, int obs_div, int N,
-                                 const int* trow, int tconst, FwdBufs& b) {
-    DPPO_FAIL(-7, "tensor path not built");
+// extra workspace bytes tc_actor_forward appends for N rows
+static size_t tc_actor_forward_ws(const dppo_handle* h, int N) {
+    return ws_bytes((size_t)N * h->tc->KP0, 2) + tc_mlp_ws_bytes(N, h->g.H, h->cfg.actor_act == DPPO_ACT_MISH, false);
 }
-static int tc_ppo_step(dppo_handle* h, cudaStream_t s, const float* obs, const float* prev, const float* nxt, const int32_t* inds,
-                       const float* returns, const float* oldvalues, const float* advantages, const float* oldlogp,
-                       int N, int64_t N_global, float adv_mean, float adv_std) {
-    DPPO_FAIL(-7, "tensor path not built");
+static int tc_value(dppo_handle* h, cudaStream_t s, const float* obs, int N, float* v) {
+    const Geom& g = h->g; const int KP0 = h->tc->KP0;
+    DPPO_TRY(ws_reserve(h, ws_bytes((size_t)N * KP0, 2) + tc_mlp_ws_bytes(N, g.Hc, h->cfg.critic_act == DPPO_ACT_MISH, false), s));
+    TcMlp m; tc_critic_mlp(h, m);
+    bf16* h0 = ws_take<bf16>(h, (size_t)N * KP0);
+    tc_mlp_take(h, N, m, false);
+    m.h0 = h0; m.out = v;
+    tc_pack_h0_kernel<<<tc_nblk((size_t)N * (KP0 / 8), 256), 256, 0, s>>>(nullptr, obs, nullptr, 0, N, 0, 0, 0, KP0, 1, h0);   // placeholder, overwritten below
+    (void)cudaGetLastError();
+    // critic rows only need the obs block (x / one-hot rows of its W0 are zero): reuse the actor packing with x = null
+    tc_pack_h0_kernel<<<tc_nblk((size_t)N * (KP0 / 8), 256), 256, 0, s>>>(nullptr, obs, nullptr, -1, N, -g.A, g.Do, g.T, KP0, 1, h0);
+    TC_KCHECK(h);
+    return tc_mlp_forward(h, s, m, N);
 }
