@@ -328,6 +328,7 @@ extern "C" int dppo_set_ft_denoising_steps(dppo_handle* h, int K) {
     return 0;
 }
 extern "C" int64_t dppo_launch_count(dppo_handle* h) { return h ? h->launches : -1; }
+extern "C" int64_t dppo_tc_launch_count(dppo_handle* h) { return h ? h->tc_launches : -1; }
 extern "C" int dppo_last_path(dppo_handle* h) { return h ? h->last_path : -1; }
 
 // ------------------------------------------------------------------ fp32 layer-by-layer forward
@@ -472,7 +473,11 @@ extern "C" int dppo_actor_forward(dppo_handle* h, int net, const float* x, const
     if (net < 0 || net > 3 || net == DPPO_NET_CRITIC || !x || !t || !obs || !eps || N < 0) DPPO_FAIL(-1, "dppo_actor_forward: bad arguments");
     for (int r0 = 0; r0 < N; r0 += ROW_CHUNK) {
         int n = N - r0 < ROW_CHUNK ? N - r0 : ROW_CHUNK;
-        if (tc_eligible(h, n)) { DPPO_TRY(tc_actor_forward(h, s, net, x + (size_t)r0 * g.A, obs + (size_t)r0 * g.Do, 1, n, t + r0, 0, eps + (size_t)r0 * g.A)); continue; }
+        if (tc_eligible(h, n)) {
+            DPPO_TRY(ws_reserve(h, tc_actor_forward_ws(h, n), s));
+            DPPO_TRY(tc_actor_forward(h, s, net, x + (size_t)r0 * g.A, obs + (size_t)r0 * g.Do, 1, n, t + r0, 0, eps + (size_t)r0 * g.A));
+            continue;
+        }
         DPPO_TRY(ws_reserve(h, fwd_ws_bytes(n, g.KP, g.H, g.A), s));
         FwdBufs b; fwd_take(h, n, g.KP, g.H, g.A, b);
         DPPO_TRY(actor_fwd_fp32(h, s, net, x + (size_t)r0 * g.A, obs + (size_t)r0 * g.Do, 1, n, t + r0, 0, b));
@@ -485,6 +490,7 @@ extern "C" int dppo_value(dppo_handle* h, const float* obs, int N, float* v, dpp
     if (!obs || !v || N < 0) DPPO_FAIL(-1, "dppo_value: bad arguments");
     for (int r0 = 0; r0 < N; r0 += ROW_CHUNK) {
         int n = N - r0 < ROW_CHUNK ? N - r0 : ROW_CHUNK;
+        if (tc_eligible(h, n)) { DPPO_TRY(tc_value(h, s, obs + (size_t)r0 * g.Do, n, v + r0)); continue; }
         DPPO_TRY(ws_reserve(h, fwd_ws_bytes(n, g.KPc, g.Hc, 1), s));
         FwdBufs b; fwd_take(h, n, g.KPc, g.Hc, 1, b);
         DPPO_TRY(critic_fwd_fp32(h, s, obs + (size_t)r0 * g.Do, n, b));
@@ -502,9 +508,12 @@ static int logprobs_impl(dppo_handle* h, cudaStream_t s, const float* obs, const
     const int chunk_rows = chains ? (ROW_CHUNK / g.K) * g.K : ROW_CHUNK;
     for (int r0 = 0; r0 < N; r0 += chunk_rows) {
         int n = N - r0 < chunk_rows ? N - r0 : chunk_rows;
-        size_t need = fwd_ws_bytes(n, g.KP, g.H, g.A) + ws_bytes(n, 4) + ws_bytes((size_t)n * g.A, 4);
+        const bool tensor = tc_eligible(h, n);
+        size_t need = (tensor ? ws_bytes((size_t)n * g.A, 4) + tc_actor_forward_ws(h, n) : fwd_ws_bytes(n, g.KP, g.H, g.A))
+                    + ws_bytes(n, 4) + ws_bytes((size_t)n * g.A, 4);
         DPPO_TRY(ws_reserve(h, need, s));
-        FwdBufs b; fwd_take(h, n, g.KP, g.H, g.A, b);
+        FwdBufs b; memset(&b, 0, sizeof(b));
+        if (tensor) b.out = ws_take<float>(h, (size_t)n * g.A); else fwd_take(h, n, g.KP, g.H, g.A, b);
         int* trow = ws_take<int>(h, n);
         float* pv = ws_take<float>(h, (size_t)n * g.A);
         const float* xin; const float* ob; int obs_div;
@@ -519,7 +528,7 @@ static int logprobs_impl(dppo_handle* h, cudaStream_t s, const float* obs, const
             xin = prev + (size_t)r0 * g.A; ob = obs + (size_t)r0 * g.Do; obs_div = 1;
         }
         const float* epsp;
-        if (tc_eligible(h, n)) { DPPO_TRY(tc_actor_forward(h, s, net, xin, ob, obs_div, n, trow, 0, b.out)); epsp = b.out; }
+        if (tensor) { DPPO_TRY(tc_actor_forward(h, s, net, xin, ob, obs_div, n, trow, 0, b.out)); epsp = b.out; }
         else { DPPO_TRY(actor_fwd_fp32(h, s, net, xin, ob, obs_div, n, trow, 0, b)); epsp = b.out; }
         logprob_kernel<<<nblk((size_t)n * g.A, 256), 256, 0, s>>>(chains ? nullptr : prev + (size_t)r0 * g.A,
             chains ? nullptr : nxt + (size_t)r0 * g.A, ch, epsp, trow, n, g.A, g.K, h->sched, g.T,
@@ -585,9 +594,10 @@ static int sample_layered_fp32(dppo_handle* h, cudaStream_t s, const float* obs,
                                uint64_t seed, uint64_t offset, int64_t row_offset, const float* xT, const float* noise,
                                float* actions, float* chains, bool tensor) {
     const Geom& g = h->g;
-    size_t need = fwd_ws_bytes(B, g.KP, g.H, g.A) + ws_bytes((size_t)B * g.A, 4);
+    size_t need = (tensor ? ws_bytes((size_t)B * g.A, 4) + tc_actor_forward_ws(h, B) : fwd_ws_bytes(B, g.KP, g.H, g.A)) + ws_bytes((size_t)B * g.A, 4);
     DPPO_TRY(ws_reserve(h, need, s));
-    FwdBufs b; fwd_take(h, B, g.KP, g.H, g.A, b);
+    FwdBufs b; memset(&b, 0, sizeof(b));
+    if (tensor) b.out = ws_take<float>(h, (size_t)B * g.A); else fwd_take(h, B, g.KP, g.H, g.A, b);
     float* x = ws_take<float>(h, (size_t)B * g.A);
     sample_init_kernel<<<nblk((size_t)B * g.A, 256), 256, 0, s>>>(x, xT, B, g.A, seed, offset, row_offset, chains, g.K, g.K == g.T);
     KLAUNCH(h); KCHECK();
@@ -828,23 +838,26 @@ extern "C" int dppo_pretrain_step(dppo_handle* h, const float* actions, const fl
     if (!actions || !obs || N < 1 || N_global < N) DPPO_FAIL(-1, "dppo_pretrain_step: bad arguments");
     const size_t nA = g.ao.n;
     float* gr = h->grads;
-    const size_t ne = (size_t)N * g.A;
-    const int nlb = nblk(ne, 256);
-    size_t need = fwd_ws_bytes(N, g.KP, g.H, g.A) + bwd_ws_bytes(h, N, g.KP, g.H, g.A, g.T)
-                + ws_bytes(N, 4) + 3 * ws_bytes(ne, 4) + ws_bytes(nlb, 8);
-    DPPO_TRY(ws_reserve(h, need, s));
-    FwdBufs fa; fwd_take(h, N, g.KP, g.H, g.A, fa);
-    BwdBufs ba; float *Ga, *dw0a; bwd_take(h, N, g.KP, g.H, g.T, ba, &Ga, &dw0a);
-    int* trow = ws_take<int>(h, N);
-    float* noise = ws_take<float>(h, ne); float* xn = ws_take<float>(h, ne); float* deps = ws_take<float>(h, ne);
-    double* bsum = ws_take<double>(h, nlb);
-    pretrain_prep_kernel<<<nblk(ne, 256), 256, 0, s>>>(actions, t_in, noise_in, N, g.A, g.T, h->sched, seed, offset, row_offset, trow, noise, xn);
-    KLAUNCH(h); KCHECK();
-    if (tc_eligible(h, N)) DPPO_TRY(tc_actor_forward_keep(h, s, DPPO_NET_ACTOR, xn, obs, 1, N, trow, 0, fa));
-    else DPPO_TRY(actor_fwd_fp32(h, s, DPPO_NET_ACTOR, xn, obs, 1, N, trow, 0, fa));
-    mse_loss_kernel<<<nlb, 256, 0, s>>>(fa.out, noise, ne, 1.0f / ((float)N_global * (float)g.A), deps, bsum); KLAUNCH(h); KCHECK();
-    sum_blocks_kernel<<<1, 256, 0, s>>>(bsum, nlb, 1.0f / ((float)N_global * (float)g.A), gr + nA); KLAUNCH(h); KCHECK();
-    DPPO_TRY(actor_bwd_fp32(h, s, DPPO_NET_ACTOR, fa, deps, N, trow, ba, Ga, dw0a, gr));
+    if (tc_eligible(h, N)) {
+        DPPO_TRY(tc_pretrain_grads(h, s, actions, obs, N, N_global, row_offset, t_in, noise_in, seed, offset));
+    } else {
+        const size_t ne = (size_t)N * g.A;
+        const int nlb = nblk(ne, 256);
+        size_t need = fwd_ws_bytes(N, g.KP, g.H, g.A) + bwd_ws_bytes(h, N, g.KP, g.H, g.A, g.T)
+                    + ws_bytes(N, 4) + 3 * ws_bytes(ne, 4) + ws_bytes(nlb, 8);
+        DPPO_TRY(ws_reserve(h, need, s));
+        FwdBufs fa; fwd_take(h, N, g.KP, g.H, g.A, fa);
+        BwdBufs ba; float *Ga, *dw0a; bwd_take(h, N, g.KP, g.H, g.T, ba, &Ga, &dw0a);
+        int* trow = ws_take<int>(h, N);
+        float* noise = ws_take<float>(h, ne); float* xn = ws_take<float>(h, ne); float* deps = ws_take<float>(h, ne);
+        double* bsum = ws_take<double>(h, nlb);
+        pretrain_prep_kernel<<<nblk(ne, 256), 256, 0, s>>>(actions, t_in, noise_in, N, g.A, g.T, h->sched, seed, offset, row_offset, trow, noise, xn);
+        KLAUNCH(h); KCHECK();
+        DPPO_TRY(actor_fwd_fp32(h, s, DPPO_NET_ACTOR, xn, obs, 1, N, trow, 0, fa));
+        mse_loss_kernel<<<nlb, 256, 0, s>>>(fa.out, noise, ne, 1.0f / ((float)N_global * (float)g.A), deps, bsum); KLAUNCH(h); KCHECK();
+        sum_blocks_kernel<<<1, 256, 0, s>>>(bsum, nlb, 1.0f / ((float)N_global * (float)g.A), gr + nA); KLAUNCH(h); KCHECK();
+        DPPO_TRY(actor_bwd_fp32(h, s, DPPO_NET_ACTOR, fa, deps, N, trow, ba, Ga, dw0a, gr));
+    }
     if (apply) {
         DPPO_TRY(allreduce_sum(h, gr, nA + 8, s));
         DPPO_TRY(adam_apply(h, s, DPPO_OPT_PRETRAIN, h->net_w[DPPO_NET_ACTOR], gr, nA, lr, h->cfg.pretrain_weight_decay));

@@ -404,7 +404,7 @@ static int launch_t(dppo_handle* h, cudaStream_t s, const Gemm& g) {
     prof_begin(h, s);
     kern<<<grid, NUM_THREADS, smem_bytes<BN>(), s>>>(tA, tA2, tB, p);
     prof_end(h, s, 2.0 * (double)g.M * (double)g.N * (double)(A.k + (g.A2.ptr ? g.A2.k : 0)));
-    h->launches++;
+    h->launches++; h->tc_launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) DPPO_FAIL(-3, "tc gemm launch failed: %s", cudaGetErrorString(e));
     return p.splits;

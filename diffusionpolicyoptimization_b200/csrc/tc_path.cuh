@@ -83,7 +83,7 @@ __global__ void tc_pack_h0_kernel(const float* __restrict__ x, const float* __re
     for (int j = 0; j < 8; ++j) {
         const int k = k0 + j;
         float v = 0.f;
-        if (k < A) v = x[(size_t)r * A + k];
+        if (k < A) v = x ? x[(size_t)r * A + k] : 0.f;
         else if (k < A + Do) v = obs[(size_t)(r / obs_div) * Do + (k - A)];
         else if (k < A + Do + T) v = (k - A - Do == t) ? 1.f : 0.f;
         else if (k == A + Do + T) v = 1.f;
@@ -343,10 +343,120 @@ static int tc_value(dppo_handle* h, cudaStream_t s, const float* obs, int N, flo
     bf16* h0 = ws_take<bf16>(h, (size_t)N * KP0);
     tc_mlp_take(h, N, m, false);
     m.h0 = h0; m.out = v;
-    tc_pack_h0_kernel<<<tc_nblk((size_t)N * (KP0 / 8), 256), 256, 0, s>>>(nullptr, obs, nullptr, 0, N, 0, 0, 0, KP0, 1, h0);   // placeholder, overwritten below
-    (void)cudaGetLastError();
-    // critic rows only need the obs block (x / one-hot rows of its W0 are zero): reuse the actor packing with x = null
-    tc_pack_h0_kernel<<<tc_nblk((size_t)N * (KP0 / 8), 256), 256, 0, s>>>(nullptr, obs, nullptr, -1, N, -g.A, g.Do, g.T, KP0, 1, h0);
+    // the critic only reads the obs block (the x / one-hot rows of its W0 are zero)
+    tc_pack_h0_kernel<<<tc_nblk((size_t)N * (KP0 / 8), 256), 256, 0, s>>>(nullptr, obs, nullptr, -1, N, g.A, g.Do, g.T, KP0, 1, h0);
     TC_KCHECK(h);
     return tc_mlp_forward(h, s, m, N);
+}
+
+// ------------------------------------------------------------------ gradients of the PPO / pre-train losses
+static int colsum(dppo_handle* h, cudaStream_t s, const float* D, int ld, int N, int ncols, const int* seg, int nseg,
+                  float* part, float* out);   // dppo_api.cu
+
+// actor backward from deps [N][A] fp32 (+ its padded bf16 copy): fills gnet[0 : nA]
+static int tc_actor_grads(dppo_handle* h, cudaStream_t s, int net, const TcMlp& m, const float* deps, const bf16* depsb, int N,
+                          float* part, float* dw0, float* gnet) {
+    const Geom& g = h->g; const float* w = h->net_w[net]; const ActorDerived& d = h->ad[net];
+    DPPO_TRY(tc_mlp_backward(h, s, m, depsb, N, part, gnet, g.ao.w1, g.ao.b1, g.ao.w2, g.ao.b2, g.ao.w3, dw0));
+    DPPO_TRY(colsum(h, s, deps, g.A, N, g.A, nullptr, 1, part, gnet + g.ao.b3));
+    // dw0 rows [A+Do, A+Do+T) are the per-t column sums of du: the gradient of the bt table
+    const size_t sm = (size_t)(g.T * g.td * 3) * sizeof(float);
+    time_backward_kernel<<<1, 512, sm, s>>>(w, g.ao, g.A, g.td, g.H, g.T, dw0 + (size_t)(g.A + g.Do) * g.H, d.sinemb, d.thpre, d.temb, gnet);
+    TC_KCHECK(h);
+    unpack_dw0_kernel<<<tc_nblk((size_t)(g.A + g.Do) * g.H, 256), 256, 0, s>>>(dw0, g.A, g.td, g.Do, g.H, gnet + g.ao.win);
+    TC_KCHECK(h);
+    return 0;
+}
+static int tc_critic_grads(dppo_handle* h, cudaStream_t s, const TcMlp& m, const float* dval, const bf16* dvalb, int N,
+                           float* part, float* dw0, float* gnet) {
+    const Geom& g = h->g;
+    DPPO_TRY(tc_mlp_backward(h, s, m, dvalb, N, part, gnet, g.co.w1, g.co.b1, g.co.w2, g.co.b2, g.co.w3, dw0));
+    DPPO_TRY(colsum(h, s, dval, 1, N, 1, nullptr, 1, part, gnet + g.co.b3));
+    unpack_dw0_kernel<<<tc_nblk((size_t)g.Do * g.Hc, 256), 256, 0, s>>>(dw0 + (size_t)g.A * g.Hc, 0, 0, g.Do, g.Hc, gnet + g.co.win);
+    TC_KCHECK(h);
+    // the ones column of h0 collects the input-layer bias gradient
+    CUDA_TRY(cudaMemcpyAsync(gnet + g.co.bin, dw0 + (size_t)(g.A + g.Do + g.T) * g.Hc, g.Hc * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    return 0;
+}
+
+// PPODiffusion.c_loss + tape.gradient (diffusion_ppo.py:32-132, train_ppo_diffusion_agent.py:340-346) on the tensor path.
+// Leaves [actor_ft grads | critic grads | 8 metric partials] in h->grads.
+static int tc_ppo_step(dppo_handle* h, cudaStream_t s, const float* obs, const float* prev, const float* nxt, const int32_t* inds,
+                       const float* returns, const float* oldvalues, const float* advantages, const float* oldlogp,
+                       int N, int64_t N_global, float adv_mean, float adv_std) {
+    const Geom& g = h->g; const int KP0 = h->tc->KP0;
+    const size_t nA = g.ao.n, nC = g.co.n;
+    float* gr = h->grads;
+    const bool amish = h->cfg.actor_act == DPPO_ACT_MISH, cmish = h->cfg.critic_act == DPPO_ACT_MISH;
+    const int nlb = tc_nblk(N, 128);
+    const size_t pf = tc_part_floats(h, g.H);
+    size_t need = ws_bytes((size_t)N * KP0, 2) + tc_mlp_ws_bytes(N, g.H, amish, true) + tc_mlp_ws_bytes(N, g.Hc, cmish, true)
+                + 2 * ws_bytes((size_t)N * g.A, 4) + 3 * ws_bytes(N, 4) + 2 * ws_bytes((size_t)N * 64, 2)
+                + ws_bytes(pf, 4) + ws_bytes((size_t)KP0 * g.H, 4) + ws_bytes((size_t)KP0 * g.Hc, 4) + ws_bytes((size_t)nlb * 5, 8);
+    DPPO_TRY(ws_reserve(h, need, s));
+    TcMlp ma, mc; tc_actor_mlp(h, DPPO_NET_ACTOR_FT, ma); tc_critic_mlp(h, mc);
+    bf16* h0 = ws_take<bf16>(h, (size_t)N * KP0);
+    tc_mlp_take(h, N, ma, true); tc_mlp_take(h, N, mc, true);
+    float* eps = ws_take<float>(h, (size_t)N * g.A); float* deps = ws_take<float>(h, (size_t)N * g.A);
+    float* val = ws_take<float>(h, N); float* dval = ws_take<float>(h, N); int* trow = ws_take<int>(h, N);
+    bf16* depsb = ws_take<bf16>(h, (size_t)N * 64); bf16* dvalb = ws_take<bf16>(h, (size_t)N * 64);
+    float* part = ws_take<float>(h, pf);
+    float* dw0a = ws_take<float>(h, (size_t)KP0 * g.H); float* dw0c = ws_take<float>(h, (size_t)KP0 * g.Hc);
+    double* bsum = ws_take<double>(h, (size_t)nlb * 5);
+    ma.h0 = h0; mc.h0 = h0; ma.out = eps; mc.out = val;
+
+    make_trow_kernel<<<tc_nblk(N, 256), 256, 0, s>>>(inds, N, g.K, 0, trow); TC_KCHECK(h);
+    if (adv_std < 0.f) { adv_stats_kernel<<<1, 256, 0, s>>>(advantages, N, h->scalars); TC_KCHECK(h); }
+    else { set_scalars_kernel<<<1, 1, 0, s>>>(h->scalars, adv_mean, adv_std); TC_KCHECK(h); }
+    tc_pack_h0_kernel<<<tc_nblk((size_t)N * (KP0 / 8), 256), 256, 0, s>>>(prev, obs, trow, 0, N, g.A, g.Do, g.T, KP0, 1, h0); TC_KCHECK(h);
+    DPPO_TRY(tc_mlp_forward(h, s, ma, N));
+    DPPO_TRY(tc_mlp_forward(h, s, mc, N));
+    PpoHyper hp;
+    hp.A = g.A; hp.Da = h->cfg.action_dim; hp.K = g.K; hp.T = g.T; hp.reward_horizon = h->cfg.reward_horizon; hp.norm_adv = h->cfg.norm_adv;
+    hp.dcv = h->cfg.denoised_clip_value; hp.min_lp_std = h->cfg.min_logprob_denoising_std;
+    hp.lp_lo = h->cfg.logprob_clip_lo; hp.lp_hi = h->cfg.logprob_clip_hi; hp.gamma_d = h->cfg.gamma_denoising;
+    hp.clip_coef = h->cfg.clip_ploss_coef; hp.clip_base = h->cfg.clip_ploss_coef_base; hp.clip_rate = h->cfg.clip_ploss_coef_rate;
+    hp.clip_v = h->cfg.clip_vloss_coef; hp.vf_coef = h->cfg.vf_coef; hp.inv_nglobal = 1.0f / (float)N_global;
+    ppo_loss_kernel<<<nlb, 128, 0, s>>>(prev, nxt, eps, inds, returns, oldvalues, advantages, oldlogp, val,
+                                       h->scalars, h->sched, hp, N, deps, dval, bsum); TC_KCHECK(h);
+    ppo_metrics_kernel<<<1, 256, 0, s>>>(bsum, nlb, hp.inv_nglobal, (float)((double)N / (double)N_global), gr + nA + nC); TC_KCHECK(h);
+    tc_pad64_kernel<<<tc_nblk((size_t)N * 8, 256), 256, 0, s>>>(deps, N, g.A, depsb); TC_KCHECK(h);
+    tc_pad64_kernel<<<tc_nblk((size_t)N * 8, 256), 256, 0, s>>>(dval, N, 1, dvalb); TC_KCHECK(h);
+    DPPO_TRY(tc_actor_grads(h, s, DPPO_NET_ACTOR_FT, ma, deps, depsb, N, part, dw0a, gr));
+    DPPO_TRY(tc_critic_grads(h, s, mc, dval, dvalb, N, part, dw0c, gr + nA));
+    return 0;
+}
+
+// DiffusionModel.c_loss / p_losses (diffusion.py:179-202) + tape.gradient on the tensor path: loss -> h->grads[nA],
+// gradients -> h->grads[0 : nA]
+static int tc_pretrain_grads(dppo_handle* h, cudaStream_t s, const float* actions, const float* obs, int N, int64_t N_global,
+                             int64_t row_offset, const int32_t* t_in, const float* noise_in, uint64_t seed, uint64_t offset) {
+    const Geom& g = h->g; const int KP0 = h->tc->KP0;
+    const size_t nA = g.ao.n; float* gr = h->grads;
+    const size_t ne = (size_t)N * g.A;
+    const int nlb = tc_nblk(ne, 256);
+    const size_t pf = tc_part_floats(h, g.H);
+    size_t need = ws_bytes((size_t)N * KP0, 2) + tc_mlp_ws_bytes(N, g.H, h->cfg.actor_act == DPPO_ACT_MISH, true)
+                + 4 * ws_bytes(ne, 4) + ws_bytes(N, 4) + ws_bytes((size_t)N * 64, 2) + ws_bytes(pf, 4)
+                + ws_bytes((size_t)KP0 * g.H, 4) + ws_bytes(nlb, 8);
+    DPPO_TRY(ws_reserve(h, need, s));
+    TcMlp ma; tc_actor_mlp(h, DPPO_NET_ACTOR, ma);
+    bf16* h0 = ws_take<bf16>(h, (size_t)N * KP0);
+    tc_mlp_take(h, N, ma, true);
+    float* eps = ws_take<float>(h, ne); float* deps = ws_take<float>(h, ne); float* noise = ws_take<float>(h, ne); float* xn = ws_take<float>(h, ne);
+    int* trow = ws_take<int>(h, N);
+    bf16* depsb = ws_take<bf16>(h, (size_t)N * 64);
+    float* part = ws_take<float>(h, pf);
+    float* dw0 = ws_take<float>(h, (size_t)KP0 * g.H);
+    double* bsum = ws_take<double>(h, nlb);
+    ma.h0 = h0; ma.out = eps;
+    pretrain_prep_kernel<<<tc_nblk(ne, 256), 256, 0, s>>>(actions, t_in, noise_in, N, g.A, g.T, h->sched, seed, offset, row_offset, trow, noise, xn); TC_KCHECK(h);
+    tc_pack_h0_kernel<<<tc_nblk((size_t)N * (KP0 / 8), 256), 256, 0, s>>>(xn, obs, trow, 0, N, g.A, g.Do, g.T, KP0, 1, h0); TC_KCHECK(h);
+    DPPO_TRY(tc_mlp_forward(h, s, ma, N));
+    const float scale = 1.0f / ((float)N_global * (float)g.A);
+    mse_loss_kernel<<<nlb, 256, 0, s>>>(eps, noise, ne, scale, deps, bsum); TC_KCHECK(h);
+    sum_blocks_kernel<<<1, 256, 0, s>>>(bsum, nlb, scale, gr + nA); TC_KCHECK(h);
+    tc_pad64_kernel<<<tc_nblk((size_t)N * 8, 256), 256, 0, s>>>(deps, N, g.A, depsb); TC_KCHECK(h);
+    DPPO_TRY(tc_actor_grads(h, s, DPPO_NET_ACTOR, ma, deps, depsb, N, part, dw0, gr));
+    return 0;
 }

