@@ -23,7 +23,7 @@ EXPORTS = (
     "dppo_get_opt_state", "dppo_set_ft_denoising_steps", "dppo_actor_forward", "dppo_value",
     "dppo_sample", "dppo_sample_host", "dppo_logprobs", "dppo_logprobs_subsample", "dppo_ppo_step",
     "dppo_ppo_step_host", "dppo_pretrain_step", "dppo_ema_update", "dppo_comm_unique_id",
-    "dppo_comm_init", "dppo_launch_count", "dppo_tc_launch_count", "dppo_last_path", "dppo_force_path", "dppo_profile_enable", "dppo_debug_tc_gemm",
+    "dppo_comm_init", "dppo_launch_count", "dppo_tc_launch_count", "dppo_fused_launch_count", "dppo_last_path", "dppo_force_path", "dppo_profile_enable", "dppo_debug_tc_gemm",
     "dppo_profile_read",
 )
 
@@ -93,6 +93,7 @@ def load():
         "dppo_comm_init": (C.c_int, [vp, vp, i32, i32]),
         "dppo_launch_count": (i64, [vp]),
         "dppo_tc_launch_count": (i64, [vp]),
+        "dppo_fused_launch_count": (i64, [vp]),
         "dppo_last_path": (C.c_int, [vp]),
         "dppo_force_path": (C.c_int, [vp, i32]),
         "dppo_profile_enable": (C.c_int, [vp, i32]),

@@ -137,6 +137,7 @@ struct dppo_handle {
     void* comm = nullptr; int rank = 0, world = 1;
     int64_t launches = 0;
     int64_t tc_launches = 0;
+    int64_t fused_launches = 0;   // of those, fused layer-chain launches
     int cluster_max = -1; // max co-resident 16-CTA clusters (-1 unknown, 0 = not launchable)
     int last_path = 0;    // sampler path of the last dppo_sample: 1 cluster, 2 layered fp32, 3 tensor
     int force_path = 0;   // test hook: 0 auto, 1 force cluster sampler, 2 forbid it

@@ -329,6 +329,7 @@ extern "C" int dppo_set_ft_denoising_steps(dppo_handle* h, int K) {
 }
 extern "C" int64_t dppo_launch_count(dppo_handle* h) { return h ? h->launches : -1; }
 extern "C" int64_t dppo_tc_launch_count(dppo_handle* h) { return h ? h->tc_launches : -1; }
+extern "C" int64_t dppo_fused_launch_count(dppo_handle* h) { return h ? h->fused_launches : -1; }
 extern "C" int dppo_last_path(dppo_handle* h) { return h ? h->last_path : -1; }
 
 // ------------------------------------------------------------------ fp32 layer-by-layer forward
@@ -509,6 +510,7 @@ static int logprobs_impl(dppo_handle* h, cudaStream_t s, const float* obs, const
     for (int r0 = 0; r0 < N; r0 += chunk_rows) {
         int n = N - r0 < chunk_rows ? N - r0 : chunk_rows;
         const bool tensor = tc_eligible(h, n);
+        const bool fusedlp = tensor && fc_ok(h);
         size_t need = (tensor ? ws_bytes((size_t)n * g.A, 4) + tc_actor_forward_ws(h, n) : fwd_ws_bytes(n, g.KP, g.H, g.A))
                     + ws_bytes(n, 4) + ws_bytes((size_t)n * g.A, 4);
         DPPO_TRY(ws_reserve(h, need, s));
@@ -521,13 +523,23 @@ static int logprobs_impl(dppo_handle* h, cudaStream_t s, const float* obs, const
         if (chains) {
             ch = chains + (size_t)(r0 / g.K) * (g.K + 1) * g.A;
             make_trow_kernel<<<nblk(n, 256), 256, 0, s>>>(nullptr, n, g.K, 1, trow); KLAUNCH(h); KCHECK();
-            chains_prev_kernel<<<nblk((size_t)n * g.A, 256), 256, 0, s>>>(ch, n, g.A, g.K, pv); KLAUNCH(h); KCHECK();
+            if (!fusedlp) { chains_prev_kernel<<<nblk((size_t)n * g.A, 256), 256, 0, s>>>(ch, n, g.A, g.K, pv); KLAUNCH(h); KCHECK(); }
             xin = pv; ob = obs + (size_t)(r0 / g.K) * g.Do; obs_div = g.K;
         } else {
             make_trow_kernel<<<nblk(n, 256), 256, 0, s>>>(inds + r0, n, g.K, 0, trow); KLAUNCH(h); KCHECK();
             xin = prev + (size_t)r0 * g.A; ob = obs + (size_t)r0 * g.Do; obs_div = 1;
         }
         const float* epsp;
+        if (fusedlp) {
+            // pack h0 straight from prev rows / the chains tensor, then forward + Gaussian log-prob in one fused launch
+            bf16* h0 = ws_take<bf16>(h, (size_t)n * h->tc->KP0);
+            tc_pack_h0_kernel<<<nblk((size_t)n * (h->tc->KP0 / 8), 256), 256, 0, s>>>(chains ? ch : prev + (size_t)r0 * g.A, ob, trow, 0, n, g.A, g.Do, g.T,
+                                                                                      h->tc->KP0, obs_div, h0, chains ? g.K : 0);
+            KLAUNCH(h); KCHECK();
+            DPPO_TRY(fc_actor_infer(h, s, net, h0, n, fc::FINAL_LOGP, logp + (size_t)r0 * g.A, chains ? nullptr : prev + (size_t)r0 * g.A,
+                                    chains ? nullptr : nxt + (size_t)r0 * g.A, ch, trow));
+            continue;
+        }
         if (tensor) { DPPO_TRY(tc_actor_forward(h, s, net, xin, ob, obs_div, n, trow, 0, b.out)); epsp = b.out; }
         else { DPPO_TRY(actor_fwd_fp32(h, s, net, xin, ob, obs_div, n, trow, 0, b)); epsp = b.out; }
         logprob_kernel<<<nblk((size_t)n * g.A, 256), 256, 0, s>>>(chains ? nullptr : prev + (size_t)r0 * g.A,
@@ -640,6 +652,10 @@ extern "C" int dppo_sample(dppo_handle* h, const float* obs, int B, int determin
         if (h->force_path == 1) return r;
         h->cluster_max = 0;   // not launchable here: remember and fall through to the layered path
         (void)cudaGetLastError();
+    }
+    if (tensor && fc_ok(h)) {
+        h->last_path = 4;
+        return fc_sample(h, s, obs, B, use_base_policy, hp, seed, offset, row_offset, xT, noise, actions, chains);
     }
     h->last_path = tensor ? 3 : 2;
     return sample_layered_fp32(h, s, obs, B, use_base_policy, hp, seed, offset, row_offset, xT, noise, actions, chains, tensor);

@@ -15,16 +15,18 @@
 //   dv, dh1, du     [N][H] bf16 gradients; deps / dvalue are padded to [N][64] bf16
 // Weights: fp32 masters stay in h->params; bf16 operand copies are rebuilt after every update:
 //   w2w0 [(H+KP0)][H] = [W2 ; W0 rows in h0 order]   (MN-major B of the forward layers, K-major B of dX)
-//   w1   [H][H],  w3t [32][H] = W3^T (zero padded),  w3p [H][64] = W3 (zero padded)
+//   w1   [H][H],  w3t [64][H] = W3^T (zero padded),  w3p [H][64] = W3 (zero padded),  w1t / w2t = W1^T / W2^T
 #pragma once
 #include "common.cuh"
 #include "simt_kernels.cuh"
 #include "tc_gemm.cuh"
+#include "fused_chain.cuh"
 
 typedef __nv_bfloat16 bf16;
 
 struct TcNetW {
     bf16 *w2w0, *w1, *w3t, *w3p;
+    bf16 *w1t, *w2t;       // W1^T, W2^T [out][in]: MN-major B operands of the fused backward chain (actors only)
     float* bias2;          // critic: b2 + b_in (the residual's input-layer bias rides with block.l2's)
     int H;
 };
@@ -36,9 +38,13 @@ struct TcState {
 // ------------------------------------------------------------------ small kernels
 __global__ void tc_pack_actor_kernel(const float* __restrict__ w, ActorOff o, int A, int td, int Do, int T, int H, int KP0,
                                      const float* __restrict__ bt, bf16* __restrict__ w2w0, bf16* __restrict__ w1,
-                                     bf16* __restrict__ w3t, bf16* __restrict__ w3p) {
+                                     bf16* __restrict__ w3t, bf16* __restrict__ w3p, bf16* __restrict__ w1t, bf16* __restrict__ w2t) {
     const size_t stride = (size_t)gridDim.x * blockDim.x, i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (size_t i = i0; i < (size_t)H * H; i += stride) { w2w0[i] = __float2bfloat16(w[o.w2 + i]); w1[i] = __float2bfloat16(w[o.w1 + i]); }
+    for (size_t i = i0; i < (size_t)H * H; i += stride) {
+        w2w0[i] = __float2bfloat16(w[o.w2 + i]); w1[i] = __float2bfloat16(w[o.w1 + i]);
+        const size_t r = i / H, c = i % H;            // transposed copies: coalesced writes, strided (L2-resident) reads
+        w1t[i] = __float2bfloat16(w[o.w1 + c * H + r]); w2t[i] = __float2bfloat16(w[o.w2 + c * H + r]);
+    }
     for (size_t i = i0; i < (size_t)KP0 * H; i += stride) {
         int k = (int)(i / H), c = (int)(i % H);
         float v = 0.f;
@@ -47,7 +53,7 @@ __global__ void tc_pack_actor_kernel(const float* __restrict__ w, ActorOff o, in
         else if (k < A + Do + T) v = bt[(size_t)(k - A - Do) * H + c];
         w2w0[(size_t)H * H + i] = __float2bfloat16(v);
     }
-    for (size_t i = i0; i < (size_t)32 * H; i += stride) {
+    for (size_t i = i0; i < (size_t)64 * H; i += stride) {
         int a = (int)(i / H), k = (int)(i % H);
         w3t[i] = __float2bfloat16(a < A ? w[o.w3 + (size_t)k * A + a] : 0.f);
     }
@@ -66,24 +72,26 @@ __global__ void tc_pack_critic_kernel(const float* __restrict__ w, CriticOff o, 
         float v = (k >= A && k < A + Do) ? w[o.win + (size_t)(k - A) * Hc + c] : 0.f;
         w2w0[(size_t)Hc * Hc + i] = __float2bfloat16(v);
     }
-    for (size_t i = i0; i < (size_t)32 * Hc; i += stride) { int a = (int)(i / Hc), k = (int)(i % Hc); w3t[i] = __float2bfloat16(a == 0 ? w[o.w3 + k] : 0.f); }
+    for (size_t i = i0; i < (size_t)64 * Hc; i += stride) { int a = (int)(i / Hc), k = (int)(i % Hc); w3t[i] = __float2bfloat16(a == 0 ? w[o.w3 + k] : 0.f); }
     for (size_t i = i0; i < (size_t)Hc * 64; i += stride) { int k = (int)(i / 64), a = (int)(i % 64); w3p[i] = __float2bfloat16(a == 0 ? w[o.w3 + k] : 0.f); }
     for (size_t i = i0; i < (size_t)Hc; i += stride) bias2[i] = w[o.b2 + i] + w[o.bin + i];
 }
 // h0[r] = [x[r] | obs[r / obs_div] | onehot(t_r) | 1 | 0..]; one thread per 8 consecutive columns (16-byte store)
+// chainK > 0: x is a chains tensor [B][chainK+1][A] and row r = b*chainK + k reads chains[b][k] (get_logprobs)
 __global__ void tc_pack_h0_kernel(const float* __restrict__ x, const float* __restrict__ obs, const int* __restrict__ trow, int tconst,
-                                  int N, int A, int Do, int T, int KP0, int obs_div, bf16* __restrict__ h0) {
+                                  int N, int A, int Do, int T, int KP0, int obs_div, bf16* __restrict__ h0, int chainK = 0) {
     const int g8 = KP0 / 8;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)N * g8) return;
     const int r = (int)(i / g8), k0 = (int)(i % g8) * 8;
     const int t = trow ? trow[r] : tconst;
+    const size_t xrow = chainK > 0 ? (size_t)(r / chainK) * (chainK + 1) + (r % chainK) : (size_t)r;
     __align__(16) bf16 o[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int k = k0 + j;
         float v = 0.f;
-        if (k < A) v = x ? x[(size_t)r * A + k] : 0.f;
+        if (k < A) v = x ? x[xrow * A + k] : 0.f;
         else if (k < A + Do) v = obs[(size_t)(r / obs_div) * Do + (k - A)];
         else if (k < A + Do + T) v = (k - A - Do == t) ? 1.f : 0.f;
         else if (k == A + Do + T) v = 1.f;
@@ -149,7 +157,9 @@ static int tc_init(dppo_handle* h) {
         w.H = H;
         CUDA_TRY(cudaMalloc(&w.w2w0, (size_t)(H + st->KP0) * H * sizeof(bf16)));
         CUDA_TRY(cudaMalloc(&w.w1, (size_t)H * H * sizeof(bf16)));
-        CUDA_TRY(cudaMalloc(&w.w3t, (size_t)32 * H * sizeof(bf16)));
+        CUDA_TRY(cudaMalloc(&w.w3t, (size_t)64 * H * sizeof(bf16)));
+        CUDA_TRY(cudaMalloc(&w.w1t, (size_t)H * H * sizeof(bf16)));
+        CUDA_TRY(cudaMalloc(&w.w2t, (size_t)H * H * sizeof(bf16)));
         CUDA_TRY(cudaMalloc(&w.w3p, (size_t)H * 64 * sizeof(bf16)));
         CUDA_TRY(cudaMalloc(&w.bias2, (size_t)H * sizeof(float)));
     }
@@ -159,7 +169,7 @@ static void tc_destroy(dppo_handle* h) {
     if (!h->tc) return;
     for (int net = 0; net < 4; ++net) {
         TcNetW& w = h->tc->net[net];
-        cudaFree(w.w2w0); cudaFree(w.w1); cudaFree(w.w3t); cudaFree(w.w3p); cudaFree(w.bias2);
+        cudaFree(w.w2w0); cudaFree(w.w1); cudaFree(w.w3t); cudaFree(w.w3p); cudaFree(w.bias2); cudaFree(w.w1t); cudaFree(w.w2t);
     }
     delete h->tc; h->tc = nullptr;
 }
@@ -175,7 +185,7 @@ static int tc_refresh_net(dppo_handle* h, int net, cudaStream_t s) {
     if (net == DPPO_NET_CRITIC)
         tc_pack_critic_kernel<<<128, 256, 0, s>>>(h->net_w[net], g.co, g.A, g.Do, g.Hc, h->tc->KP0, w.w2w0, w.w1, w.w3t, w.w3p, w.bias2);
     else
-        tc_pack_actor_kernel<<<256, 256, 0, s>>>(h->net_w[net], g.ao, g.A, g.td, g.Do, g.T, g.H, h->tc->KP0, h->ad[net].bt, w.w2w0, w.w1, w.w3t, w.w3p);
+        tc_pack_actor_kernel<<<256, 256, 0, s>>>(h->net_w[net], g.ao, g.A, g.td, g.Do, g.T, g.H, h->tc->KP0, h->ad[net].bt, w.w2w0, w.w1, w.w3t, w.w3p, w.w1t, w.w2t);
     h->launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) DPPO_FAIL(-3, "tc pack launch failed: %s", cudaGetErrorString(e));
@@ -185,6 +195,103 @@ static int tc_refresh_net(dppo_handle* h, int net, cudaStream_t s) {
 #define TC_KCHECK(h) do { (h)->launches++; cudaError_t _e = cudaGetLastError(); if (_e != cudaSuccess) { \
     dppo_set_error("kernel launch failed at %s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(_e)); return -3; } } while (0)
 static inline int tc_nblk(size_t n, int b) { return (int)((n + b - 1) / b); }
+
+// ------------------------------------------------------------------ fused layer-chain programs (fused_chain.cuh)
+static bool fc_ok(const dppo_handle* h) {
+    const Geom& g = h->g;
+    return tc_shapes_ok(h) && h->tc->KP0 == 64 && h->cfg.actor_act == DPPO_ACT_RELU && (g.H == 512 || g.H == 256) && g.A <= 32
+        && h->force_path != 3;
+}
+static int fc_weight_maps(const dppo_handle* h, int net, CUtensorMap* m) {
+    const TcNetW& W = h->tc->net[net]; const int H = h->g.H;
+    DPPO_TRY(fc::weight_map(&m[0], W.w2w0, H + 64, H));
+    DPPO_TRY(fc::weight_map(&m[1], W.w1, H, H));
+    DPPO_TRY(fc::weight_map(&m[2], W.w3p, H, 64));
+    return 0;
+}
+// forward program: L0 relu(H0 W0), L1 relu(X W1 + b1), L2 X W2 + H0 W0 + b2, L3 X W3 + b3; weight maps at m[wbase..wbase+2]
+static void fc_fwd_layers(const dppo_handle* h, int net, int wbase, fc::Layer* L) {
+    const Geom& g = h->g; const float* w = h->net_w[net]; const int H = g.H;
+    memset(L, 0, sizeof(fc::Layer) * fc::MAXL);
+    for (int i = 0; i < fc::MAXL; ++i) L[i].store_map = -1;
+    L[0].a_src = 0; L[0].wmap = wbase; L[0].wrow_h0 = H; L[0].n = H; L[0].act = 1;
+    L[1].a_src = 1; L[1].wmap = wbase + 1; L[1].n = H; L[1].bias = w + g.ao.b1; L[1].act = 1;
+    L[2].a_src = 2; L[2].wmap = wbase; L[2].wrow_h0 = H; L[2].n = H; L[2].bias = w + g.ao.b2; L[2].h0_last = 1;
+    L[3].a_src = 1; L[3].wmap = wbase + 2; L[3].n = 64; L[3].bias = w + g.ao.b3;
+}
+static double fc_fwd_flops(const dppo_handle* h, double rows) { const double H = h->g.H; return 2.0 * rows * (64 * H + H * H + (H + 64) * H + H * 64); }
+static void fc_common(const dppo_handle* h, fc::Params& p, int N) {
+    const Geom& g = h->g;
+    memset(&p, 0, sizeof(p));
+    p.rows = N; p.A = g.A; p.Do = g.Do; p.T = g.T; p.K = g.K; p.sch = h->sched;
+    p.dcv = h->cfg.denoised_clip_value; p.min_lp_std = h->cfg.min_logprob_denoising_std;
+}
+// inference forward from a packed h0: final = eps store or Gaussian log-prob
+static int fc_actor_infer(dppo_handle* h, cudaStream_t s, int net, const bf16* h0, int N, int mode, float* out,
+                          const float* prev, const float* next, const float* chains, const int* trow) {
+    fc::Maps maps; fc::Params p; fc_common(h, p, N);
+    DPPO_TRY(fc::rowtile_map(&maps.m[0], h0, N, 64));
+    DPPO_TRY(fc_weight_maps(h, net, &maps.m[1]));
+    for (int i = 4; i < fc::NMAPS; ++i) maps.m[i] = maps.m[0];
+    p.nlayers = 4; p.final_mode = mode; p.h0_from_tma = 1;
+    fc_fwd_layers(h, net, 1, p.L[0]);
+    p.out = out; p.prev = prev; p.next = next; p.chains = chains; p.trow = trow;
+    return fc::launch_chain(h, s, h->g.H, maps, p, fc_fwd_flops(h, N));
+}
+// training forward: eps + the tensors the backward needs (a0, a1, v in HBM via TMA store, ReLU bit masks)
+static int fc_actor_train_fwd(dppo_handle* h, cudaStream_t s, int net, const bf16* h0, int N, bf16* a0, bf16* a1, bf16* v,
+                              uint32_t* m0, uint32_t* m1, float* eps) {
+    const int H = h->g.H;
+    fc::Maps maps; fc::Params p; fc_common(h, p, N);
+    DPPO_TRY(fc::rowtile_map(&maps.m[0], h0, N, 64));
+    DPPO_TRY(fc_weight_maps(h, net, &maps.m[1]));
+    DPPO_TRY(fc::rowtile_map(&maps.m[4], a0, N, H));
+    DPPO_TRY(fc::rowtile_map(&maps.m[5], a1, N, H));
+    DPPO_TRY(fc::rowtile_map(&maps.m[6], v, N, H));
+    maps.m[7] = maps.m[0];
+    p.nlayers = 4; p.final_mode = fc::FINAL_EPS; p.h0_from_tma = 1;
+    fc_fwd_layers(h, net, 1, p.L[0]);
+    p.L[0][0].store_map = 4; p.L[0][0].mask_out = m0;
+    p.L[0][1].store_map = 5; p.L[0][1].mask_out = m1;
+    p.L[0][2].store_map = 6;
+    p.out = eps;
+    return fc::launch_chain(h, s, H, maps, p, fc_fwd_flops(h, N));
+}
+// backward chain: dv = deps W3^T, dh1 = (dv W2^T) . m1, du = (dh1 W1^T) . m0   (du excludes the residual path: dW0 adds h0^T dv)
+static int fc_actor_bwd(dppo_handle* h, cudaStream_t s, int net, const bf16* depsb, int N, const uint32_t* m0, const uint32_t* m1,
+                        bf16* dv, bf16* dh1, bf16* du) {
+    const int H = h->g.H; const TcNetW& W = h->tc->net[net];
+    fc::Maps maps; fc::Params p; fc_common(h, p, N);
+    DPPO_TRY(fc::rowtile_map(&maps.m[0], depsb, N, 64));
+    DPPO_TRY(fc::weight_map(&maps.m[1], W.w3t, 64, H));
+    DPPO_TRY(fc::weight_map(&maps.m[2], W.w2t, H, H));
+    DPPO_TRY(fc::weight_map(&maps.m[3], W.w1t, H, H));
+    DPPO_TRY(fc::rowtile_map(&maps.m[4], dv, N, H));
+    DPPO_TRY(fc::rowtile_map(&maps.m[5], dh1, N, H));
+    DPPO_TRY(fc::rowtile_map(&maps.m[6], du, N, H));
+    maps.m[7] = maps.m[0];
+    p.nlayers = 3; p.final_mode = fc::FINAL_STORE; p.h0_from_tma = 1;
+    fc::Layer* L = p.L[0];
+    memset(L, 0, sizeof(fc::Layer) * fc::MAXL);
+    L[0].a_src = 0; L[0].wmap = 1; L[0].wrow_h0 = 0; L[0].n = H; L[0].h0_last = 1; L[0].store_map = 4;
+    L[1].a_src = 1; L[1].wmap = 2; L[1].n = H; L[1].mask_in = m1; L[1].store_map = 5;
+    L[2].a_src = 1; L[2].wmap = 3; L[2].n = H; L[2].mask_in = m0; L[2].store_map = 6;
+    return fc::launch_chain(h, s, H, maps, p, 2.0 * N * ((double)64 * H + 2.0 * H * H));
+}
+// VPGDiffusion.call for large batches: the whole T-step chain in ONE launch
+static int fc_sample(dppo_handle* h, cudaStream_t s, const float* obs, int B, int use_base, SampleHyper hp, uint64_t seed,
+                     uint64_t offset, int64_t row_offset, const float* xT, const float* noise, float* actions, float* chains) {
+    fc::Maps maps; fc::Params p; fc_common(h, p, B);
+    DPPO_TRY(fc_weight_maps(h, DPPO_NET_ACTOR, &maps.m[1]));
+    DPPO_TRY(fc_weight_maps(h, DPPO_NET_ACTOR_FT, &maps.m[4]));
+    maps.m[0] = maps.m[1]; maps.m[7] = maps.m[1];
+    p.nlayers = 4; p.final_mode = fc::FINAL_SAMPLE; p.h0_from_tma = 0;
+    fc_fwd_layers(h, DPPO_NET_ACTOR, 1, p.L[0]);
+    fc_fwd_layers(h, DPPO_NET_ACTOR_FT, 4, p.L[1]);
+    p.obs = obs; p.xT = xT; p.noise = noise; p.actions = actions; p.chains_out = chains; p.hp = hp; p.use_base_policy = use_base;
+    p.seed = seed; p.offset = offset; p.row_offset = row_offset;
+    return fc::launch_chain(h, s, h->g.H, maps, p, fc_fwd_flops(h, B) * h->g.T);
+}
 
 // ------------------------------------------------------------------ GEMM helpers
 static tc::Operand opK(const bf16* p, int64_t mn, int64_t k, int64_t ld) { return tc::Operand{p, false, mn, k, ld}; }
@@ -204,10 +311,12 @@ struct TcMlp {
     bf16 *a0, *a1, *v, *pre0, *pre1;      // pre* only when act1 == 2
     float* out;                            // [N][NO] fp32
     bf16 *dv, *dh1, *du;                   // backward
+    uint32_t *m0, *m1;                     // fused chain: ReLU bit masks [N][H/32] of layer 0 / block.l1
+    int fused, net;                        // fused: the actor runs on the fused layer-chain kernel
 };
 static size_t tc_mlp_ws_bytes(int N, int H, bool mish, bool bwd) {
     size_t one = ws_bytes((size_t)N * H, sizeof(bf16));
-    return one * (3 + (mish ? 2 : 0) + (bwd ? 3 : 0));
+    return one * (3 + (mish ? 2 : 0) + (bwd ? 3 : 0)) + 2 * ws_bytes((size_t)N * (H / 32), 4);
 }
 static void tc_mlp_take(dppo_handle* h, int N, TcMlp& m, bool bwd) {
     const size_t n = (size_t)N * m.H;
@@ -216,9 +325,11 @@ static void tc_mlp_take(dppo_handle* h, int N, TcMlp& m, bool bwd) {
     if (m.act1 == 2) { m.pre0 = ws_take<bf16>(h, n); m.pre1 = ws_take<bf16>(h, n); }
     m.dv = m.dh1 = m.du = nullptr;
     if (bwd) { m.dv = ws_take<bf16>(h, n); m.dh1 = ws_take<bf16>(h, n); m.du = ws_take<bf16>(h, n); }
+    m.m0 = ws_take<uint32_t>(h, (size_t)N * (m.H / 32)); m.m1 = ws_take<uint32_t>(h, (size_t)N * (m.H / 32));
 }
 static int tc_mlp_forward(dppo_handle* h, cudaStream_t s, const TcMlp& m, int N) {
     const int H = m.H, KP0 = m.KP0; const TcNetW& W = *m.W;
+    if (m.fused) return fc_actor_train_fwd(h, s, m.net, m.h0, N, m.a0, m.a1, m.v, m.m0, m.m1, m.out);
     // L0: a0 = act(h0 W0 (+ b0))
     tc::Gemm g = gemm_of(opK(m.h0, N, KP0, KP0), opMN(W.w2w0 + (size_t)H * H, H, KP0, H), N, H);
     g.epi.bias = m.b0; g.epi.act = m.act1; g.epi.out_bf16 = m.a0; g.epi.ld_bf16 = H; g.epi.out_pre = m.pre0; g.epi.ld_pre = H;
@@ -249,13 +360,21 @@ static int tc_splits_for(const dppo_handle* h, int M, int N, int rows) {
     return splits;
 }
 // dW[M][ncols] = X^T D  (X [rows][M] bf16, D [rows][Nd] bf16), deterministic split-K over the rows
+// (+ X^T D2 when D2 is given: the partial sums of both products are reduced together)
 static int tc_dw(dppo_handle* h, cudaStream_t s, const bf16* X, int M, const bf16* D, int Nd, int rows, float* part,
-                 float* out, int out_rows, int out_cols, int ld_out) {
+                 float* out, int out_rows, int out_cols, int ld_out, const bf16* D2 = nullptr) {
     tc::Gemm g = gemm_of(opMN(X, M, rows, M), opMN(D, Nd, rows, Nd), M, Nd);
     g.splits = tc_splits_for(h, M, Nd, rows);
     g.epi.out_f32 = part; g.epi.ld_f32 = Nd; g.epi.split_stride = (size_t)M * Nd;
     int S = tc::launch(h, s, g);
     if (S < 0) return S;
+    if (D2) {
+        g.B = opMN(D2, Nd, rows, Nd);
+        g.epi.out_f32 = part + (size_t)S * M * Nd;
+        int S2 = tc::launch(h, s, g);
+        if (S2 < 0) return S2;
+        S += S2;
+    }
     tc_reduce2d_kernel<<<tc_nblk((size_t)out_rows * out_cols, 256), 256, 0, s>>>(part, S, (size_t)M * Nd, out_rows, out_cols, Nd, out, ld_out);
     TC_KCHECK(h);
     return 0;
@@ -278,6 +397,17 @@ static size_t tc_part_floats(const dppo_handle* h, int H) {
 static int tc_mlp_backward(dppo_handle* h, cudaStream_t s, const TcMlp& m, const bf16* doutb, int N, float* part,
                            float* gnet, size_t ow1, size_t ob1, size_t ow2, size_t ob2, size_t ow3, float* dw0) {
     const int H = m.H, KP0 = m.KP0; const TcNetW& W = *m.W;
+    if (m.fused) {
+        // one launch: dv, dh1 and the non-residual part of du; the residual path joins in dW0 = h0^T du + h0^T dv
+        DPPO_TRY(fc_actor_bwd(h, s, m.net, doutb, N, m.m0, m.m1, m.dv, m.dh1, m.du));
+        DPPO_TRY(tc_dw(h, s, m.v, H, doutb, 64, N, part, gnet + ow3, H, m.NO, m.NO));
+        DPPO_TRY(tc_dw(h, s, m.a1, H, m.dv, H, N, part, gnet + ow2, H, H, H));
+        DPPO_TRY(tc_dw(h, s, m.a0, H, m.dh1, H, N, part, gnet + ow1, H, H, H));
+        DPPO_TRY(tc_dw(h, s, m.h0, KP0, m.du, H, N, part, dw0, KP0, H, H, m.dv));
+        DPPO_TRY(tc_colsum(h, s, m.dv, N, H, part, gnet + ob2));
+        DPPO_TRY(tc_colsum(h, s, m.dh1, N, H, part, gnet + ob1));
+        return 0;
+    }
     // dv = dout W3^T
     tc::Gemm g = gemm_of(opK(doutb, N, 64, 64), opK(W.w3p, H, 64, 64), N, H);
     g.epi.out_bf16 = m.dv; g.epi.ld_bf16 = H;
@@ -306,11 +436,13 @@ static int tc_mlp_backward(dppo_handle* h, cudaStream_t s, const TcMlp& m, const
 static void tc_actor_mlp(const dppo_handle* h, int net, TcMlp& m) {
     const Geom& g = h->g; const float* w = h->net_w[net];
     m.W = &h->tc->net[net]; m.H = g.H; m.NO = g.A; m.act1 = h->cfg.actor_act + 1; m.KP0 = h->tc->KP0;
+    m.fused = fc_ok(h) ? 1 : 0; m.net = net;
     m.b0 = nullptr; m.b1 = w + g.ao.b1; m.b2 = w + g.ao.b2; m.b3 = w + g.ao.b3;
 }
 static void tc_critic_mlp(const dppo_handle* h, TcMlp& m) {
     const Geom& g = h->g; const float* w = h->net_w[DPPO_NET_CRITIC];
     m.W = &h->tc->net[DPPO_NET_CRITIC]; m.H = g.Hc; m.NO = 1; m.act1 = h->cfg.critic_act + 1; m.KP0 = h->tc->KP0;
+    m.fused = 0; m.net = DPPO_NET_CRITIC;
     m.b0 = w + g.co.bin; m.b1 = w + g.co.b1; m.b2 = m.W->bias2; m.b3 = w + g.co.b3;
 }
 
@@ -318,6 +450,17 @@ static void tc_critic_mlp(const dppo_handle* h, TcMlp& m) {
 static int tc_actor_forward(dppo_handle* h, cudaStream_t s, int net, const float* x, const float* obs, int obs_div, int N,
                             const int* trow, int tconst, float* eps) {
     const Geom& g = h->g; const int KP0 = h->tc->KP0;
+    if (fc_ok(h)) {
+        const size_t need = h->ws.used + ws_bytes((size_t)N * KP0, 2);
+        if (need > h->ws.cap) DPPO_FAIL(-7, "tc_actor_forward: workspace too small (%zu > %zu)", need, h->ws.cap);
+        const size_t mark = h->ws.used;
+        bf16* h0 = ws_take<bf16>(h, (size_t)N * KP0);
+        tc_pack_h0_kernel<<<tc_nblk((size_t)N * (KP0 / 8), 256), 256, 0, s>>>(x, obs, trow, tconst, N, g.A, g.Do, g.T, KP0, obs_div, h0);
+        TC_KCHECK(h);
+        int r = fc_actor_infer(h, s, net, h0, N, fc::FINAL_EPS, eps, nullptr, nullptr, nullptr, nullptr);
+        h->ws.used = mark;
+        return r;
+    }
     // the caller may hold workspace pointers (eps, trow) below ws.used: only append
     const size_t need = h->ws.used + ws_bytes((size_t)N * KP0, 2) + tc_mlp_ws_bytes(N, g.H, h->cfg.actor_act == DPPO_ACT_MISH, false);
     if (need > h->ws.cap) DPPO_FAIL(-7, "tc_actor_forward: workspace too small (%zu > %zu)", need, h->ws.cap);

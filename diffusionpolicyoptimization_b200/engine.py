@@ -234,6 +234,9 @@ class Engine:
     def tc_launch_count(self) -> int:
         return int(self.lib.dppo_tc_launch_count(self.h))
 
+    def fused_launch_count(self) -> int:
+        return int(self.lib.dppo_fused_launch_count(self.h))
+
     def last_path(self) -> int:
         return int(self.lib.dppo_last_path(self.h))
 

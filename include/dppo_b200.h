@@ -183,10 +183,14 @@ int dppo_comm_init(dppo_handle* h, const char* id128, int rank, int world);
 int64_t dppo_launch_count(dppo_handle* h);
 /* Of those, the tcgen05 GEMM launches (0 in DPPO_PREC_FP32 mode and below the row threshold). */
 int64_t dppo_tc_launch_count(dppo_handle* h);
+/* Of those, launches of the fused layer-chain kernel (whole MLP forward / backward / T-step sampler per launch). */
+int64_t dppo_fused_launch_count(dppo_handle* h);
 /* Which sampler the last dppo_sample used: 1 = persistent cluster kernel (one launch, T steps on
- * chip), 2 = layer-by-layer fp32, 3 = layer-by-layer tcgen05.  Test / bench introspection. */
+ * chip, fp32 FFMA), 2 = layer-by-layer fp32, 3 = layer-by-layer tcgen05, 4 = fused tcgen05 chain
+ * (one launch, T steps on chip).  Test / bench introspection. */
 int dppo_last_path(dppo_handle* h);
-/* Test hook: 0 = automatic dispatch, 1 = force the cluster sampler, 2 = forbid it. */
+/* Test hook: 0 = automatic dispatch, 1 = force the cluster sampler, 2 = forbid it,
+ * 3 = forbid the fused tcgen05 chain (the tensor path then runs one GEMM launch per layer). */
 int dppo_force_path(dppo_handle* h, int path);
 /* Live kernel timing for the roofline: when enabled, every GEMM-class launch (the MLP layers and
  * their gradients: >97% of the path's flops) is bracketed by CUDA events on the launching stream.
