@@ -81,6 +81,26 @@ __device__ __forceinline__ float philox_normal(uint64_t seed, uint64_t offset, i
     sincospif(2.f * u1, &sn, &cs);
     return (a & 1) ? rad * sn : rad * cs;
 }
+// the four normals of Philox block `blk` (elements a = 4*blk .. 4*blk+3): identical values to philox_normal
+__device__ __forceinline__ void philox_normal4(uint64_t seed, uint64_t offset, int64_t row, int slot, int blk, float (&out)[4]) {
+    Philox4 c;
+    c.x = (uint32_t)blk | ((uint32_t)slot << 8);
+    c.y = (uint32_t)offset;
+    c.z = (uint32_t)(uint64_t)row;
+    c.w = (uint32_t)((uint64_t)row >> 32);
+    Philox4 r = philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32) + (uint32_t)(offset >> 32));
+#pragma unroll
+    for (int hlf = 0; hlf < 2; ++hlf) {
+        const uint32_t b0 = hlf ? r.z : r.x, b1 = hlf ? r.w : r.y;
+        float u0 = ((float)b0 + 0.5f) * 2.3283064365386963e-10f;
+        float u1 = ((float)b1 + 0.5f) * 2.3283064365386963e-10f;
+        u0 = fminf(fmaxf(u0, 1.1754944e-38f), 0.99999994f);
+        float rad = sqrtf(-2.f * logf(u0));
+        float sn, cs;
+        sincospif(2.f * u1, &sn, &cs);
+        out[hlf * 2 + 0] = rad * cs; out[hlf * 2 + 1] = rad * sn;
+    }
+}
 __device__ __forceinline__ uint32_t philox_uint(uint64_t seed, uint64_t offset, int64_t row, int slot) {
     Philox4 c;
     c.x = ((uint32_t)slot << 8);
@@ -137,6 +157,7 @@ struct dppo_handle {
     void* comm = nullptr; int rank = 0, world = 1;
     int64_t launches = 0;
     int64_t tc_launches = 0;
+    long long* chain_dbg = nullptr;   // dev tool: per-CTA cycle counters of the last fused-chain launch [sm_count][8]
     int64_t fused_launches = 0;   // of those, fused layer-chain launches
     int cluster_max = -1; // max co-resident 16-CTA clusters (-1 unknown, 0 = not launchable)
     int last_path = 0;    // sampler path of the last dppo_sample: 1 cluster, 2 layered fp32, 3 tensor

@@ -889,6 +889,34 @@ extern "C" int dppo_ema_update(dppo_handle* h, float decay, dppo_stream_t st) {
     ema_kernel<<<nblk(n, 256), 256, 0, s>>>(h->net_w[DPPO_NET_ACTOR_EMA], h->net_w[DPPO_NET_ACTOR], n, decay); KLAUNCH(h); KCHECK();
     return prep_net(h, DPPO_NET_ACTOR_EMA, s);
 }
+// dev tool: enable per-CTA cycle counters of the fused chain kernel and read them back (host out [sm_count][8])
+extern "C" int dppo_debug_chain_timing(dppo_handle* h, int enable, long long* out_host, int* sm_count) {
+    if (!h) DPPO_FAIL(-1, "null handle");
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (sm_count) *sm_count = h->sm_count;
+    if (enable && !h->chain_dbg) { CUDA_TRY(cudaMalloc(&h->chain_dbg, (size_t)h->sm_count * 8 * sizeof(long long))); CUDA_TRY(cudaMemset(h->chain_dbg, 0, (size_t)h->sm_count * 8 * sizeof(long long))); }
+    if (out_host && h->chain_dbg) { CUDA_TRY(cudaDeviceSynchronize()); CUDA_TRY(cudaMemcpy(out_host, h->chain_dbg, (size_t)h->sm_count * 8 * sizeof(long long), cudaMemcpyDeviceToHost)); }
+    if (!enable && h->chain_dbg) { CUDA_TRY(cudaDeviceSynchronize()); cudaFree(h->chain_dbg); h->chain_dbg = nullptr; }
+    return 0;
+}
+// dev probe (tools/mma_probe.py): out_host [2*grid] per CTA, see fc::mma_probe_kernel
+extern "C" int dppo_debug_mma_probe(dppo_handle* h, int grid, int mode, int iters, int N, int depth, long long* out_host) {
+    if (!h || !out_host || grid < 1 || grid > 1024 || depth < 0 || depth > 31) DPPO_FAIL(-1, "dppo_debug_mma_probe: bad arguments");
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (!tc_shapes_ok(h)) DPPO_FAIL(-7, "tensor path unavailable");
+    CUtensorMap wm;
+    DPPO_TRY(fc::weight_map(&wm, h->tc->net[DPPO_NET_ACTOR].w1, h->g.H, h->g.H));
+    long long* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, (size_t)grid * 2 * sizeof(long long)));
+    CUDA_TRY(cudaMemset(d, 0, (size_t)grid * 2 * sizeof(long long)));
+    const int smem = 16384 * 5 + 1024 + 256;
+    CUDA_TRY(cudaFuncSetAttribute(fc::mma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    fc::mma_probe_kernel<<<grid, 128, smem>>>(wm, mode, iters, N, depth, d);
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(out_host, d, (size_t)grid * 2 * sizeof(long long), cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    return 0;
+}
 extern "C" int dppo_force_path(dppo_handle* h, int path) { if (!h) return -1; h->force_path = path; return 0; }
 
 extern "C" int dppo_debug_tc_gemm(dppo_handle* h, const void* A, int a_mn, int64_t lda, const void* A2, int64_t lda2, int K2,

@@ -11,7 +11,8 @@
 //
 //   warp 0     TMA producer (weight ring, H0 tiles)
 //   warp 1     tcgen05.mma issuer (one elected thread), TMEM allocation
-//   warps 2-5  epilogue: tcgen05.ld -> bias / ReLU / ReLU-mask -> bf16 -> swizzled st.shared into X
+//   warps 2-9  epilogue (two warps per TMEM lane quadrant, each takes half of the columns; TMEM loads
+//              software-pipelined): tcgen05.ld -> bias / ReLU / ReLU-mask -> bf16 -> swizzled st.shared into X
 //              (+ TMA store of X to HBM when the backward pass needs the tensor), and the final-layer
 //              math: eps store, Gaussian log-prob, or the DDPM posterior step of the sampler.
 //
@@ -29,7 +30,7 @@
 namespace fc {
 using namespace tc;
 
-constexpr int FBM = 128, WK = 32, NSTAGE = 4, FTHREADS = 192, MAXL = 4, NMAPS = 8;
+constexpr int FBM = 128, WK = 32, NSTAGE = 4, FTHREADS = 320, MAXL = 4, NMAPS = 8;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
 constexpr int STAGE_BYTES = WK * 256 * 2;      // 16 KB
 constexpr int H0_BYTES = FBM * 64 * 2;         // 16 KB
 
@@ -62,6 +63,7 @@ struct Params {
     float* actions; float* chains_out;
     SampleHyper hp; int use_base_policy;
     uint64_t seed, offset; int64_t row_offset;
+    long long* dbg;            // optional [grid][8] cycle counters (dev tool): see chain_kernel
 };
 struct Maps { CUtensorMap m[NMAPS]; };
 
@@ -73,7 +75,7 @@ __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -82,27 +84,104 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&t);
 }
 
-template <int H> constexpr size_t chain_smem_bytes() {
-    return (size_t)(H / 64) * 16384 + H0_BYTES + (size_t)NSTAGE * STAGE_BYTES + 1024 + 256;
+// One lane of a converged warp (elect.sync).  The issue warps keep warp-uniform control flow and elect a lane only
+// around the tcgen05 / TMA instructions: inside a lane-divergent branch (`if (lane == 0)`) nvcc wraps every
+// uniform-datapath instruction (UTCHMMA, UTCBAR, UTMALDG) in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall loop,
+// which made the single issuing thread the bottleneck (tools/mma_probe.py: ~90 cycles per tcgen05.mma issued).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xFFFFFFFF;\n\tselp.b32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+// raw shared-address variants for the single-thread issue loops (no generic->shared conversion per call)
+__device__ __forceinline__ bool mbar_try_wait_addr(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_addr(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait_addr(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait_addr(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) { printf("fused chain: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+    }
+}
+__device__ __forceinline__ void mbar_expect_tx_addr(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_addr(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_addr(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// tcgen05.mma with the two shared-memory descriptors given as (low word, shared high word)
+__device__ __forceinline__ void umma_bf16_split(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tmov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\tsetp.ne.b32 p, %5, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+                 ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate) : "memory");
 }
 
-// write this thread's row of the H0 tile: [x (A) | obs (Do) | onehot(t) (T) | 1 | 0..], 128B-swizzled
-__device__ __forceinline__ void build_h0_row(uint32_t h0_addr, int rloc, const float (&x)[32], const float* __restrict__ obs_row,
-                                             int A, int Do, int T, int t, bool valid) {
+template <int H> constexpr size_t chain_smem_bytes() {
+    return (size_t)(H / 64) * 16384 + H0_BYTES + (size_t)NSTAGE * STAGE_BYTES + 2 * 512 * sizeof(float) + 1024 + 256;
+}
+
+// asynchronous TMEM load of 32 columns (no wait) and the matching wait, tied to the destination registers so
+// that no use of them can be scheduled ahead of the wait
+__device__ __forceinline__ void tmem_ld32_async(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+        : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+          "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+          "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+          "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+        :: "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+        : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+          "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+        :: "memory");
+}
+
+// H0 row image [x (A) | obs (Do) | onehot(t) (T) | 1 | 0..] (64 bf16, 128B-swizzled).  The two epilogue threads of a
+// row split it: half 0 owns x[0:16) and writes 16-byte chunks {0,1,4,5}; half 1 owns x[16:32) and writes {2,3,6,7}.
+__device__ __forceinline__ void build_h0_half(uint32_t h0_addr, int rloc, int half, const float (&x)[16], const float* __restrict__ obs_row,
+                                              int A, int Do, int T, int t, bool valid) {
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
+    for (int ci = 0; ci < 4; ++ci) {
+        const int c = (ci < 2 ? 0 : 4) + half * 2 + (ci & 1);         // chunk index 0..7
         uint32_t w[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             float v2[2];
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const int k = c * 8 + j * 2 + e;
+                const int k = c * 8 + j * 2 + e;                      // column
+                const int xi = (ci & 1) * 8 + j * 2 + e;              // index into this half's x (only meaningful for ci < 2)
                 float v = 0.f;
                 if (valid) {
-                    if (k < 32 && k < A) v = x[k < 32 ? k : 0];
-                    else if (k < A + Do) v = __ldg(obs_row + (k - A));
-                    else if (k < A + Do + T) v = (k - A - Do == t) ? 1.f : 0.f;
+                    if (ci < 2 && k < A) v = x[xi];
+                    else if (k >= A && k < A + Do) v = __ldg(obs_row + (k - A));
+                    else if (k >= A + Do && k < A + Do + T) v = (k - A - Do == t) ? 1.f : 0.f;
                     else if (k == A + Do + T) v = 1.f;
                 }
                 v2[e] = v;
@@ -113,7 +192,7 @@ __device__ __forceinline__ void build_h0_row(uint32_t h0_addr, int rloc, const f
     }
 }
 
-template <int H>
+template <int H, bool TIMING>
 __global__ void __launch_bounds__(FTHREADS, 1) chain_kernel(const __grid_constant__ Maps maps, const Params p) {
     constexpr int XT = H / 64;
     constexpr int X_BYTES = XT * 16384;
@@ -122,7 +201,8 @@ __global__ void __launch_bounds__(FTHREADS, 1) chain_kernel(const __grid_constan
     uint8_t* sX = smem;
     uint8_t* sH0 = sX + X_BYTES;
     uint8_t* sW = sH0 + H0_BYTES;
-    uint64_t* bars = (uint64_t*)(sW + NSTAGE * STAGE_BYTES);
+    float* sBias = (float*)(sW + NSTAGE * STAGE_BYTES);           // 2 x 512 fp32, double buffered across layers
+    uint64_t* bars = (uint64_t*)(sBias + 2 * 512);
     uint64_t* w_full = bars;
     uint64_t* w_empty = bars + NSTAGE;
     uint64_t* h0_full = bars + 2 * NSTAGE;
@@ -139,7 +219,7 @@ __global__ void __launch_bounds__(FTHREADS, 1) chain_kernel(const __grid_constan
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < NMAPS; ++i) tma_prefetch_desc(&maps.m[i]);
         for (int i = 0; i < NSTAGE; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-        mbar_init(h0_full, 1); mbar_init(h0_empty, 1); mbar_init(acc_full, 1); mbar_init(x_full, 4);
+        mbar_init(h0_full, 1); mbar_init(h0_empty, 1); mbar_init(acc_full, 1); mbar_init(x_full, 8);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -149,17 +229,24 @@ __global__ void __launch_bounds__(FTHREADS, 1) chain_kernel(const __grid_constan
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);    // warp-uniform for the compiler
 
     if (warp == 0) {
         // ===================================================== TMA producer
-        if (lane == 0) {
+        // Warp-uniform control flow; one elected lane issues the TMA instructions of a stage.
+        {
             int stage = 0; uint32_t phase = 0, h0_phase = 0;
+            long long t_wempty = 0;
+            const uint32_t w_addr = smem_u32(sW);
+            const uint32_t wfull_addr = smem_u32(w_full), wempty_addr = smem_u32(w_empty);
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 if (p.h0_from_tma) {
                     mbar_wait(h0_empty, h0_phase ^ 1);
-                    mbar_expect_tx(h0_full, H0_BYTES);
-                    tma_load_2d(sH0, &maps.m[0], h0_full, 0, tile * FBM);
+                    if (elect_one()) {
+                        mbar_expect_tx(h0_full, H0_BYTES);
+                        tma_load_2d(sH0, &maps.m[0], h0_full, 0, tile * FBM);
+                    }
+                    __syncwarp();
                     h0_phase ^= 1;
                 }
                 for (int step = 0; step < nsteps; ++step) {
@@ -168,26 +255,50 @@ __global__ void __launch_bounds__(FTHREADS, 1) chain_kernel(const __grid_constan
                         const Layer& L = p.L[net][l];
                         const int n_cur = L.n < 256 ? L.n : 256, nhc = L.n / n_cur;
                         const int kx = L.a_src >= 1 ? H / WK : 0, kh = L.a_src != 1 ? 64 / WK : 0;
+                        const CUtensorMap* wm = &maps.m[L.wmap];
+                        const uint32_t tx = (uint32_t)(WK * n_cur * 2);
+                        const int nbox = n_cur / 64;
                         for (int nh = 0; nh < nhc; ++nh) {
+                            const int col = nh * n_cur;
+                            int krow = kx ? L.wrow_x : L.wrow_h0;
                             for (int s = 0; s < kx + kh; ++s) {
-                                const int krow = s < kx ? L.wrow_x + s * WK : L.wrow_h0 + (s - kx) * WK;
-                                mbar_wait(&w_empty[stage], phase ^ 1);
-                                mbar_expect_tx(&w_full[stage], (uint32_t)(WK * n_cur * 2));
-                                uint8_t* dst = sW + stage * STAGE_BYTES;
-                                for (int j = 0; j < n_cur / 64; ++j)
-                                    tma_load_2d(dst + j * (WK * 128), &maps.m[L.wmap], &w_full[stage], nh * n_cur + j * 64, krow);
+                                if (s == kx) krow = L.wrow_h0;
+                                const uint32_t full_bar = wfull_addr + stage * 8;
+                                if (TIMING) { const long long c0 = clock64(); mbar_wait_addr(wempty_addr + stage * 8, phase ^ 1); t_wempty += clock64() - c0; }
+                                else mbar_wait_addr(wempty_addr + stage * 8, phase ^ 1);
+                                if (elect_one()) {
+                                    mbar_expect_tx_addr(full_bar, tx);
+                                    const uint32_t dst = w_addr + stage * STAGE_BYTES;
+                                    tma_load_2d_addr(dst, wm, full_bar, col, krow);
+                                    if (nbox == 4) {
+                                        tma_load_2d_addr(dst + 1 * (WK * 128), wm, full_bar, col + 64, krow);
+                                        tma_load_2d_addr(dst + 2 * (WK * 128), wm, full_bar, col + 128, krow);
+                                        tma_load_2d_addr(dst + 3 * (WK * 128), wm, full_bar, col + 192, krow);
+                                    }
+                                }
+                                __syncwarp();
+                                krow += WK;
                                 if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                             }
                         }
                     }
                 }
             }
+            if (TIMING && p.dbg && lane == 0) p.dbg[blockIdx.x * 8 + 0] = t_wempty;
         }
     } else if (warp == 1) {
         // ===================================================== MMA issuer
-        if (lane == 0) {
+        // The issuing thread is latency bound on its own instruction stream (~6 cycles per dependent instruction,
+        // measured with tools/mma_probe.py), so descriptors are kept as 32-bit halves: the high word and the B
+        // descriptors of the four ring slots are loop invariants, the A descriptor advances by an add.
+        {
             int stage = 0; uint32_t phase = 0, h0_phase = 0, x_phase = 0;
-            const uint32_t x_addr = smem_u32(sX), h0_addr = smem_u32(sH0);
+            const uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);          // SBO = 1024 B, version 1, SWIZZLE_128B
+            const uint32_t a_lo_x = ((smem_u32(sX) >> 4) & 0x3FFFu) | (1u << 16);     // K-major A: LBO = 16 B
+            const uint32_t a_lo_h0 = ((smem_u32(sH0) >> 4) & 0x3FFFu) | (1u << 16);
+            const uint32_t b_lo_0 = ((smem_u32(sW) >> 4) & 0x3FFFu) | ((uint32_t)(WK * 128 >> 4) << 16);   // MN-major B: LBO = one 64-column atom
+            const uint32_t wfull_addr = smem_u32(w_full), wempty_addr = smem_u32(w_empty);
+            long long t_x = 0, t_w = 0; const long long t_begin = TIMING ? clock64() : 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 bool h0_waited = false;
                 for (int step = 0; step < nsteps; ++step) {
@@ -197,63 +308,84 @@ __global__ void __launch_bounds__(FTHREADS, 1) chain_kernel(const __grid_constan
                         const int n_cur = L.n < 256 ? L.n : 256, nhc = L.n / n_cur;
                         const int kx = L.a_src >= 1 ? H / WK : 0, kh = L.a_src != 1 ? 64 / WK : 0;
                         const uint32_t idesc = make_idesc(FBM, n_cur, false, true);
+                        const bool h0_rel = L.h0_last && p.h0_from_tma;
                         // previous epilogue done: X / H0 written, TMEM drained
-                        mbar_wait(x_full, x_phase); x_phase ^= 1;
+                        if (TIMING) { const long long c0 = clock64(); mbar_wait(x_full, x_phase); t_x += clock64() - c0; } else mbar_wait(x_full, x_phase);
+                        x_phase ^= 1;
                         if (L.a_src != 1 && p.h0_from_tma && !h0_waited) { mbar_wait(h0_full, h0_phase); h0_phase ^= 1; h0_waited = true; }
                         tcgen05_fence_after();
                         for (int nh = 0; nh < nhc; ++nh) {
                             const uint32_t tmem_d = tmem_base + (uint32_t)(nh * 256);
+                            uint32_t accf = 0u;
+                            uint32_t a_lo = kx ? a_lo_x : a_lo_h0;
                             for (int s = 0; s < kx + kh; ++s) {
-                                mbar_wait(&w_full[stage], phase);
+                                if (s == kx) a_lo = a_lo_h0;
+                                if (TIMING) { const long long c0 = clock64(); mbar_wait_addr(wfull_addr + stage * 8, phase); t_w += clock64() - c0; }
+                                else mbar_wait_addr(wfull_addr + stage * 8, phase);
                                 tcgen05_fence_after();
-                                const uint32_t b0 = smem_u32(sW + stage * STAGE_BYTES);
-#pragma unroll
-                                for (int q = 0; q < WK / 16; ++q) {
-                                    uint32_t a_at;
-                                    if (s < kx) { const int k = s * WK + q * 16; a_at = x_addr + (k >> 6) * 16384 + (k & 63) * 2; }
-                                    else { const int k = (s - kx) * WK + q * 16; a_at = h0_addr + k * 2; }
-                                    const uint64_t da = make_desc(a_at, 16, 1024);
-                                    const uint64_t db = make_desc(b0 + q * 2048, WK * 128, 1024);
-                                    umma_bf16(tmem_d, da, db, idesc, (s > 0 || q > 0) ? 1u : 0u);
+                                const uint32_t b_lo = b_lo_0 + (uint32_t)stage * (STAGE_BYTES >> 4);
+                                if (elect_one()) {
+                                    umma_bf16_split(tmem_d, a_lo, b_lo, desc_hi, idesc, accf);
+                                    umma_bf16_split(tmem_d, a_lo + 2u, b_lo + (2048u >> 4), desc_hi, idesc, 1u);
+                                    tcgen05_commit_addr(wempty_addr + stage * 8);
                                 }
-                                tcgen05_commit(&w_empty[stage]);
+                                __syncwarp();
+                                accf = 1u;
+                                // next 32 columns of A: +64 B inside a 128-byte row, then on to the next 64-column tile
+                                a_lo += (s & 1) ? (16384u >> 4) - 4u : 4u;
                                 if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                             }
                         }
-                        tcgen05_commit(acc_full);
-                        if (L.h0_last && p.h0_from_tma) tcgen05_commit(h0_empty);
+                        if (elect_one()) {
+                            tcgen05_commit(acc_full);
+                            if (h0_rel) tcgen05_commit(h0_empty);
+                        }
+                        __syncwarp();
                     }
                 }
             }
+            if (TIMING && p.dbg && lane == 0) { p.dbg[blockIdx.x * 8 + 1] = t_x; p.dbg[blockIdx.x * 8 + 2] = t_w; p.dbg[blockIdx.x * 8 + 3] = clock64() - t_begin; }
         }
     } else {
-        // ===================================================== epilogue warps
-        const int quad = warp & 3;
+        // ===================================================== epilogue warps (8: two per TMEM lane quadrant)
+        const int quad = warp & 3;                               // TMEM lane quadrant this warp may access
+        const int half = (warp - 2) >> 2;                        // 0: first half of the columns, 1: second half
         const int rloc = quad * 32 + lane;                       // row inside the tile == TMEM lane
         const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
         const uint32_t x_addr = smem_u32(sX), h0_addr = smem_u32(sH0);
         const bool store_thread = (warp == 2 && lane == 0);
+        const int etid = threadIdx.x - 64;                       // 0..255
         uint32_t acc_phase = 0;
+        int bias_buf = 0;
         const int A = p.A;
-        float x[32];
+        float x[16];                                             // sampler: this thread's half of the row's x
 #pragma unroll
-        for (int a = 0; a < 32; ++a) x[a] = 0.f;
+        for (int a = 0; a < 16; ++a) x[a] = 0.f;
         bool first = true;
+        long long t_acc = 0, t_gen = 0, t_fin = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int row = tile * FBM + rloc;
             const bool valid = row < p.rows;
+            const float* obs_row = p.obs + (size_t)(valid ? row : 0) * p.Do;
             if (sampler) {
                 // tile prologue: x_T (injected or Philox slot 0), first H0 image
 #pragma unroll
-                for (int a = 0; a < 32; ++a) {
-                    float v = 0.f;
-                    if (valid && a < A) {
-                        v = p.xT ? p.xT[(size_t)row * A + a] : philox_normal(p.seed, p.offset, p.row_offset + row, 0, a);
-                        if (p.chains_out && p.K == p.T) p.chains_out[((size_t)row * (p.K + 1)) * A + a] = v;
+                for (int b4 = 0; b4 < 4; ++b4) {
+                    float nz[4] = {0.f, 0.f, 0.f, 0.f};
+                    const int a0 = half * 16 + b4 * 4;
+                    if (valid && a0 < A && !p.xT) philox_normal4(p.seed, p.offset, p.row_offset + row, 0, a0 >> 2, nz);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int a = a0 + e;
+                        float v = 0.f;
+                        if (valid && a < A) {
+                            v = p.xT ? p.xT[(size_t)row * A + a] : nz[e];
+                            if (p.chains_out && p.K == p.T) p.chains_out[((size_t)row * (p.K + 1)) * A + a] = v;
+                        }
+                        x[b4 * 4 + e] = v;
                     }
-                    x[a] = v;
                 }
-                build_h0_row(h0_addr, rloc, x, p.obs + (size_t)(valid ? row : 0) * p.Do, A, p.Do, p.T, p.T - 1, valid);
+                build_h0_half(h0_addr, rloc, half, x, obs_row, A, p.Do, p.T, p.T - 1, valid);
                 fence_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(x_full);
@@ -267,48 +399,70 @@ __global__ void __launch_bounds__(FTHREADS, 1) chain_kernel(const __grid_constan
                 for (int l = 0; l < p.nlayers; ++l) {
                     const Layer& L = p.L[net][l];
                     const bool final_layer = (l == p.nlayers - 1) && p.final_mode != FINAL_STORE;
+                    // stage this layer's bias in shared memory while the MMAs run (double buffered across layers)
+                    float* sb = sBias + bias_buf * 512; bias_buf ^= 1;
+                    if (L.bias) { for (int i = etid; i < (final_layer ? A : L.n); i += 256) sb[i] = __ldg(L.bias + i); }
+                    long long c_epi = TIMING ? clock64() : 0;
                     mbar_wait(acc_full, acc_phase); acc_phase ^= 1;
+                    if (TIMING) { const long long c1 = clock64(); t_acc += c1 - c_epi; c_epi = c1; }
                     tcgen05_fence_after();
                     if (!final_layer) {
                         // ---------------- generic layer: TMEM -> X (in place)
                         if (store_thread) tma_store_wait_read();       // earlier TMA stores must have finished reading X
                         epi_barrier();
+                        const int nch = L.n / 64;                      // 32-column chunks per half
+                        const int c_first = half * nch;
                         const uint32_t* min_row = L.mask_in ? L.mask_in + (size_t)row * (H / 32) : nullptr;
                         uint32_t* mout_row = L.mask_out ? L.mask_out + (size_t)row * (H / 32) : nullptr;
                         uint32_t mo[4] = {0u, 0u, 0u, 0u};
                         uint4 mi4 = make_uint4(0u, 0u, 0u, 0u);
+                        uint32_t ra[32], rb[32];
+                        tmem_ld32_async(tmem_base + lane_base + (uint32_t)(c_first * 32), ra);
 #pragma unroll 1
-                        for (int c = 0; c < L.n / 32; ++c) {
-                            uint32_t r[32];
-                            tmem_ld32(tmem_base + lane_base + (uint32_t)(c * 32), r);
-                            const int n0 = c * 32;
-                            float v[32];
+                        for (int ci = 0; ci < nch; ci += 4) {          // nch is 4 or 8; c & 3 == u below
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                            if (L.bias) {
+                            for (int u = 0; u < 4; ++u) {
+                                const int c = c_first + ci + u;
+                                uint32_t (&r)[32] = (u & 1) ? rb : ra;
+                                tmem_ld_wait(r);
+                                if ((u & 1) == 0) tmem_ld32_async(tmem_base + lane_base + (uint32_t)((c + 1) * 32), rb);
+                                else if (u == 1 || ci + 4 < nch) tmem_ld32_async(tmem_base + lane_base + (uint32_t)((c + 1) * 32), ra);
+                                const int n0 = c * 32;
+                                float v[32];
 #pragma unroll
-                                for (int j = 0; j < 32; ++j) v[j] += __ldg(L.bias + n0 + j);
+                                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                                if (L.bias) {
+#pragma unroll
+                                    for (int j = 0; j < 32; j += 4) {
+                                        const float4 b4 = *reinterpret_cast<const float4*>(sb + n0 + j);
+                                        v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+                                    }
+                                }
+                                if (L.act == 1) {
+                                    if (mout_row) {
+                                        uint32_t bits = 0u;
+#pragma unroll
+                                        for (int j = 0; j < 32; ++j) bits |= (v[j] > 0.f ? 1u : 0u) << j;
+                                        mo[u] = bits;
+                                        if (u == 3 && valid) *reinterpret_cast<uint4*>(mout_row + (c - 3)) = make_uint4(mo[0], mo[1], mo[2], mo[3]);
+                                    }
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                                }
+                                if (min_row) {
+                                    if (u == 0) mi4 = valid ? *reinterpret_cast<const uint4*>(min_row + c) : make_uint4(0u, 0u, 0u, 0u);
+                                    const uint32_t bits = u == 0 ? mi4.x : (u == 1 ? mi4.y : (u == 2 ? mi4.z : mi4.w));
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j) v[j] = ((bits >> j) & 1u) ? v[j] : 0.f;
+                                }
+                                const uint32_t tile_addr = x_addr + (uint32_t)(n0 >> 6) * 16384u + (uint32_t)rloc * 128u;
+                                const int cb = (n0 & 63) >> 3;
+#pragma unroll
+                                for (int q = 0; q < 4; ++q)
+                                    st_shared_v4(tile_addr + (uint32_t)(((cb + q) ^ (rloc & 7)) << 4),
+                                                 pack_bf16(v[q * 8 + 0], v[q * 8 + 1]), pack_bf16(v[q * 8 + 2], v[q * 8 + 3]),
+                                                 pack_bf16(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16(v[q * 8 + 6], v[q * 8 + 7]));
                             }
-                            if (L.act == 1) {
-                                uint32_t bits = 0u;
-#pragma unroll
-                                for (int j = 0; j < 32; ++j) { bits |= (v[j] > 0.f ? 1u : 0u) << j; v[j] = fmaxf(v[j], 0.f); }
-                                mo[c & 3] = bits;
-                                if (mout_row && (c & 3) == 3 && valid) *reinterpret_cast<uint4*>(mout_row + (c - 3)) = make_uint4(mo[0], mo[1], mo[2], mo[3]);
-                            }
-                            if (min_row) {
-                                if ((c & 3) == 0) mi4 = valid ? *reinterpret_cast<const uint4*>(min_row + c) : make_uint4(0u, 0u, 0u, 0u);
-                                const uint32_t bits = (c & 3) == 0 ? mi4.x : ((c & 3) == 1 ? mi4.y : ((c & 3) == 2 ? mi4.z : mi4.w));
-#pragma unroll
-                                for (int j = 0; j < 32; ++j) v[j] = ((bits >> j) & 1u) ? v[j] : 0.f;
-                            }
-                            const uint32_t tile_addr = x_addr + (uint32_t)(n0 >> 6) * 16384u + (uint32_t)rloc * 128u;
-                            const int cb = (n0 & 63) >> 3;
-#pragma unroll
-                            for (int q = 0; q < 4; ++q)
-                                st_shared_v4(tile_addr + (uint32_t)(((cb + q) ^ (rloc & 7)) << 4),
-                                             pack_bf16(v[q * 8 + 0], v[q * 8 + 1]), pack_bf16(v[q * 8 + 2], v[q * 8 + 3]),
-                                             pack_bf16(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16(v[q * 8 + 6], v[q * 8 + 7]));
                         }
                         tcgen05_fence_before();
                         fence_async_smem();
@@ -319,18 +473,23 @@ __global__ void __launch_bounds__(FTHREADS, 1) chain_kernel(const __grid_constan
                         }
                         __syncwarp();
                         if (lane == 0) mbar_arrive(x_full);
+                        if (TIMING) t_gen += clock64() - c_epi;
                     } else {
-                        // ---------------- final layer: this thread's row of eps sits in TMEM columns [0, 32)
-                        uint32_t r[32];
-                        tmem_ld32(tmem_base + lane_base, r);
+                        // ---------------- final layer: eps of this row sits in TMEM columns [0, 32); each half takes 16
+                        uint32_t r[16];
+                        tmem_ld16(tmem_base + lane_base + (uint32_t)(half * 16), r);
                         tcgen05_fence_before();
-                        float eps[32];
+                        // eps / log-prob modes touch neither X nor H0 from here on: hand TMEM back before the math
+                        if (!sampler) { __syncwarp(); if (lane == 0) mbar_arrive(x_full); }
+                        epi_barrier();                                  // sb (bias) visible
+                        const int abase = half * 16;
+                        float eps[16];
 #pragma unroll
-                        for (int a = 0; a < 32; ++a) eps[a] = __uint_as_float(r[a]) + ((L.bias && a < A) ? __ldg(L.bias + a) : 0.f);
+                        for (int j = 0; j < 16; ++j) eps[j] = __uint_as_float(r[j]) + ((L.bias && abase + j < A) ? sb[abase + j] : 0.f);
                         if (p.final_mode == FINAL_EPS) {
                             if (valid) {
 #pragma unroll
-                                for (int a = 0; a < 32; ++a) if (a < A) p.out[(size_t)row * A + a] = eps[a];
+                                for (int j = 0; j < 16; ++j) if (abase + j < A) p.out[(size_t)row * A + abase + j] = eps[j];
                             }
                         } else if (p.final_mode == FINAL_LOGP) {
                             if (valid) {
@@ -339,35 +498,57 @@ __global__ void __launch_bounds__(FTHREADS, 1) chain_kernel(const __grid_constan
                                     const int b = row / p.K, k = row % p.K;
                                     pv = p.chains + ((size_t)b * (p.K + 1) + k) * A; nx = pv + A; t = p.K - 1 - k;
                                 } else { pv = p.prev + (size_t)row * A; nx = p.next + (size_t)row * A; t = p.trow[row]; }
+                                float xv[16], nv[16];
 #pragma unroll
-                                for (int a = 0; a < 32; ++a) if (a < A)
-                                    p.out[(size_t)row * A + a] = logprob_elem(pv[a], eps[a], nx[a], t, p.sch, p.T, p.dcv, p.min_lp_std, nullptr, nullptr, nullptr);
+                                for (int j = 0; j < 16; ++j) { const bool ok = abase + j < A; xv[j] = ok ? __ldg(pv + abase + j) : 0.f; nv[j] = ok ? __ldg(nx + abase + j) : 0.f; }
+                                const StepConst sc = step_const(p.sch, p.T, t);
+                                const float sd = logprob_std(sc, p.min_lp_std);
+                                const float lgs = 0.91893853320467274f + logf(sd);
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) if (abase + j < A)
+                                    p.out[(size_t)row * A + abase + j] = logprob_elem_c(xv[j], eps[j], nv[j], sc, sd, lgs, p.dcv, nullptr, nullptr);
                             }
                         } else {   // FINAL_SAMPLE: posterior mean, clipped noise, x update (diffusion_vpg.py:198-206,239-243,301-338)
+                            const StepConst sc = step_const(p.sch, p.T, t_s);
+                            const float sd = sample_std(sc, t_s, p.hp);
                             if (valid) {
 #pragma unroll
-                                for (int a = 0; a < 32; ++a) if (a < A) {
-                                    const float nz = p.noise ? p.noise[((size_t)step * p.rows + row) * A + a]
-                                                             : philox_normal(p.seed, p.offset, p.row_offset + row, 1 + step, a);
-                                    const float xn = ddpm_step_elem(x[a], eps[a], nz, t_s, p.sch, p.T, p.hp, t_s == 0);
-                                    x[a] = xn;
-                                    if (p.chains_out && t_s <= p.K) p.chains_out[((size_t)row * (p.K + 1) + (p.K - t_s)) * A + a] = xn;
-                                    if (t_s == 0) p.actions[(size_t)row * A + a] = xn;
+                                for (int b4 = 0; b4 < 4; ++b4) {
+                                    const int a0 = abase + b4 * 4;
+                                    if (a0 < A) {
+                                        float nz[4];
+                                        if (p.noise) {
+#pragma unroll
+                                            for (int e = 0; e < 4; ++e) nz[e] = (a0 + e < A) ? __ldg(p.noise + ((size_t)step * p.rows + row) * A + a0 + e) : 0.f;
+                                        } else philox_normal4(p.seed, p.offset, p.row_offset + row, 1 + step, a0 >> 2, nz);
+#pragma unroll
+                                        for (int e = 0; e < 4; ++e) {
+                                            const int a = a0 + e;
+                                            if (a < A) {
+                                                const float xn = ddpm_step_elem_c(x[b4 * 4 + e], eps[b4 * 4 + e], nz[e], sc, sd, p.hp, t_s == 0);
+                                                x[b4 * 4 + e] = xn;
+                                                if (p.chains_out && t_s <= p.K) p.chains_out[((size_t)row * (p.K + 1) + (p.K - t_s)) * A + a] = xn;
+                                                if (t_s == 0) p.actions[(size_t)row * A + a] = xn;
+                                            }
+                                        }
+                                    }
                                 }
                             }
                             if (step + 1 < nsteps) {
-                                build_h0_row(h0_addr, rloc, x, p.obs + (size_t)(valid ? row : 0) * p.Do, A, p.Do, p.T, t_s - 1, valid);
+                                build_h0_half(h0_addr, rloc, half, x, obs_row, A, p.Do, p.T, t_s - 1, valid);
                                 fence_async_smem();
                             }
                         }
                         __syncwarp();
                         // the sampler's last step hands over to the next tile's prologue instead
-                        if (lane == 0 && !(sampler && step + 1 == nsteps)) mbar_arrive(x_full);
+                        if (lane == 0 && sampler && step + 1 < nsteps) mbar_arrive(x_full);
+                        if (TIMING) t_fin += clock64() - c_epi;
                     }
                 }
             }
         }
         if (store_thread) tma_store_wait_all();
+        if (TIMING && p.dbg && warp == 2 && lane == 0) { p.dbg[blockIdx.x * 8 + 4] = t_acc; p.dbg[blockIdx.x * 8 + 5] = t_gen; p.dbg[blockIdx.x * 8 + 6] = t_fin; }
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -385,9 +566,13 @@ static int rowtile_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t
 
 template <int H>
 static int launch_chain_t(dppo_handle* h, cudaStream_t s, const Maps& maps, const Params& p, double flops) {
-    auto kern = chain_kernel<H>;
+    auto kern = p.dbg ? chain_kernel<H, true> : chain_kernel<H, false>;
     static bool attr_set = false;
-    if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_smem_bytes<H>())); attr_set = true; }
+    if (!attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(chain_kernel<H, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_smem_bytes<H>()));
+        CUDA_TRY(cudaFuncSetAttribute(chain_kernel<H, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_smem_bytes<H>()));
+        attr_set = true;
+    }
     const int ntiles = (p.rows + FBM - 1) / FBM;
     const int grid = ntiles < h->sm_count ? ntiles : h->sm_count;
     prof_begin(h, s);
@@ -404,4 +589,100 @@ static int launch_chain(dppo_handle* h, cudaStream_t s, int H, const Maps& maps,
     DPPO_FAIL(-7, "fused chain: unsupported hidden width %d", H);
 }
 
+}  // namespace fc
+
+// ------------------------------------------------------------------ dev probe (tools/mma_probe.py)
+// mode 0: the chain kernel's MMA issue sequence (poll a ready mbarrier, 2 x tcgen05.mma 128 x N x 16, commit) on
+//         fixed operands: cycles per 2-MMA stage, i.e. the issue cost with no data dependence at all.
+// mode 1: TMA round trip: one 16 KB weight stage (4 boxes from 4 lanes) at a time, issue -> mbarrier completion.
+// mode 2: TMA throughput with `depth` stages in flight (depth <= 4), same lean producer loop as the chain kernel.
+namespace fc {
+__global__ void __launch_bounds__(128, 1) mma_probe_kernel(const __grid_constant__ CUtensorMap wmap, int mode, int iters, int N, int depth,
+                                                           long long* out) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = smem;                 // 16 KB
+    uint8_t* sB = smem + 16384;         // 4 x 16 KB
+    uint64_t* bars = (uint64_t*)(sB + 4 * 16384);
+    uint64_t* done = bars; uint64_t* sink = bars + 1; uint64_t* tfull = bars + 2; uint64_t* ready = bars + 6;
+    uint32_t* tmem_slot = (uint32_t*)(bars + 12);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < (16384 * 5) / 4; i += blockDim.x) ((uint32_t*)smem)[i] = 0x3c003c00u;
+    if (threadIdx.x == 0) {
+        mbar_init(done, 1); mbar_init(sink, 1); mbar_init(ready, 1);
+        for (int i = 0; i < 4; ++i) mbar_init(&tfull[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_async_smem();
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (mode == 0 && warp == 1 && lane == 0) {
+        const uint32_t idesc = make_idesc(128, N, false, true);
+        const uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+        const uint32_t a_lo0 = ((smem_u32(sA) >> 4) & 0x3FFFu) | (1u << 16);
+        const uint32_t b_lo_0 = ((smem_u32(sB) >> 4) & 0x3FFFu) | ((uint32_t)(WK * 128 >> 4) << 16);
+        const uint32_t ready_addr = smem_u32(ready), sink_addr = smem_u32(sink);
+        int stage = 0; uint32_t phase = 0; uint32_t a_lo = a_lo0;
+        const long long t0 = clock64();
+        // depth bits: 1 = commit per stage, 2 = poll a ready mbarrier per stage, 4 = tcgen05.fence::after per stage, 8 = 4 MMAs per stage
+        const int nm = (depth & 8) ? 4 : 2;
+        const uint32_t d1 = (depth & 16) ? tmem_base + 256u : tmem_base;     // bit 16: alternate between two accumulators
+        for (int s = 0; s < iters; ++s) {
+            if (depth & 2) mbar_wait_addr(ready_addr, 1);           // never arrived on: the parity-1 wait succeeds at once
+            if (depth & 4) tcgen05_fence_after();
+            const uint32_t b_lo = b_lo_0 + (uint32_t)stage * (STAGE_BYTES >> 4);
+            umma_bf16_split(tmem_base, a_lo, b_lo, desc_hi, idesc, 1u);
+            umma_bf16_split(d1, a_lo + 2u, b_lo + (2048u >> 4), desc_hi, idesc, 1u);
+            if (nm == 4) {
+                umma_bf16_split(tmem_base, a_lo, b_lo, desc_hi, idesc, 1u);
+                umma_bf16_split(d1, a_lo + 2u, b_lo + (2048u >> 4), desc_hi, idesc, 1u);
+            }
+            if (depth & 1) tcgen05_commit_addr(sink_addr);
+            a_lo = (s & 1) ? a_lo0 : a_lo + 4u;
+            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+        }
+        const long long t1 = clock64();
+        tcgen05_commit(done);
+        mbar_wait(done, 0);
+        const long long t2 = clock64();
+        out[blockIdx.x * 2] = t1 - t0; out[blockIdx.x * 2 + 1] = t2 - t0;
+    }
+    if (mode >= 1 && warp == 0 && lane < 4) {
+        const uint32_t w_addr = smem_u32(sB) + (uint32_t)lane * (WK * 128);
+        const uint32_t tfull_addr = smem_u32(tfull);
+        uint32_t ph[4] = {0, 0, 0, 0};
+        const int D = mode == 1 ? 1 : depth;
+        const long long t0 = clock64();
+        int krow = (blockIdx.x * 32) % 512;
+        for (int i = 0; i < D; ++i) {
+            if (lane == 0) mbar_expect_tx_addr(tfull_addr + i * 8, 16384);
+            __syncwarp(0xf);
+            tma_load_2d_addr(w_addr + i * STAGE_BYTES, &wmap, tfull_addr + i * 8, lane * 64, krow);
+            krow = (krow + 32) & 511;
+        }
+        int i = 0;
+        for (int it = 0; it < iters; ++it) {
+            mbar_wait_addr(tfull_addr + i * 8, ph[i & 3]); ph[i & 3] ^= 1;
+            if (lane == 0) mbar_expect_tx_addr(tfull_addr + i * 8, 16384);
+            __syncwarp(0xf);
+            tma_load_2d_addr(w_addr + i * STAGE_BYTES, &wmap, tfull_addr + i * 8, lane * 64 + ((it >> 4) & 1) * 256, krow);
+            krow = (krow + 32) & 511;
+            if (++i == D) i = 0;
+        }
+        for (int k = 0; k < D; ++k) mbar_wait_addr(tfull_addr + k * 8, ph[k]);
+        if (lane == 0) { out[blockIdx.x * 2] = clock64() - t0; out[blockIdx.x * 2 + 1] = iters + D; }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
 }  // namespace fc

@@ -301,18 +301,33 @@ __global__ void make_trow_kernel(const int* __restrict__ inds, int N, int K, int
 struct SampleHyper {
     float dcv, rcv, facv, min_std; int deterministic;
 };
-__device__ __forceinline__ float ddpm_step_elem(float x, float eps, float noise, int t, const float* __restrict__ sch, int T,
-                                                const SampleHyper hp, bool last) {
-    float xr = sch[SCH_SQRT_RECIP * T + t] * x - sch[SCH_SQRT_RECIPM1 * T + t] * eps;
+// per-denoising-step constants (one gather per step instead of one per element)
+struct StepConst { float sr, srm1, c1, c2, sd; };
+__device__ __forceinline__ StepConst step_const(const float* __restrict__ sch, int T, int t) {
+    StepConst c;
+    c.sr = sch[SCH_SQRT_RECIP * T + t]; c.srm1 = sch[SCH_SQRT_RECIPM1 * T + t];
+    c.c1 = sch[SCH_COEF1 * T + t]; c.c2 = sch[SCH_COEF2 * T + t];
+    c.sd = expf(0.5f * sch[SCH_LOGVAR * T + t]);
+    return c;
+}
+// sampling std of step t (diffusion_vpg.py:301-315)
+__device__ __forceinline__ float sample_std(const StepConst& c, int t, const SampleHyper& hp) {
+    if (hp.deterministic) return (t == 0) ? 0.f : fminf(fmaxf(c.sd, 1e-3f), 1e6f);
+    return fminf(fmaxf(c.sd, hp.min_std), 1e6f);
+}
+__device__ __forceinline__ float ddpm_step_elem_c(float x, float eps, float noise, const StepConst& c, float sd, const SampleHyper& hp, bool last) {
+    float xr = c.sr * x - c.srm1 * eps;
     if (hp.dcv >= 0.f) xr = fminf(fmaxf(xr, -hp.dcv), hp.dcv);
-    float mu = sch[SCH_COEF1 * T + t] * xr + sch[SCH_COEF2 * T + t] * x;
-    float sd = expf(0.5f * sch[SCH_LOGVAR * T + t]);
-    if (hp.deterministic) sd = (t == 0) ? 0.f : fminf(fmaxf(sd, 1e-3f), 1e6f);
-    else sd = fminf(fmaxf(sd, hp.min_std), 1e6f);
+    float mu = c.c1 * xr + c.c2 * x;
     float nz = fminf(fmaxf(noise, -hp.rcv), hp.rcv);
     float xn = mu + sd * nz;
     if (last && hp.facv >= 0.f) xn = fminf(fmaxf(xn, -hp.facv), hp.facv);
     return xn;
+}
+__device__ __forceinline__ float ddpm_step_elem(float x, float eps, float noise, int t, const float* __restrict__ sch, int T,
+                                                const SampleHyper hp, bool last) {
+    const StepConst c = step_const(sch, T, t);
+    return ddpm_step_elem_c(x, eps, noise, c, sample_std(c, t, hp), hp, last);
 }
 __global__ void sample_init_kernel(float* __restrict__ x, const float* __restrict__ xT, int B, int A,
                                    uint64_t seed, uint64_t offset, int64_t row_offset,
@@ -341,16 +356,24 @@ __global__ void sample_update_kernel(float* __restrict__ x, const float* __restr
 // =====================================================================================
 // Log-prob epilogue (diffusion_vpg.py:417-422, tfp Normal.log_prob)
 // =====================================================================================
-__device__ __forceinline__ float logprob_elem(float x, float eps, float nxt, int t, const float* __restrict__ sch, int T,
-                                              float dcv, float min_lp_std, float* z_out, float* sd_out, bool* inclip) {
-    float xr = sch[SCH_SQRT_RECIP * T + t] * x - sch[SCH_SQRT_RECIPM1 * T + t] * eps;
+// Gaussian log-prob of one element given the step constants; sd already clipped, lgs = 0.5 log(2 pi) + log(sd)
+__device__ __forceinline__ float logprob_elem_c(float x, float eps, float nxt, const StepConst& c, float sd, float lgs, float dcv,
+                                                float* z_out, bool* inclip) {
+    float xr = c.sr * x - c.srm1 * eps;
     bool in = true;
     if (dcv >= 0.f) { in = (xr >= -dcv && xr <= dcv); xr = fminf(fmaxf(xr, -dcv), dcv); }
-    float mu = sch[SCH_COEF1 * T + t] * xr + sch[SCH_COEF2 * T + t] * x;
-    float sd = fminf(fmaxf(expf(0.5f * sch[SCH_LOGVAR * T + t]), min_lp_std), 1e6f);
+    float mu = c.c1 * xr + c.c2 * x;
     float z = nxt / sd - mu / sd;
-    if (z_out) { *z_out = z; *sd_out = sd; *inclip = in; }
-    return -0.5f * z * z - (0.91893853320467274f + logf(sd));
+    if (z_out) { *z_out = z; *inclip = in; }
+    return -0.5f * z * z - lgs;
+}
+__device__ __forceinline__ float logprob_std(const StepConst& c, float min_lp_std) { return fminf(fmaxf(c.sd, min_lp_std), 1e6f); }
+__device__ __forceinline__ float logprob_elem(float x, float eps, float nxt, int t, const float* __restrict__ sch, int T,
+                                              float dcv, float min_lp_std, float* z_out, float* sd_out, bool* inclip) {
+    const StepConst c = step_const(sch, T, t);
+    const float sd = logprob_std(c, min_lp_std);
+    if (sd_out) *sd_out = sd;
+    return logprob_elem_c(x, eps, nxt, c, sd, 0.91893853320467274f + logf(sd), dcv, z_out, inclip);
 }
 // prev/next either separate [N][A] arrays or derived from chains[B][K+1][A] with row = b*K+k
 __global__ void logprob_kernel(const float* __restrict__ prev, const float* __restrict__ nxt, const float* __restrict__ chains,

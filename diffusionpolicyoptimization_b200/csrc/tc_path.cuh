@@ -225,6 +225,7 @@ static void fc_common(const dppo_handle* h, fc::Params& p, int N) {
     memset(&p, 0, sizeof(p));
     p.rows = N; p.A = g.A; p.Do = g.Do; p.T = g.T; p.K = g.K; p.sch = h->sched;
     p.dcv = h->cfg.denoised_clip_value; p.min_lp_std = h->cfg.min_logprob_denoising_std;
+    p.dbg = h->chain_dbg;
 }
 // inference forward from a packed h0: final = eps store or Gaussian log-prob
 static int fc_actor_infer(dppo_handle* h, cudaStream_t s, int net, const bf16* h0, int N, int mode, float* out,

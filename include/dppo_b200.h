@@ -203,6 +203,12 @@ int dppo_force_path(dppo_handle* h, int path);
 int dppo_debug_tc_gemm(dppo_handle* h, const void* A, int a_mn, int64_t lda, const void* A2, int64_t lda2, int K2,
                        const void* B, int b_mn, int64_t ldb, int M, int N, int K, int splits,
                        const float* bias, int act, float* out_f32, void* out_bf16, dppo_stream_t s);
+/* Dev tool: per-CTA cycle counters of the fused chain kernel.  enable != 0 allocates them; out_host (optional)
+ * receives HOST [sm_count][8] = {producer wait w_empty, mma wait x_full, mma wait w_full, mma total,
+ * epilogue wait acc_full, epilogue generic layers, epilogue final layer, 0} of the last launch. */
+int dppo_debug_chain_timing(dppo_handle* h, int enable, long long* out_host, int* sm_count);
+/* Dev probe: tcgen05.mma issue cost, TMA round trip and TMA throughput per SM; see tools/mma_probe.py. */
+int dppo_debug_mma_probe(dppo_handle* h, int grid, int mode, int iters, int N, int depth, long long* out_host);
 int dppo_profile_enable(dppo_handle* h, int on);
 int dppo_profile_read(dppo_handle* h, double* gemm_ms, int64_t* gemm_launches, double* gemm_flops);
 
