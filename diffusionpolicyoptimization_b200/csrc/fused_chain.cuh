@@ -30,7 +30,7 @@
 namespace fc {
 using namespace tc;
 
-constexpr int FBM = 128, WK = 32, NSTAGE = 4, FTHREADS = 320, MAXL = 4, NMAPS = 8;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
+constexpr int FBM = 128, WK = 32, NSTAGE = 4, FTHREADS = 320, MAXL = 4, NMAPS = 10;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
 constexpr int STAGE_BYTES = WK * 256 * 2;      // 16 KB
 constexpr int H0_BYTES = FBM * 64 * 2;         // 16 KB
 
@@ -43,10 +43,13 @@ struct Layer {
     int n;                     // output width: H, or 64 for the output layer
     int h0_last;               // this layer is the tile's last reader of H0 (TMA mode): release it afterwards
     const float* bias;         // [n] fp32 or null
-    int act;                   // 0 none, 1 ReLU
+    int act;                   // 0 none, 1 ReLU, 2 Mish
     const uint32_t* mask_in;   // [rows][H/32] ReLU bit masks to multiply with, or null
     uint32_t* mask_out;        // [rows][H/32] ReLU bit masks to record, or null
     int store_map;             // tensor map for the TMA store of X ([rows][H] bf16, box [128][64]), or -1
+    // Mish networks (H = 256 only: a second [128][H] buffer G lives next to X)
+    int gate_store_map;        // act == 2: also store G = mish'(pre-activation) ([rows][H] bf16) for the backward pass, or -1
+    int gate_load_map;         // backward: multiply by the gate tile TMA-loaded from this map into G, or -1
 };
 
 struct Params {
@@ -79,11 +82,24 @@ __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 256;" 
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+__device__ __forceinline__ void ld_shared_v4(uint32_t addr, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr) : "memory");
+}
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&t);
 }
 
+// Mish and its derivative from one exponential: with n = e^x, w = n^2 + 2n:  tanh(softplus(x)) = w / (w + 2),
+// d/dx = 4 n (n + 1) / (w + 2)^2.  (tensor path only; the fp32 parity path keeps the literal x * tanh(softplus(x)))
+__device__ __forceinline__ void mish_and_grad(float x, float& y, float& g) {
+    const float n = __expf(fminf(x, 20.f));
+    const float w = n * (n + 2.f);
+    const float r = __fdividef(1.f, w + 2.f);
+    const float f = w * r;
+    y = x > 20.f ? x : x * f;
+    g = x > 20.f ? 1.f : f + x * (4.f * n * (n + 1.f)) * r * r;
+}
 // One lane of a converged warp (elect.sync).  The issue warps keep warp-uniform control flow and elect a lane only
 // around the tcgen05 / TMA instructions: inside a lane-divergent branch (`if (lane == 0)`) nvcc wraps every
 // uniform-datapath instruction (UTCHMMA, UTCBAR, UTMALDG) in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall loop,
@@ -125,7 +141,7 @@ __device__ __forceinline__ void umma_bf16_split(uint32_t tmem_d, uint32_t a_lo, 
 }
 
 template <int H> constexpr size_t chain_smem_bytes() {
-    return (size_t)(H / 64) * 16384 + H0_BYTES + (size_t)NSTAGE * STAGE_BYTES + 2 * 512 * sizeof(float) + 1024 + 256;
+    return (size_t)(H / 64) * 16384 * (H == 256 ? 2 : 1) + H0_BYTES + (size_t)NSTAGE * STAGE_BYTES + 2 * 512 * sizeof(float) + 1024 + 256;
 }
 
 // asynchronous TMEM load of 32 columns (no wait) and the matching wait, tied to the destination registers so
@@ -199,7 +215,9 @@ __global__ void __launch_bounds__(FTHREADS, 1) chain_kernel(const __grid_constan
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* sX = smem;
-    uint8_t* sH0 = sX + X_BYTES;
+    constexpr bool HASG = (H == 256);                           // room for the gate buffer next to X
+    uint8_t* sG = sX + X_BYTES;
+    uint8_t* sH0 = sG + (HASG ? X_BYTES : 0);
     uint8_t* sW = sH0 + H0_BYTES;
     float* sBias = (float*)(sW + NSTAGE * STAGE_BYTES);           // 2 x 512 fp32, double buffered across layers
     uint64_t* bars = (uint64_t*)(sBias + 2 * 512);
@@ -209,7 +227,9 @@ __global__ void __launch_bounds__(FTHREADS, 1) chain_kernel(const __grid_constan
     uint64_t* h0_empty = h0_full + 1;
     uint64_t* acc_full = h0_full + 2;
     uint64_t* x_full = h0_full + 3;
-    uint32_t* tmem_slot = (uint32_t*)(h0_full + 4);
+    uint64_t* g_full = h0_full + 4;      // TMA -> epilogue: gate tile landed in G
+    uint64_t* g_empty = h0_full + 5;     // epilogue -> TMA: G may be overwritten
+    uint32_t* tmem_slot = (uint32_t*)(h0_full + 6);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ntiles = (p.rows + FBM - 1) / FBM;
@@ -220,6 +240,7 @@ __global__ void __launch_bounds__(FTHREADS, 1) chain_kernel(const __grid_constan
         for (int i = 0; i < NMAPS; ++i) tma_prefetch_desc(&maps.m[i]);
         for (int i = 0; i < NSTAGE; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
         mbar_init(h0_full, 1); mbar_init(h0_empty, 1); mbar_init(acc_full, 1); mbar_init(x_full, 8);
+        mbar_init(g_full, 1); mbar_init(g_empty, 8);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -235,7 +256,7 @@ __global__ void __launch_bounds__(FTHREADS, 1) chain_kernel(const __grid_constan
         // ===================================================== TMA producer
         // Warp-uniform control flow; one elected lane issues the TMA instructions of a stage.
         {
-            int stage = 0; uint32_t phase = 0, h0_phase = 0;
+            int stage = 0; uint32_t phase = 0, h0_phase = 0, g_phase = 0;
             long long t_wempty = 0;
             const uint32_t w_addr = smem_u32(sW);
             const uint32_t wfull_addr = smem_u32(w_full), wempty_addr = smem_u32(w_empty);
@@ -258,6 +279,15 @@ __global__ void __launch_bounds__(FTHREADS, 1) chain_kernel(const __grid_constan
                         const CUtensorMap* wm = &maps.m[L.wmap];
                         const uint32_t tx = (uint32_t)(WK * n_cur * 2);
                         const int nbox = n_cur / 64;
+                        if (HASG && L.gate_load_map >= 0) {
+                            // gate tile of this layer: needed by its epilogue only, so it rides ahead of the weights
+                            mbar_wait(g_empty, g_phase ^ 1); g_phase ^= 1;
+                            if (elect_one()) {
+                                mbar_expect_tx(g_full, X_BYTES);
+                                for (int kb = 0; kb < XT; ++kb) tma_load_2d(sG + kb * 16384, &maps.m[L.gate_load_map], g_full, kb * 64, tile * FBM);
+                            }
+                            __syncwarp();
+                        }
                         for (int nh = 0; nh < nhc; ++nh) {
                             const int col = nh * n_cur;
                             int krow = kx ? L.wrow_x : L.wrow_h0;
@@ -352,8 +382,9 @@ __global__ void __launch_bounds__(FTHREADS, 1) chain_kernel(const __grid_constan
         const int half = (warp - 2) >> 2;                        // 0: first half of the columns, 1: second half
         const int rloc = quad * 32 + lane;                       // row inside the tile == TMEM lane
         const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
-        const uint32_t x_addr = smem_u32(sX), h0_addr = smem_u32(sH0);
+        const uint32_t x_addr = smem_u32(sX), h0_addr = smem_u32(sH0), g_addr = smem_u32(sG);
         const bool store_thread = (warp == 2 && lane == 0);
+        uint32_t gfull_phase = 0;
         const int etid = threadIdx.x - 64;                       // 0..255
         uint32_t acc_phase = 0;
         int bias_buf = 0;
@@ -416,6 +447,9 @@ __global__ void __launch_bounds__(FTHREADS, 1) chain_kernel(const __grid_constan
                         uint32_t* mout_row = L.mask_out ? L.mask_out + (size_t)row * (H / 32) : nullptr;
                         uint32_t mo[4] = {0u, 0u, 0u, 0u};
                         uint4 mi4 = make_uint4(0u, 0u, 0u, 0u);
+                        const bool gate_in = HASG && L.gate_load_map >= 0;
+                        const bool mish = HASG && L.act == 2;
+                        if (gate_in) { mbar_wait(g_full, gfull_phase); gfull_phase ^= 1; }
                         uint32_t ra[32], rb[32];
                         tmem_ld32_async(tmem_base + lane_base + (uint32_t)(c_first * 32), ra);
 #pragma unroll 1
@@ -449,6 +483,34 @@ __global__ void __launch_bounds__(FTHREADS, 1) chain_kernel(const __grid_constan
 #pragma unroll
                                     for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
                                 }
+                                const uint32_t toff = (uint32_t)(n0 >> 6) * 16384u + (uint32_t)rloc * 128u;
+                                const int cbg = (n0 & 63) >> 3;
+                                if (mish) {
+                                    // post-activation -> X (below), gate = mish'(pre) -> G
+                                    float gt[32];
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j) { float y; mish_and_grad(v[j], y, gt[j]); v[j] = y; }
+                                    if (L.gate_store_map >= 0) {
+#pragma unroll
+                                        for (int q = 0; q < 4; ++q)
+                                            st_shared_v4(g_addr + toff + (uint32_t)(((cbg + q) ^ (rloc & 7)) << 4),
+                                                         pack_bf16(gt[q * 8 + 0], gt[q * 8 + 1]), pack_bf16(gt[q * 8 + 2], gt[q * 8 + 3]),
+                                                         pack_bf16(gt[q * 8 + 4], gt[q * 8 + 5]), pack_bf16(gt[q * 8 + 6], gt[q * 8 + 7]));
+                                    }
+                                }
+                                if (gate_in) {
+#pragma unroll
+                                    for (int q = 0; q < 4; ++q) {
+                                        uint32_t g0, g1, g2, g3;
+                                        ld_shared_v4(g_addr + toff + (uint32_t)(((cbg + q) ^ (rloc & 7)) << 4), g0, g1, g2, g3);
+                                        const uint32_t gw[4] = {g0, g1, g2, g3};
+#pragma unroll
+                                        for (int e = 0; e < 4; ++e) {
+                                            const float2 gf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gw[e]));
+                                            v[q * 8 + e * 2] *= gf.x; v[q * 8 + e * 2 + 1] *= gf.y;
+                                        }
+                                    }
+                                }
                                 if (min_row) {
                                     if (u == 0) mi4 = valid ? *reinterpret_cast<const uint4*>(min_row + c) : make_uint4(0u, 0u, 0u, 0u);
                                     const uint32_t bits = u == 0 ? mi4.x : (u == 1 ? mi4.y : (u == 2 ? mi4.z : mi4.w));
@@ -466,9 +528,13 @@ __global__ void __launch_bounds__(FTHREADS, 1) chain_kernel(const __grid_constan
                         }
                         tcgen05_fence_before();
                         fence_async_smem();
+                        if (gate_in) { __syncwarp(); if (lane == 0) mbar_arrive(g_empty); }
                         epi_barrier();
-                        if (L.store_map >= 0 && store_thread) {
-                            for (int kb = 0; kb < L.n / 64; ++kb) tma_store_2d(&maps.m[L.store_map], sX + kb * 16384, kb * 64, tile * FBM);
+                        if (store_thread && (L.store_map >= 0 || (mish && L.gate_store_map >= 0))) {
+                            if (L.store_map >= 0)
+                                for (int kb = 0; kb < L.n / 64; ++kb) tma_store_2d(&maps.m[L.store_map], sX + kb * 16384, kb * 64, tile * FBM);
+                            if (mish && L.gate_store_map >= 0)
+                                for (int kb = 0; kb < L.n / 64; ++kb) tma_store_2d(&maps.m[L.gate_store_map], sG + kb * 16384, kb * 64, tile * FBM);
                             tma_store_commit();
                         }
                         __syncwarp();

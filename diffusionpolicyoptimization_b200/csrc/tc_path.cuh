@@ -64,9 +64,13 @@ __global__ void tc_pack_actor_kernel(const float* __restrict__ w, ActorOff o, in
 }
 __global__ void tc_pack_critic_kernel(const float* __restrict__ w, CriticOff o, int A, int Do, int Hc, int KP0,
                                       bf16* __restrict__ w2w0, bf16* __restrict__ w1, bf16* __restrict__ w3t,
-                                      bf16* __restrict__ w3p, float* __restrict__ bias2) {
+                                      bf16* __restrict__ w3p, float* __restrict__ bias2, bf16* __restrict__ w1t, bf16* __restrict__ w2t) {
     const size_t stride = (size_t)gridDim.x * blockDim.x, i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (size_t i = i0; i < (size_t)Hc * Hc; i += stride) { w2w0[i] = __float2bfloat16(w[o.w2 + i]); w1[i] = __float2bfloat16(w[o.w1 + i]); }
+    for (size_t i = i0; i < (size_t)Hc * Hc; i += stride) {
+        w2w0[i] = __float2bfloat16(w[o.w2 + i]); w1[i] = __float2bfloat16(w[o.w1 + i]);
+        const size_t r = i / Hc, c = i % Hc;
+        w1t[i] = __float2bfloat16(w[o.w1 + c * Hc + r]); w2t[i] = __float2bfloat16(w[o.w2 + c * Hc + r]);
+    }
     for (size_t i = i0; i < (size_t)KP0 * Hc; i += stride) {
         int k = (int)(i / Hc), c = (int)(i % Hc);
         float v = (k >= A && k < A + Do) ? w[o.win + (size_t)(k - A) * Hc + c] : 0.f;
@@ -183,7 +187,7 @@ static int tc_refresh_net(dppo_handle* h, int net, cudaStream_t s) {
     if (h->cfg.precision != DPPO_PREC_BF16 || !tc_shapes_ok(h)) return 0;
     const Geom& g = h->g; TcNetW& w = h->tc->net[net];
     if (net == DPPO_NET_CRITIC)
-        tc_pack_critic_kernel<<<128, 256, 0, s>>>(h->net_w[net], g.co, g.A, g.Do, g.Hc, h->tc->KP0, w.w2w0, w.w1, w.w3t, w.w3p, w.bias2);
+        tc_pack_critic_kernel<<<128, 256, 0, s>>>(h->net_w[net], g.co, g.A, g.Do, g.Hc, h->tc->KP0, w.w2w0, w.w1, w.w3t, w.w3p, w.bias2, w.w1t, w.w2t);
     else
         tc_pack_actor_kernel<<<256, 256, 0, s>>>(h->net_w[net], g.ao, g.A, g.td, g.Do, g.T, g.H, h->tc->KP0, h->ad[net].bt, w.w2w0, w.w1, w.w3t, w.w3p, w.w1t, w.w2t);
     h->launches++;
@@ -197,101 +201,138 @@ static int tc_refresh_net(dppo_handle* h, int net, cudaStream_t s) {
 static inline int tc_nblk(size_t n, int b) { return (int)((n + b - 1) / b); }
 
 // ------------------------------------------------------------------ fused layer-chain programs (fused_chain.cuh)
-static bool fc_ok(const dppo_handle* h) {
-    const Geom& g = h->g;
-    return tc_shapes_ok(h) && h->tc->KP0 == 64 && h->cfg.actor_act == DPPO_ACT_RELU && (g.H == 512 || g.H == 256) && g.A <= 32
-        && h->force_path != 3;
+// one residual MLP as the fused kernel sees it
+struct FcNet { int net, H, act1 /*1 ReLU, 2 Mish*/, NO; const float *b0, *b1, *b2, *b3; };
+static FcNet fc_actor_net(const dppo_handle* h, int net) {
+    const Geom& g = h->g; const float* w = h->net_w[net];
+    FcNet n; n.net = net; n.H = g.H; n.act1 = h->cfg.actor_act + 1; n.NO = g.A;
+    n.b0 = nullptr; n.b1 = w + g.ao.b1; n.b2 = w + g.ao.b2; n.b3 = w + g.ao.b3;    // b_in rides in W0's one-hot rows (bt table)
+    return n;
 }
-static int fc_weight_maps(const dppo_handle* h, int net, CUtensorMap* m) {
-    const TcNetW& W = h->tc->net[net]; const int H = h->g.H;
+static FcNet fc_critic_net(const dppo_handle* h) {
+    const Geom& g = h->g; const float* w = h->net_w[DPPO_NET_CRITIC];
+    FcNet n; n.net = DPPO_NET_CRITIC; n.H = g.Hc; n.act1 = h->cfg.critic_act + 1; n.NO = 1;
+    n.b0 = w + g.co.bin; n.b1 = w + g.co.b1; n.b2 = h->tc->net[DPPO_NET_CRITIC].bias2; n.b3 = w + g.co.b3;
+    return n;
+}
+// shapes the fused kernel covers: ReLU at H = 256 / 512, Mish at H = 256 (the gate buffer needs the shared memory)
+static bool fc_net_ok(const dppo_handle* h, const FcNet& n) {
+    if (!tc_shapes_ok(h) || h->tc->KP0 != 64 || h->force_path == 3 || n.NO > 32) return false;
+    if (n.act1 == 1) return n.H == 512 || n.H == 256;
+    if (n.act1 == 2) return n.H == 256;
+    return false;
+}
+static bool fc_ok(const dppo_handle* h) { return fc_net_ok(h, fc_actor_net(h, DPPO_NET_ACTOR)); }
+static bool fc_critic_ok(const dppo_handle* h) { return fc_net_ok(h, fc_critic_net(h)); }
+
+static int fc_weight_maps(const dppo_handle* h, const FcNet& n, CUtensorMap* m) {
+    const TcNetW& W = h->tc->net[n.net]; const int H = n.H;
     DPPO_TRY(fc::weight_map(&m[0], W.w2w0, H + 64, H));
     DPPO_TRY(fc::weight_map(&m[1], W.w1, H, H));
     DPPO_TRY(fc::weight_map(&m[2], W.w3p, H, 64));
     return 0;
 }
-// forward program: L0 relu(H0 W0), L1 relu(X W1 + b1), L2 X W2 + H0 W0 + b2, L3 X W3 + b3; weight maps at m[wbase..wbase+2]
-static void fc_fwd_layers(const dppo_handle* h, int net, int wbase, fc::Layer* L) {
-    const Geom& g = h->g; const float* w = h->net_w[net]; const int H = g.H;
+// forward program: L0 act(H0 W0 + b0), L1 act(X W1 + b1), L2 X W2 + H0 W0 + b2, L3 X W3 + b3; weight maps at m[wbase..wbase+2]
+static void fc_fwd_layers(const FcNet& n, int wbase, fc::Layer* L) {
+    const int H = n.H;
     memset(L, 0, sizeof(fc::Layer) * fc::MAXL);
-    for (int i = 0; i < fc::MAXL; ++i) L[i].store_map = -1;
-    L[0].a_src = 0; L[0].wmap = wbase; L[0].wrow_h0 = H; L[0].n = H; L[0].act = 1;
-    L[1].a_src = 1; L[1].wmap = wbase + 1; L[1].n = H; L[1].bias = w + g.ao.b1; L[1].act = 1;
-    L[2].a_src = 2; L[2].wmap = wbase; L[2].wrow_h0 = H; L[2].n = H; L[2].bias = w + g.ao.b2; L[2].h0_last = 1;
-    L[3].a_src = 1; L[3].wmap = wbase + 2; L[3].n = 64; L[3].bias = w + g.ao.b3;
+    for (int i = 0; i < fc::MAXL; ++i) { L[i].store_map = -1; L[i].gate_store_map = -1; L[i].gate_load_map = -1; }
+    L[0].a_src = 0; L[0].wmap = wbase; L[0].wrow_h0 = H; L[0].n = H; L[0].bias = n.b0; L[0].act = n.act1;
+    L[1].a_src = 1; L[1].wmap = wbase + 1; L[1].n = H; L[1].bias = n.b1; L[1].act = n.act1;
+    L[2].a_src = 2; L[2].wmap = wbase; L[2].wrow_h0 = H; L[2].n = H; L[2].bias = n.b2; L[2].h0_last = 1;
+    L[3].a_src = 1; L[3].wmap = wbase + 2; L[3].n = 64; L[3].bias = n.b3;
 }
-static double fc_fwd_flops(const dppo_handle* h, double rows) { const double H = h->g.H; return 2.0 * rows * (64 * H + H * H + (H + 64) * H + H * 64); }
-static void fc_common(const dppo_handle* h, fc::Params& p, int N) {
+static double fc_fwd_flops(double H, double rows) { return 2.0 * rows * (64 * H + H * H + (H + 64) * H + H * 64); }
+static void fc_common(const dppo_handle* h, fc::Params& p, int N, int NO) {
     const Geom& g = h->g;
     memset(&p, 0, sizeof(p));
-    p.rows = N; p.A = g.A; p.Do = g.Do; p.T = g.T; p.K = g.K; p.sch = h->sched;
+    p.rows = N; p.A = NO; p.Do = g.Do; p.T = g.T; p.K = g.K; p.sch = h->sched;
     p.dcv = h->cfg.denoised_clip_value; p.min_lp_std = h->cfg.min_logprob_denoising_std;
     p.dbg = h->chain_dbg;
 }
-// inference forward from a packed h0: final = eps store or Gaussian log-prob
-static int fc_actor_infer(dppo_handle* h, cudaStream_t s, int net, const bf16* h0, int N, int mode, float* out,
-                          const float* prev, const float* next, const float* chains, const int* trow) {
-    fc::Maps maps; fc::Params p; fc_common(h, p, N);
+// inference forward from a packed h0: final = output store (eps / value) or Gaussian log-prob
+static int fc_infer(dppo_handle* h, cudaStream_t s, const FcNet& n, const bf16* h0, int N, int mode, float* out,
+                    const float* prev, const float* next, const float* chains, const int* trow) {
+    fc::Maps maps; fc::Params p; fc_common(h, p, N, n.NO);
     DPPO_TRY(fc::rowtile_map(&maps.m[0], h0, N, 64));
-    DPPO_TRY(fc_weight_maps(h, net, &maps.m[1]));
+    DPPO_TRY(fc_weight_maps(h, n, &maps.m[1]));
     for (int i = 4; i < fc::NMAPS; ++i) maps.m[i] = maps.m[0];
     p.nlayers = 4; p.final_mode = mode; p.h0_from_tma = 1;
-    fc_fwd_layers(h, net, 1, p.L[0]);
+    fc_fwd_layers(n, 1, p.L[0]);
     p.out = out; p.prev = prev; p.next = next; p.chains = chains; p.trow = trow;
-    return fc::launch_chain(h, s, h->g.H, maps, p, fc_fwd_flops(h, N));
+    return fc::launch_chain(h, s, n.H, maps, p, fc_fwd_flops(n.H, N));
 }
-// training forward: eps + the tensors the backward needs (a0, a1, v in HBM via TMA store, ReLU bit masks)
-static int fc_actor_train_fwd(dppo_handle* h, cudaStream_t s, int net, const bf16* h0, int N, bf16* a0, bf16* a1, bf16* v,
-                              uint32_t* m0, uint32_t* m1, float* eps) {
-    const int H = h->g.H;
-    fc::Maps maps; fc::Params p; fc_common(h, p, N);
+static int fc_actor_infer(dppo_handle* h, cudaStream_t s, int net, const bf16* h0, int N, int mode, float* out,
+                          const float* prev, const float* next, const float* chains, const int* trow) {
+    return fc_infer(h, s, fc_actor_net(h, net), h0, N, mode, out, prev, next, chains, trow);
+}
+// training forward: output + the tensors the backward needs in HBM via TMA store: a0, a1, v and either the ReLU bit
+// masks (m0, m1) or the Mish gates mish'(pre-activation) (g0, g1)
+static int fc_train_fwd(dppo_handle* h, cudaStream_t s, const FcNet& n, const bf16* h0, int N, bf16* a0, bf16* a1, bf16* v,
+                        uint32_t* m0, uint32_t* m1, bf16* g0, bf16* g1, float* out) {
+    const int H = n.H;
+    fc::Maps maps; fc::Params p; fc_common(h, p, N, n.NO);
     DPPO_TRY(fc::rowtile_map(&maps.m[0], h0, N, 64));
-    DPPO_TRY(fc_weight_maps(h, net, &maps.m[1]));
+    DPPO_TRY(fc_weight_maps(h, n, &maps.m[1]));
     DPPO_TRY(fc::rowtile_map(&maps.m[4], a0, N, H));
     DPPO_TRY(fc::rowtile_map(&maps.m[5], a1, N, H));
     DPPO_TRY(fc::rowtile_map(&maps.m[6], v, N, H));
-    maps.m[7] = maps.m[0];
+    maps.m[7] = maps.m[0]; maps.m[8] = maps.m[0]; maps.m[9] = maps.m[0];
     p.nlayers = 4; p.final_mode = fc::FINAL_EPS; p.h0_from_tma = 1;
-    fc_fwd_layers(h, net, 1, p.L[0]);
-    p.L[0][0].store_map = 4; p.L[0][0].mask_out = m0;
-    p.L[0][1].store_map = 5; p.L[0][1].mask_out = m1;
-    p.L[0][2].store_map = 6;
-    p.out = eps;
-    return fc::launch_chain(h, s, H, maps, p, fc_fwd_flops(h, N));
+    fc_fwd_layers(n, 1, p.L[0]);
+    p.L[0][0].store_map = 4; p.L[0][1].store_map = 5; p.L[0][2].store_map = 6;
+    if (n.act1 == 1) { p.L[0][0].mask_out = m0; p.L[0][1].mask_out = m1; }
+    else {
+        DPPO_TRY(fc::rowtile_map(&maps.m[7], g0, N, H));
+        DPPO_TRY(fc::rowtile_map(&maps.m[8], g1, N, H));
+        p.L[0][0].gate_store_map = 7; p.L[0][1].gate_store_map = 8;
+    }
+    p.out = out;
+    return fc::launch_chain(h, s, H, maps, p, fc_fwd_flops(H, N));
 }
-// backward chain: dv = deps W3^T, dh1 = (dv W2^T) . m1, du = (dh1 W1^T) . m0   (du excludes the residual path: dW0 adds h0^T dv)
-static int fc_actor_bwd(dppo_handle* h, cudaStream_t s, int net, const bf16* depsb, int N, const uint32_t* m0, const uint32_t* m1,
-                        bf16* dv, bf16* dh1, bf16* du) {
-    const int H = h->g.H; const TcNetW& W = h->tc->net[net];
-    fc::Maps maps; fc::Params p; fc_common(h, p, N);
-    DPPO_TRY(fc::rowtile_map(&maps.m[0], depsb, N, 64));
+// backward chain: dv = dout W3^T, dh1 = (dv W2^T) . act'(h1), du = (dh1 W1^T) . act'(u)
+// (du excludes the residual path: dW0 adds h0^T dv)
+static int fc_bwd(dppo_handle* h, cudaStream_t s, const FcNet& n, const bf16* doutb, int N, const uint32_t* m0, const uint32_t* m1,
+                  const bf16* g0, const bf16* g1, bf16* dv, bf16* dh1, bf16* du) {
+    const int H = n.H; const TcNetW& W = h->tc->net[n.net];
+    fc::Maps maps; fc::Params p; fc_common(h, p, N, n.NO);
+    DPPO_TRY(fc::rowtile_map(&maps.m[0], doutb, N, 64));
     DPPO_TRY(fc::weight_map(&maps.m[1], W.w3t, 64, H));
     DPPO_TRY(fc::weight_map(&maps.m[2], W.w2t, H, H));
     DPPO_TRY(fc::weight_map(&maps.m[3], W.w1t, H, H));
     DPPO_TRY(fc::rowtile_map(&maps.m[4], dv, N, H));
     DPPO_TRY(fc::rowtile_map(&maps.m[5], dh1, N, H));
     DPPO_TRY(fc::rowtile_map(&maps.m[6], du, N, H));
-    maps.m[7] = maps.m[0];
+    maps.m[7] = maps.m[0]; maps.m[8] = maps.m[0]; maps.m[9] = maps.m[0];
     p.nlayers = 3; p.final_mode = fc::FINAL_STORE; p.h0_from_tma = 1;
     fc::Layer* L = p.L[0];
     memset(L, 0, sizeof(fc::Layer) * fc::MAXL);
+    for (int i = 0; i < fc::MAXL; ++i) { L[i].store_map = -1; L[i].gate_store_map = -1; L[i].gate_load_map = -1; }
     L[0].a_src = 0; L[0].wmap = 1; L[0].wrow_h0 = 0; L[0].n = H; L[0].h0_last = 1; L[0].store_map = 4;
-    L[1].a_src = 1; L[1].wmap = 2; L[1].n = H; L[1].mask_in = m1; L[1].store_map = 5;
-    L[2].a_src = 1; L[2].wmap = 3; L[2].n = H; L[2].mask_in = m0; L[2].store_map = 6;
+    L[1].a_src = 1; L[1].wmap = 2; L[1].n = H; L[1].store_map = 5;
+    L[2].a_src = 1; L[2].wmap = 3; L[2].n = H; L[2].store_map = 6;
+    if (n.act1 == 1) { L[1].mask_in = m1; L[2].mask_in = m0; }
+    else {
+        DPPO_TRY(fc::rowtile_map(&maps.m[7], g1, N, H));
+        DPPO_TRY(fc::rowtile_map(&maps.m[8], g0, N, H));
+        L[1].gate_load_map = 7; L[2].gate_load_map = 8;
+    }
     return fc::launch_chain(h, s, H, maps, p, 2.0 * N * ((double)64 * H + 2.0 * H * H));
 }
 // VPGDiffusion.call for large batches: the whole T-step chain in ONE launch
 static int fc_sample(dppo_handle* h, cudaStream_t s, const float* obs, int B, int use_base, SampleHyper hp, uint64_t seed,
                      uint64_t offset, int64_t row_offset, const float* xT, const float* noise, float* actions, float* chains) {
-    fc::Maps maps; fc::Params p; fc_common(h, p, B);
-    DPPO_TRY(fc_weight_maps(h, DPPO_NET_ACTOR, &maps.m[1]));
-    DPPO_TRY(fc_weight_maps(h, DPPO_NET_ACTOR_FT, &maps.m[4]));
-    maps.m[0] = maps.m[1]; maps.m[7] = maps.m[1];
+    const FcNet nb = fc_actor_net(h, DPPO_NET_ACTOR), nf = fc_actor_net(h, DPPO_NET_ACTOR_FT);
+    fc::Maps maps; fc::Params p; fc_common(h, p, B, nb.NO);
+    DPPO_TRY(fc_weight_maps(h, nb, &maps.m[1]));
+    DPPO_TRY(fc_weight_maps(h, nf, &maps.m[4]));
+    maps.m[0] = maps.m[1]; maps.m[7] = maps.m[1]; maps.m[8] = maps.m[1]; maps.m[9] = maps.m[1];
     p.nlayers = 4; p.final_mode = fc::FINAL_SAMPLE; p.h0_from_tma = 0;
-    fc_fwd_layers(h, DPPO_NET_ACTOR, 1, p.L[0]);
-    fc_fwd_layers(h, DPPO_NET_ACTOR_FT, 4, p.L[1]);
+    fc_fwd_layers(nb, 1, p.L[0]);
+    fc_fwd_layers(nf, 4, p.L[1]);
     p.obs = obs; p.xT = xT; p.noise = noise; p.actions = actions; p.chains_out = chains; p.hp = hp; p.use_base_policy = use_base;
     p.seed = seed; p.offset = offset; p.row_offset = row_offset;
-    return fc::launch_chain(h, s, h->g.H, maps, p, fc_fwd_flops(h, B) * h->g.T);
+    return fc::launch_chain(h, s, nb.H, maps, p, fc_fwd_flops(nb.H, B) * h->g.T);
 }
 
 // ------------------------------------------------------------------ GEMM helpers
@@ -330,7 +371,8 @@ static void tc_mlp_take(dppo_handle* h, int N, TcMlp& m, bool bwd) {
 }
 static int tc_mlp_forward(dppo_handle* h, cudaStream_t s, const TcMlp& m, int N) {
     const int H = m.H, KP0 = m.KP0; const TcNetW& W = *m.W;
-    if (m.fused) return fc_actor_train_fwd(h, s, m.net, m.h0, N, m.a0, m.a1, m.v, m.m0, m.m1, m.out);
+    if (m.fused) return fc_train_fwd(h, s, m.net == DPPO_NET_CRITIC ? fc_critic_net(h) : fc_actor_net(h, m.net), m.h0, N, m.a0, m.a1, m.v,
+                                     m.m0, m.m1, m.pre0, m.pre1, m.out);     // pre0 / pre1 hold the Mish gates on this path
     // L0: a0 = act(h0 W0 (+ b0))
     tc::Gemm g = gemm_of(opK(m.h0, N, KP0, KP0), opMN(W.w2w0 + (size_t)H * H, H, KP0, H), N, H);
     g.epi.bias = m.b0; g.epi.act = m.act1; g.epi.out_bf16 = m.a0; g.epi.ld_bf16 = H; g.epi.out_pre = m.pre0; g.epi.ld_pre = H;
@@ -400,7 +442,8 @@ static int tc_mlp_backward(dppo_handle* h, cudaStream_t s, const TcMlp& m, const
     const int H = m.H, KP0 = m.KP0; const TcNetW& W = *m.W;
     if (m.fused) {
         // one launch: dv, dh1 and the non-residual part of du; the residual path joins in dW0 = h0^T du + h0^T dv
-        DPPO_TRY(fc_actor_bwd(h, s, m.net, doutb, N, m.m0, m.m1, m.dv, m.dh1, m.du));
+        DPPO_TRY(fc_bwd(h, s, m.net == DPPO_NET_CRITIC ? fc_critic_net(h) : fc_actor_net(h, m.net), doutb, N, m.m0, m.m1, m.pre0, m.pre1,
+                        m.dv, m.dh1, m.du));
         DPPO_TRY(tc_dw(h, s, m.v, H, doutb, 64, N, part, gnet + ow3, H, m.NO, m.NO));
         DPPO_TRY(tc_dw(h, s, m.a1, H, m.dv, H, N, part, gnet + ow2, H, H, H));
         DPPO_TRY(tc_dw(h, s, m.a0, H, m.dh1, H, N, part, gnet + ow1, H, H, H));
@@ -443,7 +486,7 @@ static void tc_actor_mlp(const dppo_handle* h, int net, TcMlp& m) {
 static void tc_critic_mlp(const dppo_handle* h, TcMlp& m) {
     const Geom& g = h->g; const float* w = h->net_w[DPPO_NET_CRITIC];
     m.W = &h->tc->net[DPPO_NET_CRITIC]; m.H = g.Hc; m.NO = 1; m.act1 = h->cfg.critic_act + 1; m.KP0 = h->tc->KP0;
-    m.fused = 0; m.net = DPPO_NET_CRITIC;
+    m.fused = fc_critic_ok(h) ? 1 : 0; m.net = DPPO_NET_CRITIC;
     m.b0 = w + g.co.bin; m.b1 = w + g.co.b1; m.b2 = m.W->bias2; m.b3 = w + g.co.b3;
 }
 
@@ -490,6 +533,7 @@ static int tc_value(dppo_handle* h, cudaStream_t s, const float* obs, int N, flo
     // the critic only reads the obs block (the x / one-hot rows of its W0 are zero)
     tc_pack_h0_kernel<<<tc_nblk((size_t)N * (KP0 / 8), 256), 256, 0, s>>>(nullptr, obs, nullptr, -1, N, g.A, g.Do, g.T, KP0, 1, h0);
     TC_KCHECK(h);
+    if (fc_critic_ok(h)) return fc_infer(h, s, fc_critic_net(h), h0, N, fc::FINAL_EPS, v, nullptr, nullptr, nullptr, nullptr);
     return tc_mlp_forward(h, s, m, N);
 }
 
