@@ -394,7 +394,7 @@ static int colsum(dppo_handle* h, cudaStream_t s, const float* D, int ld, int N,
     }
     colsum_kernel<<<nb, 256, sm, s>>>(D, ld, N, ncols, seg, nseg, rpb, part); KLAUNCH(h); KCHECK();
     size_t n = (size_t)nseg * ncols;
-    reduce_partials_kernel<<<nblk(n, 256), 256, 0, s>>>(part, nb, n, n, out, 1.f); KLAUNCH(h); KCHECK();
+    tc_reduce_cols_kernel<<<nblk(n, 8), 256, 0, s>>>(part, nb, n, (int)n, out); KLAUNCH(h); KCHECK();
     return 0;
 }
 // dW[M=in][N=out] = aop(X)[rows][in]^T @ D[rows][out], split over rows, deterministic reduce into out

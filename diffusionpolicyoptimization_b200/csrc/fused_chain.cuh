@@ -50,6 +50,7 @@ struct Layer {
     // Mish networks (H = 256 only: a second [128][H] buffer G lives next to X)
     int gate_store_map;        // act == 2: also store G = mish'(pre-activation) ([rows][H] bf16) for the backward pass, or -1
     int gate_load_map;         // backward: multiply by the gate tile TMA-loaded from this map into G, or -1
+    int colsum_slot;           // 0 / 1: accumulate the column sums of this layer's stored X (bias gradient), or -1
 };
 
 struct Params {
@@ -66,6 +67,7 @@ struct Params {
     float* actions; float* chains_out;
     SampleHyper hp; int use_base_policy;
     uint64_t seed, offset; int64_t row_offset;
+    float* colsum_part;        // [grid][2][H] per-CTA column sums of the layers with colsum_slot >= 0 (bias gradients)
     long long* dbg;            // optional [grid][8] cycle counters (dev tool): see chain_kernel
 };
 struct Maps { CUtensorMap m[NMAPS]; };
@@ -393,6 +395,7 @@ __global__ void __launch_bounds__(FTHREADS, 1) chain_kernel(const __grid_constan
 #pragma unroll
         for (int a = 0; a < 16; ++a) x[a] = 0.f;
         bool first = true;
+        float csum[2][2] = {};                                   // column sums: thread etid (< H/2) owns columns 2*etid, 2*etid+1
         long long t_acc = 0, t_gen = 0, t_fin = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int row = tile * FBM + rloc;
@@ -539,6 +542,23 @@ __global__ void __launch_bounds__(FTHREADS, 1) chain_kernel(const __grid_constan
                         }
                         __syncwarp();
                         if (lane == 0) mbar_arrive(x_full);
+                        if (L.colsum_slot >= 0) {
+                            // bias gradient: column sums of the bf16 tile just written (valid rows only).  Runs while the
+                            // next layer's MMAs already read X; the next epilogue's barrier orders it before X is rewritten.
+                            const int nrows = min(FBM, p.rows - tile * FBM);
+                            if (etid < H / 2) {
+                                const int kb = etid >> 5, w = etid & 31;
+                                const uint32_t base = x_addr + (uint32_t)kb * 16384u + (uint32_t)(w & 3) * 4u;
+                                float s0 = 0.f, s1 = 0.f;
+                                for (int r = 0; r < nrows; ++r) {
+                                    uint32_t word;
+                                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(word) : "r"(base + (uint32_t)r * 128u + (uint32_t)(((w >> 2) ^ (r & 7)) << 4)));
+                                    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&word));
+                                    s0 += f.x; s1 += f.y;
+                                }
+                                if (L.colsum_slot == 0) { csum[0][0] += s0; csum[0][1] += s1; } else { csum[1][0] += s0; csum[1][1] += s1; }
+                            }
+                        }
                         if (TIMING) t_gen += clock64() - c_epi;
                     } else {
                         // ---------------- final layer: eps of this row sits in TMEM columns [0, 32); each half takes 16
@@ -614,6 +634,10 @@ __global__ void __launch_bounds__(FTHREADS, 1) chain_kernel(const __grid_constan
             }
         }
         if (store_thread) tma_store_wait_all();
+        if (p.colsum_part && etid < H / 2) {
+            float* dst = p.colsum_part + (size_t)blockIdx.x * 2 * H + 2 * etid;
+            dst[0] = csum[0][0]; dst[1] = csum[0][1]; dst[H] = csum[1][0]; dst[H + 1] = csum[1][1];
+        }
         if (TIMING && p.dbg && warp == 2 && lane == 0) { p.dbg[blockIdx.x * 8 + 4] = t_acc; p.dbg[blockIdx.x * 8 + 5] = t_gen; p.dbg[blockIdx.x * 8 + 6] = t_fin; }
     }
     tcgen05_fence_before();

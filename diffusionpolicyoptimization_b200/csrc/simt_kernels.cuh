@@ -592,11 +592,14 @@ __global__ void time_backward_kernel(const float* __restrict__ w, ActorOff o, in
             g[o.win + (size_t)(A + j) * H + c] = a;
         }
     }
-    for (int i = tid; i < T * td; i += nt) {        // d temb[t][j]
+    // d temb[t][j] = sum_c W_in[A+j][c] * G[t][c]: one warp per output, lanes stride over c (coalesced), shuffle reduce
+    for (int i = tid >> 5; i < T * td; i += nt >> 5) {
         int t = i / td, j = i % td;
         float s = 0.f;
-        for (int c = 0; c < H; ++c) s = fmaf(w[o.win + (size_t)(A + j) * H + c], G[(size_t)t * H + c], s);
-        dte[i] = s;
+        for (int c = tid & 31; c < H; c += 32) s = fmaf(w[o.win + (size_t)(A + j) * H + c], G[(size_t)t * H + c], s);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if ((tid & 31) == 0) dte[i] = s;
     }
     __syncthreads();
     for (int i = tid; i < T * 2 * td; i += nt) {    // d hidden pre-activation

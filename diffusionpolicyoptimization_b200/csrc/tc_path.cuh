@@ -147,6 +147,17 @@ __global__ void tc_reduce2d_kernel(const float* __restrict__ part, int S, size_t
     out[(size_t)r * ld_out + c] = s;
 }
 
+// out[c] = sum_b part[b*stride + c]: one warp per column, lanes stride over the nb partial rows (deterministic)
+__global__ void __launch_bounds__(256) tc_reduce_cols_kernel(const float* __restrict__ part, int nb, size_t stride, int ncols, float* __restrict__ out) {
+    const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (c >= ncols) return;
+    float s = 0.f;
+    for (int b = lane; b < nb; b += 32) s += part[(size_t)b * stride + c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[c] = s;
+}
+
 // ------------------------------------------------------------------ state
 static int tc_init(dppo_handle* h) {
     const Geom& g = h->g;
@@ -236,7 +247,7 @@ static int fc_weight_maps(const dppo_handle* h, const FcNet& n, CUtensorMap* m) 
 static void fc_fwd_layers(const FcNet& n, int wbase, fc::Layer* L) {
     const int H = n.H;
     memset(L, 0, sizeof(fc::Layer) * fc::MAXL);
-    for (int i = 0; i < fc::MAXL; ++i) { L[i].store_map = -1; L[i].gate_store_map = -1; L[i].gate_load_map = -1; }
+    for (int i = 0; i < fc::MAXL; ++i) { L[i].store_map = -1; L[i].gate_store_map = -1; L[i].gate_load_map = -1; L[i].colsum_slot = -1; }
     L[0].a_src = 0; L[0].wmap = wbase; L[0].wrow_h0 = H; L[0].n = H; L[0].bias = n.b0; L[0].act = n.act1;
     L[1].a_src = 1; L[1].wmap = wbase + 1; L[1].n = H; L[1].bias = n.b1; L[1].act = n.act1;
     L[2].a_src = 2; L[2].wmap = wbase; L[2].wrow_h0 = H; L[2].n = H; L[2].bias = n.b2; L[2].h0_last = 1;
@@ -292,8 +303,9 @@ static int fc_train_fwd(dppo_handle* h, cudaStream_t s, const FcNet& n, const bf
 }
 // backward chain: dv = dout W3^T, dh1 = (dv W2^T) . act'(h1), du = (dh1 W1^T) . act'(u)
 // (du excludes the residual path: dW0 adds h0^T dv)
+// colsum_part [sm_count][2][H]: per-CTA column sums of dv (slot 0 = db2) and dh1 (slot 1 = db1), reduced by the caller
 static int fc_bwd(dppo_handle* h, cudaStream_t s, const FcNet& n, const bf16* doutb, int N, const uint32_t* m0, const uint32_t* m1,
-                  const bf16* g0, const bf16* g1, bf16* dv, bf16* dh1, bf16* du) {
+                  const bf16* g0, const bf16* g1, bf16* dv, bf16* dh1, bf16* du, float* colsum_part) {
     const int H = n.H; const TcNetW& W = h->tc->net[n.net];
     fc::Maps maps; fc::Params p; fc_common(h, p, N, n.NO);
     DPPO_TRY(fc::rowtile_map(&maps.m[0], doutb, N, 64));
@@ -307,9 +319,10 @@ static int fc_bwd(dppo_handle* h, cudaStream_t s, const FcNet& n, const bf16* do
     p.nlayers = 3; p.final_mode = fc::FINAL_STORE; p.h0_from_tma = 1;
     fc::Layer* L = p.L[0];
     memset(L, 0, sizeof(fc::Layer) * fc::MAXL);
-    for (int i = 0; i < fc::MAXL; ++i) { L[i].store_map = -1; L[i].gate_store_map = -1; L[i].gate_load_map = -1; }
-    L[0].a_src = 0; L[0].wmap = 1; L[0].wrow_h0 = 0; L[0].n = H; L[0].h0_last = 1; L[0].store_map = 4;
-    L[1].a_src = 1; L[1].wmap = 2; L[1].n = H; L[1].store_map = 5;
+    for (int i = 0; i < fc::MAXL; ++i) { L[i].store_map = -1; L[i].gate_store_map = -1; L[i].gate_load_map = -1; L[i].colsum_slot = -1; }
+    L[0].a_src = 0; L[0].wmap = 1; L[0].wrow_h0 = 0; L[0].n = H; L[0].h0_last = 1; L[0].store_map = 4; L[0].colsum_slot = 0;
+    L[1].a_src = 1; L[1].wmap = 2; L[1].n = H; L[1].store_map = 5; L[1].colsum_slot = 1;
+    p.colsum_part = colsum_part;
     L[2].a_src = 1; L[2].wmap = 3; L[2].n = H; L[2].store_map = 6;
     if (n.act1 == 1) { L[1].mask_in = m1; L[2].mask_in = m0; }
     else {
@@ -442,14 +455,16 @@ static int tc_mlp_backward(dppo_handle* h, cudaStream_t s, const TcMlp& m, const
     const int H = m.H, KP0 = m.KP0; const TcNetW& W = *m.W;
     if (m.fused) {
         // one launch: dv, dh1 and the non-residual part of du; the residual path joins in dW0 = h0^T du + h0^T dv
+        const int grid = (N + 127) / 128 < h->sm_count ? (N + 127) / 128 : h->sm_count;
+        float* cpart = part;                                       // [grid][2][H]; consumed before the dW GEMMs reuse `part`
         DPPO_TRY(fc_bwd(h, s, m.net == DPPO_NET_CRITIC ? fc_critic_net(h) : fc_actor_net(h, m.net), doutb, N, m.m0, m.m1, m.pre0, m.pre1,
-                        m.dv, m.dh1, m.du));
+                        m.dv, m.dh1, m.du, cpart));
+        tc_reduce_cols_kernel<<<tc_nblk(H, 8), 256, 0, s>>>(cpart, grid, (size_t)2 * H, H, gnet + ob2); TC_KCHECK(h);
+        tc_reduce_cols_kernel<<<tc_nblk(H, 8), 256, 0, s>>>(cpart + H, grid, (size_t)2 * H, H, gnet + ob1); TC_KCHECK(h);
         DPPO_TRY(tc_dw(h, s, m.v, H, doutb, 64, N, part, gnet + ow3, H, m.NO, m.NO));
         DPPO_TRY(tc_dw(h, s, m.a1, H, m.dv, H, N, part, gnet + ow2, H, H, H));
         DPPO_TRY(tc_dw(h, s, m.a0, H, m.dh1, H, N, part, gnet + ow1, H, H, H));
         DPPO_TRY(tc_dw(h, s, m.h0, KP0, m.du, H, N, part, dw0, KP0, H, H, m.dv));
-        DPPO_TRY(tc_colsum(h, s, m.dv, N, H, part, gnet + ob2));
-        DPPO_TRY(tc_colsum(h, s, m.dh1, N, H, part, gnet + ob1));
         return 0;
     }
     // dv = dout W3^T
