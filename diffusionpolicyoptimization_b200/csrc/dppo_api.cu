@@ -226,6 +226,7 @@ extern "C" int dppo_create(const dppo_cfg* cfg, int device, dppo_handle** out) {
     if (prop.major != 10) DPPO_FAIL(-4, "dppo_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
     dppo_handle* h = new dppo_handle();
     h->cfg = *cfg; h->device = device; h->g = g; h->sm_count = prop.multiProcessorCount;
+    { const char* dv = getenv("DPPO_DETERMINISTIC"); h->deterministic = (dv && dv[0] == '1') ? 1 : 0; }
     const size_t nA = g.ao.n, nC = g.co.n;
     const size_t total = 3 * nA + nC;
     CUDA_TRY(cudaMalloc(&h->params, total * sizeof(float)));

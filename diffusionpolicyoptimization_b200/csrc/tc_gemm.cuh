@@ -28,6 +28,7 @@ struct Epi {
     const __nv_bfloat16* mask; int ldmask; int mask_mode;   // 1: *= (mask > 0), 2: *= mish'(mask)
     const __nv_bfloat16* add; int ldadd;                    // += add[m][n]
     float* out_f32; int ld_f32; size_t split_stride;        // fp32 row-major (+ split * split_stride)
+    int f32_atomic;                                         // accumulate into out_f32 with red.global.add (split-K without partials)
     __nv_bfloat16* out_bf16; int ld_bf16;                   // bf16 row-major, post-activation
     __nv_bfloat16* out_pre; int ld_pre;                     // bf16 row-major, pre-activation
 };
@@ -94,6 +95,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// one lane of a converged warp: keeps the issue warps' control flow warp-uniform so that nvcc emits the
+// uniform-datapath instructions (UTCHMMA / UTCBAR / UTMALDG) without ELECT / BRA.U.ANY waterfall loops
+__device__ __forceinline__ bool elect_one_lane() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xFFFFFFFF;\n\tselp.b32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 // shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor), 128B swizzle
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     uint64_t d = 0;
@@ -149,11 +157,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
+        // ===================== TMA producer (warp-uniform; an elected lane issues) =====================
+        {
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
                 const int split = tile / (p.m_blocks * p.n_blocks);
@@ -162,28 +170,31 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 const int kb0 = split * p.kb_per_split, kb1 = min(p.kblocks, kb0 + p.kb_per_split);
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
-                    mbar_expect_tx(&full[stage], A_STAGE + B_STAGE);
-                    uint8_t* a = sA + stage * A_STAGE;
-                    uint8_t* b = sB + stage * B_STAGE;
-                    const CUtensorMap* ma = kb < p.ka_blocks ? &tmA : &tmA2;
-                    const int ka = (kb < p.ka_blocks ? kb : kb - p.ka_blocks) * BK;
-                    if (!A_MN) tma_load_2d(a, ma, &full[stage], ka, m_blk * BM);
-                    else {
+                    if (elect_one_lane()) {
+                        mbar_expect_tx(&full[stage], A_STAGE + B_STAGE);
+                        uint8_t* a = sA + stage * A_STAGE;
+                        uint8_t* b = sB + stage * B_STAGE;
+                        const CUtensorMap* ma = kb < p.ka_blocks ? &tmA : &tmA2;
+                        const int ka = (kb < p.ka_blocks ? kb : kb - p.ka_blocks) * BK;
+                        if (!A_MN) tma_load_2d(a, ma, &full[stage], ka, m_blk * BM);
+                        else {
 #pragma unroll
-                        for (int j = 0; j < BM / 64; ++j) tma_load_2d(a + j * (64 * BK * 2), ma, &full[stage], m_blk * BM + j * 64, ka);
-                    }
-                    if (!B_MN) tma_load_2d(b, &tmB, &full[stage], kb * BK, n_blk * BN);
-                    else {
+                            for (int j = 0; j < BM / 64; ++j) tma_load_2d(a + j * (64 * BK * 2), ma, &full[stage], m_blk * BM + j * 64, ka);
+                        }
+                        if (!B_MN) tma_load_2d(b, &tmB, &full[stage], kb * BK, n_blk * BN);
+                        else {
 #pragma unroll
-                        for (int j = 0; j < BN / 64; ++j) tma_load_2d(b + j * (64 * BK * 2), &tmB, &full[stage], n_blk * BN + j * 64, kb * BK);
+                            for (int j = 0; j < BN / 64; ++j) tma_load_2d(b + j * (64 * BK * 2), &tmB, &full[stage], n_blk * BN + j * 64, kb * BK);
+                        }
                     }
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (warp-uniform; an elected lane issues) =====================
+        {
             constexpr uint32_t idesc = make_idesc(BM, BN, A_MN, B_MN);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
@@ -197,18 +208,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     mbar_wait(&full[stage], phase);
                     tcgen05_fence_after();
                     const uint32_t a0 = smem_u32(sA + stage * A_STAGE), b0 = smem_u32(sB + stage * B_STAGE);
+                    if (elect_one_lane()) {
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        // K-major: 16 bf16 = 32 B inside the 128 B swizzle row; SBO = 8 rows * 128 B.
-                        // MN-major: 16 k-rows = 2048 B; LBO = next 64-wide MN atom (64*BK*2 B), SBO = 8 k-rows.
-                        const uint64_t da = A_MN ? make_desc(a0 + k * 2048, 64 * BK * 2, 1024) : make_desc(a0 + k * 32, 16, 1024);
-                        const uint64_t db = B_MN ? make_desc(b0 + k * 2048, 64 * BK * 2, 1024) : make_desc(b0 + k * 32, 16, 1024);
-                        umma_bf16(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        for (int k = 0; k < BK / 16; ++k) {
+                            // K-major: 16 bf16 = 32 B inside the 128 B swizzle row; SBO = 8 rows * 128 B.
+                            // MN-major: 16 k-rows = 2048 B; LBO = next 64-wide MN atom (64*BK*2 B), SBO = 8 k-rows.
+                            const uint64_t da = A_MN ? make_desc(a0 + k * 2048, 64 * BK * 2, 1024) : make_desc(a0 + k * 32, 16, 1024);
+                            const uint64_t db = B_MN ? make_desc(b0 + k * 2048, 64 * BK * 2, 1024) : make_desc(b0 + k * 32, 16, 1024);
+                            umma_bf16(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        }
+                        tcgen05_commit(&empty[stage]);      // frees the smem slot when these MMAs retire
                     }
-                    tcgen05_commit(&empty[stage]);          // frees the smem slot when these MMAs retire
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                tcgen05_commit(&tfull[acc]);                // accumulator complete -> epilogue
+                if (elect_one_lane()) tcgen05_commit(&tfull[acc]);   // accumulator complete -> epilogue
+                __syncwarp();
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -310,7 +325,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                             for (int j = 0; j < 32; ++j) if (n0 + j < e.N) dst[j] = __float2bfloat16(v[j]);
                         }
                     }
-                    if (e.out_f32) {
+                    if (e.out_f32 && e.f32_atomic) {
+                        float* dst = e.out_f32 + (size_t)m * e.ld_f32 + n0;
+                        if (full32 && (e.ld_f32 & 3) == 0) {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q)
+                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + q * 4), "f"(v[q * 4]), "f"(v[q * 4 + 1]), "f"(v[q * 4 + 2]), "f"(v[q * 4 + 3]) : "memory");
+                        } else {
+                            for (int j = 0; j < 32; ++j) if (n0 + j < e.N) atomicAdd(dst + j, v[j]);
+                        }
+                    } else if (e.out_f32) {
                         float* dst = e.out_f32 + (size_t)split * e.split_stride + (size_t)m * e.ld_f32 + n0;
                         if (full32 && (e.ld_f32 & 3) == 0) {
 #pragma unroll

@@ -148,14 +148,122 @@ __global__ void tc_reduce2d_kernel(const float* __restrict__ part, int S, size_t
 }
 
 // out[c] = sum_b part[b*stride + c]: one warp per column, lanes stride over the nb partial rows (deterministic)
-__global__ void __launch_bounds__(256) tc_reduce_cols_kernel(const float* __restrict__ part, int nb, size_t stride, int ncols, float* __restrict__ out) {
+// columns >= split (when out2 is given) go to out2[c - split]
+__global__ void __launch_bounds__(256) tc_reduce_cols_kernel(const float* __restrict__ part, int nb, size_t stride, int ncols, float* __restrict__ out,
+                                                             int split = 0, float* __restrict__ out2 = nullptr) {
     const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (c >= ncols) return;
     float s = 0.f;
     for (int b = lane; b < nb; b += 32) s += part[(size_t)b * stride + c];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) out[c] = s;
+    if (lane == 0) { if (out2 && c >= split) out2[c - split] = s; else out[c] = s; }
+}
+
+// PPO loss + gradient seeds for the tensor path (diffusion_ppo.py:32-132), one thread per row, single pass:
+// writes the padded bf16 seeds the backward chains consume (depsb / dvalb [N][64]), the metric partial sums, and the
+// per-block column sums of deps / dvalue (output-layer bias gradients) - no fp32 deps round trip, no separate pad / colsum.
+__global__ void __launch_bounds__(128) tc_ppo_loss_kernel(
+    const float* __restrict__ prev, const float* __restrict__ nxt, const float* __restrict__ eps,
+    const int* __restrict__ inds, const float* __restrict__ returns, const float* __restrict__ oldvalues,
+    const float* __restrict__ advantages, const float* __restrict__ oldlogp, const float* __restrict__ newvalues,
+    const float* __restrict__ advstats, const float* __restrict__ sch, PpoHyper hp, int N,
+    bf16* __restrict__ depsb, bf16* __restrict__ dvalb, double* __restrict__ block_sums, float* __restrict__ col_part /*[blocks][A+1]*/) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const int A = hp.A;
+    double acc[5] = {0, 0, 0, 0, 0};
+    float gout[32];
+#pragma unroll
+    for (int a = 0; a < 32; ++a) gout[a] = 0.f;
+    float dv_out = 0.f;
+    if (r < N) {
+        const int ind = inds[r], t = hp.K - 1 - ind;
+        const int nuse = min(hp.reward_horizon, A / hp.Da) * hp.Da;   // newlogprobs[:, :reward_horizon, :]
+        const StepConst sc = step_const(sch, hp.T, t);
+        const float sd = logprob_std(sc, hp.min_lp_std);
+        const float lgs = 0.91893853320467274f + logf(sd);
+        float newm = 0.f, oldm = 0.f;
+        float zs[32]; uint32_t live = 0u;
+#pragma unroll
+        for (int a = 0; a < 32; ++a) {
+            zs[a] = 0.f;
+            if (a < nuse) {
+                const size_t i = (size_t)r * A + a;
+                float z; bool in;
+                const float lp = logprob_elem_c(prev[i], eps[i], nxt[i], sc, sd, lgs, hp.dcv, &z, &in);
+                newm += fminf(fmaxf(lp, hp.lp_lo), hp.lp_hi);
+                oldm += fminf(fmaxf(oldlogp[i], hp.lp_lo), hp.lp_hi);
+                zs[a] = z;
+                if (lp >= hp.lp_lo && lp <= hp.lp_hi && in) live |= 1u << a;
+            }
+        }
+        newm /= (float)nuse; oldm /= (float)nuse;
+        float adv = advantages[r];
+        if (hp.norm_adv) adv = (adv - advstats[0]) / (advstats[1] + 1e-8f);
+        adv *= powf(hp.gamma_d, (float)(hp.K - ind - 1));
+        const float logratio = newm - oldm, ratio = expf(logratio);
+        const float tt = hp.K > 1 ? (float)ind / (float)(hp.K - 1) : (float)ind;
+        const float clipc = hp.K > 1 ? hp.clip_base + (hp.clip_coef - hp.clip_base) * (expf(hp.clip_rate * tt) - 1.f) / (expf(hp.clip_rate) - 1.f) : tt;
+        const float rc = fminf(fmaxf(ratio, 1.f - clipc), 1.f + clipc);
+        const float pg1 = -adv * ratio, pg2 = -adv * rc;
+        const float pg = fmaxf(pg1, pg2);
+        const float dpg = (pg1 >= pg2) ? -adv : ((ratio >= 1.f - clipc && ratio <= 1.f + clipc) ? -adv : 0.f);
+        const float gscale = dpg * ratio * hp.inv_nglobal / (float)nuse / sd * sc.c1 * (-sc.srm1);
+#pragma unroll
+        for (int a = 0; a < 32; ++a) gout[a] = ((live >> a) & 1u) ? gscale * zs[a] : 0.f;
+        // value loss
+        const float v = newvalues[r], ret = returns[r];
+        float vl, dv;
+        if (hp.clip_v >= 0.f) {
+            const float ov = oldvalues[r];
+            const float un = (v - ret) * (v - ret);
+            const float dcl = v - ov;
+            const float vc = ov + fminf(fmaxf(dcl, -hp.clip_v), hp.clip_v);
+            const float cl = (vc - ret) * (vc - ret);
+            if (un >= cl) { vl = 0.5f * un; dv = (v - ret); }
+            else { vl = 0.5f * cl; dv = (dcl >= -hp.clip_v && dcl <= hp.clip_v) ? (vc - ret) : 0.f; }
+        } else { vl = 0.5f * (v - ret) * (v - ret); dv = (v - ret); }
+        dv_out = hp.vf_coef * dv * hp.inv_nglobal;
+        acc[0] = pg; acc[1] = vl; acc[2] = (fabsf(ratio - 1.f) > clipc) ? 1.0 : 0.0;
+        acc[3] = (ratio - 1.f) - logratio; acc[4] = ratio;
+        // padded bf16 rows: [deps (A) | 0..] and [dvalue | 0..]
+        uint4* drow = reinterpret_cast<uint4*>(depsb + (size_t)r * 64);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint4 u;
+            u.x = fc::pack_bf16(gout[q * 8 + 0], gout[q * 8 + 1]); u.y = fc::pack_bf16(gout[q * 8 + 2], gout[q * 8 + 3]);
+            u.z = fc::pack_bf16(gout[q * 8 + 4], gout[q * 8 + 5]); u.w = fc::pack_bf16(gout[q * 8 + 6], gout[q * 8 + 7]);
+            drow[q] = u;
+        }
+#pragma unroll
+        for (int q = 4; q < 8; ++q) drow[q] = make_uint4(0u, 0u, 0u, 0u);
+        uint4* vrow = reinterpret_cast<uint4*>(dvalb + (size_t)r * 64);
+        vrow[0] = make_uint4(fc::pack_bf16(dv_out, 0.f), 0u, 0u, 0u);
+#pragma unroll
+        for (int q = 1; q < 8; ++q) vrow[q] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    // ---- block reductions: metric sums (double) and column sums of the seeds
+    __shared__ double red[5][128];
+    __shared__ float cred[4][33];
+    for (int k = 0; k < 5; ++k) red[k][threadIdx.x] = acc[k];
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+#pragma unroll
+    for (int a = 0; a < 33; ++a) {
+        float v = a < 32 ? gout[a < 32 ? a : 0] : dv_out;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if (lane == 0) cred[wrp][a] = v;
+    }
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) {
+        if (threadIdx.x < o) for (int k = 0; k < 5; ++k) red[k][threadIdx.x] += red[k][threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x < 5) block_sums[(size_t)blockIdx.x * 5 + threadIdx.x] = red[threadIdx.x][0];
+    if (threadIdx.x <= A) {
+        const int a = threadIdx.x < A ? threadIdx.x : 32;
+        col_part[(size_t)blockIdx.x * (A + 1) + threadIdx.x] = cred[0][a] + cred[1][a] + cred[2][a] + cred[3][a];
+    }
 }
 
 // ------------------------------------------------------------------ state
@@ -415,12 +523,21 @@ static int tc_splits_for(const dppo_handle* h, int M, int N, int rows) {
     if (splits > 64) splits = 64;
     return splits;
 }
-// dW[M][ncols] = X^T D  (X [rows][M] bf16, D [rows][Nd] bf16), deterministic split-K over the rows
-// (+ X^T D2 when D2 is given: the partial sums of both products are reduced together)
+// dW[M][ncols] (+)= X^T D  (X [rows][M] bf16, D [rows][Nd] bf16), split-K over the rows (+ X^T D2 when D2 is given).
+// Default: every split CTA accumulates its tile into `out` with red.global.add.f32 (out must be zeroed beforehand; the
+// summation order, hence the last bits, vary run to run).  DPPO_DETERMINISTIC=1: partial tiles + a fixed-order reduction.
 static int tc_dw(dppo_handle* h, cudaStream_t s, const bf16* X, int M, const bf16* D, int Nd, int rows, float* part,
                  float* out, int out_rows, int out_cols, int ld_out, const bf16* D2 = nullptr) {
     tc::Gemm g = gemm_of(opMN(X, M, rows, M), opMN(D, Nd, rows, Nd), M, Nd);
     g.splits = tc_splits_for(h, M, Nd, rows);
+    if (!h->deterministic) {
+        g.epi.M = out_rows; g.epi.N = out_cols;
+        g.epi.out_f32 = out; g.epi.ld_f32 = ld_out; g.epi.f32_atomic = 1;
+        int S = tc::launch(h, s, g);
+        if (S < 0) return S;
+        if (D2) { g.B = opMN(D2, Nd, rows, Nd); S = tc::launch(h, s, g); if (S < 0) return S; }
+        return 0;
+    }
     g.epi.out_f32 = part; g.epi.ld_f32 = Nd; g.epi.split_stride = (size_t)M * Nd;
     int S = tc::launch(h, s, g);
     if (S < 0) return S;
@@ -561,7 +678,7 @@ static int tc_actor_grads(dppo_handle* h, cudaStream_t s, int net, const TcMlp& 
                           float* part, float* dw0, float* gnet) {
     const Geom& g = h->g; const float* w = h->net_w[net]; const ActorDerived& d = h->ad[net];
     DPPO_TRY(tc_mlp_backward(h, s, m, depsb, N, part, gnet, g.ao.w1, g.ao.b1, g.ao.w2, g.ao.b2, g.ao.w3, dw0));
-    DPPO_TRY(colsum(h, s, deps, g.A, N, g.A, nullptr, 1, part, gnet + g.ao.b3));
+    if (deps) DPPO_TRY(colsum(h, s, deps, g.A, N, g.A, nullptr, 1, part, gnet + g.ao.b3));   // else: the loss kernel already reduced it
     // dw0 rows [A+Do, A+Do+T) are the per-t column sums of du: the gradient of the bt table
     const size_t sm = (size_t)(g.T * g.td * 3) * sizeof(float);
     time_backward_kernel<<<1, 512, sm, s>>>(w, g.ao, g.A, g.td, g.H, g.T, dw0 + (size_t)(g.A + g.Do) * g.H, d.sinemb, d.thpre, d.temb, gnet);
@@ -574,7 +691,7 @@ static int tc_critic_grads(dppo_handle* h, cudaStream_t s, const TcMlp& m, const
                            float* part, float* dw0, float* gnet) {
     const Geom& g = h->g;
     DPPO_TRY(tc_mlp_backward(h, s, m, dvalb, N, part, gnet, g.co.w1, g.co.b1, g.co.w2, g.co.b2, g.co.w3, dw0));
-    DPPO_TRY(colsum(h, s, dval, 1, N, 1, nullptr, 1, part, gnet + g.co.b3));
+    if (dval) DPPO_TRY(colsum(h, s, dval, 1, N, 1, nullptr, 1, part, gnet + g.co.b3));
     unpack_dw0_kernel<<<tc_nblk((size_t)g.Do * g.Hc, 256), 256, 0, s>>>(dw0 + (size_t)g.A * g.Hc, 0, 0, g.Do, g.Hc, gnet + g.co.win);
     TC_KCHECK(h);
     // the ones column of h0 collects the input-layer bias gradient
@@ -608,6 +725,11 @@ static int tc_ppo_step(dppo_handle* h, cudaStream_t s, const float* obs, const f
     double* bsum = ws_take<double>(h, (size_t)nlb * 5);
     ma.h0 = h0; mc.h0 = h0; ma.out = eps; mc.out = val;
 
+    if (!h->deterministic) {   // the dW GEMMs accumulate atomically into the gradient buffers
+        CUDA_TRY(cudaMemsetAsync(gr, 0, (nA + nC) * sizeof(float), s));
+        CUDA_TRY(cudaMemsetAsync(dw0a, 0, (size_t)KP0 * g.H * sizeof(float), s));
+        CUDA_TRY(cudaMemsetAsync(dw0c, 0, (size_t)KP0 * g.Hc * sizeof(float), s));
+    }
     make_trow_kernel<<<tc_nblk(N, 256), 256, 0, s>>>(inds, N, g.K, 0, trow); TC_KCHECK(h);
     if (adv_std < 0.f) { adv_stats_kernel<<<1, 256, 0, s>>>(advantages, N, h->scalars); TC_KCHECK(h); }
     else { set_scalars_kernel<<<1, 1, 0, s>>>(h->scalars, adv_mean, adv_std); TC_KCHECK(h); }
@@ -620,13 +742,13 @@ static int tc_ppo_step(dppo_handle* h, cudaStream_t s, const float* obs, const f
     hp.lp_lo = h->cfg.logprob_clip_lo; hp.lp_hi = h->cfg.logprob_clip_hi; hp.gamma_d = h->cfg.gamma_denoising;
     hp.clip_coef = h->cfg.clip_ploss_coef; hp.clip_base = h->cfg.clip_ploss_coef_base; hp.clip_rate = h->cfg.clip_ploss_coef_rate;
     hp.clip_v = h->cfg.clip_vloss_coef; hp.vf_coef = h->cfg.vf_coef; hp.inv_nglobal = 1.0f / (float)N_global;
-    ppo_loss_kernel<<<nlb, 128, 0, s>>>(prev, nxt, eps, inds, returns, oldvalues, advantages, oldlogp, val,
-                                       h->scalars, h->sched, hp, N, deps, dval, bsum); TC_KCHECK(h);
+    tc_ppo_loss_kernel<<<nlb, 128, 0, s>>>(prev, nxt, eps, inds, returns, oldvalues, advantages, oldlogp, val,
+                                          h->scalars, h->sched, hp, N, depsb, dvalb, bsum, part); TC_KCHECK(h);
     ppo_metrics_kernel<<<1, 256, 0, s>>>(bsum, nlb, hp.inv_nglobal, (float)((double)N / (double)N_global), gr + nA + nC); TC_KCHECK(h);
-    tc_pad64_kernel<<<tc_nblk((size_t)N * 8, 256), 256, 0, s>>>(deps, N, g.A, depsb); TC_KCHECK(h);
-    tc_pad64_kernel<<<tc_nblk((size_t)N * 8, 256), 256, 0, s>>>(dval, N, 1, dvalb); TC_KCHECK(h);
-    DPPO_TRY(tc_actor_grads(h, s, DPPO_NET_ACTOR_FT, ma, deps, depsb, N, part, dw0a, gr));
-    DPPO_TRY(tc_critic_grads(h, s, mc, dval, dvalb, N, part, dw0c, gr + nA));
+    // output-layer bias gradients = column sums of the seeds (per-block partials from the loss kernel)
+    tc_reduce_cols_kernel<<<tc_nblk(g.A + 1, 8), 256, 0, s>>>(part, nlb, (size_t)(g.A + 1), g.A + 1, gr + g.ao.b3, g.A, gr + nA + g.co.b3); TC_KCHECK(h);
+    DPPO_TRY(tc_actor_grads(h, s, DPPO_NET_ACTOR_FT, ma, nullptr, depsb, N, part, dw0a, gr));
+    DPPO_TRY(tc_critic_grads(h, s, mc, nullptr, dvalb, N, part, dw0c, gr + nA));
     return 0;
 }
 
@@ -653,6 +775,10 @@ static int tc_pretrain_grads(dppo_handle* h, cudaStream_t s, const float* action
     float* dw0 = ws_take<float>(h, (size_t)KP0 * g.H);
     double* bsum = ws_take<double>(h, nlb);
     ma.h0 = h0; ma.out = eps;
+    if (!h->deterministic) {
+        CUDA_TRY(cudaMemsetAsync(gr, 0, nA * sizeof(float), s));
+        CUDA_TRY(cudaMemsetAsync(dw0, 0, (size_t)KP0 * g.H * sizeof(float), s));
+    }
     pretrain_prep_kernel<<<tc_nblk(ne, 256), 256, 0, s>>>(actions, t_in, noise_in, N, g.A, g.T, h->sched, seed, offset, row_offset, trow, noise, xn); TC_KCHECK(h);
     tc_pack_h0_kernel<<<tc_nblk((size_t)N * (KP0 / 8), 256), 256, 0, s>>>(xn, obs, trow, 0, N, g.A, g.Do, g.T, KP0, 1, h0); TC_KCHECK(h);
     DPPO_TRY(tc_mlp_forward(h, s, ma, N));
