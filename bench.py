@@ -9,6 +9,10 @@ weights, clipped-ratio + value loss, backward, (N>1: one all-reduce of grads+met
 metric — denoised action chunks/s of the T=20 chain at 40 env copies — is measured in the same
 run and reported under "sampling" (it is dependency-latency-bound, not a throughput kernel).
 
+Precision: the default is the tensor-core mode (tcgen05, bf16 operands, fp32 accumulation / masters / loss / AdamW) that
+BASELINE.json's north_star allows with stated looser bounds (tests/test_gpu_bf16.py); `--precision fp32` runs the strict
+parity mode (CUDA-core FFMA, 1e-4 / 1e-3 bounds) and its throughput is also reported in every line under "fp32_parity_mode".
+
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision bf16|fp32]
 """
 from __future__ import annotations
@@ -32,6 +36,7 @@ N_ROWS = 50_000            # minibatch rows per GPU (cfg train.batch_size, ft_pp
 N_ENVS = 40                # env copies per rollout step (ft_ppo_diffusion_mlp_run.yaml:26)
 METRIC = "ppo_logprob_update_samples_per_sec"
 UNIT = "samples/s"
+PATHS = {1: "persistent cluster kernel (fp32 FFMA, DSMEM)", 2: "layered fp32", 3: "layered tcgen05", 4: "fused tcgen05 chain (one launch, T steps on chip)"}
 
 
 def peaks():
@@ -273,21 +278,33 @@ def run_ours(args):
     ms_e2e = timed(e2e_step, args.steps, max(3, args.warmup // 2))
     clocks = clk.finish()
 
-    # ---- roofline of the dominant kernel class (GEMMs), timed live with CUDA events in the library
+    # ---- roofline of the dominant kernel, timed live with CUDA events inside the library (every tensor-class launch is
+    #      bracketed on its launching stream; classes: 0 fused tcgen05 layer chain, 1 tcgen05 GEMM (dW), 2 FFMA SGEMM)
     e.profile_enable(True)
     for i in range(args.steps):
         flush.zero_(); dev_step(i)
-    gemm_ms, gemm_n, gemm_fl = e.profile_read()
+    cls = [e.profile_read_class(c) for c in range(3)]
     e.profile_enable(False)
     tensor = prec == L.PREC_BF16
-    peak = pk["bf16_tflops_sustained"] if tensor else None
-    achieved = gemm_fl / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    step_ms = ms_dev / args.steps
+    names = ["fc::chain_kernel (fused tcgen05 MLP forward / backward chains)", "tc::gemm_kernel (tcgen05 split-K weight gradients)",
+             "sgemm_kernel (fp32 FFMA layers + gradients)"]
+    dom = max(range(3), key=lambda c: cls[c][0])
+    d_ms, d_n, d_fl = cls[dom]
+    achieved = d_fl / (d_ms * 1e-3) / 1e12 if d_ms > 0 else 0.0
+    all_ms = sum(c[0] for c in cls); all_fl = sum(c[2] for c in cls)
     roof = {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
             "frac": achieved / pk["bf16_tflops_sustained"], "traffic": None,
-            "kernel": "tcgen05 bf16 GEMMs (MLP layers + gradients)" if tensor else "sgemm_kernel fp32 FFMA (MLP layers + gradients)",
-            "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({pk_src})",
-            "gemm_share_of_step": gemm_ms / args.steps / (ms_dev / args.steps),
-            "launches_timed": gemm_n,
+            "kernel": names[dom],
+            "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({pk_src}); the kernel runs inside a long step",
+            "avg_launch_us": d_ms / max(d_n, 1) * 1e3, "launches_timed": d_n,
+            "algorithmic_flops_per_launch": d_fl / max(d_n, 1),
+            "share_of_step": d_ms / args.steps / step_ms,
+            "all_tensor_kernels": {"achieved": all_fl / (all_ms * 1e-3) / 1e12 if all_ms > 0 else 0.0,
+                                   "share_of_step": all_ms / args.steps / step_ms,
+                                   "classes": {names[c].split(" ")[0]: {"ms_per_step": cls[c][0] / args.steps, "launches_per_step": cls[c][1] // args.steps,
+                                                                        "tflops": cls[c][2] / (cls[c][0] * 1e-3) / 1e12 if cls[c][0] > 0 else 0.0}
+                                               for c in range(3) if cls[c][1] > 0}},
             "note": None if tensor else "fp32 parity mode runs on CUDA cores: FFMA peak is ~74.5 TFLOP/s (148 SM x 128 x 2 x 1.965 GHz); frac is still quoted against the bf16 tensor peak"}
 
     # ---- sampling half of the metric: walker2d, 40 env copies, T=20 chain, in-kernel Philox
@@ -309,24 +326,41 @@ def run_ours(args):
     samp_launches = (e.launch_count() - ls0) // 55
     samp_path = e.last_path()
     ms_s_e2e = timed(samp_e2e, 50, 5)
-    obsL = torch.rand(16384, d.Do, device=dev) * 2 - 1
+    BL = 148 * 128                                     # one 128-row tile per SM
+    obsL = torch.rand(BL, d.Do, device=dev) * 2 - 1
 
     def samp_large(i):
         cnt[0] += 1
         e.sample(obsL, seed=1, offset=cnt[0], return_chain=True)
 
-    ms_L = timed(samp_large, 3, 1)
+    ms_L = timed(samp_large, 5, 3)
     largeB_path = e.last_path()
     sampling = {
         "chunks_per_sec": world * N_ENVS * 50 / (ms_s * 1e-3), "us_per_rollout_step": ms_s / 50 * 1e3,
-        "launches_per_rollout_step": samp_launches, "path": {1: "persistent cluster kernel", 2: "layered fp32", 3: "layered tcgen05"}[samp_path],
+        "launches_per_rollout_step": samp_launches, "path": PATHS[samp_path],
         "n_envs_per_gpu": N_ENVS, "e2e_chunks_per_sec": world * N_ENVS * 50 / (ms_s_e2e * 1e-3),
         "e2e_us_per_rollout_step": ms_s_e2e / 50 * 1e3,
         "fp32_fma_frac": (N_ENVS * d.denoising_steps * Fa / (ms_s / 50 * 1e-3)) / 74.5e12,
-        "large_batch": {"rows_per_gpu": 16384, "chunks_per_sec": world * 16384 * 3 / (ms_L * 1e-3),
-                        "tflops": 16384 * d.denoising_steps * Fa * 3 / (ms_L * 1e-3) / 1e12,
-                        "path": {1: "persistent cluster kernel", 2: "layered fp32", 3: "layered tcgen05"}[largeB_path]},
+        "large_batch": {"rows_per_gpu": BL, "chunks_per_sec": world * BL * 5 / (ms_L * 1e-3),
+                        "tflops": BL * d.denoising_steps * Fa * 5 / (ms_L * 1e-3) / 1e12,
+                        "frac_of_bf16_sustained": BL * d.denoising_steps * Fa * 5 / (ms_L * 1e-3) / 1e12 / pk["bf16_tflops_sustained"],
+                        "launches_per_rollout_step": 1 if largeB_path in (1, 4) else None,
+                        "path": PATHS[largeB_path]},
     }
+
+    # ---- the strict-parity fp32 mode on the same workload (3 steps), reported beside the headline
+    fp32_mode = None
+    if tensor:
+        e32 = make_gpu_engine(L.PREC_FP32, local)
+        if world > 1:
+            e32.init_comm()
+        def dev_step32(i):
+            b = devb[i & 1]; mean, std = stats[i & 1]
+            return e32.ppo_step(*b, lr=lr, apply=True, n_global=n_global, adv_mean=mean, adv_std=std)
+        ms32 = timed(dev_step32, 3, 3)
+        fp32_mode = {"value": n_global * 3 / (ms32 * 1e-3), "unit": UNIT, "ms_per_step": ms32 / 3, "dtype": "fp32",
+                     "tflops": fps * N_ROWS / (ms32 / 3 * 1e-3) / 1e12, "frac_of_fp32_ffma_peak": fps * N_ROWS / (ms32 / 3 * 1e-3) / 74.5e12}
+        e32.close()
 
     # ---- CPU baseline (oracle port) on rank 0, bounded sample
     cpu = None
@@ -353,7 +387,7 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if tensor else "fp32", "data": "synthetic",
             "config": {"workload": f"{TASK}-v2 ft_ppo_diffusion_mlp PPO update: {N_ROWS} (env-step,k) rows per GPU "
                                    f"(obs 17, act 6, Ta 4, T 20, K 10, actor 512x3 ReLU, critic 256x3 Mish), fused loss+backward+AdamW",
-                       "global_rows": n_global, "parallelism": f"dp{world}", "precision": args.precision,
+                       "global_rows": n_global, "parallelism": f"dp{world}", "precision": args.precision if not tensor else "bf16 operands (tcgen05), fp32 accumulate/master weights/loss/AdamW",
                        "l2": "256 MB flush buffer written between timed steps; two alternating minibatches",
                        "flops_per_sample": fps},
             "clocks": clocks,
@@ -364,6 +398,7 @@ def run_ours(args):
             "roofline": roof,
             "cpu_baseline": cpu,
             "sampling": sampling,
+            "fp32_parity_mode": fp32_mode,
             "step_tflops": fps * N_ROWS / (ms_dev / args.steps * 1e-3) / 1e12,
         }
         print(json.dumps(line), flush=True)
@@ -378,7 +413,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("DPPO_BENCH_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("DPPO_BENCH_PRECISION", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -167,14 +167,15 @@ struct dppo_handle {
     // live GEMM timing (dppo_profile_*): event pairs recorded around GEMM-class launches
     int prof_on = 0;
     std::vector<cudaEvent_t> prof_ev;   // pairs
+    std::vector<int> prof_cls;          // kernel class of each pair: 0 fused chain, 1 tcgen05 GEMM, 2 FFMA SGEMM
     size_t prof_used = 0;
-    double prof_flops = 0, prof_ms_acc = 0; int64_t prof_launches = 0;
+    double prof_flops[3] = {0, 0, 0}, prof_ms_acc[3] = {0, 0, 0}; int64_t prof_launches[3] = {0, 0, 0};
 };
 
 int ws_reserve(dppo_handle* h, size_t bytes, cudaStream_t s);
 // profile bracket: call prof_begin before and prof_end after a GEMM-class launch
 void prof_begin(dppo_handle* h, cudaStream_t s);
-void prof_end(dppo_handle* h, cudaStream_t s, double flops);
+void prof_end(dppo_handle* h, cudaStream_t s, double flops, int cls);
 template <typename T> static inline T* ws_take(dppo_handle* h, size_t count) {
     size_t bytes = (count * sizeof(T) + 255) / 256 * 256;
     T* p = (T*)(h->ws.base + h->ws.used);

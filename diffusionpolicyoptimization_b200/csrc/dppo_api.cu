@@ -125,7 +125,7 @@ int ws_reserve(dppo_handle* h, size_t bytes, cudaStream_t s) {
 static int prof_flush(dppo_handle* h) {
     for (size_t i = 0; i + 1 < h->prof_used; i += 2) {
         float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, h->prof_ev[i], h->prof_ev[i + 1]) == cudaSuccess) h->prof_ms_acc += ms;
+        if (cudaEventElapsedTime(&ms, h->prof_ev[i], h->prof_ev[i + 1]) == cudaSuccess) h->prof_ms_acc[h->prof_cls[i / 2]] += ms;
     }
     h->prof_used = 0;
     return 0;
@@ -134,26 +134,38 @@ void prof_begin(dppo_handle* h, cudaStream_t s) {
     if (!h->prof_on) return;
     if (h->prof_used + 2 > h->prof_ev.size()) {
         if (h->prof_ev.size() >= 8192) { cudaDeviceSynchronize(); prof_flush(h); }
-        else for (int i = 0; i < 2; ++i) { cudaEvent_t e; cudaEventCreate(&e); h->prof_ev.push_back(e); }
+        else { for (int i = 0; i < 2; ++i) { cudaEvent_t e; cudaEventCreate(&e); h->prof_ev.push_back(e); } h->prof_cls.push_back(0); }
     }
     cudaEventRecord(h->prof_ev[h->prof_used], s);
 }
-void prof_end(dppo_handle* h, cudaStream_t s, double flops) {
+void prof_end(dppo_handle* h, cudaStream_t s, double flops, int cls) {
     if (!h->prof_on) return;
     cudaEventRecord(h->prof_ev[h->prof_used + 1], s);
-    h->prof_used += 2; h->prof_launches += 1; h->prof_flops += flops;
+    h->prof_cls[h->prof_used / 2] = cls;
+    h->prof_used += 2; h->prof_launches[cls] += 1; h->prof_flops[cls] += flops;
 }
 extern "C" int dppo_profile_enable(dppo_handle* h, int on) {
     if (!h) DPPO_FAIL(-1, "null handle");
     CUDA_TRY(cudaSetDevice(h->device)); CUDA_TRY(cudaDeviceSynchronize());
-    h->prof_used = 0; h->prof_flops = 0; h->prof_ms_acc = 0; h->prof_launches = 0; h->prof_on = on ? 1 : 0;
+    h->prof_used = 0;
+    for (int c = 0; c < 3; ++c) { h->prof_flops[c] = 0; h->prof_ms_acc[c] = 0; h->prof_launches[c] = 0; }
+    h->prof_on = on ? 1 : 0;
+    return 0;
+}
+extern "C" int dppo_profile_read_class(dppo_handle* h, int cls, double* ms, int64_t* launches, double* flops) {
+    if (!h || cls < 0 || cls > 2) DPPO_FAIL(-1, "dppo_profile_read_class: bad arguments");
+    CUDA_TRY(cudaSetDevice(h->device)); CUDA_TRY(cudaDeviceSynchronize());
+    prof_flush(h);
+    if (ms) *ms = h->prof_ms_acc[cls]; if (launches) *launches = h->prof_launches[cls]; if (flops) *flops = h->prof_flops[cls];
     return 0;
 }
 extern "C" int dppo_profile_read(dppo_handle* h, double* ms, int64_t* launches, double* flops) {
     if (!h) DPPO_FAIL(-1, "null handle");
     CUDA_TRY(cudaSetDevice(h->device)); CUDA_TRY(cudaDeviceSynchronize());
     prof_flush(h);
-    if (ms) *ms = h->prof_ms_acc; if (launches) *launches = h->prof_launches; if (flops) *flops = h->prof_flops;
+    if (ms) *ms = h->prof_ms_acc[0] + h->prof_ms_acc[1] + h->prof_ms_acc[2];
+    if (launches) *launches = h->prof_launches[0] + h->prof_launches[1] + h->prof_launches[2];
+    if (flops) *flops = h->prof_flops[0] + h->prof_flops[1] + h->prof_flops[2];
     return 0;
 }
 
@@ -183,7 +195,7 @@ static int gemm(dppo_handle* h, cudaStream_t s, bool a_km, bool b_nk, GemmP p, i
         else if (a_km && !b_nk) SG(true, false, 32); else SG(true, true, 32);
     }
 #undef SG
-    prof_end(h, s, 2.0 * (double)p.M * (double)p.N * (double)p.K);
+    prof_end(h, s, 2.0 * (double)p.M * (double)p.N * (double)p.K, 2);
     KLAUNCH(h); KCHECK();
     return splits;
 }

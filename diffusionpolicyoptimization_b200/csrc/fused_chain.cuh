@@ -667,7 +667,7 @@ static int launch_chain_t(dppo_handle* h, cudaStream_t s, const Maps& maps, cons
     const int grid = ntiles < h->sm_count ? ntiles : h->sm_count;
     prof_begin(h, s);
     kern<<<grid, FTHREADS, chain_smem_bytes<H>(), s>>>(maps, p);
-    prof_end(h, s, flops);
+    prof_end(h, s, flops, 0);
     h->launches++; h->tc_launches++; h->fused_launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) DPPO_FAIL(-3, "fused chain launch failed: %s", cudaGetErrorString(e));

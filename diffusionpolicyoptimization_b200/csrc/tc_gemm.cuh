@@ -399,6 +399,7 @@ struct Gemm {
     Operand A, A2, B;      // A2.ptr == nullptr: no K concatenation
     int M, N;              // output extents (M rows of A, N rows/cols of B)
     int splits;            // split-K factor (fp32 partial outputs)
+    double alg_flops;      // algorithmic flops (un-padded dims) for the live roofline; 0 = use the padded GEMM shape
     Epi epi;
 };
 
@@ -427,7 +428,7 @@ static int launch_t(dppo_handle* h, cudaStream_t s, const Gemm& g) {
     const int grid = tiles < h->sm_count ? tiles : h->sm_count;
     prof_begin(h, s);
     kern<<<grid, NUM_THREADS, smem_bytes<BN>(), s>>>(tA, tA2, tB, p);
-    prof_end(h, s, 2.0 * (double)g.M * (double)g.N * (double)(A.k + (g.A2.ptr ? g.A2.k : 0)));
+    prof_end(h, s, g.alg_flops > 0 ? g.alg_flops : 2.0 * (double)g.M * (double)g.N * (double)(A.k + (g.A2.ptr ? g.A2.k : 0)), 1);
     h->launches++; h->tc_launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) DPPO_FAIL(-3, "tc gemm launch failed: %s", cudaGetErrorString(e));

@@ -321,16 +321,16 @@ static inline int tc_nblk(size_t n, int b) { return (int)((n + b - 1) / b); }
 
 // ------------------------------------------------------------------ fused layer-chain programs (fused_chain.cuh)
 // one residual MLP as the fused kernel sees it
-struct FcNet { int net, H, act1 /*1 ReLU, 2 Mish*/, NO; const float *b0, *b1, *b2, *b3; };
+struct FcNet { int net, H, act1 /*1 ReLU, 2 Mish*/, NO, din /*un-padded input width*/; const float *b0, *b1, *b2, *b3; };
 static FcNet fc_actor_net(const dppo_handle* h, int net) {
     const Geom& g = h->g; const float* w = h->net_w[net];
-    FcNet n; n.net = net; n.H = g.H; n.act1 = h->cfg.actor_act + 1; n.NO = g.A;
+    FcNet n; n.net = net; n.H = g.H; n.act1 = h->cfg.actor_act + 1; n.NO = g.A; n.din = g.Din;
     n.b0 = nullptr; n.b1 = w + g.ao.b1; n.b2 = w + g.ao.b2; n.b3 = w + g.ao.b3;    // b_in rides in W0's one-hot rows (bt table)
     return n;
 }
 static FcNet fc_critic_net(const dppo_handle* h) {
     const Geom& g = h->g; const float* w = h->net_w[DPPO_NET_CRITIC];
-    FcNet n; n.net = DPPO_NET_CRITIC; n.H = g.Hc; n.act1 = h->cfg.critic_act + 1; n.NO = 1;
+    FcNet n; n.net = DPPO_NET_CRITIC; n.H = g.Hc; n.act1 = h->cfg.critic_act + 1; n.NO = 1; n.din = g.Do;
     n.b0 = w + g.co.bin; n.b1 = w + g.co.b1; n.b2 = h->tc->net[DPPO_NET_CRITIC].bias2; n.b3 = w + g.co.b3;
     return n;
 }
@@ -361,7 +361,8 @@ static void fc_fwd_layers(const FcNet& n, int wbase, fc::Layer* L) {
     L[2].a_src = 2; L[2].wmap = wbase; L[2].wrow_h0 = H; L[2].n = H; L[2].bias = n.b2; L[2].h0_last = 1;
     L[3].a_src = 1; L[3].wmap = wbase + 2; L[3].n = 64; L[3].bias = n.b3;
 }
-static double fc_fwd_flops(double H, double rows) { return 2.0 * rows * (64 * H + H * H + (H + 64) * H + H * 64); }
+// algorithmic flops (un-padded dims, time-MLP excluded): forward F = 2 (din H + 2 H^2 + H NO) per row
+static double fc_fwd_flops(const FcNet& n, double rows) { const double H = n.H; return 2.0 * rows * (n.din * H + 2.0 * H * H + H * n.NO); }
 static void fc_common(const dppo_handle* h, fc::Params& p, int N, int NO) {
     const Geom& g = h->g;
     memset(&p, 0, sizeof(p));
@@ -379,7 +380,7 @@ static int fc_infer(dppo_handle* h, cudaStream_t s, const FcNet& n, const bf16* 
     p.nlayers = 4; p.final_mode = mode; p.h0_from_tma = 1;
     fc_fwd_layers(n, 1, p.L[0]);
     p.out = out; p.prev = prev; p.next = next; p.chains = chains; p.trow = trow;
-    return fc::launch_chain(h, s, n.H, maps, p, fc_fwd_flops(n.H, N));
+    return fc::launch_chain(h, s, n.H, maps, p, fc_fwd_flops(n, N));
 }
 static int fc_actor_infer(dppo_handle* h, cudaStream_t s, int net, const bf16* h0, int N, int mode, float* out,
                           const float* prev, const float* next, const float* chains, const int* trow) {
@@ -407,7 +408,7 @@ static int fc_train_fwd(dppo_handle* h, cudaStream_t s, const FcNet& n, const bf
         p.L[0][0].gate_store_map = 7; p.L[0][1].gate_store_map = 8;
     }
     p.out = out;
-    return fc::launch_chain(h, s, H, maps, p, fc_fwd_flops(H, N));
+    return fc::launch_chain(h, s, H, maps, p, fc_fwd_flops(n, N));
 }
 // backward chain: dv = dout W3^T, dh1 = (dv W2^T) . act'(h1), du = (dh1 W1^T) . act'(u)
 // (du excludes the residual path: dW0 adds h0^T dv)
@@ -438,7 +439,7 @@ static int fc_bwd(dppo_handle* h, cudaStream_t s, const FcNet& n, const bf16* do
         DPPO_TRY(fc::rowtile_map(&maps.m[8], g0, N, H));
         L[1].gate_load_map = 7; L[2].gate_load_map = 8;
     }
-    return fc::launch_chain(h, s, H, maps, p, 2.0 * N * ((double)64 * H + 2.0 * H * H));
+    return fc::launch_chain(h, s, H, maps, p, 2.0 * N * ((double)n.NO * H + 2.0 * H * H));
 }
 // VPGDiffusion.call for large batches: the whole T-step chain in ONE launch
 static int fc_sample(dppo_handle* h, cudaStream_t s, const float* obs, int B, int use_base, SampleHyper hp, uint64_t seed,
@@ -453,7 +454,7 @@ static int fc_sample(dppo_handle* h, cudaStream_t s, const float* obs, int B, in
     fc_fwd_layers(nf, 4, p.L[1]);
     p.obs = obs; p.xT = xT; p.noise = noise; p.actions = actions; p.chains_out = chains; p.hp = hp; p.use_base_policy = use_base;
     p.seed = seed; p.offset = offset; p.row_offset = row_offset;
-    return fc::launch_chain(h, s, nb.H, maps, p, fc_fwd_flops(nb.H, B) * h->g.T);
+    return fc::launch_chain(h, s, nb.H, maps, p, fc_fwd_flops(nb, B) * h->g.T);
 }
 
 // ------------------------------------------------------------------ GEMM helpers
@@ -475,7 +476,7 @@ struct TcMlp {
     float* out;                            // [N][NO] fp32
     bf16 *dv, *dh1, *du;                   // backward
     uint32_t *m0, *m1;                     // fused chain: ReLU bit masks [N][H/32] of layer 0 / block.l1
-    int fused, net;                        // fused: the actor runs on the fused layer-chain kernel
+    int fused, net, din;                   // fused: runs on the fused layer-chain kernel; din: un-padded input width
 };
 static size_t tc_mlp_ws_bytes(int N, int H, bool mish, bool bwd) {
     size_t one = ws_bytes((size_t)N * H, sizeof(bf16));
@@ -527,15 +528,17 @@ static int tc_splits_for(const dppo_handle* h, int M, int N, int rows) {
 // Default: every split CTA accumulates its tile into `out` with red.global.add.f32 (out must be zeroed beforehand; the
 // summation order, hence the last bits, vary run to run).  DPPO_DETERMINISTIC=1: partial tiles + a fixed-order reduction.
 static int tc_dw(dppo_handle* h, cudaStream_t s, const bf16* X, int M, const bf16* D, int Nd, int rows, float* part,
-                 float* out, int out_rows, int out_cols, int ld_out, const bf16* D2 = nullptr) {
+                 float* out, int out_rows, int out_cols, int ld_out, const bf16* D2 = nullptr, int alg_rows_in = -1) {
+    const int alg_rows = alg_rows_in >= 0 ? alg_rows_in : out_rows;
     tc::Gemm g = gemm_of(opMN(X, M, rows, M), opMN(D, Nd, rows, Nd), M, Nd);
     g.splits = tc_splits_for(h, M, Nd, rows);
+    g.alg_flops = 2.0 * (double)rows * (double)alg_rows * (double)out_cols;
     if (!h->deterministic) {
         g.epi.M = out_rows; g.epi.N = out_cols;
         g.epi.out_f32 = out; g.epi.ld_f32 = ld_out; g.epi.f32_atomic = 1;
         int S = tc::launch(h, s, g);
         if (S < 0) return S;
-        if (D2) { g.B = opMN(D2, Nd, rows, Nd); S = tc::launch(h, s, g); if (S < 0) return S; }
+        if (D2) { g.B = opMN(D2, Nd, rows, Nd); g.alg_flops = 1.0; S = tc::launch(h, s, g); if (S < 0) return S; }   // residual path: not algorithmic work
         return 0;
     }
     g.epi.out_f32 = part; g.epi.ld_f32 = Nd; g.epi.split_stride = (size_t)M * Nd;
@@ -581,7 +584,7 @@ static int tc_mlp_backward(dppo_handle* h, cudaStream_t s, const TcMlp& m, const
         DPPO_TRY(tc_dw(h, s, m.v, H, doutb, 64, N, part, gnet + ow3, H, m.NO, m.NO));
         DPPO_TRY(tc_dw(h, s, m.a1, H, m.dv, H, N, part, gnet + ow2, H, H, H));
         DPPO_TRY(tc_dw(h, s, m.a0, H, m.dh1, H, N, part, gnet + ow1, H, H, H));
-        DPPO_TRY(tc_dw(h, s, m.h0, KP0, m.du, H, N, part, dw0, KP0, H, H, m.dv));
+        DPPO_TRY(tc_dw(h, s, m.h0, KP0, m.du, H, N, part, dw0, KP0, H, H, m.dv, m.din));
         return 0;
     }
     // dv = dout W3^T
@@ -602,7 +605,7 @@ static int tc_mlp_backward(dppo_handle* h, cudaStream_t s, const TcMlp& m, const
     DPPO_TRY(tc_dw(h, s, m.v, H, doutb, 64, N, part, gnet + ow3, H, m.NO, m.NO));
     DPPO_TRY(tc_dw(h, s, m.a1, H, m.dv, H, N, part, gnet + ow2, H, H, H));
     DPPO_TRY(tc_dw(h, s, m.a0, H, m.dh1, H, N, part, gnet + ow1, H, H, H));
-    DPPO_TRY(tc_dw(h, s, m.h0, KP0, m.du, H, N, part, dw0, KP0, H, H));
+    DPPO_TRY(tc_dw(h, s, m.h0, KP0, m.du, H, N, part, dw0, KP0, H, H, nullptr, m.din));
     // bias gradients of block.l1 / block.l2 (the input-layer bias comes out of dw0's constant rows)
     DPPO_TRY(tc_colsum(h, s, m.dv, N, H, part, gnet + ob2));
     DPPO_TRY(tc_colsum(h, s, m.dh1, N, H, part, gnet + ob1));
@@ -612,13 +615,13 @@ static int tc_mlp_backward(dppo_handle* h, cudaStream_t s, const TcMlp& m, const
 static void tc_actor_mlp(const dppo_handle* h, int net, TcMlp& m) {
     const Geom& g = h->g; const float* w = h->net_w[net];
     m.W = &h->tc->net[net]; m.H = g.H; m.NO = g.A; m.act1 = h->cfg.actor_act + 1; m.KP0 = h->tc->KP0;
-    m.fused = fc_ok(h) ? 1 : 0; m.net = net;
+    m.fused = fc_ok(h) ? 1 : 0; m.net = net; m.din = g.Din;
     m.b0 = nullptr; m.b1 = w + g.ao.b1; m.b2 = w + g.ao.b2; m.b3 = w + g.ao.b3;
 }
 static void tc_critic_mlp(const dppo_handle* h, TcMlp& m) {
     const Geom& g = h->g; const float* w = h->net_w[DPPO_NET_CRITIC];
     m.W = &h->tc->net[DPPO_NET_CRITIC]; m.H = g.Hc; m.NO = 1; m.act1 = h->cfg.critic_act + 1; m.KP0 = h->tc->KP0;
-    m.fused = fc_critic_ok(h) ? 1 : 0; m.net = DPPO_NET_CRITIC;
+    m.fused = fc_critic_ok(h) ? 1 : 0; m.net = DPPO_NET_CRITIC; m.din = g.Do;
     m.b0 = w + g.co.bin; m.b1 = w + g.co.b1; m.b2 = m.W->bias2; m.b3 = w + g.co.b3;
 }
 

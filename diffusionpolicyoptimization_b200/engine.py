@@ -246,6 +246,12 @@ class Engine:
     def profile_enable(self, on: bool = True):
         L.check(self.lib.dppo_profile_enable(self.h, int(on)), "dppo_profile_enable")
 
+    def profile_read_class(self, cls: int):
+        """-> (ms, launches, algorithmic flops) of one kernel class: 0 fused chain, 1 tcgen05 GEMM, 2 FFMA SGEMM."""
+        ms, n, fl = C.c_double(0), C.c_int64(0), C.c_double(0)
+        L.check(self.lib.dppo_profile_read_class(self.h, int(cls), C.byref(ms), C.byref(n), C.byref(fl)), "dppo_profile_read_class")
+        return float(ms.value), int(n.value), float(fl.value)
+
     def profile_read(self):
         """-> (gemm_ms, gemm_launches, gemm_flops) accumulated since profile_enable(True)."""
         ms, n, fl = C.c_double(0), C.c_int64(0), C.c_double(0)
