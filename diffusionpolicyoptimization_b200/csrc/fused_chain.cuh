@@ -95,12 +95,15 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 // Mish and its derivative from one exponential: with n = e^x, w = n^2 + 2n:  tanh(softplus(x)) = w / (w + 2),
 // d/dx = 4 n (n + 1) / (w + 2)^2.  (tensor path only; the fp32 parity path keeps the literal x * tanh(softplus(x)))
 __device__ __forceinline__ void mish_and_grad(float x, float& y, float& g) {
-    const float n = __expf(fminf(x, 20.f));
-    const float w = n * (n + 2.f);
-    const float r = __fdividef(1.f, w + 2.f);
+    // flush-to-zero approximations without the denormal range fix-ups nvcc adds around __expf / __fdividef; the
+    // clamp at 20 keeps w finite and the formulas already give y = x, g = 1 to fp32 precision there
+    float n, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(n) : "f"(fminf(x, 20.f) * 1.4426950408889634f));
+    const float w = fmaf(n, n, n + n);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(w + 2.f));
     const float f = w * r;
-    y = x > 20.f ? x : x * f;
-    g = x > 20.f ? 1.f : f + x * (4.f * n * (n + 1.f)) * r * r;
+    y = x * f;
+    g = fmaf(4.f * x, fmaf(n, n, n) * r * r, f);
 }
 // One lane of a converged warp (elect.sync).  The issue warps keep warp-uniform control flow and elect a lane only
 // around the tcgen05 / TMA instructions: inside a lane-divergent branch (`if (lane == 0)`) nvcc wraps every
@@ -489,16 +492,15 @@ __global__ void __launch_bounds__(FTHREADS, 1) chain_kernel(const __grid_constan
                                 const uint32_t toff = (uint32_t)(n0 >> 6) * 16384u + (uint32_t)rloc * 128u;
                                 const int cbg = (n0 & 63) >> 3;
                                 if (mish) {
-                                    // post-activation -> X (below), gate = mish'(pre) -> G
-                                    float gt[32];
+                                    // post-activation -> X (below), gate = mish'(pre) -> G; eight columns at a time keeps the live set small
 #pragma unroll
-                                    for (int j = 0; j < 32; ++j) { float y; mish_and_grad(v[j], y, gt[j]); v[j] = y; }
-                                    if (L.gate_store_map >= 0) {
+                                    for (int q = 0; q < 4; ++q) {
+                                        float gt[8];
 #pragma unroll
-                                        for (int q = 0; q < 4; ++q)
+                                        for (int j = 0; j < 8; ++j) { float y; mish_and_grad(v[q * 8 + j], y, gt[j]); v[q * 8 + j] = y; }
+                                        if (L.gate_store_map >= 0)
                                             st_shared_v4(g_addr + toff + (uint32_t)(((cbg + q) ^ (rloc & 7)) << 4),
-                                                         pack_bf16(gt[q * 8 + 0], gt[q * 8 + 1]), pack_bf16(gt[q * 8 + 2], gt[q * 8 + 3]),
-                                                         pack_bf16(gt[q * 8 + 4], gt[q * 8 + 5]), pack_bf16(gt[q * 8 + 6], gt[q * 8 + 7]));
+                                                         pack_bf16(gt[0], gt[1]), pack_bf16(gt[2], gt[3]), pack_bf16(gt[4], gt[5]), pack_bf16(gt[6], gt[7]));
                                     }
                                 }
                                 if (gate_in) {

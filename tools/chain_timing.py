@@ -28,6 +28,7 @@ def timed(fn, n=3):
     return a.elapsed_time(c) / n
 print(f"logprobs N={N}: {timed(lambda: e.logprobs_subsample(b[0], b[1], b[2], b[3])):.3f} ms"); report("logprobs")
 print(f"sample B={B}: {timed(lambda: e.sample(obs, seed=1, offset=2)):.3f} ms"); report("sample")
+print(f"value N={N}: {timed(lambda: e.value(b[0])):.3f} ms"); report("critic forward (infer)")
 ms = timed(lambda: e.ppo_step(*b, lr=1e-4, apply=False, adv_mean=0.0, adv_std=1.0))
 print(f"ppo N={N}: {ms:.3f} ms"); report("ppo(last chain = actor bwd)")
 e.close()
