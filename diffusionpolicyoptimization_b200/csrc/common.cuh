@@ -153,6 +153,7 @@ struct dppo_handle {
     // pinned + device staging for *_host calls
     char* pin = nullptr; size_t pin_cap = 0;
     char* dstage = nullptr; size_t dstage_cap = 0;
+    cudaStream_t copy_stream = nullptr; cudaEvent_t copy_ev[9];   // chunked H2D / compute overlap of dppo_ppo_step_host
     // NCCL
     void* comm = nullptr; int rank = 0, world = 1;
     int64_t launches = 0;

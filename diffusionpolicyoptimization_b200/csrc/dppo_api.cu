@@ -291,6 +291,7 @@ extern "C" void dppo_destroy(dppo_handle* h) {
     for (int i = 0; i < 2; ++i) { cudaFree(h->opt[i].m); cudaFree(h->opt[i].v); }
     for (int net = 0; net < 4; ++net) { ActorDerived& d = h->ad[net]; cudaFree(d.sinemb); cudaFree(d.thpre); cudaFree(d.temb); cudaFree(d.bt); cudaFree(d.w0p); }
     if (h->ws.base) cudaFree(h->ws.base);
+    if (h->copy_stream) { cudaStreamDestroy(h->copy_stream); for (int i = 0; i < 9; ++i) cudaEventDestroy(h->copy_ev[i]); }
     if (h->pin) cudaFreeHost(h->pin);
     if (h->dstage) cudaFree(h->dstage);
     delete h;
@@ -773,6 +774,21 @@ static int adam_apply(dppo_handle* h, cudaStream_t s, int opt, float* w, const f
 }
 
 // ------------------------------------------------------------------ PPO step
+static int prep_net(dppo_handle* h, int net, cudaStream_t s);
+// all-reduce (if a communicator is attached) + AdamW + derived-table refresh + metric / gradient read-out
+static int ppo_apply_tail(dppo_handle* h, cudaStream_t s, float lr, int apply, float* metrics8, float* grads_out) {
+    const size_t nA = h->g.ao.n, nC = h->g.co.n; float* gr = h->grads;
+    if (apply) {
+        DPPO_TRY(allreduce_sum(h, gr, nA + nC + 8, s));
+        // actor_ft and critic are contiguous in `params` and share one optimizer (train_ppo_diffusion_agent.py:354-356)
+        DPPO_TRY(adam_apply(h, s, DPPO_OPT_FINETUNE, h->net_w[DPPO_NET_ACTOR_FT], gr, nA + nC, lr, h->cfg.weight_decay));
+        DPPO_TRY(prep_net(h, DPPO_NET_ACTOR_FT, s));
+        DPPO_TRY(prep_net(h, DPPO_NET_CRITIC, s));
+    }
+    if (metrics8) CUDA_TRY(cudaMemcpyAsync(metrics8, gr + nA + nC, 8 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    if (grads_out) CUDA_TRY(cudaMemcpyAsync(grads_out, gr, (nA + nC) * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    return 0;
+}
 extern "C" int dppo_ppo_step(dppo_handle* h, const float* obs, const float* prev, const float* nxt,
                              const int32_t* inds, const float* returns, const float* oldvalues,
                              const float* advantages, const float* oldlogp, int N, int64_t N_global,
@@ -802,7 +818,7 @@ extern "C" int dppo_ppo_step(dppo_handle* h, const float* obs, const float* prev
         double* bsum = ws_take<double>(h, (size_t)nlb * 5);
 
         make_trow_kernel<<<nblk(N, 256), 256, 0, s>>>(inds, N, g.K, 0, trow); KLAUNCH(h); KCHECK();
-        if (adv_std < 0.f) { adv_stats_kernel<<<1, 256, 0, s>>>(advantages, N, h->scalars); KLAUNCH(h); KCHECK(); }
+        if (adv_std < 0.f) { adv_stats_kernel<<<1, 1024, 0, s>>>(advantages, N, h->scalars); KLAUNCH(h); KCHECK(); }
         else { set_scalars_kernel<<<1, 1, 0, s>>>(h->scalars, adv_mean, adv_std); KLAUNCH(h); KCHECK(); }
         DPPO_TRY(actor_fwd_fp32(h, s, DPPO_NET_ACTOR_FT, prev, obs, 1, N, trow, 0, fa));
         DPPO_TRY(critic_fwd_fp32(h, s, obs, N, fc));
@@ -818,16 +834,7 @@ extern "C" int dppo_ppo_step(dppo_handle* h, const float* obs, const float* prev
         DPPO_TRY(actor_bwd_fp32(h, s, DPPO_NET_ACTOR_FT, fa, deps, N, trow, ba, Ga, dw0a, gr));
         DPPO_TRY(critic_bwd_fp32(h, s, fc, dval, N, bc, Gc, dw0c, gr + nA));
     }
-    if (apply) {
-        DPPO_TRY(allreduce_sum(h, gr, nA + nC + 8, s));
-        // actor_ft and critic are contiguous in `params` and share one optimizer (train_ppo_diffusion_agent.py:354-356)
-        DPPO_TRY(adam_apply(h, s, DPPO_OPT_FINETUNE, h->net_w[DPPO_NET_ACTOR_FT], gr, nA + nC, lr, h->cfg.weight_decay));
-        DPPO_TRY(prep_net(h, DPPO_NET_ACTOR_FT, s));
-        DPPO_TRY(prep_net(h, DPPO_NET_CRITIC, s));
-    }
-    if (metrics8) CUDA_TRY(cudaMemcpyAsync(metrics8, gr + nA + nC, 8 * sizeof(float), cudaMemcpyDeviceToDevice, s));
-    if (grads_out) CUDA_TRY(cudaMemcpyAsync(grads_out, gr, (nA + nC) * sizeof(float), cudaMemcpyDeviceToDevice, s));
-    return 0;
+    return ppo_apply_tail(h, s, lr, apply, metrics8, grads_out);
 }
 
 extern "C" int dppo_ppo_step_host(dppo_handle* h, const float* obs, const float* prev, const float* nxt,
@@ -843,6 +850,46 @@ extern "C" int dppo_ppo_step_host(dppo_handle* h, const float* obs, const float*
     float* d_prev = (float*)p; p += b_x; float* d_next = (float*)p; p += b_x; float* d_olp = (float*)p; p += b_x;
     int* d_inds = (int*)p; p += b_n; float* d_ret = (float*)p; p += b_n; float* d_val = (float*)p; p += b_n; float* d_adv = (float*)p; p += b_n;
     float* d_met = (float*)p;
+    // tensor mode: chunked pipeline - the H2D copy of chunk c+1 (copy stream) overlaps the compute of chunk c
+    const int chunk_rows = (tc_eligible(h, N) && fc_ok(h) && fc_critic_ok(h) && !h->deterministic) ? tc_ppo_pipeline_chunk_rows(h, N) : 0;
+    if (chunk_rows > 0) {
+        if (!obs || !prev || !nxt || !inds || !returns || !oldvalues || !advantages || !oldlogp || N_global < N) DPPO_FAIL(-1, "dppo_ppo_step_host: bad arguments");
+        if (adv_std < 0.f && N_global != N) DPPO_FAIL(-1, "dppo_ppo_step_host: global advantage statistics are required when rows are sharded");
+        if (!h->copy_stream) {
+            CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+            for (int i = 0; i < 9; ++i) CUDA_TRY(cudaEventCreateWithFlags(&h->copy_ev[i], cudaEventDisableTiming));
+        }
+        cudaStream_t cs = h->copy_stream;
+        // staging is free: the previous *_host call synchronised `s`; the copy stream must still not overtake work queued on s
+        CUDA_TRY(cudaEventRecord(h->copy_ev[8], s));
+        CUDA_TRY(cudaStreamWaitEvent(cs, h->copy_ev[8], 0));
+        DPPO_TRY(tc_ppo_begin(h, s, N, chunk_rows, N_global));
+        const int CR = tc_plan(h).chunk_rows, nchunks = tc_plan(h).nchunks;
+        if (nchunks > 8) DPPO_FAIL(-7, "dppo_ppo_step_host: too many pipeline chunks");
+        CUDA_TRY(cudaMemcpyAsync(d_adv, advantages, (size_t)N * 4, cudaMemcpyHostToDevice, cs));
+        for (int c = 0; c < nchunks; ++c) {
+            const size_t r0 = (size_t)c * CR; if (r0 >= (size_t)N) break;
+            const size_t n = (size_t)N - r0 < (size_t)CR ? (size_t)N - r0 : (size_t)CR;
+            CUDA_TRY(cudaMemcpyAsync(d_obs + r0 * g.Do, obs + r0 * g.Do, n * g.Do * 4, cudaMemcpyHostToDevice, cs));
+            CUDA_TRY(cudaMemcpyAsync(d_prev + r0 * g.A, prev + r0 * g.A, n * g.A * 4, cudaMemcpyHostToDevice, cs));
+            CUDA_TRY(cudaMemcpyAsync(d_next + r0 * g.A, nxt + r0 * g.A, n * g.A * 4, cudaMemcpyHostToDevice, cs));
+            CUDA_TRY(cudaMemcpyAsync(d_olp + r0 * g.A, oldlogp + r0 * g.A, n * g.A * 4, cudaMemcpyHostToDevice, cs));
+            CUDA_TRY(cudaMemcpyAsync(d_inds + r0, inds + r0, n * 4, cudaMemcpyHostToDevice, cs));
+            CUDA_TRY(cudaMemcpyAsync(d_ret + r0, returns + r0, n * 4, cudaMemcpyHostToDevice, cs));
+            CUDA_TRY(cudaMemcpyAsync(d_val + r0, oldvalues + r0, n * 4, cudaMemcpyHostToDevice, cs));
+            CUDA_TRY(cudaEventRecord(h->copy_ev[c], cs));
+        }
+        for (int c = 0; c < nchunks; ++c) {
+            const size_t r0 = (size_t)c * CR; if (r0 >= (size_t)N) break;
+            const int n = (int)((size_t)N - r0 < (size_t)CR ? (size_t)N - r0 : (size_t)CR);
+            CUDA_TRY(cudaStreamWaitEvent(s, h->copy_ev[c], 0));
+            if (c == 0) DPPO_TRY(tc_ppo_adv_stats(h, s, d_adv, N, adv_mean, adv_std));     // the advantages were copied first
+            DPPO_TRY(tc_ppo_chunk(h, s, c, d_obs + r0 * g.Do, d_prev + r0 * g.A, d_next + r0 * g.A, d_inds + r0, d_ret + r0, d_val + r0,
+                                  d_adv + r0, d_olp + r0 * g.A, n));
+        }
+        DPPO_TRY(tc_ppo_finish(h, s));
+        DPPO_TRY(ppo_apply_tail(h, s, lr, apply, d_met, nullptr));
+    } else {
     CUDA_TRY(cudaMemcpyAsync(d_obs, obs, (size_t)N * g.Do * 4, cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaMemcpyAsync(d_prev, prev, (size_t)N * g.A * 4, cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaMemcpyAsync(d_next, nxt, (size_t)N * g.A * 4, cudaMemcpyHostToDevice, s));
@@ -853,6 +900,7 @@ extern "C" int dppo_ppo_step_host(dppo_handle* h, const float* obs, const float*
     CUDA_TRY(cudaMemcpyAsync(d_adv, advantages, (size_t)N * 4, cudaMemcpyHostToDevice, s));
     DPPO_TRY(dppo_ppo_step(h, d_obs, d_prev, d_next, d_inds, d_ret, d_val, d_adv, d_olp, N, N_global, adv_mean, adv_std, lr, apply,
                            d_met, nullptr, st));
+    }
     if (metrics8_host) CUDA_TRY(cudaMemcpyAsync(metrics8_host, d_met, 8 * sizeof(float), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     return 0;

@@ -409,12 +409,12 @@ struct PpoHyper {
     float inv_nglobal;
 };
 __global__ void adv_stats_kernel(const float* __restrict__ adv, int N, float* __restrict__ out /*mean,std*/) {
-    __shared__ double s1[256], s2[256];
+    __shared__ double s1[1024], s2[1024];
     double a = 0, b = 0;
     for (int i = threadIdx.x; i < N; i += blockDim.x) { double v = adv[i]; a += v; b += v * v; }
     s1[threadIdx.x] = a; s2[threadIdx.x] = b;
     __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
+    for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
         if (threadIdx.x < o) { s1[threadIdx.x] += s1[threadIdx.x + o]; s2[threadIdx.x] += s2[threadIdx.x + o]; }
         __syncthreads();
     }
@@ -582,15 +582,25 @@ __global__ void time_backward_kernel(const float* __restrict__ w, ActorOff o, in
     float* dte = sm;                 // [T][td]
     float* dh = dte + T * td;        // [T][2td]
     const int tid = threadIdx.x, nt = blockDim.x;
-    for (int c = tid; c < H; c += nt) {             // db_in and dW_in[A+j]
-        float s = 0.f;
-        for (int t = 0; t < T; ++t) s += G[(size_t)t * H + c];
-        g[o.bin + c] = s;
-        for (int j = 0; j < td; ++j) {
-            float a = 0.f;
-            for (int t = 0; t < T; ++t) a = fmaf(temb[t * td + j], G[(size_t)t * H + c], a);
-            g[o.win + (size_t)(A + j) * H + c] = a;
+    // gridDim.x == 1: one block does everything.  Otherwise block 0 does the time-MLP part and blocks 1.. split the
+    // per-column part (db_in and dW_in[A+j]) 128 columns each, 4 threads per column over j.
+    if (gridDim.x == 1 || blockIdx.x > 0) {
+        const int c0 = gridDim.x == 1 ? 0 : (blockIdx.x - 1) * 128, c1 = gridDim.x == 1 ? H : min(H, c0 + 128);
+        const int lanes = gridDim.x == 1 ? 1 : 4;            // threads per column
+        for (int i = tid; i < (c1 - c0) * lanes; i += nt) {
+            const int c = c0 + i / lanes, part = i % lanes;
+            if (part == 0) {
+                float s = 0.f;
+                for (int t = 0; t < T; ++t) s += G[(size_t)t * H + c];
+                g[o.bin + c] = s;
+            }
+            for (int j = part; j < td; j += lanes) {
+                float a = 0.f;
+                for (int t = 0; t < T; ++t) a = fmaf(temb[t * td + j], G[(size_t)t * H + c], a);
+                g[o.win + (size_t)(A + j) * H + c] = a;
+            }
         }
+        if (gridDim.x > 1) return;
     }
     // d temb[t][j] = sum_c W_in[A+j][c] * G[t][c]: one warp per output, lanes stride over c (coalesced), shuffle reduce
     for (int i = tid >> 5; i < T * td; i += nt >> 5) {

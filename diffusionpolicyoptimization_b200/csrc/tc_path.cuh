@@ -88,7 +88,8 @@ __global__ void tc_pack_h0_kernel(const float* __restrict__ x, const float* __re
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)N * g8) return;
     const int r = (int)(i / g8), k0 = (int)(i % g8) * 8;
-    const int t = trow ? trow[r] : tconst;
+    // trow given: t = trow[r], or K-1-trow[r] when tconst = -K (denoising indices); else the constant tconst
+    const int t = trow ? (tconst < 0 ? -tconst - 1 - trow[r] : trow[r]) : tconst;
     const size_t xrow = chainK > 0 ? (size_t)(r / chainK) * (chainK + 1) + (r % chainK) : (size_t)r;
     __align__(16) bf16 o[8];
 #pragma unroll
@@ -477,6 +478,7 @@ struct TcMlp {
     bf16 *dv, *dh1, *du;                   // backward
     uint32_t *m0, *m1;                     // fused chain: ReLU bit masks [N][H/32] of layer 0 / block.l1
     int fused, net, din;                   // fused: runs on the fused layer-chain kernel; din: un-padded input width
+    float* cpart;                          // fused backward: where the per-CTA bias column sums go ([sm][2][H]); null = reduce at once
 };
 static size_t tc_mlp_ws_bytes(int N, int H, bool mish, bool bwd) {
     size_t one = ws_bytes((size_t)N * H, sizeof(bf16));
@@ -576,11 +578,12 @@ static int tc_mlp_backward(dppo_handle* h, cudaStream_t s, const TcMlp& m, const
     if (m.fused) {
         // one launch: dv, dh1 and the non-residual part of du; the residual path joins in dW0 = h0^T du + h0^T dv
         const int grid = (N + 127) / 128 < h->sm_count ? (N + 127) / 128 : h->sm_count;
-        float* cpart = part;                                       // [grid][2][H]; consumed before the dW GEMMs reuse `part`
+        float* cpart = m.cpart ? m.cpart : part;                   // [grid][2][H]; `part` is consumed before the dW GEMMs reuse it
         DPPO_TRY(fc_bwd(h, s, m.net == DPPO_NET_CRITIC ? fc_critic_net(h) : fc_actor_net(h, m.net), doutb, N, m.m0, m.m1, m.pre0, m.pre1,
                         m.dv, m.dh1, m.du, cpart));
-        tc_reduce_cols_kernel<<<tc_nblk(H, 8), 256, 0, s>>>(cpart, grid, (size_t)2 * H, H, gnet + ob2); TC_KCHECK(h);
-        tc_reduce_cols_kernel<<<tc_nblk(H, 8), 256, 0, s>>>(cpart + H, grid, (size_t)2 * H, H, gnet + ob1); TC_KCHECK(h);
+        if (!m.cpart) {   // slot 0 = column sums of dv (db2), slot 1 = of dh1 (db1)
+            tc_reduce_cols_kernel<<<tc_nblk(2 * H, 8), 256, 0, s>>>(cpart, grid, (size_t)2 * H, 2 * H, gnet + ob2, H, gnet + ob1); TC_KCHECK(h);
+        }
         DPPO_TRY(tc_dw(h, s, m.v, H, doutb, 64, N, part, gnet + ow3, H, m.NO, m.NO));
         DPPO_TRY(tc_dw(h, s, m.a1, H, m.dv, H, N, part, gnet + ow2, H, H, H));
         DPPO_TRY(tc_dw(h, s, m.a0, H, m.dh1, H, N, part, gnet + ow1, H, H, H));
@@ -615,13 +618,13 @@ static int tc_mlp_backward(dppo_handle* h, cudaStream_t s, const TcMlp& m, const
 static void tc_actor_mlp(const dppo_handle* h, int net, TcMlp& m) {
     const Geom& g = h->g; const float* w = h->net_w[net];
     m.W = &h->tc->net[net]; m.H = g.H; m.NO = g.A; m.act1 = h->cfg.actor_act + 1; m.KP0 = h->tc->KP0;
-    m.fused = fc_ok(h) ? 1 : 0; m.net = net; m.din = g.Din;
+    m.fused = fc_ok(h) ? 1 : 0; m.net = net; m.din = g.Din; m.cpart = nullptr;
     m.b0 = nullptr; m.b1 = w + g.ao.b1; m.b2 = w + g.ao.b2; m.b3 = w + g.ao.b3;
 }
 static void tc_critic_mlp(const dppo_handle* h, TcMlp& m) {
     const Geom& g = h->g; const float* w = h->net_w[DPPO_NET_CRITIC];
     m.W = &h->tc->net[DPPO_NET_CRITIC]; m.H = g.Hc; m.NO = 1; m.act1 = h->cfg.critic_act + 1; m.KP0 = h->tc->KP0;
-    m.fused = fc_critic_ok(h) ? 1 : 0; m.net = DPPO_NET_CRITIC; m.din = g.Do;
+    m.fused = fc_critic_ok(h) ? 1 : 0; m.net = DPPO_NET_CRITIC; m.din = g.Do; m.cpart = nullptr;
     m.b0 = w + g.co.bin; m.b1 = w + g.co.b1; m.b2 = m.W->bias2; m.b3 = w + g.co.b3;
 }
 
@@ -702,57 +705,139 @@ static int tc_critic_grads(dppo_handle* h, cudaStream_t s, const TcMlp& m, const
     return 0;
 }
 
-// PPODiffusion.c_loss + tape.gradient (diffusion_ppo.py:32-132, train_ppo_diffusion_agent.py:340-346) on the tensor path.
-// Leaves [actor_ft grads | critic grads | 8 metric partials] in h->grads.
-static int tc_ppo_step(dppo_handle* h, cudaStream_t s, const float* obs, const float* prev, const float* nxt, const int32_t* inds,
-                       const float* returns, const float* oldvalues, const float* advantages, const float* oldlogp,
-                       int N, int64_t N_global, float adv_mean, float adv_std) {
+// PPODiffusion.c_loss + tape.gradient (diffusion_ppo.py:32-132, train_ppo_diffusion_agent.py:340-346) on the tensor path,
+// as begin / chunk x C / finish so that the host-buffer entry point can overlap the H2D copy of chunk c+1 with the
+// compute of chunk c (rows are independent; every gradient piece accumulates: dW by red.global.add, bias column sums
+// and metric sums as per-block partials reduced once in finish).  Leaves [actor_ft grads | critic grads | 8 metrics]
+// in h->grads.  The deterministic mode (fixed-order split-K reduction) supports a single chunk only.
+struct TcPpoPlan {
+    int N, nchunks, chunk_rows, blocks_done, max_blocks;
+    int64_t N_global;
+    float *part, *dw0a, *dw0c, *colb3, *cpa, *cpc;
+    double* bsum;
+    TcMlp ma, mc;
+    bf16 *h0, *depsb, *dvalb; float *eps, *val;
+    PpoHyper hp;
+};
+static TcPpoPlan g_plan_storage[16];   // indexed by device
+static TcPpoPlan& tc_plan(dppo_handle* h) { return g_plan_storage[h->device & 15]; }
+
+// chunk_rows <= 0 or >= N: one chunk
+static int tc_ppo_begin(dppo_handle* h, cudaStream_t s, int N, int chunk_rows, int64_t N_global) {
     const Geom& g = h->g; const int KP0 = h->tc->KP0;
     const size_t nA = g.ao.n, nC = g.co.n;
-    float* gr = h->grads;
+    TcPpoPlan& P = tc_plan(h);
+    if (h->deterministic || chunk_rows <= 0 || chunk_rows >= N) chunk_rows = N;
+    chunk_rows = round_up(chunk_rows, 128);
+    const int nchunks = (N + chunk_rows - 1) / chunk_rows;
+    P.N = N; P.nchunks = nchunks; P.N_global = N_global; P.blocks_done = 0;
+    P.chunk_rows = chunk_rows;
+    const int NC = P.chunk_rows < N ? P.chunk_rows : N;
+    P.max_blocks = tc_nblk(N, 128) + nchunks;
     const bool amish = h->cfg.actor_act == DPPO_ACT_MISH, cmish = h->cfg.critic_act == DPPO_ACT_MISH;
-    const int nlb = tc_nblk(N, 128);
     const size_t pf = tc_part_floats(h, g.H);
-    size_t need = ws_bytes((size_t)N * KP0, 2) + tc_mlp_ws_bytes(N, g.H, amish, true) + tc_mlp_ws_bytes(N, g.Hc, cmish, true)
-                + 2 * ws_bytes((size_t)N * g.A, 4) + 3 * ws_bytes(N, 4) + 2 * ws_bytes((size_t)N * 64, 2)
-                + ws_bytes(pf, 4) + ws_bytes((size_t)KP0 * g.H, 4) + ws_bytes((size_t)KP0 * g.Hc, 4) + ws_bytes((size_t)nlb * 5, 8);
+    const size_t n_cpa = (size_t)nchunks * h->sm_count * 2 * g.H, n_cpc = (size_t)nchunks * h->sm_count * 2 * g.Hc;
+    size_t need = ws_bytes((size_t)NC * KP0, 2) + tc_mlp_ws_bytes(NC, g.H, amish, true) + tc_mlp_ws_bytes(NC, g.Hc, cmish, true)
+                + ws_bytes((size_t)NC * g.A, 4) + ws_bytes(NC, 4) + 2 * ws_bytes((size_t)NC * 64, 2)
+                + ws_bytes(pf, 4) + ws_bytes((size_t)KP0 * g.H, 4) + ws_bytes((size_t)KP0 * g.Hc, 4)
+                + ws_bytes((size_t)P.max_blocks * 5, 8) + ws_bytes((size_t)P.max_blocks * (g.A + 1), 4) + ws_bytes(n_cpa, 4) + ws_bytes(n_cpc, 4);
     DPPO_TRY(ws_reserve(h, need, s));
-    TcMlp ma, mc; tc_actor_mlp(h, DPPO_NET_ACTOR_FT, ma); tc_critic_mlp(h, mc);
-    bf16* h0 = ws_take<bf16>(h, (size_t)N * KP0);
-    tc_mlp_take(h, N, ma, true); tc_mlp_take(h, N, mc, true);
-    float* eps = ws_take<float>(h, (size_t)N * g.A); float* deps = ws_take<float>(h, (size_t)N * g.A);
-    float* val = ws_take<float>(h, N); float* dval = ws_take<float>(h, N); int* trow = ws_take<int>(h, N);
-    bf16* depsb = ws_take<bf16>(h, (size_t)N * 64); bf16* dvalb = ws_take<bf16>(h, (size_t)N * 64);
-    float* part = ws_take<float>(h, pf);
-    float* dw0a = ws_take<float>(h, (size_t)KP0 * g.H); float* dw0c = ws_take<float>(h, (size_t)KP0 * g.Hc);
-    double* bsum = ws_take<double>(h, (size_t)nlb * 5);
-    ma.h0 = h0; mc.h0 = h0; ma.out = eps; mc.out = val;
-
+    tc_actor_mlp(h, DPPO_NET_ACTOR_FT, P.ma); tc_critic_mlp(h, P.mc);
+    P.h0 = ws_take<bf16>(h, (size_t)NC * KP0);
+    tc_mlp_take(h, NC, P.ma, true); tc_mlp_take(h, NC, P.mc, true);
+    P.eps = ws_take<float>(h, (size_t)NC * g.A); P.val = ws_take<float>(h, NC);
+    P.depsb = ws_take<bf16>(h, (size_t)NC * 64); P.dvalb = ws_take<bf16>(h, (size_t)NC * 64);
+    P.part = ws_take<float>(h, pf);
+    P.dw0a = ws_take<float>(h, (size_t)KP0 * g.H); P.dw0c = ws_take<float>(h, (size_t)KP0 * g.Hc);
+    P.bsum = ws_take<double>(h, (size_t)P.max_blocks * 5);
+    P.colb3 = ws_take<float>(h, (size_t)P.max_blocks * (g.A + 1));
+    P.cpa = ws_take<float>(h, n_cpa); P.cpc = ws_take<float>(h, n_cpc);
+    P.ma.h0 = P.h0; P.mc.h0 = P.h0; P.ma.out = P.eps; P.mc.out = P.val;
+    const bool defer = P.ma.fused && P.mc.fused && !h->deterministic;
+    if (!defer && nchunks > 1) DPPO_FAIL(-7, "tc_ppo_begin: chunked accumulation needs the fused chain kernels");
     if (!h->deterministic) {   // the dW GEMMs accumulate atomically into the gradient buffers
-        CUDA_TRY(cudaMemsetAsync(gr, 0, (nA + nC) * sizeof(float), s));
-        CUDA_TRY(cudaMemsetAsync(dw0a, 0, (size_t)KP0 * g.H * sizeof(float), s));
-        CUDA_TRY(cudaMemsetAsync(dw0c, 0, (size_t)KP0 * g.Hc * sizeof(float), s));
+        CUDA_TRY(cudaMemsetAsync(h->grads, 0, (nA + nC) * sizeof(float), s));
+        CUDA_TRY(cudaMemsetAsync(P.dw0a, 0, (size_t)KP0 * g.H * sizeof(float), s));
+        CUDA_TRY(cudaMemsetAsync(P.dw0c, 0, (size_t)KP0 * g.Hc * sizeof(float), s));
     }
-    make_trow_kernel<<<tc_nblk(N, 256), 256, 0, s>>>(inds, N, g.K, 0, trow); TC_KCHECK(h);
-    if (adv_std < 0.f) { adv_stats_kernel<<<1, 256, 0, s>>>(advantages, N, h->scalars); TC_KCHECK(h); }
-    else { set_scalars_kernel<<<1, 1, 0, s>>>(h->scalars, adv_mean, adv_std); TC_KCHECK(h); }
-    tc_pack_h0_kernel<<<tc_nblk((size_t)N * (KP0 / 8), 256), 256, 0, s>>>(prev, obs, trow, 0, N, g.A, g.Do, g.T, KP0, 1, h0); TC_KCHECK(h);
-    DPPO_TRY(tc_mlp_forward(h, s, ma, N));
-    DPPO_TRY(tc_mlp_forward(h, s, mc, N));
-    PpoHyper hp;
+    if (defer) { CUDA_TRY(cudaMemsetAsync(P.cpa, 0, n_cpa * sizeof(float), s)); CUDA_TRY(cudaMemsetAsync(P.cpc, 0, n_cpc * sizeof(float), s)); }
+    PpoHyper& hp = P.hp;
     hp.A = g.A; hp.Da = h->cfg.action_dim; hp.K = g.K; hp.T = g.T; hp.reward_horizon = h->cfg.reward_horizon; hp.norm_adv = h->cfg.norm_adv;
     hp.dcv = h->cfg.denoised_clip_value; hp.min_lp_std = h->cfg.min_logprob_denoising_std;
     hp.lp_lo = h->cfg.logprob_clip_lo; hp.lp_hi = h->cfg.logprob_clip_hi; hp.gamma_d = h->cfg.gamma_denoising;
     hp.clip_coef = h->cfg.clip_ploss_coef; hp.clip_base = h->cfg.clip_ploss_coef_base; hp.clip_rate = h->cfg.clip_ploss_coef_rate;
     hp.clip_v = h->cfg.clip_vloss_coef; hp.vf_coef = h->cfg.vf_coef; hp.inv_nglobal = 1.0f / (float)N_global;
-    tc_ppo_loss_kernel<<<nlb, 128, 0, s>>>(prev, nxt, eps, inds, returns, oldvalues, advantages, oldlogp, val,
-                                          h->scalars, h->sched, hp, N, depsb, dvalb, bsum, part); TC_KCHECK(h);
-    ppo_metrics_kernel<<<1, 256, 0, s>>>(bsum, nlb, hp.inv_nglobal, (float)((double)N / (double)N_global), gr + nA + nC); TC_KCHECK(h);
-    // output-layer bias gradients = column sums of the seeds (per-block partials from the loss kernel)
-    tc_reduce_cols_kernel<<<tc_nblk(g.A + 1, 8), 256, 0, s>>>(part, nlb, (size_t)(g.A + 1), g.A + 1, gr + g.ao.b3, g.A, gr + nA + g.co.b3); TC_KCHECK(h);
-    DPPO_TRY(tc_actor_grads(h, s, DPPO_NET_ACTOR_FT, ma, nullptr, depsb, N, part, dw0a, gr));
-    DPPO_TRY(tc_critic_grads(h, s, mc, nullptr, dvalb, N, part, dw0c, gr + nA));
     return 0;
+}
+// advantage statistics for the whole minibatch (diffusion_ppo.py:74-75): given, or computed from the device array
+static int tc_ppo_adv_stats(dppo_handle* h, cudaStream_t s, const float* advantages_all, int N, float adv_mean, float adv_std) {
+    if (adv_std < 0.f) { adv_stats_kernel<<<1, 1024, 0, s>>>(advantages_all, N, h->scalars); TC_KCHECK(h); }
+    else { set_scalars_kernel<<<1, 1, 0, s>>>(h->scalars, adv_mean, adv_std); TC_KCHECK(h); }
+    return 0;
+}
+// chunk size of the host pipeline: whole waves of 128-row tiles (one tile per SM), at most ~4 chunks; 0 = do not chunk
+static int tc_ppo_pipeline_chunk_rows(const dppo_handle* h, int N) {
+    const int wave = h->sm_count * 128;
+    if (N < 2 * wave) return 0;
+    const int k = (N + 4 * wave - 1) / (4 * wave);
+    return k * wave;
+}
+// rows [r0, r0 + n) of the minibatch; all pointers already point at row r0
+static int tc_ppo_chunk(dppo_handle* h, cudaStream_t s, int chunk, const float* obs, const float* prev, const float* nxt, const int32_t* inds,
+                        const float* returns, const float* oldvalues, const float* advantages, const float* oldlogp, int n) {
+    const Geom& g = h->g; const int KP0 = h->tc->KP0;
+    const size_t nA = g.ao.n;
+    TcPpoPlan& P = tc_plan(h);
+    if (n < 1 || n > P.chunk_rows || chunk < 0 || chunk >= P.nchunks) DPPO_FAIL(-1, "tc_ppo_chunk: bad chunk");
+    const int nlb = tc_nblk(n, 128);
+    if (P.blocks_done + nlb > P.max_blocks) DPPO_FAIL(-1, "tc_ppo_chunk: partial-sum buffers exhausted");
+    const bool defer = P.ma.fused && P.mc.fused && !h->deterministic;
+    P.ma.cpart = defer ? P.cpa + (size_t)chunk * h->sm_count * 2 * g.H : nullptr;
+    P.mc.cpart = defer ? P.cpc + (size_t)chunk * h->sm_count * 2 * g.Hc : nullptr;
+    // h0 straight from (prev, obs, K-1-inds): tconst = -(K) flags "t = K-1-trow[r]"
+    tc_pack_h0_kernel<<<tc_nblk((size_t)n * (KP0 / 8), 256), 256, 0, s>>>(prev, obs, inds, -g.K, n, g.A, g.Do, g.T, KP0, 1, P.h0); TC_KCHECK(h);
+    DPPO_TRY(tc_mlp_forward(h, s, P.ma, n));
+    DPPO_TRY(tc_mlp_forward(h, s, P.mc, n));
+    tc_ppo_loss_kernel<<<nlb, 128, 0, s>>>(prev, nxt, P.eps, inds, returns, oldvalues, advantages, oldlogp, P.val,
+                                          h->scalars, h->sched, P.hp, n, P.depsb, P.dvalb, P.bsum + (size_t)P.blocks_done * 5,
+                                          P.colb3 + (size_t)P.blocks_done * (g.A + 1)); TC_KCHECK(h);
+    P.blocks_done += nlb;
+    DPPO_TRY(tc_mlp_backward(h, s, P.ma, P.depsb, n, P.part, h->grads, g.ao.w1, g.ao.b1, g.ao.w2, g.ao.b2, g.ao.w3, P.dw0a));
+    DPPO_TRY(tc_mlp_backward(h, s, P.mc, P.dvalb, n, P.part, h->grads + nA, g.co.w1, g.co.b1, g.co.w2, g.co.b2, g.co.w3, P.dw0c));
+    return 0;
+}
+static int tc_ppo_finish(dppo_handle* h, cudaStream_t s) {
+    const Geom& g = h->g;
+    const size_t nA = g.ao.n, nC = g.co.n;
+    TcPpoPlan& P = tc_plan(h);
+    float* gr = h->grads;
+    const bool defer = P.ma.fused && P.mc.fused && !h->deterministic;
+    ppo_metrics_kernel<<<1, 256, 0, s>>>(P.bsum, P.blocks_done, P.hp.inv_nglobal, (float)((double)P.N / (double)P.N_global), gr + nA + nC); TC_KCHECK(h);
+    // output-layer bias gradients = column sums of the seeds (per-block partials from the loss kernel)
+    tc_reduce_cols_kernel<<<tc_nblk(g.A + 1, 8), 256, 0, s>>>(P.colb3, P.blocks_done, (size_t)(g.A + 1), g.A + 1, gr + g.ao.b3, g.A, gr + nA + g.co.b3); TC_KCHECK(h);
+    if (defer) {
+        const int rows = P.nchunks * h->sm_count;
+        tc_reduce_cols_kernel<<<tc_nblk(2 * g.H, 8), 256, 0, s>>>(P.cpa, rows, (size_t)2 * g.H, 2 * g.H, gr + g.ao.b2, g.H, gr + g.ao.b1); TC_KCHECK(h);
+        tc_reduce_cols_kernel<<<tc_nblk(2 * g.Hc, 8), 256, 0, s>>>(P.cpc, rows, (size_t)2 * g.Hc, 2 * g.Hc, gr + nA + g.co.b2, g.Hc, gr + nA + g.co.b1); TC_KCHECK(h);
+    }
+    // actor: dw0 rows [A+Do, A+Do+T) are the per-t column sums of du = the gradient of the bt table
+    const float* w = h->net_w[DPPO_NET_ACTOR_FT]; const ActorDerived& d = h->ad[DPPO_NET_ACTOR_FT];
+    const size_t sm = (size_t)(g.T * g.td * 3) * sizeof(float);
+    time_backward_kernel<<<1 + (g.H + 127) / 128, 512, sm, s>>>(w, g.ao, g.A, g.td, g.H, g.T, P.dw0a + (size_t)(g.A + g.Do) * g.H, d.sinemb, d.thpre, d.temb, gr);
+    TC_KCHECK(h);
+    unpack_dw0_kernel<<<tc_nblk((size_t)(g.A + g.Do) * g.H, 256), 256, 0, s>>>(P.dw0a, g.A, g.td, g.Do, g.H, gr + g.ao.win); TC_KCHECK(h);
+    // critic: obs rows of dw0 -> dW_in; the ones column of h0 collected the input-layer bias gradient
+    unpack_dw0_kernel<<<tc_nblk((size_t)g.Do * g.Hc, 256), 256, 0, s>>>(P.dw0c + (size_t)g.A * g.Hc, 0, 0, g.Do, g.Hc, gr + nA + g.co.win); TC_KCHECK(h);
+    CUDA_TRY(cudaMemcpyAsync(gr + nA + g.co.bin, P.dw0c + (size_t)(g.A + g.Do + g.T) * g.Hc, g.Hc * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    return 0;
+}
+static int tc_ppo_step(dppo_handle* h, cudaStream_t s, const float* obs, const float* prev, const float* nxt, const int32_t* inds,
+                       const float* returns, const float* oldvalues, const float* advantages, const float* oldlogp,
+                       int N, int64_t N_global, float adv_mean, float adv_std) {
+    DPPO_TRY(tc_ppo_begin(h, s, N, 0, N_global));
+    DPPO_TRY(tc_ppo_adv_stats(h, s, advantages, N, adv_mean, adv_std));
+    DPPO_TRY(tc_ppo_chunk(h, s, 0, obs, prev, nxt, inds, returns, oldvalues, advantages, oldlogp, N));
+    return tc_ppo_finish(h, s);
 }
 
 // DiffusionModel.c_loss / p_losses (diffusion.py:179-202) + tape.gradient on the tensor path: loss -> h->grads[nA],

@@ -172,3 +172,38 @@ def test_bf16_adamw_step_runs_and_refreshes_operands(pair):
     e.set_weights(L.NET_ACTOR_FT, w0)
     lp2 = e.logprobs_subsample(*args[:4])
     assert float((lp2 - lp0).abs().max()) == 0.0       # and is deterministic
+
+
+def test_bf16_host_entry_chunked_pipeline_matches_device_call(pair):
+    """dppo_ppo_step_host overlaps the H2D copy of chunk c+1 with the compute of chunk c (chunks of whole 148 x 128-row waves);
+    its metrics and post-step weights must agree with the single-chunk device-resident call on the same rows."""
+    o, e = pair
+    N = 40000        # > 2 waves of 148 x 128 rows -> 3 pipeline chunks
+    rng = np.random.default_rng(5)
+    d = o.d
+    K = d.ft_denoising_steps
+    obs = rng.uniform(-1, 1, (N, d.Do)).astype(np.float32)
+    prev = rng.standard_normal((N, d.A)).astype(np.float32)
+    nxt = (prev + 0.1 * rng.standard_normal((N, d.A))).astype(np.float32)
+    inds = rng.integers(0, K, N).astype(np.int32)
+    ret = rng.standard_normal(N).astype(np.float32); val = rng.standard_normal(N).astype(np.float32)
+    adv = rng.standard_normal(N).astype(np.float32)
+    olp = e.logprobs_subsample(obs, prev, nxt, inds).cpu().numpy() + 0.01 * rng.standard_normal((N, d.A)).astype(np.float32)
+    olp = np.ascontiguousarray(olp, np.float32)
+    w_a, w_c = e.get_weights(L.NET_ACTOR_FT).copy(), e.get_weights(L.NET_CRITIC).copy()
+    n = e.n_actor + e.n_critic
+    e.set_opt_state(L.OPT_FINETUNE, np.zeros(n, np.float32), np.zeros(n, np.float32), 0)     # earlier tests stepped the optimizer
+    m_dev, g_dev = e.ppo_step(obs, prev, nxt, inds, ret, val, adv, olp, lr=1e-3, apply=True, want_grads=True)
+    m_dev = m_dev.cpu().numpy(); g_dev = g_dev.cpu().numpy()
+    wa1 = e.get_weights(L.NET_ACTOR_FT).copy(); wc1 = e.get_weights(L.NET_CRITIC).copy()
+    # rewind weights and optimizer state, then take the same step through the host entry point
+    e.set_weights(L.NET_ACTOR_FT, w_a); e.set_weights(L.NET_CRITIC, w_c)
+    e.set_opt_state(L.OPT_FINETUNE, np.zeros(n, np.float32), np.zeros(n, np.float32), 0)
+    m_host = np.zeros(8, np.float32)
+    e.ppo_step_host(obs, prev, nxt, inds, ret, val, adv, olp, m_host, lr=1e-3, apply=True)
+    np.testing.assert_allclose(m_host, m_dev, rtol=1e-4, atol=1e-6)
+    wa2 = e.get_weights(L.NET_ACTOR_FT); wc2 = e.get_weights(L.NET_CRITIC)
+    # first Adam step moves every weight by ~lr * sign(g): compare in units of lr, allowing sign flips where g ~ 0
+    assert np.mean(np.abs(wa2 - wa1) > 0.05e-3) < 5e-3 and np.mean(np.abs(wc2 - wc1) > 0.05e-3) < 5e-3
+    e.set_weights(L.NET_ACTOR_FT, w_a); e.set_weights(L.NET_CRITIC, w_c)
+    e.set_opt_state(L.OPT_FINETUNE, np.zeros(n, np.float32), np.zeros(n, np.float32), 0)
