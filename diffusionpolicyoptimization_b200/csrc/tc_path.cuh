@@ -570,6 +570,27 @@ static size_t tc_part_floats(const dppo_handle* h, int H) {
     size_t m = a > b ? a : b;
     return m > c ? m : c;
 }
+// fused backward chain of one net (dv, dh1, du) + its bias column sums
+static int tc_mlp_backward_dx(dppo_handle* h, cudaStream_t s, const TcMlp& m, const bf16* doutb, int N, float* part, float* gnet, size_t ob1, size_t ob2) {
+    const int H = m.H;
+    const int grid = (N + 127) / 128 < h->sm_count ? (N + 127) / 128 : h->sm_count;
+    float* cpart = m.cpart ? m.cpart : part;                   // [grid][2][H]; `part` is consumed before anything reuses it
+    DPPO_TRY(fc_bwd(h, s, m.net == DPPO_NET_CRITIC ? fc_critic_net(h) : fc_actor_net(h, m.net), doutb, N, m.m0, m.m1, m.pre0, m.pre1,
+                    m.dv, m.dh1, m.du, cpart));
+    if (!m.cpart) {   // slot 0 = column sums of dv (db2), slot 1 = of dh1 (db1)
+        tc_reduce_cols_kernel<<<tc_nblk(2 * H, 8), 256, 0, s>>>(cpart, grid, (size_t)2 * H, 2 * H, gnet + ob2, H, gnet + ob1); TC_KCHECK(h);
+    }
+    return 0;
+}
+// the five weight-gradient products of one net as grouped-GEMM problems (outputs accumulate atomically)
+static void tc_mlp_dw_descs(const TcMlp& m, const bf16* doutb, int N, float* gnet, size_t ow1, size_t ow2, size_t ow3, float* dw0, tc::GroupDesc* d) {
+    const int H = m.H, KP0 = m.KP0; const double r = (double)N;
+    d[0] = tc::GroupDesc{m.a1, H, m.dv, H, gnet + ow2, H, H, H, 2.0 * r * H * H};
+    d[1] = tc::GroupDesc{m.a0, H, m.dh1, H, gnet + ow1, H, H, H, 2.0 * r * H * H};
+    d[2] = tc::GroupDesc{m.h0, KP0, m.du, H, dw0, KP0, H, H, 2.0 * r * m.din * H};
+    d[3] = tc::GroupDesc{m.h0, KP0, m.dv, H, dw0, KP0, H, H, 0.0};                    // residual path: not algorithmic work
+    d[4] = tc::GroupDesc{m.v, H, doutb, 64, gnet + ow3, H, m.NO, m.NO, 2.0 * r * H * m.NO};
+}
 // backward of the residual MLP from doutb [N][64] (bf16, zero padded).  Writes gradients of W1,b1,W2,b2,W3 into gnet
 // at the given offsets and dW0 (in h0 row order) into dw0 [KP0][H].
 static int tc_mlp_backward(dppo_handle* h, cudaStream_t s, const TcMlp& m, const bf16* doutb, int N, float* part,
@@ -577,12 +598,11 @@ static int tc_mlp_backward(dppo_handle* h, cudaStream_t s, const TcMlp& m, const
     const int H = m.H, KP0 = m.KP0; const TcNetW& W = *m.W;
     if (m.fused) {
         // one launch: dv, dh1 and the non-residual part of du; the residual path joins in dW0 = h0^T du + h0^T dv
-        const int grid = (N + 127) / 128 < h->sm_count ? (N + 127) / 128 : h->sm_count;
-        float* cpart = m.cpart ? m.cpart : part;                   // [grid][2][H]; `part` is consumed before the dW GEMMs reuse it
-        DPPO_TRY(fc_bwd(h, s, m.net == DPPO_NET_CRITIC ? fc_critic_net(h) : fc_actor_net(h, m.net), doutb, N, m.m0, m.m1, m.pre0, m.pre1,
-                        m.dv, m.dh1, m.du, cpart));
-        if (!m.cpart) {   // slot 0 = column sums of dv (db2), slot 1 = of dh1 (db1)
-            tc_reduce_cols_kernel<<<tc_nblk(2 * H, 8), 256, 0, s>>>(cpart, grid, (size_t)2 * H, 2 * H, gnet + ob2, H, gnet + ob1); TC_KCHECK(h);
+        DPPO_TRY(tc_mlp_backward_dx(h, s, m, doutb, N, part, gnet, ob1, ob2));
+        if (!h->deterministic) {   // all five weight-gradient products in one grouped launch
+            tc::GroupDesc d[5];
+            tc_mlp_dw_descs(m, doutb, N, gnet, ow1, ow2, ow3, dw0, d);
+            return tc::launch_group(h, s, d, 5, N);
         }
         DPPO_TRY(tc_dw(h, s, m.v, H, doutb, 64, N, part, gnet + ow3, H, m.NO, m.NO));
         DPPO_TRY(tc_dw(h, s, m.a1, H, m.dv, H, N, part, gnet + ow2, H, H, H));
@@ -802,6 +822,15 @@ static int tc_ppo_chunk(dppo_handle* h, cudaStream_t s, int chunk, const float* 
                                           h->scalars, h->sched, P.hp, n, P.depsb, P.dvalb, P.bsum + (size_t)P.blocks_done * 5,
                                           P.colb3 + (size_t)P.blocks_done * (g.A + 1)); TC_KCHECK(h);
     P.blocks_done += nlb;
+    if (defer) {
+        // both backward chains, then ONE grouped launch with the ten weight-gradient products of actor and critic
+        DPPO_TRY(tc_mlp_backward_dx(h, s, P.ma, P.depsb, n, P.part, h->grads, g.ao.b1, g.ao.b2));
+        DPPO_TRY(tc_mlp_backward_dx(h, s, P.mc, P.dvalb, n, P.part, h->grads + nA, g.co.b1, g.co.b2));
+        tc::GroupDesc d[10];
+        tc_mlp_dw_descs(P.ma, P.depsb, n, h->grads, g.ao.w1, g.ao.w2, g.ao.w3, P.dw0a, d);
+        tc_mlp_dw_descs(P.mc, P.dvalb, n, h->grads + nA, g.co.w1, g.co.w2, g.co.w3, P.dw0c, d + 5);
+        return tc::launch_group(h, s, d, 10, n);
+    }
     DPPO_TRY(tc_mlp_backward(h, s, P.ma, P.depsb, n, P.part, h->grads, g.ao.w1, g.ao.b1, g.ao.w2, g.ao.b2, g.ao.w3, P.dw0a));
     DPPO_TRY(tc_mlp_backward(h, s, P.mc, P.dvalb, n, P.part, h->grads + nA, g.co.w1, g.co.b1, g.co.w2, g.co.b2, g.co.w3, P.dw0c));
     return 0;
