@@ -230,11 +230,12 @@ __global__ void __launch_bounds__(FTHREADS, 1) chain_kernel(const __grid_constan
     uint64_t* w_empty = bars + NSTAGE;
     uint64_t* h0_full = bars + 2 * NSTAGE;
     uint64_t* h0_empty = h0_full + 1;
-    uint64_t* acc_full = h0_full + 2;
-    uint64_t* x_full = h0_full + 3;
-    uint64_t* g_full = h0_full + 4;      // TMA -> epilogue: gate tile landed in G
-    uint64_t* g_empty = h0_full + 5;     // epilogue -> TMA: G may be overwritten
-    uint32_t* tmem_slot = (uint32_t*)(h0_full + 6);
+    uint64_t* acc_full = h0_full + 2;    // [2] MMA -> epilogue: accumulator columns [256 h, 256 h + 256) complete
+    uint64_t* xready = h0_full + 4;      // [2] epilogue -> MMA: X tiles of half h written + TMEM columns of half h drained
+    uint64_t* xfree = h0_full + 6;       // [4] MMA -> epilogue: the last n-half has consumed X tile j (j < XT/2)
+    uint64_t* g_full = h0_full + 10;     // TMA -> epilogue: gate tile landed in G
+    uint64_t* g_empty = h0_full + 11;    // epilogue -> TMA: G may be overwritten
+    uint32_t* tmem_slot = (uint32_t*)(h0_full + 12);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ntiles = (p.rows + FBM - 1) / FBM;
@@ -244,7 +245,9 @@ __global__ void __launch_bounds__(FTHREADS, 1) chain_kernel(const __grid_constan
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < NMAPS; ++i) tma_prefetch_desc(&maps.m[i]);
         for (int i = 0; i < NSTAGE; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-        mbar_init(h0_full, 1); mbar_init(h0_empty, 1); mbar_init(acc_full, 1); mbar_init(x_full, 8);
+        mbar_init(h0_full, 1); mbar_init(h0_empty, 1);
+        mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1); mbar_init(&xready[0], 8); mbar_init(&xready[1], 8);
+        for (int i = 0; i < 4; ++i) mbar_init(&xfree[i], 1);
         mbar_init(g_full, 1); mbar_init(g_empty, 8);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -327,12 +330,13 @@ __global__ void __launch_bounds__(FTHREADS, 1) chain_kernel(const __grid_constan
         // measured with tools/mma_probe.py), so descriptors are kept as 32-bit halves: the high word and the B
         // descriptors of the four ring slots are loop invariants, the A descriptor advances by an add.
         {
-            int stage = 0; uint32_t phase = 0, h0_phase = 0, x_phase = 0;
+            int stage = 0; uint32_t phase = 0, h0_phase = 0, xr_phase = 0;
             const uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);          // SBO = 1024 B, version 1, SWIZZLE_128B
             const uint32_t a_lo_x = ((smem_u32(sX) >> 4) & 0x3FFFu) | (1u << 16);     // K-major A: LBO = 16 B
             const uint32_t a_lo_h0 = ((smem_u32(sH0) >> 4) & 0x3FFFu) | (1u << 16);
             const uint32_t b_lo_0 = ((smem_u32(sW) >> 4) & 0x3FFFu) | ((uint32_t)(WK * 128 >> 4) << 16);   // MN-major B: LBO = one 64-column atom
             const uint32_t wfull_addr = smem_u32(w_full), wempty_addr = smem_u32(w_empty);
+            constexpr int S_HALF = (XT / 2) * (64 / WK);          // first ring stage that reads X tile XT/2
             long long t_x = 0, t_w = 0; const long long t_begin = TIMING ? clock64() : 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 bool h0_waited = false;
@@ -344,25 +348,38 @@ __global__ void __launch_bounds__(FTHREADS, 1) chain_kernel(const __grid_constan
                         const int kx = L.a_src >= 1 ? H / WK : 0, kh = L.a_src != 1 ? 64 / WK : 0;
                         const uint32_t idesc = make_idesc(FBM, n_cur, false, true);
                         const bool h0_rel = L.h0_last && p.h0_from_tma;
-                        // previous epilogue done: X / H0 written, TMEM drained
-                        if (TIMING) { const long long c0 = clock64(); mbar_wait(x_full, x_phase); t_x += clock64() - c0; } else mbar_wait(x_full, x_phase);
-                        x_phase ^= 1;
+                        // xready[0]: the previous epilogue wrote X tiles [0, XT/2) (or H0) and drained the first accumulator half;
+                        // xready[1]: tiles [XT/2, XT) and the second half.  The second wait is deferred to the first stage that needs it.
+                        if (TIMING) { const long long c0 = clock64(); mbar_wait(&xready[0], xr_phase); t_x += clock64() - c0; } else mbar_wait(&xready[0], xr_phase);
+                        bool xr1_waited = false;
+                        if (kx == 0) { mbar_wait(&xready[1], xr_phase); xr1_waited = true; }
                         if (L.a_src != 1 && p.h0_from_tma && !h0_waited) { mbar_wait(h0_full, h0_phase); h0_phase ^= 1; h0_waited = true; }
                         tcgen05_fence_after();
                         for (int nh = 0; nh < nhc; ++nh) {
                             const uint32_t tmem_d = tmem_base + (uint32_t)(nh * 256);
+                            const bool last_half_of_two = (nhc == 2 && nh == 1);
                             uint32_t accf = 0u;
                             uint32_t a_lo = kx ? a_lo_x : a_lo_h0;
+                            if (last_half_of_two && kx == 0) {            // this layer never reads X: the epilogue may overwrite it at once
+                                if (elect_one()) { for (int j = 0; j < XT / 2; ++j) tcgen05_commit(&xfree[j]); }
+                                __syncwarp();
+                            }
                             for (int s = 0; s < kx + kh; ++s) {
                                 if (s == kx) a_lo = a_lo_h0;
+                                if (!xr1_waited && s == S_HALF) {
+                                    if (TIMING) { const long long c0 = clock64(); mbar_wait(&xready[1], xr_phase); t_x += clock64() - c0; } else mbar_wait(&xready[1], xr_phase);
+                                    xr1_waited = true;
+                                }
                                 if (TIMING) { const long long c0 = clock64(); mbar_wait_addr(wfull_addr + stage * 8, phase); t_w += clock64() - c0; }
                                 else mbar_wait_addr(wfull_addr + stage * 8, phase);
                                 tcgen05_fence_after();
                                 const uint32_t b_lo = b_lo_0 + (uint32_t)stage * (STAGE_BYTES >> 4);
+                                const bool free_tile = last_half_of_two && (s & 1) && s < S_HALF && s < kx;
                                 if (elect_one()) {
                                     umma_bf16_split(tmem_d, a_lo, b_lo, desc_hi, idesc, accf);
                                     umma_bf16_split(tmem_d, a_lo + 2u, b_lo + (2048u >> 4), desc_hi, idesc, 1u);
                                     tcgen05_commit_addr(wempty_addr + stage * 8);
+                                    if (free_tile) tcgen05_commit(&xfree[s >> 1]);     // X tile s/2 is not read again in this layer
                                 }
                                 __syncwarp();
                                 accf = 1u;
@@ -370,12 +387,12 @@ __global__ void __launch_bounds__(FTHREADS, 1) chain_kernel(const __grid_constan
                                 a_lo += (s & 1) ? (16384u >> 4) - 4u : 4u;
                                 if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                             }
+                            if (elect_one()) tcgen05_commit(&acc_full[nh]);
+                            __syncwarp();
                         }
-                        if (elect_one()) {
-                            tcgen05_commit(acc_full);
-                            if (h0_rel) tcgen05_commit(h0_empty);
-                        }
-                        __syncwarp();
+                        if (!xr1_waited) mbar_wait(&xready[1], xr_phase);
+                        xr_phase ^= 1;
+                        if (h0_rel) { if (elect_one()) tcgen05_commit(h0_empty); __syncwarp(); }
                     }
                 }
             }
@@ -391,7 +408,7 @@ __global__ void __launch_bounds__(FTHREADS, 1) chain_kernel(const __grid_constan
         const bool store_thread = (warp == 2 && lane == 0);
         uint32_t gfull_phase = 0;
         const int etid = threadIdx.x - 64;                       // 0..255
-        uint32_t acc_phase = 0;
+        uint32_t acc_phase[2] = {0u, 0u}, xf_phase = 0u;
         int bias_buf = 0;
         const int A = p.A;
         float x[16];                                             // sampler: this thread's half of the row's x
@@ -425,9 +442,9 @@ __global__ void __launch_bounds__(FTHREADS, 1) chain_kernel(const __grid_constan
                 build_h0_half(h0_addr, rloc, half, x, obs_row, A, p.Do, p.T, p.T - 1, valid);
                 fence_async_smem();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(x_full);
+                if (lane == 0) { mbar_arrive(&xready[0]); mbar_arrive(&xready[1]); }
             } else if (first) {
-                if (lane == 0) mbar_arrive(x_full);              // "TMEM is free" for the very first layer
+                if (lane == 0) { mbar_arrive(&xready[0]); mbar_arrive(&xready[1]); }   // "TMEM is free" for the very first layer
             }
             first = false;
             for (int step = 0; step < nsteps; ++step) {
@@ -440,33 +457,38 @@ __global__ void __launch_bounds__(FTHREADS, 1) chain_kernel(const __grid_constan
                     float* sb = sBias + bias_buf * 512; bias_buf ^= 1;
                     if (L.bias) { for (int i = etid; i < (final_layer ? A : L.n); i += 256) sb[i] = __ldg(L.bias + i); }
                     long long c_epi = TIMING ? clock64() : 0;
-                    mbar_wait(acc_full, acc_phase); acc_phase ^= 1;
-                    if (TIMING) { const long long c1 = clock64(); t_acc += c1 - c_epi; c_epi = c1; }
-                    tcgen05_fence_after();
                     if (!final_layer) {
-                        // ---------------- generic layer: TMEM -> X (in place)
-                        if (store_thread) tma_store_wait_read();       // earlier TMA stores must have finished reading X
-                        epi_barrier();
-                        const int nch = L.n / 64;                      // 32-column chunks per half
-                        const int c_first = half * nch;
+                        // ---------------- generic layer: TMEM -> X (in place).  A 512-wide layer is drained in two phases:
+                        // columns [0,256) as soon as the first n-half's MMAs are done - while the second half's MMAs still run
+                        // (X tile j is overwritten only after those MMAs have consumed it: xfree[j]) - then columns [256,512).
+                        // The next layer's MMAs start on X tiles [0, XT/2) while phase two is still writing the rest.
+                        const bool two_half = (L.n > 256);
+                        const int nphase = two_half ? 2 : 1;
                         const uint32_t* min_row = L.mask_in ? L.mask_in + (size_t)row * (H / 32) : nullptr;
                         uint32_t* mout_row = L.mask_out ? L.mask_out + (size_t)row * (H / 32) : nullptr;
-                        uint32_t mo[4] = {0u, 0u, 0u, 0u};
-                        uint4 mi4 = make_uint4(0u, 0u, 0u, 0u);
                         const bool gate_in = HASG && L.gate_load_map >= 0;
                         const bool mish = HASG && L.act == 2;
-                        if (gate_in) { mbar_wait(g_full, gfull_phase); gfull_phase ^= 1; }
-                        uint32_t ra[32], rb[32];
-                        tmem_ld32_async(tmem_base + lane_base + (uint32_t)(c_first * 32), ra);
-#pragma unroll 1
-                        for (int ci = 0; ci < nch; ci += 4) {          // nch is 4 or 8; c & 3 == u below
+                        for (int hph = 0; hph < nphase; ++hph) {
+                            mbar_wait(&acc_full[hph], acc_phase[hph]); acc_phase[hph] ^= 1;
+                            if (TIMING) { const long long c1 = clock64(); t_acc += c1 - c_epi; c_epi = c1; }
+                            tcgen05_fence_after();
+                            if (hph == 0) {
+                                if (store_thread) tma_store_wait_read();   // earlier TMA stores must have finished reading X
+                                epi_barrier();                             // ... and every warp is done with the previous layer (bias / colsum)
+                                if (gate_in) { mbar_wait(g_full, gfull_phase); gfull_phase ^= 1; }
+                            }
+                            constexpr int nch = 4;                         // 32-column chunks per warp and phase
+                            const int c_first = hph * 8 + half * nch;
+                            uint32_t mo[4] = {0u, 0u, 0u, 0u};
+                            uint4 mi4 = make_uint4(0u, 0u, 0u, 0u);
+                            uint32_t ra[32], rb[32];
+                            tmem_ld32_async(tmem_base + lane_base + (uint32_t)(c_first * 32), ra);
 #pragma unroll
                             for (int u = 0; u < 4; ++u) {
-                                const int c = c_first + ci + u;
+                                const int c = c_first + u;
                                 uint32_t (&r)[32] = (u & 1) ? rb : ra;
                                 tmem_ld_wait(r);
-                                if ((u & 1) == 0) tmem_ld32_async(tmem_base + lane_base + (uint32_t)((c + 1) * 32), rb);
-                                else if (u == 1 || ci + 4 < nch) tmem_ld32_async(tmem_base + lane_base + (uint32_t)((c + 1) * 32), ra);
+                                if (u < 3) tmem_ld32_async(tmem_base + lane_base + (uint32_t)((c + 1) * 32), (u & 1) ? ra : rb);
                                 const int n0 = c * 32;
                                 float v[32];
 #pragma unroll
@@ -506,9 +528,8 @@ __global__ void __launch_bounds__(FTHREADS, 1) chain_kernel(const __grid_constan
                                 if (gate_in) {
 #pragma unroll
                                     for (int q = 0; q < 4; ++q) {
-                                        uint32_t g0, g1, g2, g3;
-                                        ld_shared_v4(g_addr + toff + (uint32_t)(((cbg + q) ^ (rloc & 7)) << 4), g0, g1, g2, g3);
-                                        const uint32_t gw[4] = {g0, g1, g2, g3};
+                                        uint32_t gw[4];
+                                        ld_shared_v4(g_addr + toff + (uint32_t)(((cbg + q) ^ (rloc & 7)) << 4), gw[0], gw[1], gw[2], gw[3]);
 #pragma unroll
                                         for (int e = 0; e < 4; ++e) {
                                             const float2 gf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gw[e]));
@@ -522,28 +543,30 @@ __global__ void __launch_bounds__(FTHREADS, 1) chain_kernel(const __grid_constan
 #pragma unroll
                                     for (int j = 0; j < 32; ++j) v[j] = ((bits >> j) & 1u) ? v[j] : 0.f;
                                 }
-                                const uint32_t tile_addr = x_addr + (uint32_t)(n0 >> 6) * 16384u + (uint32_t)rloc * 128u;
-                                const int cb = (n0 & 63) >> 3;
+                                // first phase of a two-phase layer: the second n-half's MMAs must be done with X tile c/2
+                                if (two_half && hph == 0 && (u & 1) == 0) mbar_wait(&xfree[c >> 1], xf_phase);
 #pragma unroll
                                 for (int q = 0; q < 4; ++q)
-                                    st_shared_v4(tile_addr + (uint32_t)(((cb + q) ^ (rloc & 7)) << 4),
+                                    st_shared_v4(x_addr + toff + (uint32_t)(((cbg + q) ^ (rloc & 7)) << 4),
                                                  pack_bf16(v[q * 8 + 0], v[q * 8 + 1]), pack_bf16(v[q * 8 + 2], v[q * 8 + 3]),
                                                  pack_bf16(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16(v[q * 8 + 6], v[q * 8 + 7]));
                             }
+                            tcgen05_fence_before();
+                            fence_async_smem();
+                            if (gate_in) { __syncwarp(); if (lane == 0) mbar_arrive(g_empty); }
+                            epi_barrier();
+                            if (store_thread && (L.store_map >= 0 || (mish && L.gate_store_map >= 0))) {
+                                const int kb0 = two_half ? hph * (XT / 2) : 0, kb1 = two_half ? kb0 + XT / 2 : L.n / 64;
+                                if (L.store_map >= 0)
+                                    for (int kb = kb0; kb < kb1; ++kb) tma_store_2d(&maps.m[L.store_map], sX + kb * 16384, kb * 64, tile * FBM);
+                                if (mish && L.gate_store_map >= 0)
+                                    for (int kb = kb0; kb < kb1; ++kb) tma_store_2d(&maps.m[L.gate_store_map], sG + kb * 16384, kb * 64, tile * FBM);
+                                tma_store_commit();
+                            }
+                            __syncwarp();
+                            if (lane == 0) { mbar_arrive(&xready[two_half ? hph : 0]); if (!two_half) mbar_arrive(&xready[1]); }
                         }
-                        tcgen05_fence_before();
-                        fence_async_smem();
-                        if (gate_in) { __syncwarp(); if (lane == 0) mbar_arrive(g_empty); }
-                        epi_barrier();
-                        if (store_thread && (L.store_map >= 0 || (mish && L.gate_store_map >= 0))) {
-                            if (L.store_map >= 0)
-                                for (int kb = 0; kb < L.n / 64; ++kb) tma_store_2d(&maps.m[L.store_map], sX + kb * 16384, kb * 64, tile * FBM);
-                            if (mish && L.gate_store_map >= 0)
-                                for (int kb = 0; kb < L.n / 64; ++kb) tma_store_2d(&maps.m[L.gate_store_map], sG + kb * 16384, kb * 64, tile * FBM);
-                            tma_store_commit();
-                        }
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(x_full);
+                        if (two_half) xf_phase ^= 1;
                         if (L.colsum_slot >= 0) {
                             // bias gradient: column sums of the bf16 tile just written (valid rows only).  Runs while the
                             // next layer's MMAs already read X; the next epilogue's barrier orders it before X is rewritten.
@@ -564,11 +587,14 @@ __global__ void __launch_bounds__(FTHREADS, 1) chain_kernel(const __grid_constan
                         if (TIMING) t_gen += clock64() - c_epi;
                     } else {
                         // ---------------- final layer: eps of this row sits in TMEM columns [0, 32); each half takes 16
+                        mbar_wait(&acc_full[0], acc_phase[0]); acc_phase[0] ^= 1;
+                        if (TIMING) { const long long c1 = clock64(); t_acc += c1 - c_epi; c_epi = c1; }
+                        tcgen05_fence_after();
                         uint32_t r[16];
                         tmem_ld16(tmem_base + lane_base + (uint32_t)(half * 16), r);
                         tcgen05_fence_before();
                         // eps / log-prob modes touch neither X nor H0 from here on: hand TMEM back before the math
-                        if (!sampler) { __syncwarp(); if (lane == 0) mbar_arrive(x_full); }
+                        if (!sampler) { __syncwarp(); if (lane == 0) { mbar_arrive(&xready[0]); mbar_arrive(&xready[1]); } }
                         epi_barrier();                                  // sb (bias) visible
                         const int abase = half * 16;
                         float eps[16];
@@ -629,7 +655,7 @@ __global__ void __launch_bounds__(FTHREADS, 1) chain_kernel(const __grid_constan
                         }
                         __syncwarp();
                         // the sampler's last step hands over to the next tile's prologue instead
-                        if (lane == 0 && sampler && step + 1 < nsteps) mbar_arrive(x_full);
+                        if (lane == 0 && sampler && step + 1 < nsteps) { mbar_arrive(&xready[0]); mbar_arrive(&xready[1]); }
                         if (TIMING) t_fin += clock64() - c_epi;
                     }
                 }
