@@ -239,6 +239,7 @@ extern "C" int dppo_create(const dppo_cfg* cfg, int device, dppo_handle** out) {
     dppo_handle* h = new dppo_handle();
     h->cfg = *cfg; h->device = device; h->g = g; h->sm_count = prop.multiProcessorCount;
     { const char* dv = getenv("DPPO_DETERMINISTIC"); h->deterministic = (dv && dv[0] == '1') ? 1 : 0; }
+    { const char* cv = getenv("DPPO_CHAIN_CG"); h->chain_cg = (cv && cv[0] == '1') ? 1 : 2; }
     const size_t nA = g.ao.n, nC = g.co.n;
     const size_t total = 3 * nA + nC;
     CUDA_TRY(cudaMalloc(&h->params, total * sizeof(float)));
@@ -966,7 +967,7 @@ extern "C" int dppo_debug_mma_probe(dppo_handle* h, int grid, int mode, int iter
     CUDA_TRY(cudaSetDevice(h->device));
     if (!tc_shapes_ok(h)) DPPO_FAIL(-7, "tensor path unavailable");
     CUtensorMap wm;
-    DPPO_TRY(fc::weight_map(&wm, h->tc->net[DPPO_NET_ACTOR].w1, h->g.H, h->g.H));
+    DPPO_TRY(fc::weight_map(&wm, h->tc->net[DPPO_NET_ACTOR].w1, h->g.H, h->g.H, h->g.H, 1));
     long long* d = nullptr;
     CUDA_TRY(cudaMalloc(&d, (size_t)grid * 2 * sizeof(long long)));
     CUDA_TRY(cudaMemset(d, 0, (size_t)grid * 2 * sizeof(long long)));

@@ -145,6 +145,36 @@ __device__ __forceinline__ void umma_bf16_split(uint32_t tmem_d, uint32_t a_lo, 
                  ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate) : "memory");
 }
 
+// ---- CTA-pair (cta_group::2) helpers: the two CTAs of a cluster form one 256-row MMA; each holds its own 128 rows of A
+// and half of every B tile, the leader (rank 0) issues the MMAs and both CTAs' TMA loads report to the leader's barriers
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_rank0(uint32_t addr) {
+    uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(0)); return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t cluster_addr, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes) : "memory");
+}
+// TMA load whose completion bytes are reported to the mbarrier at the same offset in the pair's leader CTA
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_split_pair(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tmov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\tsetp.ne.b32 p, %5, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, {%6, %6, %6, %6, %6, %6, %6, %6}, p;\n\t}"
+                 ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+// commit that arrives on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void tcgen05_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+
 template <int H> constexpr size_t chain_smem_bytes() {
     return (size_t)(H / 64) * 16384 * (H == 256 ? 2 : 1) + H0_BYTES + (size_t)NSTAGE * STAGE_BYTES + 2 * 512 * sizeof(float) + 1024 + 256;
 }
@@ -213,9 +243,11 @@ __device__ __forceinline__ void build_h0_half(uint32_t h0_addr, int rloc, int ha
     }
 }
 
-template <int H, bool TIMING>
+template <int H, bool TIMING, int CG>
 __global__ void __launch_bounds__(FTHREADS, 1) chain_kernel(const __grid_constant__ Maps maps, const Params p) {
     constexpr int XT = H / 64;
+    constexpr int WKE = WK * CG;                                // k-rows per ring stage: a stage is [WKE][256 / CG] = 16 KB per CTA
+    constexpr int MPS = WKE / 16;                               // tcgen05.mma (K = 16) per stage
     constexpr int X_BYTES = XT * 16384;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -239,24 +271,33 @@ __global__ void __launch_bounds__(FTHREADS, 1) chain_kernel(const __grid_constan
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ntiles = (p.rows + FBM - 1) / FBM;
+    const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;     // rank inside the CTA pair (leader = 0)
+    const int pair0 = blockIdx.x / CG, npairs = gridDim.x / CG, ptiles = (ntiles + CG - 1) / CG;
     const bool sampler = p.final_mode == FINAL_SAMPLE;
     const int nsteps = sampler ? p.T : 1;
 
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < NMAPS; ++i) tma_prefetch_desc(&maps.m[i]);
-        for (int i = 0; i < NSTAGE; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-        mbar_init(h0_full, 1); mbar_init(h0_empty, 1);
-        mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1); mbar_init(&xready[0], 8); mbar_init(&xready[1], 8);
+        for (int i = 0; i < NSTAGE; ++i) { mbar_init(&w_full[i], CG); mbar_init(&w_empty[i], 1); }
+        mbar_init(h0_full, CG); mbar_init(h0_empty, 1);
+        mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1); mbar_init(&xready[0], 8 * CG); mbar_init(&xready[1], 8 * CG);
         for (int i = 0; i < 4; ++i) mbar_init(&xfree[i], 1);
         mbar_init(g_full, 1); mbar_init(g_empty, 8);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (CG == 2) cluster_sync_all();                            // barriers of both CTAs initialised before anything remote
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (CG == 1) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        }
     }
     tcgen05_fence_before();
     __syncthreads();
+    if (CG == 2) cluster_sync_all();
     tcgen05_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);    // warp-uniform for the compiler
 
@@ -268,12 +309,18 @@ __global__ void __launch_bounds__(FTHREADS, 1) chain_kernel(const __grid_constan
             long long t_wempty = 0;
             const uint32_t w_addr = smem_u32(sW);
             const uint32_t wfull_addr = smem_u32(w_full), wempty_addr = smem_u32(w_empty);
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            for (int pt = pair0; pt < ptiles; pt += npairs) {
+                const int tile = pt * CG + (int)rank;
                 if (p.h0_from_tma) {
                     mbar_wait(h0_empty, h0_phase ^ 1);
                     if (elect_one()) {
-                        mbar_expect_tx(h0_full, H0_BYTES);
-                        tma_load_2d(sH0, &maps.m[0], h0_full, 0, tile * FBM);
+                        if (CG == 1) {
+                            mbar_expect_tx(h0_full, H0_BYTES);
+                            tma_load_2d(sH0, &maps.m[0], h0_full, 0, tile * FBM);
+                        } else {   // own rows, but the arrival and the bytes go to the leader's barrier
+                            mbar_expect_tx_cluster(mapa_rank0(smem_u32(h0_full)), H0_BYTES);
+                            tma_load_2d_pair(smem_u32(sH0), &maps.m[0], smem_u32(h0_full), 0, tile * FBM);
+                        }
                     }
                     __syncwarp();
                     h0_phase ^= 1;
@@ -283,10 +330,11 @@ __global__ void __launch_bounds__(FTHREADS, 1) chain_kernel(const __grid_constan
                     for (int l = 0; l < p.nlayers; ++l) {
                         const Layer& L = p.L[net][l];
                         const int n_cur = L.n < 256 ? L.n : 256, nhc = L.n / n_cur;
-                        const int kx = L.a_src >= 1 ? H / WK : 0, kh = L.a_src != 1 ? 64 / WK : 0;
+                        const int kx = L.a_src >= 1 ? H / WKE : 0, kh = L.a_src != 1 ? 64 / WKE : 0;
                         const CUtensorMap* wm = &maps.m[L.wmap];
-                        const uint32_t tx = (uint32_t)(WK * n_cur * 2);
-                        const int nbox = n_cur / 64;
+                        const int n_mine = n_cur / CG;                     // this CTA's share of the B tile's columns
+                        const uint32_t tx = (uint32_t)(WKE * n_mine * 2);
+                        const int nbox = n_mine / 64;
                         if (HASG && L.gate_load_map >= 0) {
                             // gate tile of this layer: needed by its epilogue only, so it rides ahead of the weights
                             mbar_wait(g_empty, g_phase ^ 1); g_phase ^= 1;
@@ -297,7 +345,7 @@ __global__ void __launch_bounds__(FTHREADS, 1) chain_kernel(const __grid_constan
                             __syncwarp();
                         }
                         for (int nh = 0; nh < nhc; ++nh) {
-                            const int col = nh * n_cur;
+                            const int col = nh * n_cur + (int)rank * n_mine;
                             int krow = kx ? L.wrow_x : L.wrow_h0;
                             for (int s = 0; s < kx + kh; ++s) {
                                 if (s == kx) krow = L.wrow_h0;
@@ -305,17 +353,17 @@ __global__ void __launch_bounds__(FTHREADS, 1) chain_kernel(const __grid_constan
                                 if (TIMING) { const long long c0 = clock64(); mbar_wait_addr(wempty_addr + stage * 8, phase ^ 1); t_wempty += clock64() - c0; }
                                 else mbar_wait_addr(wempty_addr + stage * 8, phase ^ 1);
                                 if (elect_one()) {
-                                    mbar_expect_tx_addr(full_bar, tx);
                                     const uint32_t dst = w_addr + stage * STAGE_BYTES;
-                                    tma_load_2d_addr(dst, wm, full_bar, col, krow);
-                                    if (nbox == 4) {
-                                        tma_load_2d_addr(dst + 1 * (WK * 128), wm, full_bar, col + 64, krow);
-                                        tma_load_2d_addr(dst + 2 * (WK * 128), wm, full_bar, col + 128, krow);
-                                        tma_load_2d_addr(dst + 3 * (WK * 128), wm, full_bar, col + 192, krow);
+                                    if (CG == 1) {
+                                        mbar_expect_tx_addr(full_bar, tx);
+                                        for (int j = 0; j < nbox; ++j) tma_load_2d_addr(dst + j * (WKE * 128), wm, full_bar, col + j * 64, krow);
+                                    } else {
+                                        mbar_expect_tx_cluster(mapa_rank0(full_bar), tx);
+                                        for (int j = 0; j < nbox; ++j) tma_load_2d_pair(dst + j * (WKE * 128), wm, full_bar, col + j * 64, krow);
                                     }
                                 }
                                 __syncwarp();
-                                krow += WK;
+                                krow += WKE;
                                 if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                             }
                         }
@@ -334,19 +382,19 @@ __global__ void __launch_bounds__(FTHREADS, 1) chain_kernel(const __grid_constan
             const uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);          // SBO = 1024 B, version 1, SWIZZLE_128B
             const uint32_t a_lo_x = ((smem_u32(sX) >> 4) & 0x3FFFu) | (1u << 16);     // K-major A: LBO = 16 B
             const uint32_t a_lo_h0 = ((smem_u32(sH0) >> 4) & 0x3FFFu) | (1u << 16);
-            const uint32_t b_lo_0 = ((smem_u32(sW) >> 4) & 0x3FFFu) | ((uint32_t)(WK * 128 >> 4) << 16);   // MN-major B: LBO = one 64-column atom
+            const uint32_t b_lo_0 = ((smem_u32(sW) >> 4) & 0x3FFFu) | ((uint32_t)(WKE * 128 >> 4) << 16);  // MN-major B: LBO = one 64-column atom
             const uint32_t wfull_addr = smem_u32(w_full), wempty_addr = smem_u32(w_empty);
-            constexpr int S_HALF = (XT / 2) * (64 / WK);          // first ring stage that reads X tile XT/2
+            constexpr int S_HALF = (XT / 2) * (64 / WKE);         // first ring stage that reads X tile XT/2
             long long t_x = 0, t_w = 0; const long long t_begin = TIMING ? clock64() : 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            for (int pt = pair0; pt < ptiles && rank == 0; pt += npairs) {
                 bool h0_waited = false;
                 for (int step = 0; step < nsteps; ++step) {
                     const int net = (sampler && (p.T - 1 - step) < p.K && !p.use_base_policy) ? 1 : 0;
                     for (int l = 0; l < p.nlayers; ++l) {
                         const Layer& L = p.L[net][l];
                         const int n_cur = L.n < 256 ? L.n : 256, nhc = L.n / n_cur;
-                        const int kx = L.a_src >= 1 ? H / WK : 0, kh = L.a_src != 1 ? 64 / WK : 0;
-                        const uint32_t idesc = make_idesc(FBM, n_cur, false, true);
+                        const int kx = L.a_src >= 1 ? H / WKE : 0, kh = L.a_src != 1 ? 64 / WKE : 0;
+                        const uint32_t idesc = make_idesc(FBM * CG, n_cur, false, true);
                         const bool h0_rel = L.h0_last && p.h0_from_tma;
                         // xready[0]: the previous epilogue wrote X tiles [0, XT/2) (or H0) and drained the first accumulator half;
                         // xready[1]: tiles [XT/2, XT) and the second half.  The second wait is deferred to the first stage that needs it.
@@ -361,7 +409,7 @@ __global__ void __launch_bounds__(FTHREADS, 1) chain_kernel(const __grid_constan
                             uint32_t accf = 0u;
                             uint32_t a_lo = kx ? a_lo_x : a_lo_h0;
                             if (last_half_of_two && kx == 0) {            // this layer never reads X: the epilogue may overwrite it at once
-                                if (elect_one()) { for (int j = 0; j < XT / 2; ++j) tcgen05_commit(&xfree[j]); }
+                                if (elect_one()) { for (int j = 0; j < XT / 2; ++j) { if (CG == 1) tcgen05_commit(&xfree[j]); else tcgen05_commit_pair(smem_u32(&xfree[j])); } }
                                 __syncwarp();
                             }
                             for (int s = 0; s < kx + kh; ++s) {
@@ -374,25 +422,36 @@ __global__ void __launch_bounds__(FTHREADS, 1) chain_kernel(const __grid_constan
                                 else mbar_wait_addr(wfull_addr + stage * 8, phase);
                                 tcgen05_fence_after();
                                 const uint32_t b_lo = b_lo_0 + (uint32_t)stage * (STAGE_BYTES >> 4);
-                                const bool free_tile = last_half_of_two && (s & 1) && s < S_HALF && s < kx;
+                                // the stage that finishes X tile j (j < XT/2) in the last n-half frees it for the epilogue
+                                const bool free_tile = last_half_of_two && s < S_HALF && s < kx && (CG == 2 || (s & 1));
+                                const int tile_j = CG == 2 ? s : (s >> 1);
                                 if (elect_one()) {
-                                    umma_bf16_split(tmem_d, a_lo, b_lo, desc_hi, idesc, accf);
-                                    umma_bf16_split(tmem_d, a_lo + 2u, b_lo + (2048u >> 4), desc_hi, idesc, 1u);
-                                    tcgen05_commit_addr(wempty_addr + stage * 8);
-                                    if (free_tile) tcgen05_commit(&xfree[s >> 1]);     // X tile s/2 is not read again in this layer
+                                    if (CG == 1) {
+                                        umma_bf16_split(tmem_d, a_lo, b_lo, desc_hi, idesc, accf);
+                                        umma_bf16_split(tmem_d, a_lo + 2u, b_lo + (2048u >> 4), desc_hi, idesc, 1u);
+                                        tcgen05_commit_addr(wempty_addr + stage * 8);
+                                        if (free_tile) tcgen05_commit(&xfree[tile_j]);
+                                    } else {
+                                        umma_bf16_split_pair(tmem_d, a_lo, b_lo, desc_hi, idesc, accf);
+                                        umma_bf16_split_pair(tmem_d, a_lo + 2u, b_lo + (2048u >> 4), desc_hi, idesc, 1u);
+                                        umma_bf16_split_pair(tmem_d, a_lo + 4u, b_lo + (4096u >> 4), desc_hi, idesc, 1u);
+                                        umma_bf16_split_pair(tmem_d, a_lo + 6u, b_lo + (6144u >> 4), desc_hi, idesc, 1u);
+                                        tcgen05_commit_pair(wempty_addr + stage * 8);
+                                        if (free_tile) tcgen05_commit_pair(smem_u32(&xfree[tile_j]));
+                                    }
                                 }
                                 __syncwarp();
                                 accf = 1u;
-                                // next 32 columns of A: +64 B inside a 128-byte row, then on to the next 64-column tile
-                                a_lo += (s & 1) ? (16384u >> 4) - 4u : 4u;
+                                // CG = 1: next 32 columns of A (+64 B inside a 128-byte row, then the next 64-column tile); CG = 2: next tile
+                                if (CG == 1) a_lo += (s & 1) ? (16384u >> 4) - 4u : 4u; else a_lo += (16384u >> 4);
                                 if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                             }
-                            if (elect_one()) tcgen05_commit(&acc_full[nh]);
+                            if (elect_one()) { if (CG == 1) tcgen05_commit(&acc_full[nh]); else tcgen05_commit_pair(smem_u32(&acc_full[nh])); }
                             __syncwarp();
                         }
                         if (!xr1_waited) mbar_wait(&xready[1], xr_phase);
                         xr_phase ^= 1;
-                        if (h0_rel) { if (elect_one()) tcgen05_commit(h0_empty); __syncwarp(); }
+                        if (h0_rel) { if (elect_one()) { if (CG == 1) tcgen05_commit(h0_empty); else tcgen05_commit_pair(smem_u32(h0_empty)); } __syncwarp(); }
                     }
                 }
             }
@@ -407,6 +466,10 @@ __global__ void __launch_bounds__(FTHREADS, 1) chain_kernel(const __grid_constan
         const uint32_t x_addr = smem_u32(sX), h0_addr = smem_u32(sH0), g_addr = smem_u32(sG);
         const bool store_thread = (warp == 2 && lane == 0);
         uint32_t gfull_phase = 0;
+        // xready lives in the leader CTA: its MMA warp needs both CTAs' epilogues
+        const uint32_t xr0 = CG == 2 ? mapa_rank0(smem_u32(&xready[0])) : smem_u32(&xready[0]);
+        const uint32_t xr1 = CG == 2 ? mapa_rank0(smem_u32(&xready[1])) : smem_u32(&xready[1]);
+        auto arrive_xr = [&](uint32_t a) { if (CG == 2) mbar_arrive_cluster(a); else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory"); };
         const int etid = threadIdx.x - 64;                       // 0..255
         uint32_t acc_phase[2] = {0u, 0u}, xf_phase = 0u;
         int bias_buf = 0;
@@ -417,7 +480,8 @@ __global__ void __launch_bounds__(FTHREADS, 1) chain_kernel(const __grid_constan
         bool first = true;
         float csum[2][2] = {};                                   // column sums: thread etid (< H/2) owns columns 2*etid, 2*etid+1
         long long t_acc = 0, t_gen = 0, t_fin = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int pt = pair0; pt < ptiles; pt += npairs) {
+            const int tile = pt * CG + (int)rank;
             const int row = tile * FBM + rloc;
             const bool valid = row < p.rows;
             const float* obs_row = p.obs + (size_t)(valid ? row : 0) * p.Do;
@@ -442,9 +506,9 @@ __global__ void __launch_bounds__(FTHREADS, 1) chain_kernel(const __grid_constan
                 build_h0_half(h0_addr, rloc, half, x, obs_row, A, p.Do, p.T, p.T - 1, valid);
                 fence_async_smem();
                 __syncwarp();
-                if (lane == 0) { mbar_arrive(&xready[0]); mbar_arrive(&xready[1]); }
+                if (lane == 0) { arrive_xr(xr0); arrive_xr(xr1); }
             } else if (first) {
-                if (lane == 0) { mbar_arrive(&xready[0]); mbar_arrive(&xready[1]); }   // "TMEM is free" for the very first layer
+                if (lane == 0) { arrive_xr(xr0); arrive_xr(xr1); }   // "TMEM is free" for the very first layer
             }
             first = false;
             for (int step = 0; step < nsteps; ++step) {
@@ -564,13 +628,13 @@ __global__ void __launch_bounds__(FTHREADS, 1) chain_kernel(const __grid_constan
                                 tma_store_commit();
                             }
                             __syncwarp();
-                            if (lane == 0) { mbar_arrive(&xready[two_half ? hph : 0]); if (!two_half) mbar_arrive(&xready[1]); }
+                            if (lane == 0) { arrive_xr((two_half && hph == 1) ? xr1 : xr0); if (!two_half) arrive_xr(xr1); }
                         }
                         if (two_half) xf_phase ^= 1;
                         if (L.colsum_slot >= 0) {
                             // bias gradient: column sums of the bf16 tile just written (valid rows only).  Runs while the
                             // next layer's MMAs already read X; the next epilogue's barrier orders it before X is rewritten.
-                            const int nrows = min(FBM, p.rows - tile * FBM);
+                            const int nrows = max(0, min(FBM, p.rows - tile * FBM));
                             if (etid < H / 2) {
                                 const int kb = etid >> 5, w = etid & 31;
                                 const uint32_t base = x_addr + (uint32_t)kb * 16384u + (uint32_t)(w & 3) * 4u;
@@ -594,7 +658,7 @@ __global__ void __launch_bounds__(FTHREADS, 1) chain_kernel(const __grid_constan
                         tmem_ld16(tmem_base + lane_base + (uint32_t)(half * 16), r);
                         tcgen05_fence_before();
                         // eps / log-prob modes touch neither X nor H0 from here on: hand TMEM back before the math
-                        if (!sampler) { __syncwarp(); if (lane == 0) { mbar_arrive(&xready[0]); mbar_arrive(&xready[1]); } }
+                        if (!sampler) { __syncwarp(); if (lane == 0) { arrive_xr(xr0); arrive_xr(xr1); } }
                         epi_barrier();                                  // sb (bias) visible
                         const int abase = half * 16;
                         float eps[16];
@@ -655,7 +719,7 @@ __global__ void __launch_bounds__(FTHREADS, 1) chain_kernel(const __grid_constan
                         }
                         __syncwarp();
                         // the sampler's last step hands over to the next tile's prologue instead
-                        if (lane == 0 && sampler && step + 1 < nsteps) { mbar_arrive(&xready[0]); mbar_arrive(&xready[1]); }
+                        if (lane == 0 && sampler && step + 1 < nsteps) { arrive_xr(xr0); arrive_xr(xr1); }
                         if (TIMING) t_fin += clock64() - c_epi;
                     }
                 }
@@ -670,31 +734,49 @@ __global__ void __launch_bounds__(FTHREADS, 1) chain_kernel(const __grid_constan
     }
     tcgen05_fence_before();
     __syncthreads();
+    if (CG == 2) cluster_sync_all();        // the peer may still be signalling our barriers / reading our B halves
     if (warp == 1) {
         tcgen05_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        if (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 
 // ------------------------------------------------------------------ host side
-// weight operand [K][N] bf16 row-major: box [WK k][64 n]
-static int weight_map(CUtensorMap* m, const void* base, uint64_t K, uint64_t N) { return make_map(m, base, K, N, N, WK, 64); }
+// weight operand [K][N] bf16 row-major (leading dimension ld): box [WK * cg k][64 n]
+static int weight_map(CUtensorMap* m, const void* base, uint64_t K, uint64_t N, uint64_t ld, int cg) { return make_map(m, base, K, N, ld, WK * cg, 64); }
 // row tile source / destination [rows][cols] bf16 row-major: box [128 rows][64 cols]
 static int rowtile_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols) { return make_map(m, base, rows, cols, cols, FBM, 64); }
 
-template <int H>
+// number of CTAs a chain launch uses (cg = 2: CTA pairs, an even grid)
+static int chain_grid(const dppo_handle* h, int rows, int cg) {
+    const int ntiles = (rows + FBM - 1) / FBM;
+    if (cg == 1) return ntiles < h->sm_count ? ntiles : h->sm_count;
+    const int pairs = (ntiles + 1) / 2, maxp = h->sm_count / 2;
+    return 2 * (pairs < maxp ? pairs : maxp);
+}
+
+template <int H, int CG>
 static int launch_chain_t(dppo_handle* h, cudaStream_t s, const Maps& maps, const Params& p, double flops) {
-    auto kern = p.dbg ? chain_kernel<H, true> : chain_kernel<H, false>;
+    auto kern = p.dbg ? chain_kernel<H, true, CG> : chain_kernel<H, false, CG>;
     static bool attr_set = false;
     if (!attr_set) {
-        CUDA_TRY(cudaFuncSetAttribute(chain_kernel<H, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_smem_bytes<H>()));
-        CUDA_TRY(cudaFuncSetAttribute(chain_kernel<H, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_smem_bytes<H>()));
+        CUDA_TRY(cudaFuncSetAttribute(chain_kernel<H, true, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_smem_bytes<H>()));
+        CUDA_TRY(cudaFuncSetAttribute(chain_kernel<H, false, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_smem_bytes<H>()));
         attr_set = true;
     }
-    const int ntiles = (p.rows + FBM - 1) / FBM;
-    const int grid = ntiles < h->sm_count ? ntiles : h->sm_count;
+    const int grid = chain_grid(h, p.rows, CG);
     prof_begin(h, s);
-    kern<<<grid, FTHREADS, chain_smem_bytes<H>(), s>>>(maps, p);
+    if (CG == 1) {
+        kern<<<grid, FTHREADS, chain_smem_bytes<H>(), s>>>(maps, p);
+    } else {
+        cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1; cfg.blockDim = dim3(FTHREADS); cfg.gridDim = dim3(grid); cfg.dynamicSmemBytes = chain_smem_bytes<H>(); cfg.stream = s;
+        cudaError_t le = cudaLaunchKernelEx(&cfg, kern, maps, p);
+        if (le != cudaSuccess) DPPO_FAIL(-3, "fused chain (CTA pair) launch failed: %s", cudaGetErrorString(le));
+    }
     prof_end(h, s, flops, 0);
     h->launches++; h->tc_launches++; h->fused_launches++;
     cudaError_t e = cudaGetLastError();
@@ -702,8 +784,9 @@ static int launch_chain_t(dppo_handle* h, cudaStream_t s, const Maps& maps, cons
     return 0;
 }
 static int launch_chain(dppo_handle* h, cudaStream_t s, int H, const Maps& maps, const Params& p, double flops) {
-    if (H == 512) return launch_chain_t<512>(h, s, maps, p, flops);
-    if (H == 256) return launch_chain_t<256>(h, s, maps, p, flops);
+    const int cg = h->chain_cg;
+    if (H == 512) return cg == 2 ? launch_chain_t<512, 2>(h, s, maps, p, flops) : launch_chain_t<512, 1>(h, s, maps, p, flops);
+    if (H == 256) return cg == 2 ? launch_chain_t<256, 2>(h, s, maps, p, flops) : launch_chain_t<256, 1>(h, s, maps, p, flops);
     DPPO_FAIL(-7, "fused chain: unsupported hidden width %d", H);
 }
 

@@ -15,7 +15,7 @@
 //   dv, dh1, du     [N][H] bf16 gradients; deps / dvalue are padded to [N][64] bf16
 // Weights: fp32 masters stay in h->params; bf16 operand copies are rebuilt after every update:
 //   w2w0 [(H+KP0)][H] = [W2 ; W0 rows in h0 order]   (MN-major B of the forward layers, K-major B of dX)
-//   w1   [H][H],  w3t [64][H] = W3^T (zero padded),  w3p [H][64] = W3 (zero padded),  w1t / w2t = W1^T / W2^T
+//   w1   [H][H],  w3t [64][H] = W3^T (zero padded),  w3p [H][128] = W3 (zero padded),  w1t / w2t = W1^T / W2^T
 #pragma once
 #include "common.cuh"
 #include "simt_kernels.cuh"
@@ -57,8 +57,8 @@ __global__ void tc_pack_actor_kernel(const float* __restrict__ w, ActorOff o, in
         int a = (int)(i / H), k = (int)(i % H);
         w3t[i] = __float2bfloat16(a < A ? w[o.w3 + (size_t)k * A + a] : 0.f);
     }
-    for (size_t i = i0; i < (size_t)H * 64; i += stride) {
-        int k = (int)(i / 64), a = (int)(i % 64);
+    for (size_t i = i0; i < (size_t)H * 128; i += stride) {
+        int k = (int)(i / 128), a = (int)(i % 128);
         w3p[i] = __float2bfloat16(a < A ? w[o.w3 + (size_t)k * A + a] : 0.f);
     }
 }
@@ -77,7 +77,7 @@ __global__ void tc_pack_critic_kernel(const float* __restrict__ w, CriticOff o, 
         w2w0[(size_t)Hc * Hc + i] = __float2bfloat16(v);
     }
     for (size_t i = i0; i < (size_t)64 * Hc; i += stride) { int a = (int)(i / Hc), k = (int)(i % Hc); w3t[i] = __float2bfloat16(a == 0 ? w[o.w3 + k] : 0.f); }
-    for (size_t i = i0; i < (size_t)Hc * 64; i += stride) { int k = (int)(i / 64), a = (int)(i % 64); w3p[i] = __float2bfloat16(a == 0 ? w[o.w3 + k] : 0.f); }
+    for (size_t i = i0; i < (size_t)Hc * 128; i += stride) { int k = (int)(i / 128), a = (int)(i % 128); w3p[i] = __float2bfloat16(a == 0 ? w[o.w3 + k] : 0.f); }
     for (size_t i = i0; i < (size_t)Hc; i += stride) bias2[i] = w[o.b2 + i] + w[o.bin + i];
 }
 // h0[r] = [x[r] | obs[r / obs_div] | onehot(t_r) | 1 | 0..]; one thread per 8 consecutive columns (16-byte store)
@@ -284,7 +284,7 @@ static int tc_init(dppo_handle* h) {
         CUDA_TRY(cudaMalloc(&w.w3t, (size_t)64 * H * sizeof(bf16)));
         CUDA_TRY(cudaMalloc(&w.w1t, (size_t)H * H * sizeof(bf16)));
         CUDA_TRY(cudaMalloc(&w.w2t, (size_t)H * H * sizeof(bf16)));
-        CUDA_TRY(cudaMalloc(&w.w3p, (size_t)H * 64 * sizeof(bf16)));
+        CUDA_TRY(cudaMalloc(&w.w3p, (size_t)H * 128 * sizeof(bf16)));
         CUDA_TRY(cudaMalloc(&w.bias2, (size_t)H * sizeof(float)));
     }
     return 0;
@@ -347,20 +347,21 @@ static bool fc_critic_ok(const dppo_handle* h) { return fc_net_ok(h, fc_critic_n
 
 static int fc_weight_maps(const dppo_handle* h, const FcNet& n, CUtensorMap* m) {
     const TcNetW& W = h->tc->net[n.net]; const int H = n.H;
-    DPPO_TRY(fc::weight_map(&m[0], W.w2w0, H + 64, H));
-    DPPO_TRY(fc::weight_map(&m[1], W.w1, H, H));
-    DPPO_TRY(fc::weight_map(&m[2], W.w3p, H, 64));
+    const int cg = h->chain_cg;
+    DPPO_TRY(fc::weight_map(&m[0], W.w2w0, H + 64, H, H, cg));
+    DPPO_TRY(fc::weight_map(&m[1], W.w1, H, H, H, cg));
+    DPPO_TRY(fc::weight_map(&m[2], W.w3p, H, 64 * cg, 128, cg));      // a CTA pair splits N: the output layer is padded to 128 columns
     return 0;
 }
 // forward program: L0 act(H0 W0 + b0), L1 act(X W1 + b1), L2 X W2 + H0 W0 + b2, L3 X W3 + b3; weight maps at m[wbase..wbase+2]
-static void fc_fwd_layers(const FcNet& n, int wbase, fc::Layer* L) {
+static void fc_fwd_layers(const dppo_handle* h, const FcNet& n, int wbase, fc::Layer* L) {
     const int H = n.H;
     memset(L, 0, sizeof(fc::Layer) * fc::MAXL);
     for (int i = 0; i < fc::MAXL; ++i) { L[i].store_map = -1; L[i].gate_store_map = -1; L[i].gate_load_map = -1; L[i].colsum_slot = -1; }
     L[0].a_src = 0; L[0].wmap = wbase; L[0].wrow_h0 = H; L[0].n = H; L[0].bias = n.b0; L[0].act = n.act1;
     L[1].a_src = 1; L[1].wmap = wbase + 1; L[1].n = H; L[1].bias = n.b1; L[1].act = n.act1;
     L[2].a_src = 2; L[2].wmap = wbase; L[2].wrow_h0 = H; L[2].n = H; L[2].bias = n.b2; L[2].h0_last = 1;
-    L[3].a_src = 1; L[3].wmap = wbase + 2; L[3].n = 64; L[3].bias = n.b3;
+    L[3].a_src = 1; L[3].wmap = wbase + 2; L[3].n = 64 * h->chain_cg; L[3].bias = n.b3;
 }
 // algorithmic flops (un-padded dims, time-MLP excluded): forward F = 2 (din H + 2 H^2 + H NO) per row
 static double fc_fwd_flops(const FcNet& n, double rows) { const double H = n.H; return 2.0 * rows * (n.din * H + 2.0 * H * H + H * n.NO); }
@@ -379,7 +380,7 @@ static int fc_infer(dppo_handle* h, cudaStream_t s, const FcNet& n, const bf16* 
     DPPO_TRY(fc_weight_maps(h, n, &maps.m[1]));
     for (int i = 4; i < fc::NMAPS; ++i) maps.m[i] = maps.m[0];
     p.nlayers = 4; p.final_mode = mode; p.h0_from_tma = 1;
-    fc_fwd_layers(n, 1, p.L[0]);
+    fc_fwd_layers(h, n, 1, p.L[0]);
     p.out = out; p.prev = prev; p.next = next; p.chains = chains; p.trow = trow;
     return fc::launch_chain(h, s, n.H, maps, p, fc_fwd_flops(n, N));
 }
@@ -400,7 +401,7 @@ static int fc_train_fwd(dppo_handle* h, cudaStream_t s, const FcNet& n, const bf
     DPPO_TRY(fc::rowtile_map(&maps.m[6], v, N, H));
     maps.m[7] = maps.m[0]; maps.m[8] = maps.m[0]; maps.m[9] = maps.m[0];
     p.nlayers = 4; p.final_mode = fc::FINAL_EPS; p.h0_from_tma = 1;
-    fc_fwd_layers(n, 1, p.L[0]);
+    fc_fwd_layers(h, n, 1, p.L[0]);
     p.L[0][0].store_map = 4; p.L[0][1].store_map = 5; p.L[0][2].store_map = 6;
     if (n.act1 == 1) { p.L[0][0].mask_out = m0; p.L[0][1].mask_out = m1; }
     else {
@@ -419,9 +420,9 @@ static int fc_bwd(dppo_handle* h, cudaStream_t s, const FcNet& n, const bf16* do
     const int H = n.H; const TcNetW& W = h->tc->net[n.net];
     fc::Maps maps; fc::Params p; fc_common(h, p, N, n.NO);
     DPPO_TRY(fc::rowtile_map(&maps.m[0], doutb, N, 64));
-    DPPO_TRY(fc::weight_map(&maps.m[1], W.w3t, 64, H));
-    DPPO_TRY(fc::weight_map(&maps.m[2], W.w2t, H, H));
-    DPPO_TRY(fc::weight_map(&maps.m[3], W.w1t, H, H));
+    DPPO_TRY(fc::weight_map(&maps.m[1], W.w3t, 64, H, H, h->chain_cg));
+    DPPO_TRY(fc::weight_map(&maps.m[2], W.w2t, H, H, H, h->chain_cg));
+    DPPO_TRY(fc::weight_map(&maps.m[3], W.w1t, H, H, H, h->chain_cg));
     DPPO_TRY(fc::rowtile_map(&maps.m[4], dv, N, H));
     DPPO_TRY(fc::rowtile_map(&maps.m[5], dh1, N, H));
     DPPO_TRY(fc::rowtile_map(&maps.m[6], du, N, H));
@@ -451,8 +452,8 @@ static int fc_sample(dppo_handle* h, cudaStream_t s, const float* obs, int B, in
     DPPO_TRY(fc_weight_maps(h, nf, &maps.m[4]));
     maps.m[0] = maps.m[1]; maps.m[7] = maps.m[1]; maps.m[8] = maps.m[1]; maps.m[9] = maps.m[1];
     p.nlayers = 4; p.final_mode = fc::FINAL_SAMPLE; p.h0_from_tma = 0;
-    fc_fwd_layers(nb, 1, p.L[0]);
-    fc_fwd_layers(nf, 4, p.L[1]);
+    fc_fwd_layers(h, nb, 1, p.L[0]);
+    fc_fwd_layers(h, nf, 4, p.L[1]);
     p.obs = obs; p.xT = xT; p.noise = noise; p.actions = actions; p.chains_out = chains; p.hp = hp; p.use_base_policy = use_base;
     p.seed = seed; p.offset = offset; p.row_offset = row_offset;
     return fc::launch_chain(h, s, nb.H, maps, p, fc_fwd_flops(nb, B) * h->g.T);
@@ -573,7 +574,7 @@ static size_t tc_part_floats(const dppo_handle* h, int H) {
 // fused backward chain of one net (dv, dh1, du) + its bias column sums
 static int tc_mlp_backward_dx(dppo_handle* h, cudaStream_t s, const TcMlp& m, const bf16* doutb, int N, float* part, float* gnet, size_t ob1, size_t ob2) {
     const int H = m.H;
-    const int grid = (N + 127) / 128 < h->sm_count ? (N + 127) / 128 : h->sm_count;
+    const int grid = fc::chain_grid(h, N, h->chain_cg);
     float* cpart = m.cpart ? m.cpart : part;                   // [grid][2][H]; `part` is consumed before anything reuses it
     DPPO_TRY(fc_bwd(h, s, m.net == DPPO_NET_CRITIC ? fc_critic_net(h) : fc_actor_net(h, m.net), doutb, N, m.m0, m.m1, m.pre0, m.pre1,
                     m.dv, m.dh1, m.du, cpart));
@@ -611,7 +612,7 @@ static int tc_mlp_backward(dppo_handle* h, cudaStream_t s, const TcMlp& m, const
         return 0;
     }
     // dv = dout W3^T
-    tc::Gemm g = gemm_of(opK(doutb, N, 64, 64), opK(W.w3p, H, 64, 64), N, H);
+    tc::Gemm g = gemm_of(opK(doutb, N, 64, 64), opK(W.w3p, H, 64, 128), N, H);
     g.epi.out_bf16 = m.dv; g.epi.ld_bf16 = H;
     DPPO_TRY(tc_run(h, s, g));
     // dh1 = (dv W2^T) * act'(h1)
