@@ -207,20 +207,29 @@ static GemmP gp(const float* A, int lda, const float* B, int ldb, float* C, int 
 static inline int nblk(size_t n, int b) { return (int)((n + b - 1) / b); }
 
 // ------------------------------------------------------------------ derived tables
+// w0p (the packed fp32 layer-0 weight of the FFMA path) is rebuilt lazily: the tensor mode rarely needs it
+static int ensure_w0p(dppo_handle* h, int net, cudaStream_t s) {
+    const Geom& g = h->g;
+    if (!h->w0p_dirty[net]) return 0;
+    if (net == DPPO_NET_CRITIC)
+        pack_w0_kernel<<<nblk((size_t)g.KPc * g.Hc, 256), 256, 0, s>>>(h->net_w[net] + g.co.win, 0, 0, g.Do, g.KPc, g.Hc, h->ad[net].w0p);
+    else
+        pack_w0_kernel<<<nblk((size_t)g.KP * g.H, 256), 256, 0, s>>>(h->net_w[net] + g.ao.win, g.A, g.td, g.Do, g.KP, g.H, h->ad[net].w0p);
+    KLAUNCH(h); KCHECK();
+    h->w0p_dirty[net] = 0;
+    return 0;
+}
 static int prep_net(dppo_handle* h, int net, cudaStream_t s) {
     const Geom& g = h->g;
-    if (net == DPPO_NET_CRITIC) {
-        pack_w0_kernel<<<nblk((size_t)g.KPc * g.Hc, 256), 256, 0, s>>>(h->net_w[net] + g.co.win, 0, 0, g.Do, g.KPc, g.Hc, h->ad[net].w0p);
-        KLAUNCH(h); KCHECK();
-    } else {
+    h->w0p_dirty[net] = 1;
+    if (net != DPPO_NET_CRITIC) {
         ActorDerived& d = h->ad[net];
         int threads = g.H < 64 ? 64 : (g.H > 512 ? 512 : round_up(g.H, 32));
         if (threads < 2 * g.td) threads = round_up(2 * g.td, 32);
         actor_prep_kernel<<<g.T, threads, 4 * g.td * sizeof(float), s>>>(h->net_w[net], g.ao, g.A, g.td, g.H, d.sinemb, d.thpre, d.temb, d.bt);
         KLAUNCH(h); KCHECK();
-        pack_w0_kernel<<<nblk((size_t)g.KP * g.H, 256), 256, 0, s>>>(h->net_w[net] + g.ao.win, g.A, g.td, g.Do, g.KP, g.H, d.w0p);
-        KLAUNCH(h); KCHECK();
     }
+    if (h->cfg.precision == DPPO_PREC_FP32) DPPO_TRY(ensure_w0p(h, net, s));
     return tc_refresh_net(h, net, s);
 }
 
@@ -363,6 +372,7 @@ static int actor_fwd_fp32(dppo_handle* h, cudaStream_t s, int net, const float* 
                           const int* trow, int tconst, FwdBufs& b) {
     const Geom& g = h->g; const float* w = h->net_w[net]; const ActorDerived& d = h->ad[net];
     const int act1 = h->cfg.actor_act + 1;
+    DPPO_TRY(ensure_w0p(h, net, s));
     pack_h0_kernel<<<nblk((size_t)N * g.KP, 256), 256, 0, s>>>(x, obs, N, g.A, g.Do, g.KP, obs_div, b.h0p); KLAUNCH(h); KCHECK();
     GemmP p = gp(b.h0p, g.KP, d.w0p, g.H, b.u, g.H, N, g.H, g.KP);
     p.btab = d.bt; p.ldbt = g.H; p.trow = trow; p.tconst = tconst;
@@ -378,6 +388,7 @@ static int actor_fwd_fp32(dppo_handle* h, cudaStream_t s, int net, const float* 
 static int critic_fwd_fp32(dppo_handle* h, cudaStream_t s, const float* obs, int N, FwdBufs& b) {
     const Geom& g = h->g; const float* w = h->net_w[DPPO_NET_CRITIC]; const ActorDerived& d = h->ad[DPPO_NET_CRITIC];
     const int act1 = h->cfg.critic_act + 1;
+    DPPO_TRY(ensure_w0p(h, DPPO_NET_CRITIC, s));
     pack_h0_kernel<<<nblk((size_t)N * g.KPc, 256), 256, 0, s>>>(nullptr, obs, N, 0, g.Do, g.KPc, 1, b.h0p); KLAUNCH(h); KCHECK();
     GemmP p = gp(b.h0p, g.KPc, d.w0p, g.Hc, b.u, g.Hc, N, g.Hc, g.KPc); p.bias = w + g.co.bin;
     DPPO_TRY(gemm(h, s, false, false, p) < 0 ? -3 : 0);
@@ -956,8 +967,12 @@ extern "C" int dppo_debug_chain_timing(dppo_handle* h, int enable, long long* ou
     if (!h) DPPO_FAIL(-1, "null handle");
     CUDA_TRY(cudaSetDevice(h->device));
     if (sm_count) *sm_count = h->sm_count;
-    if (enable && !h->chain_dbg) { CUDA_TRY(cudaMalloc(&h->chain_dbg, (size_t)h->sm_count * 8 * sizeof(long long))); CUDA_TRY(cudaMemset(h->chain_dbg, 0, (size_t)h->sm_count * 8 * sizeof(long long))); }
-    if (out_host && h->chain_dbg) { CUDA_TRY(cudaDeviceSynchronize()); CUDA_TRY(cudaMemcpy(out_host, h->chain_dbg, (size_t)h->sm_count * 8 * sizeof(long long), cudaMemcpyDeviceToHost)); }
+    const size_t bytes = (size_t)16 * h->sm_count * 8 * sizeof(long long);     // 16 launch slots, round robin; reading resets the slot index
+    if (enable && !h->chain_dbg) { CUDA_TRY(cudaMalloc(&h->chain_dbg, bytes)); CUDA_TRY(cudaMemset(h->chain_dbg, 0, bytes)); h->chain_dbg_idx = 0; }
+    if (out_host && h->chain_dbg) {
+        CUDA_TRY(cudaDeviceSynchronize()); CUDA_TRY(cudaMemcpy(out_host, h->chain_dbg, bytes, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemset(h->chain_dbg, 0, bytes)); h->chain_dbg_idx = 0;
+    }
     if (!enable && h->chain_dbg) { CUDA_TRY(cudaDeviceSynchronize()); cudaFree(h->chain_dbg); h->chain_dbg = nullptr; }
     return 0;
 }

@@ -602,14 +602,21 @@ __global__ void time_backward_kernel(const float* __restrict__ w, ActorOff o, in
         }
         if (gridDim.x > 1) return;
     }
-    // d temb[t][j] = sum_c W_in[A+j][c] * G[t][c]: one warp per output, lanes stride over c (coalesced), shuffle reduce
-    for (int i = tid >> 5; i < T * td; i += nt >> 5) {
-        int t = i / td, j = i % td;
-        float s = 0.f;
-        for (int c = tid & 31; c < H; c += 32) s = fmaf(w[o.win + (size_t)(A + j) * H + c], G[(size_t)t * H + c], s);
+    // d temb[t][j] = sum_c W_in[A+j][c] * G[t][c]: one warp per j keeps its W_in row in registers (H <= 1024) and walks t;
+    // the H/32 loads of a step are independent, so the load latency is paid ~T times, not T*H/32 times
+    for (int j = tid >> 5; j < td; j += nt >> 5) {
+        const int lane = tid & 31;
+        float wr[32];
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-        if ((tid & 31) == 0) dte[i] = s;
+        for (int q = 0; q < 32; ++q) { const int c = lane + q * 32; wr[q] = c < H ? w[o.win + (size_t)(A + j) * H + c] : 0.f; }
+        for (int t = 0; t < T; ++t) {
+            float s = 0.f;
+#pragma unroll
+            for (int q = 0; q < 32; ++q) { const int c = lane + q * 32; if (c < H) s = fmaf(wr[q], G[(size_t)t * H + c], s); }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+            if (lane == 0) dte[t * td + j] = s;
+        }
     }
     __syncthreads();
     for (int i = tid; i < T * 2 * td; i += nt) {    // d hidden pre-activation

@@ -365,12 +365,13 @@ static void fc_fwd_layers(const dppo_handle* h, const FcNet& n, int wbase, fc::L
 }
 // algorithmic flops (un-padded dims, time-MLP excluded): forward F = 2 (din H + 2 H^2 + H NO) per row
 static double fc_fwd_flops(const FcNet& n, double rows) { const double H = n.H; return 2.0 * rows * (n.din * H + 2.0 * H * H + H * n.NO); }
-static void fc_common(const dppo_handle* h, fc::Params& p, int N, int NO) {
+static void fc_common(dppo_handle* h, fc::Params& p, int N, int NO) {
     const Geom& g = h->g;
     memset(&p, 0, sizeof(p));
     p.rows = N; p.A = NO; p.Do = g.Do; p.T = g.T; p.K = g.K; p.sch = h->sched;
     p.dcv = h->cfg.denoised_clip_value; p.min_lp_std = h->cfg.min_logprob_denoising_std;
-    p.dbg = h->chain_dbg;
+    // dev tool: each chain launch gets its own slot of [sm_count][8] counters (16 slots, round robin)
+    p.dbg = h->chain_dbg ? h->chain_dbg + (size_t)(h->chain_dbg_idx++ & 15) * h->sm_count * 8 : nullptr;
 }
 // inference forward from a packed h0: final = output store (eps / value) or Gaussian log-prob
 static int fc_infer(dppo_handle* h, cudaStream_t s, const FcNet& n, const bf16* h0, int N, int mode, float* out,
@@ -769,19 +770,19 @@ static int tc_ppo_begin(dppo_handle* h, cudaStream_t s, int N, int chunk_rows, i
     P.eps = ws_take<float>(h, (size_t)NC * g.A); P.val = ws_take<float>(h, NC);
     P.depsb = ws_take<bf16>(h, (size_t)NC * 64); P.dvalb = ws_take<bf16>(h, (size_t)NC * 64);
     P.part = ws_take<float>(h, pf);
-    P.dw0a = ws_take<float>(h, (size_t)KP0 * g.H); P.dw0c = ws_take<float>(h, (size_t)KP0 * g.Hc);
     P.bsum = ws_take<double>(h, (size_t)P.max_blocks * 5);
     P.colb3 = ws_take<float>(h, (size_t)P.max_blocks * (g.A + 1));
+    // the four accumulators below are adjacent so that one memset clears them
+    P.dw0a = ws_take<float>(h, (size_t)KP0 * g.H); P.dw0c = ws_take<float>(h, (size_t)KP0 * g.Hc);
     P.cpa = ws_take<float>(h, n_cpa); P.cpc = ws_take<float>(h, n_cpc);
+    const size_t acc_bytes = (size_t)((char*)(P.cpc + n_cpc) - (char*)P.dw0a);
     P.ma.h0 = P.h0; P.mc.h0 = P.h0; P.ma.out = P.eps; P.mc.out = P.val;
     const bool defer = P.ma.fused && P.mc.fused && !h->deterministic;
     if (!defer && nchunks > 1) DPPO_FAIL(-7, "tc_ppo_begin: chunked accumulation needs the fused chain kernels");
     if (!h->deterministic) {   // the dW GEMMs accumulate atomically into the gradient buffers
         CUDA_TRY(cudaMemsetAsync(h->grads, 0, (nA + nC) * sizeof(float), s));
-        CUDA_TRY(cudaMemsetAsync(P.dw0a, 0, (size_t)KP0 * g.H * sizeof(float), s));
-        CUDA_TRY(cudaMemsetAsync(P.dw0c, 0, (size_t)KP0 * g.Hc * sizeof(float), s));
+        CUDA_TRY(cudaMemsetAsync(P.dw0a, 0, acc_bytes, s));
     }
-    if (defer) { CUDA_TRY(cudaMemsetAsync(P.cpa, 0, n_cpa * sizeof(float), s)); CUDA_TRY(cudaMemsetAsync(P.cpc, 0, n_cpc * sizeof(float), s)); }
     PpoHyper& hp = P.hp;
     hp.A = g.A; hp.Da = h->cfg.action_dim; hp.K = g.K; hp.T = g.T; hp.reward_horizon = h->cfg.reward_horizon; hp.norm_adv = h->cfg.norm_adv;
     hp.dcv = h->cfg.denoised_clip_value; hp.min_lp_std = h->cfg.min_logprob_denoising_std;

@@ -204,7 +204,7 @@ int dppo_debug_tc_gemm(dppo_handle* h, const void* A, int a_mn, int64_t lda, con
                        const void* B, int b_mn, int64_t ldb, int M, int N, int K, int splits,
                        const float* bias, int act, float* out_f32, void* out_bf16, dppo_stream_t s);
 /* Dev tool: per-CTA cycle counters of the fused chain kernel.  enable != 0 allocates them; out_host (optional)
- * receives HOST [sm_count][8] = {producer wait w_empty, mma wait x_full, mma wait w_full, mma total,
+ * receives HOST [16 launch slots][sm_count][8] (slot = chain launches since the last read, round robin) = {producer wait w_empty, mma wait x_full, mma wait w_full, mma total,
  * epilogue wait acc_full, epilogue generic layers, epilogue final layer, 0} of the last launch. */
 int dppo_debug_chain_timing(dppo_handle* h, int enable, long long* out_host, int* sm_count);
 /* Dev probe: tcgen05.mma issue cost, TMA round trip and TMA throughput per SM; see tools/mma_probe.py. */

@@ -1,4 +1,4 @@
-"""Dev tool: per-role cycle counters of the fused chain kernel (dppo_debug_chain_timing)."""
+"""Dev tool: per-role cycle counters of the fused chain kernel launches (dppo_debug_chain_timing)."""
 import sys, os, ctypes as C
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -13,22 +13,23 @@ b = bench.make_gpu_batches(e, N, 1, seed=3)[0]
 obs = torch.rand(B, e.Do, device="cuda") * 2 - 1
 nsm = C.c_int(0)
 L.check(e.lib.dppo_debug_chain_timing(e.h, 1, None, C.byref(nsm)))
-buf = np.zeros((nsm.value, 8), np.int64)
-names = ["prod_wait_wempty", "mma_wait_xfull", "mma_wait_wfull", "mma_total", "epi_wait_acc", "epi_generic", "epi_final", "-"]
-def report(tag):
+buf = np.zeros((16, nsm.value, 8), np.int64)
+names = ["prod_wait_wempty", "mma_wait_xready", "mma_wait_wfull", "mma_total", "epi_wait_acc", "epi_generic", "epi_final"]
+def read():
     L.check(e.lib.dppo_debug_chain_timing(e.h, 1, buf.ctypes.data_as(C.c_void_p), None))
-    act = buf[buf[:, 3] > 0]
-    print(tag, f"({len(act)} CTAs)", {n: int(act[:, i].mean()) for i, n in enumerate(names[:7])}, "max total", int(act[:, 3].max()))
-def timed(fn, n=3):
-    fn(); torch.cuda.synchronize()
-    a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(n): fn()
-    c.record(); torch.cuda.synchronize()
-    return a.elapsed_time(c) / n
-print(f"logprobs N={N}: {timed(lambda: e.logprobs_subsample(b[0], b[1], b[2], b[3])):.3f} ms"); report("logprobs")
-print(f"sample B={B}: {timed(lambda: e.sample(obs, seed=1, offset=2)):.3f} ms"); report("sample")
-print(f"value N={N}: {timed(lambda: e.value(b[0])):.3f} ms"); report("critic forward (infer)")
-ms = timed(lambda: e.ppo_step(*b, lr=1e-4, apply=False, adv_mean=0.0, adv_std=1.0))
-print(f"ppo N={N}: {ms:.3f} ms"); report("ppo(last chain = actor bwd)")
+def report(tag, slots):
+    for sl in slots:
+        a = buf[sl]
+        lead = a[a[:, 3] > 0]      # leader CTAs carry the MMA counters
+        epi = a[a[:, 5] + a[:, 6] > 0]
+        if len(epi) == 0: continue
+        d = {n: int(lead[:, i].mean()) if i in (1, 2, 3) and len(lead) else int(epi[:, i].mean()) for i, n in enumerate(names)}
+        print(f"{tag} slot {sl} ({len(epi)} CTAs, {len(lead)} leaders)", d, flush=True)
+def once(fn):
+    fn(); torch.cuda.synchronize(); read()       # warm + clear
+    fn(); torch.cuda.synchronize(); read()
+once(lambda: e.logprobs_subsample(b[0], b[1], b[2], b[3])); report("logprobs", [0])
+once(lambda: e.sample(obs, seed=1, offset=2)); report("sample", [0])
+once(lambda: e.value(b[0])); report("critic fwd infer", [0])
+once(lambda: e.ppo_step(*b, lr=1e-4, apply=False, adv_mean=0.0, adv_std=1.0)); report("ppo [actor fwd, critic fwd, actor bwd, critic bwd]", [0, 1, 2, 3])
 e.close()
