@@ -59,7 +59,7 @@ class Clocks(threading.Thread):
 
     def run(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 self.rows.append([x.strip() for x in line.split(",")])
@@ -276,7 +276,15 @@ def run_ours(args):
     launches = e.launch_count() - l0 - 0
     launches_per_step = launches // (args.steps + args.warmup)
     ms_e2e = timed(e2e_step, args.steps, max(3, args.warmup // 2))
+    # the timed regions last only milliseconds: keep the same step running for ~0.3 s so that nvidia-smi (20 ms period)
+    # sees the clocks and throttle reasons of this workload under load
+    t_load = time.perf_counter(); n_load = 0
+    while time.perf_counter() - t_load < 0.3:
+        for i in range(20):
+            dev_step(i)
+        torch.cuda.synchronize(); n_load += 20
     clocks = clk.finish()
+    clocks["load_steps_sampled"] = n_load
 
     # ---- roofline of the dominant kernel, timed live with CUDA events inside the library (every tensor-class launch is
     #      bracketed on its launching stream; classes: 0 fused tcgen05 layer chain, 1 tcgen05 GEMM (dW), 2 FFMA SGEMM)
