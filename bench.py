@@ -276,6 +276,31 @@ def run_ours(args):
     launches = e.launch_count() - l0 - 0
     launches_per_step = launches // (args.steps + args.warmup)
     ms_e2e = timed(e2e_step, args.steps, max(3, args.warmup // 2))
+    # ---- e2e through the index-driven entry point (the reference's own data flow, :266-312): the rollout
+    #      of an iteration (P = 500 steps x 40 envs chains, old log-probs, returns/values/advantages) is uploaded from pinned
+    #      host memory once per 20 minibatch updates (update_epochs 5 x 4 minibatches) and stays resident; every step copies
+    #      only its 50 000 shuffled flat indices in and the 8 metrics out.  The upload is inside the timed region.
+    P_roll, K = 20000, d.ft_denoising_steps
+    g2 = torch.Generator(device=dev); g2.manual_seed(99 + rank)
+    obs_r = torch.rand(P_roll, d.Do, device=dev, generator=g2) * 2 - 1
+    _, chains_r = e.sample(obs_r, seed=5, offset=7)
+    olp_r = e.logprobs(obs_r, chains_r, use_base_policy=True).reshape(P_roll, K, d.A)
+    val_r = e.value(obs_r)
+    roll_host = [t.cpu().pin_memory() for t in (obs_r, chains_r, olp_r, torch.randn(P_roll, device=dev, generator=g2), val_r,
+                                                torch.randn(P_roll, device=dev, generator=g2))]
+    roll_dev = [torch.empty_like(t, device=dev) for t in roll_host]
+    inds_host = [torch.randint(0, P_roll * K, (N_ROWS,), dtype=torch.int32).pin_memory() for _ in range(2)]
+    UPLOAD_EVERY = 20
+
+    def e2e_indexed_step(i):
+        if i % UPLOAD_EVERY == 0:
+            for hb, db in zip(roll_host, roll_dev):
+                db.copy_(hb, non_blocking=True)
+        e.ppo_step_indexed(*roll_dev, inds_host[i & 1].numpy(), lr=lr, apply=True, n_global=n_global, metrics_host=metrics_host.numpy())
+
+    idx_steps = max(args.steps, UPLOAD_EVERY)
+    ms_e2e_idx = timed(e2e_indexed_step, idx_steps, UPLOAD_EVERY)     # warm-up and timed region each start with an upload
+    roll_bytes = sum(t.numel() * t.element_size() for t in roll_host)
     # the timed regions last only milliseconds: keep the same step running for ~0.3 s so that nvidia-smi (20 ms period)
     # sees the clocks and throttle reasons of this workload under load
     t_load = time.perf_counter(); n_load = 0
@@ -401,6 +426,11 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": {"value": n_global * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 32,
                     "ms_per_step": ms_e2e / args.steps, "api": "Engine.ppo_step_host -> dppo_ppo_step_host (pinned host buffers)"},
+            "e2e_indexed": {"value": n_global * idx_steps / (ms_e2e_idx * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e_idx / idx_steps,
+                            "steps": idx_steps, "h2d_bytes_per_step": N_ROWS * 4 + roll_bytes * ((idx_steps + UPLOAD_EVERY - 1) // UPLOAD_EVERY) / idx_steps,
+                            "d2h_bytes_per_step": 32,
+                            "api": "Engine.ppo_step_indexed -> dppo_ppo_step_indexed_host: rollout buffers resident in HBM (re-uploaded from pinned host "
+                                   "memory every 20 steps, inside the timed region), per step only the flat minibatch indices go in"},
             "gpu_launches": launches_per_step * args.steps,
             "gpu_launches_per_step": launches_per_step,
             "roofline": roof,

@@ -918,6 +918,59 @@ extern "C" int dppo_ppo_step_host(dppo_handle* h, const float* obs, const float*
     return 0;
 }
 
+// ------------------------------------------------------------------ index-driven PPO step
+static int ppo_indexed_impl(dppo_handle* h, cudaStream_t s, const float* obs_buf, const float* chains_buf, const float* oldlogp_buf,
+                            const float* returns_buf, const float* values_buf, const float* adv_buf, int64_t P,
+                            const int32_t* inds_dev, const int32_t* inds_host, int N, int64_t N_global, float adv_mean, float adv_std,
+                            float lr, int apply, float* metrics8, float* grads_out, float* metrics8_host) {
+    const Geom& g = h->g;
+    if (!obs_buf || !chains_buf || !oldlogp_buf || !returns_buf || !values_buf || !adv_buf || (!inds_dev && !inds_host) || N < 1 || P < 1 || N_global < N)
+        DPPO_FAIL(-1, "dppo_ppo_step_indexed: bad arguments");
+    if (g.K < 1) DPPO_FAIL(-1, "dppo_ppo_step_indexed: ft_denoising_steps must be >= 1");
+    if (P * g.K > 2000000000LL) DPPO_FAIL(-1, "dppo_ppo_step_indexed: rollout buffer too large for int32 flat indices");
+    size_t b_obs = a256((size_t)N * g.Do * 4), b_x = a256((size_t)N * g.A * 4), b_n = a256((size_t)N * 4);
+    DPPO_TRY(stage_reserve(h, b_obs + 3 * b_x + 5 * b_n + 512));
+    char* p = h->dstage;
+    float* d_obs = (float*)p; p += b_obs;
+    float* d_prev = (float*)p; p += b_x; float* d_next = (float*)p; p += b_x; float* d_olp = (float*)p; p += b_x;
+    int* d_dind = (int*)p; p += b_n; float* d_ret = (float*)p; p += b_n; float* d_val = (float*)p; p += b_n; float* d_adv = (float*)p; p += b_n;
+    int* d_inds = (int*)p; p += b_n;
+    float* d_met = (float*)p; int* d_bad = (int*)(p + 256);
+    if (inds_host) { CUDA_TRY(cudaMemcpyAsync(d_inds, inds_host, (size_t)N * 4, cudaMemcpyHostToDevice, s)); inds_dev = d_inds; }
+    CUDA_TRY(cudaMemsetAsync(d_bad, 0, sizeof(int), s));
+    const size_t total = (size_t)N * (g.Do + 3 * g.A + 4);
+    gather_minibatch_kernel<<<nblk(total, 256), 256, 0, s>>>(obs_buf, chains_buf, oldlogp_buf, returns_buf, values_buf, adv_buf, inds_dev, N, g.K, g.A, g.Do,
+                                                           (long long)P, d_obs, d_prev, d_next, d_olp, d_dind, d_ret, d_val, d_adv, d_bad);
+    KLAUNCH(h); KCHECK();
+    DPPO_TRY(dppo_ppo_step(h, d_obs, d_prev, d_next, d_dind, d_ret, d_val, d_adv, d_olp, N, N_global, adv_mean, adv_std, lr, apply,
+                           metrics8_host ? d_met : metrics8, grads_out, (dppo_stream_t)s));
+    if (metrics8_host) {
+        int bad = 0;
+        CUDA_TRY(cudaMemcpyAsync(metrics8_host, d_met, 8 * sizeof(float), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        if (bad) DPPO_FAIL(-1, "dppo_ppo_step_indexed_host: an index lies outside [0, P*K)");
+    }
+    return 0;
+}
+extern "C" int dppo_ppo_step_indexed(dppo_handle* h, const float* obs_buf, const float* chains_buf, const float* oldlogp_buf,
+                                     const float* returns_buf, const float* values_buf, const float* adv_buf, int64_t P,
+                                     const int32_t* inds_k, int N, int64_t N_global, float adv_mean, float adv_std, float lr, int apply,
+                                     float* metrics8, float* grads_out, dppo_stream_t st) {
+    ENTER(h);
+    return ppo_indexed_impl(h, (cudaStream_t)st, obs_buf, chains_buf, oldlogp_buf, returns_buf, values_buf, adv_buf, P, inds_k, nullptr, N, N_global,
+                            adv_mean, adv_std, lr, apply, metrics8, grads_out, nullptr);
+}
+extern "C" int dppo_ppo_step_indexed_host(dppo_handle* h, const float* obs_buf, const float* chains_buf, const float* oldlogp_buf,
+                                          const float* returns_buf, const float* values_buf, const float* adv_buf, int64_t P,
+                                          const int32_t* inds_k_host, int N, int64_t N_global, float adv_mean, float adv_std, float lr, int apply,
+                                          float* metrics8_host, dppo_stream_t st) {
+    ENTER(h);
+    if (!metrics8_host) DPPO_FAIL(-1, "dppo_ppo_step_indexed_host: metrics8_host is required");
+    return ppo_indexed_impl(h, (cudaStream_t)st, obs_buf, chains_buf, oldlogp_buf, returns_buf, values_buf, adv_buf, P, nullptr, inds_k_host, N, N_global,
+                            adv_mean, adv_std, lr, apply, nullptr, nullptr, metrics8_host);
+}
+
 // ------------------------------------------------------------------ pre-train step
 extern "C" int dppo_pretrain_step(dppo_handle* h, const float* actions, const float* obs, int N, int64_t N_global,
                                   int64_t row_offset, const int32_t* t_in, const float* noise_in,

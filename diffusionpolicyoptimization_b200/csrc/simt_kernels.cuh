@@ -516,6 +516,29 @@ __global__ void ppo_metrics_kernel(const double* __restrict__ block_sums, int nb
     }
 }
 
+// minibatch assembly from the resident rollout buffers (train_ppo_diffusion_agent.py:293-312): one thread per output float
+__global__ void gather_minibatch_kernel(const float* __restrict__ obs_buf, const float* __restrict__ chains_buf, const float* __restrict__ oldlogp_buf,
+                                        const float* __restrict__ ret_buf, const float* __restrict__ val_buf, const float* __restrict__ adv_buf,
+                                        const int* __restrict__ inds_k, int N, int K, int A, int Do, long long P,
+                                        float* __restrict__ obs, float* __restrict__ prev, float* __restrict__ nxt, float* __restrict__ olp,
+                                        int* __restrict__ dind, float* __restrict__ ret, float* __restrict__ val, float* __restrict__ adv, int* __restrict__ bad) {
+    const int W = Do + 3 * A + 4;                      // floats produced per row
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)N * W) return;
+    const int r = (int)(i / W), c = (int)(i % W);
+    const int flat = inds_k[r];
+    if (flat < 0 || (long long)flat >= P * K) { if (c == 0) atomicOr(bad, 1); return; }
+    const size_t b = (size_t)(flat / K); const int k = flat % K;
+    if (c < Do) obs[(size_t)r * Do + c] = obs_buf[b * Do + c];
+    else if (c < Do + A) prev[(size_t)r * A + (c - Do)] = chains_buf[(b * (K + 1) + k) * A + (c - Do)];
+    else if (c < Do + 2 * A) nxt[(size_t)r * A + (c - Do - A)] = chains_buf[(b * (K + 1) + k + 1) * A + (c - Do - A)];
+    else if (c < Do + 3 * A) olp[(size_t)r * A + (c - Do - 2 * A)] = oldlogp_buf[(b * K + k) * A + (c - Do - 2 * A)];
+    else if (c == Do + 3 * A) dind[r] = k;
+    else if (c == Do + 3 * A + 1) ret[r] = ret_buf[b];
+    else if (c == Do + 3 * A + 2) val[r] = val_buf[b];
+    else adv[r] = adv_buf[b];
+}
+
 // pre-train: x_noisy = sqrt(acp_t) x0 + sqrt(1-acp_t) noise (diffusion.py:196-202); also materialises t / noise draws
 __global__ void pretrain_prep_kernel(const float* __restrict__ x0, const int* __restrict__ t_in, const float* __restrict__ noise_in,
                                      int N, int A, int T, const float* __restrict__ sch, uint64_t seed, uint64_t offset,

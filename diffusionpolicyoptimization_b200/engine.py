@@ -193,6 +193,37 @@ class Engine:
                                             float(adv_mean), float(adv_std), float(lr), int(apply),
                                             _ptr(metrics_out), self._stream()), "dppo_ppo_step_host")
 
+    def ppo_step_indexed(self, obs_buf, chains_buf, oldlogp_buf, returns_buf, values_buf, adv_buf, inds_k, lr: float, apply=True,
+                         n_global: Optional[int] = None, adv_mean: float = 0.0, adv_std: float = -1.0, want_grads=False,
+                         metrics_host: Optional[np.ndarray] = None):
+        """Index-driven update (train_ppo_diffusion_agent.py:287-312): the rollout buffers are CUDA tensors that stay
+        resident; `inds_k` holds flat (b*K + k) indices - a CUDA int32 tensor, or (with `metrics_host`, a pinned float32[8]
+        array) a host int32 array, in which case the call copies the indices in, the metrics out and synchronises."""
+        obs_buf = _as_dev(obs_buf, self.dev).reshape(-1, self.Do)
+        P = obs_buf.shape[0]
+        chains_buf = _as_dev(chains_buf, self.dev).reshape(P, self.K + 1, self.A)
+        oldlogp_buf = _as_dev(oldlogp_buf, self.dev).reshape(P, self.K, self.A)
+        returns_buf = _as_dev(returns_buf, self.dev).reshape(P)
+        values_buf = _as_dev(values_buf, self.dev).reshape(P)
+        adv_buf = _as_dev(adv_buf, self.dev).reshape(P)
+        if metrics_host is not None:
+            inds = _as_host(inds_k, np.int32).reshape(-1) if not isinstance(inds_k, np.ndarray) else inds_k
+            N = inds.shape[0]
+            L.check(self.lib.dppo_ppo_step_indexed_host(self.h, _ptr(obs_buf), _ptr(chains_buf), _ptr(oldlogp_buf), _ptr(returns_buf),
+                                                        _ptr(values_buf), _ptr(adv_buf), P, _ptr(inds), N,
+                                                        int(n_global if n_global is not None else N), float(adv_mean), float(adv_std),
+                                                        float(lr), int(apply), _ptr(metrics_host), self._stream()), "dppo_ppo_step_indexed_host")
+            return metrics_host
+        inds = _as_dev(inds_k, self.dev, torch.int32).reshape(-1)
+        N = inds.shape[0]
+        metrics = torch.empty(8, device=self.dev, dtype=torch.float32)
+        grads = torch.empty(self.n_actor + self.n_critic, device=self.dev, dtype=torch.float32) if want_grads else None
+        L.check(self.lib.dppo_ppo_step_indexed(self.h, _ptr(obs_buf), _ptr(chains_buf), _ptr(oldlogp_buf), _ptr(returns_buf), _ptr(values_buf),
+                                               _ptr(adv_buf), P, _ptr(inds), N, int(n_global if n_global is not None else N),
+                                               float(adv_mean), float(adv_std), float(lr), int(apply), _ptr(metrics), _ptr(grads),
+                                               self._stream()), "dppo_ppo_step_indexed")
+        return (metrics, grads) if want_grads else metrics
+
     def pretrain_step(self, actions, obs, lr: float, apply=True, t=None, noise=None, seed: int = 0, offset: int = 0,
                       n_global: Optional[int] = None, row_offset: int = 0, want_grads=False):
         actions = _as_dev(actions, self.dev).reshape(-1, self.A)

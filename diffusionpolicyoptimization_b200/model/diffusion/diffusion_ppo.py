@@ -57,3 +57,15 @@ class PPODiffusion(VPGDiffusion):
         (train_ppo_diffusion_agent.py:328-356)."""
         return self._run(obs, chains_prev, chains_next, denoising_inds, returns, oldvalues, advantages, oldlogprobs,
                          use_bc_loss, reward_horizon, lr, True, n_global, adv_mean, adv_std)
+
+    def ppo_update_indexed(self, obs_k, chains_k, logprobs_k, returns_k, values_k, advantages_k, inds_k, lr,
+                           n_global=None, adv_mean=0.0, adv_std=-1.0, apply=True):
+        """One minibatch of train_ppo_diffusion_agent.py:287-356 from the device-resident rollout of this iteration:
+        obs_k [P,1,Do], chains_k [P,K+1,Ta,Da], logprobs_k [P,K,Ta,Da], returns_k / values_k / advantages_k [P] stay on
+        the GPU across the update epochs; `inds_k` is the slice of the shuffled flat (step*env, k) index the reference
+        unravels at :293-296.  Returns the 8 loss scalars (device tensor)."""
+        P = obs_k.shape[0]
+        return self.engine.ppo_step_indexed(_state({"state": obs_k}) if not isinstance(obs_k, dict) else _state(obs_k),
+                                            chains_k.reshape(P, self.ft_denoising_steps + 1, -1), logprobs_k.reshape(P, self.ft_denoising_steps, -1),
+                                            returns_k, values_k, advantages_k, inds_k, lr=lr, apply=apply, n_global=n_global,
+                                            adv_mean=adv_mean, adv_std=adv_std)

@@ -161,6 +161,26 @@ int dppo_ppo_step_host(dppo_handle* h, const float* obs, const float* chains_pre
                        const float* advantages, const float* oldlogprobs, int N_local, int64_t N_global,
                        float adv_mean, float adv_std, float lr, int apply, float* metrics8_host, dppo_stream_t s);
 
+/* Index-driven PPO update.  The reference keeps one iteration's rollout as device tensors
+ * (obs_k, chains_k, returns_k, values_k, advantages_k, logprobs_k: train_ppo_diffusion_agent.py:266-279) and assembles every
+ * minibatch on the device from a shuffled flat index (tf.random.shuffle / unravel_index / gather / gather_nd, :287-312).
+ * Here the rollout buffers stay resident in HBM (DEVICE pointers owned by the caller):
+ *   obs_buf[P][Do], chains_buf[P][K+1][A] (the sampler's `chains` output), oldlogp_buf[P][K][A] (dppo_logprobs output),
+ *   returns_buf[P], values_buf[P], adv_buf[P];  P = n_steps * n_envs.
+ * inds_k[N] (DEVICE int32) holds flat (b * K + k) indices exactly like the reference's inds_k slice; row r of the
+ * minibatch is (obs[b], chains[b][k], chains[b][k+1], k, returns[b], values[b], adv[b], oldlogp[b][k]).  The gather
+ * runs in one kernel in front of dppo_ppo_step; everything else (N_global, adv_mean/adv_std, lr, apply, outputs) is as
+ * for dppo_ppo_step (adv_std < 0: the statistics are computed over the gathered minibatch). */
+int dppo_ppo_step_indexed(dppo_handle* h, const float* obs_buf, const float* chains_buf, const float* oldlogp_buf,
+                          const float* returns_buf, const float* values_buf, const float* adv_buf, int64_t P,
+                          const int32_t* inds_k, int N_local, int64_t N_global, float adv_mean, float adv_std, float lr, int apply,
+                          float* metrics8, float* grads_or_null, dppo_stream_t s);
+/* Same with the index list and the metrics in HOST memory (the only per-minibatch host traffic). */
+int dppo_ppo_step_indexed_host(dppo_handle* h, const float* obs_buf, const float* chains_buf, const float* oldlogp_buf,
+                               const float* returns_buf, const float* values_buf, const float* adv_buf, int64_t P,
+                               const int32_t* inds_k_host, int N_local, int64_t N_global, float adv_mean, float adv_std, float lr, int apply,
+                               float* metrics8_host, dppo_stream_t s);
+
 /* DiffusionModel.c_loss / p_losses / q_sample (diffusion.py:179-202) + tape.gradient + AdamW
  * (train_diffusion_agent.py:63-69) on net DPPO_NET_ACTOR.  t_or_null[N] int32 and
  * noise_or_null[N,A] inject the draws at diffusion.py:183,187; NULL = Philox(seed, offset, row).
