@@ -22,7 +22,7 @@ EXPORTS = (
     "dppo_create", "dppo_destroy", "dppo_set_weights", "dppo_get_weights", "dppo_set_opt_state",
     "dppo_get_opt_state", "dppo_set_ft_denoising_steps", "dppo_actor_forward", "dppo_value",
     "dppo_sample", "dppo_sample_host", "dppo_logprobs", "dppo_logprobs_subsample", "dppo_ppo_step",
-    "dppo_ppo_step_host", "dppo_ppo_step_indexed", "dppo_ppo_step_indexed_host", "dppo_pretrain_step", "dppo_ema_update", "dppo_comm_unique_id",
+    "dppo_ppo_step_host", "dppo_ppo_step_indexed", "dppo_ppo_step_indexed_host", "dppo_gae", "dppo_pretrain_step", "dppo_ema_update", "dppo_comm_unique_id",
     "dppo_comm_init", "dppo_launch_count", "dppo_tc_launch_count", "dppo_fused_launch_count", "dppo_last_path", "dppo_force_path", "dppo_profile_enable", "dppo_debug_tc_gemm",
     "dppo_profile_read", "dppo_debug_chain_timing", "dppo_debug_mma_probe", "dppo_profile_read_class",
 )
@@ -89,6 +89,7 @@ def load():
         "dppo_ppo_step_host": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i64, f32, f32, f32, i32, vp, vp]),
         "dppo_ppo_step_indexed": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, i64, vp, i32, i64, f32, f32, f32, i32, vp, vp, vp]),
         "dppo_ppo_step_indexed_host": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, i64, vp, i32, i64, f32, f32, f32, i32, vp, vp]),
+        "dppo_gae": (C.c_int, [vp, vp, vp, vp, vp, i32, i32, C.c_double, C.c_double, C.c_double, vp, vp, vp]),
         "dppo_pretrain_step": (C.c_int, [vp, vp, vp, i32, i64, i64, vp, vp, u64, u64, f32, i32, vp, vp, vp]),
         "dppo_ema_update": (C.c_int, [vp, f32, vp]),
         "dppo_comm_unique_id": (C.c_int, [vp]),

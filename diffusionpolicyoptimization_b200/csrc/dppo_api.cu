@@ -291,6 +291,7 @@ extern "C" void dppo_destroy(dppo_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
+    tc_plan_free(h);
     tc_destroy(h);
     for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
     if (h->comm) {
@@ -969,6 +970,19 @@ extern "C" int dppo_ppo_step_indexed_host(dppo_handle* h, const float* obs_buf, 
     if (!metrics8_host) DPPO_FAIL(-1, "dppo_ppo_step_indexed_host: metrics8_host is required");
     return ppo_indexed_impl(h, (cudaStream_t)st, obs_buf, chains_buf, oldlogp_buf, returns_buf, values_buf, adv_buf, P, nullptr, inds_k_host, N, N_global,
                             adv_mean, adv_std, lr, apply, nullptr, nullptr, metrics8_host);
+}
+
+// ------------------------------------------------------------------ GAE
+extern "C" int dppo_gae(dppo_handle* h, const double* rewards, const float* terminated, const float* values, const float* next_values,
+                        int n_steps, int n_envs, double reward_scale_const, double gamma, double gae_lambda,
+                        float* advantages, float* returns, dppo_stream_t st) {
+    ENTER(h); cudaStream_t s = (cudaStream_t)st;
+    if (!rewards || !terminated || !values || !next_values || !advantages || !returns || n_steps < 1 || n_envs < 1)
+        DPPO_FAIL(-1, "dppo_gae: bad arguments");
+    gae_kernel<<<nblk(n_envs, 128), 128, 0, s>>>(rewards, terminated, values, next_values, n_steps, n_envs, reward_scale_const, gamma, gae_lambda,
+                                                advantages, returns);
+    KLAUNCH(h); KCHECK();
+    return 0;
 }
 
 // ------------------------------------------------------------------ pre-train step

@@ -539,6 +539,28 @@ __global__ void gather_minibatch_kernel(const float* __restrict__ obs_buf, const
     else adv[r] = adv_buf[b];
 }
 
+// GAE backward scan, one thread per env (train_ppo_diffusion_agent.py:242-263).  Explicit round-to-nearest double
+// multiplies / adds in NumPy's evaluation order (no FMA contraction), so the result is bit-identical to the reference.
+__global__ void gae_kernel(const double* __restrict__ rewards, const float* __restrict__ terminated, const float* __restrict__ values,
+                           const float* __restrict__ next_values, int S, int E, double rsc, double gamma, double lam,
+                           float* __restrict__ adv, float* __restrict__ ret) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    double last = 0.0;
+    for (int t = S - 1; t >= 0; --t) {
+        const size_t i = (size_t)t * E + e;
+        const double nextv = (t == S - 1) ? (double)next_values[e] : (double)values[i + E];
+        const double nonterm = 1.0 - (double)terminated[i];
+        const double v = (double)values[i];
+        // delta = r * rsc + gamma * nextv * nonterm - v
+        const double delta = __dsub_rn(__dadd_rn(__dmul_rn(rewards[i], rsc), __dmul_rn(__dmul_rn(gamma, nextv), nonterm)), v);
+        // last = delta + gamma * lam * nonterm * last
+        last = __dadd_rn(delta, __dmul_rn(__dmul_rn(__dmul_rn(gamma, lam), nonterm), last));
+        adv[i] = (float)last;
+        ret[i] = (float)__dadd_rn(last, v);
+    }
+}
+
 // pre-train: x_noisy = sqrt(acp_t) x0 + sqrt(1-acp_t) noise (diffusion.py:196-202); also materialises t / noise draws
 __global__ void pretrain_prep_kernel(const float* __restrict__ x0, const int* __restrict__ t_in, const float* __restrict__ noise_in,
                                      int N, int A, int T, const float* __restrict__ sch, uint64_t seed, uint64_t offset,

@@ -30,9 +30,11 @@ struct TcNetW {
     float* bias2;          // critic: b2 + b_in (the residual's input-layer bias rides with block.l2's)
     int H;
 };
+struct TcPpoPlan;
 struct TcState {
     TcNetW net[4];
     int KP0;
+    TcPpoPlan* plan;       // state of the begin / chunk / finish PPO step in flight (one per handle)
 };
 
 // ------------------------------------------------------------------ small kernels
@@ -741,8 +743,8 @@ struct TcPpoPlan {
     bf16 *h0, *depsb, *dvalb; float *eps, *val;
     PpoHyper hp;
 };
-static TcPpoPlan g_plan_storage[16];   // indexed by device
-static TcPpoPlan& tc_plan(dppo_handle* h) { return g_plan_storage[h->device & 15]; }
+static TcPpoPlan& tc_plan(dppo_handle* h) { if (!h->tc->plan) { h->tc->plan = new TcPpoPlan(); memset(h->tc->plan, 0, sizeof(TcPpoPlan)); } return *h->tc->plan; }
+static void tc_plan_free(dppo_handle* h) { if (h->tc && h->tc->plan) { delete h->tc->plan; h->tc->plan = nullptr; } }
 
 // chunk_rows <= 0 or >= N: one chunk
 static int tc_ppo_begin(dppo_handle* h, cudaStream_t s, int N, int chunk_rows, int64_t N_global) {

@@ -224,6 +224,19 @@ class Engine:
                                                self._stream()), "dppo_ppo_step_indexed")
         return (metrics, grads) if want_grads else metrics
 
+    def gae(self, rewards, terminated, values, next_values, reward_scale_const=1.0, gamma=0.999, gae_lambda=0.95):
+        """train_ppo_diffusion_agent.py:242-263 on the device: rewards [S,E] (float64), terminated [S,E], values [S,E],
+        next_values [E] -> (advantages [S,E], returns [S,E]) fp32 CUDA tensors."""
+        rewards = _as_dev(rewards, self.dev, torch.float64)
+        S, E = rewards.shape
+        terminated = _as_dev(terminated, self.dev).reshape(S, E)
+        values = _as_dev(values, self.dev).reshape(S, E)
+        next_values = _as_dev(next_values, self.dev).reshape(E)
+        adv = torch.empty(S, E, device=self.dev, dtype=torch.float32); ret = torch.empty_like(adv)
+        L.check(self.lib.dppo_gae(self.h, _ptr(rewards), _ptr(terminated), _ptr(values), _ptr(next_values), S, E,
+                                  float(reward_scale_const), float(gamma), float(gae_lambda), _ptr(adv), _ptr(ret), self._stream()), "dppo_gae")
+        return adv, ret
+
     def pretrain_step(self, actions, obs, lr: float, apply=True, t=None, noise=None, seed: int = 0, offset: int = 0,
                       n_global: Optional[int] = None, row_offset: int = 0, want_grads=False):
         actions = _as_dev(actions, self.dev).reshape(-1, self.A)

@@ -181,6 +181,16 @@ int dppo_ppo_step_indexed_host(dppo_handle* h, const float* obs_buf, const float
                                const int32_t* inds_k_host, int N_local, int64_t N_global, float adv_mean, float adv_std, float lr, int apply,
                                float* metrics8_host, dppo_stream_t s);
 
+/* GAE on the device (agent/finetune/train_ppo_diffusion_agent.py:242-263): float64 backward scan per env,
+ *   delta_t = r_t * reward_scale_const + gamma * V_{t+1} * (1 - terminated_t) - V_t
+ *   A_t = delta_t + gamma * gae_lambda * (1 - terminated_t) * A_{t+1};   returns = A + V.
+ * DEVICE pointers: rewards[S][E] float64 (env rewards are float64 NumPy in the reference), terminated[S][E] fp32 (0/1),
+ * values[S][E] fp32 (dppo_value over the rollout observations), next_values[E] fp32 (dppo_value of the last observation);
+ * advantages / returns [S][E] fp32, i.e. already in the flat (step, env) order the update indexes. */
+int dppo_gae(dppo_handle* h, const double* rewards, const float* terminated, const float* values, const float* next_values,
+             int n_steps, int n_envs, double reward_scale_const, double gamma, double gae_lambda,
+             float* advantages, float* returns, dppo_stream_t s);
+
 /* DiffusionModel.c_loss / p_losses / q_sample (diffusion.py:179-202) + tape.gradient + AdamW
  * (train_diffusion_agent.py:63-69) on net DPPO_NET_ACTOR.  t_or_null[N] int32 and
  * noise_or_null[N,A] inject the draws at diffusion.py:183,187; NULL = Philox(seed, offset, row).

@@ -439,6 +439,24 @@ def adamw_keras(params, grads, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-7,
         p.sub_(mi * alpha / (torch.sqrt(vi) + eps))
 
 
+def gae(rewards: np.ndarray, terminated: np.ndarray, values: np.ndarray, next_values: np.ndarray,
+        reward_scale_const: float = 1.0, gamma: float = 0.999, gae_lambda: float = 0.95):
+    """agent/finetune/train_ppo_diffusion_agent.py:242-263 — NumPy float64 backward scan over the rollout.
+    rewards / terminated / values: [n_steps, n_envs]; next_values: [n_envs] (critic of the last observation).
+    Returns (advantages, returns) as float64 [n_steps, n_envs] (the reference casts them to fp32 at :277-279)."""
+    rewards = np.asarray(rewards, np.float64); values = np.asarray(values, np.float64)
+    n_steps = rewards.shape[0]
+    advantages = np.zeros_like(rewards)
+    lastgaelam = 0
+    for t in reversed(range(n_steps)):
+        nextvalues = np.asarray(next_values, np.float64).reshape(1, -1) if t == n_steps - 1 else values[t + 1]
+        nonterminal = 1.0 - np.asarray(terminated[t], np.float64)
+        delta = rewards[t] * reward_scale_const + gamma * nextvalues * nonterminal - values[t]
+        lastgaelam = delta + gamma * gae_lambda * nonterminal * lastgaelam
+        advantages[t] = lastgaelam
+    return advantages, advantages + values
+
+
 def ema_update(ema_params, params, decay=0.995):
     """agent/pretrain/train_agent.py:53-58: ema <- decay*ema + (1-decay)*w."""
     for e, p in zip(ema_params, params):

@@ -312,3 +312,18 @@ def test_ppo_step_indexed_matches_host_gathered_minibatch(pair):
     bad = inds.copy(); bad[17] = P * K
     with pytest.raises(dp.DppoError):
         e.ppo_step_indexed(obs, chains, oldlogp, ret, val, adv, bad, lr=0.0, apply=False, metrics_host=mh)
+
+
+def test_gae_on_device_is_bit_identical_to_the_numpy_scan(pair):
+    """train_ppo_diffusion_agent.py:242-263 (float64 NumPy) vs dppo_gae; outputs compared after the fp32 cast."""
+    o, e = pair
+    rng = np.random.default_rng(3)
+    S, E = 500, 40
+    rewards = rng.standard_normal((S, E)) * 3.0                      # float64, like env rewards
+    terminated = (rng.random((S, E)) < 0.02).astype(np.float32)
+    values = rng.standard_normal((S, E)).astype(np.float32)
+    next_values = rng.standard_normal(E).astype(np.float32)
+    want_a, want_r = O.gae(rewards, terminated, values, next_values, reward_scale_const=0.1, gamma=0.999, gae_lambda=0.95)
+    adv, ret = e.gae(rewards, terminated, values, next_values, reward_scale_const=0.1, gamma=0.999, gae_lambda=0.95)
+    np.testing.assert_array_equal(adv.cpu().numpy(), want_a.astype(np.float32))
+    np.testing.assert_array_equal(ret.cpu().numpy(), want_r.astype(np.float32))

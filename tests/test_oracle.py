@@ -118,3 +118,16 @@ def test_oracle_reproduces_golden(path):
     np.testing.assert_allclose([float(m) for m in metrics], z["ppo_metrics"], rtol=1e-4, atol=1e-6)
     g = np.concatenate([O.flatten_params(ga), O.flatten_params(gc)])[::97]
     np.testing.assert_allclose(g, z["ppo_grads_fp"], rtol=1e-3, atol=1e-7)
+
+
+def test_gae_known_answer():
+    """Hand-computed 3-step, 2-env case of train_ppo_diffusion_agent.py:242-263 (env 1 terminates at t=1)."""
+    r = np.array([[1.0, 1.0], [2.0, 0.5], [0.0, 4.0]]); term = np.array([[0, 0], [0, 1], [0, 0]], np.float32)
+    v = np.array([[0.5, 0.5], [1.0, 1.0], [2.0, 0.0]], np.float32); nv = np.array([3.0, 1.0], np.float32)
+    g, lam = 0.9, 0.5
+    adv, ret = O.gae(r, term, v, nv, 1.0, g, lam)
+    d2 = np.array([0.0 + g * 3.0 - 2.0, 4.0 + g * 1.0 - 0.0]); a2 = d2
+    d1 = np.array([2.0 + g * 2.0 - 1.0, 0.5 + 0.0 - 1.0]); a1 = d1 + g * lam * np.array([1.0, 0.0]) * a2
+    d0 = np.array([1.0 + g * 1.0 - 0.5, 1.0 + g * 1.0 - 0.5]); a0 = d0 + g * lam * a1
+    np.testing.assert_allclose(adv, np.stack([a0, a1, a2]), rtol=1e-15)
+    np.testing.assert_allclose(ret, adv + v, rtol=1e-15)
