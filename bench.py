@@ -381,6 +381,23 @@ def run_ours(args):
                         "path": PATHS[largeB_path]},
     }
 
+    # ---- BASELINE.json configs[4]: halfcheetah-medium-v2 pre_diffusion_mlp eps-MSE pre-train step, batch 4096 per GPU
+    #      (q_sample with in-kernel Philox t / noise, forward, MSE, backward, (all-reduce), AdamW, EMA every step excluded)
+    NB = 4096
+    x0_p = torch.rand(NB, d.A, device=dev) * 2 - 1
+    obs_p = torch.rand(NB, d.Do, device=dev) * 2 - 1
+    pcnt = [0]
+
+    def pre_step(i):
+        pcnt[0] += 1
+        e.pretrain_step(x0_p, obs_p, lr=1e-3, apply=True, seed=3, offset=pcnt[0], n_global=NB * world, row_offset=rank * NB)
+
+    ms_pre = timed(pre_step, 20, 5)
+    pre_flops = 3 * Fa - 2 * d.Din * d.actor_hidden
+    pretrain = {"samples_per_sec": world * NB * 20 / (ms_pre * 1e-3), "ms_per_step": ms_pre / 20, "batch_per_gpu": NB,
+                "tflops": pre_flops * NB * 20 / (ms_pre * 1e-3) / 1e12,
+                "note": "latency-bound at this batch (32 row tiles for 148 SMs): 13.7 GFLOP per step"}
+
     # ---- the strict-parity fp32 mode on the same workload (3 steps), reported beside the headline
     fp32_mode = None
     if tensor:
@@ -436,6 +453,7 @@ def run_ours(args):
             "roofline": roof,
             "cpu_baseline": cpu,
             "sampling": sampling,
+            "pretrain": pretrain,
             "fp32_parity_mode": fp32_mode,
             "step_tflops": fps * N_ROWS / (ms_dev / args.steps * 1e-3) / 1e12,
         }

@@ -619,7 +619,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ D
 }
 
 // time-MLP + layer-0 bias backward from G[T][H] = per-t column sums of du.  One block, 512 threads.
-__global__ void time_backward_kernel(const float* __restrict__ w, ActorOff o, int A, int td, int H, int T,
+__global__ void __launch_bounds__(512) time_backward_kernel(const float* __restrict__ w, ActorOff o, int A, int td, int H, int T,
                                      const float* __restrict__ G, const float* __restrict__ sinemb,
                                      const float* __restrict__ thpre, const float* __restrict__ temb,
                                      float* __restrict__ g) {
@@ -634,12 +634,33 @@ __global__ void time_backward_kernel(const float* __restrict__ w, ActorOff o, in
         const int lanes = gridDim.x == 1 ? 1 : 4;            // threads per column
         for (int i = tid; i < (c1 - c0) * lanes; i += nt) {
             const int c = c0 + i / lanes, part = i % lanes;
-            if (part == 0) {
-                float s = 0.f;
-                for (int t = 0; t < T; ++t) s += G[(size_t)t * H + c];
-                g[o.bin + c] = s;
+            // the T values of column c are loaded up front (independent loads: one L2 latency instead of T)
+            float bsum = 0.f;
+            float acc[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) acc[q] = 0.f;
+            for (int t0 = 0; t0 < T; t0 += 32) {
+                float gc[32];
+#pragma unroll
+                for (int q = 0; q < 32; ++q) gc[q] = (t0 + q < T) ? G[(size_t)(t0 + q) * H + c] : 0.f;
+#pragma unroll
+                for (int q = 0; q < 32; ++q) bsum += gc[q];
+#pragma unroll
+                for (int jj = 0; jj < 16; ++jj) {
+                    const int j = part + jj * lanes;
+                    if (j < td) {
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) if (t0 + q < T) acc[jj] = fmaf(temb[(t0 + q) * td + j], gc[q], acc[jj]);
+                    }
+                }
             }
-            for (int j = part; j < td; j += lanes) {
+            if (part == 0) g[o.bin + c] = bsum;
+            for (int jj = 0; jj < 16; ++jj) {
+                const int j = part + jj * lanes;
+                if (j < td) g[o.win + (size_t)(A + j) * H + c] = acc[jj];
+            }
+            // time_dim > 16 * lanes columns per thread do not fit the register tile: plain loop for the rest
+            for (int j = part + 16 * lanes; j < td; j += lanes) {
                 float a = 0.f;
                 for (int t = 0; t < T; ++t) a = fmaf(temb[t * td + j], G[(size_t)t * H + c], a);
                 g[o.win + (size_t)(A + j) * H + c] = a;
