@@ -291,12 +291,20 @@ def run_ours(args):
     roll_dev = [torch.empty_like(t, device=dev) for t in roll_host]
     inds_host = [torch.randint(0, P_roll * K, (N_ROWS,), dtype=torch.int32).pin_memory() for _ in range(2)]
     UPLOAD_EVERY = 20
+    # global advantage statistics of the (uniformly indexed) rollout advantages, identical on every rank
+    adv_all = roll_host[5].to(dev)
+    if world > 1:
+        parts = [torch.empty_like(adv_all) for _ in range(world)]
+        dist.all_gather(parts, adv_all)
+        adv_all = torch.cat(parts)
+    idx_mean, idx_std = advantage_stats(adv_all.cpu().numpy())
 
     def e2e_indexed_step(i):
         if i % UPLOAD_EVERY == 0:
             for hb, db in zip(roll_host, roll_dev):
                 db.copy_(hb, non_blocking=True)
-        e.ppo_step_indexed(*roll_dev, inds_host[i & 1].numpy(), lr=lr, apply=True, n_global=n_global, metrics_host=metrics_host.numpy())
+        e.ppo_step_indexed(*roll_dev, inds_host[i & 1].numpy(), lr=lr, apply=True, n_global=n_global, adv_mean=idx_mean, adv_std=idx_std,
+                           metrics_host=metrics_host.numpy())
 
     idx_steps = max(args.steps, UPLOAD_EVERY)
     ms_e2e_idx = timed(e2e_indexed_step, idx_steps, UPLOAD_EVERY)     # warm-up and timed region each start with an upload
