@@ -1,26 +1,31 @@
-// Fused residual-MLP layer chain on tcgen05 (sm_100a): one persistent CTA per SM walks 128-row tiles and
-// runs EVERY layer of the chain for its tile with the activations resident on chip.
+// Fused residual-MLP layer chain on tcgen05 (sm_100a).  A persistent CTA PAIR (cluster of 2, cta_group::2; CG = 1 is
+// the single-CTA variant) walks 256-row tiles - 128 rows per CTA - and runs EVERY layer of the chain for its tile with
+// the activations resident on chip.
 //
 //   shared memory  X   [128][H] bf16   the current activation, stored as H/64 K-major 128B-swizzled tiles
-//                                      (exactly the image TMA would produce), i.e. directly the A operand
+//   (per CTA)                          (exactly the image TMA would produce), i.e. directly the A operand
 //                                      of the next layer's tcgen05.mma and the source of a TMA store
+//                  G   [128][H] bf16   (H = 256 only) Mish gates mish'(pre-activation): written next to X in the
+//                                      forward pass (TMA-stored for the backward), TMA-loaded in the backward pass
 //                  H0  [128][64] bf16  the packed layer-0 input tile [x | obs | onehot(t) | 1 | 0]
 //                                      (TMA-loaded, or rebuilt in place by the sampler every denoising step)
-//                  W   4 x 16 KB ring  weight tiles [32 k][256 n] (MN-major, TMA) streamed from L2
+//                  W   4 x 16 KB ring  this CTA's half of every weight tile: [64 k][128 n] (MN-major, TMA from L2);
+//                                      the pair's MMA reads both halves ([32 k][256 n] per stage when CG = 1)
 //   tensor memory  512 columns         the whole [128][H] fp32 accumulator of one layer
 //
-//   warp 0     TMA producer (weight ring, H0 tiles)
-//   warp 1     tcgen05.mma issuer (one elected thread), TMEM allocation
-//   warps 2-9  epilogue (two warps per TMEM lane quadrant, each takes half of the columns; TMEM loads
-//              software-pipelined): tcgen05.ld -> bias / ReLU / ReLU-mask -> bf16 -> swizzled st.shared into X
-//              (+ TMA store of X to HBM when the backward pass needs the tensor), and the final-layer
-//              math: eps store, Gaussian log-prob, or the DDPM posterior step of the sampler.
+//   warp 0     TMA producer (weight ring, H0 / gate tiles); loads report to the LEADER CTA's mbarriers
+//   warp 1     tcgen05.mma issuer (leader CTA only, warp-uniform + elect.sync), TMEM allocation
+//   warps 2-9  epilogue (two warps per TMEM lane quadrant; software-pipelined tcgen05.ld): bias / ReLU (+ bit mask) /
+//              Mish (+ gate) / mask or gate multiply -> bf16 -> swizzled st.shared into X (+ TMA store of X to HBM
+//              when the backward pass needs the tensor, + bias-gradient column sums), and the final-layer math:
+//              eps / value store, Gaussian log-prob, or the DDPM posterior step of the sampler.
 //
-// MMA and epilogue of one tile alternate (X is updated in place); the weight ring keeps streaming across
-// the epilogue, so the tensor pipe restarts immediately.  Three programs run on this engine:
-//   forward   L0 relu(H0 W0) -> L1 relu(X W1 + b1) -> L2 X W2 + H0 W0 + b2 (residual by K-concatenation)
-//             -> L3 X W3 + b3 ;  final = eps | log-prob | (training) eps + stored a0, a1, v + ReLU bit masks
-//   backward  B1 dv = deps W3^T -> B2 dh1 = (dv W2^T) . m1 -> B3 du = (dh1 W1^T) . m0   (each stored by TMA)
+// A 512-wide layer is drained in two phases so that epilogue and MMA overlap: columns [0,256) while the second n-half's
+// MMAs still run (X tile j is overwritten only once those MMAs consumed it: xfree[j]); the next layer's MMAs start on
+// X tiles [0, XT/2) while phase two still writes the rest (xready[0/1], acc_full[0/1]).  Programs on this engine:
+//   forward   L0 act(H0 W0 + b0) -> L1 act(X W1 + b1) -> L2 X W2 + H0 W0 + b2 (residual by K-concatenation)
+//             -> L3 X W3 + b3 ;  final = output store | log-prob | (training) + stored a0, a1, v + masks / gates
+//   backward  B1 dv = dout W3^T -> B2 dh1 = (dv W2^T) . act'(h1) -> B3 du = (dh1 W1^T) . act'(u)   (each stored by TMA)
 //   sampler   T denoising steps x forward, x kept in the epilogue threads' registers, noise from Philox
 //             (or injected), chain / actions written once: ONE launch per rollout step.
 #pragma once

@@ -1,5 +1,7 @@
-// tcgen05 path (DPPO_PREC_BF16) for large row counts: every MLP layer and every gradient is one
-// tc::gemm_kernel launch (TMA-staged bf16 operands, fp32 accumulation in TMEM, fused epilogue).
+// tcgen05 path (DPPO_PREC_BF16) for large row counts: host programs.  Forward / backward chains run on the fused
+// layer-chain kernel (fused_chain.cuh) when the shapes allow it (ReLU at H = 256 / 512, Mish at H = 256, 64-wide h0),
+// else every MLP layer is one tc::gemm_kernel launch; the weight gradients are one grouped tcgen05 launch
+// (tc::dw_group_kernel) or, in the deterministic mode, one split-K GEMM + fixed-order reduction per product.
 //
 // Data layout in HBM (all bf16 activations are row-major [rows][features]; nothing is transposed):
 //   h0   [N][KP0]   = [ x (A) | obs (Do) | onehot(t) (T) | 1 | 0.. ]          KP0 = roundup(A+Do+T+1, 64)
@@ -8,7 +10,8 @@
 //        the forward pass and its gradient (per-t column sums of du) falls out of dW0 = h0^T du.
 //        The ones column does the same for the critic's input-layer bias gradient.
 //   a0,a1 [N][H]    post-activation outputs of layer 0 / block.l1 (operands of the next layer and of dW)
-//   pre0,pre1       pre-activation copies, only stored for Mish (ReLU masks come from a > 0)
+//   pre0,pre1       Mish only: pre-activation copies (per-layer path) / gates mish'(pre) (fused path);
+//                   ReLU derivatives are bit masks m0, m1 [N][H/32] (fused path) or taken from a > 0
 //   v    [N][H]     residual-block output  v = a1 W2 + b2 + u,  u = h0 W0 re-accumulated by K-concatenating
 //                   [a1 | h0] against [W2 ; W0] instead of storing and re-reading u
 //   eps  [N][A]     fp32 (feeds the fp32 loss kernels)
