@@ -335,7 +335,12 @@ def run_ours(args):
     achieved = d_fl / (d_ms * 1e-3) / 1e12 if d_ms > 0 else 0.0
     all_ms = sum(c[0] for c in cls); all_fl = sum(c[2] for c in cls)
     roof = {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-            "frac": achieved / pk["bf16_tflops_sustained"], "traffic": None,
+            "frac": achieved / pk["bf16_tflops_sustained"],
+            # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this bench
+            # (profiles/r01_final_chain_dw_ncu.txt): mean of the step's four chain launches (actor fwd 115 MB, critic fwd 82 MB,
+            # actor bwd 112 MB, critic bwd 77 MB); algorithmic HBM bytes of the same four: 171 / 134 / 160 / 83 MB
+            "traffic": 96.5e6 if tensor and dom == 0 else None,
+            "traffic_source": "profiles/r01_final_chain_dw_ncu.txt (static, from the committed ncu capture)" if tensor and dom == 0 else None,
             "kernel": names[dom],
             "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({pk_src}); the kernel runs inside a long step",
             "avg_launch_us": d_ms / max(d_n, 1) * 1e3, "launches_timed": d_n,
