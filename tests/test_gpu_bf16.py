@@ -212,3 +212,34 @@ def test_bf16_host_entry_chunked_pipeline_matches_device_call(pair):
     assert np.mean(np.abs(wa2 - wa1) > 0.05e-3) < 5e-3 and np.mean(np.abs(wc2 - wc1) > 0.05e-3) < 5e-3
     e.set_weights(L.NET_ACTOR_FT, w_a); e.set_weights(L.NET_CRITIC, w_c)
     e.set_opt_state(L.OPT_FINETUNE, np.zeros(n, np.float32), np.zeros(n, np.float32), 0)
+
+
+def test_bf16_logprobs_row_chunking_is_seamless(pair):
+    """dppo_logprobs walks the rows in chunks of 2^18 (whole chains per chunk): results around the chunk boundary and
+    in the ragged last tile must equal those of small independent calls on the same chains."""
+    o, e = pair
+    K, A = o.d.ft_denoising_steps, o.d.A
+    B = 27001                                     # 270 010 rows: two chunks, last tile ragged
+    g = torch.Generator(device="cuda"); g.manual_seed(11)
+    obs = torch.rand(B, o.d.Do, device="cuda", generator=g) * 2 - 1
+    _, chains = e.sample(obs, seed=3, offset=4)
+    lp = e.logprobs(obs, chains).reshape(B, K, A)
+    cut = (1 << 18) // K                          # first chain of the second chunk
+    for lo, hi in ((cut - 300, cut + 300), (B - 257, B), (0, 300)):
+        part = e.logprobs(obs[lo:hi].contiguous(), chains[lo:hi].contiguous()).reshape(hi - lo, K, A)
+        assert torch.equal(part, lp[lo:hi]), (lo, hi)
+    assert torch.isfinite(lp).all()
+
+
+def test_bf16_sampler_is_shard_invariant(pair):
+    """Philox counters are keyed by the global row: sampling rows [lo, hi) with row_offset = lo reproduces the same rows
+    of a single large call bit for bit (what makes the 8-GPU rollout independent of the shard layout)."""
+    o, e = pair
+    B = 4096
+    g = torch.Generator(device="cuda"); g.manual_seed(12)
+    obs = torch.rand(B, o.d.Do, device="cuda", generator=g) * 2 - 1
+    a_all, c_all = e.sample(obs, seed=9, offset=1)
+    lo, hi = 1024, 3200
+    a_part, c_part = e.sample(obs[lo:hi].contiguous(), seed=9, offset=1, row_offset=lo)
+    assert e.last_path() == _counts(e, 4, 3)
+    assert torch.equal(a_part, a_all[lo:hi]) and torch.equal(c_part, c_all[lo:hi])
