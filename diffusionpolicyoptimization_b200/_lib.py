@@ -23,7 +23,7 @@ EXPORTS = (
     "dppo_get_opt_state", "dppo_set_ft_denoising_steps", "dppo_actor_forward", "dppo_value",
     "dppo_sample", "dppo_sample_host", "dppo_logprobs", "dppo_logprobs_subsample", "dppo_ppo_step",
     "dppo_ppo_step_host", "dppo_ppo_step_indexed", "dppo_ppo_step_indexed_host", "dppo_gae", "dppo_pretrain_step", "dppo_ema_update", "dppo_comm_unique_id",
-    "dppo_comm_init", "dppo_launch_count", "dppo_tc_launch_count", "dppo_fused_launch_count", "dppo_last_path", "dppo_force_path", "dppo_profile_enable", "dppo_debug_tc_gemm",
+    "dppo_comm_init", "dppo_comm_ipc_export", "dppo_comm_ipc_attach", "dppo_launch_count", "dppo_tc_launch_count", "dppo_fused_launch_count", "dppo_last_path", "dppo_force_path", "dppo_profile_enable", "dppo_debug_tc_gemm",
     "dppo_profile_read", "dppo_debug_chain_timing", "dppo_debug_mma_probe", "dppo_profile_read_class",
 )
 
@@ -94,6 +94,8 @@ def load():
         "dppo_ema_update": (C.c_int, [vp, f32, vp]),
         "dppo_comm_unique_id": (C.c_int, [vp]),
         "dppo_comm_init": (C.c_int, [vp, vp, i32, i32]),
+        "dppo_comm_ipc_export": (C.c_int, [vp, vp]),
+        "dppo_comm_ipc_attach": (C.c_int, [vp, vp, i32, i32]),
         "dppo_launch_count": (i64, [vp]),
         "dppo_tc_launch_count": (i64, [vp]),
         "dppo_fused_launch_count": (i64, [vp]),

@@ -156,6 +156,11 @@ struct dppo_handle {
     cudaStream_t copy_stream = nullptr; cudaEvent_t copy_ev[9];   // chunked H2D / compute overlap of dppo_ppo_step_host
     // NCCL
     void* comm = nullptr; int rank = 0, world = 1;
+    // peer-memory all-reduce fused with AdamW (dppo_comm_ipc_*): two alternating gradient buffers, flag barrier
+    float* grads_buf[2] = {nullptr, nullptr}; int grads_cur = 0; float* gsum = nullptr; size_t grads_floats = 0;
+    unsigned long long* flags = nullptr;             // [8] epoch written by each peer
+    float* peer_grads[2][8] = {}; unsigned long long* peer_flags[8] = {}; int peers_attached = 0;
+    unsigned long long epoch = 0;
     int64_t launches = 0;
     int64_t tc_launches = 0;
     int w0p_dirty[4] = {1, 1, 1, 1};  // ActorDerived::w0p is stale (rebuilt on demand by the FFMA layer-0 GEMM)

@@ -278,6 +278,7 @@ extern "C" int dppo_create(const dppo_cfg* cfg, int device, dppo_handle** out) {
     }
     CUDA_TRY(cudaMalloc(&h->grads, (nA + nC + 16) * sizeof(float)));
     CUDA_TRY(cudaMemset(h->grads, 0, (nA + nC + 16) * sizeof(float)));
+    h->grads_buf[0] = h->grads; h->grads_floats = nA + nC + 16;
     CUDA_TRY(cudaMalloc(&h->scalars, 64 * sizeof(float)));
     CUDA_TRY(cudaMemset(h->scalars, 0, 64 * sizeof(float)));
     int r = tc_init(h);
@@ -298,7 +299,12 @@ extern "C" void dppo_destroy(dppo_handle* h) {
         void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
         if (lib) { typedef int (*fn_t)(void*); fn_t f = (fn_t)dlsym(lib, "ncclCommDestroy"); if (f) f(h->comm); }
     }
-    cudaFree(h->params); cudaFree(h->sched); cudaFree(h->grads); cudaFree(h->scalars);
+    if (h->peers_attached) {
+        for (int p = 0; p < h->world; ++p) if (p != h->rank) {
+            cudaIpcCloseMemHandle(h->peer_grads[0][p]); cudaIpcCloseMemHandle(h->peer_grads[1][p]); cudaIpcCloseMemHandle(h->peer_flags[p]);
+        }
+    }
+    cudaFree(h->params); cudaFree(h->sched); cudaFree(h->grads_buf[0]); cudaFree(h->grads_buf[1]); cudaFree(h->gsum); cudaFree(h->flags); cudaFree(h->scalars);
     for (int i = 0; i < 2; ++i) { cudaFree(h->opt[i].m); cudaFree(h->opt[i].v); }
     for (int net = 0; net < 4; ++net) { ActorDerived& d = h->ad[net]; cudaFree(d.sinemb); cudaFree(d.thpre); cudaFree(d.temb); cudaFree(d.bt); cudaFree(d.w0p); }
     if (h->ws.base) cudaFree(h->ws.base);
@@ -767,6 +773,57 @@ extern "C" int dppo_comm_init(dppo_handle* h, const char* id128, int rank, int w
     h->comm = comm; h->rank = rank; h->world = world;
     return 0;
 }
+extern "C" int dppo_comm_ipc_export(dppo_handle* h, char* out) {
+    ENTER(h);
+    if (!out) DPPO_FAIL(-1, "dppo_comm_ipc_export: null");
+    if (!h->grads_buf[1]) {
+        CUDA_TRY(cudaMalloc(&h->grads_buf[1], h->grads_floats * sizeof(float))); CUDA_TRY(cudaMemset(h->grads_buf[1], 0, h->grads_floats * sizeof(float)));
+        CUDA_TRY(cudaMalloc(&h->gsum, h->grads_floats * sizeof(float))); CUDA_TRY(cudaMemset(h->gsum, 0, h->grads_floats * sizeof(float)));
+        CUDA_TRY(cudaMalloc(&h->flags, 8 * sizeof(unsigned long long))); CUDA_TRY(cudaMemset(h->flags, 0, 8 * sizeof(unsigned long long)));
+        CUDA_TRY(cudaDeviceSynchronize());
+    }
+    cudaIpcMemHandle_t hd[3];
+    CUDA_TRY(cudaIpcGetMemHandle(&hd[0], h->grads_buf[0]));
+    CUDA_TRY(cudaIpcGetMemHandle(&hd[1], h->grads_buf[1]));
+    CUDA_TRY(cudaIpcGetMemHandle(&hd[2], h->flags));
+    static_assert(sizeof(cudaIpcMemHandle_t) * 3 == DPPO_IPC_BYTES, "IPC blob size");
+    memcpy(out, hd, sizeof(hd));
+    return 0;
+}
+extern "C" int dppo_comm_ipc_attach(dppo_handle* h, const char* all_blobs, int rank, int world) {
+    ENTER(h);
+    if (!all_blobs || world < 2 || world > 8 || rank < 0 || rank >= world) DPPO_FAIL(-1, "dppo_comm_ipc_attach: bad arguments (world must be 2..8)");
+    if (!h->grads_buf[1]) DPPO_FAIL(-1, "dppo_comm_ipc_attach: call dppo_comm_ipc_export first");
+    for (int p = 0; p < world; ++p) {
+        if (p == rank) { h->peer_grads[0][p] = h->grads_buf[0]; h->peer_grads[1][p] = h->grads_buf[1]; h->peer_flags[p] = h->flags; continue; }
+        cudaIpcMemHandle_t hd[3]; memcpy(hd, all_blobs + (size_t)p * DPPO_IPC_BYTES, sizeof(hd));
+        void* ptr[3];
+        for (int k = 0; k < 3; ++k) {
+            cudaError_t e = cudaIpcOpenMemHandle(&ptr[k], hd[k], cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) DPPO_FAIL(-6, "cudaIpcOpenMemHandle(rank %d, buffer %d) failed: %s", p, k, cudaGetErrorString(e));
+        }
+        h->peer_grads[0][p] = (float*)ptr[0]; h->peer_grads[1][p] = (float*)ptr[1]; h->peer_flags[p] = (unsigned long long*)ptr[2];
+    }
+    h->rank = rank; h->world = world; h->peers_attached = 1;
+    return 0;
+}
+// fused peer-memory all-reduce + AdamW: flag barrier, then every rank sums all ranks' gradient buffers (same order everywhere)
+// and updates its replica.  The sum lands in h->gsum; the gradient buffers alternate so that peers can keep reading this one.
+static int peer_allreduce_adamw(dppo_handle* h, cudaStream_t s, int opt, float* w, size_t n_param, size_t n_total, float lr, float wd) {
+    OptState& o = h->opt[opt];
+    o.step += 1;
+    const float b1 = h->cfg.adam_beta1, b2 = h->cfg.adam_beta2;
+    const float b1p = powf(b1, (float)o.step), b2p = powf(b2, (float)o.step);
+    const float alpha = lr * sqrtf(1.f - b2p) / (1.f - b1p);
+    PeerPtrs pp; memset(&pp, 0, sizeof(pp));
+    for (int p = 0; p < h->world; ++p) { pp.g[p] = h->peer_grads[h->grads_cur][p]; pp.flags[p] = h->peer_flags[p]; }
+    h->epoch += 1;
+    peer_barrier_kernel<<<1, 32, 0, s>>>(pp, h->flags, h->rank, h->world, h->epoch); KLAUNCH(h); KCHECK();
+    peer_allreduce_adamw_kernel<<<2 * h->sm_count, 256, 0, s>>>(pp, h->world, h->gsum, w, o.m, o.v, n_param, n_total, lr, alpha, b1, b2, h->cfg.adam_eps, wd);
+    KLAUNCH(h); KCHECK();
+    h->grads_cur ^= 1; h->grads = h->grads_buf[h->grads_cur];        // the next step accumulates into the other buffer
+    return 0;
+}
 static int allreduce_sum(dppo_handle* h, float* buf, size_t n, cudaStream_t s) {
     if (h->world <= 1) return 0;
     if (!h->comm || !g_allreduce) DPPO_FAIL(-6, "all-reduce requested but no communicator attached");
@@ -792,9 +849,14 @@ static int prep_net(dppo_handle* h, int net, cudaStream_t s);
 static int ppo_apply_tail(dppo_handle* h, cudaStream_t s, float lr, int apply, float* metrics8, float* grads_out) {
     const size_t nA = h->g.ao.n, nC = h->g.co.n; float* gr = h->grads;
     if (apply) {
-        DPPO_TRY(allreduce_sum(h, gr, nA + nC + 8, s));
         // actor_ft and critic are contiguous in `params` and share one optimizer (train_ppo_diffusion_agent.py:354-356)
-        DPPO_TRY(adam_apply(h, s, DPPO_OPT_FINETUNE, h->net_w[DPPO_NET_ACTOR_FT], gr, nA + nC, lr, h->cfg.weight_decay));
+        if (h->peers_attached && h->world > 1) {
+            DPPO_TRY(peer_allreduce_adamw(h, s, DPPO_OPT_FINETUNE, h->net_w[DPPO_NET_ACTOR_FT], nA + nC, nA + nC + 8, lr, h->cfg.weight_decay));
+            gr = h->gsum;
+        } else {
+            DPPO_TRY(allreduce_sum(h, gr, nA + nC + 8, s));
+            DPPO_TRY(adam_apply(h, s, DPPO_OPT_FINETUNE, h->net_w[DPPO_NET_ACTOR_FT], gr, nA + nC, lr, h->cfg.weight_decay));
+        }
         DPPO_TRY(prep_net(h, DPPO_NET_ACTOR_FT, s));
         DPPO_TRY(prep_net(h, DPPO_NET_CRITIC, s));
     }
@@ -1015,8 +1077,13 @@ extern "C" int dppo_pretrain_step(dppo_handle* h, const float* actions, const fl
         DPPO_TRY(actor_bwd_fp32(h, s, DPPO_NET_ACTOR, fa, deps, N, trow, ba, Ga, dw0a, gr));
     }
     if (apply) {
-        DPPO_TRY(allreduce_sum(h, gr, nA + 8, s));
-        DPPO_TRY(adam_apply(h, s, DPPO_OPT_PRETRAIN, h->net_w[DPPO_NET_ACTOR], gr, nA, lr, h->cfg.pretrain_weight_decay));
+        if (h->peers_attached && h->world > 1) {
+            DPPO_TRY(peer_allreduce_adamw(h, s, DPPO_OPT_PRETRAIN, h->net_w[DPPO_NET_ACTOR], nA, nA + 8, lr, h->cfg.pretrain_weight_decay));
+            gr = h->gsum;
+        } else {
+            DPPO_TRY(allreduce_sum(h, gr, nA + 8, s));
+            DPPO_TRY(adam_apply(h, s, DPPO_OPT_PRETRAIN, h->net_w[DPPO_NET_ACTOR], gr, nA, lr, h->cfg.pretrain_weight_decay));
+        }
         DPPO_TRY(prep_net(h, DPPO_NET_ACTOR, s));
     }
     if (loss) CUDA_TRY(cudaMemcpyAsync(loss, gr + nA, sizeof(float), cudaMemcpyDeviceToDevice, s));

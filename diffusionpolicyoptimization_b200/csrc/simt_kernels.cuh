@@ -727,6 +727,50 @@ __global__ void adamw_kernel(float* __restrict__ w, const float* __restrict__ g,
     p = p - mi * alpha / (sqrtf(vi) + eps);
     w[i] = p; m[i] = mi; v[i] = vi;
 }
+// ---- peer-memory gradient all-reduce fused with AdamW (one node, P2P over NVLink / NVSwitch)
+struct PeerPtrs { const float* g[8]; unsigned long long* flags[8]; };
+// flag barrier: tell every peer "my gradient buffer of this epoch is complete", wait until all peers said so
+__global__ void peer_barrier_kernel(PeerPtrs pp, unsigned long long* my_flags, int rank, int world, unsigned long long epoch) {
+    const int p = threadIdx.x;
+    if (p >= world) return;
+    __threadfence_system();
+    *((volatile unsigned long long*)(pp.flags[p] + rank)) = epoch;
+    const long long t0 = clock64();
+    while (*((volatile unsigned long long*)(my_flags + p)) < epoch) {
+        if (clock64() - t0 > 6000000000LL) { printf("peer barrier timed out: rank %d waiting for rank %d (epoch %llu)\n", rank, p, epoch); __trap(); }
+    }
+    __threadfence_system();
+}
+// g_sum = sum over ranks (fixed order) of their gradient buffers; AdamW on the first n_param entries; the reduced vector
+// (gradients ++ metric partial sums) is written back to this rank's buffer
+__global__ void __launch_bounds__(256) peer_allreduce_adamw_kernel(PeerPtrs pp, int world, float* __restrict__ g_sum, float* __restrict__ w,
+                                                                  float* __restrict__ m, float* __restrict__ v, size_t n_param, size_t n_total,
+                                                                  float lr, float alpha, float b1, float b2, float eps, float wd) {
+    const size_t n4 = n_total / 4;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4 + (n_total & 3); i += (size_t)gridDim.x * blockDim.x) {
+        float s[4] = {0.f, 0.f, 0.f, 0.f};
+        const bool vec = i < n4;
+        const size_t e0 = vec ? i * 4 : n4 * 4 + (i - n4);
+        const int cnt = vec ? 4 : 1;
+        for (int p = 0; p < world; ++p) {
+            if (vec) { const float4 x = __ldcv(reinterpret_cast<const float4*>(pp.g[p]) + i); s[0] += x.x; s[1] += x.y; s[2] += x.z; s[3] += x.w; }
+            else s[0] += __ldcv(pp.g[p] + e0);
+        }
+        for (int k = 0; k < cnt; ++k) {
+            const size_t e = e0 + k;
+            if (e < n_param) {
+                float pw = w[e], mi = m[e], vi = v[e]; const float gi = s[k];
+                if (wd != 0.f) pw = pw - pw * (wd * lr);
+                mi = mi + (gi - mi) * (1.f - b1);
+                vi = vi + (gi * gi - vi) * (1.f - b2);
+                pw = pw - mi * alpha / (sqrtf(vi) + eps);
+                w[e] = pw; m[e] = mi; v[e] = vi;
+            }
+        }
+        // this rank's gradient buffer is one of the summands its peers are still reading: the sum goes to a separate buffer
+        if (vec) reinterpret_cast<float4*>(g_sum)[i] = make_float4(s[0], s[1], s[2], s[3]); else g_sum[e0] = s[0];
+    }
+}
 __global__ void ema_kernel(float* __restrict__ ema, const float* __restrict__ w, size_t n, float decay) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) ema[i] = ema[i] * decay + w[i] * (1.f - decay);

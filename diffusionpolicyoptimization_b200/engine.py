@@ -270,6 +270,17 @@ class Engine:
         idb = C.create_string_buffer(obj[0], 128)
         L.check(self.lib.dppo_comm_init(self.h, idb, rank, world), "dppo_comm_init")
         self.rank, self.world = rank, world
+        # single node, <= 8 ranks: attach the peers' gradient buffers (CUDA IPC) so that the update uses the fused
+        # peer-memory all-reduce + AdamW kernel instead of ncclAllReduce + AdamW (DPPO_NO_PEER_ALLREDUCE=1 keeps NCCL)
+        import os
+        if world <= 8 and os.environ.get("DPPO_NO_PEER_ALLREDUCE") != "1":
+            blob = (C.c_char * 192)()
+            L.check(self.lib.dppo_comm_ipc_export(self.h, blob), "dppo_comm_ipc_export")
+            blobs = [None] * world
+            dist.all_gather_object(blobs, bytes(blob.raw), group=group)
+            allb = C.create_string_buffer(b"".join(blobs), 192 * world)
+            L.check(self.lib.dppo_comm_ipc_attach(self.h, allb, rank, world), "dppo_comm_ipc_attach")
+            self.peer_allreduce = True
 
     # ---------------------------------------------------------------- introspection
     def launch_count(self) -> int:

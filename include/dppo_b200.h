@@ -208,6 +208,16 @@ int dppo_ema_update(dppo_handle* h, float decay, dppo_stream_t s);
  * every rank calls dppo_comm_init.  NCCL is loaded with dlopen("libnccl.so.2"). */
 int dppo_comm_unique_id(char* id128);
 int dppo_comm_init(dppo_handle* h, const char* id128, int rank, int world);
+/* Peer-memory path of that all-reduce (single node, NVLink / NVSwitch P2P): every rank exports CUDA IPC handles of its
+ * two gradient buffers and of a flag array (dppo_comm_ipc_export fills HOST out[DPPO_IPC_BYTES]); the caller gathers the
+ * blobs of all ranks (any transport) and hands the concatenation [world][DPPO_IPC_BYTES] to dppo_comm_ipc_attach.  From
+ * then on `apply = 1` steps use ONE fused kernel instead of ncclAllReduce + AdamW: after a flag barrier over peer memory
+ * every rank reads all ranks' gradients through P2P loads in the same rank order (bit-identical sums everywhere), applies
+ * AdamW to its replica of the weights and keeps the reduced gradient / metrics.  Gradient buffers alternate between
+ * steps, so the barrier of the next step also protects the buffer peers may still be reading.  world <= 8. */
+#define DPPO_IPC_BYTES 192
+int dppo_comm_ipc_export(dppo_handle* h, char* out);
+int dppo_comm_ipc_attach(dppo_handle* h, const char* all_blobs, int rank, int world);
 
 /* Count of kernel launches issued by this handle since creation (bench `gpu_launches`). */
 int64_t dppo_launch_count(dppo_handle* h);

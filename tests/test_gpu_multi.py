@@ -1,0 +1,61 @@
+"""GPU (-m gpu), needs >= 2 B200s on the box (skipped otherwise): the data-parallel update.  Two ranks take three PPO steps
+on their own shards through (a) the fused peer-memory all-reduce + AdamW kernel and (b) ncclAllReduce + AdamW; the
+replicas must stay identical across ranks, and (a) must equal (b) (two summands: fp32 addition is commutative)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, out):
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    from diffusionpolicyoptimization_b200 import _lib as L
+    from diffusionpolicyoptimization_b200.parallel import advantage_stats, shard_range
+    from oracle import dppo_oracle as O
+    from helpers import make_engine
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    o = O.make_oracle("hopper", seed=0)
+    N = 8192
+    batch = O.make_ppo_batch(o, N, pool=512, seed=7)
+    lo, hi = shard_range(N, rank, world)
+    mean, std = advantage_stats(batch[6].numpy())
+    results = {}
+    for mode in ("peer", "nccl"):
+        os.environ["DPPO_NO_PEER_ALLREDUCE"] = "1" if mode == "nccl" else "0"
+        e = make_engine(o, precision=L.PREC_BF16, device=rank)
+        e.init_comm()
+        assert getattr(e, "peer_allreduce", False) == (mode == "peer")
+        for step in range(3):
+            m = e.ppo_step(batch[0][lo:hi].reshape(hi - lo, -1), batch[1][lo:hi].reshape(hi - lo, -1), batch[2][lo:hi].reshape(hi - lo, -1),
+                           batch[3][lo:hi], batch[4][lo:hi], batch[5][lo:hi], batch[6][lo:hi], batch[7][lo:hi].reshape(hi - lo, -1),
+                           lr=1e-3, apply=True, n_global=N, adv_mean=mean, adv_std=std)
+        torch.cuda.synchronize()
+        results[mode] = (np.concatenate([e.get_weights(L.NET_ACTOR_FT), e.get_weights(L.NET_CRITIC)]), m.cpu().numpy())
+        dist.barrier()
+        e.close()
+    w_all = [None] * world
+    dist.all_gather_object(w_all, results["peer"][0].tobytes())
+    if rank == 0:
+        out["replicas_identical"] = all(b == w_all[0] for b in w_all)
+        out["peer_vs_nccl_max_abs"] = float(np.abs(results["peer"][0] - results["nccl"][0]).max())
+        out["metrics_peer"] = results["peer"][1]; out["metrics_nccl"] = results["nccl"][1]
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_peer_allreduce_adamw_matches_nccl_and_keeps_replicas_identical():
+    import torch.multiprocessing as mp
+    mgr = mp.Manager(); out = mgr.dict()
+    mp.spawn(_worker, args=(2, 29577, out), nprocs=2, join=True)
+    assert out["replicas_identical"]
+    # deterministic mode aside, the dW accumulation order varies run to run (red.global.add): compare in units of the step
+    assert out["peer_vs_nccl_max_abs"] < 2e-3, out["peer_vs_nccl_max_abs"]
+    np.testing.assert_allclose(out["metrics_peer"], out["metrics_nccl"], rtol=2e-2, atol=1e-4)
