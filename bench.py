@@ -324,22 +324,23 @@ def run_ours(args):
     e.profile_enable(True)
     for i in range(args.steps):
         flush.zero_(); dev_step(i)
-    cls = [e.profile_read_class(c) for c in range(3)]
+    cls = [e.profile_read_class(c) for c in range(4)]
     e.profile_enable(False)
     tensor = prec == L.PREC_BF16
     step_ms = ms_dev / args.steps
-    names = ["fc::chain_kernel (fused tcgen05 MLP forward / backward chains)", "tc::gemm_kernel (tcgen05 split-K weight gradients)",
-             "sgemm_kernel (fp32 FFMA layers + gradients)"]
-    dom = max(range(3), key=lambda c: cls[c][0])
+    names = ["fc::chain_kernel<512> (fused tcgen05 actor forward / backward chains, CTA pairs)", "tc::dw_group_kernel (tcgen05 grouped split-K weight gradients)",
+             "sgemm_kernel (fp32 FFMA layers + gradients)", "fc::chain_kernel<256> (fused tcgen05 Mish critic forward / backward chains)"]
+    dom = max(range(4), key=lambda c: cls[c][0])
     d_ms, d_n, d_fl = cls[dom]
     achieved = d_fl / (d_ms * 1e-3) / 1e12 if d_ms > 0 else 0.0
     all_ms = sum(c[0] for c in cls); all_fl = sum(c[2] for c in cls)
     roof = {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
             "frac": achieved / pk["bf16_tflops_sustained"],
             # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this bench
-            # (profiles/r01_final_chain_dw_ncu.txt): mean of the step's four chain launches (actor fwd 115 MB, critic fwd 82 MB,
-            # actor bwd 112 MB, critic bwd 77 MB); algorithmic HBM bytes of the same four: 171 / 134 / 160 / 83 MB
-            "traffic": 96.5e6 if tensor and dom == 0 else None,
+            # (profiles/r01_final_chain_dw_ncu.txt): mean of the step's two chain_kernel<512> launches (actor forward 115 MB,
+            # actor backward 112 MB); algorithmic HBM bytes of the same two: 171 / 160 MB (part of the stores is still in L2
+            # when the kernel ends)
+            "traffic": 113.5e6 if tensor and dom == 0 else None,
             "traffic_source": "profiles/r01_final_chain_dw_ncu.txt (static, from the committed ncu capture)" if tensor and dom == 0 else None,
             "kernel": names[dom],
             "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({pk_src}); the kernel runs inside a long step",
@@ -350,7 +351,7 @@ def run_ours(args):
                                    "share_of_step": all_ms / args.steps / step_ms,
                                    "classes": {names[c].split(" ")[0]: {"ms_per_step": cls[c][0] / args.steps, "launches_per_step": cls[c][1] // args.steps,
                                                                         "tflops": cls[c][2] / (cls[c][0] * 1e-3) / 1e12 if cls[c][0] > 0 else 0.0}
-                                               for c in range(3) if cls[c][1] > 0}},
+                                               for c in range(4) if cls[c][1] > 0}},
             "note": None if tensor else "fp32 parity mode runs on CUDA cores: FFMA peak is ~74.5 TFLOP/s (148 SM x 128 x 2 x 1.965 GHz); frac is still quoted against the bf16 tensor peak"}
 
     # ---- sampling half of the metric: walker2d, 40 env copies, T=20 chain, in-kernel Philox

@@ -176,9 +176,9 @@ struct dppo_handle {
     // live GEMM timing (dppo_profile_*): event pairs recorded around GEMM-class launches
     int prof_on = 0;
     std::vector<cudaEvent_t> prof_ev;   // pairs
-    std::vector<int> prof_cls;          // kernel class of each pair: 0 fused chain, 1 tcgen05 GEMM, 2 FFMA SGEMM
+    std::vector<int> prof_cls;          // kernel class of each pair: 0 fused chain <H = 512>, 1 tcgen05 GEMM, 2 FFMA SGEMM, 3 fused chain <H = 256>
     size_t prof_used = 0;
-    double prof_flops[3] = {0, 0, 0}, prof_ms_acc[3] = {0, 0, 0}; int64_t prof_launches[3] = {0, 0, 0};
+    double prof_flops[4] = {0, 0, 0, 0}, prof_ms_acc[4] = {0, 0, 0, 0}; int64_t prof_launches[4] = {0, 0, 0, 0};
 };
 
 int ws_reserve(dppo_handle* h, size_t bytes, cudaStream_t s);

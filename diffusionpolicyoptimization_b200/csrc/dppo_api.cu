@@ -148,12 +148,12 @@ extern "C" int dppo_profile_enable(dppo_handle* h, int on) {
     if (!h) DPPO_FAIL(-1, "null handle");
     CUDA_TRY(cudaSetDevice(h->device)); CUDA_TRY(cudaDeviceSynchronize());
     h->prof_used = 0;
-    for (int c = 0; c < 3; ++c) { h->prof_flops[c] = 0; h->prof_ms_acc[c] = 0; h->prof_launches[c] = 0; }
+    for (int c = 0; c < 4; ++c) { h->prof_flops[c] = 0; h->prof_ms_acc[c] = 0; h->prof_launches[c] = 0; }
     h->prof_on = on ? 1 : 0;
     return 0;
 }
 extern "C" int dppo_profile_read_class(dppo_handle* h, int cls, double* ms, int64_t* launches, double* flops) {
-    if (!h || cls < 0 || cls > 2) DPPO_FAIL(-1, "dppo_profile_read_class: bad arguments");
+    if (!h || cls < 0 || cls > 3) DPPO_FAIL(-1, "dppo_profile_read_class: bad arguments");
     CUDA_TRY(cudaSetDevice(h->device)); CUDA_TRY(cudaDeviceSynchronize());
     prof_flush(h);
     if (ms) *ms = h->prof_ms_acc[cls]; if (launches) *launches = h->prof_launches[cls]; if (flops) *flops = h->prof_flops[cls];
@@ -163,9 +163,9 @@ extern "C" int dppo_profile_read(dppo_handle* h, double* ms, int64_t* launches, 
     if (!h) DPPO_FAIL(-1, "null handle");
     CUDA_TRY(cudaSetDevice(h->device)); CUDA_TRY(cudaDeviceSynchronize());
     prof_flush(h);
-    if (ms) *ms = h->prof_ms_acc[0] + h->prof_ms_acc[1] + h->prof_ms_acc[2];
-    if (launches) *launches = h->prof_launches[0] + h->prof_launches[1] + h->prof_launches[2];
-    if (flops) *flops = h->prof_flops[0] + h->prof_flops[1] + h->prof_flops[2];
+    if (ms) *ms = h->prof_ms_acc[0] + h->prof_ms_acc[1] + h->prof_ms_acc[2] + h->prof_ms_acc[3];
+    if (launches) *launches = h->prof_launches[0] + h->prof_launches[1] + h->prof_launches[2] + h->prof_launches[3];
+    if (flops) *flops = h->prof_flops[0] + h->prof_flops[1] + h->prof_flops[2] + h->prof_flops[3];
     return 0;
 }
 

@@ -251,8 +251,8 @@ int dppo_debug_chain_timing(dppo_handle* h, int enable, long long* out_host, int
 int dppo_debug_mma_probe(dppo_handle* h, int grid, int mode, int iters, int N, int depth, long long* out_host);
 int dppo_profile_enable(dppo_handle* h, int on);
 int dppo_profile_read(dppo_handle* h, double* gemm_ms, int64_t* gemm_launches, double* gemm_flops);
-/* Same, per kernel class: 0 = fused tcgen05 layer-chain kernel, 1 = tcgen05 GEMM (weight gradients, per-layer
- * fallback), 2 = FFMA SGEMM (fp32 parity mode).  flops are ALGORITHMIC (un-padded dims). */
+/* Same, per kernel: 0 = fc::chain_kernel<512> (fused tcgen05 layer chain, actor width), 1 = tcgen05 GEMMs (grouped weight
+ * gradients, per-layer fallback), 2 = FFMA SGEMM (fp32 parity mode), 3 = fc::chain_kernel<256> (Mish critic width).  flops are ALGORITHMIC (un-padded dims). */
 int dppo_profile_read_class(dppo_handle* h, int cls, double* ms, int64_t* launches, double* flops);
 
 #ifdef __cplusplus
