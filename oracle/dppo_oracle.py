@@ -5,11 +5,18 @@ CPU (torch fp32 / numpy) restatement of the reference's DPPO hot path.  Only `te
 `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl reference` leg may import this
 module; the product (`diffusionpolicyoptimization_b200/`) never does.
 
-PARITY UNPINNED: the reference (jamesmshihua/DiffusionPolicyOptimization) ships no tests, golden
+PARITY PIN: the reference (jamesmshihua/DiffusionPolicyOptimization) ships no tests, golden
 vectors or known-answer files for this path, and its arithmetic lives in TensorFlow / Keras 3 /
 tensorflow-probability, none of which is installed (or installable: no network) in the build
-image.  This file therefore restates, line by line, what the reference's Python does, and restates
-the *published* semantics of the third-party ops it calls:
+image.  The pin is therefore the reference's OWN Python: tests/golden/make_ref_golden.py imports
+model/diffusion/*.py and model/common/{mlp,critic}.py unmodified from /root/reference and executes
+them over tests/golden/tf_shim/ (a torch-CPU stand-in for the ~60 TF primitives they call); the
+resulting fixtures tests/golden/ref_*.npz are checked against this file by tests/test_ref_golden.py
+and against the CUDA path by tests/test_gpu_ref_golden.py.  That pins control flow, schedule
+arithmetic, indexing, clip order, network switch, chain bookkeeping, loss/metric composition and
+gradient variable order to the reference's code.  NOT pinned (TensorFlow itself never ran): the
+numerical kernels of the third-party ops, restated here and in the shim from their *published*
+semantics:
 
   * tf.keras.layers.Dense            : y = x @ W[in,out] + b
   * tf.keras.activations.mish        : x * tanh(softplus(x))
