@@ -123,14 +123,21 @@ class Engine:
 
     def sample(self, obs, deterministic=False, use_base_policy=False, min_sampling_std: float = -1.0,
                seed: int = 0, offset: int = 0, row_offset: int = 0, x_T=None, noise=None,
-               return_chain=True) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
-        """Device-resident call: obs is (moved to) a CUDA tensor; returns CUDA tensors."""
+               return_chain=True, actions_out: Optional[torch.Tensor] = None,
+               chains_out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+        """Device-resident call: obs is (moved to) a CUDA tensor; returns CUDA tensors.  `actions_out` [B,A] /
+        `chains_out` [B,K+1,A] (contiguous fp32 CUDA views, e.g. one step of a resident rollout buffer) are written in
+        place by the sampling kernel when given."""
         obs = _as_dev(obs, self.dev).reshape(-1, self.Do)
         B = obs.shape[0]
         x_T = None if x_T is None else _as_dev(x_T, self.dev).reshape(B, self.A)
         noise = None if noise is None else _as_dev(noise, self.dev).reshape(self.T, B, self.A)
-        actions = torch.empty(B, self.A, device=self.dev, dtype=torch.float32)
-        chains = torch.empty(B, self.K + 1, self.A, device=self.dev, dtype=torch.float32) if return_chain else None
+        for name, buf, n in (("actions_out", actions_out, B * self.A), ("chains_out", chains_out, B * (self.K + 1) * self.A)):
+            if buf is not None and not (buf.is_cuda and buf.dtype == torch.float32 and buf.is_contiguous() and buf.numel() == n):
+                raise ValueError(f"{name} must be a contiguous fp32 CUDA tensor of {n} elements")
+        actions = actions_out if actions_out is not None else torch.empty(B, self.A, device=self.dev, dtype=torch.float32)
+        chains = chains_out if chains_out is not None else (
+            torch.empty(B, self.K + 1, self.A, device=self.dev, dtype=torch.float32) if return_chain else None)
         L.check(self.lib.dppo_sample(self.h, _ptr(obs), B, int(deterministic), int(use_base_policy), float(min_sampling_std),
                                      int(seed), int(offset), int(row_offset), _ptr(x_T), _ptr(noise),
                                      _ptr(actions), _ptr(chains), self._stream()), "dppo_sample")

@@ -7,7 +7,7 @@ import numpy as np
 
 from oracle import dppo_oracle as O
 
-REF_GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "ref_*.npz")))
+REF_GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "ref_hopper_*.npz")))
 REF_IDS = [os.path.basename(p)[4:-4] for p in REF_GOLDEN]
 BATCH_KEYS = ("ppo_obs", "ppo_prev", "ppo_next", "ppo_inds", "ppo_returns", "ppo_oldvalues", "ppo_adv", "ppo_oldlogp")
 

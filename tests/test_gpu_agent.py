@@ -1,0 +1,96 @@
+"""GPU: the DPPO fine-tuning loop with the rollout resident in HBM (agent/finetune/train_ppo_diffusion_agent.py of this
+package) against the CPU restatement of the reference's loop (oracle/dppo_loop.py) on a deterministic toy environment,
+with the Gaussian draws and the minibatch permutations replayed on both sides."""
+import numpy as np
+import pytest
+import torch
+
+import diffusionpolicyoptimization_b200 as dp
+from diffusionpolicyoptimization_b200 import _lib as L
+from diffusionpolicyoptimization_b200.agent.finetune.train_ppo_diffusion_agent import TrainPPODiffusionAgent
+from helpers import rel_err, max_abs
+from oracle import dppo_loop as OL
+from oracle import dppo_oracle as O
+from toy_env import ToyVecEnv
+
+pytestmark = pytest.mark.gpu
+
+E, S, ACT_STEPS, LR = 8, 6, 4, 1e-4
+
+
+def make_model(o, precision="fp32", **kw):
+    d = o.d
+    actor = dp.DiffusionMLP(action_dim=d.action_dim, horizon_steps=d.horizon_steps, cond_dim=d.obs_dim, time_dim=16,
+                            mlp_dims=[512, 512, 512], activation_type="ReLU", residual_style=True)
+    critic = dp.CriticObs(cond_dim=d.obs_dim, mlp_dims=[256, 256, 256], activation_type="Mish", residual_style=True)
+    model = dp.PPODiffusion(gamma_denoising=0.99, clip_ploss_coef=0.01, clip_ploss_coef_base=0.01, clip_ploss_coef_rate=3,
+                            randn_clip_value=3, min_sampling_denoising_std=0.1, min_logprob_denoising_std=0.1,
+                            actor=actor, critic=critic, ft_denoising_steps=d.ft_denoising_steps, horizon_steps=d.horizon_steps,
+                            obs_dim=d.obs_dim, action_dim=d.action_dim, denoising_steps=d.denoising_steps, device="cuda:0",
+                            precision=precision, **kw)
+    model.actor.set_flat_weights(O.flatten_params(o.actor))
+    model.actor_ft.set_flat_weights(O.flatten_params(o.actor_ft))
+    model.critic.set_flat_weights(O.flatten_params(o.critic))
+    return model
+
+
+def noise_fn(itr, step, B, A=12, T=20):
+    rng = np.random.default_rng(1000 + 97 * itr + step)
+    return rng.standard_normal((B, A)).astype(np.float32), rng.standard_normal((T, B, A)).astype(np.float32)
+
+
+def shuffle_fn(itr, epoch, total):
+    return np.random.default_rng(5000 + 13 * itr + epoch).permutation(total)
+
+
+def test_two_iterations_match_the_reference_loop():
+    o = O.make_oracle("hopper", seed=21)
+    model = make_model(o)
+    kw = dict(n_steps=S, act_steps=ACT_STEPS, batch_size=160, update_epochs=2, gamma=0.99, gae_lambda=0.95, target_kl=1)
+    agent = TrainPPODiffusionAgent(model, ToyVecEnv(E, 11, 3, seed=3), n_envs=E, n_train_itr=2, actor_lr=LR, force_train=True,
+                                   reset_at_iteration=False, reward_scale_running=True, noise_fn=noise_fn,
+                                   shuffle_fn=shuffle_fn, **kw)
+    venv = ToyVecEnv(E, 11, 3, seed=3)
+    scaler = OL.RewardScaler(E)
+    params = o.actor_ft + o.critic
+    opt = dict(m=[torch.zeros_like(p) for p in params], v=[torch.zeros_like(p) for p in params], step=0)
+    prev_obs, firsts0 = venv.reset_arg(), 1
+    for itr in range(2):
+        want, prev_obs, done = OL.ppo_iteration(o, opt, venv, itr, prev_obs, lr=LR, reward_scaler=scaler, reward_scale_const=1.0,
+                                                noise_fn=noise_fn, shuffle_fn=shuffle_fn, firsts0=firsts0, **kw)
+        firsts0 = done
+        got = agent.run_iteration()
+        K = o.d.ft_denoising_steps
+        assert rel_err(agent.chains_trajs.reshape(S * E, K + 1, -1), want["chains_k"].reshape(S * E, K + 1, -1)) < 5e-4
+        assert got["n_updates"] == want["n_updates"] == 6
+        for k in ("pg_loss", "v_loss", "approx_kl", "ratio", "clipfrac", "explained_var"):
+            assert abs(got[k] - want[k]) < 5e-3 * max(1.0, abs(want[k])) + 2e-5, (itr, k, got[k], want[k])
+    assert agent.opt_iterations == opt["step"] == 12
+    got_w = np.concatenate([model.engine.get_weights(L.NET_ACTOR_FT), model.engine.get_weights(L.NET_CRITIC)])
+    want_w = O.flatten_params(params)
+    moved = np.abs(want_w - np.concatenate([O.flatten_params(O.make_oracle("hopper", seed=21).actor_ft),
+                                            O.flatten_params(O.make_oracle("hopper", seed=21).critic)]))
+    assert moved.mean() > 2 * LR                      # 12 Adam steps really happened
+    frac_bad = np.mean(np.abs(got_w - want_w) > 0.25 * LR)
+    assert frac_bad < 1e-2, frac_bad
+    np.testing.assert_array_equal(model.engine.get_weights(L.NET_ACTOR), O.flatten_params(o.actor))   # base net frozen
+
+
+def test_eval_iteration_does_not_train_and_tensor_mode_runs():
+    """itr 0 is an eval iteration (val_freq, :70): deterministic sampling, no update.  Then a bf16 tensor-mode training
+    iteration on the library's own Philox stream (>= 2048 rows per minibatch)."""
+    o = O.make_oracle("hopper", seed=22)
+    model = make_model(o, precision="bf16")
+    n_envs, n_steps = 64, 8
+    agent = TrainPPODiffusionAgent(model, ToyVecEnv(n_envs, 11, 3, max_episode_steps=3, seed=4), n_envs=n_envs, n_steps=n_steps,
+                                   act_steps=ACT_STEPS, n_train_itr=3, batch_size=2560, update_epochs=3, actor_lr=3e-4, val_freq=2)
+    w0 = model.engine.get_weights(L.NET_ACTOR_FT).copy()
+    r0 = agent.run_iteration()
+    assert r0["eval_mode"] and "pg_loss" not in r0 and r0["num_episode_finished"] > 0 and r0["step"] == 0
+    np.testing.assert_array_equal(model.engine.get_weights(L.NET_ACTOR_FT), w0)
+    n0 = model.engine.tc_launch_count() + model.engine.fused_launch_count()
+    r1 = agent.run_iteration()
+    assert not r1["eval_mode"] and r1["n_updates"] == 6 and np.isfinite(r1["loss"]) and r1["step"] == n_envs * ACT_STEPS * n_steps
+    assert model.engine.tc_launch_count() + model.engine.fused_launch_count() > n0       # the tensor path ran
+    assert np.abs(model.engine.get_weights(L.NET_ACTOR_FT) - w0).max() > 1e-4
+    assert 0.0 <= r1["clipfrac"] <= 1.0 and abs(r1["ratio"] - 1.0) < 0.2

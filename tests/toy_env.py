@@ -1,0 +1,32 @@
+"""A deterministic vector environment with the reference's venv API (reset_arg / step), for agent-loop tests."""
+import numpy as np
+
+
+class ToyVecEnv:
+    def __init__(self, n_envs, obs_dim, action_dim, max_episode_steps=4, seed=0, term_threshold=0.93):
+        rng = np.random.default_rng(seed)
+        self.E, self.Do, self.Da = n_envs, obs_dim, action_dim
+        self.W = rng.normal(size=(action_dim, obs_dim)) / np.sqrt(action_dim)
+        self.s0 = rng.uniform(-0.8, 0.8, size=(n_envs, obs_dim))
+        self.max_episode_steps, self.term_threshold = max_episode_steps, term_threshold
+        self.reset_arg()
+
+    def _obs(self):
+        return {"state": self.s[:, None, :].astype(np.float32)}
+
+    def reset_arg(self, options_list=None):
+        self.s = self.s0.copy()
+        self.t = np.zeros(self.E, dtype=np.int64)
+        return self._obs()
+
+    def step(self, action):
+        a = np.asarray(action, np.float64).mean(axis=1)
+        self.s = 0.9 * self.s + 0.3 * np.tanh(a @ self.W)
+        self.t += 1
+        reward = 1.0 - (self.s ** 2).sum(-1) + 0.1 * a.sum(-1)
+        terminated = np.abs(self.s).max(-1) > self.term_threshold
+        truncated = self.t >= self.max_episode_steps
+        done = terminated | truncated
+        self.s[done] = self.s0[done]          # auto-reset like the reference's async vector env
+        self.t[done] = 0
+        return self._obs(), reward, terminated, truncated, [{} for _ in range(self.E)]
