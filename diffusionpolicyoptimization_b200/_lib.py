@@ -20,7 +20,7 @@ OPT_PRETRAIN, OPT_FINETUNE = 0, 1
 EXPORTS = (
     "dppo_abi_version", "dppo_last_error", "dppo_cfg_default", "dppo_cfg_size", "dppo_ddpm_schedule", "dppo_num_params",
     "dppo_create", "dppo_destroy", "dppo_set_weights", "dppo_get_weights", "dppo_set_opt_state",
-    "dppo_get_opt_state", "dppo_set_ft_denoising_steps", "dppo_actor_forward", "dppo_value",
+    "dppo_get_opt_state", "dppo_set_ft_denoising_steps", "dppo_set_grad_clip_norm", "dppo_actor_forward", "dppo_value",
     "dppo_sample", "dppo_sample_host", "dppo_logprobs", "dppo_logprobs_subsample", "dppo_ppo_step",
     "dppo_ppo_step_host", "dppo_ppo_step_indexed", "dppo_ppo_step_indexed_host", "dppo_gae", "dppo_pretrain_step", "dppo_ema_update", "dppo_comm_unique_id",
     "dppo_comm_init", "dppo_comm_ipc_export", "dppo_comm_ipc_attach", "dppo_launch_count", "dppo_tc_launch_count", "dppo_fused_launch_count", "dppo_last_path", "dppo_force_path", "dppo_profile_enable", "dppo_debug_tc_gemm",
@@ -79,6 +79,7 @@ def load():
         "dppo_set_opt_state": (C.c_int, [vp, i32, vp, vp, sz, i64, i32, vp]),
         "dppo_get_opt_state": (C.c_int, [vp, i32, vp, vp, sz, C.POINTER(i64), i32, vp]),
         "dppo_set_ft_denoising_steps": (C.c_int, [vp, i32]),
+        "dppo_set_grad_clip_norm": (C.c_int, [vp, f32]),
         "dppo_actor_forward": (C.c_int, [vp, i32, vp, vp, vp, i32, vp, vp]),
         "dppo_value": (C.c_int, [vp, vp, i32, vp, vp]),
         "dppo_sample": (C.c_int, [vp, vp, i32, i32, i32, f32, u64, u64, i64, vp, vp, vp, vp, vp]),

@@ -37,10 +37,10 @@ class TrainPPODiffusionAgent:
         train_ppo_agent.py:35-49).  `noise_fn(itr, step, B) -> (x_T [B,A], noise [T,B,A])` and
         `shuffle_fn(itr, epoch, total) -> int permutation` replace the library's Philox stream / torch.randperm
         (tests inject them to replay the same draws on a CPU restatement of the loop)."""
-        if max_grad_norm is not None:
-            raise NotImplementedError("per-tensor clip_by_norm (train_ppo_diffusion_agent.py:349-354) is not in the library; "
-                                      "no shipped cfg sets max_grad_norm")
         self.model, self.venv, self.engine = model, venv, model.engine
+        # :349-354: any max_grad_norm switches on tf.clip_by_norm(grad, clip_norm=1.0) per variable (the constant is the reference's)
+        self.max_grad_norm = max_grad_norm
+        self.engine.set_grad_clip_norm(1.0 if max_grad_norm is not None else None)
         self.n_envs, self.n_steps, self.act_steps = int(n_envs), int(n_steps), int(act_steps)
         self.n_train_itr, self.batch_size, self.update_epochs = int(n_train_itr), int(batch_size), int(update_epochs)
         self.gamma, self.gae_lambda, self.target_kl = gamma, gae_lambda, target_kl

@@ -358,6 +358,12 @@ extern "C" int dppo_set_ft_denoising_steps(dppo_handle* h, int K) {
     h->g.K = K; h->cfg.ft_denoising_steps = K;
     return 0;
 }
+extern "C" int dppo_set_grad_clip_norm(dppo_handle* h, float clip_norm) {
+    if (!h) DPPO_FAIL(-1, "null handle");
+    if (clip_norm != clip_norm) DPPO_FAIL(-1, "dppo_set_grad_clip_norm: NaN");
+    h->grad_clip_norm = clip_norm > 0.f ? clip_norm : 0.f;
+    return 0;
+}
 extern "C" int64_t dppo_launch_count(dppo_handle* h) { return h ? h->launches : -1; }
 extern "C" int64_t dppo_tc_launch_count(dppo_handle* h) { return h ? h->tc_launches : -1; }
 extern "C" int64_t dppo_fused_launch_count(dppo_handle* h) { return h ? h->fused_launches : -1; }
@@ -850,7 +856,18 @@ static int ppo_apply_tail(dppo_handle* h, cudaStream_t s, float lr, int apply, f
     const size_t nA = h->g.ao.n, nC = h->g.co.n; float* gr = h->grads;
     if (apply) {
         // actor_ft and critic are contiguous in `params` and share one optimizer (train_ppo_diffusion_agent.py:354-356)
-        if (h->peers_attached && h->world > 1) {
+        if (h->grad_clip_norm > 0.f) {
+            // clipping needs the norms of the REDUCED gradient before the update: reduce, (hand out the unclipped gradient), clip, update
+            DPPO_TRY(allreduce_sum(h, gr, nA + nC + 8, s));
+            if (grads_out) { CUDA_TRY(cudaMemcpyAsync(grads_out, gr, (nA + nC) * sizeof(float), cudaMemcpyDeviceToDevice, s)); grads_out = nullptr; }
+            const ActorOff& a = h->g.ao; const CriticOff& c = h->g.co;
+            const size_t offs[21] = {a.tw1, a.tb1, a.tw2, a.tb2, a.win, a.bin, a.w1, a.b1, a.w2, a.b2, a.w3, a.b3,
+                                     nA + c.win, nA + c.bin, nA + c.w1, nA + c.b1, nA + c.w2, nA + c.b2, nA + c.w3, nA + c.b3, nA + nC};
+            VarSegs segs; segs.n = 20;
+            for (int i = 0; i <= 20; ++i) segs.off[i] = (unsigned int)offs[i];
+            clip_by_norm_kernel<<<segs.n, 1024, 0, s>>>(gr, segs, h->grad_clip_norm); KLAUNCH(h); KCHECK();
+            DPPO_TRY(adam_apply(h, s, DPPO_OPT_FINETUNE, h->net_w[DPPO_NET_ACTOR_FT], gr, nA + nC, lr, h->cfg.weight_decay));
+        } else if (h->peers_attached && h->world > 1) {
             DPPO_TRY(peer_allreduce_adamw(h, s, DPPO_OPT_FINETUNE, h->net_w[DPPO_NET_ACTOR_FT], nA + nC, nA + nC + 8, lr, h->cfg.weight_decay));
             gr = h->gsum;
         } else {

@@ -727,6 +727,28 @@ __global__ void adamw_kernel(float* __restrict__ w, const float* __restrict__ g,
     p = p - mi * alpha / (sqrtf(vi) + eps);
     w[i] = p; m[i] = mi; v[i] = vi;
 }
+// tf.clip_by_norm on every variable of the flat gradient (train_ppo_diffusion_agent.py:352): one block per variable,
+// g <- g * c / max(||g||_2, c)   (l2sum == 0 -> norm 1, like TF's guarded sqrt)
+struct VarSegs { unsigned int off[24]; int n; };
+__global__ void __launch_bounds__(1024) clip_by_norm_kernel(float* __restrict__ g, VarSegs segs, float clip) {
+    const unsigned int b = segs.off[blockIdx.x], e = segs.off[blockIdx.x + 1];
+    float acc = 0.f;
+    for (unsigned int i = b + threadIdx.x; i < e; i += blockDim.x) { const float x = g[i]; acc = fmaf(x, x, acc); }
+    __shared__ float part[32];
+    __shared__ float denom;
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float t = threadIdx.x < (blockDim.x >> 5) ? part[threadIdx.x] : 0.f;
+        for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (threadIdx.x == 0) denom = fmaxf(sqrtf(t > 0.f ? t : 1.f), clip);
+    }
+    __syncthreads();
+    const float d = denom;
+    if (d == clip) return;                                   // norm <= clip: g * c / c
+    for (unsigned int i = b + threadIdx.x; i < e; i += blockDim.x) g[i] = g[i] * clip / d;
+}
 // ---- peer-memory gradient all-reduce fused with AdamW (one node, P2P over NVLink / NVSwitch)
 struct PeerPtrs { const float* g[8]; unsigned long long* flags[8]; };
 // flag barrier: tell every peer "my gradient buffer of this epoch is complete", wait until all peers said so

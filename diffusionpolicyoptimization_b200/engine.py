@@ -104,6 +104,10 @@ class Engine:
         L.check(self.lib.dppo_set_ft_denoising_steps(self.h, int(K)), "dppo_set_ft_denoising_steps")
         self.cfg.ft_denoising_steps = int(K)
 
+    def set_grad_clip_norm(self, clip_norm: Optional[float]):
+        """Per-variable tf.clip_by_norm before AdamW (train_ppo_diffusion_agent.py:349-354); None / <= 0 switches it off."""
+        L.check(self.lib.dppo_set_grad_clip_norm(self.h, float(clip_norm) if clip_norm else 0.0), "dppo_set_grad_clip_norm")
+
     # ---------------------------------------------------------------- forward-only
     def actor_forward(self, net: int, x, t, obs) -> torch.Tensor:
         x = _as_dev(x, self.dev).reshape(-1, self.A)

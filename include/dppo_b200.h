@@ -107,6 +107,12 @@ int dppo_set_opt_state(dppo_handle* h, int opt, const float* m, const float* v, 
 int dppo_get_opt_state(dppo_handle* h, int opt, float* m, float* v, size_t n, int64_t* step, int is_device, dppo_stream_t s);
 /* VPGDiffusion.step(): set the number of fine-tuned denoising steps (diffusion_vpg.py:114-142). */
 int dppo_set_ft_denoising_steps(dppo_handle* h, int K);
+/* Per-variable gradient clipping of the fine-tuning update, train_ppo_diffusion_agent.py:349-354:
+ * `[tf.clip_by_norm(g, clip_norm) for g in gradients]` (each Dense kernel / bias on its own: g * c / max(||g||_2, c)),
+ * applied after the data-parallel reduction and before AdamW.  clip_norm <= 0 switches it off (the default; no shipped
+ * cfg sets max_grad_norm).  The reference passes the constant 1.0 whatever max_grad_norm is.  `grads_out` of the
+ * ppo_step calls keeps returning the unclipped gradient (what tape.gradient returns). */
+int dppo_set_grad_clip_norm(dppo_handle* h, float clip_norm);
 
 /* DiffusionMLP.call (mlp_diffusion.py:65-90): eps[N,A] = net(x[N,A], t[N] int32, obs[N,Do]). */
 int dppo_actor_forward(dppo_handle* h, int net, const float* x, const int32_t* t, const float* obs,

@@ -446,6 +446,17 @@ def adamw_keras(params, grads, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-7,
         p.sub_(mi * alpha / (torch.sqrt(vi) + eps))
 
 
+def clip_by_norm(grads, clip_norm=1.0):
+    """[tf.clip_by_norm(g, clip_norm) for g in gradients], agent/finetune/train_ppo_diffusion_agent.py:352
+    (published TF semantics: t * clip_norm / max(sqrt(sum(t*t)), clip_norm), the sqrt guarded for an all-zero t)."""
+    out = []
+    for g in grads:
+        l2sum = (g * g).sum()
+        l2norm = torch.sqrt(torch.where(l2sum > 0, l2sum, torch.ones_like(l2sum)))
+        out.append(g * clip_norm / torch.maximum(l2norm, torch.tensor(clip_norm, dtype=g.dtype)))
+    return out
+
+
 def gae(rewards: np.ndarray, terminated: np.ndarray, values: np.ndarray, next_values: np.ndarray,
         reward_scale_const: float = 1.0, gamma: float = 0.999, gae_lambda: float = 0.95):
     """agent/finetune/train_ppo_diffusion_agent.py:242-263 — NumPy float64 backward scan over the rollout.

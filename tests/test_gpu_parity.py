@@ -192,6 +192,42 @@ def test_ppo_adamw_step_matches_keras_semantics():
     e.close()
 
 
+@pytest.mark.parametrize("clip", [0.03, 1e-3])     # 0.03: about half of the 20 variables exceed it
+def test_ppo_per_variable_clip_by_norm(clip):
+    """train_ppo_diffusion_agent.py:349-354: every variable's gradient is clipped to `clip` on its own before AdamW;
+    the gradient handed back stays the unclipped one.  Adam's update is scale-free, so the first moments carry the check."""
+    o = O.make_oracle("hopper", seed=16)
+    e = make_engine(o)
+    N = 384
+    batch = O.make_ppo_batch(o, N, pool=64, seed=17)
+    _, ga, gc = o.ppo_grads(*batch)
+    raw = ga + gc
+    norms = [float(g.norm()) for g in raw]
+    assert any(n > clip for n in norms) and (clip < 0.01 or any(n <= clip for n in norms))   # both branches of the max()
+    clipped = O.clip_by_norm(raw, clip)
+    e.set_grad_clip_norm(clip)
+    _, g = e.ppo_step(_flat_obs(batch[0]), batch[1].reshape(N, -1), batch[2].reshape(N, -1), batch[3], batch[4], batch[5],
+                      batch[6], batch[7].reshape(N, -1), lr=0.0, apply=True, want_grads=True)
+    want_raw = O.flatten_params(raw)
+    assert np.abs(g.cpu().numpy() - want_raw).max() < 1e-3 * np.abs(want_raw).max()
+    mm, _, st = e.get_opt_state(L.OPT_FINETUNE)
+    assert st == 1
+    off = 0
+    for c, n in zip(clipped, norms):
+        want = (c * (1 - o.h.beta1)).numpy().reshape(-1)
+        got = mm[off:off + want.size]; off += want.size
+        assert np.abs(got - want).max() < 2e-3 * np.abs(want).max(), (n, clip)
+    assert off == mm.size
+    # switching it off again restores the plain update
+    e.set_grad_clip_norm(None)
+    e.set_opt_state(L.OPT_FINETUNE, np.zeros_like(mm), np.zeros_like(mm), 0)
+    e.ppo_step(_flat_obs(batch[0]), batch[1].reshape(N, -1), batch[2].reshape(N, -1), batch[3], batch[4], batch[5],
+               batch[6], batch[7].reshape(N, -1), lr=0.0, apply=True)
+    mm2, _, _ = e.get_opt_state(L.OPT_FINETUNE)
+    assert np.abs(mm2 - want_raw * (1 - o.h.beta1)).max() < 2e-3 * np.abs(want_raw).max() * (1 - o.h.beta1)
+    e.close()
+
+
 @pytest.mark.parametrize("N", [64, 1500])
 def test_pretrain_loss_and_gradients(pair, N):
     o, e = pair
