@@ -94,3 +94,57 @@ def test_eval_iteration_does_not_train_and_tensor_mode_runs():
     assert model.engine.tc_launch_count() + model.engine.fused_launch_count() > n0       # the tensor path ran
     assert np.abs(model.engine.get_weights(L.NET_ACTOR_FT) - w0).max() > 1e-4
     assert 0.0 <= r1["clipfrac"] <= 1.0 and abs(r1["ratio"] - 1.0) < 0.2
+
+
+def test_pretrain_loop_matches_the_reference_loop():
+    """agent/pretrain/train_diffusion_agent.py:56-93 + train_agent.py:113-139: sequential batches (short tail), AdamW under
+    CosineDecayRestarts, EMA copy before epoch_start_ema and decay after — replayed with the same (t, eps) draws."""
+    from diffusionpolicyoptimization_b200.agent.pretrain.train_diffusion_agent import CosineDecayRestarts, TrainDiffusionAgent
+    o = O.make_oracle("hopper", seed=31)
+    d = o.d
+    actor = dp.DiffusionMLP(action_dim=3, horizon_steps=4, cond_dim=11, time_dim=16, mlp_dims=[512, 512, 512],
+                            activation_type="ReLU", residual_style=True)
+    model = dp.DiffusionModel(network=actor, horizon_steps=4, obs_dim=11, action_dim=3, denoising_steps=20, device="cuda:0",
+                              precision="fp32")
+    model.network.set_flat_weights(O.flatten_params(o.actor))
+    rng = np.random.default_rng(7)
+    M, B, EPOCHS = 300, 128, 3
+    actions = rng.uniform(-1, 1, size=(M, 4, 3)).astype(np.float32)
+    states = rng.uniform(-1, 1, size=(M, 1, 11)).astype(np.float32)
+
+    def draws_fn(epoch, batch, n):
+        r = np.random.default_rng(900 + 31 * epoch + batch)
+        return r.integers(0, 20, size=n).astype(np.int32), r.standard_normal((n, 12)).astype(np.float32)
+
+    agent = TrainDiffusionAgent(model, actions, states, n_epochs=EPOCHS, batch_size=B, learning_rate=1e-3, lr_first_cycle_steps=5,
+                                lr_min=1e-4, ema_decay=0.9, epoch_start_ema=2, update_ema_freq=1, draws_fn=draws_fn)
+    got_losses = agent.run()
+
+    sched = CosineDecayRestarts(1e-3, 5, alpha=0.1)
+    assert abs(sched(0) - 1e-3) < 1e-12 and abs(sched(5) - 1e-3) < 1e-12 and sched(4) < sched(1)     # restart every 5 steps
+    net = [p.clone() for p in o.actor]
+    ema = [p.clone() for p in net]
+    m = [torch.zeros_like(p) for p in net]; v = [torch.zeros_like(p) for p in net]
+    it, want_losses = 0, []
+    for epoch in range(1, EPOCHS + 1):
+        ep = []
+        for nb, r0 in enumerate(range(0, M, B)):
+            t, eps = draws_fn(epoch, nb, min(B, M - r0))
+            oo = O.Oracle(o.d, o.h, net, o.actor_ft, o.critic)
+            loss, g = oo.pretrain_grads(torch.from_numpy(actions[r0:r0 + B]), torch.from_numpy(states[r0:r0 + B]),
+                                        torch.from_numpy(t).long(), torch.from_numpy(eps).reshape(-1, 4, 3))
+            O.adamw_keras(net, g, m, v, it + 1, sched(it), o.h.beta1, o.h.beta2, o.h.adam_eps, 1e-6)
+            it += 1
+            ep.append(float(loss))
+        want_losses.append(float(np.mean(ep)))
+        if epoch < 2:
+            ema = [p.clone() for p in net]
+        else:
+            O.ema_update(ema, net, 0.9)
+    np.testing.assert_allclose(got_losses, want_losses, rtol=2e-3)
+    assert agent.opt_iterations == it == 9
+    got_w, want_w = model.engine.get_weights(L.NET_ACTOR), O.flatten_params(net)
+    assert np.mean(np.abs(got_w - want_w) > 0.25 * 1e-3) < 1e-2
+    got_e, want_e = model.engine.get_weights(L.NET_ACTOR_EMA), O.flatten_params(ema)
+    assert np.mean(np.abs(got_e - want_e) > 0.25 * 1e-3) < 1e-2
+    assert np.abs(got_e - got_w).max() > 1e-5                      # EMA really lags the model
