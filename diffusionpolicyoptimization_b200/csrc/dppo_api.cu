@@ -874,8 +874,12 @@ static int ppo_apply_tail(dppo_handle* h, cudaStream_t s, float lr, int apply, f
             DPPO_TRY(allreduce_sum(h, gr, nA + nC + 8, s));
             DPPO_TRY(adam_apply(h, s, DPPO_OPT_FINETUNE, h->net_w[DPPO_NET_ACTOR_FT], gr, nA + nC, lr, h->cfg.weight_decay));
         }
-        DPPO_TRY(prep_net(h, DPPO_NET_ACTOR_FT, s));
-        DPPO_TRY(prep_net(h, DPPO_NET_CRITIC, s));
+        if (h->cfg.precision == DPPO_PREC_BF16 && tc_shapes_ok(h) && 2 * h->g.td <= 256) {
+            DPPO_TRY(tc_prep_pack_ft_critic(h, s));
+        } else {
+            DPPO_TRY(prep_net(h, DPPO_NET_ACTOR_FT, s));
+            DPPO_TRY(prep_net(h, DPPO_NET_CRITIC, s));
+        }
     }
     if (metrics8) CUDA_TRY(cudaMemcpyAsync(metrics8, gr + nA + nC, 8 * sizeof(float), cudaMemcpyDeviceToDevice, s));
     if (grads_out) CUDA_TRY(cudaMemcpyAsync(grads_out, gr, (nA + nC) * sizeof(float), cudaMemcpyDeviceToDevice, s));

@@ -230,14 +230,14 @@ __global__ void reduce_partials_kernel(const float* __restrict__ part, int S, si
 // Derived tables of an actor: sinusoidal embedding -> time MLP -> per-t layer-0 bias, packed W_in
 //   modules.py:10-15, mlp_diffusion.py:40-45,83-86.  grid = T blocks of H threads (H <= 1024).
 // =====================================================================================
-__global__ void actor_prep_kernel(const float* __restrict__ w, ActorOff o, int A, int td, int H,
+// bt16 (optional): the same table rounded to bf16, written straight into the time rows of the packed layer-0 operand
+__device__ __forceinline__ void actor_prep_body(const int t, float* sm, const float* __restrict__ w, ActorOff o, int A, int td, int H,
                                   float* __restrict__ sinemb, float* __restrict__ thpre,
-                                  float* __restrict__ temb, float* __restrict__ bt) {
-    extern __shared__ float sm[];
+                                  float* __restrict__ temb, float* __restrict__ bt, __nv_bfloat16* __restrict__ bt16) {
     float* se = sm;            // [td]
     float* hp = se + td;       // [2td]
     float* te = hp + 2 * td;   // [td]
-    const int t = blockIdx.x, tid = threadIdx.x;
+    const int tid = threadIdx.x;
     const int half = td / 2;
     if (tid < td) {
         int i = tid % half;
@@ -264,7 +264,14 @@ __global__ void actor_prep_kernel(const float* __restrict__ w, ActorOff o, int A
         float s = w[o.bin + c];
         for (int j = 0; j < td; ++j) s = fmaf(te[j], w[o.win + (size_t)(A + j) * H + c], s);
         bt[(size_t)t * H + c] = s;
+        if (bt16) bt16[(size_t)t * H + c] = __float2bfloat16(s);
     }
+}
+__global__ void actor_prep_kernel(const float* __restrict__ w, ActorOff o, int A, int td, int H,
+                                  float* __restrict__ sinemb, float* __restrict__ thpre,
+                                  float* __restrict__ temb, float* __restrict__ bt) {
+    extern __shared__ float sm[];
+    actor_prep_body(blockIdx.x, sm, w, o, A, td, H, sinemb, thpre, temb, bt, nullptr);
 }
 // w0p[k][c]: k < A -> W_in[k], A <= k < A+Do -> W_in[k+td], else 0.   (skip = td for actor, 0 for critic with A=0)
 __global__ void pack_w0_kernel(const float* __restrict__ win, int A, int skip, int Do, int KP, int H,
@@ -492,19 +499,23 @@ __global__ void __launch_bounds__(128) ppo_loss_kernel(
     if (threadIdx.x < 5) block_sums[(size_t)blockIdx.x * 5 + threadIdx.x] = red[threadIdx.x][0];
 }
 // sums the per-block partials; writes metric partial sums (already divided by N_global) to dst[0..7]
-__global__ void ppo_metrics_kernel(const double* __restrict__ block_sums, int nblocks, float inv_nglobal, float frac_local,
-                                   float* __restrict__ dst) {
+// body shared by ppo_metrics_kernel and the merged tail kernel: threads >= 256 of a larger block only take part in the barriers
+__device__ __forceinline__ void ppo_metrics_body(const double* __restrict__ block_sums, int nblocks, float inv_nglobal, float frac_local,
+                                                 float* __restrict__ dst) {
     __shared__ double red[5][256];
+    const int tid = threadIdx.x;
     double a[5] = {0, 0, 0, 0, 0};
-    for (int b = threadIdx.x; b < nblocks; b += blockDim.x)
-        for (int k = 0; k < 5; ++k) a[k] += block_sums[(size_t)b * 5 + k];
-    for (int k = 0; k < 5; ++k) red[k][threadIdx.x] = a[k];
+    if (tid < 256) {
+        for (int b = tid; b < nblocks; b += 256)
+            for (int k = 0; k < 5; ++k) a[k] += block_sums[(size_t)b * 5 + k];
+        for (int k = 0; k < 5; ++k) red[k][tid] = a[k];
+    }
     __syncthreads();
     for (int o = 128; o > 0; o >>= 1) {
-        if (threadIdx.x < o) for (int k = 0; k < 5; ++k) red[k][threadIdx.x] += red[k][threadIdx.x + o];
+        if (tid < o) for (int k = 0; k < 5; ++k) red[k][tid] += red[k][tid + o];
         __syncthreads();
     }
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
         dst[0] = (float)(red[0][0] * inv_nglobal);   // pg_loss
         dst[1] = -frac_local;                         // entropy_loss = -mean(eta) = -1 (eta == 1 for DDPM)
         dst[2] = (float)(red[1][0] * inv_nglobal);   // v_loss
@@ -514,6 +525,10 @@ __global__ void ppo_metrics_kernel(const double* __restrict__ block_sums, int nb
         dst[6] = 0.f;                                 // bc_loss
         dst[7] = frac_local;                          // mean eta
     }
+}
+__global__ void ppo_metrics_kernel(const double* __restrict__ block_sums, int nblocks, float inv_nglobal, float frac_local,
+                                   float* __restrict__ dst) {
+    ppo_metrics_body(block_sums, nblocks, inv_nglobal, frac_local, dst);
 }
 
 // minibatch assembly from the resident rollout buffers (train_ppo_diffusion_agent.py:293-312): one thread per output float
@@ -619,19 +634,21 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ D
 }
 
 // time-MLP + layer-0 bias backward from G[T][H] = per-t column sums of du.  One block, 512 threads.
-__global__ void __launch_bounds__(512) time_backward_kernel(const float* __restrict__ w, ActorOff o, int A, int td, int H, int T,
+// `bid` of `nblk` blocks (a stand-alone launch or a block range of the merged tail kernel).  `staged`: sm also has room for
+// G [T][H] and the td time rows of W_in [td][H]; block 0 then reads them once, coalesced, instead of walking L2 per t.
+__device__ __forceinline__ void time_backward_body(const int bid, const int nblk, float* sm, const bool staged,
+                                     const float* __restrict__ w, ActorOff o, int A, int td, int H, int T,
                                      const float* __restrict__ G, const float* __restrict__ sinemb,
                                      const float* __restrict__ thpre, const float* __restrict__ temb,
                                      float* __restrict__ g) {
-    extern __shared__ float sm[];
     float* dte = sm;                 // [T][td]
     float* dh = dte + T * td;        // [T][2td]
     const int tid = threadIdx.x, nt = blockDim.x;
     // gridDim.x == 1: one block does everything.  Otherwise block 0 does the time-MLP part and blocks 1.. split the
     // per-column part (db_in and dW_in[A+j]) 128 columns each, 4 threads per column over j.
-    if (gridDim.x == 1 || blockIdx.x > 0) {
-        const int c0 = gridDim.x == 1 ? 0 : (blockIdx.x - 1) * 128, c1 = gridDim.x == 1 ? H : min(H, c0 + 128);
-        const int lanes = gridDim.x == 1 ? 1 : 4;            // threads per column
+    if (nblk == 1 || bid > 0) {
+        const int c0 = nblk == 1 ? 0 : (bid - 1) * 128, c1 = nblk == 1 ? H : min(H, c0 + 128);
+        const int lanes = nblk == 1 ? 1 : 4;            // threads per column
         for (int i = tid; i < (c1 - c0) * lanes; i += nt) {
             const int c = c0 + i / lanes, part = i % lanes;
             // the T values of column c are loaded up front (independent loads: one L2 latency instead of T)
@@ -666,10 +683,26 @@ __global__ void __launch_bounds__(512) time_backward_kernel(const float* __restr
                 g[o.win + (size_t)(A + j) * H + c] = a;
             }
         }
-        if (gridDim.x > 1) return;
+        if (nblk > 1) return;
     }
     // d temb[t][j] = sum_c W_in[A+j][c] * G[t][c]: one warp per j keeps its W_in row in registers (H <= 1024) and walks t;
     // the H/32 loads of a step are independent, so the load latency is paid ~T times, not T*H/32 times
+    if (staged) {
+        float* sG = dh + T * 2 * td;   // [T][H]
+        float* sW = sG + T * H;        // [td][H]: rows A .. A+td of W_in are contiguous
+        for (int i = tid; i < T * H; i += nt) sG[i] = G[i];
+        for (int i = tid; i < td * H; i += nt) sW[i] = w[o.win + (size_t)A * H + i];
+        __syncthreads();
+        const int lane = tid & 31;
+        for (int p = tid >> 5; p < T * td; p += nt >> 5) {       // same summation order as the register-tiled loop below
+            const int t = p / td, j = p % td;
+            float s = 0.f;
+            for (int c = lane; c < H; c += 32) s = fmaf(sW[j * H + c], sG[t * H + c], s);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+            if (lane == 0) dte[t * td + j] = s;
+        }
+    } else
     for (int j = tid >> 5; j < td; j += nt >> 5) {
         const int lane = tid & 31;
         float wr[32];
@@ -705,12 +738,22 @@ __global__ void __launch_bounds__(512) time_backward_kernel(const float* __restr
     for (int j = tid; j < td; j += nt) { float s = 0.f; for (int t = 0; t < T; ++t) s += dte[t * td + j]; g[o.tb2 + j] = s; }
     for (int k = tid; k < 2 * td; k += nt) { float s = 0.f; for (int t = 0; t < T; ++t) s += dh[t * 2 * td + k]; g[o.tb1 + k] = s; }
 }
+__global__ void __launch_bounds__(512) time_backward_kernel(const float* __restrict__ w, ActorOff o, int A, int td, int H, int T,
+                                     const float* __restrict__ G, const float* __restrict__ sinemb,
+                                     const float* __restrict__ thpre, const float* __restrict__ temb,
+                                     float* __restrict__ g) {
+    extern __shared__ float sm[];
+    time_backward_body(blockIdx.x, gridDim.x, sm, false, w, o, A, td, H, T, G, sinemb, thpre, temb, g);
+}
 // scatter dW0p[KP][H] rows back into dW_in: k < A -> row k; A <= k < A+Do -> row k+skip
-__global__ void unpack_dw0_kernel(const float* __restrict__ dw0p, int A, int skip, int Do, int H, float* __restrict__ gwin) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void unpack_dw0_body(const int bid, const float* __restrict__ dw0p, int A, int skip, int Do, int H, float* __restrict__ gwin) {
+    int i = bid * blockDim.x + threadIdx.x;
     if (i >= (A + Do) * H) return;
     int k = i / H, c = i % H;
     gwin[(size_t)(k < A ? k : k + skip) * H + c] = dw0p[i];
+}
+__global__ void unpack_dw0_kernel(const float* __restrict__ dw0p, int A, int skip, int Do, int H, float* __restrict__ gwin) {
+    unpack_dw0_body(blockIdx.x, dw0p, A, skip, Do, H, gwin);
 }
 
 // =====================================================================================

@@ -41,10 +41,10 @@ struct TcState {
 };
 
 // ------------------------------------------------------------------ small kernels
-__global__ void tc_pack_actor_kernel(const float* __restrict__ w, ActorOff o, int A, int td, int Do, int T, int H, int KP0,
+// bt == nullptr: the T time rows of the layer-0 operand are written elsewhere (actor_prep_body's bt16 output)
+__device__ __forceinline__ void tc_pack_actor_body(const size_t i0, const size_t stride, const float* __restrict__ w, ActorOff o, int A, int td, int Do, int T, int H, int KP0,
                                      const float* __restrict__ bt, bf16* __restrict__ w2w0, bf16* __restrict__ w1,
                                      bf16* __restrict__ w3t, bf16* __restrict__ w3p, bf16* __restrict__ w1t, bf16* __restrict__ w2t) {
-    const size_t stride = (size_t)gridDim.x * blockDim.x, i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     for (size_t i = i0; i < (size_t)H * H; i += stride) {
         w2w0[i] = __float2bfloat16(w[o.w2 + i]); w1[i] = __float2bfloat16(w[o.w1 + i]);
         const size_t r = i / H, c = i % H;            // transposed copies: coalesced writes, strided (L2-resident) reads
@@ -55,7 +55,7 @@ __global__ void tc_pack_actor_kernel(const float* __restrict__ w, ActorOff o, in
         float v = 0.f;
         if (k < A) v = w[o.win + (size_t)k * H + c];
         else if (k < A + Do) v = w[o.win + (size_t)(k + td) * H + c];
-        else if (k < A + Do + T) v = bt[(size_t)(k - A - Do) * H + c];
+        else if (k < A + Do + T) { if (!bt) continue; v = bt[(size_t)(k - A - Do) * H + c]; }
         w2w0[(size_t)H * H + i] = __float2bfloat16(v);
     }
     for (size_t i = i0; i < (size_t)64 * H; i += stride) {
@@ -67,10 +67,14 @@ __global__ void tc_pack_actor_kernel(const float* __restrict__ w, ActorOff o, in
         w3p[i] = __float2bfloat16(a < A ? w[o.w3 + (size_t)k * A + a] : 0.f);
     }
 }
-__global__ void tc_pack_critic_kernel(const float* __restrict__ w, CriticOff o, int A, int Do, int Hc, int KP0,
+__global__ void tc_pack_actor_kernel(const float* __restrict__ w, ActorOff o, int A, int td, int Do, int T, int H, int KP0,
+                                     const float* __restrict__ bt, bf16* __restrict__ w2w0, bf16* __restrict__ w1,
+                                     bf16* __restrict__ w3t, bf16* __restrict__ w3p, bf16* __restrict__ w1t, bf16* __restrict__ w2t) {
+    tc_pack_actor_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, (size_t)gridDim.x * blockDim.x, w, o, A, td, Do, T, H, KP0, bt, w2w0, w1, w3t, w3p, w1t, w2t);
+}
+__device__ __forceinline__ void tc_pack_critic_body(const size_t i0, const size_t stride, const float* __restrict__ w, CriticOff o, int A, int Do, int Hc, int KP0,
                                       bf16* __restrict__ w2w0, bf16* __restrict__ w1, bf16* __restrict__ w3t,
                                       bf16* __restrict__ w3p, float* __restrict__ bias2, bf16* __restrict__ w1t, bf16* __restrict__ w2t) {
-    const size_t stride = (size_t)gridDim.x * blockDim.x, i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     for (size_t i = i0; i < (size_t)Hc * Hc; i += stride) {
         w2w0[i] = __float2bfloat16(w[o.w2 + i]); w1[i] = __float2bfloat16(w[o.w1 + i]);
         const size_t r = i / Hc, c = i % Hc;
@@ -84,6 +88,31 @@ __global__ void tc_pack_critic_kernel(const float* __restrict__ w, CriticOff o, 
     for (size_t i = i0; i < (size_t)64 * Hc; i += stride) { int a = (int)(i / Hc), k = (int)(i % Hc); w3t[i] = __float2bfloat16(a == 0 ? w[o.w3 + k] : 0.f); }
     for (size_t i = i0; i < (size_t)Hc * 128; i += stride) { int k = (int)(i / 128), a = (int)(i % 128); w3p[i] = __float2bfloat16(a == 0 ? w[o.w3 + k] : 0.f); }
     for (size_t i = i0; i < (size_t)Hc; i += stride) bias2[i] = w[o.b2 + i] + w[o.bin + i];
+}
+__global__ void tc_pack_critic_kernel(const float* __restrict__ w, CriticOff o, int A, int Do, int Hc, int KP0,
+                                      bf16* __restrict__ w2w0, bf16* __restrict__ w1, bf16* __restrict__ w3t,
+                                      bf16* __restrict__ w3p, float* __restrict__ bias2, bf16* __restrict__ w1t, bf16* __restrict__ w2t) {
+    tc_pack_critic_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, (size_t)gridDim.x * blockDim.x, w, o, A, Do, Hc, KP0, w2w0, w1, w3t, w3p, bias2, w1t, w2t);
+}
+// After the fine-tuning AdamW step: derived time tables of actor_ft, its bf16 operand copies and the critic's, in ONE launch
+// (blocks [0,T): one denoising step's table row each | next na blocks: actor operands | rest: critic operands).
+struct TcPrepPackArgs {
+    const float* wa; ActorOff ao; const float* wc; CriticOff co; int A, td, Do, T, H, Hc, KP0, na, nc;
+    float* sinemb; float* thpre; float* temb; float* bt;
+    bf16 *a_w2w0, *a_w1, *a_w3t, *a_w3p, *a_w1t, *a_w2t;
+    bf16 *c_w2w0, *c_w1, *c_w3t, *c_w3p, *c_w1t, *c_w2t; float* c_bias2;
+};
+__global__ void __launch_bounds__(256) tc_prep_pack_kernel(const TcPrepPackArgs a) {
+    extern __shared__ float prep_sm[];
+    const int b = blockIdx.x;
+    if (b < a.T)
+        actor_prep_body(b, prep_sm, a.wa, a.ao, a.A, a.td, a.H, a.sinemb, a.thpre, a.temb, a.bt, a.a_w2w0 + (size_t)a.H * a.H + (size_t)(a.A + a.Do) * a.H);
+    else if (b < a.T + a.na)
+        tc_pack_actor_body((size_t)(b - a.T) * blockDim.x + threadIdx.x, (size_t)a.na * blockDim.x, a.wa, a.ao, a.A, a.td, a.Do, a.T, a.H, a.KP0, nullptr,
+                           a.a_w2w0, a.a_w1, a.a_w3t, a.a_w3p, a.a_w1t, a.a_w2t);
+    else
+        tc_pack_critic_body((size_t)(b - a.T - a.na) * blockDim.x + threadIdx.x, (size_t)a.nc * blockDim.x, a.wc, a.co, a.A, a.Do, a.Hc, a.KP0,
+                            a.c_w2w0, a.c_w1, a.c_w3t, a.c_w3p, a.c_bias2, a.c_w1t, a.c_w2t);
 }
 // h0[r] = [x[r] | obs[r / obs_div] | onehot(t_r) | 1 | 0..]; one thread per 8 consecutive columns (16-byte store)
 // chainK > 0: x is a chains tensor [B][chainK+1][A] and row r = b*chainK + k reads chains[b][k] (get_logprobs)
@@ -155,15 +184,49 @@ __global__ void tc_reduce2d_kernel(const float* __restrict__ part, int S, size_t
 
 // out[c] = sum_b part[b*stride + c]: one warp per column, lanes stride over the nb partial rows (deterministic)
 // columns >= split (when out2 is given) go to out2[c - split]
-__global__ void __launch_bounds__(256) tc_reduce_cols_kernel(const float* __restrict__ part, int nb, size_t stride, int ncols, float* __restrict__ out,
-                                                             int split = 0, float* __restrict__ out2 = nullptr) {
-    const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+__device__ __forceinline__ void tc_reduce_cols_body(const int bid, const float* __restrict__ part, int nb, size_t stride, int ncols,
+                                                    float* __restrict__ out, int split, float* __restrict__ out2) {
+    const int c = bid * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (c >= ncols) return;
     float s = 0.f;
     for (int b = lane; b < nb; b += 32) s += part[(size_t)b * stride + c];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) { if (out2 && c >= split) out2[c - split] = s; else out[c] = s; }
+}
+__global__ void __launch_bounds__(256) tc_reduce_cols_kernel(const float* __restrict__ part, int nb, size_t stride, int ncols, float* __restrict__ out,
+                                                             int split = 0, float* __restrict__ out2 = nullptr) {
+    tc_reduce_cols_body(blockIdx.x, part, nb, stride, ncols, out, split, out2);
+}
+
+// Everything between the grouped weight-gradient GEMM and AdamW in ONE launch (tensor path, deferred mode): the eight small
+// kernels are mutually independent, so block ranges take the roles - loss metrics | three column reductions (output-layer and
+// hidden-layer bias gradients) | time-embedding backward | the two dW0 scatters | the critic's input-bias row.
+struct TcTailArgs {
+    int first[9];                                  // first block of role r; first[8] = grid size
+    // metrics
+    const double* bsum; int blocks_done; float inv_nglobal, frac_local; float* metrics;
+    // column reductions
+    const float* colb3; int ncol3; float* b3a; int split3; float* b3c;
+    const float* cpa; int rows_a; int HA; float* b2a; float* b1a;
+    const float* cpc; int rows_c; int HC; float* b2c; float* b1c;
+    // time backward
+    const float* w; ActorOff ao; int A, td, T, Do; int tb_staged; const float* Gt; const float* sinemb; const float* thpre; const float* temb; float* gr;
+    // unpack
+    const float* dw0a; float* gwin_a; const float* dw0c_obs; float* gwin_c; const float* dw0c_bias; float* gbin_c;
+};
+__global__ void __launch_bounds__(512) tc_ppo_tail_kernel(const TcTailArgs a) {
+    extern __shared__ float tail_sm[];
+    const int b = blockIdx.x;
+    if (b < a.first[1]) ppo_metrics_body(a.bsum, a.blocks_done, a.inv_nglobal, a.frac_local, a.metrics);
+    else if (b < a.first[2]) tc_reduce_cols_body(b - a.first[1], a.colb3, a.blocks_done, (size_t)a.ncol3, a.ncol3, a.b3a, a.split3, a.b3c);
+    else if (b < a.first[3]) tc_reduce_cols_body(b - a.first[2], a.cpa, a.rows_a, (size_t)2 * a.HA, 2 * a.HA, a.b2a, a.HA, a.b1a);
+    else if (b < a.first[4]) tc_reduce_cols_body(b - a.first[3], a.cpc, a.rows_c, (size_t)2 * a.HC, 2 * a.HC, a.b2c, a.HC, a.b1c);
+    else if (b < a.first[5]) time_backward_body(b - a.first[4], a.first[5] - a.first[4], tail_sm, a.tb_staged != 0, a.w, a.ao, a.A, a.td, a.HA, a.T,
+                                                a.Gt, a.sinemb, a.thpre, a.temb, a.gr);
+    else if (b < a.first[6]) unpack_dw0_body(b - a.first[5], a.dw0a, a.A, a.td, a.Do, a.HA, a.gwin_a);
+    else if (b < a.first[7]) unpack_dw0_body(b - a.first[6], a.dw0c_obs, 0, 0, a.Do, a.HC, a.gwin_c);
+    else { const int i = (b - a.first[7]) * blockDim.x + threadIdx.x; if (i < a.HC) a.gbin_c[i] = a.dw0c_bias[i]; }
 }
 
 // PPO loss + gradient seeds for the tensor path (diffusion_ppo.py:32-132), one thread per row, single pass:
@@ -318,6 +381,24 @@ static int tc_refresh_net(dppo_handle* h, int net, cudaStream_t s) {
     h->launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) DPPO_FAIL(-3, "tc pack launch failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+// prep_net(ACTOR_FT) + prep_net(CRITIC) of the PPO update in one launch (tensor mode)
+static int tc_prep_pack_ft_critic(dppo_handle* h, cudaStream_t s) {
+    const Geom& g = h->g; TcNetW& wa = h->tc->net[DPPO_NET_ACTOR_FT]; TcNetW& wc = h->tc->net[DPPO_NET_CRITIC];
+    const ActorDerived& d = h->ad[DPPO_NET_ACTOR_FT];
+    TcPrepPackArgs a;
+    a.wa = h->net_w[DPPO_NET_ACTOR_FT]; a.ao = g.ao; a.wc = h->net_w[DPPO_NET_CRITIC]; a.co = g.co;
+    a.A = g.A; a.td = g.td; a.Do = g.Do; a.T = g.T; a.H = g.H; a.Hc = g.Hc; a.KP0 = h->tc->KP0; a.na = 256; a.nc = 128;
+    a.sinemb = d.sinemb; a.thpre = d.thpre; a.temb = d.temb; a.bt = d.bt;
+    a.a_w2w0 = wa.w2w0; a.a_w1 = wa.w1; a.a_w3t = wa.w3t; a.a_w3p = wa.w3p; a.a_w1t = wa.w1t; a.a_w2t = wa.w2t;
+    a.c_w2w0 = wc.w2w0; a.c_w1 = wc.w1; a.c_w3t = wc.w3t; a.c_w3p = wc.w3p; a.c_w1t = wc.w1t; a.c_w2t = wc.w2t; a.c_bias2 = wc.bias2;
+    h->w0p_dirty[DPPO_NET_ACTOR_FT] = 1; h->w0p_dirty[DPPO_NET_CRITIC] = 1;
+    tc_prep_pack_kernel<<<g.T + a.na + a.nc, 256, 4 * g.td * sizeof(float), s>>>(a);
+    h->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) DPPO_FAIL(-3, "tc prep/pack launch failed: %s", cudaGetErrorString(e));
     return 0;
 }
 
@@ -848,17 +929,36 @@ static int tc_ppo_finish(dppo_handle* h, cudaStream_t s) {
     TcPpoPlan& P = tc_plan(h);
     float* gr = h->grads;
     const bool defer = P.ma.fused && P.mc.fused && !h->deterministic;
+    const float* w = h->net_w[DPPO_NET_ACTOR_FT]; const ActorDerived& d = h->ad[DPPO_NET_ACTOR_FT];
+    const size_t sm = (size_t)(g.T * g.td * 3) * sizeof(float);
+    if (defer) {
+        // one launch for the eight independent small kernels between the grouped dW GEMM and AdamW
+        const size_t sm_staged = sm + (size_t)(g.T + g.td) * g.H * sizeof(float);
+        const bool staged = sm_staged <= 160 * 1024;
+        static bool attr_set = false;
+        if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(tc_ppo_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr_set = true; }
+        TcTailArgs a;
+        const int nthr = 512, wpb = nthr / 32;
+        const int nb[8] = {1, tc_nblk(g.A + 1, wpb), tc_nblk(2 * g.H, wpb), tc_nblk(2 * g.Hc, wpb), 1 + (g.H + 127) / 128,
+                           tc_nblk((size_t)(g.A + g.Do) * g.H, nthr), tc_nblk((size_t)g.Do * g.Hc, nthr), tc_nblk(g.Hc, nthr)};
+        a.first[0] = 0;
+        for (int r = 0; r < 8; ++r) a.first[r + 1] = a.first[r] + nb[r];
+        a.bsum = P.bsum; a.blocks_done = P.blocks_done; a.inv_nglobal = P.hp.inv_nglobal; a.frac_local = (float)((double)P.N / (double)P.N_global); a.metrics = gr + nA + nC;
+        a.colb3 = P.colb3; a.ncol3 = g.A + 1; a.b3a = gr + g.ao.b3; a.split3 = g.A; a.b3c = gr + nA + g.co.b3;
+        const int rows = P.nchunks * h->sm_count;
+        a.cpa = P.cpa; a.rows_a = rows; a.HA = g.H; a.b2a = gr + g.ao.b2; a.b1a = gr + g.ao.b1;
+        a.cpc = P.cpc; a.rows_c = rows; a.HC = g.Hc; a.b2c = gr + nA + g.co.b2; a.b1c = gr + nA + g.co.b1;
+        a.w = w; a.ao = g.ao; a.A = g.A; a.td = g.td; a.T = g.T; a.Do = g.Do; a.tb_staged = staged ? 1 : 0;
+        a.Gt = P.dw0a + (size_t)(g.A + g.Do) * g.H; a.sinemb = d.sinemb; a.thpre = d.thpre; a.temb = d.temb; a.gr = gr;
+        a.dw0a = P.dw0a; a.gwin_a = gr + g.ao.win; a.dw0c_obs = P.dw0c + (size_t)g.A * g.Hc; a.gwin_c = gr + nA + g.co.win;
+        a.dw0c_bias = P.dw0c + (size_t)(g.A + g.Do + g.T) * g.Hc; a.gbin_c = gr + nA + g.co.bin;
+        tc_ppo_tail_kernel<<<a.first[8], nthr, staged ? sm_staged : sm, s>>>(a); TC_KCHECK(h);
+        return 0;
+    }
     ppo_metrics_kernel<<<1, 256, 0, s>>>(P.bsum, P.blocks_done, P.hp.inv_nglobal, (float)((double)P.N / (double)P.N_global), gr + nA + nC); TC_KCHECK(h);
     // output-layer bias gradients = column sums of the seeds (per-block partials from the loss kernel)
     tc_reduce_cols_kernel<<<tc_nblk(g.A + 1, 8), 256, 0, s>>>(P.colb3, P.blocks_done, (size_t)(g.A + 1), g.A + 1, gr + g.ao.b3, g.A, gr + nA + g.co.b3); TC_KCHECK(h);
-    if (defer) {
-        const int rows = P.nchunks * h->sm_count;
-        tc_reduce_cols_kernel<<<tc_nblk(2 * g.H, 8), 256, 0, s>>>(P.cpa, rows, (size_t)2 * g.H, 2 * g.H, gr + g.ao.b2, g.H, gr + g.ao.b1); TC_KCHECK(h);
-        tc_reduce_cols_kernel<<<tc_nblk(2 * g.Hc, 8), 256, 0, s>>>(P.cpc, rows, (size_t)2 * g.Hc, 2 * g.Hc, gr + nA + g.co.b2, g.Hc, gr + nA + g.co.b1); TC_KCHECK(h);
-    }
     // actor: dw0 rows [A+Do, A+Do+T) are the per-t column sums of du = the gradient of the bt table
-    const float* w = h->net_w[DPPO_NET_ACTOR_FT]; const ActorDerived& d = h->ad[DPPO_NET_ACTOR_FT];
-    const size_t sm = (size_t)(g.T * g.td * 3) * sizeof(float);
     time_backward_kernel<<<1 + (g.H + 127) / 128, 512, sm, s>>>(w, g.ao, g.A, g.td, g.H, g.T, P.dw0a + (size_t)(g.A + g.Do) * g.H, d.sinemb, d.thpre, d.temb, gr);
     TC_KCHECK(h);
     unpack_dw0_kernel<<<tc_nblk((size_t)(g.A + g.Do) * g.H, 256), 256, 0, s>>>(P.dw0a, g.A, g.td, g.Do, g.H, gr + g.ao.win); TC_KCHECK(h);
