@@ -328,7 +328,7 @@ def run_ours(args):
     e.profile_enable(False)
     tensor = prec == L.PREC_BF16
     step_ms = ms_dev / args.steps
-    names = ["fc::chain_kernel<512> (fused tcgen05 actor forward / backward chains, CTA pairs)", "tc::dw_group_kernel (tcgen05 grouped split-K weight gradients)",
+    names = ["fc::chain_kernel<512> (fused tcgen05 actor forward / backward chains, CTA pairs)", "tcp::dw_pair_kernel (tcgen05 grouped split-K weight gradients on CTA pairs)",
              "sgemm_kernel (fp32 FFMA layers + gradients)", "fc::chain_kernel<256> (fused tcgen05 Mish critic forward / backward chains)"]
     dom = max(range(4), key=lambda c: cls[c][0])
     d_ms, d_n, d_fl = cls[dom]

@@ -249,6 +249,7 @@ extern "C" int dppo_create(const dppo_cfg* cfg, int device, dppo_handle** out) {
     h->cfg = *cfg; h->device = device; h->g = g; h->sm_count = prop.multiProcessorCount;
     { const char* dv = getenv("DPPO_DETERMINISTIC"); h->deterministic = (dv && dv[0] == '1') ? 1 : 0; }
     { const char* cv = getenv("DPPO_CHAIN_CG"); h->chain_cg = (cv && cv[0] == '1') ? 1 : 2; }
+    { const char* pv = getenv("DPPO_DW_PAIR"); h->dw_pair = (pv && pv[0] == '0') ? 0 : 1; }
     const size_t nA = g.ao.n, nC = g.co.n;
     const size_t total = 3 * nA + nC;
     CUDA_TRY(cudaMalloc(&h->params, total * sizeof(float)));

@@ -24,6 +24,7 @@
 #include "simt_kernels.cuh"
 #include "tc_gemm.cuh"
 #include "fused_chain.cuh"
+#include "tc_dw_pair.cuh"
 
 typedef __nv_bfloat16 bf16;
 
@@ -679,6 +680,15 @@ static void tc_mlp_dw_descs(const TcMlp& m, const bf16* doutb, int N, float* gne
     d[3] = tc::GroupDesc{m.h0, KP0, m.dv, H, dw0, KP0, H, H, 0.0};                    // residual path: not algorithmic work
     d[4] = tc::GroupDesc{m.v, H, doutb, 64, gnet + ow3, H, m.NO, m.NO, 2.0 * r * H * m.NO};
 }
+// the same five products for the CTA-pair kernel: the narrow layer-0 products are handed over as du^T h0 / dv^T h0 (transposed output)
+static void tc_mlp_dw_pair_descs(const TcMlp& m, const bf16* doutb, int N, float* gnet, size_t ow1, size_t ow2, size_t ow3, float* dw0, tcp::PairDesc* d) {
+    const int H = m.H, KP0 = m.KP0; const double r = (double)N;
+    d[0] = tcp::PairDesc{m.a1, H, m.dv, H, gnet + ow2, H, H, H, 0, 2.0 * r * H * H};
+    d[1] = tcp::PairDesc{m.a0, H, m.dh1, H, gnet + ow1, H, H, H, 0, 2.0 * r * H * H};
+    d[2] = tcp::PairDesc{m.du, H, m.h0, KP0, dw0, H, KP0, H, 1, 2.0 * r * m.din * H};
+    d[3] = tcp::PairDesc{m.dv, H, m.h0, KP0, dw0, H, KP0, H, 1, 0.0};                 // residual path: not algorithmic work
+    d[4] = tcp::PairDesc{m.v, H, doutb, 64, gnet + ow3, H, m.NO, m.NO, 0, 2.0 * r * H * m.NO};
+}
 // backward of the residual MLP from doutb [N][64] (bf16, zero padded).  Writes gradients of W1,b1,W2,b2,W3 into gnet
 // at the given offsets and dW0 (in h0 row order) into dw0 [KP0][H].
 static int tc_mlp_backward(dppo_handle* h, cudaStream_t s, const TcMlp& m, const bf16* doutb, int N, float* part,
@@ -688,6 +698,11 @@ static int tc_mlp_backward(dppo_handle* h, cudaStream_t s, const TcMlp& m, const
         // one launch: dv, dh1 and the non-residual part of du; the residual path joins in dW0 = h0^T du + h0^T dv
         DPPO_TRY(tc_mlp_backward_dx(h, s, m, doutb, N, part, gnet, ob1, ob2));
         if (!h->deterministic) {   // all five weight-gradient products in one grouped launch
+            if (h->dw_pair) {
+                tcp::PairDesc pd[5];
+                tc_mlp_dw_pair_descs(m, doutb, N, gnet, ow1, ow2, ow3, dw0, pd);
+                if (tcp::pair_ok(h, pd, 5)) return tcp::launch_group_pair(h, s, pd, 5, N);
+            }
             tc::GroupDesc d[5];
             tc_mlp_dw_descs(m, doutb, N, gnet, ow1, ow2, ow3, dw0, d);
             return tc::launch_group(h, s, d, 5, N);
@@ -914,6 +929,12 @@ static int tc_ppo_chunk(dppo_handle* h, cudaStream_t s, int chunk, const float* 
         // both backward chains, then ONE grouped launch with the ten weight-gradient products of actor and critic
         DPPO_TRY(tc_mlp_backward_dx(h, s, P.ma, P.depsb, n, P.part, h->grads, g.ao.b1, g.ao.b2));
         DPPO_TRY(tc_mlp_backward_dx(h, s, P.mc, P.dvalb, n, P.part, h->grads + nA, g.co.b1, g.co.b2));
+        if (h->dw_pair) {
+            tcp::PairDesc pd[10];
+            tc_mlp_dw_pair_descs(P.ma, P.depsb, n, h->grads, g.ao.w1, g.ao.w2, g.ao.w3, P.dw0a, pd);
+            tc_mlp_dw_pair_descs(P.mc, P.dvalb, n, h->grads + nA, g.co.w1, g.co.w2, g.co.w3, P.dw0c, pd + 5);
+            if (tcp::pair_ok(h, pd, 10)) return tcp::launch_group_pair(h, s, pd, 10, n);
+        }
         tc::GroupDesc d[10];
         tc_mlp_dw_descs(P.ma, P.depsb, n, h->grads, g.ao.w1, g.ao.w2, g.ao.w3, P.dw0a, d);
         tc_mlp_dw_descs(P.mc, P.dvalb, n, h->grads + nA, g.co.w1, g.co.w2, g.co.w3, P.dw0c, d + 5);
