@@ -205,6 +205,14 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
           "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
         :: "memory");
 }
+__device__ __forceinline__ void tmem_ld8_async(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait8(uint32_t (&r)[8]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+        : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]) :: "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -548,6 +556,39 @@ __global__ void __launch_bounds__(FTHREADS, 1) chain_kernel(const __grid_constan
                             }
                             constexpr int nch = 4;                         // 32-column chunks per warp and phase
                             const int c_first = hph * 8 + half * nch;
+                            if (mish) {
+                                // Mish layers (critic forward): a ROLLED loop over groups of 8 columns.  The unrolled 4 x 32-column
+                                // body below is ~45 KB of SASS per phase for this mode and the epilogue warps spent 2.4 x as many
+                                // cycles waiting for instruction fetch as issuing (ncu source page); this body stays cache resident.
+                                const uint32_t t0 = tmem_base + lane_base + (uint32_t)(c_first * 32);
+                                const uint32_t row_off = (uint32_t)rloc * 128u, sw = (uint32_t)(rloc & 7);
+                                const bool gstore = L.gate_store_map >= 0, hasb = L.bias != nullptr;
+                                auto group8 = [&](const uint32_t (&r)[8], const int col0) {
+                                    float v[8], gt[8];
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
+                                    if (hasb) {
+                                        const float4 b0 = *reinterpret_cast<const float4*>(sb + col0), b1 = *reinterpret_cast<const float4*>(sb + col0 + 4);
+                                        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+                                    }
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) { float y; mish_and_grad(v[j], y, gt[j]); v[j] = y; }
+                                    const uint32_t off = (uint32_t)(col0 >> 6) * 16384u + row_off + (((uint32_t)((col0 & 63) >> 3) ^ sw) << 4);
+                                    if (gstore) st_shared_v4(g_addr + off, pack_bf16(gt[0], gt[1]), pack_bf16(gt[2], gt[3]), pack_bf16(gt[4], gt[5]), pack_bf16(gt[6], gt[7]));
+                                    st_shared_v4(x_addr + off, pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                                };
+                                uint32_t ra8[8], rb8[8];
+                                tmem_ld8_async(t0, ra8);
+#pragma unroll 1
+                                for (int g2 = 0; g2 < nch * 4; g2 += 2) {
+                                    tmem_ld_wait8(ra8);
+                                    tmem_ld8_async(t0 + (uint32_t)((g2 + 1) * 8), rb8);
+                                    group8(ra8, c_first * 32 + g2 * 8);
+                                    tmem_ld_wait8(rb8);
+                                    if (g2 + 2 < nch * 4) tmem_ld8_async(t0 + (uint32_t)((g2 + 2) * 8), ra8);
+                                    group8(rb8, c_first * 32 + (g2 + 1) * 8);
+                                }
+                            } else {
                             uint32_t mo[4] = {0u, 0u, 0u, 0u};
                             uint4 mi4 = make_uint4(0u, 0u, 0u, 0u);
                             uint32_t ra[32], rb[32];
@@ -582,18 +623,6 @@ __global__ void __launch_bounds__(FTHREADS, 1) chain_kernel(const __grid_constan
                                 }
                                 const uint32_t toff = (uint32_t)(n0 >> 6) * 16384u + (uint32_t)rloc * 128u;
                                 const int cbg = (n0 & 63) >> 3;
-                                if (mish) {
-                                    // post-activation -> X (below), gate = mish'(pre) -> G; eight columns at a time keeps the live set small
-#pragma unroll
-                                    for (int q = 0; q < 4; ++q) {
-                                        float gt[8];
-#pragma unroll
-                                        for (int j = 0; j < 8; ++j) { float y; mish_and_grad(v[q * 8 + j], y, gt[j]); v[q * 8 + j] = y; }
-                                        if (L.gate_store_map >= 0)
-                                            st_shared_v4(g_addr + toff + (uint32_t)(((cbg + q) ^ (rloc & 7)) << 4),
-                                                         pack_bf16(gt[0], gt[1]), pack_bf16(gt[2], gt[3]), pack_bf16(gt[4], gt[5]), pack_bf16(gt[6], gt[7]));
-                                    }
-                                }
                                 if (gate_in) {
 #pragma unroll
                                     for (int q = 0; q < 4; ++q) {
@@ -619,6 +648,7 @@ __global__ void __launch_bounds__(FTHREADS, 1) chain_kernel(const __grid_constan
                                     st_shared_v4(x_addr + toff + (uint32_t)(((cbg + q) ^ (rloc & 7)) << 4),
                                                  pack_bf16(v[q * 8 + 0], v[q * 8 + 1]), pack_bf16(v[q * 8 + 2], v[q * 8 + 3]),
                                                  pack_bf16(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16(v[q * 8 + 6], v[q * 8 + 7]));
+                            }
                             }
                             tcgen05_fence_before();
                             fence_async_smem();
