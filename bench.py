@@ -321,6 +321,8 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel, timed live with CUDA events inside the library (every tensor-class launch is
     #      bracketed on its launching stream; classes: 0 fused tcgen05 layer chain, 1 tcgen05 GEMM (dW), 2 FFMA SGEMM)
+    #      While the profile is on the library runs the actor and critic chains back to back (in the timed region above the critic
+    #      chain runs on a second stream and fills the idle SMs of the actor chain's last wave), so each duration is that kernel alone.
     e.profile_enable(True)
     for i in range(args.steps):
         flush.zero_(); dev_step(i)
@@ -352,7 +354,7 @@ def run_ours(args):
                                    "classes": {names[c].split(" ")[0]: {"ms_per_step": cls[c][0] / args.steps, "launches_per_step": cls[c][1] // args.steps,
                                                                         "tflops": cls[c][2] / (cls[c][0] * 1e-3) / 1e12 if cls[c][0] > 0 else 0.0}
                                                for c in range(4) if cls[c][1] > 0}},
-            "note": None if tensor else "fp32 parity mode runs on CUDA cores: FFMA peak is ~74.5 TFLOP/s (148 SM x 128 x 2 x 1.965 GHz); frac is still quoted against the bf16 tensor peak"}
+            "note": "per-kernel durations are timed with the actor and critic chains serialized; in the timed region of `value` the critic chain overlaps the actor chain's last wave on a second stream, so shares are relative to the serialized sum" if tensor else "fp32 parity mode runs on CUDA cores: FFMA peak is ~74.5 TFLOP/s (148 SM x 128 x 2 x 1.965 GHz); frac is still quoted against the bf16 tensor peak"}
 
     # ---- sampling half of the metric: walker2d, 40 env copies, T=20 chain, in-kernel Philox
     obs40 = torch.rand(N_ENVS, d.Do, device=dev) * 2 - 1

@@ -250,6 +250,7 @@ extern "C" int dppo_create(const dppo_cfg* cfg, int device, dppo_handle** out) {
     { const char* dv = getenv("DPPO_DETERMINISTIC"); h->deterministic = (dv && dv[0] == '1') ? 1 : 0; }
     { const char* cv = getenv("DPPO_CHAIN_CG"); h->chain_cg = (cv && cv[0] == '1') ? 1 : 2; }
     { const char* pv = getenv("DPPO_DW_PAIR"); h->dw_pair = (pv && pv[0] == '0') ? 0 : 1; }
+    { const char* ov = getenv("DPPO_OVERLAP_CHAINS"); h->overlap_chains = (ov && ov[0] == '0') ? 0 : 1; }
     const size_t nA = g.ao.n, nC = g.co.n;
     const size_t total = 3 * nA + nC;
     CUDA_TRY(cudaMalloc(&h->params, total * sizeof(float)));
@@ -310,6 +311,7 @@ extern "C" void dppo_destroy(dppo_handle* h) {
     for (int net = 0; net < 4; ++net) { ActorDerived& d = h->ad[net]; cudaFree(d.sinemb); cudaFree(d.thpre); cudaFree(d.temb); cudaFree(d.bt); cudaFree(d.w0p); }
     if (h->ws.base) cudaFree(h->ws.base);
     if (h->copy_stream) { cudaStreamDestroy(h->copy_stream); for (int i = 0; i < 9; ++i) cudaEventDestroy(h->copy_ev[i]); }
+    if (h->aux_stream) { cudaStreamDestroy(h->aux_stream); for (int i = 0; i < 2; ++i) cudaEventDestroy(h->aux_ev[i]); }
     if (h->pin) cudaFreeHost(h->pin);
     if (h->dstage) cudaFree(h->dstage);
     delete h;

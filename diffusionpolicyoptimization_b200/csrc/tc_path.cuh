@@ -919,16 +919,30 @@ static int tc_ppo_chunk(dppo_handle* h, cudaStream_t s, int chunk, const float* 
     P.mc.cpart = defer ? P.cpc + (size_t)chunk * h->sm_count * 2 * g.Hc : nullptr;
     // h0 straight from (prev, obs, K-1-inds): tconst = -(K) flags "t = K-1-trow[r]"
     tc_pack_h0_kernel<<<tc_nblk((size_t)n * (KP0 / 8), 256), 256, 0, s>>>(prev, obs, inds, -g.K, n, g.A, g.Do, g.T, KP0, 1, P.h0); TC_KCHECK(h);
+    // The actor and the critic chains are independent persistent kernels whose last wave leaves a third of the SMs idle
+    // (391 row tiles on 148 SMs): the critic chain goes to a second stream so that its CTAs fill the actor chain's tail.
+    // (not while the per-kernel profile is on: its event brackets are meant to time each kernel running alone)
+    const bool overlap = defer && h->overlap_chains && !h->prof_on;
+    if (overlap && !h->aux_stream) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) CUDA_TRY(cudaEventCreateWithFlags(&h->aux_ev[i], cudaEventDisableTiming));
+    }
+    auto fork = [&]() -> int { CUDA_TRY(cudaEventRecord(h->aux_ev[0], s)); CUDA_TRY(cudaStreamWaitEvent(h->aux_stream, h->aux_ev[0], 0)); return 0; };
+    auto join = [&]() -> int { CUDA_TRY(cudaEventRecord(h->aux_ev[1], h->aux_stream)); CUDA_TRY(cudaStreamWaitEvent(s, h->aux_ev[1], 0)); return 0; };
+    if (overlap) DPPO_TRY(fork());
     DPPO_TRY(tc_mlp_forward(h, s, P.ma, n));
-    DPPO_TRY(tc_mlp_forward(h, s, P.mc, n));
+    DPPO_TRY(tc_mlp_forward(h, overlap ? h->aux_stream : s, P.mc, n));
+    if (overlap) DPPO_TRY(join());
     tc_ppo_loss_kernel<<<nlb, 128, 0, s>>>(prev, nxt, P.eps, inds, returns, oldvalues, advantages, oldlogp, P.val,
                                           h->scalars, h->sched, P.hp, n, P.depsb, P.dvalb, P.bsum + (size_t)P.blocks_done * 5,
                                           P.colb3 + (size_t)P.blocks_done * (g.A + 1)); TC_KCHECK(h);
     P.blocks_done += nlb;
     if (defer) {
         // both backward chains, then ONE grouped launch with the ten weight-gradient products of actor and critic
+        if (overlap) DPPO_TRY(fork());
         DPPO_TRY(tc_mlp_backward_dx(h, s, P.ma, P.depsb, n, P.part, h->grads, g.ao.b1, g.ao.b2));
-        DPPO_TRY(tc_mlp_backward_dx(h, s, P.mc, P.dvalb, n, P.part, h->grads + nA, g.co.b1, g.co.b2));
+        DPPO_TRY(tc_mlp_backward_dx(h, overlap ? h->aux_stream : s, P.mc, P.dvalb, n, P.part, h->grads + nA, g.co.b1, g.co.b2));
+        if (overlap) DPPO_TRY(join());
         if (h->dw_pair) {
             tcp::PairDesc pd[10];
             tc_mlp_dw_pair_descs(P.ma, P.depsb, n, h->grads, g.ao.w1, g.ao.w2, g.ao.w3, P.dw0a, pd);
