@@ -342,8 +342,8 @@ def run_ours(args):
             # (profiles/r01_final_chain_dw_ncu.txt): mean of the step's two chain_kernel<512> launches (actor forward 115 MB,
             # actor backward 112 MB); algorithmic HBM bytes of the same two: 171 / 160 MB (part of the stores is still in L2
             # when the kernel ends)
-            "traffic": 113.5e6 if tensor and dom == 0 else None,
-            "traffic_source": "profiles/r01_final_chain_dw_ncu.txt (static, from the committed ncu capture)" if tensor and dom == 0 else None,
+            "traffic": 111.9e6 if tensor and dom == 0 else None,
+            "traffic_source": "profiles/r01_chain_r1s_ncu.txt (static, from the committed ncu --set full capture: mean dram read+write of the step's two chain_kernel<512> launches)" if tensor and dom == 0 else None,
             "kernel": names[dom],
             "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({pk_src}); the kernel runs inside a long step",
             "avg_launch_us": d_ms / max(d_n, 1) * 1e3, "launches_timed": d_n,
