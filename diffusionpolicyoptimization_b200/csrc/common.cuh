@@ -165,6 +165,8 @@ struct dppo_handle {
     int64_t tc_launches = 0;
     int w0p_dirty[4] = {1, 1, 1, 1};  // ActorDerived::w0p is stale (rebuilt on demand by the FFMA layer-0 GEMM)
     int chain_cg = 2;                 // fused chain kernel: 2 = CTA pairs (tcgen05 cta_group::2), 1 = single CTAs (DPPO_CHAIN_CG=1)
+    int peer_two_shot = -1;           // DPPO_PEER_TWO_SHOT=0/1 (default: two-shot from 4 ranks)
+    float* peer_gsum[8] = {nullptr};
     int overlap_chains = 1;           // DPPO_OVERLAP_CHAINS=0: actor and critic chains back to back on one stream
     cudaStream_t aux_stream = nullptr; cudaEvent_t aux_ev[2] = {nullptr, nullptr};
     int dw_pair = 1;                  // DPPO_DW_PAIR=0: weight-gradient GEMM on single CTAs instead of CTA pairs

@@ -306,7 +306,7 @@ extern "C" void dppo_destroy(dppo_handle* h) {
             cudaIpcCloseMemHandle(h->peer_grads[0][p]); cudaIpcCloseMemHandle(h->peer_grads[1][p]); cudaIpcCloseMemHandle(h->peer_flags[p]);
         }
     }
-    cudaFree(h->params); cudaFree(h->sched); cudaFree(h->grads_buf[0]); cudaFree(h->grads_buf[1]); cudaFree(h->gsum); cudaFree(h->flags); cudaFree(h->scalars);
+    cudaFree(h->params); cudaFree(h->sched); cudaFree(h->grads_buf[0]); cudaFree(h->grads_buf[1]); /* gsum lives inside grads_buf[1] */ cudaFree(h->flags); cudaFree(h->scalars);
     for (int i = 0; i < 2; ++i) { cudaFree(h->opt[i].m); cudaFree(h->opt[i].v); }
     for (int net = 0; net < 4; ++net) { ActorDerived& d = h->ad[net]; cudaFree(d.sinemb); cudaFree(d.thpre); cudaFree(d.temb); cudaFree(d.bt); cudaFree(d.w0p); }
     if (h->ws.base) cudaFree(h->ws.base);
@@ -786,8 +786,10 @@ extern "C" int dppo_comm_ipc_export(dppo_handle* h, char* out) {
     ENTER(h);
     if (!out) DPPO_FAIL(-1, "dppo_comm_ipc_export: null");
     if (!h->grads_buf[1]) {
-        CUDA_TRY(cudaMalloc(&h->grads_buf[1], h->grads_floats * sizeof(float))); CUDA_TRY(cudaMemset(h->grads_buf[1], 0, h->grads_floats * sizeof(float)));
-        CUDA_TRY(cudaMalloc(&h->gsum, h->grads_floats * sizeof(float))); CUDA_TRY(cudaMemset(h->gsum, 0, h->grads_floats * sizeof(float)));
+        // one allocation [second gradient buffer | sum buffer]: the peers reach the sum buffer through the same IPC handle
+        const size_t gf4 = (h->grads_floats + 3) & ~(size_t)3;
+        CUDA_TRY(cudaMalloc(&h->grads_buf[1], 2 * gf4 * sizeof(float))); CUDA_TRY(cudaMemset(h->grads_buf[1], 0, 2 * gf4 * sizeof(float)));
+        h->gsum = h->grads_buf[1] + gf4;
         CUDA_TRY(cudaMalloc(&h->flags, 8 * sizeof(unsigned long long))); CUDA_TRY(cudaMemset(h->flags, 0, 8 * sizeof(unsigned long long)));
         CUDA_TRY(cudaDeviceSynchronize());
     }
@@ -804,7 +806,8 @@ extern "C" int dppo_comm_ipc_attach(dppo_handle* h, const char* all_blobs, int r
     if (!all_blobs || world < 2 || world > 8 || rank < 0 || rank >= world) DPPO_FAIL(-1, "dppo_comm_ipc_attach: bad arguments (world must be 2..8)");
     if (!h->grads_buf[1]) DPPO_FAIL(-1, "dppo_comm_ipc_attach: call dppo_comm_ipc_export first");
     for (int p = 0; p < world; ++p) {
-        if (p == rank) { h->peer_grads[0][p] = h->grads_buf[0]; h->peer_grads[1][p] = h->grads_buf[1]; h->peer_flags[p] = h->flags; continue; }
+        const size_t gf4 = (h->grads_floats + 3) & ~(size_t)3;
+        if (p == rank) { h->peer_grads[0][p] = h->grads_buf[0]; h->peer_grads[1][p] = h->grads_buf[1]; h->peer_gsum[p] = h->gsum; h->peer_flags[p] = h->flags; continue; }
         cudaIpcMemHandle_t hd[3]; memcpy(hd, all_blobs + (size_t)p * DPPO_IPC_BYTES, sizeof(hd));
         void* ptr[3];
         for (int k = 0; k < 3; ++k) {
@@ -812,8 +815,10 @@ extern "C" int dppo_comm_ipc_attach(dppo_handle* h, const char* all_blobs, int r
             if (e != cudaSuccess) DPPO_FAIL(-6, "cudaIpcOpenMemHandle(rank %d, buffer %d) failed: %s", p, k, cudaGetErrorString(e));
         }
         h->peer_grads[0][p] = (float*)ptr[0]; h->peer_grads[1][p] = (float*)ptr[1]; h->peer_flags[p] = (unsigned long long*)ptr[2];
+        h->peer_gsum[p] = (float*)ptr[1] + gf4;
     }
     h->rank = rank; h->world = world; h->peers_attached = 1;
+    if (h->peer_two_shot < 0) { const char* tv = getenv("DPPO_PEER_TWO_SHOT"); h->peer_two_shot = tv ? (tv[0] == '1') : (world >= 4); }
     return 0;
 }
 // fused peer-memory all-reduce + AdamW: flag barrier, then every rank sums all ranks' gradient buffers (same order everywhere)
@@ -828,8 +833,20 @@ static int peer_allreduce_adamw(dppo_handle* h, cudaStream_t s, int opt, float* 
     for (int p = 0; p < h->world; ++p) { pp.g[p] = h->peer_grads[h->grads_cur][p]; pp.flags[p] = h->peer_flags[p]; }
     h->epoch += 1;
     peer_barrier_kernel<<<1, 32, 0, s>>>(pp, h->flags, h->rank, h->world, h->epoch); KLAUNCH(h); KCHECK();
-    peer_allreduce_adamw_kernel<<<2 * h->sm_count, 256, 0, s>>>(pp, h->world, h->gsum, w, o.m, o.v, n_param, n_total, lr, alpha, b1, b2, h->cfg.adam_eps, wd);
-    KLAUNCH(h); KCHECK();
+    if (h->peer_two_shot == 1) {
+        // reduce-scatter + broadcast of the sum over peer memory, second barrier, AdamW on the local copy of the sum
+        PeerSums ps; memset(&ps, 0, sizeof(ps));
+        for (int p = 0; p < h->world; ++p) ps.s[p] = h->peer_gsum[p];
+        const size_t n4 = (n_total + 3) / 4, per = (n4 + h->world - 1) / h->world;
+        int grid = (int)((per + 255) / 256); if (grid > 2 * h->sm_count) grid = 2 * h->sm_count; if (grid < 1) grid = 1;
+        peer_reduce_scatter_bcast_kernel<<<grid, 256, 0, s>>>(pp, ps, h->rank, h->world, n4); KLAUNCH(h); KCHECK();
+        h->epoch += 1;
+        peer_barrier_kernel<<<1, 32, 0, s>>>(pp, h->flags, h->rank, h->world, h->epoch); KLAUNCH(h); KCHECK();
+        adamw_kernel<<<nblk(n_param, 256), 256, 0, s>>>(w, h->gsum, o.m, o.v, n_param, lr, alpha, b1, b2, h->cfg.adam_eps, wd); KLAUNCH(h); KCHECK();
+    } else {
+        peer_allreduce_adamw_kernel<<<2 * h->sm_count, 256, 0, s>>>(pp, h->world, h->gsum, w, o.m, o.v, n_param, n_total, lr, alpha, b1, b2, h->cfg.adam_eps, wd);
+        KLAUNCH(h); KCHECK();
+    }
     h->grads_cur ^= 1; h->grads = h->grads_buf[h->grads_cur];        // the next step accumulates into the other buffer
     return 0;
 }

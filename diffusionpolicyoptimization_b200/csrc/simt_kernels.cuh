@@ -836,6 +836,18 @@ __global__ void __launch_bounds__(256) peer_allreduce_adamw_kernel(PeerPtrs pp, 
         if (vec) reinterpret_cast<float4*>(g_sum)[i] = make_float4(s[0], s[1], s[2], s[3]); else g_sum[e0] = s[0];
     }
 }
+// Two-shot variant for larger worlds: after the first flag barrier rank r sums ONLY its 1/world slice of every rank's gradient
+// buffer (fixed order) and stores the result into the sum buffer of every rank (world-1 remote stores); a second flag barrier,
+// then plain AdamW on the local copy of the sum.  Per rank n floats are read and n written over NVLink instead of world * n read.
+struct PeerSums { float* s[8]; };
+__global__ void __launch_bounds__(256) peer_reduce_scatter_bcast_kernel(PeerPtrs pp, PeerSums ps, int rank, int world, size_t n4) {
+    const size_t per = (n4 + (size_t)world - 1) / (size_t)world, lo = (size_t)rank * per, hi = lo + per < n4 ? lo + per : n4;
+    for (size_t i = lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (size_t)gridDim.x * blockDim.x) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int p = 0; p < world; ++p) { const float4 x = __ldcv(reinterpret_cast<const float4*>(pp.g[p]) + i); a.x += x.x; a.y += x.y; a.z += x.z; a.w += x.w; }
+        for (int q = 0; q < world; ++q) reinterpret_cast<float4*>(ps.s[q])[i] = a;
+    }
+}
 __global__ void ema_kernel(float* __restrict__ ema, const float* __restrict__ w, size_t n, float decay) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) ema[i] = ema[i] * decay + w[i] * (1.f - decay);

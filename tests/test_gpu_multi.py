@@ -1,5 +1,5 @@
 """GPU (-m gpu), needs >= 2 B200s on the box (skipped otherwise): the data-parallel update.  Two ranks take three PPO steps
-on their own shards through (a) the fused peer-memory all-reduce + AdamW kernel and (b) ncclAllReduce + AdamW; the
+on their own shards through (a) the fused peer-memory all-reduce + AdamW kernel (one-shot and two-shot) and (b) ncclAllReduce + AdamW; the
 replicas must stay identical across ranks, and (a) must equal (b) (two summands: fp32 addition is commutative)."""
 import os
 import sys
@@ -28,11 +28,12 @@ def _worker(rank, world, port, out):
     lo, hi = shard_range(N, rank, world)
     mean, std = advantage_stats(batch[6].numpy())
     results = {}
-    for mode in ("peer", "nccl"):
+    for mode in ("peer", "peer2", "nccl"):       # one-shot, two-shot (reduce-scatter + broadcast of the sum), ncclAllReduce
         os.environ["DPPO_NO_PEER_ALLREDUCE"] = "1" if mode == "nccl" else "0"
+        os.environ["DPPO_PEER_TWO_SHOT"] = "1" if mode == "peer2" else "0"
         e = make_engine(o, precision=L.PREC_BF16, device=rank)
         e.init_comm()
-        assert getattr(e, "peer_allreduce", False) == (mode == "peer")
+        assert getattr(e, "peer_allreduce", False) == (mode != "nccl")
         for step in range(3):
             m = e.ppo_step(batch[0][lo:hi].reshape(hi - lo, -1), batch[1][lo:hi].reshape(hi - lo, -1), batch[2][lo:hi].reshape(hi - lo, -1),
                            batch[3][lo:hi], batch[4][lo:hi], batch[5][lo:hi], batch[6][lo:hi], batch[7][lo:hi].reshape(hi - lo, -1),
@@ -41,11 +42,14 @@ def _worker(rank, world, port, out):
         results[mode] = (np.concatenate([e.get_weights(L.NET_ACTOR_FT), e.get_weights(L.NET_CRITIC)]), m.cpu().numpy())
         dist.barrier()
         e.close()
-    w_all = [None] * world
-    dist.all_gather_object(w_all, results["peer"][0].tobytes())
+    ident = True
+    for mode in ("peer", "peer2"):
+        w_all = [None] * world
+        dist.all_gather_object(w_all, results[mode][0].tobytes())
+        ident = ident and all(b == w_all[0] for b in w_all)
     if rank == 0:
-        out["replicas_identical"] = all(b == w_all[0] for b in w_all)
-        out["peer_vs_nccl_max_abs"] = float(np.abs(results["peer"][0] - results["nccl"][0]).max())
+        out["replicas_identical"] = ident
+        out["peer_vs_nccl_max_abs"] = max(float(np.abs(results[m_][0] - results["nccl"][0]).max()) for m_ in ("peer", "peer2"))
         out["metrics_peer"] = results["peer"][1]; out["metrics_nccl"] = results["nccl"][1]
     dist.destroy_process_group()
 
