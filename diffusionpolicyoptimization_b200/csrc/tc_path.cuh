@@ -894,8 +894,20 @@ static int tc_ppo_begin(dppo_handle* h, cudaStream_t s, int N, int chunk_rows, i
 }
 // advantage statistics for the whole minibatch (diffusion_ppo.py:74-75): given, or computed from the device array
 static int tc_ppo_adv_stats(dppo_handle* h, cudaStream_t s, const float* advantages_all, int N, float adv_mean, float adv_std) {
-    if (adv_std < 0.f) { adv_stats_kernel<<<1, 1024, 0, s>>>(advantages_all, N, h->scalars); TC_KCHECK(h); }
-    else { set_scalars_kernel<<<1, 1, 0, s>>>(h->scalars, adv_mean, adv_std); TC_KCHECK(h); }
+    // only the loss kernel reads the statistics: with the two-stream schedule they are computed on the second stream, next to
+    // pack_h0 and the forward chains (the join in front of the loss kernel orders them)
+    TcPpoPlan& P = tc_plan(h);
+    cudaStream_t st = s;
+    if (P.ma.fused && P.mc.fused && !h->deterministic && h->overlap_chains && !h->prof_on) {
+        if (!h->aux_stream) {
+            CUDA_TRY(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
+            for (int i = 0; i < 2; ++i) CUDA_TRY(cudaEventCreateWithFlags(&h->aux_ev[i], cudaEventDisableTiming));
+        }
+        CUDA_TRY(cudaEventRecord(h->aux_ev[0], s)); CUDA_TRY(cudaStreamWaitEvent(h->aux_stream, h->aux_ev[0], 0));
+        st = h->aux_stream;
+    }
+    if (adv_std < 0.f) { adv_stats_kernel<<<1, 1024, 0, st>>>(advantages_all, N, h->scalars); TC_KCHECK(h); }
+    else { set_scalars_kernel<<<1, 1, 0, st>>>(h->scalars, adv_mean, adv_std); TC_KCHECK(h); }
     return 0;
 }
 // chunk size of the host pipeline: whole waves of 128-row tiles (one tile per SM), at most ~4 chunks; 0 = do not chunk
