@@ -336,6 +336,115 @@ __global__ void __launch_bounds__(128) tc_ppo_loss_kernel(
     }
 }
 
+// The same loss with EIGHT lanes per row (A % 4 == 0, A <= 32): lane `sub` of a row owns elements [4 sub, 4 sub + 4) and reads them
+// as one float4 per input array (coalesced; the thread-per-row kernel above walks 96-byte strides and leaves the SMs at ~10 warps).
+// 32 rows per 256-thread block.  Row scalars are computed redundantly by the row's lanes after a 3-step shuffle reduction.
+constexpr int LOSS8_ROWS = 32;
+__global__ void __launch_bounds__(256) tc_ppo_loss8_kernel(
+    const float* __restrict__ prev, const float* __restrict__ nxt, const float* __restrict__ eps,
+    const int* __restrict__ inds, const float* __restrict__ returns, const float* __restrict__ oldvalues,
+    const float* __restrict__ advantages, const float* __restrict__ oldlogp, const float* __restrict__ newvalues,
+    const float* __restrict__ advstats, const float* __restrict__ sch, PpoHyper hp, int N,
+    bf16* __restrict__ depsb, bf16* __restrict__ dvalb, double* __restrict__ block_sums, float* __restrict__ col_part /*[blocks][A+1]*/) {
+    const int tid = threadIdx.x, sub = tid & 7, lane = tid & 31, wrp = tid >> 5;
+    const int r = blockIdx.x * LOSS8_ROWS + (tid >> 3);
+    const int A = hp.A, a0 = sub * 4;
+    const bool row_ok = r < N;
+    const int nuse = min(hp.reward_horizon, A / hp.Da) * hp.Da;   // newlogprobs[:, :reward_horizon, :]
+    float z[4] = {0.f, 0.f, 0.f, 0.f}, gq[4] = {0.f, 0.f, 0.f, 0.f};
+    float newp = 0.f, oldp = 0.f, dv_out = 0.f, sd = 1.f;
+    uint32_t live = 0u;
+    double acc[5] = {0, 0, 0, 0, 0};
+    int ind = 0;
+    StepConst sc = {};
+    if (row_ok) {
+        ind = inds[r];
+        sc = step_const(sch, hp.T, hp.K - 1 - ind);
+        sd = logprob_std(sc, hp.min_lp_std);
+        if (a0 < A) {
+            const float lgs = 0.91893853320467274f + logf(sd);
+            const size_t i0 = (size_t)r * A + a0;
+            const float4 pv = *reinterpret_cast<const float4*>(prev + i0), nx = *reinterpret_cast<const float4*>(nxt + i0);
+            const float4 ep = *reinterpret_cast<const float4*>(eps + i0), ol = *reinterpret_cast<const float4*>(oldlogp + i0);
+            const float pvv[4] = {pv.x, pv.y, pv.z, pv.w}, nxv[4] = {nx.x, nx.y, nx.z, nx.w};
+            const float epv[4] = {ep.x, ep.y, ep.z, ep.w}, olv[4] = {ol.x, ol.y, ol.z, ol.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                if (a0 + e < nuse) {
+                    float zz; bool in;
+                    const float lp = logprob_elem_c(pvv[e], epv[e], nxv[e], sc, sd, lgs, hp.dcv, &zz, &in);
+                    newp += fminf(fmaxf(lp, hp.lp_lo), hp.lp_hi);
+                    oldp += fminf(fmaxf(olv[e], hp.lp_lo), hp.lp_hi);
+                    z[e] = zz;
+                    if (lp >= hp.lp_lo && lp <= hp.lp_hi && in) live |= 1u << e;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int off = 1; off < 8; off <<= 1) { newp += __shfl_xor_sync(0xffffffffu, newp, off); oldp += __shfl_xor_sync(0xffffffffu, oldp, off); }
+    if (row_ok) {
+        const float newm = newp / (float)nuse, oldm = oldp / (float)nuse;
+        float adv = advantages[r];
+        if (hp.norm_adv) adv = (adv - advstats[0]) / (advstats[1] + 1e-8f);
+        adv *= powf(hp.gamma_d, (float)(hp.K - ind - 1));
+        const float logratio = newm - oldm, ratio = expf(logratio);
+        const float tt = hp.K > 1 ? (float)ind / (float)(hp.K - 1) : (float)ind;
+        const float clipc = hp.K > 1 ? hp.clip_base + (hp.clip_coef - hp.clip_base) * (expf(hp.clip_rate * tt) - 1.f) / (expf(hp.clip_rate) - 1.f) : tt;
+        const float rc = fminf(fmaxf(ratio, 1.f - clipc), 1.f + clipc);
+        const float pg1 = -adv * ratio, pg2 = -adv * rc;
+        const float pg = fmaxf(pg1, pg2);
+        const float dpg = (pg1 >= pg2) ? -adv : ((ratio >= 1.f - clipc && ratio <= 1.f + clipc) ? -adv : 0.f);
+        const float gscale = dpg * ratio * hp.inv_nglobal / (float)nuse / sd * sc.c1 * (-sc.srm1);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) gq[e] = ((live >> e) & 1u) ? gscale * z[e] : 0.f;
+        // padded bf16 seed row [deps (A) | 0..]: this lane's 4 columns and 4 of the zero columns
+        uint2* drow = reinterpret_cast<uint2*>(depsb + (size_t)r * 64);
+        drow[sub] = make_uint2(fc::pack_bf16(gq[0], gq[1]), fc::pack_bf16(gq[2], gq[3]));
+        drow[8 + sub] = make_uint2(0u, 0u);
+        if (sub == 0) {
+            const float v = newvalues[r], ret = returns[r];
+            float vl, dv;
+            if (hp.clip_v >= 0.f) {
+                const float ov = oldvalues[r];
+                const float un = (v - ret) * (v - ret);
+                const float dcl = v - ov;
+                const float vc = ov + fminf(fmaxf(dcl, -hp.clip_v), hp.clip_v);
+                const float cl = (vc - ret) * (vc - ret);
+                if (un >= cl) { vl = 0.5f * un; dv = (v - ret); }
+                else { vl = 0.5f * cl; dv = (dcl >= -hp.clip_v && dcl <= hp.clip_v) ? (vc - ret) : 0.f; }
+            } else { vl = 0.5f * (v - ret) * (v - ret); dv = (v - ret); }
+            dv_out = hp.vf_coef * dv * hp.inv_nglobal;
+            acc[0] = pg; acc[1] = vl; acc[2] = (fabsf(ratio - 1.f) > clipc) ? 1.0 : 0.0;
+            acc[3] = (ratio - 1.f) - logratio; acc[4] = ratio;
+        }
+        // padded bf16 seed row [dvalue | 0..]: 16 bytes per lane
+        uint4* vrow = reinterpret_cast<uint4*>(dvalb + (size_t)r * 64);
+        vrow[sub] = sub == 0 ? make_uint4(fc::pack_bf16(dv_out, 0.f), 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    // ---- block reductions: rows of a warp (lanes differing in bits 3,4), then the 8 warps through shared memory
+    __shared__ double red[5][8];
+    __shared__ float cred[8][33];
+#pragma unroll
+    for (int off = 8; off < 32; off <<= 1) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], off);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) gq[e] += __shfl_xor_sync(0xffffffffu, gq[e], off);
+        dv_out += __shfl_xor_sync(0xffffffffu, dv_out, off);
+    }
+    if (lane == 0) { for (int k = 0; k < 5; ++k) red[k][wrp] = acc[k]; cred[wrp][32] = dv_out; }
+    if (lane < 8) { for (int e = 0; e < 4; ++e) cred[wrp][lane * 4 + e] = gq[e]; }
+    __syncthreads();
+    if (tid < 5) { double t = 0; for (int w = 0; w < 8; ++w) t += red[tid][w]; block_sums[(size_t)blockIdx.x * 5 + tid] = t; }
+    if (tid <= A) {
+        const int a = tid < A ? tid : 32;
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += cred[w][a];
+        col_part[(size_t)blockIdx.x * (A + 1) + tid] = t;
+    }
+}
+
 // ------------------------------------------------------------------ state
 static int tc_init(dppo_handle* h) {
     const Geom& g = h->g;
@@ -856,7 +965,7 @@ static int tc_ppo_begin(dppo_handle* h, cudaStream_t s, int N, int chunk_rows, i
     P.N = N; P.nchunks = nchunks; P.N_global = N_global; P.blocks_done = 0;
     P.chunk_rows = chunk_rows;
     const int NC = P.chunk_rows < N ? P.chunk_rows : N;
-    P.max_blocks = tc_nblk(N, 128) + nchunks;
+    P.max_blocks = tc_nblk(N, LOSS8_ROWS) + nchunks;
     const bool amish = h->cfg.actor_act == DPPO_ACT_MISH, cmish = h->cfg.critic_act == DPPO_ACT_MISH;
     const size_t pf = tc_part_floats(h, g.H);
     const size_t n_cpa = (size_t)nchunks * h->sm_count * 2 * g.H, n_cpc = (size_t)nchunks * h->sm_count * 2 * g.Hc;
@@ -924,7 +1033,8 @@ static int tc_ppo_chunk(dppo_handle* h, cudaStream_t s, int chunk, const float* 
     const size_t nA = g.ao.n;
     TcPpoPlan& P = tc_plan(h);
     if (n < 1 || n > P.chunk_rows || chunk < 0 || chunk >= P.nchunks) DPPO_FAIL(-1, "tc_ppo_chunk: bad chunk");
-    const int nlb = tc_nblk(n, 128);
+    const bool loss8 = (g.A % 4 == 0) && g.A <= 32 && ((((uintptr_t)prev | (uintptr_t)nxt | (uintptr_t)oldlogp) & 15) == 0);   // float4 row reads
+    const int nlb = loss8 ? tc_nblk(n, LOSS8_ROWS) : tc_nblk(n, 128);
     if (P.blocks_done + nlb > P.max_blocks) DPPO_FAIL(-1, "tc_ppo_chunk: partial-sum buffers exhausted");
     const bool defer = P.ma.fused && P.mc.fused && !h->deterministic;
     P.ma.cpart = defer ? P.cpa + (size_t)chunk * h->sm_count * 2 * g.H : nullptr;
@@ -945,9 +1055,15 @@ static int tc_ppo_chunk(dppo_handle* h, cudaStream_t s, int chunk, const float* 
     DPPO_TRY(tc_mlp_forward(h, s, P.ma, n));
     DPPO_TRY(tc_mlp_forward(h, overlap ? h->aux_stream : s, P.mc, n));
     if (overlap) DPPO_TRY(join());
-    tc_ppo_loss_kernel<<<nlb, 128, 0, s>>>(prev, nxt, P.eps, inds, returns, oldvalues, advantages, oldlogp, P.val,
-                                          h->scalars, h->sched, P.hp, n, P.depsb, P.dvalb, P.bsum + (size_t)P.blocks_done * 5,
-                                          P.colb3 + (size_t)P.blocks_done * (g.A + 1)); TC_KCHECK(h);
+    if (loss8)
+        tc_ppo_loss8_kernel<<<nlb, 256, 0, s>>>(prev, nxt, P.eps, inds, returns, oldvalues, advantages, oldlogp, P.val,
+                                               h->scalars, h->sched, P.hp, n, P.depsb, P.dvalb, P.bsum + (size_t)P.blocks_done * 5,
+                                               P.colb3 + (size_t)P.blocks_done * (g.A + 1));
+    else
+        tc_ppo_loss_kernel<<<nlb, 128, 0, s>>>(prev, nxt, P.eps, inds, returns, oldvalues, advantages, oldlogp, P.val,
+                                              h->scalars, h->sched, P.hp, n, P.depsb, P.dvalb, P.bsum + (size_t)P.blocks_done * 5,
+                                              P.colb3 + (size_t)P.blocks_done * (g.A + 1));
+    TC_KCHECK(h);
     P.blocks_done += nlb;
     if (defer) {
         // both backward chains, then ONE grouped launch with the ten weight-gradient products of actor and critic
