@@ -5,7 +5,7 @@ operands (activations and weight copies) are rounded to bf16 (2^-9 relative), pr
 and accumulated in fp32 in TMEM, epilogues / losses / optimizer run in fp32 on fp32 master weights.
   eps (actor forward), value ........ 2e-2 norm-wise relative
   per-step log-probs ................ 0.15 absolute (the 1/sigma^2 <= 100 factor amplifies eps error)
-  PPO / pre-train gradients ......... 8e-2 of the largest gradient entry; losses 5e-2 relative
+  PPO / pre-train gradients ......... 0.15 of the largest gradient entry in general; on this file's fixed batches 8e-2 is asserted; losses 5e-2 relative
   sampled actions (20-step chain) ... 0.1 norm-wise relative
 The tests also assert that the tensor path (not the FFMA path) produced the numbers.
 """
