@@ -589,6 +589,8 @@ __global__ void __launch_bounds__(FTHREADS, 1) chain_kernel(const __grid_constan
                                     group8(rb8, c_first * 32 + (g2 + 1) * 8);
                                 }
                             } else {
+                            if constexpr (H == 512) {
+                            // H = 512 keeps the fully unrolled chunk loop: rolling it costs register spills there and measured slower
                             uint32_t mo[4] = {0u, 0u, 0u, 0u};
                             uint4 mi4 = make_uint4(0u, 0u, 0u, 0u);
                             uint32_t ra[32], rb[32];
@@ -648,6 +650,75 @@ __global__ void __launch_bounds__(FTHREADS, 1) chain_kernel(const __grid_constan
                                     st_shared_v4(x_addr + toff + (uint32_t)(((cbg + q) ^ (rloc & 7)) << 4),
                                                  pack_bf16(v[q * 8 + 0], v[q * 8 + 1]), pack_bf16(v[q * 8 + 2], v[q * 8 + 3]),
                                                  pack_bf16(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16(v[q * 8 + 6], v[q * 8 + 7]));
+                            }
+                            } else {
+                            uint32_t ra[32], rb[32];
+                            tmem_ld32_async(tmem_base + lane_base + (uint32_t)(c_first * 32), ra);
+                            // one 32-column chunk: TMEM registers -> (+bias, ReLU (+mask out), x gate, x mask in) -> bf16 -> X
+                            auto chunk = [&](const uint32_t (&r)[32], const int c, const bool first_of_pair, const uint32_t mask_in_bits, uint32_t& mask_out_bits) {
+                                const int n0 = c * 32;
+                                float v[32];
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                                if (L.bias) {
+#pragma unroll
+                                    for (int j = 0; j < 32; j += 4) {
+                                        const float4 b4 = *reinterpret_cast<const float4*>(sb + n0 + j);
+                                        v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+                                    }
+                                }
+                                if (L.act == 1) {
+                                    if (mout_row) {
+                                        uint32_t bits = 0u;
+#pragma unroll
+                                        for (int j = 0; j < 32; ++j) bits |= (v[j] > 0.f ? 1u : 0u) << j;
+                                        mask_out_bits = bits;
+                                    }
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                                }
+                                const uint32_t toff = (uint32_t)(n0 >> 6) * 16384u + (uint32_t)rloc * 128u;
+                                const int cbg = (n0 & 63) >> 3;
+                                if (gate_in) {
+#pragma unroll
+                                    for (int q = 0; q < 4; ++q) {
+                                        uint32_t gw[4];
+                                        ld_shared_v4(g_addr + toff + (uint32_t)(((cbg + q) ^ (rloc & 7)) << 4), gw[0], gw[1], gw[2], gw[3]);
+#pragma unroll
+                                        for (int e = 0; e < 4; ++e) {
+                                            const float2 gf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gw[e]));
+                                            v[q * 8 + e * 2] *= gf.x; v[q * 8 + e * 2 + 1] *= gf.y;
+                                        }
+                                    }
+                                }
+                                if (min_row) {
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j) v[j] = ((mask_in_bits >> j) & 1u) ? v[j] : 0.f;
+                                }
+                                // first phase of a two-phase layer: the second n-half's MMAs must be done with X tile c/2
+                                if (two_half && hph == 0 && first_of_pair) mbar_wait(&xfree[c >> 1], xf_phase);
+#pragma unroll
+                                for (int q = 0; q < 4; ++q)
+                                    st_shared_v4(x_addr + toff + (uint32_t)(((cbg + q) ^ (rloc & 7)) << 4),
+                                                 pack_bf16(v[q * 8 + 0], v[q * 8 + 1]), pack_bf16(v[q * 8 + 2], v[q * 8 + 3]),
+                                                 pack_bf16(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16(v[q * 8 + 6], v[q * 8 + 7]));
+                            };
+                            // ROLLED over chunk pairs (the two TMEM register buffers alternate inside one iteration): half the SASS of the
+                            // 4 x unrolled form - the epilogue warps were stalling on instruction fetch more often than they issued
+                            auto chunk_pair = [&](const int up) {
+                                const int c = c_first + up;
+                                uint2 mi2 = make_uint2(0u, 0u), mo2 = make_uint2(0u, 0u);
+                                if (min_row && valid) mi2 = *reinterpret_cast<const uint2*>(min_row + c);
+                                tmem_ld_wait(ra);
+                                tmem_ld32_async(tmem_base + lane_base + (uint32_t)((c + 1) * 32), rb);
+                                chunk(ra, c, true, mi2.x, mo2.x);
+                                tmem_ld_wait(rb);
+                                if (up + 2 < nch) tmem_ld32_async(tmem_base + lane_base + (uint32_t)((c + 2) * 32), ra);
+                                chunk(rb, c + 1, false, mi2.y, mo2.y);
+                                if (mout_row && L.act == 1 && valid) *reinterpret_cast<uint2*>(mout_row + c) = mo2;
+                            };
+#pragma unroll 1
+                            for (int up = 0; up < nch; up += 2) chunk_pair(up);
                             }
                             }
                             tcgen05_fence_before();
