@@ -276,6 +276,14 @@ def run_ours(args):
     launches = e.launch_count() - l0 - 0
     launches_per_step = launches // (args.steps + args.warmup)
     ms_e2e = timed(e2e_step, args.steps, max(3, args.warmup // 2))
+    # the same host buffers copied to the device with nothing else running: the host-link floor of `e2e` on this box
+    h2d_dst = [torch.empty_like(t, device=dev) for t in pinned[0]]
+
+    def h2d_only(i):
+        for hb, db in zip(pinned[i & 1], h2d_dst):
+            db.copy_(hb, non_blocking=True)
+    ms_h2d = timed(h2d_only, args.steps, 2)
+    del h2d_dst
     # ---- e2e through the index-driven entry point (the reference's own data flow, :266-312): the rollout
     #      of an iteration (P = 500 steps x 40 envs chains, old log-probs, returns/values/advantages) is uploaded from pinned
     #      host memory once per 20 minibatch updates (update_epochs 5 x 4 minibatches) and stays resident; every step copies
@@ -458,7 +466,9 @@ def run_ours(args):
                        "flops_per_sample": fps},
             "clocks": clocks,
             "e2e": {"value": n_global * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 32,
-                    "ms_per_step": ms_e2e / args.steps, "api": "Engine.ppo_step_host -> dppo_ppo_step_host (pinned host buffers)"},
+                    "ms_per_step": ms_e2e / args.steps, "api": "Engine.ppo_step_host -> dppo_ppo_step_host (pinned host buffers)",
+                    "h2d_alone_ms_per_step": ms_h2d / args.steps,
+                    "h2d_alone_gbps": h2d / (ms_h2d / args.steps * 1e-3) / 1e9},
             "e2e_indexed": {"value": n_global * idx_steps / (ms_e2e_idx * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e_idx / idx_steps,
                             "steps": idx_steps, "h2d_bytes_per_step": N_ROWS * 4 + roll_bytes * ((idx_steps + UPLOAD_EVERY - 1) // UPLOAD_EVERY) / idx_steps,
                             "d2h_bytes_per_step": 32,

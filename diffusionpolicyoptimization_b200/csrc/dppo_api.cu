@@ -967,7 +967,10 @@ extern "C" int dppo_ppo_step_host(dppo_handle* h, const float* obs, const float*
     int* d_inds = (int*)p; p += b_n; float* d_ret = (float*)p; p += b_n; float* d_val = (float*)p; p += b_n; float* d_adv = (float*)p; p += b_n;
     float* d_met = (float*)p;
     // tensor mode: chunked pipeline - the H2D copy of chunk c+1 (copy stream) overlaps the compute of chunk c
-    const int chunk_rows = (tc_eligible(h, N) && fc_ok(h) && fc_critic_ok(h) && !h->deterministic) ? tc_ppo_pipeline_chunk_rows(h, N) : 0;
+    int chunk_rows = (tc_eligible(h, N) && fc_ok(h) && fc_critic_ok(h) && !h->deterministic) ? tc_ppo_pipeline_chunk_rows(h, N) : 0;
+    static int env_chunk = -2, env_lead = -2;          // dev knobs: DPPO_HOST_CHUNK_ROWS (0 = no pipeline), DPPO_HOST_LEAD_ROWS
+    if (env_chunk == -2) { const char* v = getenv("DPPO_HOST_CHUNK_ROWS"); env_chunk = v ? atoi(v) : -1; const char* l = getenv("DPPO_HOST_LEAD_ROWS"); env_lead = l ? atoi(l) : -1; }
+    if (chunk_rows > 0 && env_chunk >= 0) chunk_rows = env_chunk >= N ? 0 : env_chunk;
     if (chunk_rows > 0) {
         if (!obs || !prev || !nxt || !inds || !returns || !oldvalues || !advantages || !oldlogp || N_global < N) DPPO_FAIL(-1, "dppo_ppo_step_host: bad arguments");
         if (adv_std < 0.f && N_global != N) DPPO_FAIL(-1, "dppo_ppo_step_host: global advantage statistics are required when rows are sharded");
@@ -979,13 +982,18 @@ extern "C" int dppo_ppo_step_host(dppo_handle* h, const float* obs, const float*
         // staging is free: the previous *_host call synchronised `s`; the copy stream must still not overtake work queued on s
         CUDA_TRY(cudaEventRecord(h->copy_ev[8], s));
         CUDA_TRY(cudaStreamWaitEvent(cs, h->copy_ev[8], 0));
-        DPPO_TRY(tc_ppo_begin(h, s, N, chunk_rows, N_global));
+        // a short first chunk (a third of a wave-sized one) gets the GPU going while the bulk of the minibatch is still on the link
+        const int lead = env_lead >= 0 ? (env_lead & ~127) : (((chunk_rows / 3) + 127) & ~127);
+        DPPO_TRY(tc_ppo_begin(h, s, N, chunk_rows, N_global, lead));
         const int CR = tc_plan(h).chunk_rows, nchunks = tc_plan(h).nchunks;
         if (nchunks > 8) DPPO_FAIL(-7, "dppo_ppo_step_host: too many pipeline chunks");
+        size_t cr0[8], cn[8];
+        { size_t r = 0; for (int c = 0; c < nchunks; ++c) { size_t want = (c == 0 && tc_plan(h).lead_rows > 0) ? (size_t)tc_plan(h).lead_rows : (size_t)CR;
+                                                            cr0[c] = r; cn[c] = r >= (size_t)N ? 0 : ((size_t)N - r < want ? (size_t)N - r : want); r += cn[c]; } }
         CUDA_TRY(cudaMemcpyAsync(d_adv, advantages, (size_t)N * 4, cudaMemcpyHostToDevice, cs));
         for (int c = 0; c < nchunks; ++c) {
-            const size_t r0 = (size_t)c * CR; if (r0 >= (size_t)N) break;
-            const size_t n = (size_t)N - r0 < (size_t)CR ? (size_t)N - r0 : (size_t)CR;
+            const size_t r0 = cr0[c]; if (cn[c] == 0) break;
+            const size_t n = cn[c];
             CUDA_TRY(cudaMemcpyAsync(d_obs + r0 * g.Do, obs + r0 * g.Do, n * g.Do * 4, cudaMemcpyHostToDevice, cs));
             CUDA_TRY(cudaMemcpyAsync(d_prev + r0 * g.A, prev + r0 * g.A, n * g.A * 4, cudaMemcpyHostToDevice, cs));
             CUDA_TRY(cudaMemcpyAsync(d_next + r0 * g.A, nxt + r0 * g.A, n * g.A * 4, cudaMemcpyHostToDevice, cs));
@@ -996,8 +1004,8 @@ extern "C" int dppo_ppo_step_host(dppo_handle* h, const float* obs, const float*
             CUDA_TRY(cudaEventRecord(h->copy_ev[c], cs));
         }
         for (int c = 0; c < nchunks; ++c) {
-            const size_t r0 = (size_t)c * CR; if (r0 >= (size_t)N) break;
-            const int n = (int)((size_t)N - r0 < (size_t)CR ? (size_t)N - r0 : (size_t)CR);
+            const size_t r0 = cr0[c]; if (cn[c] == 0) break;
+            const int n = (int)cn[c];
             CUDA_TRY(cudaStreamWaitEvent(s, h->copy_ev[c], 0));
             if (c == 0) DPPO_TRY(tc_ppo_adv_stats(h, s, d_adv, N, adv_mean, adv_std));     // the advantages were copied first
             DPPO_TRY(tc_ppo_chunk(h, s, c, d_obs + r0 * g.Do, d_prev + r0 * g.A, d_next + r0 * g.A, d_inds + r0, d_ret + r0, d_val + r0,

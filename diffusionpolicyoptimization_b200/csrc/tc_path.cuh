@@ -678,6 +678,17 @@ struct TcMlp {
     int fused, net, din;                   // fused: runs on the fused layer-chain kernel; din: un-padded input width
     float* cpart;                          // fused backward: where the per-CTA bias column sums go ([sm][2][H]); null = reduce at once
 };
+// the same MLP program on rows [r0, ...) of its per-row buffers
+static TcMlp tc_mlp_at(const TcMlp& m, size_t r0) {
+    TcMlp o = m;
+    const size_t e = r0 * (size_t)m.H;
+    if (o.h0) o.h0 += r0 * (size_t)m.KP0;
+    if (o.a0) o.a0 += e; if (o.a1) o.a1 += e; if (o.v) o.v += e; if (o.pre0) o.pre0 += e; if (o.pre1) o.pre1 += e;
+    if (o.dv) o.dv += e; if (o.dh1) o.dh1 += e; if (o.du) o.du += e;
+    if (o.out) o.out += r0 * (size_t)m.NO;
+    if (o.m0) o.m0 += r0 * (size_t)(m.H / 32); if (o.m1) o.m1 += r0 * (size_t)(m.H / 32);
+    return o;
+}
 static size_t tc_mlp_ws_bytes(int N, int H, bool mish, bool bwd) {
     size_t one = ws_bytes((size_t)N * H, sizeof(bf16));
     return one * (3 + (mish ? 2 : 0) + (bwd ? 3 : 0)) + 2 * ws_bytes((size_t)N * (H / 32), 4);
@@ -943,7 +954,8 @@ static int tc_critic_grads(dppo_handle* h, cudaStream_t s, const TcMlp& m, const
 // and metric sums as per-block partials reduced once in finish).  Leaves [actor_ft grads | critic grads | 8 metrics]
 // in h->grads.  The deterministic mode (fixed-order split-K reduction) supports a single chunk only.
 struct TcPpoPlan {
-    int N, nchunks, chunk_rows, blocks_done, max_blocks;
+    int N, nchunks, chunk_rows, lead_rows, blocks_done, max_blocks;
+    int full_rows, rows_done, dw_done, dw_flush_chunk;   // multi-chunk pipeline: per-row buffers hold ALL rows, dW runs in (at most) two launches
     int64_t N_global;
     float *part, *dw0a, *dw0c, *colb3, *cpa, *cpc;
     double* bsum;
@@ -955,16 +967,22 @@ static TcPpoPlan& tc_plan(dppo_handle* h) { if (!h->tc->plan) { h->tc->plan = ne
 static void tc_plan_free(dppo_handle* h) { if (h->tc && h->tc->plan) { delete h->tc->plan; h->tc->plan = nullptr; } }
 
 // chunk_rows <= 0 or >= N: one chunk
-static int tc_ppo_begin(dppo_handle* h, cudaStream_t s, int N, int chunk_rows, int64_t N_global) {
+// lead_rows > 0: the host pipeline starts with a shorter chunk of that many rows (its copy lands early), then chunk_rows-sized ones
+static int tc_ppo_begin(dppo_handle* h, cudaStream_t s, int N, int chunk_rows, int64_t N_global, int lead_rows = 0) {
     const Geom& g = h->g; const int KP0 = h->tc->KP0;
     const size_t nA = g.ao.n, nC = g.co.n;
     TcPpoPlan& P = tc_plan(h);
     if (h->deterministic || chunk_rows <= 0 || chunk_rows >= N) chunk_rows = N;
     chunk_rows = round_up(chunk_rows, 128);
-    const int nchunks = (N + chunk_rows - 1) / chunk_rows;
+    if (lead_rows <= 0 || lead_rows >= chunk_rows || chunk_rows >= N) lead_rows = 0;
+    const int nchunks = lead_rows ? 1 + (N - lead_rows + chunk_rows - 1) / chunk_rows : (N + chunk_rows - 1) / chunk_rows;
     P.N = N; P.nchunks = nchunks; P.N_global = N_global; P.blocks_done = 0;
-    P.chunk_rows = chunk_rows;
-    const int NC = P.chunk_rows < N ? P.chunk_rows : N;
+    P.chunk_rows = chunk_rows; P.lead_rows = lead_rows;
+    // More than one chunk (host pipeline): every per-row buffer holds all N rows and chunk c works on its own row range, so that
+    // the weight-gradient GEMMs need not run once per chunk (each launch pays a full set of output-tile reductions): one launch
+    // covers the chunks of the first half while the rest is still on the link, one covers the remainder.
+    P.full_rows = nchunks > 1 ? 1 : 0; P.rows_done = 0; P.dw_done = 0; P.dw_flush_chunk = nchunks / 2 - 1;
+    const int NC = P.full_rows ? N : (P.chunk_rows < N ? P.chunk_rows : N);
     P.max_blocks = tc_nblk(N, LOSS8_ROWS) + nchunks;
     const bool amish = h->cfg.actor_act == DPPO_ACT_MISH, cmish = h->cfg.critic_act == DPPO_ACT_MISH;
     const size_t pf = tc_part_floats(h, g.H);
@@ -1019,12 +1037,15 @@ static int tc_ppo_adv_stats(dppo_handle* h, cudaStream_t s, const float* advanta
     else { set_scalars_kernel<<<1, 1, 0, st>>>(h->scalars, adv_mean, adv_std); TC_KCHECK(h); }
     return 0;
 }
-// chunk size of the host pipeline: whole waves of 128-row tiles (one tile per SM), at most ~4 chunks; 0 = do not chunk
+// chunk size of the host pipeline: half waves of 128-row tiles (one tile per SM pair member), at most 7 chunks (+ the short lead
+// chunk); 0 = do not chunk.  Every chunk costs a start-up / drain of the four persistent chain kernels (~10 us each), so the
+// pipeline recovers only part of the copy time; half-wave chunks with the weight-gradient GEMMs deferred measured best.
 static int tc_ppo_pipeline_chunk_rows(const dppo_handle* h, int N) {
     const int wave = h->sm_count * 128;
     if (N < 2 * wave) return 0;
-    const int k = (N + 4 * wave - 1) / (4 * wave);
-    return k * wave;
+    int c = wave / 2;
+    while ((N + c - 1) / c > 7) c += wave / 2;
+    return c;
 }
 // rows [r0, r0 + n) of the minibatch; all pointers already point at row r0
 static int tc_ppo_chunk(dppo_handle* h, cudaStream_t s, int chunk, const float* obs, const float* prev, const float* nxt, const int32_t* inds,
@@ -1039,8 +1060,12 @@ static int tc_ppo_chunk(dppo_handle* h, cudaStream_t s, int chunk, const float* 
     const bool defer = P.ma.fused && P.mc.fused && !h->deterministic;
     P.ma.cpart = defer ? P.cpa + (size_t)chunk * h->sm_count * 2 * g.H : nullptr;
     P.mc.cpart = defer ? P.cpc + (size_t)chunk * h->sm_count * 2 * g.Hc : nullptr;
+    const size_t r0 = P.full_rows ? (size_t)P.rows_done : 0;          // this chunk's rows inside the per-row buffers
+    if (r0 + (size_t)n > (size_t)P.N) DPPO_FAIL(-1, "tc_ppo_chunk: more rows than planned");
+    const TcMlp ma = tc_mlp_at(P.ma, r0), mc = tc_mlp_at(P.mc, r0);
+    bf16* const depsb = P.depsb + r0 * 64; bf16* const dvalb = P.dvalb + r0 * 64;
     // h0 straight from (prev, obs, K-1-inds): tconst = -(K) flags "t = K-1-trow[r]"
-    tc_pack_h0_kernel<<<tc_nblk((size_t)n * (KP0 / 8), 256), 256, 0, s>>>(prev, obs, inds, -g.K, n, g.A, g.Do, g.T, KP0, 1, P.h0); TC_KCHECK(h);
+    tc_pack_h0_kernel<<<tc_nblk((size_t)n * (KP0 / 8), 256), 256, 0, s>>>(prev, obs, inds, -g.K, n, g.A, g.Do, g.T, KP0, 1, P.h0 + r0 * KP0); TC_KCHECK(h);
     // The actor and the critic chains are independent persistent kernels whose last wave leaves a third of the SMs idle
     // (391 row tiles on 148 SMs): the critic chain goes to a second stream so that its CTAs fill the actor chain's tail.
     // (not while the per-kernel profile is on: its event brackets are meant to time each kernel running alone)
@@ -1052,38 +1077,47 @@ static int tc_ppo_chunk(dppo_handle* h, cudaStream_t s, int chunk, const float* 
     auto fork = [&]() -> int { CUDA_TRY(cudaEventRecord(h->aux_ev[0], s)); CUDA_TRY(cudaStreamWaitEvent(h->aux_stream, h->aux_ev[0], 0)); return 0; };
     auto join = [&]() -> int { CUDA_TRY(cudaEventRecord(h->aux_ev[1], h->aux_stream)); CUDA_TRY(cudaStreamWaitEvent(s, h->aux_ev[1], 0)); return 0; };
     if (overlap) DPPO_TRY(fork());
-    DPPO_TRY(tc_mlp_forward(h, s, P.ma, n));
-    DPPO_TRY(tc_mlp_forward(h, overlap ? h->aux_stream : s, P.mc, n));
+    DPPO_TRY(tc_mlp_forward(h, s, ma, n));
+    DPPO_TRY(tc_mlp_forward(h, overlap ? h->aux_stream : s, mc, n));
     if (overlap) DPPO_TRY(join());
     if (loss8)
-        tc_ppo_loss8_kernel<<<nlb, 256, 0, s>>>(prev, nxt, P.eps, inds, returns, oldvalues, advantages, oldlogp, P.val,
-                                               h->scalars, h->sched, P.hp, n, P.depsb, P.dvalb, P.bsum + (size_t)P.blocks_done * 5,
+        tc_ppo_loss8_kernel<<<nlb, 256, 0, s>>>(prev, nxt, ma.out, inds, returns, oldvalues, advantages, oldlogp, mc.out,
+                                               h->scalars, h->sched, P.hp, n, depsb, dvalb, P.bsum + (size_t)P.blocks_done * 5,
                                                P.colb3 + (size_t)P.blocks_done * (g.A + 1));
     else
-        tc_ppo_loss_kernel<<<nlb, 128, 0, s>>>(prev, nxt, P.eps, inds, returns, oldvalues, advantages, oldlogp, P.val,
-                                              h->scalars, h->sched, P.hp, n, P.depsb, P.dvalb, P.bsum + (size_t)P.blocks_done * 5,
+        tc_ppo_loss_kernel<<<nlb, 128, 0, s>>>(prev, nxt, ma.out, inds, returns, oldvalues, advantages, oldlogp, mc.out,
+                                              h->scalars, h->sched, P.hp, n, depsb, dvalb, P.bsum + (size_t)P.blocks_done * 5,
                                               P.colb3 + (size_t)P.blocks_done * (g.A + 1));
     TC_KCHECK(h);
     P.blocks_done += nlb;
     if (defer) {
         // both backward chains, then ONE grouped launch with the ten weight-gradient products of actor and critic
         if (overlap) DPPO_TRY(fork());
-        DPPO_TRY(tc_mlp_backward_dx(h, s, P.ma, P.depsb, n, P.part, h->grads, g.ao.b1, g.ao.b2));
-        DPPO_TRY(tc_mlp_backward_dx(h, overlap ? h->aux_stream : s, P.mc, P.dvalb, n, P.part, h->grads + nA, g.co.b1, g.co.b2));
+        DPPO_TRY(tc_mlp_backward_dx(h, s, ma, depsb, n, P.part, h->grads, g.ao.b1, g.ao.b2));
+        DPPO_TRY(tc_mlp_backward_dx(h, overlap ? h->aux_stream : s, mc, dvalb, n, P.part, h->grads + nA, g.co.b1, g.co.b2));
         if (overlap) DPPO_TRY(join());
+        P.rows_done += n;
+        // weight gradients over the rows accumulated since the last launch: every chunk (single-chunk call), or at the flush chunk and the end
+        if (P.full_rows && chunk != P.dw_flush_chunk && P.rows_done < P.N) return 0;
+        const size_t d0 = P.full_rows ? (size_t)P.dw_done : r0;
+        const int dn = (int)((P.full_rows ? (size_t)P.rows_done : r0 + (size_t)n) - d0);
+        const TcMlp da = tc_mlp_at(P.ma, d0), dc = tc_mlp_at(P.mc, d0);
+        const bf16* const dd = P.depsb + d0 * 64; const bf16* const dvd = P.dvalb + d0 * 64;
+        P.dw_done = P.rows_done;
         if (h->dw_pair) {
             tcp::PairDesc pd[10];
-            tc_mlp_dw_pair_descs(P.ma, P.depsb, n, h->grads, g.ao.w1, g.ao.w2, g.ao.w3, P.dw0a, pd);
-            tc_mlp_dw_pair_descs(P.mc, P.dvalb, n, h->grads + nA, g.co.w1, g.co.w2, g.co.w3, P.dw0c, pd + 5);
-            if (tcp::pair_ok(h, pd, 10)) return tcp::launch_group_pair(h, s, pd, 10, n);
+            tc_mlp_dw_pair_descs(da, dd, dn, h->grads, g.ao.w1, g.ao.w2, g.ao.w3, P.dw0a, pd);
+            tc_mlp_dw_pair_descs(dc, dvd, dn, h->grads + nA, g.co.w1, g.co.w2, g.co.w3, P.dw0c, pd + 5);
+            if (tcp::pair_ok(h, pd, 10)) return tcp::launch_group_pair(h, s, pd, 10, dn);
         }
         tc::GroupDesc d[10];
-        tc_mlp_dw_descs(P.ma, P.depsb, n, h->grads, g.ao.w1, g.ao.w2, g.ao.w3, P.dw0a, d);
-        tc_mlp_dw_descs(P.mc, P.dvalb, n, h->grads + nA, g.co.w1, g.co.w2, g.co.w3, P.dw0c, d + 5);
-        return tc::launch_group(h, s, d, 10, n);
+        tc_mlp_dw_descs(da, dd, dn, h->grads, g.ao.w1, g.ao.w2, g.ao.w3, P.dw0a, d);
+        tc_mlp_dw_descs(dc, dvd, dn, h->grads + nA, g.co.w1, g.co.w2, g.co.w3, P.dw0c, d + 5);
+        return tc::launch_group(h, s, d, 10, dn);
     }
-    DPPO_TRY(tc_mlp_backward(h, s, P.ma, P.depsb, n, P.part, h->grads, g.ao.w1, g.ao.b1, g.ao.w2, g.ao.b2, g.ao.w3, P.dw0a));
-    DPPO_TRY(tc_mlp_backward(h, s, P.mc, P.dvalb, n, P.part, h->grads + nA, g.co.w1, g.co.b1, g.co.w2, g.co.b2, g.co.w3, P.dw0c));
+    DPPO_TRY(tc_mlp_backward(h, s, ma, depsb, n, P.part, h->grads, g.ao.w1, g.ao.b1, g.ao.w2, g.ao.b2, g.ao.w3, P.dw0a));
+    DPPO_TRY(tc_mlp_backward(h, s, mc, dvalb, n, P.part, h->grads + nA, g.co.w1, g.co.b1, g.co.w2, g.co.b2, g.co.w3, P.dw0c));
+    P.rows_done += n;
     return 0;
 }
 static int tc_ppo_finish(dppo_handle* h, cudaStream_t s) {
@@ -1133,9 +1167,18 @@ static int tc_ppo_finish(dppo_handle* h, cudaStream_t s) {
 static int tc_ppo_step(dppo_handle* h, cudaStream_t s, const float* obs, const float* prev, const float* nxt, const int32_t* inds,
                        const float* returns, const float* oldvalues, const float* advantages, const float* oldlogp,
                        int N, int64_t N_global, float adv_mean, float adv_std) {
-    DPPO_TRY(tc_ppo_begin(h, s, N, 0, N_global));
+    static int dev_chunk = -2;                       // dev knob DPPO_DEV_CHUNK_ROWS: chunk the device-resident call like the host pipeline does
+    if (dev_chunk == -2) { const char* v = getenv("DPPO_DEV_CHUNK_ROWS"); dev_chunk = v ? atoi(v) : 0; }
+    const Geom& g = h->g;
+    DPPO_TRY(tc_ppo_begin(h, s, N, dev_chunk > 0 ? dev_chunk : 0, N_global));
     DPPO_TRY(tc_ppo_adv_stats(h, s, advantages, N, adv_mean, adv_std));
-    DPPO_TRY(tc_ppo_chunk(h, s, 0, obs, prev, nxt, inds, returns, oldvalues, advantages, oldlogp, N));
+    const int CR = tc_plan(h).chunk_rows, nch = tc_plan(h).nchunks;
+    for (int c = 0; c < nch; ++c) {
+        const size_t r0 = (size_t)c * CR; if (r0 >= (size_t)N) break;
+        const int n = (int)((size_t)N - r0 < (size_t)CR ? (size_t)N - r0 : (size_t)CR);
+        DPPO_TRY(tc_ppo_chunk(h, s, c, obs + r0 * g.Do, prev + r0 * g.A, nxt + r0 * g.A, inds + r0, returns + r0, oldvalues + r0, advantages + r0,
+                              oldlogp + r0 * g.A, n));
+    }
     return tc_ppo_finish(h, s);
 }
 
