@@ -564,11 +564,13 @@ __global__ void gae_kernel(const double* __restrict__ rewards, const float* __re
     double last = 0.0;
     for (int t = S - 1; t >= 0; --t) {
         const size_t i = (size_t)t * E + e;
-        const double nextv = (t == S - 1) ? (double)next_values[e] : (double)values[i + E];
+        // gamma * nextvalues: at the last step nextvalues is the critic's fp32 output and NumPy multiplies a Python float into an fp32
+        // array IN fp32 (train_ppo_diffusion_agent.py:252,259); earlier steps read the float64 values_trajs holder
+        const double gnext = (t == S - 1) ? (double)__fmul_rn((float)gamma, next_values[e]) : __dmul_rn(gamma, (double)values[i + E]);
         const double nonterm = 1.0 - (double)terminated[i];
         const double v = (double)values[i];
         // delta = r * rsc + gamma * nextv * nonterm - v
-        const double delta = __dsub_rn(__dadd_rn(__dmul_rn(rewards[i], rsc), __dmul_rn(__dmul_rn(gamma, nextv), nonterm)), v);
+        const double delta = __dsub_rn(__dadd_rn(__dmul_rn(rewards[i], rsc), __dmul_rn(gnext, nonterm)), v);
         // last = delta + gamma * lam * nonterm * last
         last = __dadd_rn(delta, __dmul_rn(__dmul_rn(__dmul_rn(gamma, lam), nonterm), last));
         adv[i] = (float)last;

@@ -467,9 +467,11 @@ def gae(rewards: np.ndarray, terminated: np.ndarray, values: np.ndarray, next_va
     advantages = np.zeros_like(rewards)
     lastgaelam = 0
     for t in reversed(range(n_steps)):
-        nextvalues = np.asarray(next_values, np.float64).reshape(1, -1) if t == n_steps - 1 else values[t + 1]
+        # :252 the bootstrap value is the critic's fp32 output, and `self.gamma * nextvalues` (Python float x fp32 array) is an fp32
+        # product in NumPy; the other steps read the float64 holder `values_trajs` (pinned by tests/golden/ref_gae.npz)
+        gnext = (np.float32(gamma) * np.asarray(next_values, np.float32).reshape(1, -1)) if t == n_steps - 1 else gamma * values[t + 1]
         nonterminal = 1.0 - np.asarray(terminated[t], np.float64)
-        delta = rewards[t] * reward_scale_const + gamma * nextvalues * nonterminal - values[t]
+        delta = rewards[t] * reward_scale_const + gnext * nonterminal - values[t]
         lastgaelam = delta + gamma * gae_lambda * nonterminal * lastgaelam
         advantages[t] = lastgaelam
     return advantages, advantages + values

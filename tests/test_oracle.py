@@ -127,7 +127,8 @@ def test_gae_known_answer():
     v = np.array([[0.5, 0.5], [1.0, 1.0], [2.0, 0.0]], np.float32); nv = np.array([3.0, 1.0], np.float32)
     g, lam = 0.9, 0.5
     adv, ret = O.gae(r, term, v, nv, 1.0, g, lam)
-    d2 = np.array([0.0 + g * 3.0 - 2.0, 4.0 + g * 1.0 - 0.0]); a2 = d2
+    gnv = (np.float32(g) * nv).astype(np.float64)       # the bootstrap term is an fp32 product in the reference (Python float x fp32 array)
+    d2 = np.array([0.0 + gnv[0] - 2.0, 4.0 + gnv[1] - 0.0]); a2 = d2
     d1 = np.array([2.0 + g * 2.0 - 1.0, 0.5 + 0.0 - 1.0]); a1 = d1 + g * lam * np.array([1.0, 0.0]) * a2
     d0 = np.array([1.0 + g * 1.0 - 0.5, 1.0 + g * 1.0 - 0.5]); a0 = d0 + g * lam * a1
     np.testing.assert_allclose(adv, np.stack([a0, a1, a2]), rtol=1e-15)
