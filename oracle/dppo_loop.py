@@ -37,6 +37,16 @@ class RewardScaler:
         return np.clip(reward / np.sqrt(self.var + self.epsilon), -self.cliprew, self.cliprew)   # :68-73
 
 
+def gather_minibatch(obs_k, chains_k, logprobs_k, returns_k, values_k, advantages_k, inds_b, K):
+    """train_ppo_diffusion_agent.py:292-312: flat index -> (env-step row, denoising index) by row-major unravel over
+    (n_steps*n_envs, K); prev / next are chains[b, k] / chains[b, k+1].  Returns the argument tuple of PPODiffusion.c_loss.
+    (Pinned by tests/golden/ref_agent_blocks.npz, produced by the reference's own lines.)"""
+    inds_b = torch.as_tensor(inds_b).long()
+    bi, ki = inds_b // K, inds_b % K
+    return (obs_k[bi], chains_k[bi, ki], chains_k[bi, ki + 1], ki.to(torch.int32), returns_k[bi], values_k[bi],
+            advantages_k[bi], logprobs_k[bi, ki])
+
+
 def ppo_iteration(o: O.Oracle, opt: dict, venv, itr: int, prev_obs_venv, *, n_steps, act_steps, batch_size,
                   update_epochs, gamma, gae_lambda, target_kl, lr, reward_scaler, reward_scale_const, noise_fn,
                   shuffle_fn, firsts0, reward_horizon=None):
@@ -83,10 +93,8 @@ def ppo_iteration(o: O.Oracle, opt: dict, venv, itr: int, prev_obs_venv, *, n_st
     for epoch in range(update_epochs):                                              # :281-370
         inds_k = torch.as_tensor(np.asarray(shuffle_fn(itr, epoch, total_steps))).long()
         for b in range(num_batch):
-            inds_b = inds_k[b * batch_size: (b + 1) * batch_size]
-            bi, ki = inds_b // K, inds_b % K                                        # tf.unravel_index :293-296
-            batch = (obs_k[bi], chains_k[bi, ki], chains_k[bi, ki + 1], ki.to(torch.int32), returns_k[bi], values_k[bi],
-                     advantages_k[bi], logprobs_k[bi, ki])
+            batch = gather_minibatch(obs_k, chains_k, logprobs_k, returns_k, values_k, advantages_k,
+                                     inds_k[b * batch_size: (b + 1) * batch_size], K)
             metrics, ga, gc = o.ppo_grads(*batch, reward_horizon=reward_horizon)
             opt["step"] += 1
             params = o.actor_ft + o.critic

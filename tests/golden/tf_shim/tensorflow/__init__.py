@@ -147,6 +147,22 @@ def where(cond, x, y):
     return _torch.where(_t(cond), x, y)
 
 
+def unravel_index(indices, dims):
+    """tf.unravel_index: row-major; returns the coordinate arrays stacked on axis 0 (unpackable like a tuple)."""
+    idx = _t(indices).long()
+    out, rem = [], idx
+    for d in reversed(_dims(dims)):
+        out.append(rem % d)
+        rem = rem // d
+    return _torch.stack(out[::-1], dim=0)
+
+
+def gather_nd(params, indices):
+    """tf.gather_nd for index tensors [N, r]: params[i0, i1, ...] per row."""
+    idx = _t(indices).long()
+    return params[tuple(idx[:, j] for j in _b.range(idx.shape[1]))]
+
+
 # ---- math -----------------------------------------------------------------------------------------
 def sqrt(x):
     return _torch.sqrt(_t(x))
