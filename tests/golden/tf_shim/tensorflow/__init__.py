@@ -400,6 +400,8 @@ keras = _ns(
         elu=_no_fn("elu"), gelu=_no_fn("gelu"), softplus=_no_fn("softplus"),
     ),
     losses=_ns("tensorflow.keras.losses", MSE=lambda a, b: ((a - b) ** 2).mean(dim=-1)),
+    optimizers=_ns("tensorflow.keras.optimizers",
+                   schedules=_ns("tensorflow.keras.optimizers.schedules", LearningRateSchedule=type("LearningRateSchedule", (), {}))),
 )
 
 for _m in (math, random, keras, keras.layers, keras.activations, keras.losses):
