@@ -5,8 +5,9 @@ CPU restatement of ONE iteration of the reference's DPPO fine-tuning loop
 (agent/finetune/train_ppo_diffusion_agent.py:59-400) on top of oracle/dppo_oracle.py: NumPy float64 holders, per-step
 sampling, value / log-prob pass, running reward scaling (util/reward_scaling.py), the GAE scan, shuffled minibatches
 gathered with fancy indexing, PPO loss + gradients + Keras-3 AdamW, KL early stop.  The Gaussian draws and the
-permutations are injected so the CUDA agent can replay them.  Parity pin: see oracle/dppo_oracle.py's header; the loop
-itself lives inside `TrainPPODiffusionAgent.run` (needs Hydra, gym, TF) and is restated, not executed.
+permutations are injected so the CUDA agent can replay them.  Parity pin: tests/golden/ref_loop.npz - two iterations produced by
+the reference's own rollout / update blocks exec'd verbatim over the TF shim (tests/golden/make_ref_loop.py); this file is checked
+against it by tests/test_ref_golden.py.
 """
 import numpy as np
 import torch

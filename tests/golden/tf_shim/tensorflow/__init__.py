@@ -147,6 +147,39 @@ def where(cond, x, y):
     return _torch.where(_t(cond), x, y)
 
 
+def split(value, num_or_size_splits, axis=0):
+    """tf.split with an integer: that many equal parts (the reference always divides evenly)."""
+    n = int(num_or_size_splits)
+    assert value.shape[axis] % n == 0
+    return list(_torch.chunk(value, n, dim=axis))
+
+
+def clip_by_norm(t, clip_norm):
+    l2sum = (t * t).sum()
+    l2norm = _torch.sqrt(_torch.where(l2sum > 0, l2sum, _torch.ones_like(l2sum)))
+    return t * clip_norm / _torch.maximum(l2norm, _torch.tensor(float(clip_norm)))
+
+
+class GradientTape:
+    """tf.GradientTape over torch autograd.  The generator runs with autograd globally OFF (TF records nothing outside a tape);
+    entering a tape switches it on, `gradient` differentiates the scalar loss wrt the given variables."""
+
+    def __enter__(self):
+        self._prev = _torch.is_grad_enabled()
+        _torch.set_grad_enabled(True)
+        return self
+
+    def __exit__(self, *exc):
+        _torch.set_grad_enabled(self._prev)
+        return False
+
+    def watch(self, x):
+        pass
+
+    def gradient(self, target, sources):
+        return list(_torch.autograd.grad(target, list(sources), allow_unused=True))
+
+
 def unravel_index(indices, dims):
     """tf.unravel_index: row-major; returns the coordinate arrays stacked on axis 0 (unpackable like a tuple)."""
     idx = _t(indices).long()
@@ -241,6 +274,11 @@ class _Random(_types.ModuleType):
 
     def uniform(self, shape_, minval=0, maxval=None, dtype=float32):
         return self.source("uniform", _dims(shape_), minval=minval, maxval=maxval, dtype=dtype)
+
+    def shuffle(self, value):
+        """tf.random.shuffle along axis 0: the permutation comes from the injected source."""
+        perm = self.source("shuffle", [int(value.shape[0])])
+        return value[perm.long()]
 
 
 random = _Random("tensorflow.random")

@@ -148,3 +148,34 @@ def test_pretrain_loop_matches_the_reference_loop():
     got_e, want_e = model.engine.get_weights(L.NET_ACTOR_EMA), O.flatten_params(ema)
     assert np.mean(np.abs(got_e - want_e) > 0.25 * 1e-3) < 1e-2
     assert np.abs(got_e - got_w).max() > 1e-5                      # EMA really lags the model
+
+
+def test_two_iterations_match_the_reference_fixture():
+    """The CUDA agent against tests/golden/ref_loop.npz - two training iterations produced by the reference's own rollout and
+    update blocks, model classes and reward scaler (exec'd / imported verbatim over the TF shim, tests/golden/make_ref_loop.py),
+    on the same toy env with the same Gaussian draws and permutations."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_loop.npz"))
+    n_envs, n_steps, act, batch, epochs = (int(v) for v in z["cfg"]); lr = float(z["lr"][0])
+    o = O.make_oracle("hopper", seed=int(z["seed"][0]))
+    model = make_model(o)
+    agent = TrainPPODiffusionAgent(
+        model, ToyVecEnv(n_envs, 11, 3, seed=3), n_envs=n_envs, n_steps=n_steps, act_steps=act, n_train_itr=2, batch_size=batch,
+        update_epochs=epochs, gamma=0.99, gae_lambda=0.95, target_kl=1, actor_lr=lr, force_train=True, reset_at_iteration=False,
+        reward_scale_running=True,
+        noise_fn=lambda itr, s, B: (z[f"it{itr}_x_T"][s].reshape(B, -1), z[f"it{itr}_noise"][s].reshape(20, B, -1)),
+        shuffle_fn=lambda itr, ep, total: z[f"it{itr}_perms"][ep])
+    K = o.d.ft_denoising_steps
+    for itr in range(2):
+        k = f"it{itr}_"
+        got = agent.run_iteration()
+        assert rel_err(agent.chains_trajs.reshape(n_steps * n_envs, K + 1, -1), z[k + "chains"].reshape(n_steps * n_envs, K + 1, -1)) < 5e-4
+        assert got["n_updates"] == int(z[k + "n_updates"][0])
+        m = z[k + "metrics"]
+        for name, idx in (("pg_loss", 0), ("v_loss", 2), ("approx_kl", 4), ("ratio", 5)):
+            assert abs(got[name] - m[idx]) < 5e-3 * max(1.0, abs(m[idx])) + 2e-5, (itr, name, got[name], m[idx])
+        assert abs(got["clipfrac"] - float(z[k + "clipfrac_mean"][0])) < 0.03
+        assert abs(got["explained_var"] - float(z[k + "explained_var"][0])) < 5e-3
+        fp = np.concatenate([model.engine.get_weights(L.NET_ACTOR_FT), model.engine.get_weights(L.NET_CRITIC)])[::97]
+        assert np.mean(np.abs(fp - z[k + "weights_fp"]) > 0.25 * lr) < 1e-2
+    assert agent.opt_iterations == 12
