@@ -115,3 +115,32 @@ def ppo_iteration(o: O.Oracle, opt: dict, venv, itr: int, prev_obs_venv, *, n_st
                returns_k=y_true, values_k=y_pred, advantages_k=advantages_k.numpy(), reward_trajs=reward_trajs,
                chains_k=chains_k.numpy(), logprobs_k=logprobs_k.numpy())
     return out, prev_obs_venv, done_venv
+
+
+def pretrain_epochs(o: O.Oracle, actions, states, *, n_epochs, batch_size, lr_fn, weight_decay, ema_decay, epoch_start_ema,
+                    update_ema_freq, draws_fn):
+    """agent/pretrain/train_diffusion_agent.py:56-120 + train_agent.py:46-58,139-148: sequential batches (short tail kept), eps-MSE
+    loss with injected (t, eps) draws, Keras-3 AdamW under `lr_fn(iteration)`, EMA copy before `epoch_start_ema` and decay after.
+    Returns (per-epoch mean losses, network params, EMA params).  Pinned by tests/golden/ref_pretrain_loop.npz."""
+    net = [p.clone() for p in o.actor]
+    ema = [p.clone() for p in net]                                     # reset_parameters() in PreTrainAgent.__init__
+    m = [torch.zeros_like(p) for p in net]; v = [torch.zeros_like(p) for p in net]
+    it, losses = 0, []
+    M = actions.shape[0]
+    for epoch in range(1, n_epochs + 1):
+        ep = []
+        for nb, r0 in enumerate(range(0, M, batch_size)):
+            a = torch.as_tensor(actions[r0:r0 + batch_size]); s = torch.as_tensor(states[r0:r0 + batch_size])
+            t, eps = draws_fn(epoch, nb, a.shape[0])
+            oo = O.Oracle(o.d, o.h, net, o.actor_ft, o.critic)
+            loss, g = oo.pretrain_grads(a, s, torch.as_tensor(t).long(), torch.as_tensor(eps).reshape(a.shape))
+            O.adamw_keras(net, g, m, v, it + 1, lr_fn(it), o.h.beta1, o.h.beta2, o.h.adam_eps, weight_decay)
+            it += 1
+            ep.append(float(loss))
+        losses.append(float(np.mean(ep)))
+        if epoch % update_ema_freq == 0:
+            if epoch < epoch_start_ema:
+                ema = [p.clone() for p in net]
+            else:
+                O.ema_update(ema, net, ema_decay)
+    return losses, net, ema

@@ -179,3 +179,33 @@ def test_two_iterations_match_the_reference_fixture():
         fp = np.concatenate([model.engine.get_weights(L.NET_ACTOR_FT), model.engine.get_weights(L.NET_CRITIC)])[::97]
         assert np.mean(np.abs(fp - z[k + "weights_fp"]) > 0.25 * lr) < 1e-2
     assert agent.opt_iterations == 12
+
+
+def test_pretrain_loop_matches_the_reference_fixture():
+    """The CUDA pre-training loop against tests/golden/ref_pretrain_loop.npz (the reference's own run loop, EMA class and step_ema
+    exec'd verbatim over the shim): per-epoch losses, final network and EMA weights."""
+    import os
+    from diffusionpolicyoptimization_b200.agent.pretrain.train_diffusion_agent import TrainDiffusionAgent
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_pretrain_loop.npz"))
+    M, B, EPOCHS, FIRST, START, FREQ = (int(v) for v in z["cfg"]); lr0, alpha, wd, decay = (float(v) for v in z["hyper"])
+    o = O.make_oracle("hopper", seed=int(z["seed"][0]))
+    actor = dp.DiffusionMLP(action_dim=3, horizon_steps=4, cond_dim=11, time_dim=16, mlp_dims=[512, 512, 512],
+                            activation_type="ReLU", residual_style=True)
+
+    def hook(cfg):
+        cfg.pretrain_weight_decay = wd
+    model = dp.DiffusionModel(network=actor, horizon_steps=4, obs_dim=11, action_dim=3, denoising_steps=20, device="cuda:0",
+                              precision="fp32", _cfg_hook=hook)
+    model.network.set_flat_weights(O.flatten_params(o.actor))
+
+    def draws_fn(epoch, nb, n):
+        off = (epoch - 1) * M + nb * B
+        return z["t"][off:off + n], z["noise"][off:off + n]
+    agent = TrainDiffusionAgent(model, z["actions"], z["states"], n_epochs=EPOCHS, batch_size=B, learning_rate=lr0,
+                                lr_first_cycle_steps=FIRST, lr_min=alpha * lr0, ema_decay=decay, epoch_start_ema=START,
+                                update_ema_freq=FREQ, draws_fn=draws_fn)
+    losses = agent.run()
+    np.testing.assert_allclose(losses, z["losses"], rtol=2e-3)
+    assert agent.opt_iterations == int(z["opt_iterations"][0])
+    assert np.mean(np.abs(model.engine.get_weights(L.NET_ACTOR)[::97] - z["net_fp"]) > 0.25 * lr0) < 1e-2
+    assert np.mean(np.abs(model.engine.get_weights(L.NET_ACTOR_EMA)[::97] - z["ema_fp"]) > 0.25 * lr0) < 1e-2
