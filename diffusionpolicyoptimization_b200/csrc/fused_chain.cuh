@@ -865,7 +865,8 @@ static int chain_grid(const dppo_handle* h, int rows, int cg) {
 template <int H, int CG>
 static int launch_chain_t(dppo_handle* h, cudaStream_t s, const Maps& maps, const Params& p, double flops) {
     auto kern = p.dbg ? chain_kernel<H, true, CG> : chain_kernel<H, false, CG>;
-    static bool attr_set = false;
+    static bool attr_set_dev[64] = {};      // function attributes are per device
+    bool& attr_set = attr_set_dev[h->device & 63];
     if (!attr_set) {
         CUDA_TRY(cudaFuncSetAttribute(chain_kernel<H, true, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_smem_bytes<H>()));
         CUDA_TRY(cudaFuncSetAttribute(chain_kernel<H, false, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_smem_bytes<H>()));

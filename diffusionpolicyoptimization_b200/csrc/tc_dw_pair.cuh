@@ -224,7 +224,8 @@ static int launch_group_pair(dppo_handle* h, cudaStream_t s, const PairDesc* d, 
         flops += d[i].alg_flops;
     }
     gp.items = items;
-    static bool attr_set = false;
+    static bool attr_set_dev[64] = {};      // function attributes are per device
+    bool& attr_set = attr_set_dev[h->device & 63];
     if (!attr_set) {
         CUDA_TRY(cudaFuncSetAttribute(dw_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair_smem_bytes()));
         attr_set = true;

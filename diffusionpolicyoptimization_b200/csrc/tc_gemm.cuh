@@ -422,7 +422,8 @@ static int launch_t(dppo_handle* h, cudaStream_t s, const Gemm& g) {
     p.splits = (p.kblocks + p.kb_per_split - 1) / p.kb_per_split;
     p.epi = g.epi;
     auto kern = gemm_kernel<BN, A_MN, B_MN>;
-    static bool attr_set = false;
+    static bool attr_set_dev[64] = {};      // function attributes are per device
+    bool& attr_set = attr_set_dev[h->device & 63];
     if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<BN>())); attr_set = true; }
     const int tiles = p.m_blocks * p.n_blocks * p.splits;
     const int grid = tiles < h->sm_count ? tiles : h->sm_count;
@@ -630,7 +631,8 @@ static int launch_group(dppo_handle* h, cudaStream_t s, const GroupDesc* d, int 
     }
     gp.items = items;
     const size_t smem = (size_t)GSTAGES * (BM * GBK * 2 + 256 * GBK * 2) + 1024 + 256;
-    static bool attr_set = false;
+    static bool attr_set_dev[64] = {};      // function attributes are per device
+    bool& attr_set = attr_set_dev[h->device & 63];
     if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(dw_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
     const int grid = items < h->sm_count ? items : h->sm_count;
     prof_begin(h, s);

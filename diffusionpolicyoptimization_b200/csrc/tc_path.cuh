@@ -1132,7 +1132,8 @@ static int tc_ppo_finish(dppo_handle* h, cudaStream_t s) {
         // one launch for the eight independent small kernels between the grouped dW GEMM and AdamW
         const size_t sm_staged = sm + (size_t)(g.T + g.td) * g.H * sizeof(float);
         const bool staged = sm_staged <= 160 * 1024;
-        static bool attr_set = false;
+        static bool attr_set_dev[64] = {};      // function attributes are per device
+    bool& attr_set = attr_set_dev[h->device & 63];
         if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(tc_ppo_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr_set = true; }
         TcTailArgs a;
         const int nthr = 512, wpb = nthr / 32;
