@@ -1050,12 +1050,20 @@ static int ppo_indexed_impl(dppo_handle* h, cudaStream_t s, const float* obs_buf
     float* d_met = (float*)p; int* d_bad = (int*)(p + 256);
     if (inds_host) { CUDA_TRY(cudaMemcpyAsync(d_inds, inds_host, (size_t)N * 4, cudaMemcpyHostToDevice, s)); inds_dev = d_inds; }
     CUDA_TRY(cudaMemsetAsync(d_bad, 0, sizeof(int), s));
+    // tensor mode: no materialised minibatch - the h0 pack and loss kernels read the rollout buffers through the flat indices
+    TcIdxView view; view.flat = inds_dev; view.K = g.K; view.P = (long long)P; view.chains = chains_buf; view.obs = obs_buf; view.olp = oldlogp_buf;
+    view.ret = returns_buf; view.val = values_buf; view.adv = adv_buf; view.bad = d_bad;
+    if (tc_eligible(h, N) && tc_ppo_indexed_ok(h, view) && (adv_std >= 0.f || N_global == N)) {
+        DPPO_TRY(tc_ppo_step_indexed(h, s, view, N, N_global, adv_mean, adv_std));
+        DPPO_TRY(ppo_apply_tail(h, s, lr, apply, metrics8_host ? d_met : metrics8, grads_out));
+    } else {
     const size_t total = (size_t)N * (g.Do + 3 * g.A + 4);
     gather_minibatch_kernel<<<nblk(total, 256), 256, 0, s>>>(obs_buf, chains_buf, oldlogp_buf, returns_buf, values_buf, adv_buf, inds_dev, N, g.K, g.A, g.Do,
                                                            (long long)P, d_obs, d_prev, d_next, d_olp, d_dind, d_ret, d_val, d_adv, d_bad);
     KLAUNCH(h); KCHECK();
     DPPO_TRY(dppo_ppo_step(h, d_obs, d_prev, d_next, d_dind, d_ret, d_val, d_adv, d_olp, N, N_global, adv_mean, adv_std, lr, apply,
                            metrics8_host ? d_met : metrics8, grads_out, (dppo_stream_t)s));
+    }
     if (metrics8_host) {
         int bad = 0;
         CUDA_TRY(cudaMemcpyAsync(metrics8_host, d_met, 8 * sizeof(float), cudaMemcpyDeviceToHost, s));

@@ -415,10 +415,16 @@ struct PpoHyper {
     float dcv, min_lp_std, lp_lo, lp_hi, gamma_d, clip_coef, clip_base, clip_rate, clip_v, vf_coef;
     float inv_nglobal;
 };
-__global__ void adv_stats_kernel(const float* __restrict__ adv, int N, float* __restrict__ out /*mean,std*/) {
+// flat != nullptr: row i of the minibatch is rollout row flat[i] / K (index-driven minibatch); out-of-range indices read row 0
+__global__ void adv_stats_kernel(const float* __restrict__ adv, int N, float* __restrict__ out /*mean,std*/,
+                                 const int* __restrict__ flat = nullptr, int K = 1, long long P = 0) {
     __shared__ double s1[1024], s2[1024];
     double a = 0, b = 0;
-    for (int i = threadIdx.x; i < N; i += blockDim.x) { double v = adv[i]; a += v; b += v * v; }
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        size_t src = i;
+        if (flat) { const int f = flat[i]; src = (f < 0 || (long long)f >= P * K) ? 0 : (size_t)(f / K); }
+        double v = adv[src]; a += v; b += v * v;
+    }
     s1[threadIdx.x] = a; s2[threadIdx.x] = b;
     __syncthreads();
     for (int o = blockDim.x >> 1; o > 0; o >>= 1) {

@@ -115,24 +115,39 @@ __global__ void __launch_bounds__(256) tc_prep_pack_kernel(const TcPrepPackArgs 
         tc_pack_critic_body((size_t)(b - a.T - a.na) * blockDim.x + threadIdx.x, (size_t)a.nc * blockDim.x, a.wc, a.co, a.A, a.Do, a.Hc, a.KP0,
                             a.c_w2w0, a.c_w1, a.c_w3t, a.c_w3p, a.c_bias2, a.c_w1t, a.c_w2t);
 }
+// Index-driven minibatch (train_ppo_diffusion_agent.py:292-312 without materialising it): row r of the minibatch is the
+// (rollout row b, denoising index k) pair of flat[r] = b * K + k; the kernels below read the resident rollout buffers directly.
+struct TcIdxView {
+    const int* flat; int K; long long P;
+    const float *chains, *obs, *olp, *ret, *val, *adv;      // [P][K+1][A], [P][Do], [P][K][A], [P], [P], [P]
+    int* bad;                                                // set to 1 when an index lies outside [0, P*K)
+};
 // h0[r] = [x[r] | obs[r / obs_div] | onehot(t_r) | 1 | 0..]; one thread per 8 consecutive columns (16-byte store)
 // chainK > 0: x is a chains tensor [B][chainK+1][A] and row r = b*chainK + k reads chains[b][k] (get_logprobs)
 __global__ void tc_pack_h0_kernel(const float* __restrict__ x, const float* __restrict__ obs, const int* __restrict__ trow, int tconst,
-                                  int N, int A, int Do, int T, int KP0, int obs_div, bf16* __restrict__ h0, int chainK = 0) {
+                                  int N, int A, int Do, int T, int KP0, int obs_div, bf16* __restrict__ h0, int chainK = 0,
+                                  const int* __restrict__ flat = nullptr, int flatK = 1, long long flatP = 0, int* __restrict__ bad = nullptr) {
     const int g8 = KP0 / 8;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)N * g8) return;
     const int r = (int)(i / g8), k0 = (int)(i % g8) * 8;
     // trow given: t = trow[r], or K-1-trow[r] when tconst = -K (denoising indices); else the constant tconst
-    const int t = trow ? (tconst < 0 ? -tconst - 1 - trow[r] : trow[r]) : tconst;
-    const size_t xrow = chainK > 0 ? (size_t)(r / chainK) * (chainK + 1) + (r % chainK) : (size_t)r;
+    int t = trow ? (tconst < 0 ? -tconst - 1 - trow[r] : trow[r]) : tconst;
+    size_t xrow = chainK > 0 ? (size_t)(r / chainK) * (chainK + 1) + (r % chainK) : (size_t)r;
+    size_t orow = (size_t)(r / obs_div);
+    if (flat) {   // index-driven: x = chains[b][k], obs = obs[b], t = K-1-k
+        int f = flat[r];
+        if (f < 0 || (long long)f >= flatP * flatK) { if (bad && k0 == 0) atomicOr(bad, 1); f = 0; }
+        const int b = f / flatK, k = f % flatK;
+        xrow = (size_t)b * (flatK + 1) + k; orow = (size_t)b; t = flatK - 1 - k;
+    }
     __align__(16) bf16 o[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int k = k0 + j;
         float v = 0.f;
         if (k < A) v = x ? x[xrow * A + k] : 0.f;
-        else if (k < A + Do) v = obs[(size_t)(r / obs_div) * Do + (k - A)];
+        else if (k < A + Do) v = obs[orow * Do + (k - A)];
         else if (k < A + Do + T) v = (k - A - Do == t) ? 1.f : 0.f;
         else if (k == A + Do + T) v = 1.f;
         o[j] = __float2bfloat16(v);
@@ -345,11 +360,24 @@ __global__ void __launch_bounds__(256) tc_ppo_loss8_kernel(
     const int* __restrict__ inds, const float* __restrict__ returns, const float* __restrict__ oldvalues,
     const float* __restrict__ advantages, const float* __restrict__ oldlogp, const float* __restrict__ newvalues,
     const float* __restrict__ advstats, const float* __restrict__ sch, PpoHyper hp, int N,
-    bf16* __restrict__ depsb, bf16* __restrict__ dvalb, double* __restrict__ block_sums, float* __restrict__ col_part /*[blocks][A+1]*/) {
+    bf16* __restrict__ depsb, bf16* __restrict__ dvalb, double* __restrict__ block_sums, float* __restrict__ col_part /*[blocks][A+1]*/,
+    const TcIdxView iv) {
     const int tid = threadIdx.x, sub = tid & 7, lane = tid & 31, wrp = tid >> 5;
     const int r = blockIdx.x * LOSS8_ROWS + (tid >> 3);
     const int A = hp.A, a0 = sub * 4;
     const bool row_ok = r < N;
+    // where this row's inputs live: the materialised minibatch arrays, or (index-driven) the resident rollout buffers
+    size_t prow = (size_t)r * A, nrow = prow, lrow = prow, srow = (size_t)r;
+    int ind_r = 0;
+    if (row_ok) {
+        if (iv.flat) {
+            int f = iv.flat[r];
+            if (f < 0 || (long long)f >= iv.P * iv.K) f = 0;                 // flagged by the h0 pack kernel
+            const size_t b = (size_t)(f / iv.K); ind_r = f % iv.K;
+            prow = (b * (iv.K + 1) + ind_r) * A; nrow = prow + A; lrow = (b * iv.K + ind_r) * A; srow = b;
+            prev = iv.chains; nxt = iv.chains; oldlogp = iv.olp; returns = iv.ret; oldvalues = iv.val; advantages = iv.adv;
+        } else ind_r = inds[r];
+    }
     const int nuse = min(hp.reward_horizon, A / hp.Da) * hp.Da;   // newlogprobs[:, :reward_horizon, :]
     float z[4] = {0.f, 0.f, 0.f, 0.f}, gq[4] = {0.f, 0.f, 0.f, 0.f};
     float newp = 0.f, oldp = 0.f, dv_out = 0.f, sd = 1.f;
@@ -358,14 +386,13 @@ __global__ void __launch_bounds__(256) tc_ppo_loss8_kernel(
     int ind = 0;
     StepConst sc = {};
     if (row_ok) {
-        ind = inds[r];
+        ind = ind_r;
         sc = step_const(sch, hp.T, hp.K - 1 - ind);
         sd = logprob_std(sc, hp.min_lp_std);
         if (a0 < A) {
             const float lgs = 0.91893853320467274f + logf(sd);
-            const size_t i0 = (size_t)r * A + a0;
-            const float4 pv = *reinterpret_cast<const float4*>(prev + i0), nx = *reinterpret_cast<const float4*>(nxt + i0);
-            const float4 ep = *reinterpret_cast<const float4*>(eps + i0), ol = *reinterpret_cast<const float4*>(oldlogp + i0);
+            const float4 pv = *reinterpret_cast<const float4*>(prev + prow + a0), nx = *reinterpret_cast<const float4*>(nxt + nrow + a0);
+            const float4 ep = *reinterpret_cast<const float4*>(eps + (size_t)r * A + a0), ol = *reinterpret_cast<const float4*>(oldlogp + lrow + a0);
             const float pvv[4] = {pv.x, pv.y, pv.z, pv.w}, nxv[4] = {nx.x, nx.y, nx.z, nx.w};
             const float epv[4] = {ep.x, ep.y, ep.z, ep.w}, olv[4] = {ol.x, ol.y, ol.z, ol.w};
 #pragma unroll
@@ -385,7 +412,7 @@ __global__ void __launch_bounds__(256) tc_ppo_loss8_kernel(
     for (int off = 1; off < 8; off <<= 1) { newp += __shfl_xor_sync(0xffffffffu, newp, off); oldp += __shfl_xor_sync(0xffffffffu, oldp, off); }
     if (row_ok) {
         const float newm = newp / (float)nuse, oldm = oldp / (float)nuse;
-        float adv = advantages[r];
+        float adv = advantages[srow];
         if (hp.norm_adv) adv = (adv - advstats[0]) / (advstats[1] + 1e-8f);
         adv *= powf(hp.gamma_d, (float)(hp.K - ind - 1));
         const float logratio = newm - oldm, ratio = expf(logratio);
@@ -403,10 +430,10 @@ __global__ void __launch_bounds__(256) tc_ppo_loss8_kernel(
         drow[sub] = make_uint2(fc::pack_bf16(gq[0], gq[1]), fc::pack_bf16(gq[2], gq[3]));
         drow[8 + sub] = make_uint2(0u, 0u);
         if (sub == 0) {
-            const float v = newvalues[r], ret = returns[r];
+            const float v = newvalues[r], ret = returns[srow];
             float vl, dv;
             if (hp.clip_v >= 0.f) {
-                const float ov = oldvalues[r];
+                const float ov = oldvalues[srow];
                 const float un = (v - ret) * (v - ret);
                 const float dcl = v - ov;
                 const float vc = ov + fminf(fmaxf(dcl, -hp.clip_v), hp.clip_v);
@@ -955,7 +982,8 @@ static int tc_critic_grads(dppo_handle* h, cudaStream_t s, const TcMlp& m, const
 // in h->grads.  The deterministic mode (fixed-order split-K reduction) supports a single chunk only.
 struct TcPpoPlan {
     int N, nchunks, chunk_rows, lead_rows, blocks_done, max_blocks;
-    int full_rows, rows_done, dw_done, dw_flush_chunk;   // multi-chunk pipeline: per-row buffers hold ALL rows, dW runs in (at most) two launches
+    int full_rows, rows_done, dw_done, dw_flush_chunk;
+    TcIdxView idx;                                        // idx.flat != nullptr: the (single) chunk reads the rollout buffers through flat indices   // multi-chunk pipeline: per-row buffers hold ALL rows, dW runs in (at most) two launches
     int64_t N_global;
     float *part, *dw0a, *dw0c, *colb3, *cpa, *cpc;
     double* bsum;
@@ -977,6 +1005,7 @@ static int tc_ppo_begin(dppo_handle* h, cudaStream_t s, int N, int chunk_rows, i
     if (lead_rows <= 0 || lead_rows >= chunk_rows || chunk_rows >= N) lead_rows = 0;
     const int nchunks = lead_rows ? 1 + (N - lead_rows + chunk_rows - 1) / chunk_rows : (N + chunk_rows - 1) / chunk_rows;
     P.N = N; P.nchunks = nchunks; P.N_global = N_global; P.blocks_done = 0;
+    memset(&P.idx, 0, sizeof(P.idx));
     P.chunk_rows = chunk_rows; P.lead_rows = lead_rows;
     // More than one chunk (host pipeline): every per-row buffer holds all N rows and chunk c works on its own row range, so that
     // the weight-gradient GEMMs need not run once per chunk (each launch pays a full set of output-tile reductions): one launch
@@ -1033,7 +1062,11 @@ static int tc_ppo_adv_stats(dppo_handle* h, cudaStream_t s, const float* advanta
         CUDA_TRY(cudaEventRecord(h->aux_ev[0], s)); CUDA_TRY(cudaStreamWaitEvent(h->aux_stream, h->aux_ev[0], 0));
         st = h->aux_stream;
     }
-    if (adv_std < 0.f) { adv_stats_kernel<<<1, 1024, 0, st>>>(advantages_all, N, h->scalars); TC_KCHECK(h); }
+    if (adv_std < 0.f) {
+        if (P.idx.flat) adv_stats_kernel<<<1, 1024, 0, st>>>(P.idx.adv, N, h->scalars, P.idx.flat, P.idx.K, P.idx.P);
+        else adv_stats_kernel<<<1, 1024, 0, st>>>(advantages_all, N, h->scalars);
+        TC_KCHECK(h);
+    }
     else { set_scalars_kernel<<<1, 1, 0, st>>>(h->scalars, adv_mean, adv_std); TC_KCHECK(h); }
     return 0;
 }
@@ -1054,7 +1087,10 @@ static int tc_ppo_chunk(dppo_handle* h, cudaStream_t s, int chunk, const float* 
     const size_t nA = g.ao.n;
     TcPpoPlan& P = tc_plan(h);
     if (n < 1 || n > P.chunk_rows || chunk < 0 || chunk >= P.nchunks) DPPO_FAIL(-1, "tc_ppo_chunk: bad chunk");
-    const bool loss8 = (g.A % 4 == 0) && g.A <= 32 && ((((uintptr_t)prev | (uintptr_t)nxt | (uintptr_t)oldlogp) & 15) == 0);   // float4 row reads
+    const TcIdxView iv = P.idx;
+    const bool loss8 = (g.A % 4 == 0) && g.A <= 32 &&
+        (iv.flat ? ((((uintptr_t)iv.chains | (uintptr_t)iv.olp) & 15) == 0) : ((((uintptr_t)prev | (uintptr_t)nxt | (uintptr_t)oldlogp) & 15) == 0));   // float4 row reads
+    if (iv.flat && (!loss8 || P.nchunks != 1)) DPPO_FAIL(-1, "tc_ppo_chunk: the index-driven minibatch needs A % 4 == 0, aligned buffers and a single chunk");
     const int nlb = loss8 ? tc_nblk(n, LOSS8_ROWS) : tc_nblk(n, 128);
     if (P.blocks_done + nlb > P.max_blocks) DPPO_FAIL(-1, "tc_ppo_chunk: partial-sum buffers exhausted");
     const bool defer = P.ma.fused && P.mc.fused && !h->deterministic;
@@ -1065,7 +1101,12 @@ static int tc_ppo_chunk(dppo_handle* h, cudaStream_t s, int chunk, const float* 
     const TcMlp ma = tc_mlp_at(P.ma, r0), mc = tc_mlp_at(P.mc, r0);
     bf16* const depsb = P.depsb + r0 * 64; bf16* const dvalb = P.dvalb + r0 * 64;
     // h0 straight from (prev, obs, K-1-inds): tconst = -(K) flags "t = K-1-trow[r]"
-    tc_pack_h0_kernel<<<tc_nblk((size_t)n * (KP0 / 8), 256), 256, 0, s>>>(prev, obs, inds, -g.K, n, g.A, g.Do, g.T, KP0, 1, P.h0 + r0 * KP0); TC_KCHECK(h);
+    if (iv.flat)
+        tc_pack_h0_kernel<<<tc_nblk((size_t)n * (KP0 / 8), 256), 256, 0, s>>>(iv.chains, iv.obs, nullptr, 0, n, g.A, g.Do, g.T, KP0, 1, P.h0 + r0 * KP0, 0,
+                                                                                iv.flat, iv.K, iv.P, iv.bad);
+    else
+        tc_pack_h0_kernel<<<tc_nblk((size_t)n * (KP0 / 8), 256), 256, 0, s>>>(prev, obs, inds, -g.K, n, g.A, g.Do, g.T, KP0, 1, P.h0 + r0 * KP0);
+    TC_KCHECK(h);
     // The actor and the critic chains are independent persistent kernels whose last wave leaves a third of the SMs idle
     // (391 row tiles on 148 SMs): the critic chain goes to a second stream so that its CTAs fill the actor chain's tail.
     // (not while the per-kernel profile is on: its event brackets are meant to time each kernel running alone)
@@ -1083,7 +1124,7 @@ static int tc_ppo_chunk(dppo_handle* h, cudaStream_t s, int chunk, const float* 
     if (loss8)
         tc_ppo_loss8_kernel<<<nlb, 256, 0, s>>>(prev, nxt, ma.out, inds, returns, oldvalues, advantages, oldlogp, mc.out,
                                                h->scalars, h->sched, P.hp, n, depsb, dvalb, P.bsum + (size_t)P.blocks_done * 5,
-                                               P.colb3 + (size_t)P.blocks_done * (g.A + 1));
+                                               P.colb3 + (size_t)P.blocks_done * (g.A + 1), iv);
     else
         tc_ppo_loss_kernel<<<nlb, 128, 0, s>>>(prev, nxt, ma.out, inds, returns, oldvalues, advantages, oldlogp, mc.out,
                                               h->scalars, h->sched, P.hp, n, depsb, dvalb, P.bsum + (size_t)P.blocks_done * 5,
@@ -1180,6 +1221,20 @@ static int tc_ppo_step(dppo_handle* h, cudaStream_t s, const float* obs, const f
         DPPO_TRY(tc_ppo_chunk(h, s, c, obs + r0 * g.Do, prev + r0 * g.A, nxt + r0 * g.A, inds + r0, returns + r0, oldvalues + r0, advantages + r0,
                               oldlogp + r0 * g.A, n));
     }
+    return tc_ppo_finish(h, s);
+}
+
+// the same update with the minibatch given as flat (rollout row, denoising index) indices into the resident rollout buffers
+static bool tc_ppo_indexed_ok(const dppo_handle* h, const TcIdxView& v) {
+    return (h->g.A % 4 == 0) && h->g.A <= 32 && ((((uintptr_t)v.chains | (uintptr_t)v.olp) & 15) == 0) && !h->deterministic &&
+           fc_ok(h) && fc_critic_ok(h);
+}
+static int tc_ppo_step_indexed(dppo_handle* h, cudaStream_t s, const TcIdxView& view, int N, int64_t N_global, float adv_mean, float adv_std) {
+    DPPO_TRY(tc_ppo_begin(h, s, N, 0, N_global));
+    tc_plan(h).idx = view;
+    DPPO_TRY(tc_ppo_adv_stats(h, s, nullptr, N, adv_mean, adv_std));
+    DPPO_TRY(tc_ppo_chunk(h, s, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, N));
+    tc_plan(h).idx.flat = nullptr;
     return tc_ppo_finish(h, s);
 }
 

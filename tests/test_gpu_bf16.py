@@ -243,3 +243,35 @@ def test_bf16_sampler_is_shard_invariant(pair):
     a_part, c_part = e.sample(obs[lo:hi].contiguous(), seed=9, offset=1, row_offset=lo)
     assert e.last_path() == _counts(e, 4, 3)
     assert torch.equal(a_part, a_all[lo:hi]) and torch.equal(c_part, c_all[lo:hi])
+
+
+def test_bf16_index_driven_update_reads_the_rollout_buffers_directly(pair):
+    """Tensor mode: dppo_ppo_step_indexed does not materialise the minibatch (the h0 pack and loss kernels address the rollout
+    buffers through the flat indices); it must agree with dppo_ppo_step on the same rows gathered on the host."""
+    o, e = pair
+    if not e.fused:
+        pytest.skip("the index-driven loads belong to the fused path")
+    d = o.d
+    P, K, A, N = 600, d.ft_denoising_steps, d.A, 4096
+    obs, x_T, noise = O.make_rollout_inputs(o, P, seed=77)
+    chains = o.sample(obs, x_T, noise).chains.reshape(P, K + 1, A)
+    g = torch.Generator().manual_seed(5)
+    olp = torch.randn(P, K, A, generator=g) * 0.3 - 1.0
+    ret, val, adv = torch.randn(P, generator=g), torch.randn(P, generator=g), torch.randn(P, generator=g)
+    flat = torch.randint(0, P * K, (N,), generator=g, dtype=torch.int64)
+    b, k = flat // K, flat % K
+    n0 = e.launch_count()
+    m1, g1 = e.ppo_step_indexed(_flat(obs), chains, olp, ret, val, adv, flat.to(torch.int32).cuda(), lr=0.0, apply=False, want_grads=True)
+    launches_indexed = e.launch_count() - n0
+    m2, g2 = e.ppo_step(_flat(obs)[b], chains[b, k], chains[b, k + 1], k.to(torch.int32), ret[b], val[b], adv[b], olp[b, k],
+                        lr=0.0, apply=False, want_grads=True)
+    torch.cuda.synchronize()
+    n1 = e.launch_count()
+    e.ppo_step(_flat(obs)[b], chains[b, k], chains[b, k + 1], k.to(torch.int32), ret[b], val[b], adv[b], olp[b, k], lr=0.0, apply=False)
+    assert launches_indexed == e.launch_count() - n1                  # no gather kernel in front of the update
+    assert torch.equal(m1, m2)                                        # the loss partial sums are reduced in a fixed order
+    scale = float(g2.abs().max())
+    assert float((g1 - g2).abs().max()) < 2e-3 * scale                # dW accumulates with atomics: order varies run to run
+    with pytest.raises(L.DppoError):
+        e.ppo_step_indexed(_flat(obs), chains, olp, ret, val, adv, np.full(N, P * K, np.int32), lr=0.0, apply=False,
+                           metrics_host=np.zeros(8, np.float32))
