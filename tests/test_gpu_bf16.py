@@ -268,7 +268,8 @@ def test_bf16_index_driven_update_reads_the_rollout_buffers_directly(pair):
     torch.cuda.synchronize()
     n1 = e.launch_count()
     e.ppo_step(_flat(obs)[b], chains[b, k], chains[b, k + 1], k.to(torch.int32), ret[b], val[b], adv[b], olp[b, k], lr=0.0, apply=False)
-    assert launches_indexed == e.launch_count() - n1                  # no gather kernel in front of the update
+    # no gather kernel in front of the update (the deterministic mode keeps the gathered path: one more launch)
+    assert launches_indexed == e.launch_count() - n1 + (1 if DETERMINISTIC else 0)
     assert torch.equal(m1, m2)                                        # the loss partial sums are reduced in a fixed order
     scale = float(g2.abs().max())
     assert float((g1 - g2).abs().max()) < 2e-3 * scale                # dW accumulates with atomics: order varies run to run
