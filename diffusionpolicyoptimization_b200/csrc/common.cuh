@@ -179,6 +179,7 @@ struct dppo_handle {
     int last_path = 0;    // sampler path of the last dppo_sample: 1 cluster, 2 layered fp32, 3 tensor
     int force_path = 0;   // test hook: 0 auto, 1 force cluster sampler, 2 forbid it
     struct TcState* tc = nullptr;   // tcgen05 path state (tc_path.cuh)
+    struct TsState* ts = nullptr;   // split-precision tcgen05 path state (ts_path.cuh, DPPO_PREC_BF16X3)
     // live GEMM timing (dppo_profile_*): event pairs recorded around GEMM-class launches
     int prof_on = 0;
     std::vector<cudaEvent_t> prof_ev;   // pairs

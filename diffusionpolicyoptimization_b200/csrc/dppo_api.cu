@@ -3,6 +3,7 @@
 #include "simt_kernels.cuh"
 #include "sample_cluster.cuh"
 #include "tc_path.cuh"
+#include "ts_path.cuh"
 #include <stdarg.h>
 #include <dlfcn.h>
 #include <cmath>
@@ -230,6 +231,7 @@ static int prep_net(dppo_handle* h, int net, cudaStream_t s) {
         KLAUNCH(h); KCHECK();
     }
     if (h->cfg.precision == DPPO_PREC_FP32) DPPO_TRY(ensure_w0p(h, net, s));
+    DPPO_TRY(ts_refresh_net(h, net, s));
     return tc_refresh_net(h, net, s);
 }
 
@@ -285,6 +287,8 @@ extern "C" int dppo_create(const dppo_cfg* cfg, int device, dppo_handle** out) {
     CUDA_TRY(cudaMemset(h->scalars, 0, 64 * sizeof(float)));
     int r = tc_init(h);
     if (r) { dppo_destroy(h); return r; }
+    r = ts_init(h);
+    if (r) { dppo_destroy(h); return r; }
     for (int net = 0; net < 4; ++net) { r = prep_net(h, net, 0); if (r) { dppo_destroy(h); return r; } }
     CUDA_TRY(cudaDeviceSynchronize());
     *out = h;
@@ -296,6 +300,7 @@ extern "C" void dppo_destroy(dppo_handle* h) {
     cudaDeviceSynchronize();
     tc_plan_free(h);
     tc_destroy(h);
+    ts_destroy(h);
     for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
     if (h->comm) {
         void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
@@ -521,6 +526,11 @@ extern "C" int dppo_actor_forward(dppo_handle* h, int net, const float* x, const
             DPPO_TRY(tc_actor_forward(h, s, net, x + (size_t)r0 * g.A, obs + (size_t)r0 * g.Do, 1, n, t + r0, 0, eps + (size_t)r0 * g.A));
             continue;
         }
+        if (ts_eligible(h, n)) {
+            DPPO_TRY(ws_reserve(h, ts_actor_forward_ws(h, n), s));
+            DPPO_TRY(ts_actor_forward(h, s, net, x + (size_t)r0 * g.A, obs + (size_t)r0 * g.Do, 1, n, t + r0, 0, eps + (size_t)r0 * g.A));
+            continue;
+        }
         DPPO_TRY(ws_reserve(h, fwd_ws_bytes(n, g.KP, g.H, g.A), s));
         FwdBufs b; fwd_take(h, n, g.KP, g.H, g.A, b);
         DPPO_TRY(actor_fwd_fp32(h, s, net, x + (size_t)r0 * g.A, obs + (size_t)r0 * g.Do, 1, n, t + r0, 0, b));
@@ -534,6 +544,7 @@ extern "C" int dppo_value(dppo_handle* h, const float* obs, int N, float* v, dpp
     for (int r0 = 0; r0 < N; r0 += ROW_CHUNK) {
         int n = N - r0 < ROW_CHUNK ? N - r0 : ROW_CHUNK;
         if (tc_eligible(h, n)) { DPPO_TRY(tc_value(h, s, obs + (size_t)r0 * g.Do, n, v + r0)); continue; }
+        if (ts_eligible(h, n)) { DPPO_TRY(ts_value(h, s, obs + (size_t)r0 * g.Do, n, v + r0)); continue; }
         DPPO_TRY(ws_reserve(h, fwd_ws_bytes(n, g.KPc, g.Hc, 1), s));
         FwdBufs b; fwd_take(h, n, g.KPc, g.Hc, 1, b);
         DPPO_TRY(critic_fwd_fp32(h, s, obs + (size_t)r0 * g.Do, n, b));
@@ -551,9 +562,10 @@ static int logprobs_impl(dppo_handle* h, cudaStream_t s, const float* obs, const
     const int chunk_rows = chains ? (ROW_CHUNK / g.K) * g.K : ROW_CHUNK;
     for (int r0 = 0; r0 < N; r0 += chunk_rows) {
         int n = N - r0 < chunk_rows ? N - r0 : chunk_rows;
-        const bool tensor = tc_eligible(h, n);
-        const bool fusedlp = tensor && fc_ok(h);
-        size_t need = (tensor ? ws_bytes((size_t)n * g.A, 4) + tc_actor_forward_ws(h, n) : fwd_ws_bytes(n, g.KP, g.H, g.A))
+        const bool split = ts_eligible(h, n);
+        const bool tensor = tc_eligible(h, n) || split;
+        const bool fusedlp = tensor && !split && fc_ok(h);
+        size_t need = (tensor ? ws_bytes((size_t)n * g.A, 4) + (split ? ts_actor_forward_ws(h, n) : tc_actor_forward_ws(h, n)) : fwd_ws_bytes(n, g.KP, g.H, g.A))
                     + ws_bytes(n, 4) + ws_bytes((size_t)n * g.A, 4);
         DPPO_TRY(ws_reserve(h, need, s));
         FwdBufs b; memset(&b, 0, sizeof(b));
@@ -582,7 +594,8 @@ static int logprobs_impl(dppo_handle* h, cudaStream_t s, const float* obs, const
                                     chains ? nullptr : nxt + (size_t)r0 * g.A, ch, trow));
             continue;
         }
-        if (tensor) { DPPO_TRY(tc_actor_forward(h, s, net, xin, ob, obs_div, n, trow, 0, b.out)); epsp = b.out; }
+        if (split) { DPPO_TRY(ts_actor_forward(h, s, net, xin, ob, obs_div, n, trow, 0, b.out)); epsp = b.out; }
+        else if (tensor) { DPPO_TRY(tc_actor_forward(h, s, net, xin, ob, obs_div, n, trow, 0, b.out)); epsp = b.out; }
         else { DPPO_TRY(actor_fwd_fp32(h, s, net, xin, ob, obs_div, n, trow, 0, b)); epsp = b.out; }
         logprob_kernel<<<nblk((size_t)n * g.A, 256), 256, 0, s>>>(chains ? nullptr : prev + (size_t)r0 * g.A,
             chains ? nullptr : nxt + (size_t)r0 * g.A, ch, epsp, trow, n, g.A, g.K, h->sched, g.T,
@@ -648,7 +661,8 @@ static int sample_layered_fp32(dppo_handle* h, cudaStream_t s, const float* obs,
                                uint64_t seed, uint64_t offset, int64_t row_offset, const float* xT, const float* noise,
                                float* actions, float* chains, bool tensor) {
     const Geom& g = h->g;
-    size_t need = (tensor ? ws_bytes((size_t)B * g.A, 4) + tc_actor_forward_ws(h, B) : fwd_ws_bytes(B, g.KP, g.H, g.A)) + ws_bytes((size_t)B * g.A, 4);
+    const bool split = tensor && ts_eligible(h, B);
+    size_t need = (tensor ? ws_bytes((size_t)B * g.A, 4) + (split ? ts_actor_forward_ws(h, B) : tc_actor_forward_ws(h, B)) : fwd_ws_bytes(B, g.KP, g.H, g.A)) + ws_bytes((size_t)B * g.A, 4);
     DPPO_TRY(ws_reserve(h, need, s));
     FwdBufs b; memset(&b, 0, sizeof(b));
     if (tensor) b.out = ws_take<float>(h, (size_t)B * g.A); else fwd_take(h, B, g.KP, g.H, g.A, b);
@@ -658,7 +672,8 @@ static int sample_layered_fp32(dppo_handle* h, cudaStream_t s, const float* obs,
     for (int i = 0; i < g.T; ++i) {
         const int t = g.T - 1 - i;
         const int net = (t < g.K && !use_base) ? DPPO_NET_ACTOR_FT : DPPO_NET_ACTOR;
-        if (tensor) DPPO_TRY(tc_actor_forward(h, s, net, x, obs, 1, B, nullptr, t, b.out));
+        if (split) DPPO_TRY(ts_actor_forward(h, s, net, x, obs, 1, B, nullptr, t, b.out));
+        else if (tensor) DPPO_TRY(tc_actor_forward(h, s, net, x, obs, 1, B, nullptr, t, b.out));
         else DPPO_TRY(actor_fwd_fp32(h, s, net, x, obs, 1, B, nullptr, t, b));
         sample_update_kernel<<<nblk((size_t)B * g.A, 256), 256, 0, s>>>(x, b.out, noise, B, g.A, t, i, h->sched, g.T, hp,
             seed, offset, row_offset, chains, g.K, t <= g.K ? g.K - t : -1, actions);
@@ -677,7 +692,8 @@ extern "C" int dppo_sample(dppo_handle* h, const float* obs, int B, int determin
     hp.dcv = h->cfg.denoised_clip_value; hp.rcv = h->cfg.randn_clip_value; hp.facv = h->cfg.final_action_clip_value;
     hp.min_std = min_sampling_std >= 0.f ? min_sampling_std : h->cfg.min_sampling_denoising_std;
     hp.deterministic = deterministic;
-    const bool tensor = tc_eligible(h, B);
+    const bool split = ts_eligible(h, B);
+    const bool tensor = tc_eligible(h, B) || split;
     const bool cluster_shape = (g.H == CS_H && g.A <= 32 && h->cfg.actor_act == DPPO_ACT_RELU && h->force_path != 2);
     // the persistent cluster kernel wins while the chain is latency bound; beyond that rows are
     // plentiful enough for real GEMM tiles
@@ -695,7 +711,7 @@ extern "C" int dppo_sample(dppo_handle* h, const float* obs, int B, int determin
         h->cluster_max = 0;   // not launchable here: remember and fall through to the layered path
         (void)cudaGetLastError();
     }
-    if (tensor && fc_ok(h)) {
+    if (tensor && !split && fc_ok(h)) {
         h->last_path = 4;
         return fc_sample(h, s, obs, B, use_base_policy, hp, seed, offset, row_offset, xT, noise, actions, chains);
     }
@@ -919,6 +935,8 @@ extern "C" int dppo_ppo_step(dppo_handle* h, const float* obs, const float* prev
     float* gr = h->grads;
     if (tc_eligible(h, N)) {
         DPPO_TRY(tc_ppo_step(h, s, obs, prev, nxt, inds, returns, oldvalues, advantages, oldlogp, N, N_global, adv_mean, adv_std));
+    } else if (ts_eligible(h, N)) {
+        DPPO_TRY(ts_ppo_step(h, s, obs, prev, nxt, inds, returns, oldvalues, advantages, oldlogp, N, N_global, adv_mean, adv_std));
     } else {
         const int nlb = nblk(N, 128);
         size_t need = fwd_ws_bytes(N, g.KP, g.H, g.A) + fwd_ws_bytes(N, g.KPc, g.Hc, 1)
@@ -1115,6 +1133,8 @@ extern "C" int dppo_pretrain_step(dppo_handle* h, const float* actions, const fl
     float* gr = h->grads;
     if (tc_eligible(h, N)) {
         DPPO_TRY(tc_pretrain_grads(h, s, actions, obs, N, N_global, row_offset, t_in, noise_in, seed, offset));
+    } else if (ts_eligible(h, N)) {
+        DPPO_TRY(ts_pretrain_grads(h, s, actions, obs, N, N_global, row_offset, t_in, noise_in, seed, offset));
     } else {
         const size_t ne = (size_t)N * g.A;
         const int nlb = nblk(ne, 256);
@@ -1200,5 +1220,30 @@ extern "C" int dppo_debug_tc_gemm(dppo_handle* h, const void* A, int a_mn, int64
     g.epi.out_f32 = out_f32; g.epi.ld_f32 = N; g.epi.split_stride = (size_t)M * N;
     g.epi.out_bf16 = (__nv_bfloat16*)out_bf16; g.epi.ld_bf16 = N;
     int r = tc::launch(h, s, g);
+    return r < 0 ? r : 0;
+}
+
+__global__ void ts_split_planes_kernel(const float* __restrict__ src, size_t n, bf16* __restrict__ p0, bf16* __restrict__ p1, bf16* __restrict__ p2) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) ts::split_bf16_3(src[i], p0[i], p1[i], p2[i]);
+}
+extern "C" int dppo_debug_split_gemm(dppo_handle* h, const float* A, int a_mn, int64_t lda, const float* B, int b_mn, int64_t ldb,
+                                     int M, int N, int K, int splits, int planes, float* out_f32, dppo_stream_t st) {
+    ENTER(h); cudaStream_t s = (cudaStream_t)st;
+    if (!A || !B || !out_f32 || M < 1 || N < 1 || K < 1 || planes < 2 || planes > 3) DPPO_FAIL(-1, "dppo_debug_split_gemm: bad arguments");
+    const size_t na = (((size_t)(a_mn ? K : M) * lda) + 7) & ~(size_t)7, nb = (((size_t)(b_mn ? K : N) * ldb) + 7) & ~(size_t)7;
+    bf16* buf = nullptr;
+    CUDA_TRY(cudaMalloc(&buf, 3 * (na + nb) * sizeof(bf16)));
+    bf16* bb = buf + 3 * na;
+    ts_split_planes_kernel<<<nblk((size_t)(a_mn ? K : M) * lda, 256), 256, 0, s>>>(A, (size_t)(a_mn ? K : M) * lda, buf, buf + na, buf + 2 * na); KLAUNCH(h);
+    ts_split_planes_kernel<<<nblk((size_t)(b_mn ? K : N) * ldb, 256), 256, 0, s>>>(B, (size_t)(b_mn ? K : N) * ldb, bb, bb + nb, bb + 2 * nb); KLAUNCH(h);
+    ts::Gemm g; memset(&g, 0, sizeof(g));
+    g.A = ts::Operand{{buf, buf + na, buf + 2 * na}, a_mn != 0, M, K, lda};
+    g.B = ts::Operand{{bb, bb + nb, bb + 2 * nb}, b_mn != 0, N, K, ldb};
+    g.M = M; g.N = N; g.splits = splits; g.planes = planes;
+    g.epi.M = M; g.epi.N = N; g.epi.out_f32 = out_f32; g.epi.ld_f32 = N; g.epi.split_stride = (size_t)M * N;
+    int r = ts::launch(h, s, g);
+    cudaStreamSynchronize(s);
+    cudaFree(buf);
     return r < 0 ? r : 0;
 }

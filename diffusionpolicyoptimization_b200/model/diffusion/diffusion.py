@@ -45,7 +45,7 @@ class DiffusionModel:
         cfg.denoised_clip_value = -1.0 if denoised_clip_value is None else float(denoised_clip_value)
         cfg.randn_clip_value = float(randn_clip_value)
         cfg.final_action_clip_value = -1.0 if final_action_clip_value is None else float(final_action_clip_value)
-        cfg.precision = {"fp32": L.PREC_FP32, "bf16": L.PREC_BF16}[precision]
+        cfg.precision = {"fp32": L.PREC_FP32, "bf16": L.PREC_BF16, "bf16x3": L.PREC_BF16X3}[precision]
         if _cfg_hook is not None:
             _cfg_hook(cfg)
         assert network.cond_dim == cfg.obs_dim * cfg.cond_steps

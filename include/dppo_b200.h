@@ -41,8 +41,11 @@ enum { DPPO_ACT_RELU = 0, DPPO_ACT_MISH = 1 };
 /* arithmetic of the MLP GEMMs */
 enum {
     DPPO_PREC_FP32 = 0, /* CUDA-core FFMA everywhere: the parity mode (1e-4 rel / 1e-3 abs)        */
-    DPPO_PREC_BF16 = 1  /* tcgen05 bf16 x bf16 -> fp32 for large row counts; fp32 master weights,
+    DPPO_PREC_BF16 = 1, /* tcgen05 bf16 x bf16 -> fp32 for large row counts; fp32 master weights,
                            fp32 epilogues; looser bound stated in DESIGN.md                         */
+    DPPO_PREC_BF16X3 = 2 /* tcgen05, every operand as bf16 hi + lo planes and every product as
+                           hi*hi + lo*hi + hi*lo into one fp32 TMEM accumulator: meets the fp32
+                           parity tolerance (1e-4 rel / 1e-3 abs) on the tensor pipe               */
 };
 /* optimizer slots */
 enum { DPPO_OPT_PRETRAIN = 0 /* actor */, DPPO_OPT_FINETUNE = 1 /* actor_ft ++ critic */ };
@@ -249,6 +252,12 @@ int dppo_force_path(dppo_handle* h, int path);
 int dppo_debug_tc_gemm(dppo_handle* h, const void* A, int a_mn, int64_t lda, const void* A2, int64_t lda2, int K2,
                        const void* B, int b_mn, int64_t ldb, int M, int N, int K, int splits,
                        const float* bias, int act, float* out_f32, void* out_bf16, dppo_stream_t s);
+/* Test hook: one split-precision tcgen05 GEMM (DPPO_PREC_BF16X3 arithmetic)  out[M,N] = A*B  on FP32 device operands:
+ * each operand is split into `planes` (2 or 3) bf16 planes on the fly and the product is the sum of the plane products
+ * (3 for two planes, 6 for three) with fp32 accumulation in tensor memory.
+ * Majorness flags as in dppo_debug_tc_gemm; out_f32 is [splits][M][N] partial sums (splits is clamped to the k-blocks). */
+int dppo_debug_split_gemm(dppo_handle* h, const float* A, int a_mn, int64_t lda, const float* B, int b_mn, int64_t ldb,
+                          int M, int N, int K, int splits, int planes, float* out_f32, dppo_stream_t s);
 /* Dev tool: per-CTA cycle counters of the fused chain kernel.  enable != 0 allocates them; out_host (optional)
  * receives HOST [16 launch slots][sm_count][8] (slot = chain launches since the last read, round robin) = {producer wait w_empty, mma wait x_full, mma wait w_full, mma total,
  * epilogue wait acc_full, epilogue generic layers, epilogue final layer, 0} of the last launch. */
