@@ -1247,3 +1247,31 @@ extern "C" int dppo_debug_split_gemm(dppo_handle* h, const float* A, int a_mn, i
     cudaFree(buf);
     return r < 0 ? r : 0;
 }
+
+__global__ void ts_sum_planes_kernel(const bf16* __restrict__ p0, const bf16* __restrict__ p1, const bf16* __restrict__ p2, size_t n, float* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = __bfloat162float(p0[i]) + __bfloat162float(p1[i]) + (p2 ? __bfloat162float(p2[i]) : 0.f);
+}
+extern "C" int dppo_debug_pair_gemm(dppo_handle* h, const float* A, int64_t lda, const float* B, int b_mn, int64_t ldb,
+                                    int M, int N, int K, int planes, const float* bias, int act, float* out_f32, uint32_t* mask_out, dppo_stream_t st) {
+    ENTER(h); cudaStream_t s = (cudaStream_t)st;
+    if (!A || !B || !out_f32 || M < 1 || N < 64 || (N % 64) || K < 1 || planes < 2 || planes > 3) DPPO_FAIL(-1, "dppo_debug_pair_gemm: bad arguments");
+    const size_t na = (((size_t)M * lda) + 7) & ~(size_t)7, nb = (((size_t)(b_mn ? K : N) * ldb) + 7) & ~(size_t)7, no = (((size_t)M * N) + 7) & ~(size_t)7;
+    bf16* buf = nullptr;
+    CUDA_TRY(cudaMalloc(&buf, 3 * (na + nb + no) * sizeof(bf16)));
+    bf16* bb = buf + 3 * na; bf16* ob = bb + 3 * nb;
+    ts_split_planes_kernel<<<nblk((size_t)M * lda, 256), 256, 0, s>>>(A, (size_t)M * lda, buf, buf + na, buf + 2 * na); KLAUNCH(h);
+    ts_split_planes_kernel<<<nblk((size_t)(b_mn ? K : N) * ldb, 256), 256, 0, s>>>(B, (size_t)(b_mn ? K : N) * ldb, bb, bb + nb, bb + 2 * nb); KLAUNCH(h);
+    tsp::Gemm g; memset(&g, 0, sizeof(g));
+    g.A = ts::Operand{{buf, buf + na, buf + 2 * na}, false, M, K, lda};
+    g.B = ts::Operand{{bb, bb + nb, bb + 2 * nb}, b_mn != 0, N, K, ldb};
+    g.M = M; g.N = N; g.planes = planes; g.dual = planes == 3 ? 1 : 0;
+    g.out[0] = ob; g.out[1] = ob + no; g.out[2] = ob + 2 * no; g.ld_out = N;
+    g.epi.M = M; g.epi.N = N; g.epi.out_planes = planes; g.epi.bias = bias; g.epi.act = act;
+    if (mask_out) { g.epi.mask_out = mask_out; g.epi.ldm = N / 32; }
+    int r = tsp::launch(h, s, g);
+    if (r == 0) { ts_sum_planes_kernel<<<nblk((size_t)M * N, 256), 256, 0, s>>>(ob, ob + no, planes == 3 ? ob + 2 * no : nullptr, (size_t)M * N, out_f32); KLAUNCH(h); }
+    cudaStreamSynchronize(s);
+    cudaFree(buf);
+    return r;
+}

@@ -15,8 +15,9 @@
 //   ts::split_gemm_kernel<BN, A_MN, B_MN, P>   D[M,N] = sum_seg sum_(i,j) A_i B_j
 //     * a shared-memory stage holds the 2 P plane tiles of one 64-deep k-block (TMA, 128-byte swizzle): each byte that
 //       enters the SM feeds 1.5 (P = 2) or 2 (P = 3) MMAs instead of the 1 of a K-concatenated formulation
-//     * 128 x BN accumulators double-buffered in TMEM; 4 epilogue warps: bias / activation / act' mask / residual add, outputs
-//       as hi + lo planes (the next GEMM's operands), fp32, or split-K partials (deterministic fixed-order reduction)
+//     * 128 x BN accumulators double-buffered in TMEM; 4 epilogue warps write fp32 (+ bias): the narrow output layer and the
+//       split-K partials of the weight gradients (deterministic fixed-order reduction).  The layers whose output is the next
+//       GEMM's operand run on tsp::pair_gemm_kernel below.
 //     * operands K-major or MN-major as stored (activations [rows][features], weights [in][out]): nothing is transposed
 //   host programs (same data flow as the per-layer bf16 programs of tc_path.cuh, every activation / gradient as two planes):
 //     forward L0..L3 (residual by K-concatenation [a1 | h0] x [W2 ; W0]), backward dv / dh1 / du, the four weight-gradient
@@ -33,12 +34,7 @@ constexpr int MAXP = 3;
 struct Epi {
     int M, N;                                         // valid extents of the output
     const float* bias;                                // [N]
-    int act;                                          // 0 none, 1 relu, 2 mish
-    const bf16* mask0; const bf16* mask1; int ldmask; int mask_mode;   // 1: *= (mask0 > 0), 2: *= mish'(mask0 + mask1)
-    const bf16* add0; const bf16* add1; int ldadd;                     // += add0 + add1
     float* out_f32; int ld_f32; size_t split_stride;  // fp32 row-major (+ split * split_stride)
-    bf16* out[MAXP]; int out_planes; int ld_out;      // post-activation planes (out_planes = 0: none)
-    bf16* pre[2]; int ld_pre;                         // pre-activation (Mish nets), two planes
 };
 struct Params {
     int m_blocks, n_blocks, splits;
@@ -46,7 +42,7 @@ struct Params {
     int ka_blocks;                                    // K blocks taken from A segment 0 (the rest from segment 1)
     Epi epi;
 };
-struct Maps { CUtensorMap a[2][MAXP], b[MAXP]; };    // [segment][plane], [plane]
+struct Maps { CUtensorMap a[2][MAXP], b[2][MAXP]; };    // [segment][plane]; k coordinates are local to the segment
 
 // stage = P A-plane tiles + P B-plane tiles of one k-block
 template <int BN, int P> __host__ __device__ constexpr int stage_bytes() { return P * (SBM * SBK * 2 + BN * SBK * 2); }
@@ -63,30 +59,7 @@ __device__ __forceinline__ void split_bf16_3(float v, bf16& p0, bf16& p1, bf16& 
     p1 = __float2bfloat16(r1);
     p2 = __float2bfloat16(r1 - __bfloat162float(p1));     // exact remainder, rounded to the third plane
 }
-// 32 consecutive outputs of one row as NP bf16 planes
-template <int NP>
-__device__ __forceinline__ void store_planes32(bf16* const (&dst)[MAXP], size_t off, const float (&v)[32], bool vec, int nvalid) {
-    if (vec) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            __align__(16) bf16 t[MAXP][8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                if (NP == 3) split_bf16_3(v[q * 8 + j], t[0][j], t[1][j], t[2][j]); else split_bf16(v[q * 8 + j], t[0][j], t[1][j]);
-            }
-#pragma unroll
-            for (int pl = 0; pl < NP; ++pl) *reinterpret_cast<uint4*>(dst[pl] + off + q * 8) = *reinterpret_cast<const uint4*>(t[pl]);
-        }
-    } else {
-        for (int j = 0; j < nvalid; ++j) {
-            bf16 t0, t1, t2 = __float2bfloat16(0.f);
-            if (NP == 3) split_bf16_3(v[j], t0, t1, t2); else split_bf16(v[j], t0, t1);
-            dst[0][off + j] = t0; dst[1][off + j] = t1; if (NP == 3) dst[2][off + j] = t2;
-        }
-    }
-}
-
-template <int BN, bool A_MN, bool B_MN, int P>
+template <int BN, bool A_MN, bool B_MN, int P, bool DUAL>
 __global__ void __launch_bounds__(STHREADS, 1) split_gemm_kernel(const __grid_constant__ Maps maps, const Params p) {
     constexpr int STG = stages<BN, P>();
     constexpr int A_TILE = SBM * SBK * 2, B_TILE = BN * SBK * 2, STAGE = stage_bytes<BN, P>();
@@ -94,7 +67,7 @@ __global__ void __launch_bounds__(STHREADS, 1) split_gemm_kernel(const __grid_co
     // the epilogue.  tcgen05 accumulation truncates: every MMA into an accumulator costs up to one ulp of ITS magnitude, biased
     // (measured: 192 accumulations per element at K = 512 left 5e-6 relative whether the operands carried 16 or 24 bits).  The
     // correction sum is 2^-8 of the main one, so its truncations vanish and the main accumulator sees K/16 of them instead of 6 K/16.
-    constexpr int NACC = P == 3 ? 2 : 1;
+    constexpr int NACC = DUAL ? 2 : 1;
     constexpr int ACC_COLS = NACC * BN;
     constexpr int TMEM_COLS = (2 * ACC_COLS <= 32) ? 32 : (2 * ACC_COLS <= 64 ? 64 : (2 * ACC_COLS <= 128 ? 128 : (2 * ACC_COLS <= 256 ? 256 : 512)));
     static_assert(STG >= 2, "a stage must fit twice");
@@ -112,7 +85,7 @@ __global__ void __launch_bounds__(STHREADS, 1) split_gemm_kernel(const __grid_co
     const int tiles = p.m_blocks * p.n_blocks * p.splits;
 
     if (warp == 0 && lane == 0) {
-        for (int pl = 0; pl < P; ++pl) { tma_prefetch_desc(&maps.a[0][pl]); tma_prefetch_desc(&maps.b[pl]); }
+        for (int pl = 0; pl < P; ++pl) { tma_prefetch_desc(&maps.a[0][pl]); tma_prefetch_desc(&maps.b[0][pl]); }
         for (int i = 0; i < STG; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -149,10 +122,10 @@ __global__ void __launch_bounds__(STHREADS, 1) split_gemm_kernel(const __grid_co
 #pragma unroll
                             for (int j = 0; j < SBM / 64; ++j) tma_load_2d(a + j * (64 * SBK * 2), &maps.a[seg][pl], &full[stage], m_blk * SBM + j * 64, ka);
                         }
-                        if (!B_MN) tma_load_2d(b, &maps.b[pl], &full[stage], kb * SBK, n_blk * BN);
+                        if (!B_MN) tma_load_2d(b, &maps.b[seg][pl], &full[stage], ka, n_blk * BN);
                         else {
 #pragma unroll
-                            for (int j = 0; j < BN / 64; ++j) tma_load_2d(b + j * (64 * SBK * 2), &maps.b[pl], &full[stage], n_blk * BN + j * 64, kb * SBK);
+                            for (int j = 0; j < BN / 64; ++j) tma_load_2d(b + j * (64 * SBK * 2), &maps.b[seg][pl], &full[stage], n_blk * BN + j * 64, ka);
                         }
                     }
                 }
@@ -241,59 +214,6 @@ __global__ void __launch_bounds__(STHREADS, 1) split_gemm_kernel(const __grid_co
 #pragma unroll
                         for (int j = 0; j < 32; ++j) if (full32 || j < nvalid) v[j] += __ldg(e.bias + n0 + j);
                     }
-                    if (e.pre[0]) {
-                        bf16* const pd[MAXP] = {e.pre[0], e.pre[1], nullptr};
-                        store_planes32<2>(pd, (size_t)m * e.ld_pre + n0, v, full32 && (e.ld_pre & 7) == 0, nvalid);
-                    }
-                    if (e.act == 1) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-                    } else if (e.act == 2) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = mish_f(v[j]);
-                    }
-                    if (e.mask0) {
-                        const bf16* sh = e.mask0 + (size_t)m * e.ldmask + n0;
-                        const bf16* sl = e.mask1 ? e.mask1 + (size_t)m * e.ldmask + n0 : nullptr;
-                        if (full32 && (e.ldmask & 7) == 0) {
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const uint4 uh = *reinterpret_cast<const uint4*>(sh + q * 8);
-                                const bf16* hb = reinterpret_cast<const bf16*>(&uh);
-                                if (e.mask_mode == 1) {
-#pragma unroll
-                                    for (int j = 0; j < 8; ++j) v[q * 8 + j] = __bfloat162float(hb[j]) > 0.f ? v[q * 8 + j] : 0.f;
-                                } else {
-                                    const uint4 ul = *reinterpret_cast<const uint4*>(sl + q * 8);
-                                    const bf16* lb = reinterpret_cast<const bf16*>(&ul);
-#pragma unroll
-                                    for (int j = 0; j < 8; ++j) v[q * 8 + j] *= mish_grad_f(__bfloat162float(hb[j]) + __bfloat162float(lb[j]));
-                                }
-                            }
-                        } else {
-                            for (int j = 0; j < nvalid; ++j) {
-                                const float mh = __bfloat162float(sh[j]);
-                                v[j] *= (e.mask_mode == 1) ? (mh > 0.f ? 1.f : 0.f) : mish_grad_f(mh + __bfloat162float(sl[j]));
-                            }
-                        }
-                    }
-                    if (e.add0) {
-                        const bf16* sh = e.add0 + (size_t)m * e.ldadd + n0;
-                        const bf16* sl = e.add1 + (size_t)m * e.ldadd + n0;
-                        if (full32 && (e.ldadd & 7) == 0) {
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const uint4 uh = *reinterpret_cast<const uint4*>(sh + q * 8), ul = *reinterpret_cast<const uint4*>(sl + q * 8);
-                                const bf16* hb = reinterpret_cast<const bf16*>(&uh); const bf16* lb = reinterpret_cast<const bf16*>(&ul);
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) v[q * 8 + j] += __bfloat162float(hb[j]) + __bfloat162float(lb[j]);
-                            }
-                        } else {
-                            for (int j = 0; j < nvalid; ++j) v[j] += __bfloat162float(sh[j]) + __bfloat162float(sl[j]);
-                        }
-                    }
-                    if (e.out_planes == 3) store_planes32<3>(e.out, (size_t)m * e.ld_out + n0, v, full32 && (e.ld_out & 7) == 0, nvalid);
-                    else if (e.out_planes == 2) store_planes32<2>(e.out, (size_t)m * e.ld_out + n0, v, full32 && (e.ld_out & 7) == 0, nvalid);
                     if (e.out_f32) {
                         float* dst = e.out_f32 + (size_t)split * e.split_stride + (size_t)m * e.ld_f32 + n0;
                         if (full32 && (e.ld_f32 & 3) == 0) {
@@ -324,14 +244,15 @@ __global__ void __launch_bounds__(STHREADS, 1) split_gemm_kernel(const __grid_co
 // One split operand: `planes` planes with the same shape.  K-major: memory is [mn][k]; MN-major: memory is [k][mn].
 struct Operand { const bf16* p[MAXP]; bool mn_major; int64_t mn, k, ld; };
 struct Gemm {
-    Operand A, A2, B;      // A2.p[0] == nullptr: no K concatenation; B spans the concatenated K
+    Operand A, A2, B, B2;  // A2.p[0] == nullptr: no K concatenation; else the K-concatenation [A | A2] x [B ; B2]
     int planes;            // 2 or 3 (every operand must carry that many)
+    int dual;              // two planes with the correction products in a second accumulator (forward GEMMs in front of kinks)
     int M, N, splits;
     double alg_flops;      // algorithmic flops (un-padded dims, ONE product per MAC) for the live roofline
     Epi epi;
 };
 
-template <int BN, bool A_MN, bool B_MN, int P>
+template <int BN, bool A_MN, bool B_MN, int P, bool DUAL>
 static int launch_t(dppo_handle* h, cudaStream_t s, const Gemm& g) {
     Maps mp;
     const Operand& A = g.A; const Operand& B = g.B;
@@ -342,8 +263,11 @@ static int launch_t(dppo_handle* h, cudaStream_t s, const Gemm& g) {
         const int src = pl < P ? pl : 0;
         DPPO_TRY(amap(&mp.a[0][pl], A.p[src], A));
         if (g.A2.p[0]) DPPO_TRY(amap(&mp.a[1][pl], g.A2.p[src], g.A2)); else mp.a[1][pl] = mp.a[0][pl];
-        if (!B_MN) DPPO_TRY(make_map(&mp.b[pl], B.p[src], B.mn, B.k, B.ld, BN, SBK));
-        else DPPO_TRY(make_map(&mp.b[pl], B.p[src], B.k, B.mn, B.ld, SBK, 64));
+        auto bmap = [&](CUtensorMap* m, const bf16* ptr, const Operand& o) -> int {
+            return B_MN ? make_map(m, ptr, o.k, o.mn, o.ld, SBK, 64) : make_map(m, ptr, o.mn, o.k, o.ld, BN, SBK);
+        };
+        DPPO_TRY(bmap(&mp.b[0][pl], B.p[src], B));
+        if (g.A2.p[0]) DPPO_TRY(bmap(&mp.b[1][pl], g.B2.p[src], g.B2)); else mp.b[1][pl] = mp.b[0][pl];
     }
     Params p;
     p.m_blocks = (g.M + SBM - 1) / SBM; p.n_blocks = (g.N + BN - 1) / BN;
@@ -354,7 +278,7 @@ static int launch_t(dppo_handle* h, cudaStream_t s, const Gemm& g) {
     p.kb_per_split = (p.kblocks + splits - 1) / splits;
     p.splits = (p.kblocks + p.kb_per_split - 1) / p.kb_per_split;
     p.epi = g.epi;
-    auto kern = split_gemm_kernel<BN, A_MN, B_MN, P>;
+    auto kern = split_gemm_kernel<BN, A_MN, B_MN, P, DUAL>;
     static bool attr_set_dev[64] = {};      // function attributes are per device
     bool& attr_set = attr_set_dev[h->device & 63];
     if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<BN, P>())); attr_set = true; }
@@ -374,16 +298,349 @@ static int launch_t(dppo_handle* h, cudaStream_t s, const Gemm& g) {
 static int launch(dppo_handle* h, cudaStream_t s, const Gemm& g) {
     const bool a = g.A.mn_major, b = g.B.mn_major;
     if (g.planes == 3) {
-        if (!a && b) return launch_t<128, false, true, 3>(h, s, g);
-        if (!a && !b && g.N <= 32) return launch_t<32, false, false, 3>(h, s, g);
+        if (!a && b) return launch_t<128, false, true, 3, true>(h, s, g);
+        if (!a && !b && g.N <= 32) return launch_t<32, false, false, 3, true>(h, s, g);
         DPPO_FAIL(-7, "split gemm: this 3-plane operand layout is not instantiated");
     }
-    if (!a && b) return launch_t<256, false, true, 2>(h, s, g);
-    if (!a && !b) return g.N <= 32 ? launch_t<32, false, false, 2>(h, s, g) : launch_t<256, false, false, 2>(h, s, g);
-    if (a && b) return g.N <= 64 ? launch_t<64, true, true, 2>(h, s, g) : launch_t<256, true, true, 2>(h, s, g);
+    if (g.dual) {
+        if (!a && b) return launch_t<128, false, true, 2, true>(h, s, g);
+        if (!a && !b && g.N <= 32) return launch_t<32, false, false, 2, true>(h, s, g);
+        DPPO_FAIL(-7, "split gemm: this dual-accumulator operand layout is not instantiated");
+    }
+    if (!a && b) return launch_t<256, false, true, 2, false>(h, s, g);
+    if (!a && !b) return g.N <= 32 ? launch_t<32, false, false, 2, false>(h, s, g) : launch_t<256, false, false, 2, false>(h, s, g);
+    if (a && b) return g.N <= 64 ? launch_t<64, true, true, 2, false>(h, s, g) : launch_t<256, true, true, 2, false>(h, s, g);
     DPPO_FAIL(-7, "split gemm: operand layout (A MN-major, B K-major) is not instantiated");
 }
 }  // namespace ts
+
+// =====================================================================================================================
+// The same plane GEMM on CTA PAIRS (cta_group::2) with a coalesced epilogue, for the layers whose output is the next GEMM's
+// operand (forward L0..L2, backward dv / dh1 / du).  What the single-CTA kernel above measured (ncu launch list,
+// profiles/r02_split_v1_launches.txt): it is bound by (a) TMA ingest - 96 KB per k-block for 1536 MMA cycles = 62 B/cycle
+// against the ~34 B/cycle an SM takes in - and (b) its thread-per-row epilogue, whose 16-byte stores touch 32 different lines
+// per warp instruction (a K = 64 layer took as long as a K = 512 one).  Here
+//   * a pair owns a 256 x BNP output tile; each CTA stages its own 128 A rows and HALF of the B tile per plane (P = 2, BNP = 256:
+//     64 KB per k-block and CTA = 42 B/cycle; P = 3 with two accumulators, BNP = 128: 72 KB for 1536 cycles);
+//   * the leader issues the 256-row tcgen05.mma for the pair, commits are multicast, both CTAs' TMA loads report to the
+//     leader's barriers (same scheme as tcp::dw_pair_kernel);
+//   * eight epilogue warps per CTA (two per TMEM lane quadrant, 32 columns each) convert a [128][64] column group to bf16
+//     planes in shared memory in the 128-byte-swizzled image a TMA store expects, and ONE thread stores each plane with
+//     cp.async.bulk.tensor: full-line writes, clipped at the matrix edge by the tensor map;
+//   * ReLU derivatives travel as bit masks [rows][N/32] (4 bytes per thread and group instead of re-reading an activation
+//     plane), Mish derivatives as two gate planes mish'(pre) written next to the activation by the forward epilogue.
+namespace tsp {
+using namespace tc;
+constexpr int PTHREADS = 320;         // warp 0: TMA, warp 1: MMA (leader) + TMEM alloc, warps 2..9: epilogue
+constexpr int SLOT = 16384;           // one [128 rows][64 columns] bf16 plane tile
+constexpr int NSLOT = 4;
+
+struct Epi {
+    int M, N;                                              // valid extents of the output
+    const float* bias; int act;                            // 0 none, 1 relu, 2 mish
+    const uint32_t* mask_in; uint32_t* mask_out; int ldm;  // ReLU bit masks [rows][ldm words]; word j = columns [32 j, 32 j + 32)
+    const bf16* gate_in[2]; int ldg;                       // Mish backward: *= gate_in[0] + gate_in[1]
+    int out_planes;                                        // 2 or 3 planes stored through maps.out
+    int gate_out;                                          // Mish forward: also store mish'(pre-activation) as two planes (maps.gate)
+};
+struct Params { int m_blocks, n_blocks, kblocks, ka_blocks; Epi epi; };
+struct Maps { CUtensorMap a[2][ts::MAXP], b[2][ts::MAXP], out[ts::MAXP], gate[2]; };
+
+template <int P, int BNP> __host__ __device__ constexpr int stage_bytes() { return P * (128 * 64 * 2 + (BNP / 2) * 64 * 2); }
+template <int P, int BNP> __host__ __device__ constexpr int stages() { return (227 * 1024 - NSLOT * SLOT - 2048) / stage_bytes<P, BNP>() > 4 ? 4 : (227 * 1024 - NSLOT * SLOT - 2048) / stage_bytes<P, BNP>(); }
+template <int P, int BNP> constexpr size_t smem_bytes() { return (size_t)stages<P, BNP>() * stage_bytes<P, BNP>() + NSLOT * SLOT + 1024 + 256; }
+
+__device__ __forceinline__ void epi_barrier8() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+template <bool B_MN, int P, bool DUAL, int BNP>
+__global__ void __launch_bounds__(PTHREADS, 1) pair_gemm_kernel(const __grid_constant__ Maps maps, const Params p) {
+    constexpr int STG = stages<P, BNP>();
+    constexpr int A_TILE = 128 * 64 * 2, B_TILE = (BNP / 2) * 64 * 2, STAGE = stage_bytes<P, BNP>();
+    constexpr int NACC = DUAL ? 2 : 1, ACC_COLS = NACC * BNP;
+    static_assert(2 * ACC_COLS <= 512, "accumulators exceed tensor memory");
+    static_assert(STG >= 2, "a stage must fit twice");
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* slots = smem + STG * STAGE;
+    uint64_t* bars = (uint64_t*)(slots + NSLOT * SLOT);
+    uint64_t* full = bars;                      // leader's: both CTAs' producers + their TMA bytes
+    uint64_t* empty = bars + STG;               // per CTA: multicast commit of the MMAs that read the stage
+    uint64_t* tfull = bars + 2 * STG;           // per CTA: multicast commit, accumulator complete
+    uint64_t* tempty = tfull + 2;               // leader's: the 16 epilogue warps of the pair drained the accumulator
+    uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = fc::cluster_ctarank();
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const int tiles = p.m_blocks * p.n_blocks;
+
+    if (warp == 0 && lane == 0) {
+        for (int pl = 0; pl < P; ++pl) { tma_prefetch_desc(&maps.a[0][pl]); tma_prefetch_desc(&maps.b[0][pl]); }
+        for (int i = 0; i < STG; ++i) { mbar_init(&full[i], 2); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 16); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    fc::cluster_sync_all();                     // barriers of both CTAs initialised before anything remote
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    fc::cluster_sync_all();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+    if (warp == 0) {
+        // ---- TMA producer (both CTAs): own 128 A rows, own half of the B tile, every plane; bytes and arrival go to the leader
+        int stage = 0; uint32_t phase = 0;
+        const uint32_t s_addr = smem_u32(smem), full_addr = smem_u32(full);
+        for (int tile = pair; tile < tiles; tile += npairs) {
+            const int m_blk = tile / p.n_blocks, n_blk = tile % p.n_blocks;
+            const int m0 = m_blk * 256 + (int)rank * 128, n0 = n_blk * BNP + (int)rank * (BNP / 2);
+            for (int kb = 0; kb < p.kblocks; ++kb) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                if (elect_one_lane()) {
+                    const uint32_t fb = full_addr + stage * 8;
+                    fc::mbar_expect_tx_cluster(fc::mapa_rank0(fb), (uint32_t)STAGE);
+                    const uint32_t sa = s_addr + stage * STAGE, sb = sa + P * A_TILE;
+                    const int seg = kb < p.ka_blocks ? 0 : 1;
+                    const int ka = (seg ? kb - p.ka_blocks : kb) * 64;
+#pragma unroll
+                    for (int pl = 0; pl < P; ++pl) {
+                        fc::tma_load_2d_pair(sa + pl * A_TILE, &maps.a[seg][pl], fb, ka, m0);
+                        if (!B_MN) fc::tma_load_2d_pair(sb + pl * B_TILE, &maps.b[seg][pl], fb, ka, n0);
+                        else {
+#pragma unroll
+                            for (int j = 0; j < BNP / 128; ++j) fc::tma_load_2d_pair(sb + pl * B_TILE + j * 8192, &maps.b[seg][pl], fb, n0 + j * 64, ka);
+                        }
+                    }
+                }
+                __syncwarp();
+                if (++stage == STG) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ---- MMA issuer: the leader only
+        if (rank == 0) {
+            constexpr uint32_t idesc = make_idesc(256, BNP, false, B_MN);
+            constexpr int NPROD = P == 3 ? 6 : 3;
+            constexpr int PA[6] = {2, 0, 1, 1, 0, 0}, PB[6] = {0, 2, 1, 0, 1, 0};       // P = 3: small terms first, A0 B0 last
+            constexpr int QA[3] = {1, 0, 0}, QB[3] = {0, 1, 0};                          // P = 2
+            int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+            for (int tile = pair; tile < tiles; tile += npairs) {
+                mbar_wait(&tempty[acc], acc_phase ^ 1);
+                tcgen05_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * ACC_COLS);
+                for (int kb = 0; kb < p.kblocks; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tcgen05_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * STAGE), sb = sa + P * A_TILE;
+                    if (elect_one_lane()) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            uint64_t da[P], db[P];
+#pragma unroll
+                            for (int pl = 0; pl < P; ++pl) {
+                                da[pl] = make_desc(sa + pl * A_TILE + k * 32, 16, 1024);
+                                db[pl] = B_MN ? make_desc(sb + pl * B_TILE + k * 2048, 8192, 1024) : make_desc(sb + pl * B_TILE + k * 32, 16, 1024);
+                            }
+#pragma unroll
+                            for (int q = 0; q < NPROD; ++q) {
+                                const int ia = P == 3 ? PA[q] : QA[q], ib = P == 3 ? PB[q] : QB[q];
+                                if (DUAL) {
+                                    const bool main = q == NPROD - 1;
+                                    tcp::umma_bf16_pair(tmem_d + (main ? 0u : (uint32_t)BNP), da[ia], db[ib], idesc, (kb > 0 || k > 0 || (!main && q > 0)) ? 1u : 0u);
+                                } else tcp::umma_bf16_pair(tmem_d, da[ia], db[ib], idesc, (kb > 0 || k > 0 || q > 0) ? 1u : 0u);
+                            }
+                        }
+                        fc::tcgen05_commit_pair(smem_u32(&empty[stage]));
+                    }
+                    __syncwarp();
+                    if (++stage == STG) { stage = 0; phase ^= 1; }
+                }
+                if (elect_one_lane()) fc::tcgen05_commit_pair(smem_u32(&tfull[acc]));
+                __syncwarp();
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ---- epilogue (both CTAs, 8 warps): own 128 rows x BNP columns in groups of 64 columns
+        const int quad = warp & 3, half = (warp - 2) >> 2;
+        const int rloc = quad * 32 + lane;
+        const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+        const bool store_thread = (warp == 2 && lane == 0);
+        const Epi& e = p.epi;
+        const uint32_t slot_addr = smem_u32(slots);
+        const uint32_t row_off = (uint32_t)rloc * 128u, sw = (uint32_t)(rloc & 7);
+        int acc = 0; uint32_t acc_phase = 0;
+        const uint32_t tempty_leader = fc::mapa_rank0(smem_u32(tempty));
+        for (int tile = pair; tile < tiles; tile += npairs) {
+            const int m_blk = tile / p.n_blocks, n_blk = tile % p.n_blocks;
+            const int row0 = m_blk * 256 + (int)rank * 128, m = row0 + rloc;
+            const bool row_ok = m < e.M;
+            mbar_wait(&tfull[acc], acc_phase);
+            tcgen05_fence_after();
+#pragma unroll 1
+            for (int g = 0; g < BNP / 64; ++g) {
+                const int n0 = n_blk * BNP + g * 64 + half * 32;              // this warp's 32 columns
+                uint32_t r[32];
+                tmem_ld32(tmem_base + lane_base + (uint32_t)(acc * ACC_COLS + g * 64 + half * 32), r);
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                if (DUAL) {
+                    tmem_ld32(tmem_base + lane_base + (uint32_t)(acc * ACC_COLS + BNP + g * 64 + half * 32), r);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(r[j]);
+                }
+                if (g == BNP / 64 - 1) {                                      // accumulator drained: hand it back before the math
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) fc::mbar_arrive_cluster(tempty_leader + acc * 8);
+                }
+                const bool col_ok = n0 < e.N;
+                if (e.bias && col_ok) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] += __ldg(e.bias + n0 + j);
+                }
+                float gt[32];
+                if (e.act == 1) {
+                    if (e.mask_out) {
+                        uint32_t bits = 0u;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) bits |= (v[j] > 0.f ? 1u : 0u) << j;
+                        if (row_ok && col_ok) e.mask_out[(size_t)m * e.ldm + (n0 >> 5)] = bits;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                } else if (e.act == 2) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) { float y; fc::mish_and_grad(v[j], y, gt[j]); v[j] = y; }
+                }
+                if (e.mask_in) {
+                    const uint32_t bits = (row_ok && col_ok) ? __ldg(e.mask_in + (size_t)m * e.ldm + (n0 >> 5)) : 0u;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = ((bits >> j) & 1u) ? v[j] : 0.f;
+                }
+                if (e.gate_in[0] && row_ok && col_ok) {
+                    const bf16* g0 = e.gate_in[0] + (size_t)m * e.ldg + n0; const bf16* g1 = e.gate_in[1] + (size_t)m * e.ldg + n0;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const uint4 uh = *reinterpret_cast<const uint4*>(g0 + q * 8), ul = *reinterpret_cast<const uint4*>(g1 + q * 8);
+                        const bf16* hb = reinterpret_cast<const bf16*>(&uh); const bf16* lb = reinterpret_cast<const bf16*>(&ul);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[q * 8 + j] *= __bfloat162float(hb[j]) + __bfloat162float(lb[j]);
+                    }
+                }
+                // the staging slots are free once the previous group's TMA stores have read them
+                if (store_thread) fc::tma_store_wait_read();
+                epi_barrier8();
+                const uint32_t c0 = (uint32_t)(half * 4);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    __align__(16) bf16 t[ts::MAXP][8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (P == 3) ts::split_bf16_3(v[q * 8 + j], t[0][j], t[1][j], t[2][j]); else ts::split_bf16(v[q * 8 + j], t[0][j], t[1][j]);
+                    }
+                    const uint32_t off = row_off + (((c0 + (uint32_t)q) ^ sw) << 4);
+#pragma unroll
+                    for (int pl = 0; pl < P; ++pl) {
+                        const uint4 u = *reinterpret_cast<const uint4*>(t[pl]);
+                        fc::st_shared_v4(slot_addr + pl * SLOT + off, u.x, u.y, u.z, u.w);
+                    }
+                    if (e.gate_out) {
+                        __align__(16) bf16 gh[8]; __align__(16) bf16 gl[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) ts::split_bf16(gt[q * 8 + j], gh[j], gl[j]);
+                        const uint4 u0 = *reinterpret_cast<const uint4*>(gh), u1 = *reinterpret_cast<const uint4*>(gl);
+                        fc::st_shared_v4(slot_addr + 2 * SLOT + off, u0.x, u0.y, u0.z, u0.w);
+                        fc::st_shared_v4(slot_addr + 3 * SLOT + off, u1.x, u1.y, u1.z, u1.w);
+                    }
+                }
+                fc::fence_async_smem();
+                epi_barrier8();
+                if (store_thread) {
+                    const int col = n_blk * BNP + g * 64;
+                    if (col < e.N) {
+                        for (int pl = 0; pl < e.out_planes; ++pl) fc::tma_store_2d(&maps.out[pl], slots + pl * SLOT, col, row0);
+                        if (e.gate_out) { fc::tma_store_2d(&maps.gate[0], slots + 2 * SLOT, col, row0); fc::tma_store_2d(&maps.gate[1], slots + 3 * SLOT, col, row0); }
+                    }
+                    fc::tma_store_commit();
+                }
+            }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        if (store_thread) fc::tma_store_wait_all();
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    fc::cluster_sync_all();                     // the peer may still be signalling our barriers / reading our B halves
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// output planes [M][N] (leading dimension ld) written by TMA; gate planes likewise
+struct Gemm {
+    ts::Operand A, A2, B, B2;      // A K-major; B K-major or MN-major; [A | A2] x [B ; B2] when A2.p[0] != nullptr
+    int planes, dual;              // 2 (single accumulator) or 3 with dual = 1
+    int M, N;
+    bf16* out[ts::MAXP]; int ld_out;
+    bf16* gate[2];
+    double alg_flops;
+    Epi epi;
+};
+
+template <bool B_MN, int P, bool DUAL, int BNP>
+static int launch_t(dppo_handle* h, cudaStream_t s, const Gemm& g) {
+    Maps mp;
+    for (int pl = 0; pl < ts::MAXP; ++pl) {
+        const int src = pl < P ? pl : 0;
+        DPPO_TRY(make_map(&mp.a[0][pl], g.A.p[src], g.A.mn, g.A.k, g.A.ld, 128, 64));
+        if (g.A2.p[0]) DPPO_TRY(make_map(&mp.a[1][pl], g.A2.p[src], g.A2.mn, g.A2.k, g.A2.ld, 128, 64)); else mp.a[1][pl] = mp.a[0][pl];
+        auto bmap = [&](CUtensorMap* m, const bf16* ptr, const ts::Operand& o) -> int {
+            return B_MN ? make_map(m, ptr, o.k, o.mn, o.ld, 64, 64) : make_map(m, ptr, o.mn, o.k, o.ld, BNP / 2, 64);
+        };
+        DPPO_TRY(bmap(&mp.b[0][pl], g.B.p[src], g.B));
+        if (g.A2.p[0]) DPPO_TRY(bmap(&mp.b[1][pl], g.B2.p[src], g.B2)); else mp.b[1][pl] = mp.b[0][pl];
+        DPPO_TRY(make_map(&mp.out[pl], g.out[pl < g.epi.out_planes ? pl : 0], g.M, g.N, g.ld_out, 128, 64));
+    }
+    for (int i = 0; i < 2; ++i) {
+        if (g.epi.gate_out) DPPO_TRY(make_map(&mp.gate[i], g.gate[i], g.M, g.N, g.ld_out, 128, 64)); else mp.gate[i] = mp.out[0];
+    }
+    Params p;
+    p.m_blocks = (g.M + 255) / 256; p.n_blocks = (g.N + BNP - 1) / BNP;
+    const int ka = (int)((g.A.k + 63) / 64), ka2 = g.A2.p[0] ? (int)((g.A2.k + 63) / 64) : 0;
+    p.kblocks = ka + ka2; p.ka_blocks = ka;
+    p.epi = g.epi;
+    auto kern = pair_gemm_kernel<B_MN, P, DUAL, BNP>;
+    static bool attr_set_dev[64] = {};      // function attributes are per device
+    bool& attr_set = attr_set_dev[h->device & 63];
+    if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<P, BNP>())); attr_set = true; }
+    const int tiles = p.m_blocks * p.n_blocks, npairs = h->sm_count / 2;
+    const int grid = 2 * (tiles < npairs ? tiles : npairs);
+    cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1; cfg.blockDim = dim3(PTHREADS); cfg.gridDim = dim3(grid); cfg.dynamicSmemBytes = smem_bytes<P, BNP>(); cfg.stream = s;
+    prof_begin(h, s);
+    cudaError_t le = cudaLaunchKernelEx(&cfg, kern, mp, p);
+    prof_end(h, s, g.alg_flops > 0 ? g.alg_flops : 2.0 * (double)g.M * (double)g.N * (double)(g.A.k + (g.A2.p[0] ? g.A2.k : 0)), 1);
+    h->launches++; h->tc_launches++;
+    if (le != cudaSuccess) DPPO_FAIL(-3, "split gemm (pair) launch failed: %s", cudaGetErrorString(le));
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) DPPO_FAIL(-3, "split gemm (pair) launch failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+static int launch(dppo_handle* h, cudaStream_t s, const Gemm& g) {
+    const bool b = g.B.mn_major;
+    if (g.planes == 3 && g.dual) return b ? launch_t<true, 3, true, 128>(h, s, g) : launch_t<false, 3, true, 128>(h, s, g);
+    if (g.planes == 2 && !g.dual) return b ? launch_t<true, 2, false, 256>(h, s, g) : launch_t<false, 2, false, 256>(h, s, g);
+    DPPO_FAIL(-7, "split gemm (pair): plane / accumulator combination not instantiated");
+}
+}  // namespace tsp
 
 // =====================================================================================================================
 // state: plane copies of the weights per net (3 planes each; the backward GEMMs read the first two)
@@ -541,30 +798,29 @@ static int ts_refresh_net(dppo_handle* h, int net, cudaStream_t s) {
 // ------------------------------------------------------------------ one residual MLP on N rows, every tensor as planes
 struct TsMlp {
     const TsNetW* W; int H, NO, act1, KP0, net, din;
-    int fp;                                // planes of the FORWARD GEMMs: 3 when the net (or what follows it) has kinks, else 2
+    int fp;                                // planes of the FORWARD GEMMs: 3 (+ two accumulators) when the net has kinks behind it, else 2
     const float *b0, *b1, *b2, *b3;
-    SplitT h0, a0, a1, v, pre0, pre1, dv, dh1, du;
+    SplitT h0, a0, a1, v, g0, g1, dv, dh1, du;   // g0 / g1: Mish gates mish'(pre-activation) of layer 0 / block.l1 (two planes)
+    uint32_t *m0, *m1;                     // ReLU bit masks [N][H/32] of layer 0 / block.l1
     float* out;                            // [N][NO] fp32
 };
-static void ts_mlp_clear(TsMlp& m) {
-    memset(&m, 0, sizeof(m));
-}
 static void ts_actor_mlp(const dppo_handle* h, int net, TsMlp& m) {
     const Geom& g = h->g; const float* w = h->net_w[net];
-    ts_mlp_clear(m);
+    memset(&m, 0, sizeof(m));
     m.W = &h->ts->net[net]; m.H = g.H; m.NO = g.A; m.act1 = h->cfg.actor_act + 1; m.KP0 = h->ts->KP0; m.net = net; m.din = g.Din;
-    m.fp = 3;                                                                        // ReLU kinks and / or the +-1 clip of x0 behind eps
+    m.fp = 3;                                                                        // ReLU kinks and the +-1 clip of x0 behind eps
     m.b0 = nullptr; m.b1 = w + g.ao.b1; m.b2 = w + g.ao.b2; m.b3 = w + g.ao.b3;      // b_in rides in W0's one-hot rows (bt table)
 }
 static void ts_critic_mlp(const dppo_handle* h, TsMlp& m) {
     const Geom& g = h->g; const float* w = h->net_w[DPPO_NET_CRITIC];
-    ts_mlp_clear(m);
+    memset(&m, 0, sizeof(m));
     m.W = &h->ts->net[DPPO_NET_CRITIC]; m.H = g.Hc; m.NO = 1; m.act1 = h->cfg.critic_act + 1; m.KP0 = h->ts->KP0; m.net = DPPO_NET_CRITIC; m.din = g.Do;
     m.fp = h->cfg.critic_act == DPPO_ACT_RELU ? 3 : 2;                               // Mish is smooth
     m.b0 = w + g.co.bin; m.b1 = w + g.co.b1; m.b2 = m.W->bias2; m.b3 = w + g.co.b3;
 }
 static size_t ts_mlp_ws_bytes(int N, int H, int KP0, bool mish, bool bwd) {
-    return 3 * (ws_bytes((size_t)N * KP0, 2) + 3 * ws_bytes((size_t)N * H, 2)) + 2 * ws_bytes((size_t)N * H, 2) * (size_t)((mish ? 2 : 0) + (bwd ? 3 : 0));
+    return 3 * (ws_bytes((size_t)N * KP0, 2) + 3 * ws_bytes((size_t)N * H, 2)) + 2 * ws_bytes((size_t)N * H, 2) * (size_t)((mish ? 2 : 0) + (bwd ? 3 : 0))
+         + 2 * ws_bytes((size_t)N * (H / 32), 4);
 }
 static SplitT ts_take(dppo_handle* h, size_t n, int planes) {
     SplitT t = split_null();
@@ -575,8 +831,9 @@ static void ts_mlp_take(dppo_handle* h, int N, TsMlp& m, bool bwd) {
     const size_t n = (size_t)N * m.H;
     m.h0 = ts_take(h, (size_t)N * m.KP0, 3);
     m.a0 = ts_take(h, n, 3); m.a1 = ts_take(h, n, 3); m.v = ts_take(h, n, 3);
-    if (m.act1 == 2) { m.pre0 = ts_take(h, n, 2); m.pre1 = ts_take(h, n, 2); }
+    if (m.act1 == 2) { m.g0 = ts_take(h, n, 2); m.g1 = ts_take(h, n, 2); }
     if (bwd) { m.dv = ts_take(h, n, 2); m.dh1 = ts_take(h, n, 2); m.du = ts_take(h, n, 2); }
+    m.m0 = ws_take<uint32_t>(h, (size_t)N * (m.H / 32)); m.m1 = ws_take<uint32_t>(h, (size_t)N * (m.H / 32));
 }
 static ts::Operand ts_op(const bf16* const* p, size_t off, bool mn_major, int64_t mn, int64_t k, int64_t ld) {
     ts::Operand o; o.mn_major = mn_major; o.mn = mn; o.k = k; o.ld = ld;
@@ -587,47 +844,52 @@ static ts::Operand tsK(const SplitT& t, int64_t mn, int64_t k, int64_t ld) { ret
 static ts::Operand tsMN(const SplitT& t, int64_t mn, int64_t k, int64_t ld) { return ts_op(t.p, 0, true, mn, k, ld); }
 static ts::Operand tswK(const TsW& w, size_t off, int64_t mn, int64_t k, int64_t ld) { return ts_op(w.p, off, false, mn, k, ld); }
 static ts::Operand tswMN(const TsW& w, size_t off, int64_t mn, int64_t k, int64_t ld) { return ts_op(w.p, off, true, mn, k, ld); }
-static ts::Gemm ts_gemm_of(ts::Operand A, ts::Operand B, int M, int N, int planes) {
+static ts::Gemm ts_gemm_of(ts::Operand A, ts::Operand B, int M, int N, int planes, int dual = 0) {
     ts::Gemm g; memset(&g, 0, sizeof(g));
-    g.A = A; g.B = B; g.M = M; g.N = N; g.splits = 1; g.planes = planes; g.epi.M = M; g.epi.N = N;
+    g.A = A; g.B = B; g.M = M; g.N = N; g.splits = 1; g.planes = planes; g.dual = dual; g.epi.M = M; g.epi.N = N;
     return g;
 }
-static void ts_epi_out(ts::Gemm& g, const SplitT& t, int planes, int ld) {
-    for (int pl = 0; pl < ts::MAXP; ++pl) g.epi.out[pl] = pl < planes ? t.p[pl] : nullptr;
-    g.epi.out_planes = planes; g.epi.ld_out = ld;
-}
 static int ts_run(dppo_handle* h, cudaStream_t s, const ts::Gemm& g) { const int r = ts::launch(h, s, g); return r < 0 ? r : 0; }
+// a layer on the pair kernel: out (planes) = epilogue(A B)
+static tsp::Gemm tsp_gemm_of(ts::Operand A, ts::Operand B, int M, int N, int planes, const SplitT& out, int out_planes, int ld_out) {
+    tsp::Gemm g; memset(&g, 0, sizeof(g));
+    g.A = A; g.B = B; g.M = M; g.N = N; g.planes = planes; g.dual = planes == 3 ? 1 : 0;
+    for (int pl = 0; pl < ts::MAXP; ++pl) g.out[pl] = out.p[pl];
+    g.ld_out = ld_out; g.epi.M = M; g.epi.N = N; g.epi.out_planes = out_planes;
+    return g;
+}
 
 static int ts_mlp_forward(dppo_handle* h, cudaStream_t s, const TsMlp& m, int N) {
     const int H = m.H, KP0 = m.KP0, P = m.fp; const TsNetW& W = *m.W;
     const size_t w0 = (size_t)H * H;
     // L0: a0 = act(h0 W0 (+ b0))
-    ts::Gemm g = ts_gemm_of(tsK(m.h0, N, KP0, KP0), tswMN(W.w2w0, w0, H, KP0, H), N, H, P);
-    g.epi.bias = m.b0; g.epi.act = m.act1; ts_epi_out(g, m.a0, P, H);
-    g.epi.pre[0] = m.pre0.p[0]; g.epi.pre[1] = m.pre0.p[1]; g.epi.ld_pre = H;
+    tsp::Gemm g = tsp_gemm_of(tsK(m.h0, N, KP0, KP0), tswMN(W.w2w0, w0, H, KP0, H), N, H, P, m.a0, P, H);
+    g.epi.bias = m.b0; g.epi.act = m.act1;
+    if (m.act1 == 1) { g.epi.mask_out = m.m0; g.epi.ldm = H / 32; } else if (m.act1 == 2) { g.epi.gate_out = 1; g.gate[0] = m.g0.p[0]; g.gate[1] = m.g0.p[1]; }
     g.alg_flops = 2.0 * N * (double)m.din * H;
-    DPPO_TRY(ts_run(h, s, g));
+    DPPO_TRY(tsp::launch(h, s, g));
     // L1: a1 = act(a0 W1 + b1)
-    g = ts_gemm_of(tsK(m.a0, N, H, H), tswMN(W.w1, 0, H, H, H), N, H, P);
-    g.epi.bias = m.b1; g.epi.act = m.act1; ts_epi_out(g, m.a1, P, H);
-    g.epi.pre[0] = m.pre1.p[0]; g.epi.pre[1] = m.pre1.p[1]; g.epi.ld_pre = H;
-    DPPO_TRY(ts_run(h, s, g));
-    // L2 + residual: v = [a1 | h0] [W2 ; W0] + b2 (+ b0)
-    g = ts_gemm_of(tsK(m.a1, N, H, H), tswMN(W.w2w0, 0, H, H + KP0, H), N, H, P);
-    g.A2 = tsK(m.h0, N, KP0, KP0);
-    g.epi.bias = m.b2; ts_epi_out(g, m.v, P, H);
+    g = tsp_gemm_of(tsK(m.a0, N, H, H), tswMN(W.w1, 0, H, H, H), N, H, P, m.a1, P, H);
+    g.epi.bias = m.b1; g.epi.act = m.act1;
+    if (m.act1 == 1) { g.epi.mask_out = m.m1; g.epi.ldm = H / 32; } else if (m.act1 == 2) { g.epi.gate_out = 1; g.gate[0] = m.g1.p[0]; g.gate[1] = m.g1.p[1]; }
+    DPPO_TRY(tsp::launch(h, s, g));
+    // L2 + residual: v = [a1 | h0] [W2 ; W0] + b2 (+ b0): the residual u = h0 W0 is re-accumulated instead of stored and re-read
+    g = tsp_gemm_of(tsK(m.a1, N, H, H), tswMN(W.w2w0, 0, H, H, H), N, H, P, m.v, P, H);
+    g.A2 = tsK(m.h0, N, KP0, KP0); g.B2 = tswMN(W.w2w0, w0, H, KP0, H);
+    g.epi.bias = m.b2;
     g.alg_flops = 2.0 * N * (double)H * H;                                       // the re-accumulated residual is not algorithmic work
-    DPPO_TRY(ts_run(h, s, g));
-    // L3: out = v W3 + b3
-    g = ts_gemm_of(tsK(m.v, N, H, H), tswK(W.w3t, 0, 32, H, H), N, m.NO, P);
-    g.epi.bias = m.b3; g.epi.out_f32 = m.out; g.epi.ld_f32 = m.NO;
-    DPPO_TRY(ts_run(h, s, g));
+    DPPO_TRY(tsp::launch(h, s, g));
+    // L3: out = v W3 + b3 (fp32, narrow: single-CTA kernel)
+    ts::Gemm o = ts_gemm_of(tsK(m.v, N, H, H), tswK(W.w3t, 0, 32, H, H), N, m.NO, P, P == 3 ? 1 : 0);
+    o.epi.bias = m.b3; o.epi.out_f32 = m.out; o.epi.ld_f32 = m.NO;
+    DPPO_TRY(ts_run(h, s, o));
     return 0;
 }
-// dW[out_rows][out_cols] = X^T D  (X [rows][M], D [rows][Nd], two planes each), split-K over the rows with a FIXED-order reduction
+// dW[out_rows][out_cols] = X^T D (+ X^T D2)  (X [rows][M], D [rows][Nd], two planes each), split-K over the rows with a FIXED-order reduction
 static int ts_dw(dppo_handle* h, cudaStream_t s, const SplitT& X, int M, const SplitT& D, int Nd, int rows, float* part, float* out, int out_rows, int out_cols,
-                 int ld_out, int alg_rows) {
+                 int ld_out, int alg_rows, const SplitT* D2 = nullptr) {
     ts::Gemm g = ts_gemm_of(tsMN(X, M, rows, M), tsMN(D, Nd, rows, Nd), M, Nd, 2);
+    if (D2) { g.A2 = g.A; g.B2 = tsMN(*D2, Nd, rows, Nd); }
     g.splits = tc_splits_for(h, M, Nd, rows);
     g.alg_flops = 2.0 * (double)rows * (double)alg_rows * (double)out_cols;
     g.epi.out_f32 = part; g.epi.ld_f32 = Nd; g.epi.split_stride = (size_t)M * Nd;
@@ -642,37 +904,31 @@ static int ts_colsum(dppo_handle* h, cudaStream_t s, const SplitT& D, int N, int
     int rpb = (N + nb - 1) / nb; nb = (N + rpb - 1) / rpb;
     if (ncols / 2 > 256 || (ncols & 1)) DPPO_FAIL(-7, "ts_colsum: %d columns unsupported", ncols);
     ts_colsum_kernel<<<nb, 256, 0, s>>>(D.p[0], D.p[1], N, ncols, rpb, part); TC_KCHECK(h);
-    reduce_partials_kernel<<<tc_nblk(ncols, 256), 256, 0, s>>>(part, nb, (size_t)ncols, (size_t)ncols, out, 1.f); TC_KCHECK(h);
+    tc_reduce_cols_kernel<<<tc_nblk(ncols, 8), 256, 0, s>>>(part, nb, (size_t)ncols, ncols, out); TC_KCHECK(h);
     return 0;
 }
 // backward of the residual MLP from dout [N][64] (two planes, zero padded).  Writes gradients of W1,b1,W2,b2,W3 into gnet at the
-// given offsets and dW0 (in h0 row order) into dw0 [KP0][H].
+// given offsets and dW0 (in h0 row order) into dw0 [KP0][H].  du excludes the residual path: dW0 = h0^T du + h0^T dv.
 static int ts_mlp_backward(dppo_handle* h, cudaStream_t s, const TsMlp& m, const SplitT& dout, int N, float* part,
                            float* gnet, size_t ow1, size_t ob1, size_t ow2, size_t ob2, size_t ow3, float* dw0) {
     const int H = m.H, KP0 = m.KP0; const TsNetW& W = *m.W;
     // dv = dout W3^T
-    ts::Gemm g = ts_gemm_of(tsK(dout, N, 64, 64), tswK(W.w3p, 0, H, 64, 128), N, H, 2);
-    ts_epi_out(g, m.dv, 2, H);
+    tsp::Gemm g = tsp_gemm_of(tsK(dout, N, 64, 64), tswK(W.w3p, 0, H, 64, 128), N, H, 2, m.dv, 2, H);
     g.alg_flops = 2.0 * N * (double)m.NO * H;
-    DPPO_TRY(ts_run(h, s, g));
+    DPPO_TRY(tsp::launch(h, s, g));
     // dh1 = (dv W2^T) * act'(h1)
-    g = ts_gemm_of(tsK(m.dv, N, H, H), tswK(W.w2w0, 0, H, H, H), N, H, 2);
-    if (m.act1 == 2) { g.epi.mask0 = m.pre1.p[0]; g.epi.mask1 = m.pre1.p[1]; } else { g.epi.mask0 = m.a1.p[0]; g.epi.mask1 = nullptr; }
-    g.epi.ldmask = H; g.epi.mask_mode = m.act1;
-    ts_epi_out(g, m.dh1, 2, H);
-    DPPO_TRY(ts_run(h, s, g));
-    // du = (dh1 W1^T) * act'(u) + dv
-    g = ts_gemm_of(tsK(m.dh1, N, H, H), tswK(W.w1, 0, H, H, H), N, H, 2);
-    if (m.act1 == 2) { g.epi.mask0 = m.pre0.p[0]; g.epi.mask1 = m.pre0.p[1]; } else { g.epi.mask0 = m.a0.p[0]; g.epi.mask1 = nullptr; }
-    g.epi.ldmask = H; g.epi.mask_mode = m.act1;
-    g.epi.add0 = m.dv.p[0]; g.epi.add1 = m.dv.p[1]; g.epi.ldadd = H;
-    ts_epi_out(g, m.du, 2, H);
-    DPPO_TRY(ts_run(h, s, g));
+    g = tsp_gemm_of(tsK(m.dv, N, H, H), tswK(W.w2w0, 0, H, H, H), N, H, 2, m.dh1, 2, H);
+    if (m.act1 == 1) { g.epi.mask_in = m.m1; g.epi.ldm = H / 32; } else if (m.act1 == 2) { g.epi.gate_in[0] = m.g1.p[0]; g.epi.gate_in[1] = m.g1.p[1]; g.epi.ldg = H; }
+    DPPO_TRY(tsp::launch(h, s, g));
+    // du = (dh1 W1^T) * act'(u)
+    g = tsp_gemm_of(tsK(m.dh1, N, H, H), tswK(W.w1, 0, H, H, H), N, H, 2, m.du, 2, H);
+    if (m.act1 == 1) { g.epi.mask_in = m.m0; g.epi.ldm = H / 32; } else if (m.act1 == 2) { g.epi.gate_in[0] = m.g0.p[0]; g.epi.gate_in[1] = m.g0.p[1]; g.epi.ldg = H; }
+    DPPO_TRY(tsp::launch(h, s, g));
     // weight gradients
     DPPO_TRY(ts_dw(h, s, m.v, H, dout, 64, N, part, gnet + ow3, H, m.NO, m.NO, H));
     DPPO_TRY(ts_dw(h, s, m.a1, H, m.dv, H, N, part, gnet + ow2, H, H, H, H));
     DPPO_TRY(ts_dw(h, s, m.a0, H, m.dh1, H, N, part, gnet + ow1, H, H, H, H));
-    DPPO_TRY(ts_dw(h, s, m.h0, KP0, m.du, H, N, part, dw0, KP0, H, H, m.din));
+    DPPO_TRY(ts_dw(h, s, m.h0, KP0, m.du, H, N, part, dw0, KP0, H, H, m.din, &m.dv));
     // bias gradients of block.l1 / block.l2 (the input-layer bias comes out of dw0's constant rows)
     DPPO_TRY(ts_colsum(h, s, m.dv, N, H, part, gnet + ob2));
     DPPO_TRY(ts_colsum(h, s, m.dh1, N, H, part, gnet + ob1));

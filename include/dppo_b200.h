@@ -258,6 +258,11 @@ int dppo_debug_tc_gemm(dppo_handle* h, const void* A, int a_mn, int64_t lda, con
  * Majorness flags as in dppo_debug_tc_gemm; out_f32 is [splits][M][N] partial sums (splits is clamped to the k-blocks). */
 int dppo_debug_split_gemm(dppo_handle* h, const float* A, int a_mn, int64_t lda, const float* B, int b_mn, int64_t ldb,
                           int M, int N, int K, int splits, int planes, float* out_f32, dppo_stream_t s);
+/* Test hook: the CTA-pair plane GEMM (ts_path.cuh)  out = act(A*B + bias)  on FP32 device operands: A [M][K] K-major, B as
+ * in dppo_debug_split_gemm, N a multiple of 64.  The kernel writes `planes` bf16 planes by TMA; out_f32 [M][N] receives
+ * their sum, mask_out (optional, act == 1) the ReLU bit masks [M][N/32]. */
+int dppo_debug_pair_gemm(dppo_handle* h, const float* A, int64_t lda, const float* B, int b_mn, int64_t ldb,
+                         int M, int N, int K, int planes, const float* bias, int act, float* out_f32, uint32_t* mask_out, dppo_stream_t s);
 /* Dev tool: per-CTA cycle counters of the fused chain kernel.  enable != 0 allocates them; out_host (optional)
  * receives HOST [16 launch slots][sm_count][8] (slot = chain launches since the last read, round robin) = {producer wait w_empty, mma wait x_full, mma wait w_full, mma total,
  * epilogue wait acc_full, epilogue generic layers, epilogue final layer, 0} of the last launch. */

@@ -79,6 +79,44 @@ def test_split_gemm_kernel_matches_float64(pair, a_mn, b_mn, M, N, K, splits, pl
     assert err < (2e-5 if planes == 2 else 3e-6), err
 
 
+@pytest.mark.parametrize("b_mn,M,N,K,planes,act", [
+    (1, 300, 512, 64, 3, 1),       # forward L0 (actor): one k-block, ReLU + bit masks, ragged M
+    (1, 1000, 512, 576, 3, 1),     # forward L1 / L2 (actor): three planes, two accumulators
+    (1, 515, 256, 320, 2, 2),      # critic forward: two planes, Mish
+    (0, 700, 512, 512, 2, 0),      # backward: K-major weights
+    (0, 260, 512, 64, 2, 0),       # dv = dout W3^T
+    (1, 40000, 512, 512, 3, 1),    # many tiles per pair (persistent loop, both accumulator buffers)
+])
+def test_pair_gemm_kernel_matches_float64(pair, b_mn, M, N, K, planes, act):
+    """tsp::pair_gemm_kernel (cta_group::2, TMA-store epilogue) on random fp32 operands vs float64."""
+    o, e = pair
+    rng = np.random.default_rng(M + 3 * N + 5 * K)
+    A = rng.standard_normal((M, K)).astype(np.float32)
+    B = (rng.standard_normal((K, N)) / np.sqrt(K)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+    a_dev = torch.from_numpy(A).cuda()
+    b_dev = torch.from_numpy(np.ascontiguousarray(B if b_mn else B.T)).cuda()
+    bias_dev = torch.from_numpy(bias).cuda()
+    out = torch.zeros(M, N, device="cuda")
+    mask = torch.zeros(M, N // 32, device="cuda", dtype=torch.int32)
+    n0 = e.tc_launch_count()
+    L.check(e.lib.dppo_debug_pair_gemm(e.h, C.c_void_p(a_dev.data_ptr()), K, C.c_void_p(b_dev.data_ptr()), b_mn, N if b_mn else K,
+                                       M, N, K, planes, C.c_void_p(bias_dev.data_ptr()), act, C.c_void_p(out.data_ptr()),
+                                       C.c_void_p(mask.data_ptr()) if act == 1 else None, e._stream()), "dppo_debug_pair_gemm")
+    torch.cuda.synchronize()
+    assert e.tc_launch_count() - n0 == 1
+    pre = A.astype(np.float64) @ B.astype(np.float64) + bias
+    want = np.maximum(pre, 0) if act == 1 else (pre * np.tanh(np.logaddexp(0, pre)) if act == 2 else pre)
+    err = np.abs(out.cpu().numpy() - want).max() / np.abs(want).max()
+    print(f"pair gemm planes={planes} b_mn={b_mn} act={act} {M}x{N}x{K}: rel err {err:.2e}")
+    assert err < (2e-5 if planes == 2 else 3e-6), err
+    if act == 1:
+        bits = mask.cpu().numpy().view(np.uint32)
+        got = ((bits[:, :, None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(M, N).astype(bool)
+        sure = np.abs(pre) > 1e-4                     # away from the kink both must agree
+        assert (got == (pre > 0))[sure].all()
+
+
 def test_split_forward_value_logprobs(pair):
     o, e = pair
     N = 3000
@@ -94,7 +132,7 @@ def test_split_forward_value_logprobs(pair):
     got = e.actor_forward(L.NET_ACTOR_FT, x.reshape(N, -1), t, _flat(obs))
     gv = e.value(_flat(obs))
     torch.cuda.synchronize()
-    assert e.tc_launch_count() - n0 == 8                       # four split GEMMs per network
+    assert e.tc_launch_count() - n0 == 8                       # four plane GEMMs per network
     err, errv = rel_err(got, want.reshape(N, -1)), rel_err(gv, wantv)
     print(f"bf16x3 eps rel err {err:.3e}, value rel err {errv:.3e}")
     assert err < 5e-6 and errv < 5e-5

@@ -14,7 +14,8 @@ task, N = (sys.argv[1] if len(sys.argv) > 1 else "hopper"), int(sys.argv[2]) if 
 modes = (sys.argv[3] if len(sys.argv) > 3 else "fp32,bf16x3").split(",")
 noclip = len(sys.argv) > 4 and sys.argv[4] == "noclip"
 o = O.make_oracle(task, seed=0, hyper=O.Hyper(denoised_clip_value=None) if noclip else None)
-batch = O.make_ppo_batch(o, N, pool=512 if N < 10000 else 4096, seed=3)
+seed = int(sys.argv[5]) if len(sys.argv) > 5 else 3
+batch = O.make_ppo_batch(o, N, pool=512 if N < 10000 else 4096, seed=seed)
 
 
 def ratio_of(b):
@@ -53,6 +54,7 @@ c = o.h.clip_ploss_coef
 dist = torch.minimum((r - (1 - c)).abs(), (r - (1 + c)).abs())
 print(f"{task} N={N}: ratio range [{float(r.min()):.4f}, {float(r.max()):.4f}], rows within 1e-4 / 1e-5 of the clip boundary: {int((dist < 1e-4).sum())} / {int((dist < 1e-5).sum())}")
 run(batch, "all rows")
-keep = dist >= 1e-4
-fb = tuple(t[keep] for t in batch)
-run(fb, f"{int(keep.sum())} rows, boundary rows dropped")
+if os.environ.get("FLIP_DROP") == "1":
+    keep = dist >= 1e-4
+    fb = tuple(t[keep] for t in batch)
+    run(fb, f"{int(keep.sum())} rows, boundary rows dropped")
