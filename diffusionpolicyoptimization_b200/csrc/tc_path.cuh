@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(256) tc_ppo_loss8_kernel(
     const float* __restrict__ advantages, const float* __restrict__ oldlogp, const float* __restrict__ newvalues,
     const float* __restrict__ advstats, const float* __restrict__ sch, PpoHyper hp, int N,
     bf16* __restrict__ depsb, bf16* __restrict__ dvalb, double* __restrict__ block_sums, float* __restrict__ col_part /*[blocks][A+1]*/,
-    const TcIdxView iv) {
+    const TcIdxView iv, bf16* __restrict__ depsb_lo = nullptr, bf16* __restrict__ dvalb_lo = nullptr /* second planes (DPPO_PREC_BF16X3) */) {
     const int tid = threadIdx.x, sub = tid & 7, lane = tid & 31, wrp = tid >> 5;
     const int r = blockIdx.x * LOSS8_ROWS + (tid >> 3);
     const int A = hp.A, a0 = sub * 4;
@@ -429,6 +429,14 @@ __global__ void __launch_bounds__(256) tc_ppo_loss8_kernel(
         uint2* drow = reinterpret_cast<uint2*>(depsb + (size_t)r * 64);
         drow[sub] = make_uint2(fc::pack_bf16(gq[0], gq[1]), fc::pack_bf16(gq[2], gq[3]));
         drow[8 + sub] = make_uint2(0u, 0u);
+        if (depsb_lo) {   // second plane: what the first one rounded away
+            float lo[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) lo[e] = gq[e] - __bfloat162float(__float2bfloat16(gq[e]));
+            uint2* lrow = reinterpret_cast<uint2*>(depsb_lo + (size_t)r * 64);
+            lrow[sub] = make_uint2(fc::pack_bf16(lo[0], lo[1]), fc::pack_bf16(lo[2], lo[3]));
+            lrow[8 + sub] = make_uint2(0u, 0u);
+        }
         if (sub == 0) {
             const float v = newvalues[r], ret = returns[srow];
             float vl, dv;
@@ -448,6 +456,10 @@ __global__ void __launch_bounds__(256) tc_ppo_loss8_kernel(
         // padded bf16 seed row [dvalue | 0..]: 16 bytes per lane
         uint4* vrow = reinterpret_cast<uint4*>(dvalb + (size_t)r * 64);
         vrow[sub] = sub == 0 ? make_uint4(fc::pack_bf16(dv_out, 0.f), 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+        if (dvalb_lo) {
+            uint4* lrow = reinterpret_cast<uint4*>(dvalb_lo + (size_t)r * 64);       // dv_out lives in the row's lane 0
+            lrow[sub] = sub == 0 ? make_uint4(fc::pack_bf16(dv_out - __bfloat162float(__float2bfloat16(dv_out)), 0.f), 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+        }
     }
     // ---- block reductions: rows of a warp (lanes differing in bits 3,4), then the 8 warps through shared memory
     __shared__ double red[5][8];
@@ -1161,6 +1173,38 @@ static int tc_ppo_chunk(dppo_handle* h, cudaStream_t s, int chunk, const float* 
     P.rows_done += n;
     return 0;
 }
+// Everything between the weight-gradient GEMM and AdamW in one launch (tc_ppo_tail_kernel): metric sums, output-layer bias
+// gradients from the loss kernel's column partials, hidden-layer bias gradients from the chains' per-row-block column sums
+// (cpa / cpc: [rows][2][H], slot 0 = dv -> db2, slot 1 = dh1 -> db1), time-embedding backward, dW0 scatters, critic input bias.
+static int tc_launch_tail(dppo_handle* h, cudaStream_t s, const double* bsum, int blocks_done, float inv_nglobal, float frac_local, const float* colb3,
+                          const float* cpa, int rows_a, const float* cpc, int rows_c, const float* dw0a, const float* dw0c) {
+    const Geom& g = h->g;
+    const size_t nA = g.ao.n, nC = g.co.n;
+    float* gr = h->grads;
+    const float* w = h->net_w[DPPO_NET_ACTOR_FT]; const ActorDerived& d = h->ad[DPPO_NET_ACTOR_FT];
+    const size_t sm = (size_t)(g.T * g.td * 3) * sizeof(float);
+    const size_t sm_staged = sm + (size_t)(g.T + g.td) * g.H * sizeof(float);
+    const bool staged = sm_staged <= 160 * 1024;
+    static bool attr_set_dev[64] = {};      // function attributes are per device
+    bool& attr_set = attr_set_dev[h->device & 63];
+    if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(tc_ppo_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr_set = true; }
+    TcTailArgs a;
+    const int nthr = 512, wpb = nthr / 32;
+    const int nb[8] = {1, tc_nblk(g.A + 1, wpb), tc_nblk(2 * g.H, wpb), tc_nblk(2 * g.Hc, wpb), 1 + (g.H + 127) / 128,
+                       tc_nblk((size_t)(g.A + g.Do) * g.H, nthr), tc_nblk((size_t)g.Do * g.Hc, nthr), tc_nblk(g.Hc, nthr)};
+    a.first[0] = 0;
+    for (int r = 0; r < 8; ++r) a.first[r + 1] = a.first[r] + nb[r];
+    a.bsum = bsum; a.blocks_done = blocks_done; a.inv_nglobal = inv_nglobal; a.frac_local = frac_local; a.metrics = gr + nA + nC;
+    a.colb3 = colb3; a.ncol3 = g.A + 1; a.b3a = gr + g.ao.b3; a.split3 = g.A; a.b3c = gr + nA + g.co.b3;
+    a.cpa = cpa; a.rows_a = rows_a; a.HA = g.H; a.b2a = gr + g.ao.b2; a.b1a = gr + g.ao.b1;
+    a.cpc = cpc; a.rows_c = rows_c; a.HC = g.Hc; a.b2c = gr + nA + g.co.b2; a.b1c = gr + nA + g.co.b1;
+    a.w = w; a.ao = g.ao; a.A = g.A; a.td = g.td; a.T = g.T; a.Do = g.Do; a.tb_staged = staged ? 1 : 0;
+    a.Gt = dw0a + (size_t)(g.A + g.Do) * g.H; a.sinemb = d.sinemb; a.thpre = d.thpre; a.temb = d.temb; a.gr = gr;
+    a.dw0a = dw0a; a.gwin_a = gr + g.ao.win; a.dw0c_obs = dw0c + (size_t)g.A * g.Hc; a.gwin_c = gr + nA + g.co.win;
+    a.dw0c_bias = dw0c + (size_t)(g.A + g.Do + g.T) * g.Hc; a.gbin_c = gr + nA + g.co.bin;
+    tc_ppo_tail_kernel<<<a.first[8], nthr, staged ? sm_staged : sm, s>>>(a); TC_KCHECK(h);
+    return 0;
+}
 static int tc_ppo_finish(dppo_handle* h, cudaStream_t s) {
     const Geom& g = h->g;
     const size_t nA = g.ao.n, nC = g.co.n;
@@ -1169,31 +1213,8 @@ static int tc_ppo_finish(dppo_handle* h, cudaStream_t s) {
     const bool defer = P.ma.fused && P.mc.fused && !h->deterministic;
     const float* w = h->net_w[DPPO_NET_ACTOR_FT]; const ActorDerived& d = h->ad[DPPO_NET_ACTOR_FT];
     const size_t sm = (size_t)(g.T * g.td * 3) * sizeof(float);
-    if (defer) {
-        // one launch for the eight independent small kernels between the grouped dW GEMM and AdamW
-        const size_t sm_staged = sm + (size_t)(g.T + g.td) * g.H * sizeof(float);
-        const bool staged = sm_staged <= 160 * 1024;
-        static bool attr_set_dev[64] = {};      // function attributes are per device
-    bool& attr_set = attr_set_dev[h->device & 63];
-        if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(tc_ppo_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr_set = true; }
-        TcTailArgs a;
-        const int nthr = 512, wpb = nthr / 32;
-        const int nb[8] = {1, tc_nblk(g.A + 1, wpb), tc_nblk(2 * g.H, wpb), tc_nblk(2 * g.Hc, wpb), 1 + (g.H + 127) / 128,
-                           tc_nblk((size_t)(g.A + g.Do) * g.H, nthr), tc_nblk((size_t)g.Do * g.Hc, nthr), tc_nblk(g.Hc, nthr)};
-        a.first[0] = 0;
-        for (int r = 0; r < 8; ++r) a.first[r + 1] = a.first[r] + nb[r];
-        a.bsum = P.bsum; a.blocks_done = P.blocks_done; a.inv_nglobal = P.hp.inv_nglobal; a.frac_local = (float)((double)P.N / (double)P.N_global); a.metrics = gr + nA + nC;
-        a.colb3 = P.colb3; a.ncol3 = g.A + 1; a.b3a = gr + g.ao.b3; a.split3 = g.A; a.b3c = gr + nA + g.co.b3;
-        const int rows = P.nchunks * h->sm_count;
-        a.cpa = P.cpa; a.rows_a = rows; a.HA = g.H; a.b2a = gr + g.ao.b2; a.b1a = gr + g.ao.b1;
-        a.cpc = P.cpc; a.rows_c = rows; a.HC = g.Hc; a.b2c = gr + nA + g.co.b2; a.b1c = gr + nA + g.co.b1;
-        a.w = w; a.ao = g.ao; a.A = g.A; a.td = g.td; a.T = g.T; a.Do = g.Do; a.tb_staged = staged ? 1 : 0;
-        a.Gt = P.dw0a + (size_t)(g.A + g.Do) * g.H; a.sinemb = d.sinemb; a.thpre = d.thpre; a.temb = d.temb; a.gr = gr;
-        a.dw0a = P.dw0a; a.gwin_a = gr + g.ao.win; a.dw0c_obs = P.dw0c + (size_t)g.A * g.Hc; a.gwin_c = gr + nA + g.co.win;
-        a.dw0c_bias = P.dw0c + (size_t)(g.A + g.Do + g.T) * g.Hc; a.gbin_c = gr + nA + g.co.bin;
-        tc_ppo_tail_kernel<<<a.first[8], nthr, staged ? sm_staged : sm, s>>>(a); TC_KCHECK(h);
-        return 0;
-    }
+    if (defer) return tc_launch_tail(h, s, P.bsum, P.blocks_done, P.hp.inv_nglobal, (float)((double)P.N / (double)P.N_global), P.colb3,
+                                     P.cpa, P.nchunks * h->sm_count, P.cpc, P.nchunks * h->sm_count, P.dw0a, P.dw0c);
     ppo_metrics_kernel<<<1, 256, 0, s>>>(P.bsum, P.blocks_done, P.hp.inv_nglobal, (float)((double)P.N / (double)P.N_global), gr + nA + nC); TC_KCHECK(h);
     // output-layer bias gradients = column sums of the seeds (per-block partials from the loss kernel)
     tc_reduce_cols_kernel<<<tc_nblk(g.A + 1, 8), 256, 0, s>>>(P.colb3, P.blocks_done, (size_t)(g.A + 1), g.A + 1, gr + g.ao.b3, g.A, gr + nA + g.co.b3); TC_KCHECK(h);

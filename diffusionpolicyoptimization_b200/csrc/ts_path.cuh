@@ -314,6 +314,9 @@ static int launch(dppo_handle* h, cudaStream_t s, const Gemm& g) {
 }
 }  // namespace ts
 
+struct SplitT { bf16* p[ts::MAXP]; };
+static inline SplitT split_null() { SplitT t; t.p[0] = t.p[1] = t.p[2] = nullptr; return t; }
+
 // =====================================================================================================================
 // The same plane GEMM on CTA PAIRS (cta_group::2) with a coalesced epilogue, for the layers whose output is the next GEMM's
 // operand (forward L0..L2, backward dv / dh1 / du).  What the single-CTA kernel above measured (ncu launch list,
@@ -342,6 +345,8 @@ struct Epi {
     const bf16* gate_in[2]; int ldg;                       // Mish backward: *= gate_in[0] + gate_in[1]
     int out_planes;                                        // 2 or 3 planes stored through maps.out
     int gate_out;                                          // Mish forward: also store mish'(pre-activation) as two planes (maps.gate)
+    float* colsum_part; int colsum_ld;                     // bias gradient: per 32-row block column sums of the fp32 result,
+                                                           // written to colsum_part[rowblock * colsum_ld + column] (rowblock = row / 32)
 };
 struct Params { int m_blocks, n_blocks, kblocks, ka_blocks; Epi epi; };
 struct Maps { CUtensorMap a[2][ts::MAXP], b[2][ts::MAXP], out[ts::MAXP], gate[2]; };
@@ -474,6 +479,9 @@ __global__ void __launch_bounds__(PTHREADS, 1) pair_gemm_kernel(const __grid_con
         const uint32_t row_off = (uint32_t)rloc * 128u, sw = (uint32_t)(rloc & 7);
         int acc = 0; uint32_t acc_phase = 0;
         const uint32_t tempty_leader = fc::mapa_rank0(smem_u32(tempty));
+        // two planes and no gate planes: the four slots hold two staging buffers, the TMA store of a group overlaps the next group's math
+        const bool dbuf = (P == 2) && !e.gate_out;
+        uint32_t gcount = 0;
         for (int tile = pair; tile < tiles; tile += npairs) {
             const int m_blk = tile / p.n_blocks, n_blk = tile % p.n_blocks;
             const int row0 = m_blk * 256 + (int)rank * 128, m = row0 + rloc;
@@ -532,8 +540,26 @@ __global__ void __launch_bounds__(PTHREADS, 1) pair_gemm_kernel(const __grid_con
                         for (int j = 0; j < 8; ++j) v[q * 8 + j] *= __bfloat162float(hb[j]) + __bfloat162float(lb[j]);
                     }
                 }
-                // the staging slots are free once the previous group's TMA stores have read them
-                if (store_thread) fc::tma_store_wait_read();
+                if (e.colsum_part) {
+                    // column sums over this warp's 32 rows by recursive halving: lane j ends with the sum of column n0 + j
+                    float cs[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) cs[j] = v[j];
+#pragma unroll
+                    for (int off = 16; off >= 1; off >>= 1) {
+#pragma unroll
+                        for (int i = 0; i < off; ++i) {
+                            const bool up = (lane & off) != 0;
+                            const float send = up ? cs[i] : cs[i + off], keep = up ? cs[i + off] : cs[i];
+                            cs[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                        }
+                    }
+                    if (col_ok && row0 + quad * 32 < e.M) e.colsum_part[(size_t)((row0 >> 5) + quad) * e.colsum_ld + n0 + lane] = cs[0];
+                }
+                // the staging slots are free once the TMA stores that last used them have read them
+                const uint32_t sbuf = dbuf ? (gcount & 1u) * 2u : 0u;
+                ++gcount;
+                if (store_thread) { if (dbuf) fc::tma_store_wait_read1(); else fc::tma_store_wait_read(); }
                 epi_barrier8();
                 const uint32_t c0 = (uint32_t)(half * 4);
 #pragma unroll
@@ -547,7 +573,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) pair_gemm_kernel(const __grid_con
 #pragma unroll
                     for (int pl = 0; pl < P; ++pl) {
                         const uint4 u = *reinterpret_cast<const uint4*>(t[pl]);
-                        fc::st_shared_v4(slot_addr + pl * SLOT + off, u.x, u.y, u.z, u.w);
+                        fc::st_shared_v4(slot_addr + (sbuf + pl) * SLOT + off, u.x, u.y, u.z, u.w);
                     }
                     if (e.gate_out) {
                         __align__(16) bf16 gh[8]; __align__(16) bf16 gl[8];
@@ -563,7 +589,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) pair_gemm_kernel(const __grid_con
                 if (store_thread) {
                     const int col = n_blk * BNP + g * 64;
                     if (col < e.N) {
-                        for (int pl = 0; pl < e.out_planes; ++pl) fc::tma_store_2d(&maps.out[pl], slots + pl * SLOT, col, row0);
+                        for (int pl = 0; pl < e.out_planes; ++pl) fc::tma_store_2d(&maps.out[pl], slots + (sbuf + pl) * SLOT, col, row0);
                         if (e.gate_out) { fc::tma_store_2d(&maps.gate[0], slots + 2 * SLOT, col, row0); fc::tma_store_2d(&maps.gate[1], slots + 3 * SLOT, col, row0); }
                     }
                     fc::tma_store_commit();
@@ -640,6 +666,249 @@ static int launch(dppo_handle* h, cudaStream_t s, const Gemm& g) {
     if (g.planes == 2 && !g.dual) return b ? launch_t<true, 2, false, 256>(h, s, g) : launch_t<false, 2, false, 256>(h, s, g);
     DPPO_FAIL(-7, "split gemm (pair): plane / accumulator combination not instantiated");
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Grouped weight-gradient GEMM on CTA pairs, two planes per operand:  out_p = X_p^T D_p (+ X2_p^T D2_p)  for up to 10 problems in
+// ONE launch (the plane version of tcp::dw_pair_kernel, same wave-balanced K splits).  Every (output tile, K split) item writes
+// its fp32 partial tile; dw_reduce_kernel sums an output's partials in a fixed order, so the gradients are bit-reproducible.
+constexpr int DSTAGES = 3, DMAXP = 10, DMAPS = 12;
+struct DwProb {
+    int m_blocks, n_blocks, nb_cta;   // 256-row output blocks; column blocks of nb_cta * 128; 64-column D boxes per CTA per k-block
+    int splits, kb_per_split, item_begin;
+    int kb_seg0, kb_total;            // k-blocks of the first (X, D) segment / in total (second segment: maps[map2])
+    int map2;
+    int M_valid, N_valid, ld_out, transposed;
+    float* out;
+};
+struct DwParams { int nprob, items; float* part; DwProb p[DMAXP]; };
+struct DwMaps { CUtensorMap a[DMAPS][2], b[DMAPS][2]; };
+constexpr size_t dw_smem_bytes() { return (size_t)DSTAGES * 65536 + 1024 + 256; }
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) dw_pair_kernel(const __grid_constant__ DwMaps maps, const DwParams gp) {
+    constexpr int A_TILE = 128 * 64 * 2, B_TILE = 128 * 64 * 2, STAGE = 2 * (A_TILE + B_TILE);
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = (uint64_t*)(smem + DSTAGES * STAGE);
+    uint64_t* full = bars; uint64_t* empty = bars + DSTAGES; uint64_t* tfull = bars + 2 * DSTAGES; uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = fc::cluster_ctarank();
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < DSTAGES; ++i) { mbar_init(&full[i], 2); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    fc::cluster_sync_all();
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    fc::cluster_sync_all();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+    auto decode = [&](int item, int& pi, int& m_blk, int& n_blk, int& split) {
+        pi = 0;
+        while (pi + 1 < gp.nprob && item >= gp.p[pi + 1].item_begin) ++pi;
+        const DwProb& P = gp.p[pi];
+        const int local = item - P.item_begin, per = P.m_blocks * P.n_blocks;
+        split = local / per; const int rem = local % per;
+        m_blk = rem / P.n_blocks; n_blk = rem % P.n_blocks;
+    };
+
+    if (warp == 0) {
+        int stage = 0; uint32_t phase = 0;
+        const uint32_t s_addr = smem_u32(smem), full_addr = smem_u32(full);
+        for (int item = pair; item < gp.items; item += npairs) {
+            int pi, m_blk, n_blk, split; decode(item, pi, m_blk, n_blk, split);
+            const DwProb& P = gp.p[pi];
+            const int kb0 = split * P.kb_per_split, kb1 = min(P.kb_total, kb0 + P.kb_per_split);
+            const uint32_t tx = (uint32_t)(2 * (A_TILE + P.nb_cta * 64 * 64 * 2));
+            const int m0 = m_blk * 256 + (int)rank * 128, n0 = n_blk * (P.nb_cta * 128) + (int)rank * (P.nb_cta * 64);
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                if (elect_one_lane()) {
+                    const uint32_t fb = full_addr + stage * 8;
+                    fc::mbar_expect_tx_cluster(fc::mapa_rank0(fb), tx);
+                    const int mi = kb < P.kb_seg0 ? pi : P.map2;
+                    const int kr = (kb < P.kb_seg0 ? kb : kb - P.kb_seg0) * 64;
+#pragma unroll
+                    for (int pl = 0; pl < 2; ++pl) {
+                        const uint32_t a = s_addr + stage * STAGE + pl * A_TILE, b = s_addr + stage * STAGE + 2 * A_TILE + pl * B_TILE;
+                        fc::tma_load_2d_pair(a, &maps.a[mi][pl], fb, m0, kr);
+                        fc::tma_load_2d_pair(a + 8192, &maps.a[mi][pl], fb, m0 + 64, kr);
+                        for (int j = 0; j < P.nb_cta; ++j) fc::tma_load_2d_pair(b + j * 8192, &maps.b[mi][pl], fb, n0 + j * 64, kr);
+                    }
+                }
+                __syncwarp();
+                if (++stage == DSTAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (rank == 0) {
+            int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+            for (int item = pair; item < gp.items; item += npairs) {
+                int pi, m_blk, n_blk, split; decode(item, pi, m_blk, n_blk, split);
+                const DwProb& P = gp.p[pi];
+                const int kb0 = split * P.kb_per_split, kb1 = min(P.kb_total, kb0 + P.kb_per_split);
+                const uint32_t idesc = make_idesc(256, P.nb_cta * 128, true, true);
+                mbar_wait(&tempty[acc], acc_phase ^ 1);
+                tcgen05_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 256);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tcgen05_fence_after();
+                    const uint32_t a0 = smem_u32(smem + stage * STAGE), b0 = a0 + 2 * A_TILE;
+                    if (elect_one_lane()) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t da0 = make_desc(a0 + k * 2048, 8192, 1024), da1 = make_desc(a0 + A_TILE + k * 2048, 8192, 1024);
+                            const uint64_t db0 = make_desc(b0 + k * 2048, 8192, 1024), db1 = make_desc(b0 + B_TILE + k * 2048, 8192, 1024);
+                            tcp::umma_bf16_pair(tmem_d, da1, db0, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                            tcp::umma_bf16_pair(tmem_d, da0, db1, idesc, 1u);
+                            tcp::umma_bf16_pair(tmem_d, da0, db0, idesc, 1u);
+                        }
+                        fc::tcgen05_commit_pair(smem_u32(&empty[stage]));
+                    }
+                    __syncwarp();
+                    if (++stage == DSTAGES) { stage = 0; phase ^= 1; }
+                }
+                if (elect_one_lane()) fc::tcgen05_commit_pair(smem_u32(&tfull[acc]));
+                __syncwarp();
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // epilogue (both CTAs): own 128 rows x the N tile of the item's partial [256][256] fp32
+        const int quad = warp & 3;
+        int acc = 0; uint32_t acc_phase = 0;
+        const uint32_t tempty_leader = fc::mapa_rank0(smem_u32(tempty));
+        for (int item = pair; item < gp.items; item += npairs) {
+            int pi, m_blk, n_blk, split; decode(item, pi, m_blk, n_blk, split);
+            const DwProb& P = gp.p[pi];
+            mbar_wait(&tfull[acc], acc_phase);
+            tcgen05_fence_after();
+            float* dst = gp.part + (size_t)item * 65536 + (size_t)((int)rank * 128 + quad * 32 + lane) * 256;
+            const int ntile = P.nb_cta * 128;
+#pragma unroll 1
+            for (int c = 0; c < ntile / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * 256 + c * 32), r);
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    *reinterpret_cast<float4*>(dst + c * 32 + q * 4) = make_float4(__uint_as_float(r[q * 4]), __uint_as_float(r[q * 4 + 1]), __uint_as_float(r[q * 4 + 2]), __uint_as_float(r[q * 4 + 3]));
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) fc::mbar_arrive_cluster(tempty_leader + acc * 8);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    fc::cluster_sync_all();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+// out[m][n] (or out[n][m] when transposed) = sum over the problem's K splits of its partial tiles, in split order
+__global__ void __launch_bounds__(256) dw_reduce_kernel(const DwParams gp, const int* __restrict__ elem_begin) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int pi = 0;
+    while (pi + 1 < gp.nprob && i >= elem_begin[pi + 1]) ++pi;
+    if (i >= elem_begin[gp.nprob]) return;
+    const DwProb& P = gp.p[pi];
+    const int local = i - elem_begin[pi];
+    // the fastest index follows the output's memory order
+    const int m = P.transposed ? local % P.M_valid : local / P.N_valid, n = P.transposed ? local / P.M_valid : local % P.N_valid;
+    const int ntile = P.nb_cta * 128, per = P.m_blocks * P.n_blocks;
+    const int tile = (m >> 8) * P.n_blocks + n / ntile;
+    const float* src = gp.part + (size_t)(P.item_begin + tile) * 65536 + (size_t)(m & 255) * 256 + (n % ntile);
+    float acc = 0.f;
+    for (int sidx = 0; sidx < P.splits; ++sidx) acc += src[(size_t)sidx * per * 65536];
+    if (P.transposed) P.out[(size_t)n * P.ld_out + m] = acc; else P.out[(size_t)m * P.ld_out + n] = acc;
+}
+
+// one problem: out = X^T D (+ X2^T D2), X [rows][M], D [rows][Nd] (two planes each); transposed: out[n][m] (ld_out = row length of that layout)
+struct DwDesc { SplitT X; int M; SplitT D; int Nd; SplitT X2, D2; float* out; int M_valid, N_valid, ld_out, transposed; double alg_flops; };
+
+static int launch_dw_group(dppo_handle* h, cudaStream_t s, const DwDesc* d, int n, int rows, float* part, size_t part_floats, int* elem_begin_dev) {
+    if (n < 1 || n > DMAXP) DPPO_FAIL(-1, "launch_dw_group: bad problem count %d", n);
+    DwMaps maps; DwParams gp; memset(&gp, 0, sizeof(gp));
+    gp.nprob = n; gp.part = part;
+    const int kblocks = (rows + 63) / 64;
+    const int npairs = h->sm_count / 2;
+    double w[DMAXP]; int tiles[DMAXP]; int nmap = n;
+    for (int i = 0; i < n; ++i) {
+        DwProb& P = gp.p[i];
+        if (d[i].M % 64 || d[i].Nd % 64) DPPO_FAIL(-7, "launch_dw_group: operand widths must be multiples of 64");
+        for (int pl = 0; pl < 2; ++pl) {
+            DPPO_TRY(make_map(&maps.a[i][pl], d[i].X.p[pl], rows, d[i].M, d[i].M, 64, 64));
+            DPPO_TRY(make_map(&maps.b[i][pl], d[i].D.p[pl], rows, d[i].Nd, d[i].Nd, 64, 64));
+        }
+        P.kb_seg0 = kblocks; P.kb_total = kblocks; P.map2 = i;
+        if (d[i].X2.p[0]) {
+            if (nmap >= DMAPS) DPPO_FAIL(-7, "launch_dw_group: too many second segments");
+            for (int pl = 0; pl < 2; ++pl) {
+                DPPO_TRY(make_map(&maps.a[nmap][pl], d[i].X2.p[pl], rows, d[i].M, d[i].M, 64, 64));
+                DPPO_TRY(make_map(&maps.b[nmap][pl], d[i].D2.p[pl], rows, d[i].Nd, d[i].Nd, 64, 64));
+            }
+            P.map2 = nmap++; P.kb_total = 2 * kblocks;
+        }
+        P.m_blocks = (d[i].M + 255) / 256;
+        const int nb64 = (d[i].Nd + 63) / 64;
+        P.nb_cta = nb64 <= 2 ? 1 : 2;
+        P.n_blocks = (nb64 + 2 * P.nb_cta - 1) / (2 * P.nb_cta);
+        P.M_valid = d[i].M_valid; P.N_valid = d[i].N_valid; P.ld_out = d[i].ld_out; P.out = d[i].out; P.transposed = d[i].transposed;
+        tiles[i] = P.m_blocks * P.n_blocks;
+        w[i] = (P.nb_cta == 2 ? 1.0 : 0.75) * P.kb_total;              // k-block time of a 128-wide tile: 48 KB staged per CTA instead of 64 KB
+    }
+    for (int i = nmap; i < DMAPS; ++i) for (int pl = 0; pl < 2; ++pl) { maps.a[i][pl] = maps.a[0][0]; maps.b[i][pl] = maps.b[0][0]; }
+    // K splits: the smallest per-item budget for which all items fit the pairs in ONE wave (bisection), at least 4 k-blocks per item
+    auto items_for = [&](double budget) { int it = 0; for (int i = 0; i < n; ++i) { int sp = (int)ceil(w[i] / budget); if (sp < 1) sp = 1; it += tiles[i] * sp; } return it; };
+    double lo = 4.0, hi = 2.0 * kblocks;
+    if (items_for(lo) <= npairs) hi = lo;
+    for (int it = 0; it < 40 && hi - lo > 0.25; ++it) { const double mid = 0.5 * (lo + hi); if (items_for(mid) <= npairs) hi = mid; else lo = mid; }
+    int items = 0; double flops = 0; int eb[DMAXP + 1];
+    eb[0] = 0;
+    for (int i = 0; i < n; ++i) {
+        DwProb& P = gp.p[i];
+        int splits = (int)ceil(w[i] / hi);
+        if (splits < 1) splits = 1;
+        if (splits > P.kb_total) splits = P.kb_total;
+        P.kb_per_split = (P.kb_total + splits - 1) / splits;
+        P.splits = (P.kb_total + P.kb_per_split - 1) / P.kb_per_split;
+        P.item_begin = items; items += tiles[i] * P.splits;
+        flops += d[i].alg_flops;
+        eb[i + 1] = eb[i] + P.M_valid * P.N_valid;
+    }
+    gp.items = items;
+    if ((size_t)items * 65536 > part_floats) DPPO_FAIL(-7, "launch_dw_group: partial buffer too small (%d items)", items);
+    CUDA_TRY(cudaMemcpyAsync(elem_begin_dev, eb, (n + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
+    static bool attr_set_dev[64] = {};      // function attributes are per device
+    bool& attr_set = attr_set_dev[h->device & 63];
+    if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(dw_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dw_smem_bytes())); attr_set = true; }
+    const int grid = 2 * (items < npairs ? items : npairs);
+    cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1; cfg.blockDim = dim3(NUM_THREADS); cfg.gridDim = dim3(grid); cfg.dynamicSmemBytes = dw_smem_bytes(); cfg.stream = s;
+    prof_begin(h, s);
+    cudaError_t le = cudaLaunchKernelEx(&cfg, dw_pair_kernel, maps, gp);
+    prof_end(h, s, flops, 1);
+    h->launches++; h->tc_launches++;
+    if (le != cudaSuccess) DPPO_FAIL(-3, "grouped dW (plane pair) launch failed: %s", cudaGetErrorString(le));
+    dw_reduce_kernel<<<(eb[n] + 255) / 256, 256, 0, s>>>(gp, elem_begin_dev);
+    h->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) DPPO_FAIL(-3, "grouped dW (plane pair) launch failed: %s", cudaGetErrorString(e));
+    return 0;
+}
 }  // namespace tsp
 
 // =====================================================================================================================
@@ -651,8 +920,6 @@ struct TsNetW {
     int H;
 };
 struct TsState { TsNetW net[4]; int KP0; };
-struct SplitT { bf16* p[ts::MAXP]; };
-static inline SplitT split_null() { SplitT t; t.p[0] = t.p[1] = t.p[2] = nullptr; return t; }
 
 __device__ __forceinline__ void ts_put(const TsW& W, size_t i, float v) {
     bf16 a, b, c; ts::split_bf16_3(v, a, b, c);
@@ -907,34 +1174,37 @@ static int ts_colsum(dppo_handle* h, cudaStream_t s, const SplitT& D, int N, int
     tc_reduce_cols_kernel<<<tc_nblk(ncols, 8), 256, 0, s>>>(part, nb, (size_t)ncols, ncols, out); TC_KCHECK(h);
     return 0;
 }
-// backward of the residual MLP from dout [N][64] (two planes, zero padded).  Writes gradients of W1,b1,W2,b2,W3 into gnet at the
-// given offsets and dW0 (in h0 row order) into dw0 [KP0][H].  du excludes the residual path: dW0 = h0^T du + h0^T dv.
-static int ts_mlp_backward(dppo_handle* h, cudaStream_t s, const TsMlp& m, const SplitT& dout, int N, float* part,
-                           float* gnet, size_t ow1, size_t ob1, size_t ow2, size_t ob2, size_t ow3, float* dw0) {
-    const int H = m.H, KP0 = m.KP0; const TsNetW& W = *m.W;
-    // dv = dout W3^T
+// backward chain of the residual MLP from dout [N][64] (two planes, zero padded): dv = dout W3^T, dh1 = (dv W2^T) . act'(h1),
+// du = (dh1 W1^T) . act'(u).  du excludes the residual path: dW0 = h0^T du + h0^T dv.
+// cpart [ceil(N/32)][2][H]: per 32-row block column sums of dv (slot 0 = db2) and dh1 (slot 1 = db1), written by the epilogues
+static int ts_mlp_backward_dx(dppo_handle* h, cudaStream_t s, const TsMlp& m, const SplitT& dout, int N, float* cpart) {
+    const int H = m.H; const TsNetW& W = *m.W;
     tsp::Gemm g = tsp_gemm_of(tsK(dout, N, 64, 64), tswK(W.w3p, 0, H, 64, 128), N, H, 2, m.dv, 2, H);
     g.alg_flops = 2.0 * N * (double)m.NO * H;
+    g.epi.colsum_part = cpart; g.epi.colsum_ld = 2 * H;
     DPPO_TRY(tsp::launch(h, s, g));
-    // dh1 = (dv W2^T) * act'(h1)
     g = tsp_gemm_of(tsK(m.dv, N, H, H), tswK(W.w2w0, 0, H, H, H), N, H, 2, m.dh1, 2, H);
+    g.epi.colsum_part = cpart + H; g.epi.colsum_ld = 2 * H;
     if (m.act1 == 1) { g.epi.mask_in = m.m1; g.epi.ldm = H / 32; } else if (m.act1 == 2) { g.epi.gate_in[0] = m.g1.p[0]; g.epi.gate_in[1] = m.g1.p[1]; g.epi.ldg = H; }
     DPPO_TRY(tsp::launch(h, s, g));
-    // du = (dh1 W1^T) * act'(u)
     g = tsp_gemm_of(tsK(m.dh1, N, H, H), tswK(W.w1, 0, H, H, H), N, H, 2, m.du, 2, H);
     if (m.act1 == 1) { g.epi.mask_in = m.m0; g.epi.ldm = H / 32; } else if (m.act1 == 2) { g.epi.gate_in[0] = m.g0.p[0]; g.epi.gate_in[1] = m.g0.p[1]; g.epi.ldg = H; }
     DPPO_TRY(tsp::launch(h, s, g));
-    // weight gradients
-    DPPO_TRY(ts_dw(h, s, m.v, H, dout, 64, N, part, gnet + ow3, H, m.NO, m.NO, H));
-    DPPO_TRY(ts_dw(h, s, m.a1, H, m.dv, H, N, part, gnet + ow2, H, H, H, H));
-    DPPO_TRY(ts_dw(h, s, m.a0, H, m.dh1, H, N, part, gnet + ow1, H, H, H, H));
-    DPPO_TRY(ts_dw(h, s, m.h0, KP0, m.du, H, N, part, dw0, KP0, H, H, m.din, &m.dv));
-    // bias gradients of block.l1 / block.l2 (the input-layer bias comes out of dw0's constant rows)
-    DPPO_TRY(ts_colsum(h, s, m.dv, N, H, part, gnet + ob2));
-    DPPO_TRY(ts_colsum(h, s, m.dh1, N, H, part, gnet + ob1));
     return 0;
 }
-
+// the four weight-gradient products of one net for the grouped pair kernel; the narrow layer-0 product is handed over as
+// du^T h0 + dv^T h0 (wide operand on M, output written transposed into dw0 [KP0][H])
+static void ts_mlp_dw_descs(const TsMlp& m, const SplitT& dout, int N, float* gnet, size_t ow1, size_t ow2, size_t ow3, float* dw0, tsp::DwDesc* d) {
+    const int H = m.H, KP0 = m.KP0; const double r = (double)N; const SplitT none = split_null();
+    d[0] = tsp::DwDesc{m.a1, H, m.dv, H, none, none, gnet + ow2, H, H, H, 0, 2.0 * r * H * H};
+    d[1] = tsp::DwDesc{m.a0, H, m.dh1, H, none, none, gnet + ow1, H, H, H, 0, 2.0 * r * H * H};
+    d[2] = tsp::DwDesc{m.du, H, m.h0, KP0, m.dv, m.h0, dw0, H, KP0, H, 1, 2.0 * r * m.din * H};
+    d[3] = tsp::DwDesc{m.v, H, dout, 64, none, none, gnet + ow3, H, m.NO, m.NO, 0, 2.0 * r * H * m.NO};
+}
+static size_t ts_part_floats(const dppo_handle* h, int H) {
+    const size_t a = tc_part_floats(h, H), b = (size_t)(h->sm_count / 2 + 1) * 65536;
+    return a > b ? a : b;
+}
 // ------------------------------------------------------------------ forward-only programs
 static size_t ts_actor_forward_ws(const dppo_handle* h, int N) { return ts_mlp_ws_bytes(N, h->g.H, h->ts->KP0, h->cfg.actor_act == DPPO_ACT_MISH, false); }
 // eps[N][A] = actor(x, t, obs); appends to the workspace (the caller may hold pointers below ws.used)
@@ -965,32 +1235,9 @@ static int ts_value(dppo_handle* h, cudaStream_t s, const float* obs, int N, flo
 }
 
 // ------------------------------------------------------------------ gradients
-// actor backward from deps [N][A] fp32: fills gnet[0 : nA]
-static int ts_actor_grads(dppo_handle* h, cudaStream_t s, int net, const TsMlp& m, const float* deps, const SplitT& depsb, int N, float* part, float* dw0, float* gnet) {
-    const Geom& g = h->g; const float* w = h->net_w[net]; const ActorDerived& d = h->ad[net];
-    DPPO_TRY(ts_mlp_backward(h, s, m, depsb, N, part, gnet, g.ao.w1, g.ao.b1, g.ao.w2, g.ao.b2, g.ao.w3, dw0));
-    DPPO_TRY(colsum(h, s, deps, g.A, N, g.A, nullptr, 1, part, gnet + g.ao.b3));
-    // dw0 rows [A+Do, A+Do+T) are the per-t column sums of du: the gradient of the bt table
-    const size_t sm = (size_t)(g.T * g.td * 3) * sizeof(float);
-    time_backward_kernel<<<1, 512, sm, s>>>(w, g.ao, g.A, g.td, g.H, g.T, dw0 + (size_t)(g.A + g.Do) * g.H, d.sinemb, d.thpre, d.temb, gnet);
-    TC_KCHECK(h);
-    unpack_dw0_kernel<<<tc_nblk((size_t)(g.A + g.Do) * g.H, 256), 256, 0, s>>>(dw0, g.A, g.td, g.Do, g.H, gnet + g.ao.win);
-    TC_KCHECK(h);
-    return 0;
-}
-static int ts_critic_grads(dppo_handle* h, cudaStream_t s, const TsMlp& m, const float* dval, const SplitT& dvalb, int N, float* part, float* dw0, float* gnet) {
-    const Geom& g = h->g;
-    DPPO_TRY(ts_mlp_backward(h, s, m, dvalb, N, part, gnet, g.co.w1, g.co.b1, g.co.w2, g.co.b2, g.co.w3, dw0));
-    DPPO_TRY(colsum(h, s, dval, 1, N, 1, nullptr, 1, part, gnet + g.co.b3));
-    unpack_dw0_kernel<<<tc_nblk((size_t)g.Do * g.Hc, 256), 256, 0, s>>>(dw0 + (size_t)g.A * g.Hc, 0, 0, g.Do, g.Hc, gnet + g.co.win);
-    TC_KCHECK(h);
-    // the ones column of h0 collects the input-layer bias gradient
-    CUDA_TRY(cudaMemcpyAsync(gnet + g.co.bin, dw0 + (size_t)(g.A + g.Do + g.T) * g.Hc, g.Hc * sizeof(float), cudaMemcpyDeviceToDevice, s));
-    return 0;
-}
-
 // PPODiffusion.c_loss + tape.gradient (diffusion_ppo.py:32-132, train_ppo_diffusion_agent.py:340-346).  Leaves
-// [actor_ft grads | critic grads | 8 metrics] in h->grads.  The loss itself is the fp32 parity path's kernel.
+// [actor_ft grads | critic grads | 8 metrics] in h->grads.  16 plane-GEMM launches + 6 small kernels:
+// adv-stats (second stream) | h0 pack | 4 + 4 forward | loss | 3 + 3 backward | grouped dW + reduce | tail.
 static int ts_ppo_step(dppo_handle* h, cudaStream_t s, const float* obs, const float* prev, const float* nxt, const int32_t* inds,
                        const float* returns, const float* oldvalues, const float* advantages, const float* oldlogp,
                        int N, int64_t N_global, float adv_mean, float adv_std) {
@@ -998,11 +1245,14 @@ static int ts_ppo_step(dppo_handle* h, cudaStream_t s, const float* obs, const f
     const size_t nA = g.ao.n, nC = g.co.n;
     float* gr = h->grads;
     const bool amish = h->cfg.actor_act == DPPO_ACT_MISH, cmish = h->cfg.critic_act == DPPO_ACT_MISH;
-    const int nlb = tc_nblk(N, 128);
-    const size_t pf = tc_part_floats(h, g.H);
+    const bool loss8 = (g.A % 4 == 0) && g.A <= 32 && ((((uintptr_t)prev | (uintptr_t)nxt | (uintptr_t)oldlogp) & 15) == 0);   // float4 row reads
+    const int nlb = loss8 ? tc_nblk(N, LOSS8_ROWS) : tc_nblk(N, 128);
+    const int nrb = (N + 31) / 32;
+    const size_t pf = ts_part_floats(h, g.H);
     const size_t need = ts_mlp_ws_bytes(N, g.H, KP0, amish, true) + ts_mlp_ws_bytes(N, g.Hc, KP0, cmish, true)
                       + 2 * ws_bytes((size_t)N * g.A, 4) + 2 * ws_bytes(N, 4) + 4 * ws_bytes((size_t)N * 64, 2)
-                      + ws_bytes(pf, 4) + ws_bytes((size_t)KP0 * g.H, 4) + ws_bytes((size_t)KP0 * g.Hc, 4) + ws_bytes((size_t)nlb * 5, 8);
+                      + ws_bytes(pf, 4) + ws_bytes((size_t)KP0 * g.H, 4) + ws_bytes((size_t)KP0 * g.Hc, 4) + ws_bytes((size_t)nlb * 5, 8) + ws_bytes(16, 4)
+                      + ws_bytes((size_t)nlb * (g.A + 1), 4) + ws_bytes((size_t)nrb * 2 * g.H, 4) + ws_bytes((size_t)nrb * 2 * g.Hc, 4);
     DPPO_TRY(ws_reserve(h, need, s));
     TsMlp ma, mc; ts_actor_mlp(h, DPPO_NET_ACTOR_FT, ma); ts_critic_mlp(h, mc);
     ts_mlp_take(h, N, ma, true); ts_mlp_take(h, N, mc, true);
@@ -1012,28 +1262,70 @@ static int ts_ppo_step(dppo_handle* h, cudaStream_t s, const float* obs, const f
     float* part = ws_take<float>(h, pf);
     float* dw0a = ws_take<float>(h, (size_t)KP0 * g.H); float* dw0c = ws_take<float>(h, (size_t)KP0 * g.Hc);
     double* bsum = ws_take<double>(h, (size_t)nlb * 5);
+    int* ebeg = ws_take<int>(h, 16);
+    float* colb3 = ws_take<float>(h, (size_t)nlb * (g.A + 1));
+    float* cpa = ws_take<float>(h, (size_t)nrb * 2 * g.H); float* cpc = ws_take<float>(h, (size_t)nrb * 2 * g.Hc);
     ma.out = eps; mc.out = val;
-    if (adv_std < 0.f) { adv_stats_kernel<<<1, 1024, 0, s>>>(advantages, N, h->scalars); TC_KCHECK(h); }
+    // only the loss kernel reads the advantage statistics: they are computed on the second stream, next to the forward GEMMs
+    cudaStream_t st = s;
+    const bool side = adv_std < 0.f && !h->prof_on;
+    if (side) {
+        if (!h->aux_stream) {
+            CUDA_TRY(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
+            for (int i = 0; i < 2; ++i) CUDA_TRY(cudaEventCreateWithFlags(&h->aux_ev[i], cudaEventDisableTiming));
+        }
+        CUDA_TRY(cudaEventRecord(h->aux_ev[0], s)); CUDA_TRY(cudaStreamWaitEvent(h->aux_stream, h->aux_ev[0], 0));
+        st = h->aux_stream;
+    }
+    if (adv_std < 0.f) { adv_stats_kernel<<<1, 1024, 0, st>>>(advantages, N, h->scalars); TC_KCHECK(h); }
     else { set_scalars_kernel<<<1, 1, 0, s>>>(h->scalars, adv_mean, adv_std); TC_KCHECK(h); }
+    if (side) CUDA_TRY(cudaEventRecord(h->aux_ev[1], h->aux_stream));
     // h0 straight from (prev, obs, K-1-inds): tconst = -(K) flags "t = K-1-trow[r]"; the critic reads the same tile (its x / one-hot rows of W0 are zero)
     ts_pack_h0_kernel<<<tc_nblk((size_t)N * (KP0 / 8), 256), 256, 0, s>>>(prev, obs, inds, -g.K, N, g.A, g.Do, g.T, KP0, 1, ma.h0, 0);
     TC_KCHECK(h);
     mc.h0 = ma.h0;
     DPPO_TRY(ts_mlp_forward(h, s, ma, N));
     DPPO_TRY(ts_mlp_forward(h, s, mc, N));
+    if (side) CUDA_TRY(cudaStreamWaitEvent(s, h->aux_ev[1], 0));
     PpoHyper hp;
     hp.A = g.A; hp.Da = h->cfg.action_dim; hp.K = g.K; hp.T = g.T; hp.reward_horizon = h->cfg.reward_horizon; hp.norm_adv = h->cfg.norm_adv;
     hp.dcv = h->cfg.denoised_clip_value; hp.min_lp_std = h->cfg.min_logprob_denoising_std;
     hp.lp_lo = h->cfg.logprob_clip_lo; hp.lp_hi = h->cfg.logprob_clip_hi; hp.gamma_d = h->cfg.gamma_denoising;
     hp.clip_coef = h->cfg.clip_ploss_coef; hp.clip_base = h->cfg.clip_ploss_coef_base; hp.clip_rate = h->cfg.clip_ploss_coef_rate;
     hp.clip_v = h->cfg.clip_vloss_coef; hp.vf_coef = h->cfg.vf_coef; hp.inv_nglobal = 1.0f / (float)N_global;
-    ppo_loss_kernel<<<nlb, 128, 0, s>>>(prev, nxt, eps, inds, returns, oldvalues, advantages, oldlogp, val, h->scalars, h->sched, hp, N, deps, dval, bsum);
-    TC_KCHECK(h);
-    ppo_metrics_kernel<<<1, 256, 0, s>>>(bsum, nlb, hp.inv_nglobal, (float)((double)N / (double)N_global), gr + nA + nC); TC_KCHECK(h);
-    ts_pad64_kernel<<<tc_nblk((size_t)N * 8, 256), 256, 0, s>>>(deps, N, g.A, depsb.p[0], depsb.p[1]); TC_KCHECK(h);
-    ts_pad64_kernel<<<tc_nblk((size_t)N * 8, 256), 256, 0, s>>>(dval, N, 1, dvalb.p[0], dvalb.p[1]); TC_KCHECK(h);
-    DPPO_TRY(ts_actor_grads(h, s, DPPO_NET_ACTOR_FT, ma, deps, depsb, N, part, dw0a, gr));
-    DPPO_TRY(ts_critic_grads(h, s, mc, dval, dvalb, N, part, dw0c, gr + nA));
+    const float frac_local = (float)((double)N / (double)N_global);
+    if (loss8) {
+        // loss, metric partial sums, the two-plane padded gradient seeds and the output-bias column partials in one pass
+        TcIdxView iv; memset(&iv, 0, sizeof(iv));
+        tc_ppo_loss8_kernel<<<nlb, 256, 0, s>>>(prev, nxt, eps, inds, returns, oldvalues, advantages, oldlogp, val, h->scalars, h->sched, hp, N,
+                                               depsb.p[0], dvalb.p[0], bsum, colb3, iv, depsb.p[1], dvalb.p[1]);
+        TC_KCHECK(h);
+    } else {
+        ppo_loss_kernel<<<nlb, 128, 0, s>>>(prev, nxt, eps, inds, returns, oldvalues, advantages, oldlogp, val, h->scalars, h->sched, hp, N, deps, dval, bsum);
+        TC_KCHECK(h);
+        ts_pad64_kernel<<<tc_nblk((size_t)N * 8, 256), 256, 0, s>>>(deps, N, g.A, depsb.p[0], depsb.p[1]); TC_KCHECK(h);
+        ts_pad64_kernel<<<tc_nblk((size_t)N * 8, 256), 256, 0, s>>>(dval, N, 1, dvalb.p[0], dvalb.p[1]); TC_KCHECK(h);
+    }
+    // both backward chains, then ONE grouped launch with the eight weight-gradient products of actor and critic
+    DPPO_TRY(ts_mlp_backward_dx(h, s, ma, depsb, N, cpa));
+    DPPO_TRY(ts_mlp_backward_dx(h, s, mc, dvalb, N, cpc));
+    tsp::DwDesc dd[8];
+    ts_mlp_dw_descs(ma, depsb, N, gr, g.ao.w1, g.ao.w2, g.ao.w3, dw0a, dd);
+    ts_mlp_dw_descs(mc, dvalb, N, gr + nA, g.co.w1, g.co.w2, g.co.w3, dw0c, dd + 4);
+    DPPO_TRY(tsp::launch_dw_group(h, s, dd, 8, N, part, pf, ebeg));
+    if (loss8) return tc_launch_tail(h, s, bsum, nlb, hp.inv_nglobal, frac_local, colb3, cpa, nrb, cpc, nrb, dw0a, dw0c);
+    // (unaligned / wide action rows) the same pieces as separate launches
+    ppo_metrics_kernel<<<1, 256, 0, s>>>(bsum, nlb, hp.inv_nglobal, frac_local, gr + nA + nC); TC_KCHECK(h);
+    DPPO_TRY(colsum(h, s, deps, g.A, N, g.A, nullptr, 1, part, gr + g.ao.b3));
+    DPPO_TRY(colsum(h, s, dval, 1, N, 1, nullptr, 1, part, gr + nA + g.co.b3));
+    tc_reduce_cols_kernel<<<tc_nblk(2 * g.H, 8), 256, 0, s>>>(cpa, nrb, (size_t)2 * g.H, 2 * g.H, gr + g.ao.b2, g.H, gr + g.ao.b1); TC_KCHECK(h);
+    tc_reduce_cols_kernel<<<tc_nblk(2 * g.Hc, 8), 256, 0, s>>>(cpc, nrb, (size_t)2 * g.Hc, 2 * g.Hc, gr + nA + g.co.b2, g.Hc, gr + nA + g.co.b1); TC_KCHECK(h);
+    const float* w = h->net_w[DPPO_NET_ACTOR_FT]; const ActorDerived& d = h->ad[DPPO_NET_ACTOR_FT];
+    const size_t sm = (size_t)(g.T * g.td * 3) * sizeof(float);
+    time_backward_kernel<<<1 + (g.H + 127) / 128, 512, sm, s>>>(w, g.ao, g.A, g.td, g.H, g.T, dw0a + (size_t)(g.A + g.Do) * g.H, d.sinemb, d.thpre, d.temb, gr); TC_KCHECK(h);
+    unpack_dw0_kernel<<<tc_nblk((size_t)(g.A + g.Do) * g.H, 256), 256, 0, s>>>(dw0a, g.A, g.td, g.Do, g.H, gr + g.ao.win); TC_KCHECK(h);
+    unpack_dw0_kernel<<<tc_nblk((size_t)g.Do * g.Hc, 256), 256, 0, s>>>(dw0c + (size_t)g.A * g.Hc, 0, 0, g.Do, g.Hc, gr + nA + g.co.win); TC_KCHECK(h);
+    CUDA_TRY(cudaMemcpyAsync(gr + nA + g.co.bin, dw0c + (size_t)(g.A + g.Do + g.T) * g.Hc, g.Hc * sizeof(float), cudaMemcpyDeviceToDevice, s));
     return 0;
 }
 
@@ -1044,9 +1336,11 @@ static int ts_pretrain_grads(dppo_handle* h, cudaStream_t s, const float* action
     const size_t nA = g.ao.n; float* gr = h->grads;
     const size_t ne = (size_t)N * g.A;
     const int nlb = tc_nblk(ne, 256);
-    const size_t pf = tc_part_floats(h, g.H);
+    const int nrb = (N + 31) / 32;
+    const size_t pf = ts_part_floats(h, g.H);
     const size_t need = ts_mlp_ws_bytes(N, g.H, KP0, h->cfg.actor_act == DPPO_ACT_MISH, true) + 4 * ws_bytes(ne, 4) + ws_bytes(N, 4)
-                      + 2 * ws_bytes((size_t)N * 64, 2) + ws_bytes(pf, 4) + ws_bytes((size_t)KP0 * g.H, 4) + ws_bytes(nlb, 8);
+                      + 2 * ws_bytes((size_t)N * 64, 2) + ws_bytes(pf, 4) + ws_bytes((size_t)KP0 * g.H, 4) + ws_bytes(nlb, 8) + ws_bytes(16, 4)
+                      + ws_bytes((size_t)nrb * 2 * g.H, 4);
     DPPO_TRY(ws_reserve(h, need, s));
     TsMlp ma; ts_actor_mlp(h, DPPO_NET_ACTOR, ma);
     ts_mlp_take(h, N, ma, true);
@@ -1056,6 +1350,8 @@ static int ts_pretrain_grads(dppo_handle* h, cudaStream_t s, const float* action
     float* part = ws_take<float>(h, pf);
     float* dw0 = ws_take<float>(h, (size_t)KP0 * g.H);
     double* bsum = ws_take<double>(h, nlb);
+    int* ebeg = ws_take<int>(h, 16);
+    float* cpa = ws_take<float>(h, (size_t)nrb * 2 * g.H);
     ma.out = eps;
     pretrain_prep_kernel<<<tc_nblk(ne, 256), 256, 0, s>>>(actions, t_in, noise_in, N, g.A, g.T, h->sched, seed, offset, row_offset, trow, noise, xn); TC_KCHECK(h);
     ts_pack_h0_kernel<<<tc_nblk((size_t)N * (KP0 / 8), 256), 256, 0, s>>>(xn, obs, trow, 0, N, g.A, g.Do, g.T, KP0, 1, ma.h0, 0); TC_KCHECK(h);
@@ -1064,6 +1360,15 @@ static int ts_pretrain_grads(dppo_handle* h, cudaStream_t s, const float* action
     mse_loss_kernel<<<nlb, 256, 0, s>>>(eps, noise, ne, scale, deps, bsum); TC_KCHECK(h);
     sum_blocks_kernel<<<1, 256, 0, s>>>(bsum, nlb, scale, gr + nA); TC_KCHECK(h);
     ts_pad64_kernel<<<tc_nblk((size_t)N * 8, 256), 256, 0, s>>>(deps, N, g.A, depsb.p[0], depsb.p[1]); TC_KCHECK(h);
-    DPPO_TRY(ts_actor_grads(h, s, DPPO_NET_ACTOR, ma, deps, depsb, N, part, dw0, gr));
+    DPPO_TRY(ts_mlp_backward_dx(h, s, ma, depsb, N, cpa));
+    tsp::DwDesc dd[4];
+    ts_mlp_dw_descs(ma, depsb, N, gr, g.ao.w1, g.ao.w2, g.ao.w3, dw0, dd);
+    DPPO_TRY(tsp::launch_dw_group(h, s, dd, 4, N, part, pf, ebeg));
+    tc_reduce_cols_kernel<<<tc_nblk(2 * g.H, 8), 256, 0, s>>>(cpa, nrb, (size_t)2 * g.H, 2 * g.H, gr + g.ao.b2, g.H, gr + g.ao.b1); TC_KCHECK(h);
+    DPPO_TRY(colsum(h, s, deps, g.A, N, g.A, nullptr, 1, part, gr + g.ao.b3));
+    const float* w = h->net_w[DPPO_NET_ACTOR]; const ActorDerived& d = h->ad[DPPO_NET_ACTOR];
+    const size_t sm = (size_t)(g.T * g.td * 3) * sizeof(float);
+    time_backward_kernel<<<1 + (g.H + 127) / 128, 512, sm, s>>>(w, g.ao, g.A, g.td, g.H, g.T, dw0 + (size_t)(g.A + g.Do) * g.H, d.sinemb, d.thpre, d.temb, gr); TC_KCHECK(h);
+    unpack_dw0_kernel<<<tc_nblk((size_t)(g.A + g.Do) * g.H, 256), 256, 0, s>>>(dw0, g.A, g.td, g.Do, g.H, gr + g.ao.win); TC_KCHECK(h);
     return 0;
 }
