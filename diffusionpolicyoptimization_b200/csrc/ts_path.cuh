@@ -1266,27 +1266,31 @@ static int ts_ppo_step(dppo_handle* h, cudaStream_t s, const float* obs, const f
     float* colb3 = ws_take<float>(h, (size_t)nlb * (g.A + 1));
     float* cpa = ws_take<float>(h, (size_t)nrb * 2 * g.H); float* cpc = ws_take<float>(h, (size_t)nrb * 2 * g.Hc);
     ma.out = eps; mc.out = val;
-    // only the loss kernel reads the advantage statistics: they are computed on the second stream, next to the forward GEMMs
-    cudaStream_t st = s;
-    const bool side = adv_std < 0.f && !h->prof_on;
+    // The critic's GEMMs are independent of the actor's until the loss (and again until the weight gradients) and their tiles are
+    // short (K = 256: epilogue-latency-bound), while every persistent GEMM leaves SMs idle in its last wave: the critic (and the
+    // advantage statistics, which only the loss kernel reads) run on a second stream and fill the actor kernels' tails.
+    // (not while the per-kernel profile is on: its event brackets are meant to time each kernel running alone)
+    const bool side = h->overlap_chains && !h->prof_on;
+    cudaStream_t sc = s;
     if (side) {
         if (!h->aux_stream) {
             CUDA_TRY(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
             for (int i = 0; i < 2; ++i) CUDA_TRY(cudaEventCreateWithFlags(&h->aux_ev[i], cudaEventDisableTiming));
         }
-        CUDA_TRY(cudaEventRecord(h->aux_ev[0], s)); CUDA_TRY(cudaStreamWaitEvent(h->aux_stream, h->aux_ev[0], 0));
-        st = h->aux_stream;
+        sc = h->aux_stream;
     }
-    if (adv_std < 0.f) { adv_stats_kernel<<<1, 1024, 0, st>>>(advantages, N, h->scalars); TC_KCHECK(h); }
-    else { set_scalars_kernel<<<1, 1, 0, s>>>(h->scalars, adv_mean, adv_std); TC_KCHECK(h); }
-    if (side) CUDA_TRY(cudaEventRecord(h->aux_ev[1], h->aux_stream));
+    auto fork = [&]() -> int { if (side) { CUDA_TRY(cudaEventRecord(h->aux_ev[0], s)); CUDA_TRY(cudaStreamWaitEvent(sc, h->aux_ev[0], 0)); } return 0; };
+    auto join = [&]() -> int { if (side) { CUDA_TRY(cudaEventRecord(h->aux_ev[1], sc)); CUDA_TRY(cudaStreamWaitEvent(s, h->aux_ev[1], 0)); } return 0; };
     // h0 straight from (prev, obs, K-1-inds): tconst = -(K) flags "t = K-1-trow[r]"; the critic reads the same tile (its x / one-hot rows of W0 are zero)
     ts_pack_h0_kernel<<<tc_nblk((size_t)N * (KP0 / 8), 256), 256, 0, s>>>(prev, obs, inds, -g.K, N, g.A, g.Do, g.T, KP0, 1, ma.h0, 0);
     TC_KCHECK(h);
     mc.h0 = ma.h0;
+    DPPO_TRY(fork());
+    if (adv_std < 0.f) { adv_stats_kernel<<<1, 1024, 0, sc>>>(advantages, N, h->scalars); TC_KCHECK(h); }
+    else { set_scalars_kernel<<<1, 1, 0, sc>>>(h->scalars, adv_mean, adv_std); TC_KCHECK(h); }
     DPPO_TRY(ts_mlp_forward(h, s, ma, N));
-    DPPO_TRY(ts_mlp_forward(h, s, mc, N));
-    if (side) CUDA_TRY(cudaStreamWaitEvent(s, h->aux_ev[1], 0));
+    DPPO_TRY(ts_mlp_forward(h, sc, mc, N));
+    DPPO_TRY(join());
     PpoHyper hp;
     hp.A = g.A; hp.Da = h->cfg.action_dim; hp.K = g.K; hp.T = g.T; hp.reward_horizon = h->cfg.reward_horizon; hp.norm_adv = h->cfg.norm_adv;
     hp.dcv = h->cfg.denoised_clip_value; hp.min_lp_std = h->cfg.min_logprob_denoising_std;
@@ -1307,8 +1311,10 @@ static int ts_ppo_step(dppo_handle* h, cudaStream_t s, const float* obs, const f
         ts_pad64_kernel<<<tc_nblk((size_t)N * 8, 256), 256, 0, s>>>(dval, N, 1, dvalb.p[0], dvalb.p[1]); TC_KCHECK(h);
     }
     // both backward chains, then ONE grouped launch with the eight weight-gradient products of actor and critic
+    DPPO_TRY(fork());
     DPPO_TRY(ts_mlp_backward_dx(h, s, ma, depsb, N, cpa));
-    DPPO_TRY(ts_mlp_backward_dx(h, s, mc, dvalb, N, cpc));
+    DPPO_TRY(ts_mlp_backward_dx(h, sc, mc, dvalb, N, cpc));
+    DPPO_TRY(join());
     tsp::DwDesc dd[8];
     ts_mlp_dw_descs(ma, depsb, N, gr, g.ao.w1, g.ao.w2, g.ao.w3, dw0a, dd);
     ts_mlp_dw_descs(mc, dvalb, N, gr + nA, g.co.w1, g.co.w2, g.co.w3, dw0c, dd + 4);
