@@ -161,6 +161,9 @@ struct dppo_handle {
     unsigned long long* flags = nullptr;             // [8] epoch written by each peer
     float* peer_grads[2][8] = {}; unsigned long long* peer_flags[8] = {}; int peers_attached = 0;
     unsigned long long epoch = 0;
+    int* comm_status = nullptr;                      // device: raised by a peer barrier that timed out (lives in `scalars`)
+    long long peer_timeout_cycles = 0;
+    const int* skip_update = nullptr;                // device flag of the step in flight: non-zero = leave weights / moments untouched (bad minibatch indices)
     int64_t launches = 0;
     int64_t tc_launches = 0;
     int w0p_dirty[4] = {1, 1, 1, 1};  // ActorDerived::w0p is stale (rebuilt on demand by the FFMA layer-0 GEMM)
@@ -186,12 +189,13 @@ struct dppo_handle {
     std::vector<int> prof_cls;          // kernel class of each pair: 0 fused chain <H = 512>, 1 tcgen05 GEMM, 2 FFMA SGEMM, 3 fused chain <H = 256>
     size_t prof_used = 0;
     double prof_flops[4] = {0, 0, 0, 0}, prof_ms_acc[4] = {0, 0, 0, 0}; int64_t prof_launches[4] = {0, 0, 0, 0};
+    double prof_exec[4] = {0, 0, 0, 0};   // flops the tensor pipe executed (plane modes issue 3 or 6 products per algorithmic multiply-add)
 };
 
 int ws_reserve(dppo_handle* h, size_t bytes, cudaStream_t s);
 // profile bracket: call prof_begin before and prof_end after a GEMM-class launch
 void prof_begin(dppo_handle* h, cudaStream_t s);
-void prof_end(dppo_handle* h, cudaStream_t s, double flops, int cls);
+void prof_end(dppo_handle* h, cudaStream_t s, double flops, int cls, double exec_flops = -1.0);   // exec_flops: tensor-pipe flops actually issued (default: = flops)
 template <typename T> static inline T* ws_take(dppo_handle* h, size_t count) {
     size_t bytes = (count * sizeof(T) + 255) / 256 * 256;
     T* p = (T*)(h->ws.base + h->ws.used);

@@ -139,17 +139,17 @@ void prof_begin(dppo_handle* h, cudaStream_t s) {
     }
     cudaEventRecord(h->prof_ev[h->prof_used], s);
 }
-void prof_end(dppo_handle* h, cudaStream_t s, double flops, int cls) {
+void prof_end(dppo_handle* h, cudaStream_t s, double flops, int cls, double exec_flops) {
     if (!h->prof_on) return;
     cudaEventRecord(h->prof_ev[h->prof_used + 1], s);
     h->prof_cls[h->prof_used / 2] = cls;
-    h->prof_used += 2; h->prof_launches[cls] += 1; h->prof_flops[cls] += flops;
+    h->prof_used += 2; h->prof_launches[cls] += 1; h->prof_flops[cls] += flops; h->prof_exec[cls] += exec_flops >= 0 ? exec_flops : flops;
 }
 extern "C" int dppo_profile_enable(dppo_handle* h, int on) {
     if (!h) DPPO_FAIL(-1, "null handle");
     CUDA_TRY(cudaSetDevice(h->device)); CUDA_TRY(cudaDeviceSynchronize());
     h->prof_used = 0;
-    for (int c = 0; c < 4; ++c) { h->prof_flops[c] = 0; h->prof_ms_acc[c] = 0; h->prof_launches[c] = 0; }
+    for (int c = 0; c < 4; ++c) { h->prof_flops[c] = 0; h->prof_ms_acc[c] = 0; h->prof_launches[c] = 0; h->prof_exec[c] = 0; }
     h->prof_on = on ? 1 : 0;
     return 0;
 }
@@ -158,6 +158,11 @@ extern "C" int dppo_profile_read_class(dppo_handle* h, int cls, double* ms, int6
     CUDA_TRY(cudaSetDevice(h->device)); CUDA_TRY(cudaDeviceSynchronize());
     prof_flush(h);
     if (ms) *ms = h->prof_ms_acc[cls]; if (launches) *launches = h->prof_launches[cls]; if (flops) *flops = h->prof_flops[cls];
+    return 0;
+}
+extern "C" int dppo_profile_read_exec(dppo_handle* h, int cls, double* exec_flops) {
+    if (!h || cls < 0 || cls > 3 || !exec_flops) DPPO_FAIL(-1, "dppo_profile_read_exec: bad arguments");
+    *exec_flops = h->prof_exec[cls];
     return 0;
 }
 extern "C" int dppo_profile_read(dppo_handle* h, double* ms, int64_t* launches, double* flops) {
@@ -236,8 +241,15 @@ static int prep_net(dppo_handle* h, int net, cudaStream_t s) {
 }
 
 // ------------------------------------------------------------------ create / destroy
+static int dppo_create_impl(const dppo_cfg* cfg, int device, dppo_handle** out, dppo_handle** partial);
 extern "C" int dppo_create(const dppo_cfg* cfg, int device, dppo_handle** out) {
     if (!cfg || !out) DPPO_FAIL(-1, "dppo_create: null argument");
+    dppo_handle* partial = nullptr;
+    const int r = dppo_create_impl(cfg, device, out, &partial);
+    if (r != 0 && partial) { std::string msg = dppo_last_error(); dppo_destroy(partial); dppo_set_error("%s", msg.c_str()); }   // every failure path frees what was allocated
+    return r;
+}
+static int dppo_create_impl(const dppo_cfg* cfg, int device, dppo_handle** out, dppo_handle** partial) {
     Geom g;
     if (make_geom(cfg, &g)) DPPO_FAIL(-1, "dppo_create: invalid configuration");
     int ndev = 0;
@@ -248,7 +260,10 @@ extern "C" int dppo_create(const dppo_cfg* cfg, int device, dppo_handle** out) {
     cudaDeviceProp prop; CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) DPPO_FAIL(-4, "dppo_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
     dppo_handle* h = new dppo_handle();
+    *partial = h;
     h->cfg = *cfg; h->device = device; h->g = g; h->sm_count = prop.multiProcessorCount;
+    { const char* tv = getenv("DPPO_PEER_TIMEOUT_S"); double sec = tv ? atof(tv) : 600.0; if (!(sec > 0)) sec = 600.0;
+      h->peer_timeout_cycles = (long long)(sec * 1e3 * (double)prop.clockRate); }
     { const char* dv = getenv("DPPO_DETERMINISTIC"); h->deterministic = (dv && dv[0] == '1') ? 1 : 0; }
     { const char* cv = getenv("DPPO_CHAIN_CG"); h->chain_cg = (cv && cv[0] == '1') ? 1 : 2; }
     { const char* pv = getenv("DPPO_DW_PAIR"); h->dw_pair = (pv && pv[0] == '0') ? 0 : 1; }
@@ -285,13 +300,12 @@ extern "C" int dppo_create(const dppo_cfg* cfg, int device, dppo_handle** out) {
     h->grads_buf[0] = h->grads; h->grads_floats = nA + nC + 16;
     CUDA_TRY(cudaMalloc(&h->scalars, 64 * sizeof(float)));
     CUDA_TRY(cudaMemset(h->scalars, 0, 64 * sizeof(float)));
-    int r = tc_init(h);
-    if (r) { dppo_destroy(h); return r; }
-    r = ts_init(h);
-    if (r) { dppo_destroy(h); return r; }
-    for (int net = 0; net < 4; ++net) { r = prep_net(h, net, 0); if (r) { dppo_destroy(h); return r; } }
+    h->comm_status = reinterpret_cast<int*>(h->scalars + 32);
+    DPPO_TRY(tc_init(h));
+    DPPO_TRY(ts_init(h));
+    for (int net = 0; net < 4; ++net) DPPO_TRY(prep_net(h, net, 0));
     CUDA_TRY(cudaDeviceSynchronize());
-    *out = h;
+    *out = h; *partial = nullptr;
     return 0;
 }
 extern "C" void dppo_destroy(dppo_handle* h) {
@@ -848,19 +862,20 @@ static int peer_allreduce_adamw(dppo_handle* h, cudaStream_t s, int opt, float* 
     PeerPtrs pp; memset(&pp, 0, sizeof(pp));
     for (int p = 0; p < h->world; ++p) { pp.g[p] = h->peer_grads[h->grads_cur][p]; pp.flags[p] = h->peer_flags[p]; }
     h->epoch += 1;
-    peer_barrier_kernel<<<1, 32, 0, s>>>(pp, h->flags, h->rank, h->world, h->epoch); KLAUNCH(h); KCHECK();
+    peer_barrier_kernel<<<1, 32, 0, s>>>(pp, h->flags, h->rank, h->world, h->epoch, h->peer_timeout_cycles, h->comm_status); KLAUNCH(h); KCHECK();
     if (h->peer_two_shot == 1) {
         // reduce-scatter + broadcast of the sum over peer memory, second barrier, AdamW on the local copy of the sum
         PeerSums ps; memset(&ps, 0, sizeof(ps));
         for (int p = 0; p < h->world; ++p) ps.s[p] = h->peer_gsum[p];
         const size_t n4 = (n_total + 3) / 4, per = (n4 + h->world - 1) / h->world;
         int grid = (int)((per + 255) / 256); if (grid > 2 * h->sm_count) grid = 2 * h->sm_count; if (grid < 1) grid = 1;
-        peer_reduce_scatter_bcast_kernel<<<grid, 256, 0, s>>>(pp, ps, h->rank, h->world, n4); KLAUNCH(h); KCHECK();
+        peer_reduce_scatter_bcast_kernel<<<grid, 256, 0, s>>>(pp, ps, h->rank, h->world, n4, h->comm_status); KLAUNCH(h); KCHECK();
         h->epoch += 1;
-        peer_barrier_kernel<<<1, 32, 0, s>>>(pp, h->flags, h->rank, h->world, h->epoch); KLAUNCH(h); KCHECK();
-        adamw_kernel<<<nblk(n_param, 256), 256, 0, s>>>(w, h->gsum, o.m, o.v, n_param, lr, alpha, b1, b2, h->cfg.adam_eps, wd); KLAUNCH(h); KCHECK();
+        peer_barrier_kernel<<<1, 32, 0, s>>>(pp, h->flags, h->rank, h->world, h->epoch, h->peer_timeout_cycles, h->comm_status); KLAUNCH(h); KCHECK();
+        adamw_kernel<<<nblk(n_param, 256), 256, 0, s>>>(w, h->gsum, o.m, o.v, n_param, lr, alpha, b1, b2, h->cfg.adam_eps, wd, h->skip_update, h->comm_status); KLAUNCH(h); KCHECK();
     } else {
-        peer_allreduce_adamw_kernel<<<2 * h->sm_count, 256, 0, s>>>(pp, h->world, h->gsum, w, o.m, o.v, n_param, n_total, lr, alpha, b1, b2, h->cfg.adam_eps, wd);
+        peer_allreduce_adamw_kernel<<<2 * h->sm_count, 256, 0, s>>>(pp, h->world, h->gsum, w, o.m, o.v, n_param, n_total, lr, alpha, b1, b2, h->cfg.adam_eps, wd,
+                                                                  h->skip_update, h->comm_status);
         KLAUNCH(h); KCHECK();
     }
     h->grads_cur ^= 1; h->grads = h->grads_buf[h->grads_cur];        // the next step accumulates into the other buffer
@@ -874,6 +889,16 @@ static int allreduce_sum(dppo_handle* h, float* buf, size_t n, cudaStream_t s) {
     return 0;
 }
 
+// 0 = healthy; 1 = a peer barrier timed out (a rank died or fell more than DPPO_PEER_TIMEOUT_S behind): the updates since were skipped
+extern "C" int dppo_comm_status(dppo_handle* h) {
+    ENTER(h);
+    int st = 0;
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(&st, h->comm_status, sizeof(int), cudaMemcpyDeviceToHost));
+    if (st) DPPO_FAIL(-6, "peer-memory gradient exchange: a flag barrier timed out; weights and optimizer state were left untouched since");
+    return 0;
+}
+
 // ------------------------------------------------------------------ AdamW
 static int adam_apply(dppo_handle* h, cudaStream_t s, int opt, float* w, const float* g, size_t n, float lr, float wd) {
     OptState& o = h->opt[opt];
@@ -881,7 +906,7 @@ static int adam_apply(dppo_handle* h, cudaStream_t s, int opt, float* w, const f
     const float b1 = h->cfg.adam_beta1, b2 = h->cfg.adam_beta2;
     float b1p = powf(b1, (float)o.step), b2p = powf(b2, (float)o.step);
     float alpha = lr * sqrtf(1.f - b2p) / (1.f - b1p);
-    adamw_kernel<<<nblk(n, 256), 256, 0, s>>>(w, g, o.m, o.v, n, lr, alpha, b1, b2, h->cfg.adam_eps, wd); KLAUNCH(h); KCHECK();
+    adamw_kernel<<<nblk(n, 256), 256, 0, s>>>(w, g, o.m, o.v, n, lr, alpha, b1, b2, h->cfg.adam_eps, wd, h->skip_update, nullptr); KLAUNCH(h); KCHECK();
     return 0;
 }
 
@@ -916,6 +941,11 @@ static int ppo_apply_tail(dppo_handle* h, cudaStream_t s, float lr, int apply, f
             DPPO_TRY(prep_net(h, DPPO_NET_ACTOR_FT, s));
             DPPO_TRY(prep_net(h, DPPO_NET_CRITIC, s));
         }
+    }
+    else if (h->world > 1) {
+        // loss + gradients only (critic warm-up iterations, diagnostics): the metrics / gradients handed out are still the GLOBAL
+        // ones, so that the KL early stop (train_ppo_diffusion_agent.py:366-368) is taken on the same value by every rank
+        DPPO_TRY(allreduce_sum(h, gr, nA + nC + 8, s));
     }
     if (metrics8) CUDA_TRY(cudaMemcpyAsync(metrics8, gr + nA + nC, 8 * sizeof(float), cudaMemcpyDeviceToDevice, s));
     if (grads_out) CUDA_TRY(cudaMemcpyAsync(grads_out, gr, (nA + nC) * sizeof(float), cudaMemcpyDeviceToDevice, s));
@@ -1071,6 +1101,11 @@ static int ppo_indexed_impl(dppo_handle* h, cudaStream_t s, const float* obs_buf
     // tensor mode: no materialised minibatch - the h0 pack and loss kernels read the rollout buffers through the flat indices
     TcIdxView view; view.flat = inds_dev; view.K = g.K; view.P = (long long)P; view.chains = chains_buf; view.obs = obs_buf; view.olp = oldlogp_buf;
     view.ret = returns_buf; view.val = values_buf; view.adv = adv_buf; view.bad = d_bad;
+    // an index outside [0, P*K) must not reach the optimizer: the pack / gather kernels raise d_bad, which turns AdamW (and the
+    // operand refresh that follows) into a no-op on the device; the host variant then returns an error, the device variant
+    // hands back NaN metrics
+    struct SkipGuard { dppo_handle* h; ~SkipGuard() { h->skip_update = nullptr; } } guard{h};
+    h->skip_update = d_bad;
     if (tc_eligible(h, N) && tc_ppo_indexed_ok(h, view) && (adv_std >= 0.f || N_global == N)) {
         DPPO_TRY(tc_ppo_step_indexed(h, s, view, N, N_global, adv_mean, adv_std));
         DPPO_TRY(ppo_apply_tail(h, s, lr, apply, metrics8_host ? d_met : metrics8, grads_out));
@@ -1082,12 +1117,13 @@ static int ppo_indexed_impl(dppo_handle* h, cudaStream_t s, const float* obs_buf
     DPPO_TRY(dppo_ppo_step(h, d_obs, d_prev, d_next, d_dind, d_ret, d_val, d_adv, d_olp, N, N_global, adv_mean, adv_std, lr, apply,
                            metrics8_host ? d_met : metrics8, grads_out, (dppo_stream_t)s));
     }
+    if (!metrics8_host && metrics8) { poison_metrics_kernel<<<1, 32, 0, s>>>(metrics8, d_bad); KLAUNCH(h); KCHECK(); }
     if (metrics8_host) {
         int bad = 0;
         CUDA_TRY(cudaMemcpyAsync(metrics8_host, d_met, 8 * sizeof(float), cudaMemcpyDeviceToHost, s));
         CUDA_TRY(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, s));
         CUDA_TRY(cudaStreamSynchronize(s));
-        if (bad) DPPO_FAIL(-1, "dppo_ppo_step_indexed_host: an index lies outside [0, P*K)");
+        if (bad) DPPO_FAIL(-1, "dppo_ppo_step_indexed_host: an index lies outside [0, P*K); the optimizer step was skipped");
     }
     return 0;
 }

@@ -767,10 +767,13 @@ __global__ void unpack_dw0_kernel(const float* __restrict__ dw0p, int A, int ski
 // =====================================================================================
 // Keras-3 AdamW (decoupled decay first, then Adam with folded bias correction)
 // =====================================================================================
+// skip[0] | skip[1] != 0 (optional device flags: bad minibatch indices, a peer barrier that timed out): leave everything untouched
 __global__ void adamw_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                             size_t n, float lr, float alpha, float b1, float b2, float eps, float wd) {
+                             size_t n, float lr, float alpha, float b1, float b2, float eps, float wd,
+                             const int* __restrict__ skip0 = nullptr, const int* __restrict__ skip1 = nullptr) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if ((skip0 && *skip0) || (skip1 && *skip1)) return;
     float p = w[i], gi = g[i], mi = m[i], vi = v[i];
     if (wd != 0.f) p = p - p * (wd * lr);
     mi = mi + (gi - mi) * (1.f - b1);
@@ -803,14 +806,24 @@ __global__ void __launch_bounds__(1024) clip_by_norm_kernel(float* __restrict__ 
 // ---- peer-memory gradient all-reduce fused with AdamW (one node, P2P over NVLink / NVSwitch)
 struct PeerPtrs { const float* g[8]; unsigned long long* flags[8]; };
 // flag barrier: tell every peer "my gradient buffer of this epoch is complete", wait until all peers said so
-__global__ void peer_barrier_kernel(PeerPtrs pp, unsigned long long* my_flags, int rank, int world, unsigned long long epoch) {
+// A rank may arrive long before its peers (each steps its own host envs): the wait is bounded by `timeout_cycles` (host: seconds x
+// SM clock, DPPO_PEER_TIMEOUT_S, default 600 s) and a timeout does NOT trap - it raises status[0], which makes the reduce / AdamW
+// kernels that follow no-ops (weights and optimizer state stay intact) and is reported by the next host-side status check.
+__global__ void peer_barrier_kernel(PeerPtrs pp, unsigned long long* my_flags, int rank, int world, unsigned long long epoch,
+                                    long long timeout_cycles, int* __restrict__ status) {
     const int p = threadIdx.x;
     if (p >= world) return;
+    if (*((volatile int*)status)) return;                       // an earlier barrier already failed
     __threadfence_system();
     *((volatile unsigned long long*)(pp.flags[p] + rank)) = epoch;
     const long long t0 = clock64();
     while (*((volatile unsigned long long*)(my_flags + p)) < epoch) {
-        if (clock64() - t0 > 6000000000LL) { printf("peer barrier timed out: rank %d waiting for rank %d (epoch %llu)\n", rank, p, epoch); __trap(); }
+        if (clock64() - t0 > timeout_cycles) {
+            printf("peer barrier timed out: rank %d waiting for rank %d (epoch %llu)\n", rank, p, epoch);
+            atomicExch(status, 1);
+            break;
+        }
+        __nanosleep(64);
     }
     __threadfence_system();
 }
@@ -818,7 +831,10 @@ __global__ void peer_barrier_kernel(PeerPtrs pp, unsigned long long* my_flags, i
 // (gradients ++ metric partial sums) is written back to this rank's buffer
 __global__ void __launch_bounds__(256) peer_allreduce_adamw_kernel(PeerPtrs pp, int world, float* __restrict__ g_sum, float* __restrict__ w,
                                                                   float* __restrict__ m, float* __restrict__ v, size_t n_param, size_t n_total,
-                                                                  float lr, float alpha, float b1, float b2, float eps, float wd) {
+                                                                  float lr, float alpha, float b1, float b2, float eps, float wd,
+                                                                  const int* __restrict__ skip0 = nullptr, const int* __restrict__ skip1 = nullptr) {
+    const bool no_update = (skip0 && *skip0) || (skip1 && *skip1);
+    if (skip1 && *skip1) return;                                   // failed barrier: the peers' buffers are not ready
     const size_t n4 = n_total / 4;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4 + (n_total & 3); i += (size_t)gridDim.x * blockDim.x) {
         float s[4] = {0.f, 0.f, 0.f, 0.f};
@@ -831,7 +847,7 @@ __global__ void __launch_bounds__(256) peer_allreduce_adamw_kernel(PeerPtrs pp, 
         }
         for (int k = 0; k < cnt; ++k) {
             const size_t e = e0 + k;
-            if (e < n_param) {
+            if (e < n_param && !no_update) {
                 float pw = w[e], mi = m[e], vi = v[e]; const float gi = s[k];
                 if (wd != 0.f) pw = pw - pw * (wd * lr);
                 mi = mi + (gi - mi) * (1.f - b1);
@@ -848,13 +864,18 @@ __global__ void __launch_bounds__(256) peer_allreduce_adamw_kernel(PeerPtrs pp, 
 // buffer (fixed order) and stores the result into the sum buffer of every rank (world-1 remote stores); a second flag barrier,
 // then plain AdamW on the local copy of the sum.  Per rank n floats are read and n written over NVLink instead of world * n read.
 struct PeerSums { float* s[8]; };
-__global__ void __launch_bounds__(256) peer_reduce_scatter_bcast_kernel(PeerPtrs pp, PeerSums ps, int rank, int world, size_t n4) {
+__global__ void __launch_bounds__(256) peer_reduce_scatter_bcast_kernel(PeerPtrs pp, PeerSums ps, int rank, int world, size_t n4, const int* __restrict__ status) {
+    if (*status) return;
     const size_t per = (n4 + (size_t)world - 1) / (size_t)world, lo = (size_t)rank * per, hi = lo + per < n4 ? lo + per : n4;
     for (size_t i = lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (size_t)gridDim.x * blockDim.x) {
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int p = 0; p < world; ++p) { const float4 x = __ldcv(reinterpret_cast<const float4*>(pp.g[p]) + i); a.x += x.x; a.y += x.y; a.z += x.z; a.w += x.w; }
         for (int q = 0; q < world; ++q) reinterpret_cast<float4*>(ps.s[q])[i] = a;
     }
+}
+// metrics of an update whose minibatch indices were out of range (the AdamW step was skipped): NaN, so that a device-side caller cannot miss it
+__global__ void poison_metrics_kernel(float* __restrict__ metrics8, const int* __restrict__ bad) {
+    if (*bad && threadIdx.x < 8) metrics8[threadIdx.x] = __int_as_float(0x7fc00000);
 }
 __global__ void ema_kernel(float* __restrict__ ema, const float* __restrict__ w, size_t n, float decay) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

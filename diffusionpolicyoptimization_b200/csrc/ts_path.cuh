@@ -7,9 +7,9 @@
 //   P = 3 (24-bit operands, forward GEMMs):                     A B ~= A0 B0 + A0 B1 + A1 B0 + A1 B1 + A0 B2 + A2 B0   (2^-27)
 // Why the forward pass needs P = 3: the loss is only piecewise smooth (ReLU kinks, the +-1 clip of x0, the PPO ratio clip).  A
 // forward deviation eps from the reference flips about eps * density units across a kink, and every flipped unit switches a
-// whole gradient term on or off: the actor-gradient error against the oracle grows like sqrt(eps) - 2e-3 of the largest
+// whole gradient term on or off: the actor-gradient error against the reference grows like sqrt(eps) - 2e-3 of the largest
 // entry with 16-bit forward operands (measured, tools/flip_probe.py), against the 1e-3 north_star's fp32 mode is held to.
-// With 24-bit forward operands the forward pass is as close to the oracle as the FFMA path is; the backward and
+// With 24-bit forward operands the forward pass is as close to the reference as the FFMA path is; the backward and
 // weight-gradient GEMMs are smooth in their operands and keep P = 2 (1e-5 relative).
 //
 //   ts::split_gemm_kernel<BN, A_MN, B_MN, P>   D[M,N] = sum_seg sum_(i,j) A_i B_j
@@ -286,7 +286,8 @@ static int launch_t(dppo_handle* h, cudaStream_t s, const Gemm& g) {
     const int grid = tiles < h->sm_count ? tiles : h->sm_count;
     prof_begin(h, s);
     kern<<<grid, STHREADS, smem_bytes<BN, P>(), s>>>(mp, p);
-    prof_end(h, s, g.alg_flops > 0 ? g.alg_flops : 2.0 * (double)g.M * (double)g.N * (double)(A.k + (g.A2.p[0] ? g.A2.k : 0)), 1);
+    prof_end(h, s, g.alg_flops > 0 ? g.alg_flops : 2.0 * (double)g.M * (double)g.N * (double)(A.k + (g.A2.p[0] ? g.A2.k : 0)), 3,
+             (P == 3 ? 6.0 : 3.0) * 2.0 * (double)p.m_blocks * SBM * (double)p.n_blocks * BN * (double)p.kblocks * SBK);
     h->launches++; h->tc_launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) DPPO_FAIL(-3, "split gemm launch failed: %s", cudaGetErrorString(e));
@@ -653,7 +654,8 @@ static int launch_t(dppo_handle* h, cudaStream_t s, const Gemm& g) {
     cfg.attrs = at; cfg.numAttrs = 1; cfg.blockDim = dim3(PTHREADS); cfg.gridDim = dim3(grid); cfg.dynamicSmemBytes = smem_bytes<P, BNP>(); cfg.stream = s;
     prof_begin(h, s);
     cudaError_t le = cudaLaunchKernelEx(&cfg, kern, mp, p);
-    prof_end(h, s, g.alg_flops > 0 ? g.alg_flops : 2.0 * (double)g.M * (double)g.N * (double)(g.A.k + (g.A2.p[0] ? g.A2.k : 0)), 1);
+    prof_end(h, s, g.alg_flops > 0 ? g.alg_flops : 2.0 * (double)g.M * (double)g.N * (double)(g.A.k + (g.A2.p[0] ? g.A2.k : 0)), 0,
+             (P == 3 ? 6.0 : 3.0) * 2.0 * (double)p.m_blocks * 256.0 * (double)p.n_blocks * BNP * (double)p.kblocks * 64.0);
     h->launches++; h->tc_launches++;
     if (le != cudaSuccess) DPPO_FAIL(-3, "split gemm (pair) launch failed: %s", cudaGetErrorString(le));
     cudaError_t e = cudaGetLastError();
@@ -900,7 +902,9 @@ static int launch_dw_group(dppo_handle* h, cudaStream_t s, const DwDesc* d, int 
     cfg.attrs = at; cfg.numAttrs = 1; cfg.blockDim = dim3(NUM_THREADS); cfg.gridDim = dim3(grid); cfg.dynamicSmemBytes = dw_smem_bytes(); cfg.stream = s;
     prof_begin(h, s);
     cudaError_t le = cudaLaunchKernelEx(&cfg, dw_pair_kernel, maps, gp);
-    prof_end(h, s, flops, 1);
+    double exec = 0;
+    for (int i = 0; i < n; ++i) exec += 3.0 * 2.0 * 256.0 * (double)(gp.p[i].nb_cta * 128) * 64.0 * (double)gp.p[i].kb_total * (double)(gp.p[i].m_blocks * gp.p[i].n_blocks);
+    prof_end(h, s, flops, 1, exec);
     h->launches++; h->tc_launches++;
     if (le != cudaSuccess) DPPO_FAIL(-3, "grouped dW (plane pair) launch failed: %s", cudaGetErrorString(le));
     dw_reduce_kernel<<<(eb[n] + 255) / 256, 256, 0, s>>>(gp, elem_begin_dev);

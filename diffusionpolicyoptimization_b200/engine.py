@@ -318,6 +318,12 @@ class Engine:
         L.check(self.lib.dppo_profile_read_class(self.h, int(cls), C.byref(ms), C.byref(n), C.byref(fl)), "dppo_profile_read_class")
         return float(ms.value), int(n.value), float(fl.value)
 
+    def profile_read_exec(self, cls: int) -> float:
+        """Tensor-pipe flops the launches of a class issued (call after profile_read_class)."""
+        fl = C.c_double(0)
+        L.check(self.lib.dppo_profile_read_exec(self.h, int(cls), C.byref(fl)), "dppo_profile_read_exec")
+        return float(fl.value)
+
     def profile_read(self):
         """-> (gemm_ms, gemm_launches, gemm_flops) accumulated since profile_enable(True)."""
         ms, n, fl = C.c_double(0), C.c_int64(0), C.c_double(0)

@@ -85,9 +85,22 @@ class _Net:
 
     # reference checkpoints are Keras .weights.h5 (finetune/train_agent.py:127-142); h5py is not a
     # dependency here, so flat .npz files carry the same variable order.
+    @staticmethod
+    def _npz_path(path):
+        path = str(path)
+        return path if path.endswith(".npz") else path + ".npz"        # np.savez appends the suffix: save and load must agree
+
     def save_weights(self, path):
-        np.savez(path, **{f"v{i}": w for i, w in enumerate(self.get_weights())})
+        path = str(path)
+        if path.endswith(".h5"):
+            from ...util.keras_h5 import save_keras_weights_h5
+            return save_keras_weights_h5(path, self.get_weights(), self.keras_variable_paths())
+        np.savez(self._npz_path(path), **{f"v{i}": w for i, w in enumerate(self.get_weights())})
 
     def load_weights(self, path):
-        z = np.load(path)
+        path = str(path)
+        if path.endswith(".h5"):
+            from ...util.keras_h5 import load_keras_weights_h5
+            return self.set_weights(load_keras_weights_h5(path, self.keras_variable_paths(), self.shapes))
+        z = np.load(self._npz_path(path))
         self.set_weights([z[f"v{i}"] for i in range(len(self.shapes))])

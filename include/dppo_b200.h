@@ -230,6 +230,9 @@ int dppo_comm_ipc_attach(dppo_handle* h, const char* all_blobs, int rank, int wo
 
 /* Count of kernel launches issued by this handle since creation (bench `gpu_launches`). */
 int64_t dppo_launch_count(dppo_handle* h);
+/* Health of the peer-memory gradient exchange (dppo_comm_ipc_attach): 0, or an error once a flag barrier timed out
+ * (DPPO_PEER_TIMEOUT_S seconds, default 600): from then on the updates are skipped on the device, nothing traps. */
+int dppo_comm_status(dppo_handle* h);
 /* Of those, the tcgen05 GEMM launches (0 in DPPO_PREC_FP32 mode and below the row threshold). */
 int64_t dppo_tc_launch_count(dppo_handle* h);
 /* Of those, launches of the fused layer-chain kernel (whole MLP forward / backward / T-step sampler per launch). */
@@ -271,6 +274,9 @@ int dppo_debug_chain_timing(dppo_handle* h, int enable, long long* out_host, int
 int dppo_debug_mma_probe(dppo_handle* h, int grid, int mode, int iters, int N, int depth, long long* out_host);
 int dppo_profile_enable(dppo_handle* h, int on);
 int dppo_profile_read(dppo_handle* h, double* gemm_ms, int64_t* gemm_launches, double* gemm_flops);
+/* Tensor-pipe flops the launches of a class actually ISSUED (padded tiles; the plane modes issue 3 or 6 products per algorithmic
+ * multiply-add), accumulated like the algorithmic count; call after dppo_profile_read_class (which synchronises). */
+int dppo_profile_read_exec(dppo_handle* h, int cls, double* exec_flops);
 /* Same, per kernel: 0 = fc::chain_kernel<512> (fused tcgen05 layer chain, actor width), 1 = tcgen05 GEMMs (grouped weight
  * gradients, per-layer fallback), 2 = FFMA SGEMM (fp32 parity mode), 3 = fc::chain_kernel<256> (Mish critic width).  flops are ALGORITHMIC (un-padded dims). */
 int dppo_profile_read_class(dppo_handle* h, int cls, double* ms, int64_t* launches, double* flops);

@@ -268,11 +268,22 @@ def test_bf16_index_driven_update_reads_the_rollout_buffers_directly(pair):
     torch.cuda.synchronize()
     n1 = e.launch_count()
     e.ppo_step(_flat(obs)[b], chains[b, k], chains[b, k + 1], k.to(torch.int32), ret[b], val[b], adv[b], olp[b, k], lr=0.0, apply=False)
-    # no gather kernel in front of the update (the deterministic mode keeps the gathered path: one more launch)
-    assert launches_indexed == e.launch_count() - n1 + (1 if DETERMINISTIC else 0)
+    # no gather kernel in front of the update (the deterministic mode keeps the gathered path: one more launch); the device variant
+    # ends with the one-warp kernel that turns the metrics into NaN when an index was out of range
+    assert launches_indexed == e.launch_count() - n1 + 1 + (1 if DETERMINISTIC else 0)
     assert torch.equal(m1, m2)                                        # the loss partial sums are reduced in a fixed order
     scale = float(g2.abs().max())
     assert float((g1 - g2).abs().max()) < 2e-3 * scale                # dW accumulates with atomics: order varies run to run
     with pytest.raises(L.DppoError):
         e.ppo_step_indexed(_flat(obs), chains, olp, ret, val, adv, np.full(N, P * K, np.int32), lr=0.0, apply=False,
                            metrics_host=np.zeros(8, np.float32))
+    # an out-of-range index must never reach the optimizer: weights and moments untouched, NaN metrics on the device variant
+    w0 = e.get_weights(L.NET_ACTOR_FT).copy(); m0, v0, st0 = e.get_opt_state(L.OPT_FINETUNE)
+    bad = flat.to(torch.int32).clone(); bad[17] = P * K + 3
+    mb = e.ppo_step_indexed(_flat(obs), chains, olp, ret, val, adv, bad.cuda(), lr=1e-3, apply=True)
+    assert torch.isnan(mb).all()
+    with pytest.raises(L.DppoError):
+        e.ppo_step_indexed(_flat(obs), chains, olp, ret, val, adv, bad.numpy(), lr=1e-3, apply=True, metrics_host=np.zeros(8, np.float32))
+    m1_, v1_, _ = e.get_opt_state(L.OPT_FINETUNE)
+    assert np.array_equal(e.get_weights(L.NET_ACTOR_FT), w0) and np.array_equal(m1_, m0) and np.array_equal(v1_, v0)
+    e.set_opt_state(L.OPT_FINETUNE, m0, v0, st0)                      # the step counter did advance: restore it for the shared fixture
