@@ -12,6 +12,14 @@ reference is where the data lives:
 * a minibatch is the slice of the shuffled flat index handed to `dppo_ppo_step_indexed` (reference: `tf.gather` /
   `gather_nd` of seven tensors, :287-312), loss + backward + AdamW fused in the same call (:314-356).
 
+Data parallel (absent in the reference): under an initialised `torch.distributed` group every rank owns a
+contiguous block of the `n_envs` env copies (its own `venv` with that many envs, its own resident rollout) and a replica of
+the weights (`model.engine.init_comm()` is called here).  Every rank draws the SAME minibatch permutation over the global
+(step, env, k) pool and keeps the rows of its env block (`parallel.local_minibatch`), so the union over ranks is exactly the
+reference's minibatch; the advantage normalisation of a minibatch (diffusion_ppo.py:74-75) uses the global mean / std from one
+small all-reduce of (sum, sum of squares); the library's gradient exchange returns global metrics, so the KL early stop
+(:366-368) is taken identically everywhere; reward scaling and episode statistics run on the all-gathered (tiny) reward arrays.
+
 Only rewards / terminated / firsts and the reward scaler stay on the host (float64 NumPy, like the reference), because the
 environment produces them there.  `venv` needs `reset_arg(options_list) -> {"state": [E,To,Do]}` and
 `step(action [E,act_steps,Da]) -> (obs dict, reward [E], terminated [E], truncated [E], info)`, the reference's vector-env API.
@@ -22,6 +30,7 @@ import time as _time
 import numpy as np
 import torch
 
+from ...parallel import local_minibatch, shard_range, stats_from_moments
 from ...util.reward_scaling import RunningRewardScaler
 
 log = logging.getLogger(__name__)
@@ -38,6 +47,15 @@ class TrainPPODiffusionAgent:
         `shuffle_fn(itr, epoch, total) -> int permutation` replace the library's Philox stream / torch.randperm
         (tests inject them to replay the same draws on a CPU restatement of the loop)."""
         self.model, self.venv, self.engine = model, venv, model.engine
+        # data parallel: `n_envs` is the GLOBAL env count; this rank steps env columns [env_lo, env_hi) (its venv has that many)
+        import torch.distributed as dist
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank() if self.world > 1 else 0
+        self.n_envs_global = int(n_envs)
+        self.env_lo, self.env_hi = shard_range(int(n_envs), self.rank, self.world)
+        if self.world > 1:
+            self.engine.init_comm()
+        n_envs = self.env_hi - self.env_lo
         # :349-354: any max_grad_norm switches on tf.clip_by_norm(grad, clip_norm=1.0) per variable (the constant is the reference's)
         self.max_grad_norm = max_grad_norm
         self.engine.set_grad_clip_norm(1.0 if max_grad_norm is not None else None)
@@ -55,7 +73,7 @@ class TrainPPODiffusionAgent:
         self.furniture_sparse_reward, self.log_freq = furniture_sparse_reward, log_freq
         self.n_cond_step, self.obs_dim = model.cfg.cond_steps, model.cfg.obs_dim
         self.horizon_steps, self.action_dim = model.horizon_steps, model.action_dim
-        self.running_reward_scaler = RunningRewardScaler(self.n_envs) if reward_scale_running else None   # train_ppo_agent.py:70-72
+        self.running_reward_scaler = RunningRewardScaler(self.n_envs_global) if reward_scale_running else None   # train_ppo_agent.py:70-72
         self.noise_fn, self.shuffle_fn = noise_fn, shuffle_fn
         self._perm_gen = torch.Generator().manual_seed(seed)
         self.itr, self.cnt_train_step, self.opt_iterations = 0, 0, 0
@@ -114,7 +132,7 @@ class TrainPPODiffusionAgent:
                 kw["x_T"], kw["noise"] = self.noise_fn(self.itr, step, E)
             self.engine.sample(self.obs_trajs[step], deterministic=eval_mode,
                                min_sampling_std=float(self.model.get_min_sampling_denoising_std()),
-                               seed=self.model.seed, offset=self.model._next_offset(),
+                               seed=self.model.seed, offset=self.model._next_offset(), row_offset=self.env_lo,
                                actions_out=self.actions_dev, chains_out=self.chains_trajs[step], **kw)
             self.actions_stage.copy_(self.actions_dev, non_blocking=True)
             stream.synchronize()
@@ -126,7 +144,7 @@ class TrainPPODiffusionAgent:
             terminated_trajs[step] = terminated_venv
             firsts_trajs[step + 1] = done_venv
             prev_obs_venv = obs_venv
-            self.cnt_train_step += E * self.act_steps if not eval_mode else 0
+            self.cnt_train_step += self.n_envs_global * self.act_steps if not eval_mode else 0
         self._prev_obs_venv, self._done_venv = prev_obs_venv, done_venv
 
         result = {"itr": self.itr, "step": self.cnt_train_step, "eval_mode": eval_mode}
@@ -152,10 +170,21 @@ class TrainPPODiffusionAgent:
                              r["itr"], r["step"], r["loss"], r["pg_loss"], r["v_loss"], r["avg_episode_reward"], r["time"])
         return self.run_results
 
+    # ---------------------------------------------------------------- data-parallel plumbing (tiny host arrays)
+    def _gather_envs(self, x):
+        """[..., E_local] host array of every rank -> [..., E_global] (env columns in rank order), identical on every rank."""
+        if self.world == 1:
+            return x
+        import torch.distributed as dist
+        parts = [None] * self.world
+        dist.all_gather_object(parts, np.ascontiguousarray(x))
+        return np.concatenate(parts, axis=-1)
+
     # ---------------------------------------------------------------- :145-186, host bookkeeping
     def _summarize_episodes(self, firsts_trajs, reward_trajs):
+        firsts_trajs, reward_trajs = self._gather_envs(firsts_trajs), self._gather_envs(reward_trajs)
         spans = []
-        for env_ind in range(self.n_envs):
+        for env_ind in range(self.n_envs_global):
             starts = np.where(firsts_trajs[:, env_ind] == 1)[0]
             spans += [(env_ind, a, b - 1) for a, b in zip(starts[:-1], starts[1:]) if b - a > 1]
         if not spans:
@@ -175,14 +204,16 @@ class TrainPPODiffusionAgent:
         chains_k = self.chains_trajs.reshape(S * E, K + 1, -1)
         values_k = eng.value(obs_k)                                  # :205
         logprobs_k = eng.logprobs(obs_k, chains_k)                   # :223  [S*E*K, A], row = b*K + k
-        if self.reward_scale_running:                                # :232-236
-            reward_trajs = self.running_reward_scaler(reward=reward_trajs.T, first=firsts_trajs[:-1].T).T
+        if self.reward_scale_running:                                # :232-236 (running statistics over ALL env copies: gathered, then this rank's columns)
+            scaled = self.running_reward_scaler(reward=self._gather_envs(reward_trajs).T, first=self._gather_envs(firsts_trajs)[:-1].T).T
+            reward_trajs = np.ascontiguousarray(scaled[:, self.env_lo:self.env_hi])
         next_values = eng.value(np.ascontiguousarray(obs_venv["state"], np.float32).reshape(E, -1))   # :252
         advantages_k, returns_k = eng.gae(np.ascontiguousarray(reward_trajs), terminated_trajs, values_k.reshape(S, E),
                                           next_values, self.reward_scale_const, self.gamma, self.gae_lambda)
 
-        total_steps = S * E * K
+        total_steps = S * self.n_envs_global * K                     # the GLOBAL (step, env, k) pool
         num_batch = max(1, total_steps // self.batch_size)           # :285, the tail is skipped
+        adv_flat = advantages_k.reshape(-1)
         clipfracs, metrics, flag_break = [], None, False
         apply = self.itr >= self.n_critic_warmup_itr                 # :348
         for update_epoch in range(self.update_epochs):
@@ -192,10 +223,23 @@ class TrainPPODiffusionAgent:
                 inds_k = torch.randperm(total_steps, generator=self._perm_gen).to(torch.int32).numpy()   # :284
             for batch in range(num_batch):
                 inds_b = inds_k[batch * self.batch_size: (batch + 1) * self.batch_size]
+                kw = {}
+                if self.world > 1:
+                    # this rank's rows of the global minibatch + the minibatch's global advantage statistics (one small all-reduce)
+                    import torch.distributed as dist
+                    n_glob = int(inds_b.shape[0])
+                    inds_b = local_minibatch(inds_b, self.n_envs_global, K, self.env_lo, self.env_hi)
+                    if inds_b.shape[0] < 1:
+                        raise RuntimeError("a rank holds no row of this minibatch: use fewer ranks or a larger batch_size")
+                    a = adv_flat[torch.from_numpy(inds_b // K).to(adv_flat.device, torch.int64)].to(torch.float64)
+                    mom = torch.stack([a.sum(), (a * a).sum()])
+                    dist.all_reduce(mom)
+                    mean, std = stats_from_moments(float(mom[0]), float(mom[1]), n_glob)
+                    kw = dict(n_global=n_glob, adv_mean=mean, adv_std=std)
                 stage = self.inds_stage[: inds_b.shape[0]]
                 stage.copy_(torch.from_numpy(np.ascontiguousarray(inds_b)))
                 eng.ppo_step_indexed(obs_k, chains_k, logprobs_k, returns_k, values_k, advantages_k, stage.numpy(),
-                                     lr=self._lr(), apply=apply, metrics_host=self.metrics_stage.numpy())
+                                     lr=self._lr(), apply=apply, metrics_host=self.metrics_stage.numpy(), **kw)
                 if apply:
                     self.opt_iterations += 1
                 metrics = self.metrics_stage.numpy().copy()
@@ -206,7 +250,8 @@ class TrainPPODiffusionAgent:
                     break
             if flag_break:
                 break
-        y_pred, y_true = values_k.cpu().numpy(), returns_k.reshape(-1).cpu().numpy()     # :373-377
+        y_pred = self._gather_envs(values_k.reshape(S, -1).cpu().numpy()).reshape(-1)     # :373-377 (over the whole rollout)
+        y_true = self._gather_envs(returns_k.reshape(S, -1).cpu().numpy()).reshape(-1)
         var_y = np.var(y_true)
         explained_var = np.nan if var_y == 0 else 1 - np.var(y_true - y_pred) / var_y
         pg_loss, entropy_loss, v_loss, _cf, approx_kl, ratio, bc_loss, eta = [float(m) for m in metrics]

@@ -72,3 +72,66 @@ def test_two_rank_gradient_equals_unsharded():
     metrics, ga, gc = o.ppo_grads(*batch)
     want = np.concatenate([O.flatten_params(ga), O.flatten_params(gc), np.array([float(m) for m in metrics], np.float32)])
     np.testing.assert_allclose(got, want, rtol=2e-4, atol=2e-6)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the data-parallel agent's host logic (agent/finetune/train_ppo_diffusion_agent.py of the package): every rank draws the same
+# permutation over the GLOBAL (step, env, k) pool and keeps the rows of its env block; the minibatch's advantage statistics come
+# from one all-reduce of (sum, sum of squares)
+def test_local_minibatch_partitions_the_global_one():
+    from diffusionpolicyoptimization_b200.parallel import local_minibatch
+    S, E, K = 5, 7, 3
+    rng = np.random.default_rng(0)
+    pool = rng.standard_normal((S, E, K))                        # one value per (step, env, k)
+    perm = rng.permutation(S * E * K)
+    for world in (1, 2, 3):
+        for b0 in range(0, S * E * K - 20, 20):
+            mb = perm[b0:b0 + 20]
+            want = np.sort(pool.reshape(-1)[mb])
+            got = []
+            for r in range(world):
+                lo, hi = shard_range(E, r, world)
+                loc = local_minibatch(mb, E, K, lo, hi)
+                assert loc.dtype == np.int32 and (loc >= 0).all() and (loc < S * (hi - lo) * K).all()
+                got.append(np.ascontiguousarray(pool[:, lo:hi]).reshape(-1)[loc])    # the rank's own resident rollout
+            np.testing.assert_array_equal(np.sort(np.concatenate(got)), want)
+
+
+def _agent_stats_worker(rank, world, port, q):
+    from diffusionpolicyoptimization_b200.parallel import local_minibatch, stats_from_moments
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    S, E, K = 6, 8, 10
+    rng = np.random.default_rng(5)
+    adv = rng.standard_normal((S, E)).astype(np.float32)         # advantages per (step, env), identical on both ranks here
+    perm = np.random.default_rng(9).permutation(S * E * K)      # the same draw on every rank
+    lo, hi = shard_range(E, rank, world)
+    mine = torch.from_numpy(np.ascontiguousarray(adv[:, lo:hi]).reshape(-1))
+    out = []
+    for b0 in range(0, S * E * K, 160):
+        mb = perm[b0:b0 + 160]
+        loc = local_minibatch(mb, E, K, lo, hi)
+        a = mine[torch.from_numpy(loc // K).long()].to(torch.float64)
+        mom = torch.stack([a.sum(), (a * a).sum()])
+        dist.all_reduce(mom)                                     # the one small collective per minibatch
+        out.append(stats_from_moments(float(mom[0]), float(mom[1]), len(mb)))
+    if rank == 0:
+        q.put((np.array(out), adv, perm))
+    dist.destroy_process_group()
+
+
+def test_two_rank_advantage_statistics_equal_the_unsharded_ones():
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_agent_stats_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got, adv, perm = q.get()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    K = 10
+    for i, b0 in enumerate(range(0, adv.size * K, 160)):
+        rows = adv.reshape(-1)[perm[b0:b0 + 160] // K].astype(np.float64)      # diffusion_ppo.py:74-75 on the un-sharded minibatch
+        np.testing.assert_allclose(got[i], [rows.mean(), rows.std()], rtol=2e-6, atol=1e-7)

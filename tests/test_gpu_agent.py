@@ -18,7 +18,7 @@ pytestmark = pytest.mark.gpu
 E, S, ACT_STEPS, LR = 8, 6, 4, 1e-4
 
 
-def make_model(o, precision="fp32", **kw):
+def make_model(o, precision="fp32", device="cuda:0", **kw):
     d = o.d
     actor = dp.DiffusionMLP(action_dim=d.action_dim, horizon_steps=d.horizon_steps, cond_dim=d.obs_dim, time_dim=16,
                             mlp_dims=[512, 512, 512], activation_type="ReLU", residual_style=True)
@@ -26,7 +26,7 @@ def make_model(o, precision="fp32", **kw):
     model = dp.PPODiffusion(gamma_denoising=0.99, clip_ploss_coef=0.01, clip_ploss_coef_base=0.01, clip_ploss_coef_rate=3,
                             randn_clip_value=3, min_sampling_denoising_std=0.1, min_logprob_denoising_std=0.1,
                             actor=actor, critic=critic, ft_denoising_steps=d.ft_denoising_steps, horizon_steps=d.horizon_steps,
-                            obs_dim=d.obs_dim, action_dim=d.action_dim, denoising_steps=d.denoising_steps, device="cuda:0",
+                            obs_dim=d.obs_dim, action_dim=d.action_dim, denoising_steps=d.denoising_steps, device=device,
                             precision=precision, **kw)
     model.actor.set_flat_weights(O.flatten_params(o.actor))
     model.actor_ft.set_flat_weights(O.flatten_params(o.actor_ft))

@@ -95,3 +95,79 @@ def test_sharded_update_matches_the_unsharded_one(prec):
         # AdamW's first step moves an entry by ~lr * g / (|g| + eps): compare in units of lr (entries with |g| ~ eps amplify 1e-9 errors)
         assert r["w_first_frac_within_0p02lr"] > 0.999 and r["w_first_err_lr"] < 1.0, (mode, r)
     assert out["peer_vs_nccl_lr"] < 2.0
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def _agent_worker(rank, world, port, out):
+    """Two ranks, four env copies each, replay the two training iterations of tests/test_gpu_agent.py: the data-parallel agent
+    must reproduce the reference loop (oracle/dppo_loop.py on the un-sharded environment) within the single-rank bounds."""
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    from diffusionpolicyoptimization_b200 import _lib as L
+    from diffusionpolicyoptimization_b200.agent.finetune.train_ppo_diffusion_agent import TrainPPODiffusionAgent
+    from diffusionpolicyoptimization_b200.parallel import shard_range
+    from oracle import dppo_loop as OL
+    from oracle import dppo_oracle as O
+    from helpers import rel_err
+    from toy_env import ToyVecEnv
+    import test_gpu_agent as T
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    E, S = T.E, T.S
+    lo, hi = shard_range(E, rank, world)
+    o = O.make_oracle("hopper", seed=21)
+    model = T.make_model(o, device=f"cuda:{rank}")
+
+    def noise_local(itr, step, B):
+        x_T, nz = T.noise_fn(itr, step, E)                      # the global draws; this rank's env block
+        return x_T[lo:hi], nz[:, lo:hi]
+
+    kw = dict(n_steps=S, act_steps=T.ACT_STEPS, batch_size=160, update_epochs=2, gamma=0.99, gae_lambda=0.95, target_kl=1)
+    agent = TrainPPODiffusionAgent(model, ToyVecEnv(E, 11, 3, seed=3).shard(lo, hi), n_envs=E, n_train_itr=2, actor_lr=T.LR, force_train=True,
+                                   reset_at_iteration=False, reward_scale_running=True, noise_fn=noise_local, shuffle_fn=T.shuffle_fn, **kw)
+    assert agent.world == world and agent.n_envs == hi - lo
+    got = [agent.run_iteration() for _ in range(2)]
+    w = np.concatenate([model.engine.get_weights(L.NET_ACTOR_FT), model.engine.get_weights(L.NET_CRITIC)])
+    digests = [None] * world
+    dist.all_gather_object(digests, w.tobytes())
+    chains = [None] * world
+    dist.all_gather_object(chains, agent.chains_trajs.cpu().numpy())
+    if rank == 0:
+        venv = ToyVecEnv(E, 11, 3, seed=3)
+        scaler = OL.RewardScaler(E)
+        params = o.actor_ft + o.critic
+        opt = dict(m=[torch.zeros_like(p) for p in params], v=[torch.zeros_like(p) for p in params], step=0)
+        prev_obs, firsts0 = venv.reset_arg(), 1
+        errs = {}
+        for itr in range(2):
+            want, prev_obs, done = OL.ppo_iteration(o, opt, venv, itr, prev_obs, lr=T.LR, reward_scaler=scaler, reward_scale_const=1.0,
+                                                    noise_fn=T.noise_fn, shuffle_fn=T.shuffle_fn, firsts0=firsts0, **kw)
+            firsts0 = done
+            for k in ("pg_loss", "v_loss", "approx_kl", "ratio", "clipfrac", "explained_var"):
+                errs[(itr, k)] = (float(got[itr][k]), float(want[k]))
+            errs[(itr, "n_updates")] = (got[itr]["n_updates"], want["n_updates"])
+        K = o.d.ft_denoising_steps
+        got_chains = np.concatenate(chains, axis=1)             # [S, E, K+1, A] in env order (last iteration)
+        out["chains_err"] = rel_err(got_chains.reshape(S * E, K + 1, -1), want["chains_k"].reshape(S * E, K + 1, -1))
+        out["errs"] = errs
+        out["frac_bad"] = float(np.mean(np.abs(w - O.flatten_params(params)) > 0.25 * T.LR))
+        out["opt_steps"] = (agent.opt_iterations, opt["step"])
+        out["replicas_identical"] = all(b == digests[0] for b in digests)
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_data_parallel_agent_reproduces_the_reference_loop():
+    import torch.multiprocessing as mp
+    mgr = mp.Manager(); out = mgr.dict()
+    mp.spawn(_agent_worker, args=(2, 29591, out), nprocs=2, join=True)
+    print(dict(out))
+    assert out["replicas_identical"] and out["opt_steps"] == (12, 12)
+    assert out["chains_err"] < 5e-4
+    for (itr, k), (g, w) in out["errs"].items():
+        if k == "n_updates":
+            assert g == w == 6
+        else:
+            assert abs(g - w) < 5e-3 * max(1.0, abs(w)) + 2e-5, (itr, k, g, w)
+    assert out["frac_bad"] < 1e-2

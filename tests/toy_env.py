@@ -11,6 +11,15 @@ class ToyVecEnv:
         self.max_episode_steps, self.term_threshold = max_episode_steps, term_threshold
         self.reset_arg()
 
+    def shard(self, lo, hi):
+        """The env copies [lo, hi) of this vector env as their own vector env (data-parallel ranks step their own block)."""
+        import copy
+        o = copy.copy(self)
+        o.E = hi - lo
+        o.s0 = self.s0[lo:hi].copy()
+        o.reset_arg()
+        return o
+
     def _obs(self):
         return {"state": self.s[:, None, :].astype(np.float32)}
 
