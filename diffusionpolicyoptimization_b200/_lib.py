@@ -21,7 +21,7 @@ EXPORTS = (
     "dppo_abi_version", "dppo_last_error", "dppo_cfg_default", "dppo_cfg_size", "dppo_ddpm_schedule", "dppo_num_params",
     "dppo_create", "dppo_destroy", "dppo_set_weights", "dppo_get_weights", "dppo_set_opt_state",
     "dppo_get_opt_state", "dppo_set_ft_denoising_steps", "dppo_set_grad_clip_norm", "dppo_actor_forward", "dppo_value",
-    "dppo_sample", "dppo_sample_host", "dppo_logprobs", "dppo_logprobs_subsample", "dppo_ppo_step",
+    "dppo_sample", "dppo_sample_host", "dppo_set_env_normalization", "dppo_rollout_step", "dppo_logprobs", "dppo_logprobs_subsample", "dppo_ppo_step",
     "dppo_ppo_step_host", "dppo_ppo_step_indexed", "dppo_ppo_step_indexed_host", "dppo_gae", "dppo_pretrain_step", "dppo_ema_update", "dppo_comm_unique_id",
     "dppo_comm_init", "dppo_comm_ipc_export", "dppo_comm_ipc_attach", "dppo_comm_status", "dppo_launch_count", "dppo_tc_launch_count", "dppo_fused_launch_count", "dppo_last_path", "dppo_force_path", "dppo_profile_enable", "dppo_debug_tc_gemm",
     "dppo_profile_read", "dppo_debug_chain_timing", "dppo_debug_mma_probe", "dppo_profile_read_class", "dppo_profile_read_exec", "dppo_debug_split_gemm", "dppo_debug_pair_gemm",
@@ -84,6 +84,8 @@ def load():
         "dppo_value": (C.c_int, [vp, vp, i32, vp, vp]),
         "dppo_sample": (C.c_int, [vp, vp, i32, i32, i32, f32, u64, u64, i64, vp, vp, vp, vp, vp]),
         "dppo_sample_host": (C.c_int, [vp, vp, i32, i32, i32, f32, u64, u64, i64, vp, vp, vp, vp, vp]),
+        "dppo_set_env_normalization": (C.c_int, [vp, vp, vp, vp, vp]),
+        "dppo_rollout_step": (C.c_int, [vp, vp, i32, i32, i32, f32, u64, u64, i64, vp, vp, vp, vp, vp, vp, i32, vp]),
         "dppo_logprobs": (C.c_int, [vp, vp, vp, i32, i32, vp, vp]),
         "dppo_logprobs_subsample": (C.c_int, [vp, vp, vp, vp, vp, i32, i32, vp, vp]),
         "dppo_ppo_step": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i64, f32, f32, f32, i32, vp, vp, vp]),

@@ -41,11 +41,16 @@ class TrainPPODiffusionAgent:
                  gamma=0.99, gae_lambda=0.95, target_kl=1, actor_lr=1e-4, val_freq=10, force_train=False,
                  reset_at_iteration=True, reward_scale_running=True, reward_scale_const=1.0, n_critic_warmup_itr=0,
                  reward_horizon=None, max_grad_norm=None, best_reward_threshold_for_success=3.0,
-                 furniture_sparse_reward=False, log_freq=1, seed=42, noise_fn=None, shuffle_fn=None):
+                 furniture_sparse_reward=False, log_freq=1, seed=42, noise_fn=None, shuffle_fn=None, normalization=None):
         """`actor_lr`: float or a schedule called with the optimizer's iteration count (Keras semantics of
         train_ppo_agent.py:35-49).  `noise_fn(itr, step, B) -> (x_T [B,A], noise [T,B,A])` and
         `shuffle_fn(itr, epoch, total) -> int permutation` replace the library's Philox stream / torch.randperm
-        (tests inject them to replay the same draws on a CPU restatement of the loop)."""
+        (tests inject them to replay the same draws on a CPU restatement of the loop).
+        `normalization`: dict with obs_min / obs_max / action_min / action_max (the task's normalization.npz).  When
+        given, `venv` is the RAW environment (no MujocoLocomotionLowdimWrapper): it emits raw float64 observations and takes raw
+        actions; normalize_obs, the fp32 cast, the `[:, :act_steps]` slice and unnormalize_action (mujoco_locomotion_lowdim.py:57-62,
+        train_ppo_diffusion_agent.py:111-123) run on the device around the sampler (`dppo_rollout_step`), with the obs / action exchange
+        through two alternating pinned host buffers that the kernels read and write directly."""
         self.model, self.venv, self.engine = model, venv, model.engine
         # data parallel: `n_envs` is the GLOBAL env count; this rank steps env columns [env_lo, env_hi) (its venv has that many)
         import torch.distributed as dist
@@ -75,6 +80,10 @@ class TrainPPODiffusionAgent:
         self.horizon_steps, self.action_dim = model.horizon_steps, model.action_dim
         self.running_reward_scaler = RunningRewardScaler(self.n_envs_global) if reward_scale_running else None   # train_ppo_agent.py:70-72
         self.noise_fn, self.shuffle_fn = noise_fn, shuffle_fn
+        self.normalization = None
+        if normalization is not None:
+            self.normalization = {k: np.asarray(normalization[k], np.float32).reshape(-1) for k in ("obs_min", "obs_max", "action_min", "action_max")}
+            self.engine.set_env_normalization(**self.normalization)
         self._perm_gen = torch.Generator().manual_seed(seed)
         self.itr, self.cnt_train_step, self.opt_iterations = 0, 0, 0
         self.run_results = []
@@ -93,6 +102,9 @@ class TrainPPODiffusionAgent:
         self.actions_dev = torch.zeros(E, A, device=dev)
         self.obs_stage = torch.zeros(E, Do).pin_memory()
         self.actions_stage = torch.zeros(E, A).pin_memory()
+        # raw env exchange (normalization given): two alternating pinned buffers per direction
+        self.raw_obs_stage = [torch.zeros(E, Do, dtype=torch.float64).pin_memory() for _ in range(2)]
+        self.raw_act_stage = [torch.zeros(E, self.act_steps * self.action_dim).pin_memory() for _ in range(2)]
         self.inds_stage = torch.zeros(self.batch_size, dtype=torch.int32).pin_memory()
         self.metrics_stage = torch.zeros(8).pin_memory()
 
@@ -125,19 +137,29 @@ class TrainPPODiffusionAgent:
         stream = torch.cuda.current_stream(self.engine.dev)
 
         for step in range(S):                                        # :107-142
-            self.obs_stage.copy_(torch.from_numpy(np.ascontiguousarray(prev_obs_venv["state"], np.float32)).reshape(E, -1))
-            self.obs_trajs[step].copy_(self.obs_stage, non_blocking=True)
             kw = {}
             if self.noise_fn is not None:
                 kw["x_T"], kw["noise"] = self.noise_fn(self.itr, step, E)
-            self.engine.sample(self.obs_trajs[step], deterministic=eval_mode,
-                               min_sampling_std=float(self.model.get_min_sampling_denoising_std()),
-                               seed=self.model.seed, offset=self.model._next_offset(), row_offset=self.env_lo,
-                               actions_out=self.actions_dev, chains_out=self.chains_trajs[step], **kw)
-            self.actions_stage.copy_(self.actions_dev, non_blocking=True)
-            stream.synchronize()
-            output_venv = self.actions_stage.numpy().reshape(E, self.horizon_steps, self.action_dim)
-            action_venv = output_venv[:, : self.act_steps]          # :123
+            if self.normalization is not None:
+                # raw observations in, raw actions out: normalisation, slice and un-normalisation run on the device (8f.4)
+                ro, ra = self.raw_obs_stage[step & 1], self.raw_act_stage[step & 1]
+                ro.copy_(torch.from_numpy(np.ascontiguousarray(prev_obs_venv["state"], np.float64)).reshape(E, -1))
+                self.engine.rollout_step(ro, self.obs_trajs[step], self.actions_dev, self.chains_trajs[step], ra, self.act_steps,
+                                         deterministic=eval_mode, min_sampling_std=float(self.model.get_min_sampling_denoising_std()),
+                                         seed=self.model.seed, offset=self.model._next_offset(), row_offset=self.env_lo, **kw)
+                stream.synchronize()
+                action_venv = ra.numpy().reshape(E, self.act_steps, self.action_dim)
+            else:
+                self.obs_stage.copy_(torch.from_numpy(np.ascontiguousarray(prev_obs_venv["state"], np.float32)).reshape(E, -1))
+                self.obs_trajs[step].copy_(self.obs_stage, non_blocking=True)
+                self.engine.sample(self.obs_trajs[step], deterministic=eval_mode,
+                                   min_sampling_std=float(self.model.get_min_sampling_denoising_std()),
+                                   seed=self.model.seed, offset=self.model._next_offset(), row_offset=self.env_lo,
+                                   actions_out=self.actions_dev, chains_out=self.chains_trajs[step], **kw)
+                self.actions_stage.copy_(self.actions_dev, non_blocking=True)
+                stream.synchronize()
+                output_venv = self.actions_stage.numpy().reshape(E, self.horizon_steps, self.action_dim)
+                action_venv = output_venv[:, : self.act_steps]      # :123
             obs_venv, reward_venv, terminated_venv, truncated_venv, _info = self.venv.step(np.array(action_venv))
             done_venv = terminated_venv | truncated_venv
             reward_trajs[step] = reward_venv
@@ -207,7 +229,11 @@ class TrainPPODiffusionAgent:
         if self.reward_scale_running:                                # :232-236 (running statistics over ALL env copies: gathered, then this rank's columns)
             scaled = self.running_reward_scaler(reward=self._gather_envs(reward_trajs).T, first=self._gather_envs(firsts_trajs)[:-1].T).T
             reward_trajs = np.ascontiguousarray(scaled[:, self.env_lo:self.env_hi])
-        next_values = eng.value(np.ascontiguousarray(obs_venv["state"], np.float32).reshape(E, -1))   # :252
+        last_obs = obs_venv["state"]
+        if self.normalization is not None:                           # the raw env's last observation: normalize_obs on the host (tiny)
+            n = self.normalization
+            last_obs = 2 * ((np.asarray(last_obs, np.float64) - n["obs_min"]) / (n["obs_max"] - n["obs_min"] + 1e-6) - 0.5)
+        next_values = eng.value(np.ascontiguousarray(last_obs, np.float32).reshape(E, -1))   # :252
         advantages_k, returns_k = eng.gae(np.ascontiguousarray(reward_trajs), terminated_trajs, values_k.reshape(S, E),
                                           next_values, self.reward_scale_const, self.gamma, self.gae_lambda)
 

@@ -182,6 +182,7 @@ struct dppo_handle {
     int last_path = 0;    // sampler path of the last dppo_sample: 1 cluster, 2 layered fp32, 3 tensor
     int force_path = 0;   // test hook: 0 auto, 1 force cluster sampler, 2 forbid it
     struct TcState* tc = nullptr;   // tcgen05 path state (tc_path.cuh)
+    float* env_norm = nullptr;      // device [2 * obs_dim + 2 * action_dim]: obs_min, obs_max, action_min, action_max (dppo_set_env_normalization)
     struct TsState* ts = nullptr;   // split-precision tcgen05 path state (ts_path.cuh, DPPO_PREC_BF16X3)
     // live GEMM timing (dppo_profile_*): event pairs recorded around GEMM-class launches
     int prof_on = 0;

@@ -325,6 +325,7 @@ extern "C" void dppo_destroy(dppo_handle* h) {
             cudaIpcCloseMemHandle(h->peer_grads[0][p]); cudaIpcCloseMemHandle(h->peer_grads[1][p]); cudaIpcCloseMemHandle(h->peer_flags[p]);
         }
     }
+    cudaFree(h->env_norm);
     cudaFree(h->params); cudaFree(h->sched); cudaFree(h->grads_buf[0]); cudaFree(h->grads_buf[1]); /* gsum lives inside grads_buf[1] */ cudaFree(h->flags); cudaFree(h->scalars);
     for (int i = 0; i < 2; ++i) { cudaFree(h->opt[i].m); cudaFree(h->opt[i].v); }
     for (int net = 0; net < 4; ++net) { ActorDerived& d = h->ad[net]; cudaFree(d.sinemb); cudaFree(d.thpre); cudaFree(d.temb); cudaFree(d.bt); cudaFree(d.w0p); }
@@ -696,12 +697,72 @@ static int sample_layered_fp32(dppo_handle* h, cudaStream_t s, const float* obs,
     return 0;
 }
 
+// ---- env-side glue: MujocoLocomotionLowdimWrapper's normalisation around the sampler
+// normalize_obs (mujoco_locomotion_lowdim.py:57-58): float64 raw observation, fp32 constants, fp32 denominator (max - min + 1e-6),
+// float64 arithmetic, then the agent's cast to fp32 (train_ppo_diffusion_agent.py:111-113)
+__global__ void env_normalize_obs_kernel(const double* __restrict__ raw, int n, int obs_dim, const float* __restrict__ omin, const float* __restrict__ omax,
+                                         float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int j = i % obs_dim;
+    const double den = (double)__fadd_rn(__fsub_rn(omax[j], omin[j]), 1e-6f);
+    const double q = __ddiv_rn(__dsub_rn(raw[i], (double)omin[j]), den);
+    out[i] = (float)__dmul_rn(2.0, __dsub_rn(q, 0.5));
+}
+__global__ void env_unnormalize_actions_kernel(const float* __restrict__ actions, int B, int A, int act_cols, int Da, const float* __restrict__ amin,
+                                               const float* __restrict__ amax, float* __restrict__ raw) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * act_cols) return;
+    const int r = i / act_cols, a = i % act_cols;
+    raw[i] = env_unnormalize_action(actions[(size_t)r * A + a], amin[a % Da], amax[a % Da]);
+}
+struct EnvEpi { float* raw_actions; int act_steps; };
+static int sample_impl(dppo_handle* h, const float* obs, int B, int deterministic, int use_base_policy,
+                       float min_sampling_std, uint64_t seed, uint64_t offset, int64_t row_offset,
+                       const float* xT, const float* noise, float* actions, float* chains, dppo_stream_t st, const EnvEpi* env);
 extern "C" int dppo_sample(dppo_handle* h, const float* obs, int B, int deterministic, int use_base_policy,
                            float min_sampling_std, uint64_t seed, uint64_t offset, int64_t row_offset,
                            const float* xT, const float* noise, float* actions, float* chains, dppo_stream_t st) {
+    return sample_impl(h, obs, B, deterministic, use_base_policy, min_sampling_std, seed, offset, row_offset, xT, noise, actions, chains, st, nullptr);
+}
+extern "C" int dppo_set_env_normalization(dppo_handle* h, const float* obs_min, const float* obs_max, const float* action_min, const float* action_max) {
+    ENTER(h);
+    if (!obs_min || !obs_max || !action_min || !action_max) DPPO_FAIL(-1, "dppo_set_env_normalization: null argument");
+    const int od = h->cfg.obs_dim, ad = h->cfg.action_dim;
+    if (!h->env_norm) CUDA_TRY(cudaMalloc(&h->env_norm, (size_t)(2 * od + 2 * ad) * sizeof(float)));
+    CUDA_TRY(cudaMemcpy(h->env_norm, obs_min, od * sizeof(float), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(h->env_norm + od, obs_max, od * sizeof(float), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(h->env_norm + 2 * od, action_min, ad * sizeof(float), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(h->env_norm + 2 * od + ad, action_max, ad * sizeof(float), cudaMemcpyHostToDevice));
+    return 0;
+}
+extern "C" int dppo_rollout_step(dppo_handle* h, const double* raw_obs, int E, int deterministic, int use_base_policy, float min_sampling_std,
+                                 uint64_t seed, uint64_t offset, int64_t row_offset, const float* xT, const float* noise,
+                                 float* obs_out, float* actions, float* chains, float* raw_actions, int act_steps, dppo_stream_t st) {
+    ENTER(h); cudaStream_t s = (cudaStream_t)st; const Geom& g = h->g;
+    if (!raw_obs || !obs_out || !actions || !raw_actions || E < 1 || act_steps < 1 || act_steps > h->cfg.horizon_steps)
+        DPPO_FAIL(-1, "dppo_rollout_step: bad arguments");
+    if (!h->env_norm) DPPO_FAIL(-1, "dppo_rollout_step: call dppo_set_env_normalization first");
+    const int od = h->cfg.obs_dim;
+    env_normalize_obs_kernel<<<nblk((size_t)E * g.Do, 128), 128, 0, s>>>(raw_obs, E * g.Do, od, h->env_norm, h->env_norm + od, obs_out); KLAUNCH(h); KCHECK();
+    EnvEpi env{raw_actions, act_steps};
+    return sample_impl(h, obs_out, E, deterministic, use_base_policy, min_sampling_std, seed, offset, row_offset, xT, noise, actions, chains, st, &env);
+}
+static int sample_impl(dppo_handle* h, const float* obs, int B, int deterministic, int use_base_policy,
+                       float min_sampling_std, uint64_t seed, uint64_t offset, int64_t row_offset,
+                       const float* xT, const float* noise, float* actions, float* chains, dppo_stream_t st, const EnvEpi* env) {
     ENTER(h); cudaStream_t s = (cudaStream_t)st; const Geom& g = h->g;
     if (!obs || !actions || B < 0) DPPO_FAIL(-1, "dppo_sample: bad arguments");
     if (B == 0) return 0;
+    const int od_ = h->cfg.obs_dim, ad_ = h->cfg.action_dim;
+    const float* amin = h->env_norm ? h->env_norm + 2 * od_ : nullptr; const float* amax = h->env_norm ? h->env_norm + 2 * od_ + ad_ : nullptr;
+    // paths without the fused epilogue: one more small kernel after the chain
+    auto env_tail = [&]() -> int {
+        if (!env) return 0;
+        const int ac = env->act_steps * ad_;
+        env_unnormalize_actions_kernel<<<nblk((size_t)B * ac, 128), 128, 0, s>>>(actions, B, g.A, ac, ad_, amin, amax, env->raw_actions); KLAUNCH(h); KCHECK();
+        return 0;
+    };
     SampleHyper hp;
     hp.dcv = h->cfg.denoised_clip_value; hp.rcv = h->cfg.randn_clip_value; hp.facv = h->cfg.final_action_clip_value;
     hp.min_std = min_sampling_std >= 0.f ? min_sampling_std : h->cfg.min_sampling_denoising_std;
@@ -719,6 +780,7 @@ extern "C" int dppo_sample(dppo_handle* h, const float* obs, int B, int determin
         p.o = g.ao; p.obs = obs; p.xT = xT; p.noise = noise; p.actions = actions; p.chains = chains; p.sch = h->sched;
         p.B = B; p.A = g.A; p.Do = g.Do; p.T = g.T; p.K = g.K; p.td = g.td; p.use_base_policy = use_base_policy;
         p.hp = hp; p.seed = seed; p.offset = offset; p.row_offset = row_offset;
+        if (env) { p.raw_actions = env->raw_actions; p.act_min = amin; p.act_max = amax; p.act_cols = env->act_steps * ad_; p.Da = ad_; }
         int r = g.A <= 12 ? cluster_dispatch<12>(h, s, p, B) : (g.A <= 24 ? cluster_dispatch<24>(h, s, p, B) : cluster_dispatch<32>(h, s, p, B));
         if (r == 0) { h->last_path = 1; return 0; }
         if (h->force_path == 1) return r;
@@ -727,10 +789,12 @@ extern "C" int dppo_sample(dppo_handle* h, const float* obs, int B, int determin
     }
     if (tensor && !split && fc_ok(h)) {
         h->last_path = 4;
-        return fc_sample(h, s, obs, B, use_base_policy, hp, seed, offset, row_offset, xT, noise, actions, chains);
+        DPPO_TRY(fc_sample(h, s, obs, B, use_base_policy, hp, seed, offset, row_offset, xT, noise, actions, chains));
+        return env_tail();
     }
     h->last_path = tensor ? 3 : 2;
-    return sample_layered_fp32(h, s, obs, B, use_base_policy, hp, seed, offset, row_offset, xT, noise, actions, chains, tensor);
+    DPPO_TRY(sample_layered_fp32(h, s, obs, B, use_base_policy, hp, seed, offset, row_offset, xT, noise, actions, chains, tensor));
+    return env_tail();
 }
 
 static int stage_reserve(dppo_handle* h, size_t bytes) {

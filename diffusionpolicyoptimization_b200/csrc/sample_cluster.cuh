@@ -33,7 +33,15 @@ struct ClusterSampleP {
     int B, A, Do, T, K, td, nchunks, use_base_policy;
     SampleHyper hp;
     uint64_t seed, offset; int64_t row_offset;
+    // env-side epilogue: the first act_cols = act_steps * Da entries of every action chunk, un-normalised like
+    // MujocoLocomotionLowdimWrapper.unnormalize_action, written where the env workers read them (pinned host memory or device)
+    float* raw_actions; const float* act_min; const float* act_max; int act_cols, Da;
 };
+// env/gym_utils/wrapper/mujoco_locomotion_lowdim.py:60-62 in NumPy's fp32 evaluation order (no FMA contraction)
+__device__ __forceinline__ float env_unnormalize_action(float a, float amin, float amax) {
+    const float a01 = __fdiv_rn(__fadd_rn(a, 1.f), 2.f);
+    return __fadd_rn(__fmul_rn(a01, __fsub_rn(amax, amin)), amin);
+}
 
 template <int AP, int R>
 constexpr size_t cluster_sample_smem_floats() {
@@ -229,7 +237,11 @@ __global__ void __launch_bounds__(CS_THREADS, 1) sample_cluster_kernel(const Clu
                     xs[tid] = xn;
                     if (crank == 0) {
                         if (p.chains && t <= K) p.chains[((size_t)row * (K + 1) + (K - t)) * A + a] = xn;
-                        if (t == 0) p.actions[(size_t)row * A + a] = xn;
+                        if (t == 0) {
+                            p.actions[(size_t)row * A + a] = xn;
+                            if (p.raw_actions && a < p.act_cols)
+                                p.raw_actions[(size_t)row * p.act_cols + a] = env_unnormalize_action(xn, p.act_min[a % p.Da], p.act_max[a % p.Da]);
+                        }
                     }
                 }
             }

@@ -147,6 +147,31 @@ class Engine:
                                      _ptr(actions), _ptr(chains), self._stream()), "dppo_sample")
         return actions, chains
 
+    def set_env_normalization(self, obs_min, obs_max, action_min, action_max):
+        """The task's normalization.npz (mujoco_locomotion_lowdim.py:21-25): enables `rollout_step`."""
+        arrs = [_as_host(a).reshape(-1) for a in (obs_min, obs_max, action_min, action_max)]
+        if arrs[0].size != self.cfg.obs_dim or arrs[1].size != self.cfg.obs_dim or arrs[2].size != self.cfg.action_dim or arrs[3].size != self.cfg.action_dim:
+            raise ValueError("normalisation arrays must have obs_dim / action_dim entries")
+        L.check(self.lib.dppo_set_env_normalization(self.h, *[_ptr(a) for a in arrs]), "dppo_set_env_normalization")
+
+    def rollout_step(self, raw_obs, obs_out, actions_out, chains_out, raw_actions_out, act_steps, deterministic=False, use_base_policy=False,
+                     min_sampling_std: float = -1.0, seed: int = 0, offset: int = 0, row_offset: int = 0, x_T=None, noise=None):
+        """One rollout step around RAW env data: `raw_obs` float64 [E, To*obs_dim] and `raw_actions_out` fp32
+        [E, act_steps*action_dim] are pinned host tensors (or CUDA tensors) the kernels read / write directly; `obs_out` [E,Do],
+        `actions_out` [E,A], `chains_out` [E,K+1,A] are CUDA tensors.  Asynchronous: synchronise the stream before the envs read
+        `raw_actions_out`."""
+        E = obs_out.shape[0]
+        if raw_obs.dtype != torch.float64 or raw_actions_out.dtype != torch.float32:
+            raise ValueError("raw_obs must be float64 and raw_actions_out float32")
+        for t in (raw_obs, raw_actions_out):
+            if not (t.is_cuda or t.is_pinned()) or not t.is_contiguous():
+                raise ValueError("host tensors handed to rollout_step must be pinned and contiguous")
+        x_T = None if x_T is None else _as_dev(x_T, self.dev).reshape(E, self.A)
+        noise = None if noise is None else _as_dev(noise, self.dev).reshape(self.T, E, self.A)
+        L.check(self.lib.dppo_rollout_step(self.h, _ptr(raw_obs), E, int(deterministic), int(use_base_policy), float(min_sampling_std),
+                                           int(seed), int(offset), int(row_offset), _ptr(x_T), _ptr(noise), _ptr(obs_out), _ptr(actions_out),
+                                           _ptr(chains_out), _ptr(raw_actions_out), int(act_steps), self._stream()), "dppo_rollout_step")
+
     def sample_host(self, obs: np.ndarray, actions_out: np.ndarray, chains_out: Optional[np.ndarray],
                     deterministic=False, use_base_policy=False, min_sampling_std: float = -1.0,
                     seed: int = 0, offset: int = 0, row_offset: int = 0, x_T=None, noise=None):

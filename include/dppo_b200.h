@@ -135,6 +135,20 @@ int dppo_sample(dppo_handle* h, const float* obs, int B, int deterministic, int 
                 float min_sampling_std, uint64_t seed, uint64_t offset, int64_t row_offset,
                 const float* x_T_or_null, const float* noise_or_null,
                 float* actions, float* chains_or_null, dppo_stream_t s);
+/* Env-side glue.  dppo_set_env_normalization: the four arrays of the task's normalization.npz
+ * (obs_min / obs_max [obs_dim], action_min / action_max [action_dim], host fp32), as loaded by
+ * env/gym_utils/wrapper/mujoco_locomotion_lowdim.py:21-25.
+ * dppo_rollout_step = one rollout step of agent/finetune/train_ppo_diffusion_agent.py:106-132 around RAW env data:
+ *   raw_obs [E][cond_steps*obs_dim] float64 (device, or pinned host memory read through UVA) is normalised exactly like
+ *   normalize_obs (:57-58) + the agent's fp32 cast (:111-113) into obs_out [E][Do] (device, e.g. obs_trajs[step]);
+ *   the chain runs as in dppo_sample (actions [E][A] and chains on the device);
+ *   raw_actions [E][act_steps*action_dim] fp32 (device, or pinned host memory) receives trajectories[:, :act_steps] (:121)
+ *   un-normalised like unnormalize_action (:60-62) - written by the sampling kernel's own epilogue on the persistent
+ *   cluster path (small env batches): two launches, no copy calls; the caller synchronises the stream and steps the envs. */
+int dppo_set_env_normalization(dppo_handle* h, const float* obs_min, const float* obs_max, const float* action_min, const float* action_max);
+int dppo_rollout_step(dppo_handle* h, const double* raw_obs, int E, int deterministic, int use_base_policy, float min_sampling_std,
+                      uint64_t seed, uint64_t offset, int64_t row_offset, const float* xT, const float* noise,
+                      float* obs_out, float* actions, float* chains, float* raw_actions, int act_steps, dppo_stream_t s);
 /* Same call with HOST buffers (the reference caller passes NumPy and does np.array() on the result:
  * train_ppo_diffusion_agent.py:111-132).  H2D + kernel + D2H + stream sync inside. */
 int dppo_sample_host(dppo_handle* h, const float* obs_host, int B, int deterministic, int use_base_policy,

@@ -11,7 +11,7 @@ from diffusionpolicyoptimization_b200.agent.finetune.train_ppo_diffusion_agent i
 from helpers import rel_err, max_abs
 from oracle import dppo_loop as OL
 from oracle import dppo_oracle as O
-from toy_env import ToyVecEnv
+from toy_env import NormalizingVecWrapper, RawToyVecEnv, ToyVecEnv
 
 pytestmark = pytest.mark.gpu
 
@@ -74,6 +74,57 @@ def test_two_iterations_match_the_reference_loop():
     frac_bad = np.mean(np.abs(got_w - want_w) > 0.25 * LR)
     assert frac_bad < 1e-2, frac_bad
     np.testing.assert_array_equal(model.engine.get_weights(L.NET_ACTOR), O.flatten_params(o.actor))   # base net frozen
+
+
+def test_fused_env_normalisation_equals_the_reference_wrapper():
+    """the agent around a RAW env with `normalization=` (normalize_obs / slice / unnormalize_action on the device,
+    pinned exchange) must reproduce, bit for bit, the agent around the same env behind the reference's normalising wrapper
+    (env/gym_utils/wrapper/mujoco_locomotion_lowdim.py:57-62 restated in tests/toy_env.py)."""
+    rng = np.random.default_rng(12)
+    norm = {"obs_min": rng.uniform(-3, -1, 11).astype(np.float32), "obs_max": rng.uniform(1, 4, 11).astype(np.float32),
+            "action_min": rng.uniform(-1.2, -0.8, 3).astype(np.float32), "action_max": rng.uniform(0.8, 1.2, 3).astype(np.float32)}
+    res = []
+    for fused in (False, True):
+        o = O.make_oracle("hopper", seed=23)
+        model = make_model(o)
+        raw = RawToyVecEnv(E, 11, 3, norm, seed=3)
+        venv = raw if fused else NormalizingVecWrapper(raw, norm)
+        agent = TrainPPODiffusionAgent(model, venv, n_envs=E, n_steps=S, act_steps=ACT_STEPS, n_train_itr=1, batch_size=160, update_epochs=1,
+                                       actor_lr=LR, force_train=True, noise_fn=noise_fn, shuffle_fn=shuffle_fn,
+                                       normalization=norm if fused else None)
+        n0 = model.engine.launch_count()
+        r = agent.run_iteration()
+        res.append((agent.obs_trajs.cpu().numpy().copy(), agent.chains_trajs.cpu().numpy().copy(), model.engine.get_weights(L.NET_ACTOR_FT).copy(),
+                    r["pg_loss"], r["avg_episode_reward"]))
+        model.engine.close()
+    for a, b in zip(res[0], res[1]):
+        np.testing.assert_array_equal(a, b)
+    assert np.abs(res[0][0]).max() <= 1.0 + 1e-5                     # the rollout buffer holds normalised observations
+
+
+def test_rollout_step_is_two_launches_on_the_cluster_path():
+    o = O.make_oracle("hopper", seed=24)
+    model = make_model(o)
+    e = model.engine
+    rng = np.random.default_rng(1)
+    norm = {"obs_min": -np.ones(11, np.float32) * 2, "obs_max": np.ones(11, np.float32) * 3, "action_min": -np.ones(3, np.float32), "action_max": np.ones(3, np.float32) * 2}
+    e.set_env_normalization(**norm)
+    B, act_steps = 40, 4
+    raw_obs = torch.from_numpy(rng.uniform(-2, 3, (B, 11))).pin_memory()
+    raw_act = torch.zeros(B, act_steps * 3).pin_memory()
+    obs_out = torch.zeros(B, 11, device="cuda"); act = torch.zeros(B, 12, device="cuda"); ch = torch.zeros(B, 11, 12, device="cuda")
+    n0 = e.launch_count()
+    e.rollout_step(raw_obs, obs_out, act, ch, raw_act, act_steps, seed=5, offset=9)
+    torch.cuda.synchronize()
+    assert e.launch_count() - n0 == 2 and e.last_path() == 1         # normalise kernel + the persistent sampler (un-normalising epilogue)
+    want_obs = (2 * ((raw_obs.numpy() - norm["obs_min"]) / (norm["obs_max"] - norm["obs_min"] + 1e-6) - 0.5)).astype(np.float32)
+    np.testing.assert_array_equal(obs_out.cpu().numpy(), want_obs)
+    a = act.cpu().numpy().reshape(B, 4, 3)[:, :act_steps]
+    want_act = ((a + 1) / 2) * (norm["action_max"] - norm["action_min"]) + norm["action_min"]
+    np.testing.assert_array_equal(raw_act.numpy().reshape(B, act_steps, 3), want_act.astype(np.float32))
+    a2, _ = e.sample(obs_out, seed=5, offset=9)                      # same chain as the plain sampler on the normalised observations
+    assert torch.equal(a2, act)
+    e.close()
 
 
 def test_eval_iteration_does_not_train_and_tensor_mode_runs():

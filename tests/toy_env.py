@@ -39,3 +39,45 @@ class ToyVecEnv:
         self.s[done] = self.s0[done]          # auto-reset like the reference's async vector env
         self.t[done] = 0
         return self._obs(), reward, terminated, truncated, [{} for _ in range(self.E)]
+
+
+class RawToyVecEnv(ToyVecEnv):
+    """The same dynamics behind RAW interfaces, like a MuJoCo env before MujocoLocomotionLowdimWrapper: float64 observations in
+    physical units, actions in physical units.  `norm` holds the task's obs_min / obs_max / action_min / action_max (fp32)."""
+
+    def __init__(self, n_envs, obs_dim, action_dim, norm, **kw):
+        self.norm = norm
+        super().__init__(n_envs, obs_dim, action_dim, **kw)
+
+    def _obs(self):
+        n = self.norm       # physical units: invert normalize_obs in float64
+        raw = (self.s / 2 + 0.5) * (n["obs_max"].astype(np.float64) - n["obs_min"] + 1e-6) + n["obs_min"]
+        return {"state": raw[:, None, :]}
+
+    def step(self, raw_action):
+        n = self.norm       # back to [-1, 1] for the toy dynamics
+        a = (np.asarray(raw_action, np.float64) - n["action_min"]) / (n["action_max"].astype(np.float64) - n["action_min"]) * 2 - 1
+        return super().step(a)
+
+
+class NormalizingVecWrapper:
+    """env/gym_utils/wrapper/mujoco_locomotion_lowdim.py:57-62 restated for a vector env (same NumPy expressions per element)."""
+
+    def __init__(self, env, norm):
+        self.env = env
+        self.obs_min, self.obs_max = norm["obs_min"], norm["obs_max"]
+        self.action_min, self.action_max = norm["action_min"], norm["action_max"]
+
+    def normalize_obs(self, obs):
+        return 2 * ((obs - self.obs_min) / (self.obs_max - self.obs_min + 1e-6) - 0.5)
+
+    def unnormalize_action(self, action):
+        action = (action + 1) / 2  # [-1, 1] -> [0, 1]
+        return action * (self.action_max - self.action_min) + self.action_min
+
+    def reset_arg(self, options_list=None):
+        return {"state": self.normalize_obs(self.env.reset_arg(options_list)["state"])}
+
+    def step(self, action):
+        obs, r, term, trunc, info = self.env.step(self.unnormalize_action(action))
+        return {"state": self.normalize_obs(obs["state"])}, r, term, trunc, info
