@@ -108,6 +108,31 @@ class TrainPPODiffusionAgent:
         self.inds_stage = torch.zeros(self.batch_size, dtype=torch.int32).pin_memory()
         self.metrics_stage = torch.zeros(8).pin_memory()
 
+    # ---------------------------------------------------------------- checkpoints (train_agent.py:127-142)
+    def save_model(self, checkpoint_dir):
+        """`state_{itr}.weights.h5` in the reference's Keras layout (rank 0 only) + `state_{itr}.opt.npz` with what the reference
+        does NOT save but a true resume needs: AdamW moments / step, the optimizer iteration count, the reward scaler."""
+        import os
+        if self.rank != 0:
+            return None
+        os.makedirs(checkpoint_dir, exist_ok=True)
+        path = os.path.join(checkpoint_dir, f"state_{self.itr}.weights.h5")
+        self.model.save_weights(path)
+        m, v, step = self.engine.get_opt_state(1)
+        extra = dict(m=m, v=v, step=step, itr=self.itr, opt_iterations=self.opt_iterations, cnt_train_step=self.cnt_train_step)
+        np.savez(os.path.join(checkpoint_dir, f"state_{self.itr}.opt.npz"), **extra)
+        log.info("Saved model to %s", path)
+        return path
+
+    def load(self, checkpoint_dir, itr, with_optimizer=True):
+        import os
+        self.model.load_weights(os.path.join(checkpoint_dir, f"state_{itr}.weights.h5"))
+        side = os.path.join(checkpoint_dir, f"state_{itr}.opt.npz")
+        if with_optimizer and os.path.exists(side):
+            z = np.load(side, allow_pickle=False)
+            self.engine.set_opt_state(1, z["m"], z["v"], int(z["step"]))
+            self.itr, self.opt_iterations, self.cnt_train_step = int(z["itr"]), int(z["opt_iterations"]), int(z["cnt_train_step"])
+
     def reset_env_all(self, options_venv=None):
         """train_agent.py:144-153."""
         options_venv = options_venv if options_venv is not None else [{} for _ in range(self.n_envs)]

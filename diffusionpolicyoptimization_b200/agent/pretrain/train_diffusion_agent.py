@@ -89,3 +89,41 @@ class TrainDiffusionAgent:
         for _ in range(self.n_epochs):
             self.run_epoch()
         return self.loss_history
+
+    # ---------------------------------------------------------------- checkpoints (agent/pretrain/train_agent.py:150-162)
+    def _ema_weights(self):
+        flat = self.engine.get_weights(L.NET_ACTOR_EMA)
+        out, off = [], 0
+        for shp in self.model.network.shapes:
+            n = int(np.prod(shp)); out.append(flat[off:off + n].reshape(shp)); off += n
+        return out
+
+    def save_model(self, checkpoint_dir, epoch=None):
+        """`state_{epoch}.weights.h5` (network) and `ema_state_{epoch}.weights.h5` (EMA copy) in the reference's Keras layout, plus
+        `state_{epoch}.opt.npz` with the AdamW moments / step / schedule position the reference does not save."""
+        import os
+        from ...util.keras_h5 import save_keras_weights_h5
+        epoch = self.epoch if epoch is None else epoch
+        os.makedirs(checkpoint_dir, exist_ok=True)
+        path = os.path.join(checkpoint_dir, f"state_{epoch}.weights.h5")
+        net = self.model.network
+        net.save_weights(path)
+        save_keras_weights_h5(path.replace("state_", "ema_state_"), self._ema_weights(), net.keras_variable_paths())
+        m, v, step = self.engine.get_opt_state(L.OPT_PRETRAIN)
+        np.savez(os.path.join(checkpoint_dir, f"state_{epoch}.opt.npz"), m=m, v=v, step=step, epoch=self.epoch, opt_iterations=self.opt_iterations)
+        log.info("Saved model to %s", path)
+        return path
+
+    def load_model(self, checkpoint_dir, epoch, with_optimizer=True):
+        import os
+        from ...util.keras_h5 import load_keras_weights_h5
+        path = os.path.join(checkpoint_dir, f"state_{epoch}.weights.h5")
+        net = self.model.network
+        net.load_weights(path)
+        ema = load_keras_weights_h5(path.replace("state_", "ema_state_"), net.keras_variable_paths(), net.shapes)
+        self.engine.set_weights(L.NET_ACTOR_EMA, np.concatenate([w.reshape(-1) for w in ema]))
+        side = os.path.join(checkpoint_dir, f"state_{epoch}.opt.npz")
+        if with_optimizer and os.path.exists(side):
+            z = np.load(side)
+            self.engine.set_opt_state(L.OPT_PRETRAIN, z["m"], z["v"], int(z["step"]))
+            self.epoch, self.opt_iterations = int(z["epoch"]), int(z["opt_iterations"])

@@ -26,3 +26,7 @@ class CriticObs(_Net):
         return self._engine.value(state).reshape(-1, 1)
 
     call = __call__
+
+    def keras_variable_paths(self, prefix=""):
+        from ...util.keras_h5 import keras_paths_critic_obs
+        return keras_paths_critic_obs(prefix)

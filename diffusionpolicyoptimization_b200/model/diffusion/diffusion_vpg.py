@@ -44,6 +44,21 @@ class VPGDiffusion(DiffusionModel):
         self.critic = critic
         critic._bind(self.engine, L.NET_CRITIC)
 
+    # ---- Keras model.save_weights / load_weights of the whole fine-tuning model (agent/finetune/train_agent.py:127-142): one
+    #      `.weights.h5` file with actor/ (= network), actor_ft/ and critic/ (util/keras_h5.py documents the assumed layout)
+    def save_weights(self, path):
+        from ...util.keras_h5 import write_h5
+        data = {}
+        for prefix, net in (("actor", self.actor), ("actor_ft", self.actor_ft), ("critic", self.critic)):
+            for pth, w in zip(net.keras_variable_paths(prefix), net.get_weights()):
+                data[pth] = w
+        write_h5(str(path), data)
+
+    def load_weights(self, path):
+        from ...util.keras_h5 import load_keras_weights_h5
+        for prefix, net in (("actor", self.actor), ("actor_ft", self.actor_ft), ("critic", self.critic)):
+            net.set_weights(load_keras_weights_h5(str(path), net.keras_variable_paths(prefix), net.shapes))
+
     # ---- diffusion_vpg.py:114-148
     def step(self):
         if type(self.min_sampling_denoising_std) is not float:

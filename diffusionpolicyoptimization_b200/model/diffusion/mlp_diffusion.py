@@ -28,3 +28,8 @@ class DiffusionMLP(_Net):
         return eps.reshape(-1, self.horizon_steps, self.action_dim)
 
     call = __call__
+
+    def keras_variable_paths(self, prefix=""):
+        """Dataset paths of this network inside a Keras-3 `.weights.h5` file, in flat variable order (util/keras_h5.py)."""
+        from ...util.keras_h5 import keras_paths_diffusion_mlp
+        return keras_paths_diffusion_mlp(prefix)

@@ -127,6 +127,33 @@ def test_rollout_step_is_two_launches_on_the_cluster_path():
     e.close()
 
 
+def test_checkpoints_in_the_reference_layout_round_trip(tmp_path):
+    """agent/finetune/train_agent.py:127-142: `state_{itr}.weights.h5` (Keras layout, util/keras_h5.py) + the optimizer side-car."""
+    from diffusionpolicyoptimization_b200.util.keras_h5 import H5Reader
+    o = O.make_oracle("hopper", seed=25)
+    model = make_model(o)
+    agent = TrainPPODiffusionAgent(model, ToyVecEnv(E, 11, 3, seed=3), n_envs=E, n_steps=S, act_steps=ACT_STEPS, n_train_itr=1, batch_size=160,
+                                   update_epochs=1, actor_lr=LR, force_train=True)
+    agent.run_iteration()
+    path = agent.save_model(str(tmp_path))
+    names = set(H5Reader(path).datasets)
+    assert "actor_ft/mlp_mean/input_layer/vars/0" in names and "critic/Q1/output_layer/vars/1" in names and len(names) == 12 + 12 + 8
+    w = [model.engine.get_weights(n).copy() for n in (L.NET_ACTOR, L.NET_ACTOR_FT, L.NET_CRITIC)]
+    mo, vo, so = model.engine.get_opt_state(L.OPT_FINETUNE)
+    model2 = make_model(O.make_oracle("hopper", seed=26))
+    agent2 = TrainPPODiffusionAgent(model2, ToyVecEnv(E, 11, 3, seed=3), n_envs=E, n_steps=S, act_steps=ACT_STEPS, n_train_itr=1, batch_size=160,
+                                    update_epochs=1, actor_lr=LR, force_train=True)
+    agent2.load(str(tmp_path), 1)
+    for n, ww in zip((L.NET_ACTOR, L.NET_ACTOR_FT, L.NET_CRITIC), w):
+        np.testing.assert_array_equal(model2.engine.get_weights(n), ww)
+    m2, v2, s2 = model2.engine.get_opt_state(L.OPT_FINETUNE)
+    assert s2 == so and np.array_equal(m2, mo) and np.array_equal(v2, vo) and agent2.itr == 1 and agent2.opt_iterations == agent.opt_iterations
+    # the restored model behaves identically
+    obs = torch.rand(64, 11, device="cuda") * 2 - 1
+    a1, _ = model.engine.sample(obs, seed=1, offset=3); a2, _ = model2.engine.sample(obs, seed=1, offset=3)
+    assert torch.equal(a1, a2)
+
+
 def test_eval_iteration_does_not_train_and_tensor_mode_runs():
     """itr 0 is an eval iteration (val_freq, :70): deterministic sampling, no update.  Then a bf16 tensor-mode training
     iteration on the library's own Philox stream (>= 2048 rows per minibatch)."""
