@@ -1173,6 +1173,9 @@ static int ppo_indexed_impl(dppo_handle* h, cudaStream_t s, const float* obs_buf
     if (tc_eligible(h, N) && tc_ppo_indexed_ok(h, view) && (adv_std >= 0.f || N_global == N)) {
         DPPO_TRY(tc_ppo_step_indexed(h, s, view, N, N_global, adv_mean, adv_std));
         DPPO_TRY(ppo_apply_tail(h, s, lr, apply, metrics8_host ? d_met : metrics8, grads_out));
+    } else if (ts_eligible(h, N) && ts_ppo_indexed_ok(h, view) && (adv_std >= 0.f || N_global == N)) {
+        DPPO_TRY(ts_ppo_step(h, s, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, N, N_global, adv_mean, adv_std, &view));
+        DPPO_TRY(ppo_apply_tail(h, s, lr, apply, metrics8_host ? d_met : metrics8, grads_out));
     } else {
     const size_t total = (size_t)N * (g.Do + 3 * g.A + 4);
     gather_minibatch_kernel<<<nblk(total, 256), 256, 0, s>>>(obs_buf, chains_buf, oldlogp_buf, returns_buf, values_buf, adv_buf, inds_dev, N, g.K, g.A, g.Do,

@@ -964,15 +964,24 @@ __global__ void ts_pack_critic_kernel(const float* __restrict__ w, CriticOff o, 
     for (size_t i = i0; i < (size_t)Hc; i += stride) W.bias2[i] = w[o.b2 + i] + w[o.bin + i];
 }
 // h0[r] = [x[r] | obs[r / obs_div] | onehot(t_r) | 1 | 0..] as three planes (tc_pack_h0_kernel's layout); one thread per 8 columns
+// flat != nullptr (index-driven minibatch, train_ppo_diffusion_agent.py:292-312 without materialising it): row r is the (rollout row b,
+// denoising index k) pair of flat[r] = b * flatK + k: x = chains[b][k], obs = obs[b], t = flatK - 1 - k; bad indices raise *bad and read row 0
 __global__ void ts_pack_h0_kernel(const float* __restrict__ x, const float* __restrict__ obs, const int* __restrict__ trow, int tconst,
-                                  int N, int A, int Do, int T, int KP0, int obs_div, const SplitT h0, int chainK) {
+                                  int N, int A, int Do, int T, int KP0, int obs_div, const SplitT h0, int chainK,
+                                  const int* __restrict__ flat = nullptr, int flatK = 1, long long flatP = 0, int* __restrict__ bad = nullptr) {
     const int g8 = KP0 / 8;
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)N * g8) return;
     const int r = (int)(i / g8), k0 = (int)(i % g8) * 8;
-    const int t = trow ? (tconst < 0 ? -tconst - 1 - trow[r] : trow[r]) : tconst;
-    const size_t xrow = chainK > 0 ? (size_t)(r / chainK) * (chainK + 1) + (r % chainK) : (size_t)r;
-    const size_t orow = (size_t)(r / obs_div);
+    int t = trow ? (tconst < 0 ? -tconst - 1 - trow[r] : trow[r]) : tconst;
+    size_t xrow = chainK > 0 ? (size_t)(r / chainK) * (chainK + 1) + (r % chainK) : (size_t)r;
+    size_t orow = (size_t)(r / obs_div);
+    if (flat) {
+        int f = flat[r];
+        if (f < 0 || (long long)f >= flatP * flatK) { if (bad && k0 == 0) atomicOr(bad, 1); f = 0; }
+        const int b = f / flatK, k = f % flatK;
+        xrow = (size_t)b * (flatK + 1) + k; orow = (size_t)b; t = flatK - 1 - k;
+    }
     __align__(16) bf16 o3[3][8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -1242,14 +1251,20 @@ static int ts_value(dppo_handle* h, cudaStream_t s, const float* obs, int N, flo
 // PPODiffusion.c_loss + tape.gradient (diffusion_ppo.py:32-132, train_ppo_diffusion_agent.py:340-346).  Leaves
 // [actor_ft grads | critic grads | 8 metrics] in h->grads.  16 plane-GEMM launches + 6 small kernels:
 // adv-stats (second stream) | h0 pack | 4 + 4 forward | loss | 3 + 3 backward | grouped dW + reduce | tail.
+// shapes / alignment the index-driven variant needs (float4 row reads of the resident rollout buffers)
+static bool ts_ppo_indexed_ok(const dppo_handle* h, const TcIdxView& v) {
+    return (h->g.A % 4 == 0) && h->g.A <= 32 && ((((uintptr_t)v.chains | (uintptr_t)v.olp) & 15) == 0);
+}
+// idx (optional): the minibatch is given as flat (rollout row, denoising index) indices into the resident rollout buffers; the h0 pack,
+// the advantage statistics and the loss kernel address those buffers directly (no gathered copy), the row pointers are unused
 static int ts_ppo_step(dppo_handle* h, cudaStream_t s, const float* obs, const float* prev, const float* nxt, const int32_t* inds,
                        const float* returns, const float* oldvalues, const float* advantages, const float* oldlogp,
-                       int N, int64_t N_global, float adv_mean, float adv_std) {
+                       int N, int64_t N_global, float adv_mean, float adv_std, const TcIdxView* idx = nullptr) {
     const Geom& g = h->g; const int KP0 = h->ts->KP0;
     const size_t nA = g.ao.n, nC = g.co.n;
     float* gr = h->grads;
     const bool amish = h->cfg.actor_act == DPPO_ACT_MISH, cmish = h->cfg.critic_act == DPPO_ACT_MISH;
-    const bool loss8 = (g.A % 4 == 0) && g.A <= 32 && ((((uintptr_t)prev | (uintptr_t)nxt | (uintptr_t)oldlogp) & 15) == 0);   // float4 row reads
+    const bool loss8 = idx ? true : (g.A % 4 == 0) && g.A <= 32 && ((((uintptr_t)prev | (uintptr_t)nxt | (uintptr_t)oldlogp) & 15) == 0);   // float4 row reads
     const int nlb = loss8 ? tc_nblk(N, LOSS8_ROWS) : tc_nblk(N, 128);
     const int nrb = (N + 31) / 32;
     const size_t pf = ts_part_floats(h, g.H);
@@ -1286,11 +1301,17 @@ static int ts_ppo_step(dppo_handle* h, cudaStream_t s, const float* obs, const f
     auto fork = [&]() -> int { if (side) { CUDA_TRY(cudaEventRecord(h->aux_ev[0], s)); CUDA_TRY(cudaStreamWaitEvent(sc, h->aux_ev[0], 0)); } return 0; };
     auto join = [&]() -> int { if (side) { CUDA_TRY(cudaEventRecord(h->aux_ev[1], sc)); CUDA_TRY(cudaStreamWaitEvent(s, h->aux_ev[1], 0)); } return 0; };
     // h0 straight from (prev, obs, K-1-inds): tconst = -(K) flags "t = K-1-trow[r]"; the critic reads the same tile (its x / one-hot rows of W0 are zero)
-    ts_pack_h0_kernel<<<tc_nblk((size_t)N * (KP0 / 8), 256), 256, 0, s>>>(prev, obs, inds, -g.K, N, g.A, g.Do, g.T, KP0, 1, ma.h0, 0);
+    if (idx) ts_pack_h0_kernel<<<tc_nblk((size_t)N * (KP0 / 8), 256), 256, 0, s>>>(idx->chains, idx->obs, nullptr, 0, N, g.A, g.Do, g.T, KP0, 1, ma.h0, 0,
+                                                                                     idx->flat, idx->K, idx->P, idx->bad);
+    else ts_pack_h0_kernel<<<tc_nblk((size_t)N * (KP0 / 8), 256), 256, 0, s>>>(prev, obs, inds, -g.K, N, g.A, g.Do, g.T, KP0, 1, ma.h0, 0);
     TC_KCHECK(h);
     mc.h0 = ma.h0;
     DPPO_TRY(fork());
-    if (adv_std < 0.f) { adv_stats_kernel<<<1, 1024, 0, sc>>>(advantages, N, h->scalars); TC_KCHECK(h); }
+    if (adv_std < 0.f) {
+        if (idx) adv_stats_kernel<<<1, 1024, 0, sc>>>(idx->adv, N, h->scalars, idx->flat, idx->K, idx->P);
+        else adv_stats_kernel<<<1, 1024, 0, sc>>>(advantages, N, h->scalars);
+        TC_KCHECK(h);
+    }
     else { set_scalars_kernel<<<1, 1, 0, sc>>>(h->scalars, adv_mean, adv_std); TC_KCHECK(h); }
     DPPO_TRY(ts_mlp_forward(h, s, ma, N));
     DPPO_TRY(ts_mlp_forward(h, sc, mc, N));
@@ -1305,6 +1326,7 @@ static int ts_ppo_step(dppo_handle* h, cudaStream_t s, const float* obs, const f
     if (loss8) {
         // loss, metric partial sums, the two-plane padded gradient seeds and the output-bias column partials in one pass
         TcIdxView iv; memset(&iv, 0, sizeof(iv));
+        if (idx) iv = *idx;
         tc_ppo_loss8_kernel<<<nlb, 256, 0, s>>>(prev, nxt, eps, inds, returns, oldvalues, advantages, oldlogp, val, h->scalars, h->sched, hp, N,
                                                depsb.p[0], dvalb.p[0], bsum, colb3, iv, depsb.p[1], dvalb.p[1]);
         TC_KCHECK(h);

@@ -226,3 +226,33 @@ def test_split_pretrain_and_large_batch_sampler(pair):
     print(f"bf16x3 sampler: max {float(diff.max()):.2e} mean {float(diff.mean()):.2e}")
     assert rel_err(a, want.trajectories.reshape(B, -1)) < 1e-4 and float(diff.mean()) < 1e-6
     assert float((ch.cpu() - want.chains.reshape(B, d.ft_denoising_steps + 1, -1)).abs().mean()) < 1e-6
+
+
+def test_split_index_driven_update_reads_the_rollout_buffers_directly(pair):
+    """dppo_ppo_step_indexed in the bf16x3 mode: no materialised minibatch (h0 pack, advantage statistics and loss kernel address the
+    resident rollout through the flat indices); bit-identical to dppo_ppo_step on the rows gathered on the host (train_ppo_diffusion_agent.py:292-312)."""
+    o, e = pair
+    d = o.d
+    P, K, A, N = 600, d.ft_denoising_steps, d.A, 4096
+    obs, x_T, noise = O.make_rollout_inputs(o, P, seed=77)
+    chains = o.sample(obs, x_T, noise).chains.reshape(P, K + 1, A)
+    g = torch.Generator().manual_seed(5)
+    olp = torch.randn(P, K, A, generator=g) * 0.3 - 1.0
+    ret, val, adv = torch.randn(P, generator=g), torch.randn(P, generator=g), torch.randn(P, generator=g)
+    flat = torch.randint(0, P * K, (N,), generator=g, dtype=torch.int64)
+    b, k = flat // K, flat % K
+    n0 = e.launch_count()
+    m1, g1 = e.ppo_step_indexed(_flat(obs), chains, olp, ret, val, adv, flat.to(torch.int32).cuda(), lr=0.0, apply=False, want_grads=True)
+    launches_indexed = e.launch_count() - n0
+    n1 = e.launch_count()
+    m2, g2 = e.ppo_step(_flat(obs)[b], chains[b, k], chains[b, k + 1], k.to(torch.int32), ret[b], val[b], adv[b], olp[b, k],
+                        lr=0.0, apply=False, want_grads=True)
+    torch.cuda.synchronize()
+    assert launches_indexed == e.launch_count() - n1 + 1         # + the NaN-on-bad-index kernel of the device variant, no gather kernel
+    assert torch.equal(m1, m2) and torch.equal(g1, g2)
+    w0 = e.get_weights(L.NET_ACTOR_FT).copy()
+    bad = flat.to(torch.int32).clone(); bad[3] = -1
+    assert torch.isnan(e.ppo_step_indexed(_flat(obs), chains, olp, ret, val, adv, bad.cuda(), lr=1e-3, apply=True)).all()
+    np.testing.assert_array_equal(e.get_weights(L.NET_ACTOR_FT), w0)
+    m0, v0, s0 = e.get_opt_state(L.OPT_FINETUNE)
+    e.set_opt_state(L.OPT_FINETUNE, m0, v0, s0 - 1)              # the skipped update still counted a step: undo for the shared fixture
