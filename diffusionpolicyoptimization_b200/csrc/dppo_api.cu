@@ -1326,24 +1326,29 @@ extern "C" int dppo_debug_tc_gemm(dppo_handle* h, const void* A, int a_mn, int64
     return r < 0 ? r : 0;
 }
 
-__global__ void ts_split_planes_kernel(const float* __restrict__ src, size_t n, bf16* __restrict__ p0, bf16* __restrict__ p1, bf16* __restrict__ p2) {
+// f16_scale > 0: two fp16 planes of f16_scale * src (the forward operand format); else three bf16 planes
+__global__ void ts_split_planes_kernel(const float* __restrict__ src, size_t n, bf16* __restrict__ p0, bf16* __restrict__ p1, bf16* __restrict__ p2, float f16_scale = 0.f) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) ts::split_bf16_3(src[i], p0[i], p1[i], p2[i]);
+    if (i >= n) return;
+    if (f16_scale > 0.f) ts::split_f16(src[i] * f16_scale, p0[i], p1[i]);
+    else ts::split_bf16_3(src[i], p0[i], p1[i], p2[i]);
 }
 extern "C" int dppo_debug_split_gemm(dppo_handle* h, const float* A, int a_mn, int64_t lda, const float* B, int b_mn, int64_t ldb,
                                      int M, int N, int K, int splits, int planes, float* out_f32, dppo_stream_t st) {
     ENTER(h); cudaStream_t s = (cudaStream_t)st;
-    if (!A || !B || !out_f32 || M < 1 || N < 1 || K < 1 || planes < 2 || planes > 3) DPPO_FAIL(-1, "dppo_debug_split_gemm: bad arguments");
+    if (!A || !B || !out_f32 || M < 1 || N < 1 || K < 1 || planes < 2 || planes > 4) DPPO_FAIL(-1, "dppo_debug_split_gemm: bad arguments");
+    const bool f16 = planes == 4;          // two fp16 planes per operand, B scaled, two accumulators
     const size_t na = (((size_t)(a_mn ? K : M) * lda) + 7) & ~(size_t)7, nb = (((size_t)(b_mn ? K : N) * ldb) + 7) & ~(size_t)7;
     bf16* buf = nullptr;
     CUDA_TRY(cudaMalloc(&buf, 3 * (na + nb) * sizeof(bf16)));
     bf16* bb = buf + 3 * na;
-    ts_split_planes_kernel<<<nblk((size_t)(a_mn ? K : M) * lda, 256), 256, 0, s>>>(A, (size_t)(a_mn ? K : M) * lda, buf, buf + na, buf + 2 * na); KLAUNCH(h);
-    ts_split_planes_kernel<<<nblk((size_t)(b_mn ? K : N) * ldb, 256), 256, 0, s>>>(B, (size_t)(b_mn ? K : N) * ldb, bb, bb + nb, bb + 2 * nb); KLAUNCH(h);
+    ts_split_planes_kernel<<<nblk((size_t)(a_mn ? K : M) * lda, 256), 256, 0, s>>>(A, (size_t)(a_mn ? K : M) * lda, buf, buf + na, buf + 2 * na, f16 ? 1.f : 0.f); KLAUNCH(h);
+    ts_split_planes_kernel<<<nblk((size_t)(b_mn ? K : N) * ldb, 256), 256, 0, s>>>(B, (size_t)(b_mn ? K : N) * ldb, bb, bb + nb, bb + 2 * nb, f16 ? ts::F16_WSCALE : 0.f); KLAUNCH(h);
     ts::Gemm g; memset(&g, 0, sizeof(g));
     g.A = ts::Operand{{buf, buf + na, buf + 2 * na}, a_mn != 0, M, K, lda};
     g.B = ts::Operand{{bb, bb + nb, bb + 2 * nb}, b_mn != 0, N, K, ldb};
-    g.M = M; g.N = N; g.splits = splits; g.planes = planes;
+    g.M = M; g.N = N; g.splits = splits; g.planes = f16 ? 2 : planes;
+    if (f16) { g.f16 = 1; g.dual = 1; g.epi.scale = 1.0f / ts::F16_WSCALE; }
     g.epi.M = M; g.epi.N = N; g.epi.out_f32 = out_f32; g.epi.ld_f32 = N; g.epi.split_stride = (size_t)M * N;
     int r = ts::launch(h, s, g);
     cudaStreamSynchronize(s);
@@ -1351,29 +1356,33 @@ extern "C" int dppo_debug_split_gemm(dppo_handle* h, const float* A, int a_mn, i
     return r < 0 ? r : 0;
 }
 
-__global__ void ts_sum_planes_kernel(const bf16* __restrict__ p0, const bf16* __restrict__ p1, const bf16* __restrict__ p2, size_t n, float* __restrict__ out) {
+__global__ void ts_sum_planes_kernel(const bf16* __restrict__ p0, const bf16* __restrict__ p1, const bf16* __restrict__ p2, size_t n, float* __restrict__ out, int f16 = 0) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = __bfloat162float(p0[i]) + __bfloat162float(p1[i]) + (p2 ? __bfloat162float(p2[i]) : 0.f);
+    if (i >= n) return;
+    if (f16) out[i] = ts::f16_plane_value(p0[i]) + ts::f16_plane_value(p1[i]);
+    else out[i] = __bfloat162float(p0[i]) + __bfloat162float(p1[i]) + (p2 ? __bfloat162float(p2[i]) : 0.f);
 }
 extern "C" int dppo_debug_pair_gemm(dppo_handle* h, const float* A, int64_t lda, const float* B, int b_mn, int64_t ldb,
                                     int M, int N, int K, int planes, const float* bias, int act, float* out_f32, uint32_t* mask_out, dppo_stream_t st) {
     ENTER(h); cudaStream_t s = (cudaStream_t)st;
-    if (!A || !B || !out_f32 || M < 1 || N < 64 || (N % 64) || K < 1 || planes < 2 || planes > 3) DPPO_FAIL(-1, "dppo_debug_pair_gemm: bad arguments");
+    if (!A || !B || !out_f32 || M < 1 || N < 64 || (N % 64) || K < 1 || planes < 2 || planes > 4) DPPO_FAIL(-1, "dppo_debug_pair_gemm: bad arguments");
+    const bool f16 = planes == 4;          // fp16 planes in and out, B scaled, two accumulators
     const size_t na = (((size_t)M * lda) + 7) & ~(size_t)7, nb = (((size_t)(b_mn ? K : N) * ldb) + 7) & ~(size_t)7, no = (((size_t)M * N) + 7) & ~(size_t)7;
     bf16* buf = nullptr;
     CUDA_TRY(cudaMalloc(&buf, 3 * (na + nb + no) * sizeof(bf16)));
     bf16* bb = buf + 3 * na; bf16* ob = bb + 3 * nb;
-    ts_split_planes_kernel<<<nblk((size_t)M * lda, 256), 256, 0, s>>>(A, (size_t)M * lda, buf, buf + na, buf + 2 * na); KLAUNCH(h);
-    ts_split_planes_kernel<<<nblk((size_t)(b_mn ? K : N) * ldb, 256), 256, 0, s>>>(B, (size_t)(b_mn ? K : N) * ldb, bb, bb + nb, bb + 2 * nb); KLAUNCH(h);
+    ts_split_planes_kernel<<<nblk((size_t)M * lda, 256), 256, 0, s>>>(A, (size_t)M * lda, buf, buf + na, buf + 2 * na, f16 ? 1.f : 0.f); KLAUNCH(h);
+    ts_split_planes_kernel<<<nblk((size_t)(b_mn ? K : N) * ldb, 256), 256, 0, s>>>(B, (size_t)(b_mn ? K : N) * ldb, bb, bb + nb, bb + 2 * nb, f16 ? ts::F16_WSCALE : 0.f); KLAUNCH(h);
     tsp::Gemm g; memset(&g, 0, sizeof(g));
     g.A = ts::Operand{{buf, buf + na, buf + 2 * na}, false, M, K, lda};
     g.B = ts::Operand{{bb, bb + nb, bb + 2 * nb}, b_mn != 0, N, K, ldb};
-    g.M = M; g.N = N; g.planes = planes; g.dual = planes == 3 ? 1 : 0;
+    g.M = M; g.N = N; g.planes = f16 ? 2 : planes; g.dual = (planes == 3 || f16) ? 1 : 0;
+    if (f16) { g.f16 = 1; g.epi.scale = 1.0f / ts::F16_WSCALE; }
     g.out[0] = ob; g.out[1] = ob + no; g.out[2] = ob + 2 * no; g.ld_out = N;
-    g.epi.M = M; g.epi.N = N; g.epi.out_planes = planes; g.epi.bias = bias; g.epi.act = act;
+    g.epi.M = M; g.epi.N = N; g.epi.out_planes = f16 ? 2 : planes; g.epi.bias = bias; g.epi.act = act;
     if (mask_out) { g.epi.mask_out = mask_out; g.epi.ldm = N / 32; }
     int r = tsp::launch(h, s, g);
-    if (r == 0) { ts_sum_planes_kernel<<<nblk((size_t)M * N, 256), 256, 0, s>>>(ob, ob + no, planes == 3 ? ob + 2 * no : nullptr, (size_t)M * N, out_f32); KLAUNCH(h); }
+    if (r == 0) { ts_sum_planes_kernel<<<nblk((size_t)M * N, 256), 256, 0, s>>>(ob, ob + no, planes == 3 ? ob + 2 * no : nullptr, (size_t)M * N, out_f32, f16 ? 1 : 0); KLAUNCH(h); }
     cudaStreamSynchronize(s);
     cudaFree(buf);
     return r;

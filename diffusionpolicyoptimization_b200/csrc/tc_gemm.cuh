@@ -112,9 +112,9 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
     d |= (uint64_t)2 << 61;          // SWIZZLE_128B
     return d;
 }
-__host__ __device__ constexpr uint32_t make_idesc(int umma_m, int umma_n, bool a_mn, bool b_mn) {
+__host__ __device__ constexpr uint32_t make_idesc(int umma_m, int umma_n, bool a_mn, bool b_mn, bool a_bf16 = true, bool b_bf16 = true) {
     return (1u << 4)                      // D format  : F32
-         | (1u << 7) | (1u << 10)         // A, B format: BF16
+         | ((a_bf16 ? 1u : 0u) << 7) | ((b_bf16 ? 1u : 0u) << 10)   // A, B format: BF16 (1) or F16 (0), chosen per operand
          | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16)
          | ((uint32_t)(umma_n >> 3) << 17) | ((uint32_t)(umma_m >> 4) << 24);
 }

@@ -9,8 +9,16 @@
 // forward deviation eps from the reference flips about eps * density units across a kink, and every flipped unit switches a
 // whole gradient term on or off: the actor-gradient error against the reference grows like sqrt(eps) - 2e-3 of the largest
 // entry with 16-bit forward operands (measured, tools/flip_probe.py), against the 1e-3 north_star's fp32 mode is held to.
-// With 24-bit forward operands the forward pass is as close to the reference as the FFMA path is; the backward and
+// With >= 22-bit forward operands the forward pass is as close to the reference as the FFMA path is; the backward and
 // weight-gradient GEMMs are smooth in their operands and keep P = 2 (1e-5 relative).
+//   F16 (forward GEMMs in front of kinks): the same 22 bits from TWO fp16 planes h0 = fp16(x), h1 = fp16(x - h0) (11 bits each) and
+//   three products A0 B0 | A1 B0 + A0 B1 in two accumulators: half the MMAs and two thirds of the operand bytes of P = 3 - these
+//   GEMMs are bound by the bytes an SM can take in, not by the tensor pipe.  fp16's narrow exponent is handled by scale: weights are
+//   stored as planes of 2^10 w (|w| < 64; a weight of 1e-5 still keeps 11 + 8 bits) and the epilogue multiplies by 2^-10; activations are
+//   O(1) and unscaled (below 0.1 the second plane is subnormal: absolute error 3e-8 per element, 2e-8 on a K = 512 output).  Gradients
+//   keep bf16 planes (they carry 1/N: fp16 would flush them), and one tcgen05.mma cannot take an fp16 and a bf16 operand (the
+//   descriptor has a format field per operand, the hardware traps on a mixed one: measured), so when a backward pass follows the
+//   forward epilogue ALSO stores the two bf16 planes of each activation for the weight-gradient GEMMs.
 //
 //   ts::split_gemm_kernel<BN, A_MN, B_MN, P>   D[M,N] = sum_seg sum_(i,j) A_i B_j
 //     * a shared-memory stage holds the 2 P plane tiles of one 64-deep k-block (TMA, 128-byte swizzle): each byte that
@@ -35,6 +43,7 @@ struct Epi {
     int M, N;                                         // valid extents of the output
     const float* bias;                                // [N]
     float* out_f32; int ld_f32; size_t split_stride;  // fp32 row-major (+ split * split_stride)
+    float scale;                                      // F16 kernels: the accumulators are multiplied by this (1 / weight scale)
 };
 struct Params {
     int m_blocks, n_blocks, splits;
@@ -59,7 +68,21 @@ __device__ __forceinline__ void split_bf16_3(float v, bf16& p0, bf16& p1, bf16& 
     p1 = __float2bfloat16(r1);
     p2 = __float2bfloat16(r1 - __bfloat162float(p1));     // exact remainder, rounded to the third plane
 }
-template <int BN, bool A_MN, bool B_MN, int P, bool DUAL>
+// fp16 planes live in the same 16-bit containers as the bf16 ones (the tensor maps only see 2-byte elements)
+__device__ __forceinline__ bf16 f16_bits(float v, float& back) {
+    const __half hv = __float2half_rn(v);
+    back = __half2float(hv);
+    return __ushort_as_bfloat16(__half_as_ushort(hv));
+}
+__device__ __forceinline__ void split_f16(float v, bf16& hi, bf16& lo) {
+    float b0, b1;
+    hi = f16_bits(v, b0);
+    lo = f16_bits(v - b0, b1);
+}
+__device__ __forceinline__ float f16_plane_value(bf16 b) { return __half2float(__ushort_as_half(__bfloat16_as_ushort(b))); }
+constexpr float F16_WSCALE = 1024.f;     // forward weights are stored as fp16 planes of 2^10 w
+
+template <int BN, bool A_MN, bool B_MN, int P, bool DUAL, bool F16 = false>
 __global__ void __launch_bounds__(STHREADS, 1) split_gemm_kernel(const __grid_constant__ Maps maps, const Params p) {
     constexpr int STG = stages<BN, P>();
     constexpr int A_TILE = SBM * SBK * 2, B_TILE = BN * SBK * 2, STAGE = stage_bytes<BN, P>();
@@ -135,7 +158,7 @@ __global__ void __launch_bounds__(STHREADS, 1) split_gemm_kernel(const __grid_co
         }
     } else if (warp == 1) {
         // ===================== MMA issuer: all plane products of a k-step into one accumulator =====================
-        constexpr uint32_t idesc = make_idesc(SBM, BN, A_MN, B_MN);
+        constexpr uint32_t idesc = make_idesc(SBM, BN, A_MN, B_MN, !F16, !F16);
         // (A plane, B plane) pairs, small terms first
         constexpr int NPROD = P == 3 ? 6 : 3;
         constexpr int PA[6] = {2, 0, 1, 1, 0, 0}, PB[6] = {0, 2, 1, 0, 1, 0};       // P = 3
@@ -206,6 +229,10 @@ __global__ void __launch_bounds__(STHREADS, 1) split_gemm_kernel(const __grid_co
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(r[j]);
                 }
+                if (F16) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] *= e.scale;
+                }
                 const int n0 = n_blk * BN + c * 32;
                 if (row_ok && n0 < e.N) {
                     const bool full32 = n0 + 32 <= e.N;
@@ -247,12 +274,13 @@ struct Gemm {
     Operand A, A2, B, B2;  // A2.p[0] == nullptr: no K concatenation; else the K-concatenation [A | A2] x [B ; B2]
     int planes;            // 2 or 3 (every operand must carry that many)
     int dual;              // two planes with the correction products in a second accumulator (forward GEMMs in front of kinks)
+    int f16;               // operands are fp16 planes (planes = 2, dual = 1), B scaled by 1 / epi.scale
     int M, N, splits;
     double alg_flops;      // algorithmic flops (un-padded dims, ONE product per MAC) for the live roofline
     Epi epi;
 };
 
-template <int BN, bool A_MN, bool B_MN, int P, bool DUAL>
+template <int BN, bool A_MN, bool B_MN, int P, bool DUAL, bool F16 = false>
 static int launch_t(dppo_handle* h, cudaStream_t s, const Gemm& g) {
     Maps mp;
     const Operand& A = g.A; const Operand& B = g.B;
@@ -278,7 +306,7 @@ static int launch_t(dppo_handle* h, cudaStream_t s, const Gemm& g) {
     p.kb_per_split = (p.kblocks + splits - 1) / splits;
     p.splits = (p.kblocks + p.kb_per_split - 1) / p.kb_per_split;
     p.epi = g.epi;
-    auto kern = split_gemm_kernel<BN, A_MN, B_MN, P, DUAL>;
+    auto kern = split_gemm_kernel<BN, A_MN, B_MN, P, DUAL, F16>;
     static bool attr_set_dev[64] = {};      // function attributes are per device
     bool& attr_set = attr_set_dev[h->device & 63];
     if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<BN, P>())); attr_set = true; }
@@ -298,6 +326,11 @@ static int launch_t(dppo_handle* h, cudaStream_t s, const Gemm& g) {
 // (MN-major both, P = 2).
 static int launch(dppo_handle* h, cudaStream_t s, const Gemm& g) {
     const bool a = g.A.mn_major, b = g.B.mn_major;
+    if (g.f16) {
+        if (g.planes == 2 && g.dual && !a && !b && g.N <= 32) return launch_t<32, false, false, 2, true, true>(h, s, g);
+        if (g.planes == 2 && g.dual && !a && b) return launch_t<128, false, true, 2, true, true>(h, s, g);
+        DPPO_FAIL(-7, "split gemm: this fp16-plane operand layout is not instantiated");
+    }
     if (g.planes == 3) {
         if (!a && b) return launch_t<128, false, true, 3, true>(h, s, g);
         if (!a && !b && g.N <= 32) return launch_t<32, false, false, 3, true>(h, s, g);
@@ -336,8 +369,7 @@ static inline SplitT split_null() { SplitT t; t.p[0] = t.p[1] = t.p[2] = nullptr
 namespace tsp {
 using namespace tc;
 constexpr int PTHREADS = 320;         // warp 0: TMA, warp 1: MMA (leader) + TMEM alloc, warps 2..9: epilogue
-constexpr int SLOT = 16384;           // one [128 rows][64 columns] bf16 plane tile
-constexpr int NSLOT = 4;
+constexpr int SLOT = 16384;           // one [128 rows][64 columns] 16-bit plane tile
 
 struct Epi {
     int M, N;                                              // valid extents of the output
@@ -348,23 +380,36 @@ struct Epi {
     int gate_out;                                          // Mish forward: also store mish'(pre-activation) as two planes (maps.gate)
     float* colsum_part; int colsum_ld;                     // bias gradient: per 32-row block column sums of the fp32 result,
                                                            // written to colsum_part[rowblock * colsum_ld + column] (rowblock = row / 32)
+    float scale;                                           // F16 kernels: accumulators *= scale (1 / weight scale) before the bias
+    int out2;                                              // F16 kernels: also store the result as two bf16 planes (maps.out2)
 };
-struct Params { int m_blocks, n_blocks, kblocks, ka_blocks; Epi epi; };
-struct Maps { CUtensorMap a[2][ts::MAXP], b[2][ts::MAXP], out[ts::MAXP], gate[2]; };
+struct Params {
+    int m_blocks, n_blocks, kblocks, ka_blocks;
+    int stg, nslot, dbuf;            // shared-memory plan (host): load stages, staging slots, two staging buffers of nslot / 2 slots
+    Epi epi;
+};
+struct Maps { CUtensorMap a[2][ts::MAXP], b[2][ts::MAXP], out[ts::MAXP], gate[2], out2[2]; };
 
 template <int P, int BNP> __host__ __device__ constexpr int stage_bytes() { return P * (128 * 64 * 2 + (BNP / 2) * 64 * 2); }
-template <int P, int BNP> __host__ __device__ constexpr int stages() { return (227 * 1024 - NSLOT * SLOT - 2048) / stage_bytes<P, BNP>() > 4 ? 4 : (227 * 1024 - NSLOT * SLOT - 2048) / stage_bytes<P, BNP>(); }
-template <int P, int BNP> constexpr size_t smem_bytes() { return (size_t)stages<P, BNP>() * stage_bytes<P, BNP>() + NSLOT * SLOT + 1024 + 256; }
+// The 227 KB of a CTA are split between load stages and epilogue staging slots per launch.  Measured (50 000 x 512 x 512 layers): a
+// third load stage is worth more than a second staging buffer (fp16 forward layer 100 -> 88 us), a second staging buffer more than a
+// fourth stage; two stages are the minimum.
+constexpr int SMEM_BUDGET = 227 * 1024 - 1024 - 256;
+static inline void smem_plan(int stage_bytes, int planes_staged, int& stg, int& nslot, int& dbuf) {
+    nslot = planes_staged; dbuf = 0;
+    stg = (SMEM_BUDGET - nslot * SLOT) / stage_bytes;
+    if (stg >= 3 && (SMEM_BUDGET - 2 * nslot * SLOT) / stage_bytes >= 3) { nslot *= 2; dbuf = 1; stg = (SMEM_BUDGET - nslot * SLOT) / stage_bytes; }
+    if (stg > 4) stg = 4;
+}
 
 __device__ __forceinline__ void epi_barrier8() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-template <bool B_MN, int P, bool DUAL, int BNP>
+template <bool B_MN, int P, bool DUAL, int BNP, bool F16 = false>
 __global__ void __launch_bounds__(PTHREADS, 1) pair_gemm_kernel(const __grid_constant__ Maps maps, const Params p) {
-    constexpr int STG = stages<P, BNP>();
+    const int STG = p.stg, NSLOT = p.nslot;
     constexpr int A_TILE = 128 * 64 * 2, B_TILE = (BNP / 2) * 64 * 2, STAGE = stage_bytes<P, BNP>();
     constexpr int NACC = DUAL ? 2 : 1, ACC_COLS = NACC * BNP;
     static_assert(2 * ACC_COLS <= 512, "accumulators exceed tensor memory");
-    static_assert(STG >= 2, "a stage must fit twice");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* slots = smem + STG * STAGE;
@@ -428,7 +473,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) pair_gemm_kernel(const __grid_con
     } else if (warp == 1) {
         // ---- MMA issuer: the leader only
         if (rank == 0) {
-            constexpr uint32_t idesc = make_idesc(256, BNP, false, B_MN);
+            constexpr uint32_t idesc = make_idesc(256, BNP, false, B_MN, !F16, !F16);
             constexpr int NPROD = P == 3 ? 6 : 3;
             constexpr int PA[6] = {2, 0, 1, 1, 0, 0}, PB[6] = {0, 2, 1, 0, 1, 0};       // P = 3: small terms first, A0 B0 last
             constexpr int QA[3] = {1, 0, 0}, QB[3] = {0, 1, 0};                          // P = 2
@@ -480,8 +525,11 @@ __global__ void __launch_bounds__(PTHREADS, 1) pair_gemm_kernel(const __grid_con
         const uint32_t row_off = (uint32_t)rloc * 128u, sw = (uint32_t)(rloc & 7);
         int acc = 0; uint32_t acc_phase = 0;
         const uint32_t tempty_leader = fc::mapa_rank0(smem_u32(tempty));
-        // two planes and no gate planes: the four slots hold two staging buffers, the TMA store of a group overlaps the next group's math
-        const bool dbuf = (P == 2) && !e.gate_out;
+        // a staging buffer: [out planes | bf16 copies (out2) | gate planes]; with two buffers (p.dbuf) the TMA store of a group overlaps
+        // the next group's math
+        const uint32_t BUF = (uint32_t)(p.dbuf ? p.nslot / 2 : p.nslot);
+        const bool dbuf = p.dbuf != 0;
+        const uint32_t o2 = (uint32_t)P, og = o2 + ((F16 && e.out2) ? 2u : 0u);     // slot offsets of the copies / the gates inside a buffer
         uint32_t gcount = 0;
         for (int tile = pair; tile < tiles; tile += npairs) {
             const int m_blk = tile / p.n_blocks, n_blk = tile % p.n_blocks;
@@ -501,6 +549,10 @@ __global__ void __launch_bounds__(PTHREADS, 1) pair_gemm_kernel(const __grid_con
                     tmem_ld32(tmem_base + lane_base + (uint32_t)(acc * ACC_COLS + BNP + g * 64 + half * 32), r);
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(r[j]);
+                }
+                if (F16) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] *= e.scale;
                 }
                 if (g == BNP / 64 - 1) {                                      // accumulator drained: hand it back before the math
                     tcgen05_fence_before();
@@ -558,7 +610,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) pair_gemm_kernel(const __grid_con
                     if (col_ok && row0 + quad * 32 < e.M) e.colsum_part[(size_t)((row0 >> 5) + quad) * e.colsum_ld + n0 + lane] = cs[0];
                 }
                 // the staging slots are free once the TMA stores that last used them have read them
-                const uint32_t sbuf = dbuf ? (gcount & 1u) * 2u : 0u;
+                const uint32_t sbuf = dbuf ? (gcount & 1u) * BUF : 0u;
                 ++gcount;
                 if (store_thread) { if (dbuf) fc::tma_store_wait_read1(); else fc::tma_store_wait_read(); }
                 epi_barrier8();
@@ -568,7 +620,9 @@ __global__ void __launch_bounds__(PTHREADS, 1) pair_gemm_kernel(const __grid_con
                     __align__(16) bf16 t[ts::MAXP][8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        if (P == 3) ts::split_bf16_3(v[q * 8 + j], t[0][j], t[1][j], t[2][j]); else ts::split_bf16(v[q * 8 + j], t[0][j], t[1][j]);
+                        if (F16) ts::split_f16(v[q * 8 + j], t[0][j], t[1][j]);
+                        else if (P == 3) ts::split_bf16_3(v[q * 8 + j], t[0][j], t[1][j], t[2][j]);
+                        else ts::split_bf16(v[q * 8 + j], t[0][j], t[1][j]);
                     }
                     const uint32_t off = row_off + (((c0 + (uint32_t)q) ^ sw) << 4);
 #pragma unroll
@@ -576,13 +630,21 @@ __global__ void __launch_bounds__(PTHREADS, 1) pair_gemm_kernel(const __grid_con
                         const uint4 u = *reinterpret_cast<const uint4*>(t[pl]);
                         fc::st_shared_v4(slot_addr + (sbuf + pl) * SLOT + off, u.x, u.y, u.z, u.w);
                     }
+                    if (F16 && e.out2) {
+                        __align__(16) bf16 bh[8]; __align__(16) bf16 bl[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) ts::split_bf16(v[q * 8 + j], bh[j], bl[j]);
+                        const uint4 u0 = *reinterpret_cast<const uint4*>(bh), u1 = *reinterpret_cast<const uint4*>(bl);
+                        fc::st_shared_v4(slot_addr + (sbuf + o2) * SLOT + off, u0.x, u0.y, u0.z, u0.w);
+                        fc::st_shared_v4(slot_addr + (sbuf + o2 + 1) * SLOT + off, u1.x, u1.y, u1.z, u1.w);
+                    }
                     if (e.gate_out) {
                         __align__(16) bf16 gh[8]; __align__(16) bf16 gl[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) ts::split_bf16(gt[q * 8 + j], gh[j], gl[j]);
                         const uint4 u0 = *reinterpret_cast<const uint4*>(gh), u1 = *reinterpret_cast<const uint4*>(gl);
-                        fc::st_shared_v4(slot_addr + 2 * SLOT + off, u0.x, u0.y, u0.z, u0.w);
-                        fc::st_shared_v4(slot_addr + 3 * SLOT + off, u1.x, u1.y, u1.z, u1.w);
+                        fc::st_shared_v4(slot_addr + (sbuf + og) * SLOT + off, u0.x, u0.y, u0.z, u0.w);
+                        fc::st_shared_v4(slot_addr + (sbuf + og + 1) * SLOT + off, u1.x, u1.y, u1.z, u1.w);
                     }
                 }
                 fc::fence_async_smem();
@@ -591,7 +653,8 @@ __global__ void __launch_bounds__(PTHREADS, 1) pair_gemm_kernel(const __grid_con
                     const int col = n_blk * BNP + g * 64;
                     if (col < e.N) {
                         for (int pl = 0; pl < e.out_planes; ++pl) fc::tma_store_2d(&maps.out[pl], slots + (sbuf + pl) * SLOT, col, row0);
-                        if (e.gate_out) { fc::tma_store_2d(&maps.gate[0], slots + 2 * SLOT, col, row0); fc::tma_store_2d(&maps.gate[1], slots + 3 * SLOT, col, row0); }
+                        if (F16 && e.out2) { fc::tma_store_2d(&maps.out2[0], slots + (sbuf + o2) * SLOT, col, row0); fc::tma_store_2d(&maps.out2[1], slots + (sbuf + o2 + 1) * SLOT, col, row0); }
+                        if (e.gate_out) { fc::tma_store_2d(&maps.gate[0], slots + (sbuf + og) * SLOT, col, row0); fc::tma_store_2d(&maps.gate[1], slots + (sbuf + og + 1) * SLOT, col, row0); }
                     }
                     fc::tma_store_commit();
                 }
@@ -613,14 +676,16 @@ __global__ void __launch_bounds__(PTHREADS, 1) pair_gemm_kernel(const __grid_con
 struct Gemm {
     ts::Operand A, A2, B, B2;      // A K-major; B K-major or MN-major; [A | A2] x [B ; B2] when A2.p[0] != nullptr
     int planes, dual;              // 2 (single accumulator) or 3 with dual = 1
+    int f16;                       // fp16 planes in and out (planes = 2, dual = 1); B carries the weight scale, epi.scale its inverse
     int M, N;
     bf16* out[ts::MAXP]; int ld_out;
     bf16* gate[2];
+    bf16* out2[2];                 // f16 only: bf16 copies of the output planes (epi.out2)
     double alg_flops;
     Epi epi;
 };
 
-template <bool B_MN, int P, bool DUAL, int BNP>
+template <bool B_MN, int P, bool DUAL, int BNP, bool F16 = false>
 static int launch_t(dppo_handle* h, cudaStream_t s, const Gemm& g) {
     Maps mp;
     for (int pl = 0; pl < ts::MAXP; ++pl) {
@@ -636,22 +701,27 @@ static int launch_t(dppo_handle* h, cudaStream_t s, const Gemm& g) {
     }
     for (int i = 0; i < 2; ++i) {
         if (g.epi.gate_out) DPPO_TRY(make_map(&mp.gate[i], g.gate[i], g.M, g.N, g.ld_out, 128, 64)); else mp.gate[i] = mp.out[0];
+        if (g.epi.out2) DPPO_TRY(make_map(&mp.out2[i], g.out2[i], g.M, g.N, g.ld_out, 128, 64)); else mp.out2[i] = mp.out[0];
     }
+    if (g.epi.out2 && !F16) DPPO_FAIL(-7, "split gemm (pair): bf16 copies are an option of the fp16-plane kernel");
     Params p;
     p.m_blocks = (g.M + 255) / 256; p.n_blocks = (g.N + BNP - 1) / BNP;
     const int ka = (int)((g.A.k + 63) / 64), ka2 = g.A2.p[0] ? (int)((g.A2.k + 63) / 64) : 0;
     p.kblocks = ka + ka2; p.ka_blocks = ka;
     p.epi = g.epi;
-    auto kern = pair_gemm_kernel<B_MN, P, DUAL, BNP>;
+    smem_plan(stage_bytes<P, BNP>(), P + (g.epi.out2 ? 2 : 0) + (g.epi.gate_out ? 2 : 0), p.stg, p.nslot, p.dbuf);
+    if (p.stg < 2 || g.epi.out_planes > P) DPPO_FAIL(-7, "split gemm (pair): shared-memory plan does not fit (%d stages, %d slots)", p.stg, p.nslot);
+    const size_t smem_bytes = (size_t)p.stg * stage_bytes<P, BNP>() + (size_t)p.nslot * SLOT + 1024 + 256;
+    auto kern = pair_gemm_kernel<B_MN, P, DUAL, BNP, F16>;
     static bool attr_set_dev[64] = {};      // function attributes are per device
     bool& attr_set = attr_set_dev[h->device & 63];
-    if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<P, BNP>())); attr_set = true; }
+    if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_set = true; }
     const int tiles = p.m_blocks * p.n_blocks, npairs = h->sm_count / 2;
     const int grid = 2 * (tiles < npairs ? tiles : npairs);
     cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1; cfg.blockDim = dim3(PTHREADS); cfg.gridDim = dim3(grid); cfg.dynamicSmemBytes = smem_bytes<P, BNP>(); cfg.stream = s;
+    cfg.attrs = at; cfg.numAttrs = 1; cfg.blockDim = dim3(PTHREADS); cfg.gridDim = dim3(grid); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = s;
     prof_begin(h, s);
     cudaError_t le = cudaLaunchKernelEx(&cfg, kern, mp, p);
     prof_end(h, s, g.alg_flops > 0 ? g.alg_flops : 2.0 * (double)g.M * (double)g.N * (double)(g.A.k + (g.A2.p[0] ? g.A2.k : 0)), 0,
@@ -664,6 +734,10 @@ static int launch_t(dppo_handle* h, cudaStream_t s, const Gemm& g) {
 }
 static int launch(dppo_handle* h, cudaStream_t s, const Gemm& g) {
     const bool b = g.B.mn_major;
+    if (g.f16) {
+        if (g.planes == 2 && g.dual) return b ? launch_t<true, 2, true, 128, true>(h, s, g) : launch_t<false, 2, true, 128, true>(h, s, g);
+        DPPO_FAIL(-7, "split gemm (pair): fp16 planes need two planes and two accumulators");
+    }
     if (g.planes == 3 && g.dual) return b ? launch_t<true, 3, true, 128>(h, s, g) : launch_t<false, 3, true, 128>(h, s, g);
     if (g.planes == 2 && !g.dual) return b ? launch_t<true, 2, false, 256>(h, s, g) : launch_t<false, 2, false, 256>(h, s, g);
     DPPO_FAIL(-7, "split gemm (pair): plane / accumulator combination not instantiated");
@@ -916,36 +990,44 @@ static int launch_dw_group(dppo_handle* h, cudaStream_t s, const DwDesc* d, int 
 }  // namespace tsp
 
 // =====================================================================================================================
-// state: plane copies of the weights per net (3 planes each; the backward GEMMs read the first two)
+// state: plane copies of the weights per net: two bf16 planes (backward GEMMs; forward of a smooth net) and two fp16 planes of
+// 2^10 w (forward GEMMs of a net with kinks behind it)
 struct TsW { bf16* p[ts::MAXP]; };
 struct TsNetW {
     TsW w2w0, w1, w3t, w3p;
+    TsW fw2w0, fw1, fw3t;                 // fp16 planes, scaled by ts::F16_WSCALE
     float* bias2;                         // critic: b2 + b_in (the residual's input-layer bias rides with block.l2's)
     int H;
 };
 struct TsState { TsNetW net[4]; int KP0; };
 
 __device__ __forceinline__ void ts_put(const TsW& W, size_t i, float v) {
-    bf16 a, b, c; ts::split_bf16_3(v, a, b, c);
-    W.p[0][i] = a; W.p[1][i] = b; W.p[2][i] = c;
+    bf16 a, b; ts::split_bf16(v, a, b);
+    W.p[0][i] = a; W.p[1][i] = b;
 }
+__device__ __forceinline__ void ts_put_f16(const TsW& W, size_t i, float v) {
+    bf16 a, b; ts::split_f16(v * ts::F16_WSCALE, a, b);
+    W.p[0][i] = a; W.p[1][i] = b;
+}
+__device__ __forceinline__ void ts_put2(const TsW& W, const TsW& F, size_t i, float v) { ts_put(W, i, v); ts_put_f16(F, i, v); }
 // same operand layouts as tc_pack_actor_body (w2w0 = [W2 ; W0 rows in h0 order], w3t = W3^T padded to 64 rows, w3p = W3 padded to
-// 128 columns), each as three planes; no transposed copies (the backward GEMMs read W1 / W2 K-major as stored)
+// 128 columns), each as two bf16 planes (+ two fp16 planes for the forward operands); no transposed copies (the backward GEMMs read
+// W1 / W2 K-major as stored)
 __global__ void ts_pack_actor_kernel(const float* __restrict__ w, ActorOff o, int A, int td, int Do, int T, int H, int KP0,
                                      const float* __restrict__ bt, const TsNetW W) {
     const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = i0; i < (size_t)H * H; i += stride) { ts_put(W.w2w0, i, w[o.w2 + i]); ts_put(W.w1, i, w[o.w1 + i]); }
+    for (size_t i = i0; i < (size_t)H * H; i += stride) { ts_put2(W.w2w0, W.fw2w0, i, w[o.w2 + i]); ts_put2(W.w1, W.fw1, i, w[o.w1 + i]); }
     for (size_t i = i0; i < (size_t)KP0 * H; i += stride) {
         const int k = (int)(i / H), c = (int)(i % H);
         float v = 0.f;
         if (k < A) v = w[o.win + (size_t)k * H + c];
         else if (k < A + Do) v = w[o.win + (size_t)(k + td) * H + c];
         else if (k < A + Do + T) v = bt[(size_t)(k - A - Do) * H + c];
-        ts_put(W.w2w0, (size_t)H * H + i, v);
+        ts_put2(W.w2w0, W.fw2w0, (size_t)H * H + i, v);
     }
     for (size_t i = i0; i < (size_t)64 * H; i += stride) {
         const int a = (int)(i / H), k = (int)(i % H);
-        ts_put(W.w3t, i, a < A ? w[o.w3 + (size_t)k * A + a] : 0.f);
+        ts_put2(W.w3t, W.fw3t, i, a < A ? w[o.w3 + (size_t)k * A + a] : 0.f);
     }
     for (size_t i = i0; i < (size_t)H * 128; i += stride) {
         const int k = (int)(i / 128), a = (int)(i % 128);
@@ -954,20 +1036,21 @@ __global__ void ts_pack_actor_kernel(const float* __restrict__ w, ActorOff o, in
 }
 __global__ void ts_pack_critic_kernel(const float* __restrict__ w, CriticOff o, int A, int Do, int Hc, int KP0, const TsNetW W) {
     const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = i0; i < (size_t)Hc * Hc; i += stride) { ts_put(W.w2w0, i, w[o.w2 + i]); ts_put(W.w1, i, w[o.w1 + i]); }
+    for (size_t i = i0; i < (size_t)Hc * Hc; i += stride) { ts_put2(W.w2w0, W.fw2w0, i, w[o.w2 + i]); ts_put2(W.w1, W.fw1, i, w[o.w1 + i]); }
     for (size_t i = i0; i < (size_t)KP0 * Hc; i += stride) {
         const int k = (int)(i / Hc), c = (int)(i % Hc);
-        ts_put(W.w2w0, (size_t)Hc * Hc + i, (k >= A && k < A + Do) ? w[o.win + (size_t)(k - A) * Hc + c] : 0.f);
+        ts_put2(W.w2w0, W.fw2w0, (size_t)Hc * Hc + i, (k >= A && k < A + Do) ? w[o.win + (size_t)(k - A) * Hc + c] : 0.f);
     }
-    for (size_t i = i0; i < (size_t)64 * Hc; i += stride) { const int a = (int)(i / Hc), k = (int)(i % Hc); ts_put(W.w3t, i, a == 0 ? w[o.w3 + k] : 0.f); }
+    for (size_t i = i0; i < (size_t)64 * Hc; i += stride) { const int a = (int)(i / Hc), k = (int)(i % Hc); ts_put2(W.w3t, W.fw3t, i, a == 0 ? w[o.w3 + k] : 0.f); }
     for (size_t i = i0; i < (size_t)Hc * 128; i += stride) { const int k = (int)(i / 128), a = (int)(i % 128); ts_put(W.w3p, i, a == 0 ? w[o.w3 + k] : 0.f); }
     for (size_t i = i0; i < (size_t)Hc; i += stride) W.bias2[i] = w[o.b2 + i] + w[o.bin + i];
 }
-// h0[r] = [x[r] | obs[r / obs_div] | onehot(t_r) | 1 | 0..] as three planes (tc_pack_h0_kernel's layout); one thread per 8 columns
+// h0[r] = [x[r] | obs[r / obs_div] | onehot(t_r) | 1 | 0..] (tc_pack_h0_kernel's layout) as two fp16 planes (hf, when given) and / or two
+// bf16 planes (hb, when given); one thread per 8 columns
 // flat != nullptr (index-driven minibatch, train_ppo_diffusion_agent.py:292-312 without materialising it): row r is the (rollout row b,
 // denoising index k) pair of flat[r] = b * flatK + k: x = chains[b][k], obs = obs[b], t = flatK - 1 - k; bad indices raise *bad and read row 0
 __global__ void ts_pack_h0_kernel(const float* __restrict__ x, const float* __restrict__ obs, const int* __restrict__ trow, int tconst,
-                                  int N, int A, int Do, int T, int KP0, int obs_div, const SplitT h0, int chainK,
+                                  int N, int A, int Do, int T, int KP0, int obs_div, const SplitT hf, const SplitT hb, int chainK,
                                   const int* __restrict__ flat = nullptr, int flatK = 1, long long flatP = 0, int* __restrict__ bad = nullptr) {
     const int g8 = KP0 / 8;
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -982,7 +1065,7 @@ __global__ void ts_pack_h0_kernel(const float* __restrict__ x, const float* __re
         const int b = f / flatK, k = f % flatK;
         xrow = (size_t)b * (flatK + 1) + k; orow = (size_t)b; t = flatK - 1 - k;
     }
-    __align__(16) bf16 o3[3][8];
+    __align__(16) bf16 o3[4][8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int k = k0 + j;
@@ -991,10 +1074,14 @@ __global__ void ts_pack_h0_kernel(const float* __restrict__ x, const float* __re
         else if (k < A + Do) v = obs[orow * Do + (k - A)];
         else if (k < A + Do + T) v = (k - A - Do == t) ? 1.f : 0.f;
         else if (k == A + Do + T) v = 1.f;
-        ts::split_bf16_3(v, o3[0][j], o3[1][j], o3[2][j]);
+        ts::split_f16(v, o3[0][j], o3[1][j]);
+        ts::split_bf16(v, o3[2][j], o3[3][j]);
     }
 #pragma unroll
-    for (int pl = 0; pl < 3; ++pl) *reinterpret_cast<uint4*>(h0.p[pl] + (size_t)r * KP0 + k0) = *reinterpret_cast<const uint4*>(o3[pl]);
+    for (int pl = 0; pl < 2; ++pl) {
+        if (hf.p[0]) *reinterpret_cast<uint4*>(hf.p[pl] + (size_t)r * KP0 + k0) = *reinterpret_cast<const uint4*>(o3[pl]);
+        if (hb.p[0]) *reinterpret_cast<uint4*>(hb.p[pl] + (size_t)r * KP0 + k0) = *reinterpret_cast<const uint4*>(o3[2 + pl]);
+    }
 }
 // dst[r][0:64] = [src[r][0:ncols] | 0..] as two planes
 __global__ void ts_pad64_kernel(const float* __restrict__ src, int N, int ncols, bf16* __restrict__ hi, bf16* __restrict__ lo) {
@@ -1038,8 +1125,8 @@ static bool ts_eligible(const dppo_handle* h, int rows) {
     return h->cfg.precision == DPPO_PREC_BF16X3 && ts_shapes_ok(h) && rows >= TS_MIN_ROWS;
 }
 static int ts_alloc_w(TsW& w, size_t n) {
-    CUDA_TRY(cudaMalloc(&w.p[0], ts::MAXP * n * sizeof(bf16)));
-    for (int pl = 1; pl < ts::MAXP; ++pl) w.p[pl] = w.p[0] + pl * n;
+    CUDA_TRY(cudaMalloc(&w.p[0], 2 * n * sizeof(bf16)));
+    w.p[1] = w.p[0] + n; w.p[2] = nullptr;
     return 0;
 }
 static int ts_init(dppo_handle* h) {
@@ -1056,13 +1143,14 @@ static int ts_init(dppo_handle* h) {
         w.H = (int)H;
         DPPO_TRY(ts_alloc_w(w.w2w0, (H + st->KP0) * H)); DPPO_TRY(ts_alloc_w(w.w1, H * H));
         DPPO_TRY(ts_alloc_w(w.w3t, 64 * H)); DPPO_TRY(ts_alloc_w(w.w3p, H * 128));
+        DPPO_TRY(ts_alloc_w(w.fw2w0, (H + st->KP0) * H)); DPPO_TRY(ts_alloc_w(w.fw1, H * H)); DPPO_TRY(ts_alloc_w(w.fw3t, 64 * H));
         CUDA_TRY(cudaMalloc(&w.bias2, H * sizeof(float)));
     }
     return 0;
 }
 static void ts_destroy(dppo_handle* h) {
     if (!h->ts) return;
-    for (int net = 0; net < 4; ++net) { TsNetW& w = h->ts->net[net]; cudaFree(w.w2w0.p[0]); cudaFree(w.w1.p[0]); cudaFree(w.w3t.p[0]); cudaFree(w.w3p.p[0]); cudaFree(w.bias2); }
+    for (int net = 0; net < 4; ++net) { TsNetW& w = h->ts->net[net]; cudaFree(w.w2w0.p[0]); cudaFree(w.w1.p[0]); cudaFree(w.w3t.p[0]); cudaFree(w.w3p.p[0]); cudaFree(w.fw2w0.p[0]); cudaFree(w.fw1.p[0]); cudaFree(w.fw3t.p[0]); cudaFree(w.bias2); }
     delete h->ts; h->ts = nullptr;
 }
 // rebuild the plane copies of one net (after set_weights / an optimizer step; the actor's bt table must be current)
@@ -1078,9 +1166,11 @@ static int ts_refresh_net(dppo_handle* h, int net, cudaStream_t s) {
 // ------------------------------------------------------------------ one residual MLP on N rows, every tensor as planes
 struct TsMlp {
     const TsNetW* W; int H, NO, act1, KP0, net, din;
-    int fp;                                // planes of the FORWARD GEMMs: 3 (+ two accumulators) when the net has kinks behind it, else 2
+    int fp;                                // FORWARD GEMMs: 4 = two fp16 planes + two accumulators (22 bits) when the net has kinks behind it,
+                                           // 2 = two bf16 planes, one accumulator (16 bits).  h0 / a0 / a1 / v carry that format.
     const float *b0, *b1, *b2, *b3;
     SplitT h0, a0, a1, v, g0, g1, dv, dh1, du;   // g0 / g1: Mish gates mish'(pre-activation) of layer 0 / block.l1 (two planes)
+    SplitT h0b, a0b, a1b, vb;              // fp = 4 with a backward pass: bf16 copies (two planes) for the weight-gradient GEMMs
     uint32_t *m0, *m1;                     // ReLU bit masks [N][H/32] of layer 0 / block.l1
     float* out;                            // [N][NO] fp32
 };
@@ -1088,18 +1178,18 @@ static void ts_actor_mlp(const dppo_handle* h, int net, TsMlp& m) {
     const Geom& g = h->g; const float* w = h->net_w[net];
     memset(&m, 0, sizeof(m));
     m.W = &h->ts->net[net]; m.H = g.H; m.NO = g.A; m.act1 = h->cfg.actor_act + 1; m.KP0 = h->ts->KP0; m.net = net; m.din = g.Din;
-    m.fp = 3;                                                                        // ReLU kinks and the +-1 clip of x0 behind eps
+    m.fp = 4;                                                                        // ReLU kinks and the +-1 clip of x0 behind eps
     m.b0 = nullptr; m.b1 = w + g.ao.b1; m.b2 = w + g.ao.b2; m.b3 = w + g.ao.b3;      // b_in rides in W0's one-hot rows (bt table)
 }
 static void ts_critic_mlp(const dppo_handle* h, TsMlp& m) {
     const Geom& g = h->g; const float* w = h->net_w[DPPO_NET_CRITIC];
     memset(&m, 0, sizeof(m));
     m.W = &h->ts->net[DPPO_NET_CRITIC]; m.H = g.Hc; m.NO = 1; m.act1 = h->cfg.critic_act + 1; m.KP0 = h->ts->KP0; m.net = DPPO_NET_CRITIC; m.din = g.Do;
-    m.fp = h->cfg.critic_act == DPPO_ACT_RELU ? 3 : 2;                               // Mish is smooth
+    m.fp = h->cfg.critic_act == DPPO_ACT_RELU ? 4 : 2;                               // Mish is smooth
     m.b0 = w + g.co.bin; m.b1 = w + g.co.b1; m.b2 = m.W->bias2; m.b3 = w + g.co.b3;
 }
 static size_t ts_mlp_ws_bytes(int N, int H, int KP0, bool mish, bool bwd) {
-    return 3 * (ws_bytes((size_t)N * KP0, 2) + 3 * ws_bytes((size_t)N * H, 2)) + 2 * ws_bytes((size_t)N * H, 2) * (size_t)((mish ? 2 : 0) + (bwd ? 3 : 0))
+    return 2 * (2 * ws_bytes((size_t)N * KP0, 2) + 3 * ws_bytes((size_t)N * H, 2)) + 2 * ws_bytes((size_t)N * H, 2) * (size_t)((mish ? 2 : 0) + (bwd ? 6 : 0))
          + 2 * ws_bytes((size_t)N * (H / 32), 4);
 }
 static SplitT ts_take(dppo_handle* h, size_t n, int planes) {
@@ -1109,10 +1199,11 @@ static SplitT ts_take(dppo_handle* h, size_t n, int planes) {
 }
 static void ts_mlp_take(dppo_handle* h, int N, TsMlp& m, bool bwd) {
     const size_t n = (size_t)N * m.H;
-    m.h0 = ts_take(h, (size_t)N * m.KP0, 3);
-    m.a0 = ts_take(h, n, 3); m.a1 = ts_take(h, n, 3); m.v = ts_take(h, n, 3);
+    m.h0 = ts_take(h, (size_t)N * m.KP0, 2);
+    m.a0 = ts_take(h, n, 2); m.a1 = ts_take(h, n, 2); m.v = ts_take(h, n, 2);
     if (m.act1 == 2) { m.g0 = ts_take(h, n, 2); m.g1 = ts_take(h, n, 2); }
     if (bwd) { m.dv = ts_take(h, n, 2); m.dh1 = ts_take(h, n, 2); m.du = ts_take(h, n, 2); }
+    if (bwd && m.fp == 4) { m.h0b = ts_take(h, (size_t)N * m.KP0, 2); m.a0b = ts_take(h, n, 2); m.a1b = ts_take(h, n, 2); m.vb = ts_take(h, n, 2); }
     m.m0 = ws_take<uint32_t>(h, (size_t)N * (m.H / 32)); m.m1 = ws_take<uint32_t>(h, (size_t)N * (m.H / 32));
 }
 static ts::Operand ts_op(const bf16* const* p, size_t off, bool mn_major, int64_t mn, int64_t k, int64_t ld) {
@@ -1133,7 +1224,9 @@ static int ts_run(dppo_handle* h, cudaStream_t s, const ts::Gemm& g) { const int
 // a layer on the pair kernel: out (planes) = epilogue(A B)
 static tsp::Gemm tsp_gemm_of(ts::Operand A, ts::Operand B, int M, int N, int planes, const SplitT& out, int out_planes, int ld_out) {
     tsp::Gemm g; memset(&g, 0, sizeof(g));
-    g.A = A; g.B = B; g.M = M; g.N = N; g.planes = planes; g.dual = planes == 3 ? 1 : 0;
+    if (planes == 4) { planes = 2; out_planes = 2; g.f16 = 1; g.dual = 1; g.epi.scale = 1.0f / ts::F16_WSCALE; }   // fp16 planes in and out
+    else g.dual = planes == 3 ? 1 : 0;
+    g.A = A; g.B = B; g.M = M; g.N = N; g.planes = planes;
     for (int pl = 0; pl < ts::MAXP; ++pl) g.out[pl] = out.p[pl];
     g.ld_out = ld_out; g.epi.M = M; g.epi.N = N; g.epi.out_planes = out_planes;
     return g;
@@ -1142,25 +1235,31 @@ static tsp::Gemm tsp_gemm_of(ts::Operand A, ts::Operand B, int M, int N, int pla
 static int ts_mlp_forward(dppo_handle* h, cudaStream_t s, const TsMlp& m, int N) {
     const int H = m.H, KP0 = m.KP0, P = m.fp; const TsNetW& W = *m.W;
     const size_t w0 = (size_t)H * H;
+    const bool f16 = P == 4;
+    const TsW& Ww2w0 = f16 ? W.fw2w0 : W.w2w0; const TsW& Ww1 = f16 ? W.fw1 : W.w1; const TsW& Ww3t = f16 ? W.fw3t : W.w3t;
     // L0: a0 = act(h0 W0 (+ b0))
-    tsp::Gemm g = tsp_gemm_of(tsK(m.h0, N, KP0, KP0), tswMN(W.w2w0, w0, H, KP0, H), N, H, P, m.a0, P, H);
+    tsp::Gemm g = tsp_gemm_of(tsK(m.h0, N, KP0, KP0), tswMN(Ww2w0, w0, H, KP0, H), N, H, P, m.a0, P, H);
     g.epi.bias = m.b0; g.epi.act = m.act1;
+    if (m.a0b.p[0]) { g.out2[0] = m.a0b.p[0]; g.out2[1] = m.a0b.p[1]; g.epi.out2 = 1; }
     if (m.act1 == 1) { g.epi.mask_out = m.m0; g.epi.ldm = H / 32; } else if (m.act1 == 2) { g.epi.gate_out = 1; g.gate[0] = m.g0.p[0]; g.gate[1] = m.g0.p[1]; }
     g.alg_flops = 2.0 * N * (double)m.din * H;
     DPPO_TRY(tsp::launch(h, s, g));
     // L1: a1 = act(a0 W1 + b1)
-    g = tsp_gemm_of(tsK(m.a0, N, H, H), tswMN(W.w1, 0, H, H, H), N, H, P, m.a1, P, H);
+    g = tsp_gemm_of(tsK(m.a0, N, H, H), tswMN(Ww1, 0, H, H, H), N, H, P, m.a1, P, H);
     g.epi.bias = m.b1; g.epi.act = m.act1;
+    if (m.a1b.p[0]) { g.out2[0] = m.a1b.p[0]; g.out2[1] = m.a1b.p[1]; g.epi.out2 = 1; }
     if (m.act1 == 1) { g.epi.mask_out = m.m1; g.epi.ldm = H / 32; } else if (m.act1 == 2) { g.epi.gate_out = 1; g.gate[0] = m.g1.p[0]; g.gate[1] = m.g1.p[1]; }
     DPPO_TRY(tsp::launch(h, s, g));
     // L2 + residual: v = [a1 | h0] [W2 ; W0] + b2 (+ b0): the residual u = h0 W0 is re-accumulated instead of stored and re-read
-    g = tsp_gemm_of(tsK(m.a1, N, H, H), tswMN(W.w2w0, 0, H, H, H), N, H, P, m.v, P, H);
-    g.A2 = tsK(m.h0, N, KP0, KP0); g.B2 = tswMN(W.w2w0, w0, H, KP0, H);
+    g = tsp_gemm_of(tsK(m.a1, N, H, H), tswMN(Ww2w0, 0, H, H, H), N, H, P, m.v, P, H);
+    g.A2 = tsK(m.h0, N, KP0, KP0); g.B2 = tswMN(Ww2w0, w0, H, KP0, H);
     g.epi.bias = m.b2;
+    if (m.vb.p[0]) { g.out2[0] = m.vb.p[0]; g.out2[1] = m.vb.p[1]; g.epi.out2 = 1; }
     g.alg_flops = 2.0 * N * (double)H * H;                                       // the re-accumulated residual is not algorithmic work
     DPPO_TRY(tsp::launch(h, s, g));
     // L3: out = v W3 + b3 (fp32, narrow: single-CTA kernel)
-    ts::Gemm o = ts_gemm_of(tsK(m.v, N, H, H), tswK(W.w3t, 0, 32, H, H), N, m.NO, P, P == 3 ? 1 : 0);
+    ts::Gemm o = ts_gemm_of(tsK(m.v, N, H, H), tswK(Ww3t, 0, 32, H, H), N, m.NO, 2, f16 ? 1 : 0);
+    if (f16) { o.f16 = 1; o.epi.scale = 1.0f / ts::F16_WSCALE; }
     o.epi.bias = m.b3; o.epi.out_f32 = m.out; o.epi.ld_f32 = m.NO;
     DPPO_TRY(ts_run(h, s, o));
     return 0;
@@ -1209,10 +1308,13 @@ static int ts_mlp_backward_dx(dppo_handle* h, cudaStream_t s, const TsMlp& m, co
 // du^T h0 + dv^T h0 (wide operand on M, output written transposed into dw0 [KP0][H])
 static void ts_mlp_dw_descs(const TsMlp& m, const SplitT& dout, int N, float* gnet, size_t ow1, size_t ow2, size_t ow3, float* dw0, tsp::DwDesc* d) {
     const int H = m.H, KP0 = m.KP0; const double r = (double)N; const SplitT none = split_null();
-    d[0] = tsp::DwDesc{m.a1, H, m.dv, H, none, none, gnet + ow2, H, H, H, 0, 2.0 * r * H * H};
-    d[1] = tsp::DwDesc{m.a0, H, m.dh1, H, none, none, gnet + ow1, H, H, H, 0, 2.0 * r * H * H};
-    d[2] = tsp::DwDesc{m.du, H, m.h0, KP0, m.dv, m.h0, dw0, H, KP0, H, 1, 2.0 * r * m.din * H};
-    d[3] = tsp::DwDesc{m.v, H, dout, 64, none, none, gnet + ow3, H, m.NO, m.NO, 0, 2.0 * r * H * m.NO};
+    // (fp = 4: the bf16 copies of the activations - one tcgen05.mma cannot take an fp16 and a bf16 operand, and the gradients are bf16)
+    const bool f = m.fp == 4;
+    const SplitT& a0 = f ? m.a0b : m.a0; const SplitT& a1 = f ? m.a1b : m.a1; const SplitT& v = f ? m.vb : m.v; const SplitT& h0 = f ? m.h0b : m.h0;
+    d[0] = tsp::DwDesc{a1, H, m.dv, H, none, none, gnet + ow2, H, H, H, 0, 2.0 * r * H * H};
+    d[1] = tsp::DwDesc{a0, H, m.dh1, H, none, none, gnet + ow1, H, H, H, 0, 2.0 * r * H * H};
+    d[2] = tsp::DwDesc{m.du, H, h0, KP0, m.dv, h0, dw0, H, KP0, H, 1, 2.0 * r * m.din * H};
+    d[3] = tsp::DwDesc{v, H, dout, 64, none, none, gnet + ow3, H, m.NO, m.NO, 0, 2.0 * r * H * m.NO};
 }
 static size_t ts_part_floats(const dppo_handle* h, int H) {
     const size_t a = tc_part_floats(h, H), b = (size_t)(h->sm_count / 2 + 1) * 65536;
@@ -1230,7 +1332,7 @@ static int ts_actor_forward(dppo_handle* h, cudaStream_t s, int net, const float
     TsMlp m; ts_actor_mlp(h, net, m);
     ts_mlp_take(h, N, m, false);
     m.out = eps;
-    ts_pack_h0_kernel<<<tc_nblk((size_t)N * (KP0 / 8), 256), 256, 0, s>>>(x, obs, trow, tconst, N, g.A, g.Do, g.T, KP0, obs_div, m.h0, chainK);
+    ts_pack_h0_kernel<<<tc_nblk((size_t)N * (KP0 / 8), 256), 256, 0, s>>>(x, obs, trow, tconst, N, g.A, g.Do, g.T, KP0, obs_div, m.h0, split_null(), chainK);
     TC_KCHECK(h);
     const int r = ts_mlp_forward(h, s, m, N);
     h->ws.used = mark;
@@ -1242,7 +1344,8 @@ static int ts_value(dppo_handle* h, cudaStream_t s, const float* obs, int N, flo
     TsMlp m; ts_critic_mlp(h, m);
     ts_mlp_take(h, N, m, false);
     m.out = v;
-    ts_pack_h0_kernel<<<tc_nblk((size_t)N * (KP0 / 8), 256), 256, 0, s>>>(nullptr, obs, nullptr, -1, N, g.A, g.Do, g.T, KP0, 1, m.h0, 0);
+    ts_pack_h0_kernel<<<tc_nblk((size_t)N * (KP0 / 8), 256), 256, 0, s>>>(nullptr, obs, nullptr, -1, N, g.A, g.Do, g.T, KP0, 1,
+                                                                          m.fp == 4 ? m.h0 : split_null(), m.fp == 4 ? split_null() : m.h0, 0);
     TC_KCHECK(h);
     return ts_mlp_forward(h, s, m, N);
 }
@@ -1301,11 +1404,14 @@ static int ts_ppo_step(dppo_handle* h, cudaStream_t s, const float* obs, const f
     auto fork = [&]() -> int { if (side) { CUDA_TRY(cudaEventRecord(h->aux_ev[0], s)); CUDA_TRY(cudaStreamWaitEvent(sc, h->aux_ev[0], 0)); } return 0; };
     auto join = [&]() -> int { if (side) { CUDA_TRY(cudaEventRecord(h->aux_ev[1], sc)); CUDA_TRY(cudaStreamWaitEvent(s, h->aux_ev[1], 0)); } return 0; };
     // h0 straight from (prev, obs, K-1-inds): tconst = -(K) flags "t = K-1-trow[r]"; the critic reads the same tile (its x / one-hot rows of W0 are zero)
-    if (idx) ts_pack_h0_kernel<<<tc_nblk((size_t)N * (KP0 / 8), 256), 256, 0, s>>>(idx->chains, idx->obs, nullptr, 0, N, g.A, g.Do, g.T, KP0, 1, ma.h0, 0,
+    // (the actor takes fp16 planes; a smooth critic the bf16 ones written by the same pass, a critic with kinks shares the actor's)
+    const SplitT hb = ma.h0b;                                   // bf16 copy: the weight-gradient operand, and a smooth critic's input
+    if (mc.fp != 4) mc.h0 = ma.h0b;
+    if (idx) ts_pack_h0_kernel<<<tc_nblk((size_t)N * (KP0 / 8), 256), 256, 0, s>>>(idx->chains, idx->obs, nullptr, 0, N, g.A, g.Do, g.T, KP0, 1, ma.h0, hb, 0,
                                                                                      idx->flat, idx->K, idx->P, idx->bad);
-    else ts_pack_h0_kernel<<<tc_nblk((size_t)N * (KP0 / 8), 256), 256, 0, s>>>(prev, obs, inds, -g.K, N, g.A, g.Do, g.T, KP0, 1, ma.h0, 0);
+    else ts_pack_h0_kernel<<<tc_nblk((size_t)N * (KP0 / 8), 256), 256, 0, s>>>(prev, obs, inds, -g.K, N, g.A, g.Do, g.T, KP0, 1, ma.h0, hb, 0);
     TC_KCHECK(h);
-    mc.h0 = ma.h0;
+    if (mc.fp == 4) { mc.h0 = ma.h0; mc.h0b = ma.h0b; }
     DPPO_TRY(fork());
     if (adv_std < 0.f) {
         if (idx) adv_stats_kernel<<<1, 1024, 0, sc>>>(idx->adv, N, h->scalars, idx->flat, idx->K, idx->P);
@@ -1386,7 +1492,7 @@ static int ts_pretrain_grads(dppo_handle* h, cudaStream_t s, const float* action
     float* cpa = ws_take<float>(h, (size_t)nrb * 2 * g.H);
     ma.out = eps;
     pretrain_prep_kernel<<<tc_nblk(ne, 256), 256, 0, s>>>(actions, t_in, noise_in, N, g.A, g.T, h->sched, seed, offset, row_offset, trow, noise, xn); TC_KCHECK(h);
-    ts_pack_h0_kernel<<<tc_nblk((size_t)N * (KP0 / 8), 256), 256, 0, s>>>(xn, obs, trow, 0, N, g.A, g.Do, g.T, KP0, 1, ma.h0, 0); TC_KCHECK(h);
+    ts_pack_h0_kernel<<<tc_nblk((size_t)N * (KP0 / 8), 256), 256, 0, s>>>(xn, obs, trow, 0, N, g.A, g.Do, g.T, KP0, 1, ma.h0, ma.h0b, 0); TC_KCHECK(h);
     DPPO_TRY(ts_mlp_forward(h, s, ma, N));
     const float scale = 1.0f / ((float)N_global * (float)g.A);
     mse_loss_kernel<<<nlb, 256, 0, s>>>(eps, noise, ne, scale, deps, bsum); TC_KCHECK(h);

@@ -1,8 +1,8 @@
 """GPU (-m gpu): the split-precision tcgen05 mode (DPPO_PREC_BF16X3) against the fp32 oracle at north_star's fp32 tolerance.
 
-Every operand is carried as bf16 planes (three = 24 mantissa bits in the actor's forward GEMMs, two = 16 bits in the smooth
-Mish critic, the backward and the weight-gradient GEMMs) and every product is the sum of the exact plane products with fp32
-accumulation in tensor memory (csrc/ts_path.cuh), so the bounds here are the fp32 mode's (tests/test_gpu_parity.py), not the
+Every operand is carried as 16-bit planes (two fp16 planes = 22 mantissa bits in the actor's forward GEMMs, two bf16 planes = 16
+bits in the smooth Mish critic, the backward and the weight-gradient GEMMs) and every product is the sum of the exact plane products
+with fp32 accumulation in tensor memory (csrc/ts_path.cuh), so the bounds here are the fp32 mode's (tests/test_gpu_parity.py), not the
 bf16 mode's.  Measured on a B200 in brackets:
   eps ............................... 5e-6 norm-wise relative [1.0e-6]; value 5e-5 [1.2e-5]
   per-step log-probs ................ 1e-3 absolute (north_star) [5.7e-6]
@@ -41,6 +41,8 @@ def _flat(obs):
     (0, 1, 1000, 256, 320, 1, 3),
     (0, 0, 1000, 24, 512, 1, 2),   # output layer: narrow N
     (0, 0, 1000, 24, 512, 1, 3),
+    (0, 1, 300, 512, 576, 1, 4),   # planes = 4: two fp16 planes (B scaled by 2^10), two accumulators - the forward format
+    (0, 0, 1000, 24, 512, 1, 4),   # the actor's output layer
     (0, 0, 260, 512, 64, 1, 2),    # dv = dout W3^T: one k-block
     (0, 0, 515, 256, 256, 1, 2),   # critic backward
     (1, 1, 512, 512, 5000, 7, 2),  # weight gradient: both MN-major, K = rows (ragged), split-K partials
@@ -86,6 +88,9 @@ def test_split_gemm_kernel_matches_float64(pair, a_mn, b_mn, M, N, K, splits, pl
     (0, 700, 512, 512, 2, 0),      # backward: K-major weights
     (0, 260, 512, 64, 2, 0),       # dv = dout W3^T
     (1, 40000, 512, 512, 3, 1),    # many tiles per pair (persistent loop, both accumulator buffers)
+    (1, 300, 512, 64, 4, 1),       # planes = 4: the forward layers as they run - fp16 planes in and out, two accumulators
+    (1, 1000, 512, 576, 4, 1),
+    (1, 40000, 512, 512, 4, 1),
 ])
 def test_pair_gemm_kernel_matches_float64(pair, b_mn, M, N, K, planes, act):
     """tsp::pair_gemm_kernel (cta_group::2, TMA-store epilogue) on random fp32 operands vs float64."""
