@@ -10,7 +10,7 @@ metric — denoised action chunks/s of the T=20 chain at 40 env copies — is me
 run and reported under "sampling" (it is dependency-latency-bound, not a throughput kernel).
 
 Precision: the headline (`value`, `e2e`, `roofline`) is the fp32-FAITHFUL tensor-core mode `bf16x3` (tcgen05; every operand
-as bf16 planes, every product as the sum of exact plane products, fp32 accumulation: it meets north_star's fp32 tolerance,
+as two 16-bit planes (fp16 in the forward pass, bf16 behind it), every product as the sum of exact plane products, fp32 accumulation: it meets north_star's fp32 tolerance,
 tests/test_gpu_fullsize_oracle.py), i.e. the reference's own precision.  The faster plain-bf16 tensor mode (looser stated
 bounds) and the CUDA-core FFMA mode are measured in the same run and reported under "bf16_mode" / "fp32_ffma_mode".
 `--precision bf16|fp32` makes one of those the headline instead.
@@ -43,7 +43,7 @@ WORKLOAD = (f"{TASK}-v2 ft_ppo_diffusion_mlp PPO update: {N_ROWS} (env-step,k) r
             "(obs 17, act 6, Ta 4, T 20, K 10, actor 512x3 ReLU, critic 256x3 Mish), loss + backward + AdamW")
 DTYPES = {"bf16x3": "bf16x3", "bf16": "bf16", "fp32": "fp32"}
 PRECISION_NOTE = {
-    "bf16x3": "tcgen05, operands as bf16 planes (3 in the actor forward, 2 elsewhere), exact plane products, fp32 accumulate / masters / loss / AdamW: fp32-faithful (north_star tolerance)",
+    "bf16x3": "tcgen05, operands as 16-bit planes (two fp16 planes = 22 bits in the actor forward, two bf16 planes elsewhere), exact plane products (3 per multiply-add), fp32 accumulate / masters / loss / AdamW: fp32-faithful (north_star tolerance)",
     "bf16": "tcgen05, bf16 operands, fp32 accumulate / masters / loss / AdamW: looser stated bounds (tests/test_gpu_bf16.py)",
     "fp32": "CUDA-core FFMA everywhere",
 }

@@ -386,6 +386,7 @@ struct Epi {
 struct Params {
     int m_blocks, n_blocks, kblocks, ka_blocks;
     int stg, nslot, dbuf;            // shared-memory plan (host): load stages, staging slots, two staging buffers of nslot / 2 slots
+    int gslot;                       // first of the four slots behind the staging slots that take the gate planes in (Mish backward)
     Epi epi;
 };
 struct Maps { CUtensorMap a[2][ts::MAXP], b[2][ts::MAXP], out[ts::MAXP], gate[2], out2[2]; };
@@ -395,10 +396,11 @@ template <int P, int BNP> __host__ __device__ constexpr int stage_bytes() { retu
 // third load stage is worth more than a second staging buffer (fp16 forward layer 100 -> 88 us), a second staging buffer more than a
 // fourth stage; two stages are the minimum.
 constexpr int SMEM_BUDGET = 227 * 1024 - 1024 - 256;
-static inline void smem_plan(int stage_bytes, int planes_staged, int& stg, int& nslot, int& dbuf) {
+static inline void smem_plan(int stage_bytes, int planes_staged, int fixed_slots, int& stg, int& nslot, int& dbuf) {
+    const int budget = SMEM_BUDGET - fixed_slots * SLOT;
     nslot = planes_staged; dbuf = 0;
-    stg = (SMEM_BUDGET - nslot * SLOT) / stage_bytes;
-    if (stg >= 3 && (SMEM_BUDGET - 2 * nslot * SLOT) / stage_bytes >= 3) { nslot *= 2; dbuf = 1; stg = (SMEM_BUDGET - nslot * SLOT) / stage_bytes; }
+    stg = (budget - nslot * SLOT) / stage_bytes;
+    if (stg >= 3 && (budget - 2 * nslot * SLOT) / stage_bytes >= 3) { nslot *= 2; dbuf = 1; stg = (budget - nslot * SLOT) / stage_bytes; }
     if (stg > 4) stg = 4;
 }
 
@@ -406,7 +408,7 @@ __device__ __forceinline__ void epi_barrier8() { asm volatile("bar.sync 1, 256;"
 
 template <bool B_MN, int P, bool DUAL, int BNP, bool F16 = false>
 __global__ void __launch_bounds__(PTHREADS, 1) pair_gemm_kernel(const __grid_constant__ Maps maps, const Params p) {
-    const int STG = p.stg, NSLOT = p.nslot;
+    const int STG = p.stg, NSLOT = p.nslot + (p.epi.gate_in[0] ? 4 : 0);
     constexpr int A_TILE = 128 * 64 * 2, B_TILE = (BNP / 2) * 64 * 2, STAGE = stage_bytes<P, BNP>();
     constexpr int NACC = DUAL ? 2 : 1, ACC_COLS = NACC * BNP;
     static_assert(2 * ACC_COLS <= 512, "accumulators exceed tensor memory");
@@ -418,7 +420,8 @@ __global__ void __launch_bounds__(PTHREADS, 1) pair_gemm_kernel(const __grid_con
     uint64_t* empty = bars + STG;               // per CTA: multicast commit of the MMAs that read the stage
     uint64_t* tfull = bars + 2 * STG;           // per CTA: multicast commit, accumulator complete
     uint64_t* tempty = tfull + 2;               // leader's: the 16 epilogue warps of the pair drained the accumulator
-    uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+    uint64_t* gfull = tempty + 2;               // per CTA: the gate planes of a column group arrived (TMA, two buffers)
+    uint32_t* tmem_slot = (uint32_t*)(gfull + 2);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = fc::cluster_ctarank();
     const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
@@ -427,7 +430,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) pair_gemm_kernel(const __grid_con
     if (warp == 0 && lane == 0) {
         for (int pl = 0; pl < P; ++pl) { tma_prefetch_desc(&maps.a[0][pl]); tma_prefetch_desc(&maps.b[0][pl]); }
         for (int i = 0; i < STG; ++i) { mbar_init(&full[i], 2); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 16); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 16); mbar_init(&gfull[i], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     fc::cluster_sync_all();                     // barriers of both CTAs initialised before anything remote
@@ -531,6 +534,19 @@ __global__ void __launch_bounds__(PTHREADS, 1) pair_gemm_kernel(const __grid_con
         const bool dbuf = p.dbuf != 0;
         const uint32_t o2 = (uint32_t)P, og = o2 + ((F16 && e.out2) ? 2u : 0u);     // slot offsets of the copies / the gates inside a buffer
         uint32_t gcount = 0;
+        // Mish backward: the gate planes mish'(pre-activation) of a column group come in by TMA one group ahead of their use (two
+        // buffers of two planes; the store thread issues, everyone waits on the buffer's barrier).  A buffer is re-filled after all
+        // eight warps have passed the barriers of the group that read it.
+        const bool gin = e.gate_in[0] != nullptr;
+        auto gate_issue = [&](int t, int g, uint32_t gi) {
+            const int mb = t / p.n_blocks, nb = t % p.n_blocks;
+            uint64_t* bar = &gfull[gi & 1u];
+            uint8_t* dst = slots + (size_t)(p.gslot + 2 * (int)(gi & 1u)) * SLOT;
+            mbar_expect_tx(bar, 2 * SLOT);
+            tma_load_2d(dst, &maps.gate[0], bar, nb * BNP + g * 64, mb * 256 + (int)rank * 128);
+            tma_load_2d(dst + SLOT, &maps.gate[1], bar, nb * BNP + g * 64, mb * 256 + (int)rank * 128);
+        };
+        if (gin && store_thread && pair < tiles) gate_issue(pair, 0, 0u);
         for (int tile = pair; tile < tiles; tile += npairs) {
             const int m_blk = tile / p.n_blocks, n_blk = tile % p.n_blocks;
             const int row0 = m_blk * 256 + (int)rank * 128, m = row0 + rloc;
@@ -540,6 +556,10 @@ __global__ void __launch_bounds__(PTHREADS, 1) pair_gemm_kernel(const __grid_con
 #pragma unroll 1
             for (int g = 0; g < BNP / 64; ++g) {
                 const int n0 = n_blk * BNP + g * 64 + half * 32;              // this warp's 32 columns
+                if (gin && store_thread) {                                    // next group's gates (this tile's, or the next tile's first)
+                    if (g + 1 < BNP / 64) gate_issue(tile, g + 1, gcount + 1u);
+                    else if (tile + npairs < tiles) gate_issue(tile + npairs, 0, gcount + 1u);
+                }
                 uint32_t r[32];
                 tmem_ld32(tmem_base + lane_base + (uint32_t)(acc * ACC_COLS + g * 64 + half * 32), r);
                 float v[32];
@@ -583,11 +603,15 @@ __global__ void __launch_bounds__(PTHREADS, 1) pair_gemm_kernel(const __grid_con
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = ((bits >> j) & 1u) ? v[j] : 0.f;
                 }
-                if (e.gate_in[0] && row_ok && col_ok) {
-                    const bf16* g0 = e.gate_in[0] + (size_t)m * e.ldg + n0; const bf16* g1 = e.gate_in[1] + (size_t)m * e.ldg + n0;
+                if (gin) {
+                    mbar_wait(&gfull[gcount & 1u], (gcount >> 1) & 1u);
+                    const uint32_t ga = slot_addr + (uint32_t)(p.gslot + 2 * (int)(gcount & 1u)) * SLOT + row_off;
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        const uint4 uh = *reinterpret_cast<const uint4*>(g0 + q * 8), ul = *reinterpret_cast<const uint4*>(g1 + q * 8);
+                        uint4 uh, ul;
+                        const uint32_t off = ((uint32_t)(half * 4 + q) ^ sw) << 4;
+                        fc::ld_shared_v4(ga + off, uh.x, uh.y, uh.z, uh.w);
+                        fc::ld_shared_v4(ga + SLOT + off, ul.x, ul.y, ul.z, ul.w);
                         const bf16* hb = reinterpret_cast<const bf16*>(&uh); const bf16* lb = reinterpret_cast<const bf16*>(&ul);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) v[q * 8 + j] *= __bfloat162float(hb[j]) + __bfloat162float(lb[j]);
@@ -700,7 +724,9 @@ static int launch_t(dppo_handle* h, cudaStream_t s, const Gemm& g) {
         DPPO_TRY(make_map(&mp.out[pl], g.out[pl < g.epi.out_planes ? pl : 0], g.M, g.N, g.ld_out, 128, 64));
     }
     for (int i = 0; i < 2; ++i) {
-        if (g.epi.gate_out) DPPO_TRY(make_map(&mp.gate[i], g.gate[i], g.M, g.N, g.ld_out, 128, 64)); else mp.gate[i] = mp.out[0];
+        if (g.epi.gate_out) DPPO_TRY(make_map(&mp.gate[i], g.gate[i], g.M, g.N, g.ld_out, 128, 64));
+        else if (g.epi.gate_in[0]) DPPO_TRY(make_map(&mp.gate[i], g.epi.gate_in[i], g.M, g.N, g.epi.ldg, 128, 64));
+        else mp.gate[i] = mp.out[0];
         if (g.epi.out2) DPPO_TRY(make_map(&mp.out2[i], g.out2[i], g.M, g.N, g.ld_out, 128, 64)); else mp.out2[i] = mp.out[0];
     }
     if (g.epi.out2 && !F16) DPPO_FAIL(-7, "split gemm (pair): bf16 copies are an option of the fp16-plane kernel");
@@ -709,9 +735,11 @@ static int launch_t(dppo_handle* h, cudaStream_t s, const Gemm& g) {
     const int ka = (int)((g.A.k + 63) / 64), ka2 = g.A2.p[0] ? (int)((g.A2.k + 63) / 64) : 0;
     p.kblocks = ka + ka2; p.ka_blocks = ka;
     p.epi = g.epi;
-    smem_plan(stage_bytes<P, BNP>(), P + (g.epi.out2 ? 2 : 0) + (g.epi.gate_out ? 2 : 0), p.stg, p.nslot, p.dbuf);
+    if (g.epi.gate_out && g.epi.gate_in[0]) DPPO_FAIL(-7, "split gemm (pair): gate planes go out (forward) or come in (backward), not both");
+    smem_plan(stage_bytes<P, BNP>(), P + (g.epi.out2 ? 2 : 0) + (g.epi.gate_out ? 2 : 0), g.epi.gate_in[0] ? 4 : 0, p.stg, p.nslot, p.dbuf);
+    p.gslot = p.nslot;
     if (p.stg < 2 || g.epi.out_planes > P) DPPO_FAIL(-7, "split gemm (pair): shared-memory plan does not fit (%d stages, %d slots)", p.stg, p.nslot);
-    const size_t smem_bytes = (size_t)p.stg * stage_bytes<P, BNP>() + (size_t)p.nslot * SLOT + 1024 + 256;
+    const size_t smem_bytes = (size_t)p.stg * stage_bytes<P, BNP>() + (size_t)(p.nslot + (g.epi.gate_in[0] ? 4 : 0)) * SLOT + 1024 + 256;
     auto kern = pair_gemm_kernel<B_MN, P, DUAL, BNP, F16>;
     static bool attr_set_dev[64] = {};      // function attributes are per device
     bool& attr_set = attr_set_dev[h->device & 63];
