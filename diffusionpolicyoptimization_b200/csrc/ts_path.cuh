@@ -79,6 +79,21 @@ __device__ __forceinline__ void split_f16(float v, bf16& hi, bf16& lo) {
     hi = f16_bits(v, b0);
     lo = f16_bits(v - b0, b1);
 }
+// two values at a time with the packed conversions (F2FP.*.PACK_AB; the scalar __float2bfloat16 compiles to F2F on the quarter-rate
+// conversion pipe): hi2 / lo2 hold (a, b) as the low / high 16 bits
+__device__ __forceinline__ void split_bf16_pair(float a, float b, uint32_t& hi2, uint32_t& lo2) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h);
+    const float ra = a - __uint_as_float(hb << 16), rb = b - __uint_as_float(hb & 0xffff0000u);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(ra, rb);
+    hi2 = hb; lo2 = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ void split_f16_pair(float a, float b, uint32_t& hi2, uint32_t& lo2) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 back = __half22float2(h);
+    const __half2 l = __floats2half2_rn(a - back.x, b - back.y);
+    hi2 = *reinterpret_cast<const uint32_t*>(&h); lo2 = *reinterpret_cast<const uint32_t*>(&l);
+}
 __device__ __forceinline__ float f16_plane_value(bf16 b) { return __half2float(__ushort_as_half(__bfloat16_as_ushort(b))); }
 constexpr float F16_WSCALE = 1024.f;     // forward weights are stored as fp16 planes of 2^10 w
 
@@ -641,34 +656,39 @@ __global__ void __launch_bounds__(PTHREADS, 1) pair_gemm_kernel(const __grid_con
                 const uint32_t c0 = (uint32_t)(half * 4);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    __align__(16) bf16 t[ts::MAXP][8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        if (F16) ts::split_f16(v[q * 8 + j], t[0][j], t[1][j]);
-                        else if (P == 3) ts::split_bf16_3(v[q * 8 + j], t[0][j], t[1][j], t[2][j]);
-                        else ts::split_bf16(v[q * 8 + j], t[0][j], t[1][j]);
-                    }
                     const uint32_t off = row_off + (((c0 + (uint32_t)q) ^ sw) << 4);
+                    if (P == 3) {
+                        __align__(16) bf16 t[ts::MAXP][8];
 #pragma unroll
-                    for (int pl = 0; pl < P; ++pl) {
-                        const uint4 u = *reinterpret_cast<const uint4*>(t[pl]);
-                        fc::st_shared_v4(slot_addr + (sbuf + pl) * SLOT + off, u.x, u.y, u.z, u.w);
+                        for (int j = 0; j < 8; ++j) ts::split_bf16_3(v[q * 8 + j], t[0][j], t[1][j], t[2][j]);
+#pragma unroll
+                        for (int pl = 0; pl < P; ++pl) {
+                            const uint4 u = *reinterpret_cast<const uint4*>(t[pl]);
+                            fc::st_shared_v4(slot_addr + (sbuf + pl) * SLOT + off, u.x, u.y, u.z, u.w);
+                        }
+                    } else {
+                        uint32_t hi[4], lo[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            if (F16) ts::split_f16_pair(v[q * 8 + 2 * j], v[q * 8 + 2 * j + 1], hi[j], lo[j]);
+                            else ts::split_bf16_pair(v[q * 8 + 2 * j], v[q * 8 + 2 * j + 1], hi[j], lo[j]);
+                        }
+                        fc::st_shared_v4(slot_addr + sbuf * SLOT + off, hi[0], hi[1], hi[2], hi[3]);
+                        fc::st_shared_v4(slot_addr + (sbuf + 1) * SLOT + off, lo[0], lo[1], lo[2], lo[3]);
                     }
                     if (F16 && e.out2) {
-                        __align__(16) bf16 bh[8]; __align__(16) bf16 bl[8];
+                        uint32_t hi[4], lo[4];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) ts::split_bf16(v[q * 8 + j], bh[j], bl[j]);
-                        const uint4 u0 = *reinterpret_cast<const uint4*>(bh), u1 = *reinterpret_cast<const uint4*>(bl);
-                        fc::st_shared_v4(slot_addr + (sbuf + o2) * SLOT + off, u0.x, u0.y, u0.z, u0.w);
-                        fc::st_shared_v4(slot_addr + (sbuf + o2 + 1) * SLOT + off, u1.x, u1.y, u1.z, u1.w);
+                        for (int j = 0; j < 4; ++j) ts::split_bf16_pair(v[q * 8 + 2 * j], v[q * 8 + 2 * j + 1], hi[j], lo[j]);
+                        fc::st_shared_v4(slot_addr + (sbuf + o2) * SLOT + off, hi[0], hi[1], hi[2], hi[3]);
+                        fc::st_shared_v4(slot_addr + (sbuf + o2 + 1) * SLOT + off, lo[0], lo[1], lo[2], lo[3]);
                     }
                     if (e.gate_out) {
-                        __align__(16) bf16 gh[8]; __align__(16) bf16 gl[8];
+                        uint32_t hi[4], lo[4];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) ts::split_bf16(gt[q * 8 + j], gh[j], gl[j]);
-                        const uint4 u0 = *reinterpret_cast<const uint4*>(gh), u1 = *reinterpret_cast<const uint4*>(gl);
-                        fc::st_shared_v4(slot_addr + (sbuf + og) * SLOT + off, u0.x, u0.y, u0.z, u0.w);
-                        fc::st_shared_v4(slot_addr + (sbuf + og + 1) * SLOT + off, u1.x, u1.y, u1.z, u1.w);
+                        for (int j = 0; j < 4; ++j) ts::split_bf16_pair(gt[q * 8 + 2 * j], gt[q * 8 + 2 * j + 1], hi[j], lo[j]);
+                        fc::st_shared_v4(slot_addr + (sbuf + og) * SLOT + off, hi[0], hi[1], hi[2], hi[3]);
+                        fc::st_shared_v4(slot_addr + (sbuf + og + 1) * SLOT + off, lo[0], lo[1], lo[2], lo[3]);
                     }
                 }
                 fc::fence_async_smem();
