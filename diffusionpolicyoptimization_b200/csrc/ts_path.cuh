@@ -409,13 +409,14 @@ struct Maps { CUtensorMap a[2][ts::MAXP], b[2][ts::MAXP], out[ts::MAXP], gate[2]
 template <int P, int BNP> __host__ __device__ constexpr int stage_bytes() { return P * (128 * 64 * 2 + (BNP / 2) * 64 * 2); }
 // The 227 KB of a CTA are split between load stages and epilogue staging slots per launch.  Measured (50 000 x 512 x 512 layers): a
 // third load stage is worth more than a second staging buffer (fp16 forward layer 100 -> 88 us), a second staging buffer more than a
-// fourth stage; two stages are the minimum.
+// fourth stage; two stages are the minimum - and all a layer of one or two k-blocks can use: there the second staging buffer comes first.
 constexpr int SMEM_BUDGET = 227 * 1024 - 1024 - 256;
-static inline void smem_plan(int stage_bytes, int planes_staged, int fixed_slots, int& stg, int& nslot, int& dbuf) {
+static inline void smem_plan(int stage_bytes, int planes_staged, int fixed_slots, int kblocks, int& stg, int& nslot, int& dbuf) {
     const int budget = SMEM_BUDGET - fixed_slots * SLOT;
+    const int want = kblocks <= 2 ? 2 : 3;
     nslot = planes_staged; dbuf = 0;
     stg = (budget - nslot * SLOT) / stage_bytes;
-    if (stg >= 3 && (budget - 2 * nslot * SLOT) / stage_bytes >= 3) { nslot *= 2; dbuf = 1; stg = (budget - nslot * SLOT) / stage_bytes; }
+    if (stg >= want && (budget - 2 * nslot * SLOT) / stage_bytes >= want) { nslot *= 2; dbuf = 1; stg = (budget - nslot * SLOT) / stage_bytes; }
     if (stg > 4) stg = 4;
 }
 
@@ -756,7 +757,7 @@ static int launch_t(dppo_handle* h, cudaStream_t s, const Gemm& g) {
     p.kblocks = ka + ka2; p.ka_blocks = ka;
     p.epi = g.epi;
     if (g.epi.gate_out && g.epi.gate_in[0]) DPPO_FAIL(-7, "split gemm (pair): gate planes go out (forward) or come in (backward), not both");
-    smem_plan(stage_bytes<P, BNP>(), P + (g.epi.out2 ? 2 : 0) + (g.epi.gate_out ? 2 : 0), g.epi.gate_in[0] ? 4 : 0, p.stg, p.nslot, p.dbuf);
+    smem_plan(stage_bytes<P, BNP>(), P + (g.epi.out2 ? 2 : 0) + (g.epi.gate_out ? 2 : 0), g.epi.gate_in[0] ? 4 : 0, p.kblocks, p.stg, p.nslot, p.dbuf);
     p.gslot = p.nslot;
     if (p.stg < 2 || g.epi.out_planes > P) DPPO_FAIL(-7, "split gemm (pair): shared-memory plan does not fit (%d stages, %d slots)", p.stg, p.nslot);
     const size_t smem_bytes = (size_t)p.stg * stage_bytes<P, BNP>() + (size_t)(p.nslot + (g.epi.gate_in[0] ? 4 : 0)) * SLOT + 1024 + 256;
