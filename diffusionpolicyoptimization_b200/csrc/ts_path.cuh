@@ -421,6 +421,16 @@ static inline void smem_plan(int stage_bytes, int planes_staged, int fixed_slots
 }
 
 __device__ __forceinline__ void epi_barrier8() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// launches of consecutive plane GEMMs in one stream overlap the next grid's prologue with the previous grid's last wave (DPPO_NO_PDL=1: off)
+static inline bool pdl_enabled() { static int v = -1; if (v < 0) { const char* e = getenv("DPPO_NO_PDL"); v = (e && atoi(e)) ? 0 : 1; } return v != 0; }
+static inline int pdl_attrs(cudaLaunchAttribute* at) {
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    if (!pdl_enabled()) return 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[1].val.programmaticStreamSerializationAllowed = 1;
+    return 2;
+}
 
 template <bool B_MN, int P, bool DUAL, int BNP, bool F16 = false>
 __global__ void __launch_bounds__(PTHREADS, 1) pair_gemm_kernel(const __grid_constant__ Maps maps, const Params p) {
@@ -442,6 +452,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) pair_gemm_kernel(const __grid_con
     const uint32_t rank = fc::cluster_ctarank();
     const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
     const int tiles = p.m_blocks * p.n_blocks;
+    pdl_launch_dependents();                    // the next kernel's CTAs may take this SM as soon as this CTA is gone
 
     if (warp == 0 && lane == 0) {
         for (int pl = 0; pl < P; ++pl) { tma_prefetch_desc(&maps.a[0][pl]); tma_prefetch_desc(&maps.b[0][pl]); }
@@ -459,6 +470,9 @@ __global__ void __launch_bounds__(PTHREADS, 1) pair_gemm_kernel(const __grid_con
     fc::cluster_sync_all();
     tcgen05_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+    // programmatic dependent launch: this grid may have been scheduled while the previous kernel of the stream was draining (its barriers,
+    // tensor memory and tensor-map prefetches above overlap that tail); nothing global is touched before the previous grid has completed
+    pdl_wait();
 
     if (warp == 0) {
         // ---- TMA producer (both CTAs): own 128 A rows, own half of the B tile, every plane; bytes and arrival go to the leader
@@ -768,9 +782,8 @@ static int launch_t(dppo_handle* h, cudaStream_t s, const Gemm& g) {
     const int tiles = p.m_blocks * p.n_blocks, npairs = h->sm_count / 2;
     const int grid = 2 * (tiles < npairs ? tiles : npairs);
     cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1; cfg.blockDim = dim3(PTHREADS); cfg.gridDim = dim3(grid); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = s;
+    cudaLaunchAttribute at[2];
+    cfg.attrs = at; cfg.numAttrs = pdl_attrs(at); cfg.blockDim = dim3(PTHREADS); cfg.gridDim = dim3(grid); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = s;
     prof_begin(h, s);
     cudaError_t le = cudaLaunchKernelEx(&cfg, kern, mp, p);
     prof_end(h, s, g.alg_flops > 0 ? g.alg_flops : 2.0 * (double)g.M * (double)g.N * (double)(g.A.k + (g.A2.p[0] ? g.A2.k : 0)), 0,
@@ -819,6 +832,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dw_pair_kernel(const __grid_co
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = fc::cluster_ctarank();
     const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    pdl_launch_dependents();
 
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < DSTAGES; ++i) { mbar_init(&full[i], 2); mbar_init(&empty[i], 1); }
@@ -835,6 +849,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dw_pair_kernel(const __grid_co
     fc::cluster_sync_all();
     tcgen05_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+    pdl_wait();
 
     auto decode = [&](int item, int& pi, int& m_blk, int& n_blk, int& split) {
         pi = 0;
@@ -1020,9 +1035,8 @@ static int launch_dw_group(dppo_handle* h, cudaStream_t s, const DwDesc* d, int 
     if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(dw_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dw_smem_bytes())); attr_set = true; }
     const int grid = 2 * (items < npairs ? items : npairs);
     cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1; cfg.blockDim = dim3(NUM_THREADS); cfg.gridDim = dim3(grid); cfg.dynamicSmemBytes = dw_smem_bytes(); cfg.stream = s;
+    cudaLaunchAttribute at[2];
+    cfg.attrs = at; cfg.numAttrs = pdl_attrs(at); cfg.blockDim = dim3(NUM_THREADS); cfg.gridDim = dim3(grid); cfg.dynamicSmemBytes = dw_smem_bytes(); cfg.stream = s;
     prof_begin(h, s);
     cudaError_t le = cudaLaunchKernelEx(&cfg, dw_pair_kernel, maps, gp);
     double exec = 0;
