@@ -210,6 +210,30 @@ __device__ __forceinline__ void tc_reduce_cols_body(const int bid, const float* 
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) { if (out2 && c >= split) out2[c - split] = s; else out[c] = s; }
 }
+// the same sums for MANY partial rows (the plane GEMM epilogues leave one row per 32 batch rows: 1563 at 50 000): a 512-thread block owns 32
+// columns, lane = column, its 16 warps stride over the rows (every read a full 128-byte line), fixed-order combine through shared memory
+__device__ __forceinline__ void tc_reduce_cols_wide_body(const int bid, const float* __restrict__ part, int nb, size_t stride, int ncols,
+                                                         float* __restrict__ out, int split, float* __restrict__ out2) {
+    __shared__ float red[16][33];
+    const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5, c = bid * 32 + lane;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    if (c < ncols) {
+        int b = rg;
+        for (; b + 48 < nb; b += 64) {
+            s0 += part[(size_t)b * stride + c]; s1 += part[(size_t)(b + 16) * stride + c];
+            s2 += part[(size_t)(b + 32) * stride + c]; s3 += part[(size_t)(b + 48) * stride + c];
+        }
+        for (; b < nb; b += 16) s0 += part[(size_t)b * stride + c];
+    }
+    red[rg][lane] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (rg == 0 && c < ncols) {
+        float s = 0.f;
+#pragma unroll
+        for (int g = 0; g < 16; ++g) s += red[g][lane];
+        if (out2 && c >= split) out2[c - split] = s; else out[c] = s;
+    }
+}
 __global__ void __launch_bounds__(256) tc_reduce_cols_kernel(const float* __restrict__ part, int nb, size_t stride, int ncols, float* __restrict__ out,
                                                              int split = 0, float* __restrict__ out2 = nullptr) {
     tc_reduce_cols_body(blockIdx.x, part, nb, stride, ncols, out, split, out2);
@@ -222,7 +246,8 @@ struct TcTailArgs {
     int first[9];                                  // first block of role r; first[8] = grid size
     // metrics
     const double* bsum; int blocks_done; float inv_nglobal, frac_local; float* metrics;
-    // column reductions
+    // column reductions (wide: the 32-columns-per-block body for many partial rows)
+    int wide;
     const float* colb3; int ncol3; float* b3a; int split3; float* b3c;
     const float* cpa; int rows_a; int HA; float* b2a; float* b1a;
     const float* cpc; int rows_c; int HC; float* b2c; float* b1c;
@@ -236,8 +261,13 @@ __global__ void __launch_bounds__(512) tc_ppo_tail_kernel(const TcTailArgs a) {
     const int b = blockIdx.x;
     if (b < a.first[1]) ppo_metrics_body(a.bsum, a.blocks_done, a.inv_nglobal, a.frac_local, a.metrics);
     else if (b < a.first[2]) tc_reduce_cols_body(b - a.first[1], a.colb3, a.blocks_done, (size_t)a.ncol3, a.ncol3, a.b3a, a.split3, a.b3c);
-    else if (b < a.first[3]) tc_reduce_cols_body(b - a.first[2], a.cpa, a.rows_a, (size_t)2 * a.HA, 2 * a.HA, a.b2a, a.HA, a.b1a);
-    else if (b < a.first[4]) tc_reduce_cols_body(b - a.first[3], a.cpc, a.rows_c, (size_t)2 * a.HC, 2 * a.HC, a.b2c, a.HC, a.b1c);
+    else if (b < a.first[3]) {
+        if (a.wide) tc_reduce_cols_wide_body(b - a.first[2], a.cpa, a.rows_a, (size_t)2 * a.HA, 2 * a.HA, a.b2a, a.HA, a.b1a);
+        else tc_reduce_cols_body(b - a.first[2], a.cpa, a.rows_a, (size_t)2 * a.HA, 2 * a.HA, a.b2a, a.HA, a.b1a);
+    } else if (b < a.first[4]) {
+        if (a.wide) tc_reduce_cols_wide_body(b - a.first[3], a.cpc, a.rows_c, (size_t)2 * a.HC, 2 * a.HC, a.b2c, a.HC, a.b1c);
+        else tc_reduce_cols_body(b - a.first[3], a.cpc, a.rows_c, (size_t)2 * a.HC, 2 * a.HC, a.b2c, a.HC, a.b1c);
+    }
     else if (b < a.first[5]) time_backward_body(b - a.first[4], a.first[5] - a.first[4], tail_sm, a.tb_staged != 0, a.w, a.ao, a.A, a.td, a.HA, a.T,
                                                 a.Gt, a.sinemb, a.thpre, a.temb, a.gr);
     else if (b < a.first[6]) unpack_dw0_body(b - a.first[5], a.dw0a, a.A, a.td, a.Do, a.HA, a.gwin_a);
@@ -1190,7 +1220,10 @@ static int tc_launch_tail(dppo_handle* h, cudaStream_t s, const double* bsum, in
     if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(tc_ppo_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr_set = true; }
     TcTailArgs a;
     const int nthr = 512, wpb = nthr / 32;
-    const int nb[8] = {1, tc_nblk(g.A + 1, wpb), tc_nblk(2 * g.H, wpb), tc_nblk(2 * g.Hc, wpb), 1 + (g.H + 127) / 128,
+    const bool wide = rows_a >= 256;         // many partial rows (plane GEMM epilogues): the coalesced 32-columns-per-block reduction
+    const int cpb = wide ? 32 : wpb;
+    a.wide = wide ? 1 : 0;
+    const int nb[8] = {1, tc_nblk(g.A + 1, wpb), tc_nblk(2 * g.H, cpb), tc_nblk(2 * g.Hc, cpb), 1 + (g.H + 127) / 128,
                        tc_nblk((size_t)(g.A + g.Do) * g.H, nthr), tc_nblk((size_t)g.Do * g.Hc, nthr), tc_nblk(g.Hc, nthr)};
     a.first[0] = 0;
     for (int r = 0; r < 8; ++r) a.first[r + 1] = a.first[r] + nb[r];

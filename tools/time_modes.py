@@ -11,14 +11,20 @@ from diffusionpolicyoptimization_b200 import _lib as L
 MODES = {"fp32": L.PREC_FP32, "bf16": L.PREC_BF16, "bf16x3": L.PREC_BF16X3}
 
 
-def timeit(fn, iters=10, warm=3):
+def timeit(fn, iters=10, warm=3, blocks=7):
+    """median over `blocks` timed blocks of `iters` calls (the min is printed too: clocks move under the power cap)"""
     for _ in range(warm): fn()
     torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(iters): fn()
-    b.record(); torch.cuda.synchronize()
-    return a.elapsed_time(b) / iters
+    ts = []
+    for _ in range(blocks):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters): fn()
+        b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b) / iters)
+    ts.sort()
+    timeit.last_min = ts[0]
+    return ts[len(ts) // 2]
 
 
 modes = (sys.argv[1] if len(sys.argv) > 1 else "bf16x3").split(",")
@@ -30,7 +36,7 @@ for i in (0, 1, 2, 7): args[i] = args[i].reshape(N, -1).contiguous()
 for mode in modes:
     e = make_engine(o, precision=MODES[mode])
     ms = timeit(lambda: e.ppo_step(*args, lr=1e-4, apply=True))
-    print(f"[{mode}] ppo N={N}: {ms:.3f} ms  {N/ms*1e3/1e6:.2f} M samples/s  ({4.141568e6*N/ms/1e9:.1f} algorithmic TFLOP/s)", flush=True)
+    print(f"[{mode}] ppo N={N}: {ms:.3f} ms  {N/ms*1e3/1e6:.2f} M samples/s  ({4.141568e6*N/ms/1e9:.1f} algorithmic TFLOP/s)  [min {timeit.last_min:.3f} ms]", flush=True)
     e.profile_enable(True)
     l0 = e.launch_count()
     for _ in range(5): e.ppo_step(*args, lr=1e-4, apply=True)
