@@ -216,16 +216,18 @@ __device__ __forceinline__ void tc_reduce_cols_wide_body(const int bid, const fl
                                                          float* __restrict__ out, int split, float* __restrict__ out2) {
     __shared__ float red[16][33];
     const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5, c = bid * 32 + lane;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    float sacc[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) sacc[q] = 0.f;
     if (c < ncols) {
         int b = rg;
-        for (; b + 48 < nb; b += 64) {
-            s0 += part[(size_t)b * stride + c]; s1 += part[(size_t)(b + 16) * stride + c];
-            s2 += part[(size_t)(b + 32) * stride + c]; s3 += part[(size_t)(b + 48) * stride + c];
+        for (; b + 112 < nb; b += 128) {          // eight independent loads in flight per thread
+#pragma unroll
+            for (int q = 0; q < 8; ++q) sacc[q] += part[(size_t)(b + 16 * q) * stride + c];
         }
-        for (; b < nb; b += 16) s0 += part[(size_t)b * stride + c];
+        for (; b < nb; b += 16) sacc[0] += part[(size_t)b * stride + c];
     }
-    red[rg][lane] = (s0 + s1) + (s2 + s3);
+    red[rg][lane] = ((sacc[0] + sacc[1]) + (sacc[2] + sacc[3])) + ((sacc[4] + sacc[5]) + (sacc[6] + sacc[7]));
     __syncthreads();
     if (rg == 0 && c < ncols) {
         float s = 0.f;
@@ -247,7 +249,7 @@ struct TcTailArgs {
     // metrics
     const double* bsum; int blocks_done; float inv_nglobal, frac_local; float* metrics;
     // column reductions (wide: the 32-columns-per-block body for many partial rows)
-    int wide;
+    int wide, wide3;
     const float* colb3; int ncol3; float* b3a; int split3; float* b3c;
     const float* cpa; int rows_a; int HA; float* b2a; float* b1a;
     const float* cpc; int rows_c; int HC; float* b2c; float* b1c;
@@ -260,7 +262,10 @@ __global__ void __launch_bounds__(512) tc_ppo_tail_kernel(const TcTailArgs a) {
     extern __shared__ float tail_sm[];
     const int b = blockIdx.x;
     if (b < a.first[1]) ppo_metrics_body(a.bsum, a.blocks_done, a.inv_nglobal, a.frac_local, a.metrics);
-    else if (b < a.first[2]) tc_reduce_cols_body(b - a.first[1], a.colb3, a.blocks_done, (size_t)a.ncol3, a.ncol3, a.b3a, a.split3, a.b3c);
+    else if (b < a.first[2]) {
+        if (a.wide3) tc_reduce_cols_wide_body(b - a.first[1], a.colb3, a.blocks_done, (size_t)a.ncol3, a.ncol3, a.b3a, a.split3, a.b3c);
+        else tc_reduce_cols_body(b - a.first[1], a.colb3, a.blocks_done, (size_t)a.ncol3, a.ncol3, a.b3a, a.split3, a.b3c);
+    }
     else if (b < a.first[3]) {
         if (a.wide) tc_reduce_cols_wide_body(b - a.first[2], a.cpa, a.rows_a, (size_t)2 * a.HA, 2 * a.HA, a.b2a, a.HA, a.b1a);
         else tc_reduce_cols_body(b - a.first[2], a.cpa, a.rows_a, (size_t)2 * a.HA, 2 * a.HA, a.b2a, a.HA, a.b1a);
@@ -1222,8 +1227,9 @@ static int tc_launch_tail(dppo_handle* h, cudaStream_t s, const double* bsum, in
     const int nthr = 512, wpb = nthr / 32;
     const bool wide = rows_a >= 256;         // many partial rows (plane GEMM epilogues): the coalesced 32-columns-per-block reduction
     const int cpb = wide ? 32 : wpb;
-    a.wide = wide ? 1 : 0;
-    const int nb[8] = {1, tc_nblk(g.A + 1, wpb), tc_nblk(2 * g.H, cpb), tc_nblk(2 * g.Hc, cpb), 1 + (g.H + 127) / 128,
+    const bool wide3 = blocks_done >= 256;
+    a.wide = wide ? 1 : 0; a.wide3 = wide3 ? 1 : 0;
+    const int nb[8] = {1, tc_nblk(g.A + 1, wide3 ? 32 : wpb), tc_nblk(2 * g.H, cpb), tc_nblk(2 * g.Hc, cpb), 1 + (g.H + 127) / 128,
                        tc_nblk((size_t)(g.A + g.Do) * g.H, nthr), tc_nblk((size_t)g.Do * g.Hc, nthr), tc_nblk(g.Hc, nthr)};
     a.first[0] = 0;
     for (int r = 0; r < 8; ++r) a.first[r + 1] = a.first[r] + nb[r];
