@@ -129,6 +129,10 @@ struct ActorDerived {
     float* temb;    // [T][td]
     float* bt;      // [T][H]   = b_in + temb(t) @ W_in[A:A+td]
     float* w0p;     // [KP][H]  = rows of W_in for [x | obs], zero padded
+    // no activation sits between block.l2 and the output layer: eps = (a1 W2 + b2 + u) W3 + b3 = a1 (W2 W3) + u W3 + (b2 W3 + b3).
+    // Forward-only programs (the samplers, the log-prob forward) use the folded operands and skip the H x H product.
+    float* w23;     // [H][A]   = W2 @ W3   (double accumulation, rounded once)
+    float* b23;     // [A]      = b2 @ W3 + b3
 };
 
 struct OptState { float* m; float* v; int64_t step; size_t n; };
@@ -167,6 +171,7 @@ struct dppo_handle {
     int64_t launches = 0;
     int64_t tc_launches = 0;
     int w0p_dirty[4] = {1, 1, 1, 1};  // ActorDerived::w0p is stale (rebuilt on demand by the FFMA layer-0 GEMM)
+    int w23_dirty[4] = {1, 1, 1, 1};     // folded output-layer tables (ActorDerived::w23 / b23) need a rebuild
     int chain_cg = 2;                 // fused chain kernel: 2 = CTA pairs (tcgen05 cta_group::2), 1 = single CTAs (DPPO_CHAIN_CG=1)
     int peer_two_shot = -1;           // DPPO_PEER_TWO_SHOT=0/1 (default: two-shot from 4 ranks)
     float* peer_gsum[8] = {nullptr};

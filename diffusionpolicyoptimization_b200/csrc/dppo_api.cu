@@ -225,9 +225,19 @@ static int ensure_w0p(dppo_handle* h, int net, cudaStream_t s) {
     h->w0p_dirty[net] = 0;
     return 0;
 }
+// the folded output layer (W2 W3, b2 W3 + b3) is rebuilt lazily too: only forward-only programs read it, updates come in runs
+static int ensure_w23(dppo_handle* h, int net, cudaStream_t s) {
+    const Geom& g = h->g;
+    if (!h->w23_dirty[net] || net == DPPO_NET_CRITIC) return 0;
+    const float* w = h->net_w[net]; ActorDerived& d = h->ad[net];
+    fold_output_kernel<<<nblk((size_t)(g.H + 1) * g.A, 128), 128, 0, s>>>(w + g.ao.w2, w + g.ao.b2, w + g.ao.w3, w + g.ao.b3, g.H, g.A, d.w23, d.b23);
+    KLAUNCH(h); KCHECK();
+    h->w23_dirty[net] = 0;
+    return 0;
+}
 static int prep_net(dppo_handle* h, int net, cudaStream_t s) {
     const Geom& g = h->g;
-    h->w0p_dirty[net] = 1;
+    h->w0p_dirty[net] = 1; h->w23_dirty[net] = 1;
     if (net != DPPO_NET_CRITIC) {
         ActorDerived& d = h->ad[net];
         int threads = g.H < 64 ? 64 : (g.H > 512 ? 512 : round_up(g.H, 32));
@@ -284,6 +294,7 @@ static int dppo_create_impl(const dppo_cfg* cfg, int device, dppo_handle** out, 
         CUDA_TRY(cudaMalloc(&d.thpre, (size_t)g.T * 2 * g.td * sizeof(float)));
         CUDA_TRY(cudaMalloc(&d.temb, (size_t)g.T * g.td * sizeof(float)));
         CUDA_TRY(cudaMalloc(&d.bt, (size_t)g.T * g.H * sizeof(float)));
+        CUDA_TRY(cudaMalloc(&d.w23, (size_t)g.H * g.A * sizeof(float))); CUDA_TRY(cudaMalloc(&d.b23, (size_t)g.A * sizeof(float)));
         CUDA_TRY(cudaMalloc(&d.w0p, (size_t)g.KP * g.H * sizeof(float)));
     }
     DPPO_TRY(dppo_ddpm_schedule(g.T, h->sched_host));
@@ -328,7 +339,7 @@ extern "C" void dppo_destroy(dppo_handle* h) {
     cudaFree(h->env_norm);
     cudaFree(h->params); cudaFree(h->sched); cudaFree(h->grads_buf[0]); cudaFree(h->grads_buf[1]); /* gsum lives inside grads_buf[1] */ cudaFree(h->flags); cudaFree(h->scalars);
     for (int i = 0; i < 2; ++i) { cudaFree(h->opt[i].m); cudaFree(h->opt[i].v); }
-    for (int net = 0; net < 4; ++net) { ActorDerived& d = h->ad[net]; cudaFree(d.sinemb); cudaFree(d.thpre); cudaFree(d.temb); cudaFree(d.bt); cudaFree(d.w0p); }
+    for (int net = 0; net < 4; ++net) { ActorDerived& d = h->ad[net]; cudaFree(d.sinemb); cudaFree(d.thpre); cudaFree(d.temb); cudaFree(d.bt); cudaFree(d.w0p); cudaFree(d.w23); cudaFree(d.b23); }
     if (h->ws.base) cudaFree(h->ws.base);
     if (h->copy_stream) { cudaStreamDestroy(h->copy_stream); for (int i = 0; i < 9; ++i) cudaEventDestroy(h->copy_ev[i]); }
     if (h->aux_stream) { cudaStreamDestroy(h->aux_stream); for (int i = 0; i < 2; ++i) cudaEventDestroy(h->aux_ev[i]); }
@@ -777,6 +788,9 @@ static int sample_impl(dppo_handle* h, const float* obs, int B, int deterministi
         ClusterSampleP p; memset(&p, 0, sizeof(p));
         p.w[0] = h->net_w[DPPO_NET_ACTOR]; p.w[1] = h->net_w[DPPO_NET_ACTOR_FT];
         p.bt[0] = h->ad[DPPO_NET_ACTOR].bt; p.bt[1] = h->ad[DPPO_NET_ACTOR_FT].bt;
+        DPPO_TRY(ensure_w23(h, DPPO_NET_ACTOR, s)); DPPO_TRY(ensure_w23(h, DPPO_NET_ACTOR_FT, s));
+        p.w23[0] = h->ad[DPPO_NET_ACTOR].w23; p.w23[1] = h->ad[DPPO_NET_ACTOR_FT].w23;
+        p.b23[0] = h->ad[DPPO_NET_ACTOR].b23; p.b23[1] = h->ad[DPPO_NET_ACTOR_FT].b23;
         p.o = g.ao; p.obs = obs; p.xT = xT; p.noise = noise; p.actions = actions; p.chains = chains; p.sch = h->sched;
         p.B = B; p.A = g.A; p.Do = g.Do; p.T = g.T; p.K = g.K; p.td = g.td; p.use_base_policy = use_base_policy;
         p.hp = hp; p.seed = seed; p.offset = offset; p.row_offset = row_offset;

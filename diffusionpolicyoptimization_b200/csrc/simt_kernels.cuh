@@ -273,6 +273,18 @@ __global__ void actor_prep_kernel(const float* __restrict__ w, ActorOff o, int A
     extern __shared__ float sm[];
     actor_prep_body(blockIdx.x, sm, w, o, A, td, H, sinemb, thpre, temb, bt, nullptr);
 }
+// w23[k][a] = sum_j W2[k][j] W3[j][a] (k < H), b23[a] = b3[a] + sum_j b2[j] W3[j][a] (the thread row k == H): products of the folded output
+// layer (MLP / ResidualMLP of model/common/mlp.py: the last Dense follows the residual add without an activation)
+__global__ void fold_output_kernel(const float* __restrict__ w2, const float* __restrict__ b2, const float* __restrict__ w3, const float* __restrict__ b3,
+                                   int H, int A, float* __restrict__ w23, float* __restrict__ b23) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (H + 1) * A) return;
+    const int k = i / A, a = i % A;
+    const float* row = k < H ? w2 + (size_t)k * H : b2;
+    double acc = k < H ? 0.0 : (double)b3[a];
+    for (int j = 0; j < H; ++j) acc += (double)row[j] * (double)w3[(size_t)j * A + a];
+    if (k < H) w23[(size_t)k * A + a] = (float)acc; else b23[a] = (float)acc;
+}
 // w0p[k][c]: k < A -> W_in[k], A <= k < A+Do -> W_in[k+td], else 0.   (skip = td for actor, 0 for critic with A=0)
 __global__ void pack_w0_kernel(const float* __restrict__ win, int A, int skip, int Do, int KP, int H,
                                float* __restrict__ w0p) {

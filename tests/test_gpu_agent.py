@@ -113,6 +113,7 @@ def test_rollout_step_is_two_launches_on_the_cluster_path():
     raw_obs = torch.from_numpy(rng.uniform(-2, 3, (B, 11))).pin_memory()
     raw_act = torch.zeros(B, act_steps * 3).pin_memory()
     obs_out = torch.zeros(B, 11, device="cuda"); act = torch.zeros(B, 12, device="cuda"); ch = torch.zeros(B, 11, 12, device="cuda")
+    e.rollout_step(raw_obs, obs_out, act, ch, raw_act, act_steps, seed=5, offset=9)     # first call after new weights: + the two folded-output-layer tables
     n0 = e.launch_count()
     e.rollout_step(raw_obs, obs_out, act, ch, raw_act, act_steps, seed=5, offset=9)
     torch.cuda.synchronize()
