@@ -225,16 +225,6 @@ static int ensure_w0p(dppo_handle* h, int net, cudaStream_t s) {
     h->w0p_dirty[net] = 0;
     return 0;
 }
-// the folded output layer (W2 W3, b2 W3 + b3) is rebuilt lazily too: only forward-only programs read it, updates come in runs
-static int ensure_w23(dppo_handle* h, int net, cudaStream_t s) {
-    const Geom& g = h->g;
-    if (!h->w23_dirty[net] || net == DPPO_NET_CRITIC) return 0;
-    const float* w = h->net_w[net]; ActorDerived& d = h->ad[net];
-    fold_output_kernel<<<nblk((size_t)(g.H + 1) * g.A, 128), 128, 0, s>>>(w + g.ao.w2, w + g.ao.b2, w + g.ao.w3, w + g.ao.b3, g.H, g.A, d.w23, d.b23);
-    KLAUNCH(h); KCHECK();
-    h->w23_dirty[net] = 0;
-    return 0;
-}
 static int prep_net(dppo_handle* h, int net, cudaStream_t s) {
     const Geom& g = h->g;
     h->w0p_dirty[net] = 1; h->w23_dirty[net] = 1;
@@ -698,7 +688,7 @@ static int sample_layered_fp32(dppo_handle* h, cudaStream_t s, const float* obs,
     for (int i = 0; i < g.T; ++i) {
         const int t = g.T - 1 - i;
         const int net = (t < g.K && !use_base) ? DPPO_NET_ACTOR_FT : DPPO_NET_ACTOR;
-        if (split) DPPO_TRY(ts_actor_forward(h, s, net, x, obs, 1, B, nullptr, t, b.out));
+        if (split) DPPO_TRY(ts_actor_forward(h, s, net, x, obs, 1, B, nullptr, t, b.out, 0, true));
         else if (tensor) DPPO_TRY(tc_actor_forward(h, s, net, x, obs, 1, B, nullptr, t, b.out));
         else DPPO_TRY(actor_fwd_fp32(h, s, net, x, obs, 1, B, nullptr, t, b));
         sample_update_kernel<<<nblk((size_t)B * g.A, 256), 256, 0, s>>>(x, b.out, noise, B, g.A, t, i, h->sched, g.T, hp,

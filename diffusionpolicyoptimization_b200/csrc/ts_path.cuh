@@ -1059,10 +1059,12 @@ struct TsW { bf16* p[ts::MAXP]; };
 struct TsNetW {
     TsW w2w0, w1, w3t, w3p;
     TsW fw2w0, fw1, fw3t;                 // fp16 planes, scaled by ts::F16_WSCALE
+    TsW ffold;                            // actors: [64][H + KP0] fp16 planes of 2^10 [W2 W3 ; W0 W3]^T - the folded output layer of the
+                                          // forward-only programs: eps = [a1 | h0] [W2 W3 ; W0 W3] + (b2 W3 + b3)
     float* bias2;                         // critic: b2 + b_in (the residual's input-layer bias rides with block.l2's)
     int H;
 };
-struct TsState { TsNetW net[4]; int KP0; };
+struct TsState { TsNetW net[4]; int KP0; int fold_dirty[4]; };
 
 __device__ __forceinline__ void ts_put(const TsW& W, size_t i, float v) {
     bf16 a, b; ts::split_bf16(v, a, b);
@@ -1182,6 +1184,42 @@ __global__ void __launch_bounds__(256) ts_colsum_kernel(const bf16* __restrict__
     }
 }
 
+// the folded output layer (W2 W3, b2 W3 + b3; ActorDerived::w23 / b23) is rebuilt lazily: only forward-only programs read it, updates come in runs
+static int ensure_w23(dppo_handle* h, int net, cudaStream_t s) {
+    const Geom& g = h->g;
+    if (!h->w23_dirty[net] || net == DPPO_NET_CRITIC) return 0;
+    const float* w = h->net_w[net]; ActorDerived& d = h->ad[net];
+    fold_output_kernel<<<tc_nblk((size_t)(g.H + 1) * g.A, 128), 128, 0, s>>>(w + g.ao.w2, w + g.ao.b2, w + g.ao.w3, w + g.ao.b3, g.H, g.A, d.w23, d.b23);
+    TC_KCHECK(h);
+    h->w23_dirty[net] = 0;
+    return 0;
+}
+// ffold[a][k]: k < H -> (W2 W3)[k][a]; H <= k < H + KP0 -> (W0 W3)[k - H][a] with W0 = the h0-order rows [x | obs | bt[t] | 0..] of layer 0
+// (its bias rides in the bt rows), as fp16 planes of 2^10 x; rows a >= A are zero.  One thread per element, double accumulation.
+__global__ void ts_pack_fold_kernel(const float* __restrict__ w, ActorOff o, int A, int td, int Do, int T, int H, int KP0,
+                                    const float* __restrict__ bt, const float* __restrict__ w23, const TsW F) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int ld = H + KP0;
+    if (i >= (size_t)64 * ld) return;
+    const int a = (int)(i / ld), k = (int)(i % ld);
+    float v = 0.f;
+    if (a < A) {
+        if (k < H) v = w23[(size_t)k * A + a];
+        else {
+            const int k0 = k - H;
+            const float* row = nullptr;
+            if (k0 < A) row = w + o.win + (size_t)k0 * H;
+            else if (k0 < A + Do) row = w + o.win + (size_t)(k0 + td) * H;
+            else if (k0 < A + Do + T) row = bt + (size_t)(k0 - A - Do) * H;
+            if (row) {
+                double acc = 0.0;
+                for (int j = 0; j < H; ++j) acc += (double)row[j] * (double)w[o.w3 + (size_t)j * A + a];
+                v = (float)acc;
+            }
+        }
+    }
+    ts_put_f16(F, i, v);
+}
 static const int TS_MIN_ROWS = 2048;
 static bool ts_shapes_ok(const dppo_handle* h) { return h->ts && h->ts->net[0].w1.p[0] != nullptr; }
 static bool ts_eligible(const dppo_handle* h, int rows) {
@@ -1207,19 +1245,22 @@ static int ts_init(dppo_handle* h) {
         DPPO_TRY(ts_alloc_w(w.w2w0, (H + st->KP0) * H)); DPPO_TRY(ts_alloc_w(w.w1, H * H));
         DPPO_TRY(ts_alloc_w(w.w3t, 64 * H)); DPPO_TRY(ts_alloc_w(w.w3p, H * 128));
         DPPO_TRY(ts_alloc_w(w.fw2w0, (H + st->KP0) * H)); DPPO_TRY(ts_alloc_w(w.fw1, H * H)); DPPO_TRY(ts_alloc_w(w.fw3t, 64 * H));
+        if (net != DPPO_NET_CRITIC) DPPO_TRY(ts_alloc_w(w.ffold, 64 * (H + st->KP0)));
+        st->fold_dirty[net] = 1;
         CUDA_TRY(cudaMalloc(&w.bias2, H * sizeof(float)));
     }
     return 0;
 }
 static void ts_destroy(dppo_handle* h) {
     if (!h->ts) return;
-    for (int net = 0; net < 4; ++net) { TsNetW& w = h->ts->net[net]; cudaFree(w.w2w0.p[0]); cudaFree(w.w1.p[0]); cudaFree(w.w3t.p[0]); cudaFree(w.w3p.p[0]); cudaFree(w.fw2w0.p[0]); cudaFree(w.fw1.p[0]); cudaFree(w.fw3t.p[0]); cudaFree(w.bias2); }
+    for (int net = 0; net < 4; ++net) { TsNetW& w = h->ts->net[net]; cudaFree(w.w2w0.p[0]); cudaFree(w.w1.p[0]); cudaFree(w.w3t.p[0]); cudaFree(w.w3p.p[0]); cudaFree(w.fw2w0.p[0]); cudaFree(w.fw1.p[0]); cudaFree(w.fw3t.p[0]); cudaFree(w.ffold.p[0]); cudaFree(w.bias2); }
     delete h->ts; h->ts = nullptr;
 }
 // rebuild the plane copies of one net (after set_weights / an optimizer step; the actor's bt table must be current)
 static int ts_refresh_net(dppo_handle* h, int net, cudaStream_t s) {
     if (h->cfg.precision != DPPO_PREC_BF16X3 || !ts_shapes_ok(h)) return 0;
     const Geom& g = h->g; const TsNetW& w = h->ts->net[net];
+    h->ts->fold_dirty[net] = 1;
     if (net == DPPO_NET_CRITIC) ts_pack_critic_kernel<<<128, 256, 0, s>>>(h->net_w[net], g.co, g.A, g.Do, g.Hc, h->ts->KP0, w);
     else ts_pack_actor_kernel<<<256, 256, 0, s>>>(h->net_w[net], g.ao, g.A, g.td, g.Do, g.T, g.H, h->ts->KP0, h->ad[net].bt, w);
     TC_KCHECK(h);
@@ -1234,6 +1275,8 @@ struct TsMlp {
     const float *b0, *b1, *b2, *b3;
     SplitT h0, a0, a1, v, g0, g1, dv, dh1, du;   // g0 / g1: Mish gates mish'(pre-activation) of layer 0 / block.l1 (two planes)
     SplitT h0b, a0b, a1b, vb;              // fp = 4 with a backward pass: bf16 copies (two planes) for the weight-gradient GEMMs
+    int fold;                              // forward-only actor: eps = [a1 | h0] [W2 W3 ; W0 W3] + (b2 W3 + b3), block.l2's product is skipped
+    const float* bfold;                    // b2 W3 + b3
     uint32_t *m0, *m1;                     // ReLU bit masks [N][H/32] of layer 0 / block.l1
     float* out;                            // [N][NO] fp32
 };
@@ -1313,6 +1356,16 @@ static int ts_mlp_forward(dppo_handle* h, cudaStream_t s, const TsMlp& m, int N)
     if (m.a1b.p[0]) { g.out2[0] = m.a1b.p[0]; g.out2[1] = m.a1b.p[1]; g.epi.out2 = 1; }
     if (m.act1 == 1) { g.epi.mask_out = m.m1; g.epi.ldm = H / 32; } else if (m.act1 == 2) { g.epi.gate_out = 1; g.gate[0] = m.g1.p[0]; g.gate[1] = m.g1.p[1]; }
     DPPO_TRY(tsp::launch(h, s, g));
+    if (m.fold) {
+        // no activation between block.l2 and the output layer: out = [a1 | h0] [W2 W3 ; W0 W3] + (b2 W3 + b3), one narrow GEMM
+        ts::Gemm o = ts_gemm_of(tsK(m.a1, N, H, H), tswK(W.ffold, 0, 32, H, H + KP0), N, m.NO, 2, 1);
+        o.A2 = tsK(m.h0, N, KP0, KP0); o.B2 = tswK(W.ffold, (size_t)H, 32, KP0, H + KP0);
+        o.f16 = 1; o.epi.scale = 1.0f / ts::F16_WSCALE;
+        o.epi.bias = m.bfold; o.epi.out_f32 = m.out; o.epi.ld_f32 = m.NO;
+        o.alg_flops = 2.0 * N * ((double)H * H + (double)H * m.NO);        // the algorithmic work it stands for
+        DPPO_TRY(ts_run(h, s, o));
+        return 0;
+    }
     // L2 + residual: v = [a1 | h0] [W2 ; W0] + b2 (+ b0): the residual u = h0 W0 is re-accumulated instead of stored and re-read
     g = tsp_gemm_of(tsK(m.a1, N, H, H), tswMN(Ww2w0, 0, H, H, H), N, H, P, m.v, P, H);
     g.A2 = tsK(m.h0, N, KP0, KP0); g.B2 = tswMN(Ww2w0, w0, H, KP0, H);
@@ -1384,10 +1437,12 @@ static size_t ts_part_floats(const dppo_handle* h, int H) {
     return a > b ? a : b;
 }
 // ------------------------------------------------------------------ forward-only programs
+// DPPO_NO_FOLD=1: forward-only programs evaluate block.l2 and the output layer as two products, like the training forward
+static inline bool ts_no_fold() { static int v = -1; if (v < 0) { const char* e = getenv("DPPO_NO_FOLD"); v = (e && atoi(e)) ? 1 : 0; } return v != 0; }
 static size_t ts_actor_forward_ws(const dppo_handle* h, int N) { return ts_mlp_ws_bytes(N, h->g.H, h->ts->KP0, h->cfg.actor_act == DPPO_ACT_MISH, false); }
 // eps[N][A] = actor(x, t, obs); appends to the workspace (the caller may hold pointers below ws.used)
 static int ts_actor_forward(dppo_handle* h, cudaStream_t s, int net, const float* x, const float* obs, int obs_div, int N,
-                            const int* trow, int tconst, float* eps, int chainK = 0) {
+                            const int* trow, int tconst, float* eps, int chainK = 0, bool fold_ok = false) {
     const Geom& g = h->g; const int KP0 = h->ts->KP0;
     const size_t need = h->ws.used + ts_actor_forward_ws(h, N);
     if (need > h->ws.cap) DPPO_FAIL(-7, "ts_actor_forward: workspace too small (%zu > %zu)", need, h->ws.cap);
@@ -1395,6 +1450,18 @@ static int ts_actor_forward(dppo_handle* h, cudaStream_t s, int net, const float
     TsMlp m; ts_actor_mlp(h, net, m);
     ts_mlp_take(h, N, m, false);
     m.out = eps;
+    // fold_ok: the samplers.  The log-prob forward keeps the training forward's arithmetic so that the PPO ratio of unchanged weights is
+    // exactly 1 (old log-probs from dppo_logprobs, new ones inside dppo_ppo_step: tests/test_gpu_fullsize_oracle.py)
+    if (fold_ok && m.fp == 4 && !ts_no_fold()) {
+        if (h->ts->fold_dirty[net]) {
+            DPPO_TRY(ensure_w23(h, net, s));
+            ts_pack_fold_kernel<<<tc_nblk((size_t)64 * (g.H + KP0), 128), 128, 0, s>>>(h->net_w[net], g.ao, g.A, g.td, g.Do, g.T, g.H, KP0, h->ad[net].bt,
+                                                                                      h->ad[net].w23, h->ts->net[net].ffold);
+            TC_KCHECK(h);
+            h->ts->fold_dirty[net] = 0;
+        }
+        m.fold = 1; m.bfold = h->ad[net].b23;
+    }
     ts_pack_h0_kernel<<<tc_nblk((size_t)N * (KP0 / 8), 256), 256, 0, s>>>(x, obs, trow, tconst, N, g.A, g.Do, g.T, KP0, obs_div, m.h0, split_null(), chainK);
     TC_KCHECK(h);
     const int r = ts_mlp_forward(h, s, m, N);
