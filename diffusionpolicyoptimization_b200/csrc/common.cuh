@@ -176,7 +176,7 @@ struct dppo_handle {
     int peer_two_shot = -1;           // DPPO_PEER_TWO_SHOT=0/1 (default: two-shot from 4 ranks)
     float* peer_gsum[8] = {nullptr};
     int overlap_chains = 1;           // DPPO_OVERLAP_CHAINS=0: actor and critic chains back to back on one stream
-    cudaStream_t aux_stream = nullptr; cudaEvent_t aux_ev[2] = {nullptr, nullptr};
+    cudaStream_t aux_stream = nullptr; cudaEvent_t aux_ev[3] = {nullptr, nullptr, nullptr};
     int dw_pair = 1;                  // DPPO_DW_PAIR=0: weight-gradient GEMM on single CTAs instead of CTA pairs
     float grad_clip_norm = 0.f;       // dppo_set_grad_clip_norm: per-variable tf.clip_by_norm before AdamW (<= 0: off)
     int deterministic = 0;            // DPPO_DETERMINISTIC=1: fixed-order split-K reductions instead of red.global.add

@@ -332,7 +332,7 @@ extern "C" void dppo_destroy(dppo_handle* h) {
     for (int net = 0; net < 4; ++net) { ActorDerived& d = h->ad[net]; cudaFree(d.sinemb); cudaFree(d.thpre); cudaFree(d.temb); cudaFree(d.bt); cudaFree(d.w0p); cudaFree(d.w23); cudaFree(d.b23); }
     if (h->ws.base) cudaFree(h->ws.base);
     if (h->copy_stream) { cudaStreamDestroy(h->copy_stream); for (int i = 0; i < 9; ++i) cudaEventDestroy(h->copy_ev[i]); }
-    if (h->aux_stream) { cudaStreamDestroy(h->aux_stream); for (int i = 0; i < 2; ++i) cudaEventDestroy(h->aux_ev[i]); }
+    if (h->aux_stream) { cudaStreamDestroy(h->aux_stream); for (int i = 0; i < 3; ++i) if (h->aux_ev[i]) cudaEventDestroy(h->aux_ev[i]); }
     if (h->pin) cudaFreeHost(h->pin);
     if (h->dstage) cudaFree(h->dstage);
     delete h;
@@ -688,7 +688,7 @@ static int sample_layered_fp32(dppo_handle* h, cudaStream_t s, const float* obs,
     for (int i = 0; i < g.T; ++i) {
         const int t = g.T - 1 - i;
         const int net = (t < g.K && !use_base) ? DPPO_NET_ACTOR_FT : DPPO_NET_ACTOR;
-        if (split) DPPO_TRY(ts_actor_forward(h, s, net, x, obs, 1, B, nullptr, t, b.out, 0, true));
+        if (split) DPPO_TRY(ts_actor_forward(h, s, net, x, obs, 1, B, nullptr, t, b.out));
         else if (tensor) DPPO_TRY(tc_actor_forward(h, s, net, x, obs, 1, B, nullptr, t, b.out));
         else DPPO_TRY(actor_fwd_fp32(h, s, net, x, obs, 1, B, nullptr, t, b));
         sample_update_kernel<<<nblk((size_t)B * g.A, 256), 256, 0, s>>>(x, b.out, noise, B, g.A, t, i, h->sched, g.T, hp,

@@ -1059,12 +1059,13 @@ struct TsW { bf16* p[ts::MAXP]; };
 struct TsNetW {
     TsW w2w0, w1, w3t, w3p;
     TsW fw2w0, fw1, fw3t;                 // fp16 planes, scaled by ts::F16_WSCALE
-    TsW ffold;                            // actors: [64][H + KP0] fp16 planes of 2^10 [W2 W3 ; W0 W3]^T - the folded output layer of the
-                                          // forward-only programs: eps = [a1 | h0] [W2 W3 ; W0 W3] + (b2 W3 + b3)
+    TsW ffold;                            // [64][H + KP0] planes of [W2 W3 ; W0 W3]^T (fp16 x 2^10 when the net's forward runs on fp16 planes, else
+                                          // bf16): the folded output layer, out = [a1 | h0] [W2 W3 ; W0 W3] + bfold
+    float* bfold;                         // [64]  (b2 (+ b_in)) W3 + b3
     float* bias2;                         // critic: b2 + b_in (the residual's input-layer bias rides with block.l2's)
     int H;
 };
-struct TsState { TsNetW net[4]; int KP0; int fold_dirty[4]; };
+struct TsState { TsNetW net[4]; int KP0; int fold_dirty[4]; char* dw3_buf; size_t dw3_bytes; };
 
 __device__ __forceinline__ void ts_put(const TsW& W, size_t i, float v) {
     bf16 a, b; ts::split_bf16(v, a, b);
@@ -1194,31 +1195,78 @@ static int ensure_w23(dppo_handle* h, int net, cudaStream_t s) {
     h->w23_dirty[net] = 0;
     return 0;
 }
-// ffold[a][k]: k < H -> (W2 W3)[k][a]; H <= k < H + KP0 -> (W0 W3)[k - H][a] with W0 = the h0-order rows [x | obs | bt[t] | 0..] of layer 0
-// (its bias rides in the bt rows), as fp16 planes of 2^10 x; rows a >= A are zero.  One thread per element, double accumulation.
-__global__ void ts_pack_fold_kernel(const float* __restrict__ w, ActorOff o, int A, int td, int Do, int T, int H, int KP0,
-                                    const float* __restrict__ bt, const float* __restrict__ w23, const TsW F) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int ld = H + KP0;
-    if (i >= (size_t)64 * ld) return;
-    const int a = (int)(i / ld), k = (int)(i % ld);
-    float v = 0.f;
-    if (a < A) {
-        if (k < H) v = w23[(size_t)k * A + a];
-        else {
-            const int k0 = k - H;
-            const float* row = nullptr;
-            if (k0 < A) row = w + o.win + (size_t)k0 * H;
-            else if (k0 < A + Do) row = w + o.win + (size_t)(k0 + td) * H;
-            else if (k0 < A + Do + T) row = bt + (size_t)(k0 - A - Do) * H;
-            if (row) {
-                double acc = 0.0;
-                for (int j = 0; j < H; ++j) acc += (double)row[j] * (double)w[o.w3 + (size_t)j * A + a];
-                v = (float)acc;
+// Folded output layer of one net.  No activation sits between block.l2 and the last Dense (model/common/mlp.py), so
+//   out = (a1 W2 + b2 + u) W3 + b3 = [a1 | h0] [W2 W3 ; W0 W3] + ((b2 + b0) W3 + b3),      u = h0 W0 + b0
+// with W0 = the h0-order rows of layer 0 ([x | obs | bt[t] | 0..]; the actor's b0 rides in the bt rows, the critic's is `b0`).
+// ffold[a][k] (a < 64, k < H + KP0) = that matrix transposed, as fp16 planes of 2^10 x (f16) or bf16 planes; bfold[a] the bias.
+// One thread per (k, a) and one for each bias entry; double accumulation, rounded once.
+struct TsFoldArgs {
+    const float *w2, *w3, *b2, *b3, *b0;      // [H][H], [H][NO], [H], [NO], [H] or null
+    const float *win; int x_rows, x_skip;     // layer-0 rows of h0 columns [0, A): win + k0 * H when k0 < x_rows (else zero)
+    int obs_skip;                             // rows of h0 columns [A, A + Do): win + (k0 - A + obs_skip) * H
+    const float* bt;                          // rows of h0 columns [A + Do, A + Do + T): bt + (k0 - A - Do) * H, or null
+    int A, Do, T, H, NO, KP0, f16;
+};
+// one warp per output row k (k == H + KP0: the bias row): the lanes split j (16 products each, fp32), W3 sits transposed and padded in
+// shared memory (conflict-free both ways), the lane partials meet in a butterfly.  (A first version accumulated in double: 30 us - the
+// CUDA-core fp64 rate of this part - for sums that are rounded to 22-bit planes anyway.)
+__global__ void __launch_bounds__(256) ts_fold_kernel(const TsFoldArgs f, const TsW F, float* __restrict__ bfold) {
+    extern __shared__ float w3t[];               // [NO][H + 1]
+    const int H = f.H, NO = f.NO, ld = f.H + f.KP0, HP = f.H + 1;
+    for (int i0 = threadIdx.x; i0 < H * NO; i0 += blockDim.x * 8) {        // eight loads in flight per thread (one per iteration: 29 us of latency)
+        float t8[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const int i = i0 + u * blockDim.x; t8[u] = i < H * NO ? __ldg(f.w3 + i) : 0.f; }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const int i = i0 + u * blockDim.x; if (i < H * NO) w3t[(size_t)(i % NO) * HP + i / NO] = t8[u]; }
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (k > ld) return;
+    const float* row = nullptr; bool bias_row = false;
+    if (k < H) row = f.w2 + (size_t)k * H;
+    else if (k < ld) {
+        const int k0 = k - H;
+        if (k0 < f.A) { if (k0 < f.x_rows) row = f.win + (size_t)(k0 + f.x_skip) * H; }
+        else if (k0 < f.A + f.Do) row = f.win + (size_t)(k0 - f.A + f.obs_skip) * H;
+        else if (k0 < f.A + f.Do + f.T) { if (f.bt) row = f.bt + (size_t)(k0 - f.A - f.Do) * H; }
+    } else { row = f.b2; bias_row = true; }
+    float rv[32];                                // the lane's row elements, all loads in flight at once
+#pragma unroll
+    for (int q = 0; q < 32; ++q) {
+        const int j = lane + 32 * q;
+        rv[q] = (row && j < H) ? row[j] : 0.f;
+        if (bias_row && f.b0 && j < H) rv[q] += f.b0[j];
+    }
+    for (int a0 = 0; a0 < 64; a0 += 8) {
+        float acc[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+        if (row && a0 < NO) {
+#pragma unroll
+            for (int qq = 0; qq < 32; ++qq) {
+                const int j = lane + 32 * qq;
+                if (j < H) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) if (a0 + q < NO) acc[q] = fmaf(rv[qq], w3t[(size_t)(a0 + q) * HP + j], acc[q]);
+                }
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], off);
             }
         }
+        if (lane < 8) {
+            const int a = a0 + lane;
+            float v = 0.f;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) if (q == lane) v = acc[q];
+            if (bias_row) bfold[a] = a < NO ? v + f.b3[a] : 0.f;
+            else if (f.f16) ts_put_f16(F, (size_t)a * ld + k, v);
+            else ts_put(F, (size_t)a * ld + k, v);
+        }
     }
-    ts_put_f16(F, i, v);
 }
 static const int TS_MIN_ROWS = 2048;
 static bool ts_shapes_ok(const dppo_handle* h) { return h->ts && h->ts->net[0].w1.p[0] != nullptr; }
@@ -1245,7 +1293,8 @@ static int ts_init(dppo_handle* h) {
         DPPO_TRY(ts_alloc_w(w.w2w0, (H + st->KP0) * H)); DPPO_TRY(ts_alloc_w(w.w1, H * H));
         DPPO_TRY(ts_alloc_w(w.w3t, 64 * H)); DPPO_TRY(ts_alloc_w(w.w3p, H * 128));
         DPPO_TRY(ts_alloc_w(w.fw2w0, (H + st->KP0) * H)); DPPO_TRY(ts_alloc_w(w.fw1, H * H)); DPPO_TRY(ts_alloc_w(w.fw3t, 64 * H));
-        if (net != DPPO_NET_CRITIC) DPPO_TRY(ts_alloc_w(w.ffold, 64 * (H + st->KP0)));
+        DPPO_TRY(ts_alloc_w(w.ffold, 64 * (H + st->KP0)));
+        CUDA_TRY(cudaMalloc(&w.bfold, 64 * sizeof(float)));
         st->fold_dirty[net] = 1;
         CUDA_TRY(cudaMalloc(&w.bias2, H * sizeof(float)));
     }
@@ -1253,7 +1302,8 @@ static int ts_init(dppo_handle* h) {
 }
 static void ts_destroy(dppo_handle* h) {
     if (!h->ts) return;
-    for (int net = 0; net < 4; ++net) { TsNetW& w = h->ts->net[net]; cudaFree(w.w2w0.p[0]); cudaFree(w.w1.p[0]); cudaFree(w.w3t.p[0]); cudaFree(w.w3p.p[0]); cudaFree(w.fw2w0.p[0]); cudaFree(w.fw1.p[0]); cudaFree(w.fw3t.p[0]); cudaFree(w.ffold.p[0]); cudaFree(w.bias2); }
+    cudaFree(h->ts->dw3_buf);
+    for (int net = 0; net < 4; ++net) { TsNetW& w = h->ts->net[net]; cudaFree(w.w2w0.p[0]); cudaFree(w.w1.p[0]); cudaFree(w.w3t.p[0]); cudaFree(w.w3p.p[0]); cudaFree(w.fw2w0.p[0]); cudaFree(w.fw1.p[0]); cudaFree(w.fw3t.p[0]); cudaFree(w.ffold.p[0]); cudaFree(w.bfold); cudaFree(w.bias2); }
     delete h->ts; h->ts = nullptr;
 }
 // rebuild the plane copies of one net (after set_weights / an optimizer step; the actor's bt table must be current)
@@ -1275,11 +1325,39 @@ struct TsMlp {
     const float *b0, *b1, *b2, *b3;
     SplitT h0, a0, a1, v, g0, g1, dv, dh1, du;   // g0 / g1: Mish gates mish'(pre-activation) of layer 0 / block.l1 (two planes)
     SplitT h0b, a0b, a1b, vb;              // fp = 4 with a backward pass: bf16 copies (two planes) for the weight-gradient GEMMs
-    int fold;                              // forward-only actor: eps = [a1 | h0] [W2 W3 ; W0 W3] + (b2 W3 + b3), block.l2's product is skipped
-    const float* bfold;                    // b2 W3 + b3
+    int fold;                              // out = [a1 | h0] [W2 W3 ; W0 W3] + bfold: block.l2's H x H product is skipped and v never formed (the
+                                           // caller has run ts_ensure_fold).  The weight gradient of the output layer is then assembled from
+                                           // a1^T dout and h0^T dout (ts_dw3_assemble_kernel).
+    cudaEvent_t fold_ev;                   // when set: the folded operands are being rebuilt on another stream; wait in front of the folded GEMM
     uint32_t *m0, *m1;                     // ReLU bit masks [N][H/32] of layer 0 / block.l1
     float* out;                            // [N][NO] fp32
 };
+// DPPO_NO_FOLD=1: block.l2 and the output layer as two products everywhere (the unfolded programs; A/B and debugging)
+static inline bool ts_no_fold() { static int v = -1; if (v < 0) { const char* e = getenv("DPPO_NO_FOLD"); v = (e && atoi(e)) ? 1 : 0; } return v != 0; }
+// rebuild the folded output layer of one net if its weights changed (lazily: set_weights / AdamW only mark it stale)
+static int ts_ensure_fold(dppo_handle* h, int net, cudaStream_t s) {
+    if (!h->ts->fold_dirty[net]) return 0;
+    const Geom& g = h->g; const TsNetW& W = h->ts->net[net]; const float* w = h->net_w[net];
+    TsFoldArgs f; memset(&f, 0, sizeof(f));
+    f.A = g.A; f.Do = g.Do; f.T = g.T; f.KP0 = h->ts->KP0;
+    if (net == DPPO_NET_CRITIC) {
+        f.H = g.Hc; f.NO = 1; f.w2 = w + g.co.w2; f.w3 = w + g.co.w3; f.b2 = w + g.co.b2; f.b3 = w + g.co.b3; f.b0 = w + g.co.bin;
+        f.win = w + g.co.win; f.x_rows = 0; f.obs_skip = 0; f.bt = nullptr;
+        f.f16 = h->cfg.critic_act == DPPO_ACT_RELU ? 1 : 0;
+    } else {
+        f.H = g.H; f.NO = g.A; f.w2 = w + g.ao.w2; f.w3 = w + g.ao.w3; f.b2 = w + g.ao.b2; f.b3 = w + g.ao.b3; f.b0 = nullptr;
+        f.win = w + g.ao.win; f.x_rows = g.A; f.x_skip = 0; f.obs_skip = g.A + g.td; f.bt = h->ad[net].bt;
+        f.f16 = 1;
+    }
+    static bool attr_set_dev[64] = {};
+    if (!attr_set_dev[h->device & 63]) { CUDA_TRY(cudaFuncSetAttribute(ts_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr_set_dev[h->device & 63] = true; }
+    const size_t sm = (size_t)(f.H + 1) * f.NO * sizeof(float);
+    if (sm > 96 * 1024 || f.H > 1024) DPPO_FAIL(-7, "ts_ensure_fold: output layer too wide for the fold kernel");
+    ts_fold_kernel<<<tc_nblk((size_t)(f.H + f.KP0 + 1), 8), 256, sm, s>>>(f, W.ffold, W.bfold);
+    TC_KCHECK(h);
+    h->ts->fold_dirty[net] = 0;
+    return 0;
+}
 static void ts_actor_mlp(const dppo_handle* h, int net, TsMlp& m) {
     const Geom& g = h->g; const float* w = h->net_w[net];
     memset(&m, 0, sizeof(m));
@@ -1357,12 +1435,13 @@ static int ts_mlp_forward(dppo_handle* h, cudaStream_t s, const TsMlp& m, int N)
     if (m.act1 == 1) { g.epi.mask_out = m.m1; g.epi.ldm = H / 32; } else if (m.act1 == 2) { g.epi.gate_out = 1; g.gate[0] = m.g1.p[0]; g.gate[1] = m.g1.p[1]; }
     DPPO_TRY(tsp::launch(h, s, g));
     if (m.fold) {
-        // no activation between block.l2 and the output layer: out = [a1 | h0] [W2 W3 ; W0 W3] + (b2 W3 + b3), one narrow GEMM
-        ts::Gemm o = ts_gemm_of(tsK(m.a1, N, H, H), tswK(W.ffold, 0, 32, H, H + KP0), N, m.NO, 2, 1);
+        // no activation between block.l2 and the output layer: out = [a1 | h0] [W2 W3 ; W0 W3] + bfold, one narrow GEMM
+        ts::Gemm o = ts_gemm_of(tsK(m.a1, N, H, H), tswK(W.ffold, 0, 32, H, H + KP0), N, m.NO, 2, f16 ? 1 : 0);
         o.A2 = tsK(m.h0, N, KP0, KP0); o.B2 = tswK(W.ffold, (size_t)H, 32, KP0, H + KP0);
-        o.f16 = 1; o.epi.scale = 1.0f / ts::F16_WSCALE;
-        o.epi.bias = m.bfold; o.epi.out_f32 = m.out; o.epi.ld_f32 = m.NO;
+        if (f16) { o.f16 = 1; o.epi.scale = 1.0f / ts::F16_WSCALE; }
+        o.epi.bias = W.bfold; o.epi.out_f32 = m.out; o.epi.ld_f32 = m.NO;
         o.alg_flops = 2.0 * N * ((double)H * H + (double)H * m.NO);        // the algorithmic work it stands for
+        if (m.fold_ev) CUDA_TRY(cudaStreamWaitEvent(s, m.fold_ev, 0));
         DPPO_TRY(ts_run(h, s, o));
         return 0;
     }
@@ -1422,7 +1501,9 @@ static int ts_mlp_backward_dx(dppo_handle* h, cudaStream_t s, const TsMlp& m, co
 }
 // the four weight-gradient products of one net for the grouped pair kernel; the narrow layer-0 product is handed over as
 // du^T h0 + dv^T h0 (wide operand on M, output written transposed into dw0 [KP0][H])
-static void ts_mlp_dw_descs(const TsMlp& m, const SplitT& dout, int N, float* gnet, size_t ow1, size_t ow2, size_t ow3, float* dw0, tsp::DwDesc* d) {
+// (fold: d[3] = a1^T dout -> g1 [H][NO] and d[4] = h0^T dout -> g0 [KP0][NO] instead of v^T dout; returns the number of problems)
+static int ts_mlp_dw_descs(const TsMlp& m, const SplitT& dout, int N, float* gnet, size_t ow1, size_t ow2, size_t ow3, float* dw0, tsp::DwDesc* d,
+                           float* g1 = nullptr, float* g0 = nullptr) {
     const int H = m.H, KP0 = m.KP0; const double r = (double)N; const SplitT none = split_null();
     // (fp = 4: the bf16 copies of the activations - one tcgen05.mma cannot take an fp16 and a bf16 operand, and the gradients are bf16)
     const bool f = m.fp == 4;
@@ -1430,19 +1511,144 @@ static void ts_mlp_dw_descs(const TsMlp& m, const SplitT& dout, int N, float* gn
     d[0] = tsp::DwDesc{a1, H, m.dv, H, none, none, gnet + ow2, H, H, H, 0, 2.0 * r * H * H};
     d[1] = tsp::DwDesc{a0, H, m.dh1, H, none, none, gnet + ow1, H, H, H, 0, 2.0 * r * H * H};
     d[2] = tsp::DwDesc{m.du, H, h0, KP0, m.dv, h0, dw0, H, KP0, H, 1, 2.0 * r * m.din * H};
+    if (m.fold) {
+        d[3] = tsp::DwDesc{a1, H, dout, 64, none, none, g1, H, m.NO, m.NO, 0, 2.0 * r * H * m.NO};
+        d[4] = tsp::DwDesc{h0, KP0, dout, 64, none, none, g0, KP0, m.NO, m.NO, 0, 0.0};
+        return 5;
+    }
     d[3] = tsp::DwDesc{v, H, dout, 64, none, none, gnet + ow3, H, m.NO, m.NO, 0, 2.0 * r * H * m.NO};
+    return 4;
+}
+// dW3[j][a] = sum_r v[r][j] dout[r][a] with v = a1 W2 + (b2 + b0) + h0 W0 never formed:
+//   dW3 = W2^T (a1^T dout) + W0^T (h0^T dout) + (b2 + b0) (1^T dout),   1^T dout = the row of h0^T dout that belongs to h0's ones column
+// g1 = a1^T dout [H][NO], g0 = h0^T dout [KP0][NO] come from the grouped weight-gradient launch.  One thread per (a, j), j fastest.
+struct TsDw3Args {
+    const float *w2, *b2, *b0, *win, *bt, *g1, *g0; float* out;
+    int x_rows, x_skip, obs_skip, A, Do, T, H, NO, KP0;
+};
+// Grid = (32-column chunk of j) x (KS slices of k): a block sums its k slice for its 32 columns (lane = j: every W2 / W0 read is a
+// coalesced 128-byte row segment, all of a warp's loads in flight at once; g1 / g0 rows in shared memory), writes the partial
+// [32][NO] tile, and the LAST block of a column chunk to finish (a counter per chunk) adds the KS partials in slice order - the result
+// does not depend on which block that is.  (A first version walked all k in one block per chunk: 41 us of serialised load latency.)
+constexpr int DW3_KS = 8;
+__device__ __forceinline__ void ts_dw3_assemble_body(const TsDw3Args& f, int bid, float* sm, float* __restrict__ part, int* __restrict__ done) {
+    const int H = f.H, NO = f.NO, KT = f.A + f.Do + f.T, K = H + KT;       // k < H: W2 rows; then the h0-order rows of layer 0
+    const int jc = bid / DW3_KS, ks = bid % DW3_KS;
+    const int kper = (K + DW3_KS - 1) / DW3_KS, kbeg = ks * kper, kend = min(K, kbeg + kper);
+    float* gs = sm;                                   // [kper][NO]
+    float* red = gs + (size_t)kper * NO;              // [16][32][NO]
+    __shared__ int last_flag;
+    for (int i = threadIdx.x; i < (kend - kbeg) * NO; i += blockDim.x) {
+        const int k = kbeg + i / NO, a = i % NO;
+        gs[i] = k < H ? f.g1[(size_t)k * NO + a] : f.g0[(size_t)(k - H) * NO + a];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5, j = jc * 32 + lane;
+    auto row_of = [&](int k) -> const float* {
+        if (k < H) return f.w2 + (size_t)k * H;
+        const int k0 = k - H;
+        if (k0 < f.A) return k0 < f.x_rows ? f.win + (size_t)(k0 + f.x_skip) * H : nullptr;
+        if (k0 < f.A + f.Do) return f.win + (size_t)(k0 - f.A + f.obs_skip) * H;
+        return f.bt ? f.bt + (size_t)(k0 - f.A - f.Do) * H : nullptr;
+    };
+    float wv[8];                                      // this warp's k: kbeg + warp + u * nw (kper <= 8 * nw)
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const int k = kbeg + warp + u * nw;
+        const float* row = (k < kend && j < H) ? row_of(k) : nullptr;
+        wv[u] = row ? row[j] : 0.f;
+    }
+    for (int a = 0; a < NO; ++a) {
+        float acc = 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int kl = warp + u * nw;
+            if (kbeg + kl < kend) acc = fmaf(wv[u], gs[(size_t)kl * NO + a], acc);
+        }
+        red[((size_t)warp * 32 + lane) * NO + a] = acc;
+    }
+    __syncthreads();
+    float* mine = part + ((size_t)jc * DW3_KS + ks) * 32 * NO;
+    for (int i = threadIdx.x; i < 32 * NO; i += blockDim.x) {
+        float s = 0.f;
+        for (int w = 0; w < nw; ++w) s += red[(size_t)w * 32 * NO + i];
+        mine[i] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last_flag = (atomicAdd(done + jc, 1) == DW3_KS - 1) ? 1 : 0;
+    __syncthreads();
+    if (!last_flag) return;
+    __threadfence();
+    const float* ones = f.g0 + (size_t)KT * NO;        // g0 row A + Do + T = 1^T dout
+    for (int i = threadIdx.x; i < 32 * NO; i += blockDim.x) {
+        const int l = i / NO, a = i % NO, jj = jc * 32 + l;
+        if (jj >= H) continue;
+        float s = 0.f;
+        for (int q = 0; q < DW3_KS; ++q) s += __ldcg(part + ((size_t)jc * DW3_KS + q) * 32 * NO + i);
+        const float bias = f.b2[jj] + (f.b0 ? f.b0[jj] : 0.f);
+        f.out[(size_t)jj * NO + a] = fmaf(bias, ones[a], s);
+    }
+    if (threadIdx.x == 0) done[jc] = 0;                // ready for the next launch
+}
+__global__ void __launch_bounds__(512) ts_dw3_assemble_kernel(const TsDw3Args fa, int blocks_a, const TsDw3Args fc, float* __restrict__ part, int* __restrict__ done) {
+    extern __shared__ float dw3_sm[];
+    if ((int)blockIdx.x < blocks_a) ts_dw3_assemble_body(fa, blockIdx.x, dw3_sm, part, done);
+    else ts_dw3_assemble_body(fc, blockIdx.x - blocks_a, dw3_sm, part + (size_t)blocks_a * 32 * fa.NO, done + blocks_a / DW3_KS);
+}
+static inline int tsDW3KS() { return DW3_KS; }
+static TsDw3Args ts_dw3_args(const dppo_handle* h, int net, const float* g1, const float* g0, float* out) {
+    const Geom& g = h->g; const float* w = h->net_w[net];
+    TsDw3Args f; memset(&f, 0, sizeof(f));
+    f.A = g.A; f.Do = g.Do; f.T = g.T; f.KP0 = h->ts->KP0; f.g1 = g1; f.g0 = g0; f.out = out;
+    if (net == DPPO_NET_CRITIC) {
+        f.H = g.Hc; f.NO = 1; f.w2 = w + g.co.w2; f.b2 = w + g.co.b2; f.b0 = w + g.co.bin; f.win = w + g.co.win; f.x_rows = 0; f.obs_skip = 0; f.bt = nullptr;
+    } else {
+        f.H = g.H; f.NO = g.A; f.w2 = w + g.ao.w2; f.b2 = w + g.ao.b2; f.b0 = nullptr; f.win = w + g.ao.win; f.x_rows = g.A; f.x_skip = 0;
+        f.obs_skip = g.A + g.td; f.bt = h->ad[net].bt;
+    }
+    return f;
+}
+// launches the assembly for the actor (and the critic when gc1 != nullptr)
+static int ts_dw3_assemble(dppo_handle* h, cudaStream_t s, int actor_net, const float* ga1, const float* ga0, float* outa,
+                           const float* gc1, const float* gc0, float* outc) {
+    const Geom& g = h->g;
+    const TsDw3Args fa = ts_dw3_args(h, actor_net, ga1, ga0, outa);
+    TsDw3Args fc = fa; int nbc = 0;
+    if (gc1) { fc = ts_dw3_args(h, DPPO_NET_CRITIC, gc1, gc0, outc); nbc = tc_nblk((size_t)g.Hc, 32) * tsDW3KS(); }
+    const int nba = tc_nblk((size_t)g.H, 32) * tsDW3KS();
+    auto smf = [&](const TsDw3Args& f) { const int K = f.H + f.A + f.Do + f.T; return (size_t)(((K + DW3_KS - 1) / DW3_KS) * f.NO + 16 * 32 * f.NO) * sizeof(float); };
+    auto kper = [&](const TsDw3Args& f) { return (f.H + f.A + f.Do + f.T + DW3_KS - 1) / DW3_KS; };
+    const size_t sm = smf(fa) > smf(fc) ? smf(fa) : smf(fc);
+    static bool attr_set_dev[64] = {};
+    if (!attr_set_dev[h->device & 63]) { CUDA_TRY(cudaFuncSetAttribute(ts_dw3_assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); attr_set_dev[h->device & 63] = true; }
+    if (sm > 100 * 1024 || g.A > 32 || kper(fa) > 128 || kper(fc) > 128) DPPO_FAIL(-7, "ts_dw3_assemble: shape not covered");
+    TsState* st = h->ts;
+    // buffer: [256 chunk counters (always at the front: launches with and without the critic share them, every launch leaves them zero)
+    //          | partial tiles]
+    const size_t need = 1024 + ((size_t)nba * 32 * g.A + (size_t)nbc * 32) * sizeof(float);
+    if ((nba + nbc) / DW3_KS > 256) DPPO_FAIL(-7, "ts_dw3_assemble: too many column chunks");
+    if (st->dw3_bytes < need) {
+        CUDA_TRY(cudaStreamSynchronize(s));
+        if (st->dw3_buf) cudaFree(st->dw3_buf);
+        CUDA_TRY(cudaMalloc(&st->dw3_buf, need)); CUDA_TRY(cudaMemsetAsync(st->dw3_buf, 0, need, s));
+        st->dw3_bytes = need;
+    }
+    int* done = reinterpret_cast<int*>(st->dw3_buf);
+    float* partb = reinterpret_cast<float*>(st->dw3_buf + 1024);
+    ts_dw3_assemble_kernel<<<nba + nbc, 512, sm, s>>>(fa, nba, fc, partb, done);
+    TC_KCHECK(h);
+    return 0;
 }
 static size_t ts_part_floats(const dppo_handle* h, int H) {
     const size_t a = tc_part_floats(h, H), b = (size_t)(h->sm_count / 2 + 1) * 65536;
     return a > b ? a : b;
 }
 // ------------------------------------------------------------------ forward-only programs
-// DPPO_NO_FOLD=1: forward-only programs evaluate block.l2 and the output layer as two products, like the training forward
-static inline bool ts_no_fold() { static int v = -1; if (v < 0) { const char* e = getenv("DPPO_NO_FOLD"); v = (e && atoi(e)) ? 1 : 0; } return v != 0; }
 static size_t ts_actor_forward_ws(const dppo_handle* h, int N) { return ts_mlp_ws_bytes(N, h->g.H, h->ts->KP0, h->cfg.actor_act == DPPO_ACT_MISH, false); }
 // eps[N][A] = actor(x, t, obs); appends to the workspace (the caller may hold pointers below ws.used)
 static int ts_actor_forward(dppo_handle* h, cudaStream_t s, int net, const float* x, const float* obs, int obs_div, int N,
-                            const int* trow, int tconst, float* eps, int chainK = 0, bool fold_ok = false) {
+                            const int* trow, int tconst, float* eps, int chainK = 0) {
     const Geom& g = h->g; const int KP0 = h->ts->KP0;
     const size_t need = h->ws.used + ts_actor_forward_ws(h, N);
     if (need > h->ws.cap) DPPO_FAIL(-7, "ts_actor_forward: workspace too small (%zu > %zu)", need, h->ws.cap);
@@ -1450,18 +1656,9 @@ static int ts_actor_forward(dppo_handle* h, cudaStream_t s, int net, const float
     TsMlp m; ts_actor_mlp(h, net, m);
     ts_mlp_take(h, N, m, false);
     m.out = eps;
-    // fold_ok: the samplers.  The log-prob forward keeps the training forward's arithmetic so that the PPO ratio of unchanged weights is
-    // exactly 1 (old log-probs from dppo_logprobs, new ones inside dppo_ppo_step: tests/test_gpu_fullsize_oracle.py)
-    if (fold_ok && m.fp == 4 && !ts_no_fold()) {
-        if (h->ts->fold_dirty[net]) {
-            DPPO_TRY(ensure_w23(h, net, s));
-            ts_pack_fold_kernel<<<tc_nblk((size_t)64 * (g.H + KP0), 128), 128, 0, s>>>(h->net_w[net], g.ao, g.A, g.td, g.Do, g.T, g.H, KP0, h->ad[net].bt,
-                                                                                      h->ad[net].w23, h->ts->net[net].ffold);
-            TC_KCHECK(h);
-            h->ts->fold_dirty[net] = 0;
-        }
-        m.fold = 1; m.bfold = h->ad[net].b23;
-    }
+    // every program of this mode folds (or none: DPPO_NO_FOLD), so that the log-prob forward and the update's forward are the same
+    // arithmetic and the PPO ratio of unchanged weights is exactly 1 (tests/test_gpu_fullsize_oracle.py)
+    if (!ts_no_fold()) { DPPO_TRY(ts_ensure_fold(h, net, s)); m.fold = 1; }
     ts_pack_h0_kernel<<<tc_nblk((size_t)N * (KP0 / 8), 256), 256, 0, s>>>(x, obs, trow, tconst, N, g.A, g.Do, g.T, KP0, obs_div, m.h0, split_null(), chainK);
     TC_KCHECK(h);
     const int r = ts_mlp_forward(h, s, m, N);
@@ -1474,6 +1671,7 @@ static int ts_value(dppo_handle* h, cudaStream_t s, const float* obs, int N, flo
     TsMlp m; ts_critic_mlp(h, m);
     ts_mlp_take(h, N, m, false);
     m.out = v;
+    if (!ts_no_fold()) { DPPO_TRY(ts_ensure_fold(h, DPPO_NET_CRITIC, s)); m.fold = 1; }
     ts_pack_h0_kernel<<<tc_nblk((size_t)N * (KP0 / 8), 256), 256, 0, s>>>(nullptr, obs, nullptr, -1, N, g.A, g.Do, g.T, KP0, 1,
                                                                           m.fp == 4 ? m.h0 : split_null(), m.fp == 4 ? split_null() : m.h0, 0);
     TC_KCHECK(h);
@@ -1504,7 +1702,8 @@ static int ts_ppo_step(dppo_handle* h, cudaStream_t s, const float* obs, const f
     const size_t need = ts_mlp_ws_bytes(N, g.H, KP0, amish, true) + ts_mlp_ws_bytes(N, g.Hc, KP0, cmish, true)
                       + 2 * ws_bytes((size_t)N * g.A, 4) + 2 * ws_bytes(N, 4) + 4 * ws_bytes((size_t)N * 64, 2)
                       + ws_bytes(pf, 4) + ws_bytes((size_t)KP0 * g.H, 4) + ws_bytes((size_t)KP0 * g.Hc, 4) + ws_bytes((size_t)nlb * 5, 8) + ws_bytes(16, 4)
-                      + ws_bytes((size_t)nlb * (g.A + 1), 4) + ws_bytes((size_t)nrb * 2 * g.H, 4) + ws_bytes((size_t)nrb * 2 * g.Hc, 4);
+                      + ws_bytes((size_t)nlb * (g.A + 1), 4) + ws_bytes((size_t)nrb * 2 * g.H, 4) + ws_bytes((size_t)nrb * 2 * g.Hc, 4)
+                      + ws_bytes((size_t)(g.H + g.Hc + 2 * KP0) * 32, 4);
     DPPO_TRY(ws_reserve(h, need, s));
     TsMlp ma, mc; ts_actor_mlp(h, DPPO_NET_ACTOR_FT, ma); ts_critic_mlp(h, mc);
     ts_mlp_take(h, N, ma, true); ts_mlp_take(h, N, mc, true);
@@ -1517,6 +1716,10 @@ static int ts_ppo_step(dppo_handle* h, cudaStream_t s, const float* obs, const f
     int* ebeg = ws_take<int>(h, 16);
     float* colb3 = ws_take<float>(h, (size_t)nlb * (g.A + 1));
     float* cpa = ws_take<float>(h, (size_t)nrb * 2 * g.H); float* cpc = ws_take<float>(h, (size_t)nrb * 2 * g.Hc);
+    float* gfold = ws_take<float>(h, (size_t)(g.H + g.Hc + 2 * KP0) * 32);       // a1^T dout / h0^T dout of both nets (folded output layer)
+    float* ga1 = gfold; float* ga0 = ga1 + (size_t)g.H * g.A; float* gc1 = ga0 + (size_t)KP0 * g.A; float* gc0 = gc1 + g.Hc;
+    const bool fold = !ts_no_fold();
+    ma.fold = mc.fold = fold ? 1 : 0;
     ma.out = eps; mc.out = val;
     // The critic's GEMMs are independent of the actor's until the loss (and again until the weight gradients) and their tiles are
     // short (K = 256: epilogue-latency-bound), while every persistent GEMM leaves SMs idle in its last wave: the critic (and the
@@ -1529,6 +1732,7 @@ static int ts_ppo_step(dppo_handle* h, cudaStream_t s, const float* obs, const f
             CUDA_TRY(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
             for (int i = 0; i < 2; ++i) CUDA_TRY(cudaEventCreateWithFlags(&h->aux_ev[i], cudaEventDisableTiming));
         }
+        if (!h->aux_ev[2]) CUDA_TRY(cudaEventCreateWithFlags(&h->aux_ev[2], cudaEventDisableTiming));
         sc = h->aux_stream;
     }
     auto fork = [&]() -> int { if (side) { CUDA_TRY(cudaEventRecord(h->aux_ev[0], s)); CUDA_TRY(cudaStreamWaitEvent(sc, h->aux_ev[0], 0)); } return 0; };
@@ -1543,6 +1747,11 @@ static int ts_ppo_step(dppo_handle* h, cudaStream_t s, const float* obs, const f
     TC_KCHECK(h);
     if (mc.fp == 4) { mc.h0 = ma.h0; mc.h0b = ma.h0b; }
     DPPO_TRY(fork());
+    // the folded output layers of the current weights (stale after every AdamW step): on the second stream, under the actor's L0 / L1
+    if (fold) {
+        DPPO_TRY(ts_ensure_fold(h, DPPO_NET_ACTOR_FT, sc)); DPPO_TRY(ts_ensure_fold(h, DPPO_NET_CRITIC, sc));
+        if (side) { CUDA_TRY(cudaEventRecord(h->aux_ev[2], sc)); ma.fold_ev = h->aux_ev[2]; }      // the actor's stream waits in front of its folded GEMM only
+    }
     if (adv_std < 0.f) {
         if (idx) adv_stats_kernel<<<1, 1024, 0, sc>>>(idx->adv, N, h->scalars, idx->flat, idx->K, idx->P);
         else adv_stats_kernel<<<1, 1024, 0, sc>>>(advantages, N, h->scalars);
@@ -1577,11 +1786,21 @@ static int ts_ppo_step(dppo_handle* h, cudaStream_t s, const float* obs, const f
     DPPO_TRY(ts_mlp_backward_dx(h, s, ma, depsb, N, cpa));
     DPPO_TRY(ts_mlp_backward_dx(h, sc, mc, dvalb, N, cpc));
     DPPO_TRY(join());
-    tsp::DwDesc dd[8];
-    ts_mlp_dw_descs(ma, depsb, N, gr, g.ao.w1, g.ao.w2, g.ao.w3, dw0a, dd);
-    ts_mlp_dw_descs(mc, dvalb, N, gr + nA, g.co.w1, g.co.w2, g.co.w3, dw0c, dd + 4);
-    DPPO_TRY(tsp::launch_dw_group(h, s, dd, 8, N, part, pf, ebeg));
-    if (loss8) return tc_launch_tail(h, s, bsum, nlb, hp.inv_nglobal, frac_local, colb3, cpa, nrb, cpc, nrb, dw0a, dw0c);
+    tsp::DwDesc dd[10];
+    const int nda = ts_mlp_dw_descs(ma, depsb, N, gr, g.ao.w1, g.ao.w2, g.ao.w3, dw0a, dd, ga1, ga0);
+    const int ndc = ts_mlp_dw_descs(mc, dvalb, N, gr + nA, g.co.w1, g.co.w2, g.co.w3, dw0c, dd + nda, gc1, gc0);
+    DPPO_TRY(tsp::launch_dw_group(h, s, dd, nda + ndc, N, part, pf, ebeg));
+    // the output layers' weight gradients are assembled next to the merged tail kernel (both only read the reduced dW outputs)
+    if (fold) {
+        DPPO_TRY(fork());
+        DPPO_TRY(ts_dw3_assemble(h, sc, DPPO_NET_ACTOR_FT, ga1, ga0, gr + g.ao.w3, gc1, gc0, gr + nA + g.co.w3));
+    }
+    if (loss8) {
+        DPPO_TRY(tc_launch_tail(h, s, bsum, nlb, hp.inv_nglobal, frac_local, colb3, cpa, nrb, cpc, nrb, dw0a, dw0c));
+        if (fold) DPPO_TRY(join());
+        return 0;
+    }
+    if (fold) DPPO_TRY(join());
     // (unaligned / wide action rows) the same pieces as separate launches
     ppo_metrics_kernel<<<1, 256, 0, s>>>(bsum, nlb, hp.inv_nglobal, frac_local, gr + nA + nC); TC_KCHECK(h);
     DPPO_TRY(colsum(h, s, deps, g.A, N, g.A, nullptr, 1, part, gr + g.ao.b3));
@@ -1608,10 +1827,12 @@ static int ts_pretrain_grads(dppo_handle* h, cudaStream_t s, const float* action
     const size_t pf = ts_part_floats(h, g.H);
     const size_t need = ts_mlp_ws_bytes(N, g.H, KP0, h->cfg.actor_act == DPPO_ACT_MISH, true) + 4 * ws_bytes(ne, 4) + ws_bytes(N, 4)
                       + 2 * ws_bytes((size_t)N * 64, 2) + ws_bytes(pf, 4) + ws_bytes((size_t)KP0 * g.H, 4) + ws_bytes(nlb, 8) + ws_bytes(16, 4)
-                      + ws_bytes((size_t)nrb * 2 * g.H, 4);
+                      + ws_bytes((size_t)nrb * 2 * g.H, 4) + ws_bytes((size_t)(g.H + KP0) * 32, 4);
     DPPO_TRY(ws_reserve(h, need, s));
     TsMlp ma; ts_actor_mlp(h, DPPO_NET_ACTOR, ma);
     ts_mlp_take(h, N, ma, true);
+    float* ga1 = ws_take<float>(h, (size_t)(g.H + KP0) * 32); float* ga0 = ga1 + (size_t)g.H * g.A;
+    if (!ts_no_fold()) { DPPO_TRY(ts_ensure_fold(h, DPPO_NET_ACTOR, s)); ma.fold = 1; }
     float* eps = ws_take<float>(h, ne); float* deps = ws_take<float>(h, ne); float* noise = ws_take<float>(h, ne); float* xn = ws_take<float>(h, ne);
     int* trow = ws_take<int>(h, N);
     SplitT depsb = ts_take(h, (size_t)N * 64, 2);
@@ -1629,9 +1850,10 @@ static int ts_pretrain_grads(dppo_handle* h, cudaStream_t s, const float* action
     sum_blocks_kernel<<<1, 256, 0, s>>>(bsum, nlb, scale, gr + nA); TC_KCHECK(h);
     ts_pad64_kernel<<<tc_nblk((size_t)N * 8, 256), 256, 0, s>>>(deps, N, g.A, depsb.p[0], depsb.p[1]); TC_KCHECK(h);
     DPPO_TRY(ts_mlp_backward_dx(h, s, ma, depsb, N, cpa));
-    tsp::DwDesc dd[4];
-    ts_mlp_dw_descs(ma, depsb, N, gr, g.ao.w1, g.ao.w2, g.ao.w3, dw0, dd);
-    DPPO_TRY(tsp::launch_dw_group(h, s, dd, 4, N, part, pf, ebeg));
+    tsp::DwDesc dd[5];
+    const int nd = ts_mlp_dw_descs(ma, depsb, N, gr, g.ao.w1, g.ao.w2, g.ao.w3, dw0, dd, ga1, ga0);
+    DPPO_TRY(tsp::launch_dw_group(h, s, dd, nd, N, part, pf, ebeg));
+    if (ma.fold) DPPO_TRY(ts_dw3_assemble(h, s, DPPO_NET_ACTOR, ga1, ga0, gr + g.ao.w3, nullptr, nullptr, nullptr));
     tc_reduce_cols_kernel<<<tc_nblk(2 * g.H, 8), 256, 0, s>>>(cpa, nrb, (size_t)2 * g.H, 2 * g.H, gr + g.ao.b2, g.H, gr + g.ao.b1); TC_KCHECK(h);
     DPPO_TRY(colsum(h, s, deps, g.A, N, g.A, nullptr, 1, part, gr + g.ao.b3));
     const float* w = h->net_w[DPPO_NET_ACTOR]; const ActorDerived& d = h->ad[DPPO_NET_ACTOR];

@@ -137,7 +137,7 @@ def test_split_forward_value_logprobs(pair):
     got = e.actor_forward(L.NET_ACTOR_FT, x.reshape(N, -1), t, _flat(obs))
     gv = e.value(_flat(obs))
     torch.cuda.synchronize()
-    assert e.tc_launch_count() - n0 == 8                       # four plane GEMMs per network
+    assert e.tc_launch_count() - n0 == 6                       # three plane GEMMs per network: L0, L1, the folded [block.l2 ; output] layer
     err, errv = rel_err(got, want.reshape(N, -1)), rel_err(gv, wantv)
     print(f"bf16x3 eps rel err {err:.3e}, value rel err {errv:.3e}")
     assert err < 5e-6 and errv < 5e-5
@@ -162,7 +162,7 @@ def test_split_ppo_step_matches_oracle(pair):
     m, g = e.ppo_step(_flat(batch[0]), batch[1].reshape(N, -1), batch[2].reshape(N, -1), batch[3], batch[4], batch[5], batch[6],
                       batch[7].reshape(N, -1), lr=0.0, apply=False, want_grads=True)
     torch.cuda.synchronize()
-    assert e.tc_launch_count() - n0 == 2 * (4 + 3) + 1          # per net: 4 forward + 3 backward plane GEMMs; one grouped weight-gradient launch
+    assert e.tc_launch_count() - n0 == 2 * (3 + 3) + 1          # per net: 3 forward + 3 backward plane GEMMs; one grouped weight-gradient launch
     wg = np.concatenate([O.flatten_params(ga), O.flatten_params(gc)])
     g = g.cpu().numpy()
     nA = e.n_actor
@@ -214,7 +214,7 @@ def test_split_pretrain_and_large_batch_sampler(pair):
     n0 = e.tc_launch_count()
     loss, pg = e.pretrain_step(acts.reshape(N, -1), _flat(st), lr=1e-3, apply=False, t=tt, noise=nz.reshape(N, -1), want_grads=True)
     torch.cuda.synchronize()
-    assert e.tc_launch_count() - n0 == 8                        # 4 forward + 3 backward + the grouped weight-gradient launch
+    assert e.tc_launch_count() - n0 == 7                        # 3 forward + 3 backward + the grouped weight-gradient launch
     wg = O.flatten_params(want_g)
     err_g = float(np.abs(pg.cpu().numpy() - wg).max() / np.abs(wg).max())
     print(f"bf16x3 pre-train: loss {float(loss):.6f} vs {float(want_l):.6f}, grad {err_g:.3e} of max")
@@ -246,6 +246,8 @@ def test_split_index_driven_update_reads_the_rollout_buffers_directly(pair):
     ret, val, adv = torch.randn(P, generator=g), torch.randn(P, generator=g), torch.randn(P, generator=g)
     flat = torch.randint(0, P * K, (N,), generator=g, dtype=torch.int64)
     b, k = flat // K, flat % K
+    e.ppo_step_indexed(_flat(obs), chains, olp, ret, val, adv, flat.to(torch.int32).cuda(), lr=0.0, apply=False)
+    # (the folded output layers of the current weights are now built: they cost one small launch per net after a weight change)
     n0 = e.launch_count()
     m1, g1 = e.ppo_step_indexed(_flat(obs), chains, olp, ret, val, adv, flat.to(torch.int32).cuda(), lr=0.0, apply=False, want_grads=True)
     launches_indexed = e.launch_count() - n0
