@@ -1657,7 +1657,7 @@ static int ts_actor_forward(dppo_handle* h, cudaStream_t s, int net, const float
     ts_mlp_take(h, N, m, false);
     m.out = eps;
     // every program of this mode folds (or none: DPPO_NO_FOLD), so that the log-prob forward and the update's forward are the same
-    // arithmetic and the PPO ratio of unchanged weights is exactly 1 (tests/test_gpu_fullsize_oracle.py)
+    // arithmetic and the PPO ratio of unchanged weights is exactly 1 (the full-size parity tests assert it)
     if (!ts_no_fold()) { DPPO_TRY(ts_ensure_fold(h, net, s)); m.fold = 1; }
     ts_pack_h0_kernel<<<tc_nblk((size_t)N * (KP0 / 8), 256), 256, 0, s>>>(x, obs, trow, tconst, N, g.A, g.Do, g.T, KP0, obs_div, m.h0, split_null(), chainK);
     TC_KCHECK(h);
