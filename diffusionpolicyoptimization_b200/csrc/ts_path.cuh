@@ -1795,7 +1795,9 @@ static int ts_ppo_step(dppo_handle* h, cudaStream_t s, const float* obs, const f
         DPPO_TRY(fork());
         DPPO_TRY(ts_dw3_assemble(h, sc, DPPO_NET_ACTOR_FT, ga1, ga0, gr + g.ao.w3, gc1, gc0, gr + nA + g.co.w3));
     }
-    if (loss8) {
+    static int split_tail = -1;     // dev knob DPPO_TS_SPLIT_TAIL=1: the tail's roles as separate launches (to time them one by one)
+    if (split_tail < 0) { const char* e = getenv("DPPO_TS_SPLIT_TAIL"); split_tail = (e && atoi(e)) ? 1 : 0; }
+    if (loss8 && !split_tail) {
         DPPO_TRY(tc_launch_tail(h, s, bsum, nlb, hp.inv_nglobal, frac_local, colb3, cpa, nrb, cpc, nrb, dw0a, dw0c));
         if (fold) DPPO_TRY(join());
         return 0;
@@ -1803,8 +1805,12 @@ static int ts_ppo_step(dppo_handle* h, cudaStream_t s, const float* obs, const f
     if (fold) DPPO_TRY(join());
     // (unaligned / wide action rows) the same pieces as separate launches
     ppo_metrics_kernel<<<1, 256, 0, s>>>(bsum, nlb, hp.inv_nglobal, frac_local, gr + nA + nC); TC_KCHECK(h);
-    DPPO_TRY(colsum(h, s, deps, g.A, N, g.A, nullptr, 1, part, gr + g.ao.b3));
-    DPPO_TRY(colsum(h, s, dval, 1, N, 1, nullptr, 1, part, gr + nA + g.co.b3));
+    if (loss8) {
+        tc_reduce_cols_kernel<<<tc_nblk(g.A + 1, 8), 256, 0, s>>>(colb3, nlb, (size_t)(g.A + 1), g.A + 1, gr + g.ao.b3, g.A, gr + nA + g.co.b3); TC_KCHECK(h);
+    } else {
+        DPPO_TRY(colsum(h, s, deps, g.A, N, g.A, nullptr, 1, part, gr + g.ao.b3));
+        DPPO_TRY(colsum(h, s, dval, 1, N, 1, nullptr, 1, part, gr + nA + g.co.b3));
+    }
     tc_reduce_cols_kernel<<<tc_nblk(2 * g.H, 8), 256, 0, s>>>(cpa, nrb, (size_t)2 * g.H, 2 * g.H, gr + g.ao.b2, g.H, gr + g.ao.b1); TC_KCHECK(h);
     tc_reduce_cols_kernel<<<tc_nblk(2 * g.Hc, 8), 256, 0, s>>>(cpc, nrb, (size_t)2 * g.Hc, 2 * g.Hc, gr + nA + g.co.b2, g.Hc, gr + nA + g.co.b1); TC_KCHECK(h);
     const float* w = h->net_w[DPPO_NET_ACTOR_FT]; const ActorDerived& d = h->ad[DPPO_NET_ACTOR_FT];
