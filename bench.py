@@ -365,14 +365,17 @@ def run_ours(args):
                                                                             "tflops": cls[c][2] / (cls[c][0] * 1e-3) / 1e12 if cls[c][0] > 0 else 0.0}
                                                    for c in range(4) if cls[c][1] > 0}}}
         if md == "bf16x3":
-            roof["note"] = ("achieved / frac count ALGORITHMIC flops (one multiply-add per weight and row) against the bf16 tensor peak; the plane arithmetic "
-                            "executes 6 tcgen05 products per algorithmic MAC in the actor's forward layers and 3 elsewhere, so the ceiling of this mode is "
-                            "1/6 .. 1/3 of the pipe; kernels that overlap on two streams in `value` run back to back while they are timed")
+            roof["note"] = ("achieved / frac count ALGORITHMIC flops (one multiply-add per weight and row of the unfolded network) against the bf16 tensor peak; "
+                            "the plane arithmetic executes 3 tcgen05 products per multiply-add (two 16-bit planes per operand), so the ceiling of this mode is "
+                            "1/3 of the pipe; kernels that overlap on two streams in `value` run back to back while they are timed")
         elif md == "bf16":
             roof["note"] = "per-kernel durations are timed with the actor and critic chains serialized; in `value` the critic chain overlaps the actor chain's last wave"
         else:
-            roof["bound"] = "fp32-fma"
-            roof["note"] = "CUDA-core FFMA mode: frac is quoted against the bf16 tensor peak for comparability; against the derived FFMA peak (148 SM x 128 x 2 x 1.965 GHz = 74.5 TFLOP/s) it is achieved / 74.5"
+            ffma = eng.ffma_peak_tflops()
+            roof["bound"] = "fp32-fma"; roof["peak"] = ffma; roof["frac"] = achieved / ffma if ffma > 0 else None
+            roof["peak_source"] = "measured on this GPU (dppo_debug_ffma_peak: 16 independent fmaf chains per thread, 2048 threads per SM, CUDA events); derived 148 SM x 128 x 2 x 1.965 GHz = 74.5"
+            roof["issued_tflops"] = None; roof["issued_frac_of_peak"] = None
+            roof["note"] = "CUDA-core FFMA mode: the dominant class is sgemm_kernel (128x128x16 register tiles); frac is against the MEASURED FFMA rate"
         return roof
 
     clk = Clocks(local); clk.start()
@@ -557,9 +560,8 @@ def run_ours(args):
         lps = (eo.launch_count() - l1) // (nst + 3)
         blk = {"value": n_global * nst / (ms_o * 1e-3), "unit": UNIT, "ms_per_step": ms_o / nst, "dtype": DTYPES[md], "precision": PRECISION_NOTE[md],
                "gpu_launches_per_step": lps, "step_tflops": fps * rows / (ms_o / nst * 1e-3) / 1e12}
+        blk["roofline"] = roofline_of(eo, md, ms_o / nst)
         if md != "fp32":
-            saved = args.steps
-            blk["roofline"] = roofline_of(eo, md, ms_o / nst)
 
             def e2e_o(i, eo=eo):
                 if i % UPLOAD_EVERY == 0:
@@ -573,7 +575,19 @@ def run_ours(args):
             blk["sampling_large_batch"] = large_block(eo, md)
             blk["pretrain"] = pre_block(eo, md)
         else:
-            blk["frac_of_fp32_ffma_peak"] = fps * rows / (ms_o / nst * 1e-3) / 74.5e12
+            ffma = blk["roofline"]["peak"]
+            blk["fp32_ffma_peak_measured_tflops"] = ffma
+            blk["frac_of_fp32_ffma_peak"] = fps * rows / (ms_o / nst * 1e-3) / (ffma * 1e12) if ffma else None
+
+            def e2e_f(i, eo=eo):
+                if i % UPLOAD_EVERY == 0:
+                    for hb, db in zip(roll_host, roll_dev):
+                        db.copy_(hb, non_blocking=True)
+                eo.ppo_step_indexed(*roll_dev, inds_host[i & 1].numpy(), lr=lr, apply=True, n_global=n_global, adv_mean=idx_mean, adv_std=idx_std,
+                                    metrics_host=metrics_host.numpy())
+            ms_fi = timed(e2e_f, 4, 2)
+            blk["e2e"] = {"value": n_global * 4 / (ms_fi * 1e-3), "unit": UNIT, "ms_per_step": ms_fi / 4,
+                          "api": "Engine.ppo_step_indexed (as the headline e2e; 4 timed steps, rollout resident)"}
         other[md] = blk
         eo.close()
 

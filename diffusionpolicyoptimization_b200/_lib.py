@@ -24,7 +24,7 @@ EXPORTS = (
     "dppo_sample", "dppo_sample_host", "dppo_set_env_normalization", "dppo_rollout_step", "dppo_logprobs", "dppo_logprobs_subsample", "dppo_ppo_step",
     "dppo_ppo_step_host", "dppo_ppo_step_indexed", "dppo_ppo_step_indexed_host", "dppo_gae", "dppo_pretrain_step", "dppo_ema_update", "dppo_comm_unique_id",
     "dppo_comm_init", "dppo_comm_ipc_export", "dppo_comm_ipc_attach", "dppo_comm_status", "dppo_launch_count", "dppo_tc_launch_count", "dppo_fused_launch_count", "dppo_last_path", "dppo_force_path", "dppo_profile_enable", "dppo_debug_tc_gemm",
-    "dppo_profile_read", "dppo_debug_chain_timing", "dppo_debug_mma_probe", "dppo_profile_read_class", "dppo_profile_read_exec", "dppo_debug_split_gemm", "dppo_debug_pair_gemm",
+    "dppo_profile_read", "dppo_debug_chain_timing", "dppo_debug_mma_probe", "dppo_debug_ffma_peak", "dppo_profile_read_class", "dppo_profile_read_exec", "dppo_debug_split_gemm", "dppo_debug_pair_gemm",
 )
 
 
@@ -111,6 +111,7 @@ def load():
         "dppo_debug_pair_gemm": (C.c_int, [vp, vp, i64, vp, i32, i64, i32, i32, i32, i32, vp, i32, vp, vp, vp]),
         "dppo_debug_chain_timing": (C.c_int, [vp, i32, vp, C.POINTER(C.c_int)]),
         "dppo_debug_mma_probe": (C.c_int, [vp, i32, i32, i32, i32, i32, vp]),
+        "dppo_debug_ffma_peak": (C.c_int, [vp, C.POINTER(C.c_double)]),
         "dppo_profile_read_class": (C.c_int, [vp, i32, C.POINTER(C.c_double), C.POINTER(i64), C.POINTER(C.c_double)]),
         "dppo_profile_read_exec": (C.c_int, [vp, i32, C.POINTER(C.c_double)]),
         "dppo_profile_read": (C.c_int, [vp, C.POINTER(C.c_double), C.POINTER(i64), C.POINTER(C.c_double)]),

@@ -1295,6 +1295,36 @@ extern "C" int dppo_debug_chain_timing(dppo_handle* h, int enable, long long* ou
     return 0;
 }
 // dev probe (tools/mma_probe.py): out_host [2*grid] per CTA, see fc::mma_probe_kernel
+__global__ void __launch_bounds__(256) ffma_peak_kernel(float* __restrict__ out, int iters, float x, float y) {
+    float a[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) a[j] = (float)(threadIdx.x + j) * 1e-6f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) a[j] = fmaf(a[j], x, y);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) s += a[j];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+extern "C" int dppo_debug_ffma_peak(dppo_handle* h, double* tflops) {
+    ENTER(h);
+    if (!tflops) DPPO_FAIL(-1, "dppo_debug_ffma_peak: bad arguments");
+    const int blocks = h->sm_count * 8, iters = 8192;
+    float* out = nullptr;
+    CUDA_TRY(cudaMalloc(&out, (size_t)blocks * 256 * sizeof(float)));
+    cudaEvent_t a, b; CUDA_TRY(cudaEventCreate(&a)); CUDA_TRY(cudaEventCreate(&b));
+    ffma_peak_kernel<<<blocks, 256>>>(out, iters, 0.999f, 1e-3f);
+    CUDA_TRY(cudaEventRecord(a, 0));
+    for (int r = 0; r < 4; ++r) ffma_peak_kernel<<<blocks, 256>>>(out, iters, 0.999f, 1e-3f);
+    CUDA_TRY(cudaEventRecord(b, 0));
+    CUDA_TRY(cudaEventSynchronize(b));
+    float ms = 0.f; CUDA_TRY(cudaEventElapsedTime(&ms, a, b));
+    cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(out);
+    *tflops = 4.0 * (double)blocks * 256.0 * (double)iters * 16.0 * 2.0 / ((double)ms * 1e-3) / 1e12;
+    return 0;
+}
 extern "C" int dppo_debug_mma_probe(dppo_handle* h, int grid, int mode, int iters, int N, int depth, long long* out_host) {
     if (!h || !out_host || grid < 1 || grid > 1024 || depth < 0 || depth > 31) DPPO_FAIL(-1, "dppo_debug_mma_probe: bad arguments");
     CUDA_TRY(cudaSetDevice(h->device));

@@ -109,6 +109,12 @@ class Engine:
         L.check(self.lib.dppo_set_grad_clip_norm(self.h, float(clip_norm) if clip_norm else 0.0), "dppo_set_grad_clip_norm")
 
     # ---------------------------------------------------------------- forward-only
+    def ffma_peak_tflops(self) -> float:
+        """Measured sustained CUDA-core FFMA rate of this GPU (bench.py: the strict-fp32 mode's roofline denominator)."""
+        v = C.c_double(0.0)
+        L.check(self.lib.dppo_debug_ffma_peak(self.h, C.byref(v)), "dppo_debug_ffma_peak")
+        return float(v.value)
+
     def actor_forward(self, net: int, x, t, obs) -> torch.Tensor:
         x = _as_dev(x, self.dev).reshape(-1, self.A)
         N = x.shape[0]

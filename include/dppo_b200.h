@@ -286,6 +286,9 @@ int dppo_debug_pair_gemm(dppo_handle* h, const float* A, int64_t lda, const floa
 int dppo_debug_chain_timing(dppo_handle* h, int enable, long long* out_host, int* sm_count);
 /* Dev probe: tcgen05.mma issue cost, TMA round trip and TMA throughput per SM; see tools/mma_probe.py. */
 int dppo_debug_mma_probe(dppo_handle* h, int grid, int mode, int iters, int N, int depth, long long* out_host);
+/* Measurement aid for bench.py (the strict-fp32 mode's roofline denominator): sustained CUDA-core FFMA rate of this GPU in TFLOP/s -
+ * 16 independent fmaf chains per thread, 2048 threads per SM, timed with CUDA events after a warm-up launch. */
+int dppo_debug_ffma_peak(dppo_handle* h, double* tflops);
 int dppo_profile_enable(dppo_handle* h, int on);
 int dppo_profile_read(dppo_handle* h, double* gemm_ms, int64_t* gemm_launches, double* gemm_flops);
 /* Tensor-pipe flops the launches of a class actually ISSUED (padded tiles; the plane modes issue 3 or 6 products per algorithmic
