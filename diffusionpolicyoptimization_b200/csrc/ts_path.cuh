@@ -4,8 +4,9 @@
 // each) and every product is evaluated as a sum of exact bf16 x bf16 plane products accumulated in fp32 in tensor memory,
 // several tcgen05.mma per k-step into ONE accumulator:
 //   P = 2 (16-bit operands, backward / weight-gradient GEMMs):  A B ~= A0 B0 + A1 B0 + A0 B1              (dropped: 2^-18)
-//   P = 3 (24-bit operands, forward GEMMs):                     A B ~= A0 B0 + A0 B1 + A1 B0 + A1 B1 + A0 B2 + A2 B0   (2^-27)
-// Why the forward pass needs P = 3: the loss is only piecewise smooth (ReLU kinks, the +-1 clip of x0, the PPO ratio clip).  A
+//   P = 3 (24-bit operands; the first forward version, kept for the debug GEMM entry points and the tests that compare the variants):
+//                                                               A B ~= A0 B0 + A0 B1 + A1 B0 + A1 B1 + A0 B2 + A2 B0   (2^-27)
+// Why the forward pass needs more than 16 bits: the loss is only piecewise smooth (ReLU kinks, the +-1 clip of x0, the PPO ratio clip).  A
 // forward deviation eps from the reference flips about eps * density units across a kink, and every flipped unit switches a
 // whole gradient term on or off: the actor-gradient error against the reference grows like sqrt(eps) - 2e-3 of the largest
 // entry with 16-bit forward operands (measured, tools/flip_probe.py), against the 1e-3 north_star's fp32 mode is held to.
@@ -1680,8 +1681,8 @@ static int ts_value(dppo_handle* h, cudaStream_t s, const float* obs, int N, flo
 
 // ------------------------------------------------------------------ gradients
 // PPODiffusion.c_loss + tape.gradient (diffusion_ppo.py:32-132, train_ppo_diffusion_agent.py:340-346).  Leaves
-// [actor_ft grads | critic grads | 8 metrics] in h->grads.  16 plane-GEMM launches + 6 small kernels:
-// adv-stats (second stream) | h0 pack | 4 + 4 forward | loss | 3 + 3 backward | grouped dW + reduce | tail.
+// [actor_ft grads | critic grads | 8 metrics] in h->grads.  13 plane-GEMM launches + 8 small kernels:
+// h0 pack | folded output layers + adv-stats (second stream) | 3 + 3 forward | loss | 3 + 3 backward | grouped dW + reduce | tail || dW3 assembly.
 // shapes / alignment the index-driven variant needs (float4 row reads of the resident rollout buffers)
 static bool ts_ppo_indexed_ok(const dppo_handle* h, const TcIdxView& v) {
     return (h->g.A % 4 == 0) && h->g.A <= 32 && ((((uintptr_t)v.chains | (uintptr_t)v.olp) & 15) == 0);
