@@ -13,6 +13,7 @@
 //   * fused epilogue: + bias, activation, * act'(mask), + residual, fp32 / bf16 (pre- and post-
 //     activation) stores, split-K partial outputs.
 #pragma once
+#include <unordered_map>
 #include "common.cuh"
 #include <cuda.h>
 
@@ -376,7 +377,35 @@ static int load_encode() {
     return 0;
 }
 // row-major bf16 matrix [rows][cols] with leading dimension ld (elements); box = [box_rows][box_cols]
+// A tensor map is a pure function of (address, extents, pitch, box): the programs of a step re-create the same few hundred descriptors
+// every call (workspace addresses are stable), and cuTensorMapEncodeTiled costs about a microsecond each - more host time per step than
+// all the launches together.  Per-thread cache, dropped wholesale when it grows past 8192 entries.
+struct MapKey {
+    const void* base; uint64_t rows, cols, ld; uint32_t br, bc;
+    bool operator==(const MapKey& o) const { return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && br == o.br && bc == o.bc; }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey& k) const {
+        uint64_t h = (uint64_t)(uintptr_t)k.base * 0x9E3779B97F4A7C15ull;
+        h ^= (k.rows + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2));
+        h ^= (k.cols * 0xC2B2AE3D27D4EB4Full + (h << 6) + (h >> 2));
+        h ^= (k.ld * 0x165667B19E3779F9ull + (h << 6) + (h >> 2));
+        h ^= (((uint64_t)k.br << 32 | k.bc) + (h << 6) + (h >> 2));
+        return (size_t)h;
+    }
+};
+static int make_map_uncached(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols);
 static int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols) {
+    static thread_local std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+    const MapKey k{base, rows, cols, ld, box_rows, box_cols};
+    auto it = cache.find(k);
+    if (it != cache.end()) { *m = it->second; return 0; }
+    DPPO_TRY(make_map_uncached(m, base, rows, cols, ld, box_rows, box_cols));
+    if (cache.size() > 8192) cache.clear();
+    cache.emplace(k, *m);
+    return 0;
+}
+static int make_map_uncached(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols) {
     DPPO_TRY(load_encode());
     if ((((uintptr_t)base) & 15) || ((ld * 2) & 15)) DPPO_FAIL(-8, "tensor map operand is not 16-byte aligned (ld=%llu)", (unsigned long long)ld);
     cuuint64_t dims[2] = {cols, rows};
