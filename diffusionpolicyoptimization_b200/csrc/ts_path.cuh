@@ -1417,13 +1417,16 @@ static tsp::Gemm tsp_gemm_of(ts::Operand A, ts::Operand B, int M, int N, int pla
     return g;
 }
 
-static int ts_mlp_forward(dppo_handle* h, cudaStream_t s, const TsMlp& m, int N) {
+// phase 0: the whole forward; 1: L0 and L1 only; 2: what follows L1 (lets a caller enqueue other streams' work in between)
+static int ts_mlp_forward(dppo_handle* h, cudaStream_t s, const TsMlp& m, int N, int phase = 0) {
     const int H = m.H, KP0 = m.KP0, P = m.fp; const TsNetW& W = *m.W;
     const size_t w0 = (size_t)H * H;
     const bool f16 = P == 4;
     const TsW& Ww2w0 = f16 ? W.fw2w0 : W.w2w0; const TsW& Ww1 = f16 ? W.fw1 : W.w1; const TsW& Ww3t = f16 ? W.fw3t : W.w3t;
+    tsp::Gemm g;
+    if (phase != 2) {
     // L0: a0 = act(h0 W0 (+ b0))
-    tsp::Gemm g = tsp_gemm_of(tsK(m.h0, N, KP0, KP0), tswMN(Ww2w0, w0, H, KP0, H), N, H, P, m.a0, P, H);
+    g = tsp_gemm_of(tsK(m.h0, N, KP0, KP0), tswMN(Ww2w0, w0, H, KP0, H), N, H, P, m.a0, P, H);
     g.epi.bias = m.b0; g.epi.act = m.act1;
     if (m.a0b.p[0]) { g.out2[0] = m.a0b.p[0]; g.out2[1] = m.a0b.p[1]; g.epi.out2 = 1; }
     if (m.act1 == 1) { g.epi.mask_out = m.m0; g.epi.ldm = H / 32; } else if (m.act1 == 2) { g.epi.gate_out = 1; g.gate[0] = m.g0.p[0]; g.gate[1] = m.g0.p[1]; }
@@ -1435,6 +1438,8 @@ static int ts_mlp_forward(dppo_handle* h, cudaStream_t s, const TsMlp& m, int N)
     if (m.a1b.p[0]) { g.out2[0] = m.a1b.p[0]; g.out2[1] = m.a1b.p[1]; g.epi.out2 = 1; }
     if (m.act1 == 1) { g.epi.mask_out = m.m1; g.epi.ldm = H / 32; } else if (m.act1 == 2) { g.epi.gate_out = 1; g.gate[0] = m.g1.p[0]; g.gate[1] = m.g1.p[1]; }
     DPPO_TRY(tsp::launch(h, s, g));
+    }
+    if (phase == 1) return 0;
     if (m.fold) {
         // no activation between block.l2 and the output layer: out = [a1 | h0] [W2 W3 ; W0 W3] + bfold, one narrow GEMM
         ts::Gemm o = ts_gemm_of(tsK(m.a1, N, H, H), tswK(W.ffold, 0, 32, H, H + KP0), N, m.NO, 2, f16 ? 1 : 0);
@@ -1747,7 +1752,13 @@ static int ts_ppo_step(dppo_handle* h, cudaStream_t s, const float* obs, const f
     else ts_pack_h0_kernel<<<tc_nblk((size_t)N * (KP0 / 8), 256), 256, 0, s>>>(prev, obs, inds, -g.K, N, g.A, g.Do, g.T, KP0, 1, ma.h0, hb, 0);
     TC_KCHECK(h);
     if (mc.fp == 4) { mc.h0 = ma.h0; mc.h0b = ma.h0b; }
-    DPPO_TRY(fork());
+    // The actor's two big layers are handed to the GPU before the host enqueues the second stream's kernels: after a step that ended with
+    // the metrics on the host the device is idle, and the short first kernels would otherwise run at the host's launch rate.
+    if (side) {
+        CUDA_TRY(cudaEventRecord(h->aux_ev[0], s));
+        DPPO_TRY(ts_mlp_forward(h, s, ma, N, 1));
+        CUDA_TRY(cudaStreamWaitEvent(sc, h->aux_ev[0], 0));
+    }
     // the folded output layers of the current weights (stale after every AdamW step): on the second stream, under the actor's L0 / L1
     if (fold) {
         DPPO_TRY(ts_ensure_fold(h, DPPO_NET_ACTOR_FT, sc)); DPPO_TRY(ts_ensure_fold(h, DPPO_NET_CRITIC, sc));
@@ -1759,7 +1770,7 @@ static int ts_ppo_step(dppo_handle* h, cudaStream_t s, const float* obs, const f
         TC_KCHECK(h);
     }
     else { set_scalars_kernel<<<1, 1, 0, sc>>>(h->scalars, adv_mean, adv_std); TC_KCHECK(h); }
-    DPPO_TRY(ts_mlp_forward(h, s, ma, N));
+    DPPO_TRY(ts_mlp_forward(h, s, ma, N, side ? 2 : 0));
     DPPO_TRY(ts_mlp_forward(h, sc, mc, N));
     DPPO_TRY(join());
     PpoHyper hp;
