@@ -10,7 +10,7 @@ from oracle import dppo_oracle as O
 from toy_env import ToyVecEnv
 from test_gpu_agent import make_model
 o = O.make_oracle("hopper", seed=5)
-model = make_model(o, precision="bf16")
+model = make_model(o, precision=(sys.argv[1] if len(sys.argv) > 1 else "bf16"))
 E, S = 256, 10
 sched = CosineAnnealingWarmupRestarts2(1e-4, 1000, 1.0, 1e-4, 1e-4, 10, 1.0)
 agent = TrainPPODiffusionAgent(model, ToyVecEnv(E, 11, 3, max_episode_steps=5, seed=9), n_envs=E, n_steps=S, act_steps=4, n_train_itr=12,
