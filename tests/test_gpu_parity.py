@@ -364,3 +364,12 @@ def test_gae_on_device_is_bit_identical_to_the_numpy_scan(pair):
     adv, ret = e.gae(rewards, terminated, values, next_values, reward_scale_const=0.1, gamma=0.999, gae_lambda=0.95)
     np.testing.assert_array_equal(adv.cpu().numpy(), want_a.astype(np.float32))
     np.testing.assert_array_equal(ret.cpu().numpy(), want_r.astype(np.float32))
+
+
+def test_ffma_peak_probe_is_plausible(pair):
+    """bench.py's roofline denominator of the strict-fp32 mode: the measured CUDA-core FFMA rate of this GPU (derived peak of a B200:
+    148 SM x 128 lanes x 2 x 1.965 GHz = 74.5 TFLOP/s)."""
+    o, e = pair
+    v = e.ffma_peak_tflops()
+    print(f"measured FFMA rate {v:.1f} TFLOP/s")
+    assert 40.0 < v < 80.0, v
