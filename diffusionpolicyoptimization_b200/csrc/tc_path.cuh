@@ -1212,7 +1212,9 @@ static int tc_ppo_chunk(dppo_handle* h, cudaStream_t s, int chunk, const float* 
 // gradients from the loss kernel's column partials, hidden-layer bias gradients from the chains' per-row-block column sums
 // (cpa / cpc: [rows][2][H], slot 0 = dv -> db2, slot 1 = dh1 -> db1), time-embedding backward, dW0 scatters, critic input bias.
 static int tc_launch_tail(dppo_handle* h, cudaStream_t s, const double* bsum, int blocks_done, float inv_nglobal, float frac_local, const float* colb3,
-                          const float* cpa, int rows_a, const float* cpc, int rows_c, const float* dw0a, const float* dw0c) {
+                          const float* cpa, int rows_a, const float* cpc, int rows_c, const float* dw0a, const float* dw0c,
+                          float* b2a_out = nullptr, float* b2c_out = nullptr) {   // b2*_out: where the slot-0 sums go instead of the b2 gradients
+                                                                                    // (programs that never form dv leave slot 0 unwritten)
     const Geom& g = h->g;
     const size_t nA = g.ao.n, nC = g.co.n;
     float* gr = h->grads;
@@ -1235,8 +1237,8 @@ static int tc_launch_tail(dppo_handle* h, cudaStream_t s, const double* bsum, in
     for (int r = 0; r < 8; ++r) a.first[r + 1] = a.first[r] + nb[r];
     a.bsum = bsum; a.blocks_done = blocks_done; a.inv_nglobal = inv_nglobal; a.frac_local = frac_local; a.metrics = gr + nA + nC;
     a.colb3 = colb3; a.ncol3 = g.A + 1; a.b3a = gr + g.ao.b3; a.split3 = g.A; a.b3c = gr + nA + g.co.b3;
-    a.cpa = cpa; a.rows_a = rows_a; a.HA = g.H; a.b2a = gr + g.ao.b2; a.b1a = gr + g.ao.b1;
-    a.cpc = cpc; a.rows_c = rows_c; a.HC = g.Hc; a.b2c = gr + nA + g.co.b2; a.b1c = gr + nA + g.co.b1;
+    a.cpa = cpa; a.rows_a = rows_a; a.HA = g.H; a.b2a = b2a_out ? b2a_out : gr + g.ao.b2; a.b1a = gr + g.ao.b1;
+    a.cpc = cpc; a.rows_c = rows_c; a.HC = g.Hc; a.b2c = b2c_out ? b2c_out : gr + nA + g.co.b2; a.b1c = gr + nA + g.co.b1;
     a.w = w; a.ao = g.ao; a.A = g.A; a.td = g.td; a.T = g.T; a.Do = g.Do; a.tb_staged = staged ? 1 : 0;
     a.Gt = dw0a + (size_t)(g.A + g.Do) * g.H; a.sinemb = d.sinemb; a.thpre = d.thpre; a.temb = d.temb; a.gr = gr;
     a.dw0a = dw0a; a.gwin_a = gr + g.ao.win; a.dw0c_obs = dw0c + (size_t)g.A * g.Hc; a.gwin_c = gr + nA + g.co.win;

@@ -1063,6 +1063,7 @@ struct TsNetW {
     TsW ffold;                            // [64][H + KP0] planes of [W2 W3 ; W0 W3]^T (fp16 x 2^10 when the net's forward runs on fp16 planes, else
                                           // bf16): the folded output layer, out = [a1 | h0] [W2 W3 ; W0 W3] + bfold
     float* bfold;                         // [64]  (b2 (+ b_in)) W3 + b3
+    TsW w23p;                             // [H][128] bf16 planes of W2 W3 (columns >= NO zero): dh1 = (dout (W2 W3)^T) . act'(h1) without forming dv
     float* bias2;                         // critic: b2 + b_in (the residual's input-layer bias rides with block.l2's)
     int H;
 };
@@ -1211,7 +1212,7 @@ struct TsFoldArgs {
 // one warp per output row k (k == H + KP0: the bias row): the lanes split j (16 products each, fp32), W3 sits transposed and padded in
 // shared memory (conflict-free both ways), the lane partials meet in a butterfly.  (A first version accumulated in double: 30 us - the
 // CUDA-core fp64 rate of this part - for sums that are rounded to 22-bit planes anyway.)
-__global__ void __launch_bounds__(256) ts_fold_kernel(const TsFoldArgs f, const TsW F, float* __restrict__ bfold) {
+__global__ void __launch_bounds__(256) ts_fold_kernel(const TsFoldArgs f, const TsW F, float* __restrict__ bfold, const TsW B23) {
     extern __shared__ float w3t[];               // [NO][H + 1]
     const int H = f.H, NO = f.NO, ld = f.H + f.KP0, HP = f.H + 1;
     for (int i0 = threadIdx.x; i0 < H * NO; i0 += blockDim.x * 8) {        // eight loads in flight per thread (one per iteration: 29 us of latency)
@@ -1266,6 +1267,7 @@ __global__ void __launch_bounds__(256) ts_fold_kernel(const TsFoldArgs f, const 
             if (bias_row) bfold[a] = a < NO ? v + f.b3[a] : 0.f;
             else if (f.f16) ts_put_f16(F, (size_t)a * ld + k, v);
             else ts_put(F, (size_t)a * ld + k, v);
+            if (!bias_row && k < H) ts_put(B23, (size_t)k * 128 + a, v);          // the backward operand (bf16 planes, row k of W2 W3)
         }
     }
 }
@@ -1296,6 +1298,7 @@ static int ts_init(dppo_handle* h) {
         DPPO_TRY(ts_alloc_w(w.fw2w0, (H + st->KP0) * H)); DPPO_TRY(ts_alloc_w(w.fw1, H * H)); DPPO_TRY(ts_alloc_w(w.fw3t, 64 * H));
         DPPO_TRY(ts_alloc_w(w.ffold, 64 * (H + st->KP0)));
         CUDA_TRY(cudaMalloc(&w.bfold, 64 * sizeof(float)));
+        DPPO_TRY(ts_alloc_w(w.w23p, H * 128)); CUDA_TRY(cudaMemset(w.w23p.p[0], 0, 2 * H * 128 * sizeof(bf16)));
         st->fold_dirty[net] = 1;
         CUDA_TRY(cudaMalloc(&w.bias2, H * sizeof(float)));
     }
@@ -1304,7 +1307,7 @@ static int ts_init(dppo_handle* h) {
 static void ts_destroy(dppo_handle* h) {
     if (!h->ts) return;
     cudaFree(h->ts->dw3_buf);
-    for (int net = 0; net < 4; ++net) { TsNetW& w = h->ts->net[net]; cudaFree(w.w2w0.p[0]); cudaFree(w.w1.p[0]); cudaFree(w.w3t.p[0]); cudaFree(w.w3p.p[0]); cudaFree(w.fw2w0.p[0]); cudaFree(w.fw1.p[0]); cudaFree(w.fw3t.p[0]); cudaFree(w.ffold.p[0]); cudaFree(w.bfold); cudaFree(w.bias2); }
+    for (int net = 0; net < 4; ++net) { TsNetW& w = h->ts->net[net]; cudaFree(w.w2w0.p[0]); cudaFree(w.w1.p[0]); cudaFree(w.w3t.p[0]); cudaFree(w.w3p.p[0]); cudaFree(w.fw2w0.p[0]); cudaFree(w.fw1.p[0]); cudaFree(w.fw3t.p[0]); cudaFree(w.ffold.p[0]); cudaFree(w.bfold); cudaFree(w.w23p.p[0]); cudaFree(w.bias2); }
     delete h->ts; h->ts = nullptr;
 }
 // rebuild the plane copies of one net (after set_weights / an optimizer step; the actor's bt table must be current)
@@ -1354,7 +1357,7 @@ static int ts_ensure_fold(dppo_handle* h, int net, cudaStream_t s) {
     if (!attr_set_dev[h->device & 63]) { CUDA_TRY(cudaFuncSetAttribute(ts_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr_set_dev[h->device & 63] = true; }
     const size_t sm = (size_t)(f.H + 1) * f.NO * sizeof(float);
     if (sm > 96 * 1024 || f.H > 1024) DPPO_FAIL(-7, "ts_ensure_fold: output layer too wide for the fold kernel");
-    ts_fold_kernel<<<tc_nblk((size_t)(f.H + f.KP0 + 1), 8), 256, sm, s>>>(f, W.ffold, W.bfold);
+    ts_fold_kernel<<<tc_nblk((size_t)(f.H + f.KP0 + 1), 8), 256, sm, s>>>(f, W.ffold, W.bfold, W.w23p);
     TC_KCHECK(h);
     h->ts->fold_dirty[net] = 0;
     return 0;
@@ -1490,13 +1493,22 @@ static int ts_colsum(dppo_handle* h, cudaStream_t s, const SplitT& D, int N, int
 // backward chain of the residual MLP from dout [N][64] (two planes, zero padded): dv = dout W3^T, dh1 = (dv W2^T) . act'(h1),
 // du = (dh1 W1^T) . act'(u).  du excludes the residual path: dW0 = h0^T du + h0^T dv.
 // cpart [ceil(N/32)][2][H]: per 32-row block column sums of dv (slot 0 = db2) and dh1 (slot 1 = db1), written by the epilogues
+// m.fold: dv = dout W3^T has rank NO and is never formed: dh1 = (dout (W2 W3)^T) . act'(h1) is ONE K = 64 product, and everything else dv
+// fed - dW2 = a1^T dv = (a1^T dout) W3^T, the residual part of dW0 = (h0^T dout) W3^T, db2 = (1^T dout) W3^T - is assembled from the small
+// products a1^T dout / h0^T dout the folded output layer needs anyway (ts_dw3_assemble_kernel).  cpart slot 0 then stays unwritten.
 static int ts_mlp_backward_dx(dppo_handle* h, cudaStream_t s, const TsMlp& m, const SplitT& dout, int N, float* cpart) {
     const int H = m.H; const TsNetW& W = *m.W;
-    tsp::Gemm g = tsp_gemm_of(tsK(dout, N, 64, 64), tswK(W.w3p, 0, H, 64, 128), N, H, 2, m.dv, 2, H);
+    tsp::Gemm g;
+    if (m.fold) {
+        g = tsp_gemm_of(tsK(dout, N, 64, 64), tswK(W.w23p, 0, H, 64, 128), N, H, 2, m.dh1, 2, H);
+        g.alg_flops = 2.0 * N * ((double)m.NO * H + (double)H * H);              // the two products it stands for
+    } else {
+    g = tsp_gemm_of(tsK(dout, N, 64, 64), tswK(W.w3p, 0, H, 64, 128), N, H, 2, m.dv, 2, H);
     g.alg_flops = 2.0 * N * (double)m.NO * H;
     g.epi.colsum_part = cpart; g.epi.colsum_ld = 2 * H;
     DPPO_TRY(tsp::launch(h, s, g));
     g = tsp_gemm_of(tsK(m.dv, N, H, H), tswK(W.w2w0, 0, H, H, H), N, H, 2, m.dh1, 2, H);
+    }
     g.epi.colsum_part = cpart + H; g.epi.colsum_ld = 2 * H;
     if (m.act1 == 1) { g.epi.mask_in = m.m1; g.epi.ldm = H / 32; } else if (m.act1 == 2) { g.epi.gate_in[0] = m.g1.p[0]; g.epi.gate_in[1] = m.g1.p[1]; g.epi.ldg = H; }
     DPPO_TRY(tsp::launch(h, s, g));
@@ -1517,10 +1529,12 @@ static int ts_mlp_dw_descs(const TsMlp& m, const SplitT& dout, int N, float* gne
     d[0] = tsp::DwDesc{a1, H, m.dv, H, none, none, gnet + ow2, H, H, H, 0, 2.0 * r * H * H};
     d[1] = tsp::DwDesc{a0, H, m.dh1, H, none, none, gnet + ow1, H, H, H, 0, 2.0 * r * H * H};
     d[2] = tsp::DwDesc{m.du, H, h0, KP0, m.dv, h0, dw0, H, KP0, H, 1, 2.0 * r * m.din * H};
-    if (m.fold) {
-        d[3] = tsp::DwDesc{a1, H, dout, 64, none, none, g1, H, m.NO, m.NO, 0, 2.0 * r * H * m.NO};
-        d[4] = tsp::DwDesc{h0, KP0, dout, 64, none, none, g0, KP0, m.NO, m.NO, 0, 0.0};
-        return 5;
+    if (m.fold) {          // no dv: dW2 and the residual part of dW0 come out of g1 / g0 (see ts_mlp_backward_dx)
+        d[0] = tsp::DwDesc{a0, H, m.dh1, H, none, none, gnet + ow1, H, H, H, 0, 2.0 * r * H * H};
+        d[1] = tsp::DwDesc{m.du, H, h0, KP0, none, none, dw0, H, KP0, H, 1, 2.0 * r * m.din * H};
+        d[2] = tsp::DwDesc{a1, H, dout, 64, none, none, g1, H, m.NO, m.NO, 0, 2.0 * r * (H * m.NO + (double)H * H)};
+        d[3] = tsp::DwDesc{h0, KP0, dout, 64, none, none, g0, KP0, m.NO, m.NO, 0, 0.0};
+        return 4;
     }
     d[3] = tsp::DwDesc{v, H, dout, 64, none, none, gnet + ow3, H, m.NO, m.NO, 0, 2.0 * r * H * m.NO};
     return 4;
@@ -1531,6 +1545,9 @@ static int ts_mlp_dw_descs(const TsMlp& m, const SplitT& dout, int N, float* gne
 struct TsDw3Args {
     const float *w2, *b2, *b0, *win, *bt, *g1, *g0; float* out;
     int x_rows, x_skip, obs_skip, A, Do, T, H, NO, KP0;
+    // what dv = dout W3^T would have fed, from the same two small products (rank NO):
+    //   dW2 = g1 W3^T [H][H],   dw0 [KP0][H] += g0 W3^T (the residual path's share of the layer-0 gradient),   db2 = (1^T dout) W3^T
+    const float* w3; float *dw2, *dw0, *db2;
 };
 // Grid = (32-column chunk of j) x (KS slices of k): a block sums its k slice for its 32 columns (lane = j: every W2 / W0 read is a
 // coalesced 128-byte row segment, all of a warp's loads in flight at once; g1 / g0 rows in shared memory), writes the partial
@@ -1597,31 +1614,74 @@ __device__ __forceinline__ void ts_dw3_assemble_body(const TsDw3Args& f, int bid
     }
     if (threadIdx.x == 0) done[jc] = 0;                // ready for the next launch
 }
-__global__ void __launch_bounds__(512) ts_dw3_assemble_kernel(const TsDw3Args fa, int blocks_a, const TsDw3Args fc, float* __restrict__ part, int* __restrict__ done) {
+// rows q of [g1 ; g0 ; 1^T dout] times W3^T: a block takes DW3_RB rows, thread j keeps row j of W3 in registers
+constexpr int DW3_RB = 8;
+__device__ __forceinline__ void ts_rank_rows_body(const TsDw3Args& f, int bid, float* sm) {
+    const int H = f.H, NO = f.NO, nrows = H + f.KP0 + 1, q0 = bid * DW3_RB;
+    const int ones = f.A + f.Do + f.T;
+    for (int i = threadIdx.x; i < DW3_RB * NO; i += blockDim.x) {
+        const int q = q0 + i / NO, a = i % NO;
+        float v = 0.f;
+        if (q < H) v = f.g1[(size_t)q * NO + a];
+        else if (q < H + f.KP0) v = f.g0[(size_t)(q - H) * NO + a];
+        else if (q == H + f.KP0) v = f.g0[(size_t)ones * NO + a];
+        sm[i] = v;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < H; j += blockDim.x) {
+        float w3r[32];
+#pragma unroll
+        for (int a = 0; a < 32; ++a) w3r[a] = a < NO ? __ldg(f.w3 + (size_t)j * NO + a) : 0.f;
+#pragma unroll
+        for (int r = 0; r < DW3_RB; ++r) {
+            const int q = q0 + r;
+            if (q >= nrows) break;
+            float acc = 0.f;
+#pragma unroll
+            for (int a = 0; a < 32; ++a) if (a < NO) acc = fmaf(sm[r * NO + a], w3r[a], acc);
+            if (q < H) f.dw2[(size_t)q * H + j] = acc;
+            else if (q < H + f.KP0) f.dw0[(size_t)(q - H) * H + j] += acc;
+            else f.db2[j] = acc;
+        }
+    }
+}
+__global__ void __launch_bounds__(512) ts_dw3_assemble_kernel(const TsDw3Args fa, int blocks_a, const TsDw3Args fc, int blocks_c,
+                                                              float* __restrict__ part, int* __restrict__ done, int rank_a, int rank_c) {
     extern __shared__ float dw3_sm[];
-    if ((int)blockIdx.x < blocks_a) ts_dw3_assemble_body(fa, blockIdx.x, dw3_sm, part, done);
-    else ts_dw3_assemble_body(fc, blockIdx.x - blocks_a, dw3_sm, part + (size_t)blocks_a * 32 * fa.NO, done + blocks_a / DW3_KS);
+    int b = blockIdx.x;
+    if (b < blocks_a) { ts_dw3_assemble_body(fa, b, dw3_sm, part, done); return; }
+    b -= blocks_a;
+    if (b < blocks_c) { ts_dw3_assemble_body(fc, b, dw3_sm, part + (size_t)blocks_a * 32 * fa.NO, done + blocks_a / DW3_KS); return; }
+    b -= blocks_c;
+    if (b < rank_a) { ts_rank_rows_body(fa, b, dw3_sm); return; }
+    b -= rank_a;
+    if (b < rank_c) ts_rank_rows_body(fc, b, dw3_sm);
 }
 static inline int tsDW3KS() { return DW3_KS; }
-static TsDw3Args ts_dw3_args(const dppo_handle* h, int net, const float* g1, const float* g0, float* out) {
+// gnet: this net's slice of the flat gradient; dw0: its [KP0][H] layer-0 staging buffer
+static TsDw3Args ts_dw3_args(const dppo_handle* h, int net, const float* g1, const float* g0, float* gnet, float* dw0) {
     const Geom& g = h->g; const float* w = h->net_w[net];
     TsDw3Args f; memset(&f, 0, sizeof(f));
-    f.A = g.A; f.Do = g.Do; f.T = g.T; f.KP0 = h->ts->KP0; f.g1 = g1; f.g0 = g0; f.out = out;
+    f.A = g.A; f.Do = g.Do; f.T = g.T; f.KP0 = h->ts->KP0; f.g1 = g1; f.g0 = g0; f.dw0 = dw0;
     if (net == DPPO_NET_CRITIC) {
         f.H = g.Hc; f.NO = 1; f.w2 = w + g.co.w2; f.b2 = w + g.co.b2; f.b0 = w + g.co.bin; f.win = w + g.co.win; f.x_rows = 0; f.obs_skip = 0; f.bt = nullptr;
+        f.w3 = w + g.co.w3; f.out = gnet + g.co.w3; f.dw2 = gnet + g.co.w2; f.db2 = gnet + g.co.b2;
     } else {
         f.H = g.H; f.NO = g.A; f.w2 = w + g.ao.w2; f.b2 = w + g.ao.b2; f.b0 = nullptr; f.win = w + g.ao.win; f.x_rows = g.A; f.x_skip = 0;
         f.obs_skip = g.A + g.td; f.bt = h->ad[net].bt;
+        f.w3 = w + g.ao.w3; f.out = gnet + g.ao.w3; f.dw2 = gnet + g.ao.w2; f.db2 = gnet + g.ao.b2;
     }
     return f;
 }
-// launches the assembly for the actor (and the critic when gc1 != nullptr)
-static int ts_dw3_assemble(dppo_handle* h, cudaStream_t s, int actor_net, const float* ga1, const float* ga0, float* outa,
-                           const float* gc1, const float* gc0, float* outc) {
+// launches the assembly for the actor (and the critic when gc1 != nullptr): dW3, dW2, db2 and the residual share of dw0.  Must run after the
+// grouped weight-gradient launch (g1, g0, dw0) and BEFORE anything that reads dw0 (the tail kernel)
+static int ts_dw3_assemble(dppo_handle* h, cudaStream_t s, int actor_net, const float* ga1, const float* ga0, float* gneta, float* dw0a,
+                           const float* gc1, const float* gc0, float* gnetc, float* dw0c) {
     const Geom& g = h->g;
-    const TsDw3Args fa = ts_dw3_args(h, actor_net, ga1, ga0, outa);
-    TsDw3Args fc = fa; int nbc = 0;
-    if (gc1) { fc = ts_dw3_args(h, DPPO_NET_CRITIC, gc1, gc0, outc); nbc = tc_nblk((size_t)g.Hc, 32) * tsDW3KS(); }
+    const TsDw3Args fa = ts_dw3_args(h, actor_net, ga1, ga0, gneta, dw0a);
+    TsDw3Args fc = fa; int nbc = 0, nrc = 0;
+    const int nra = tc_nblk((size_t)(g.H + h->ts->KP0 + 1), DW3_RB);
+    if (gc1) { fc = ts_dw3_args(h, DPPO_NET_CRITIC, gc1, gc0, gnetc, dw0c); nbc = tc_nblk((size_t)g.Hc, 32) * tsDW3KS(); nrc = tc_nblk((size_t)(g.Hc + h->ts->KP0 + 1), DW3_RB); }
     const int nba = tc_nblk((size_t)g.H, 32) * tsDW3KS();
     auto smf = [&](const TsDw3Args& f) { const int K = f.H + f.A + f.Do + f.T; return (size_t)(((K + DW3_KS - 1) / DW3_KS) * f.NO + 16 * 32 * f.NO) * sizeof(float); };
     auto kper = [&](const TsDw3Args& f) { return (f.H + f.A + f.Do + f.T + DW3_KS - 1) / DW3_KS; };
@@ -1642,7 +1702,7 @@ static int ts_dw3_assemble(dppo_handle* h, cudaStream_t s, int actor_net, const 
     }
     int* done = reinterpret_cast<int*>(st->dw3_buf);
     float* partb = reinterpret_cast<float*>(st->dw3_buf + 1024);
-    ts_dw3_assemble_kernel<<<nba + nbc, 512, sm, s>>>(fa, nba, fc, partb, done);
+    ts_dw3_assemble_kernel<<<nba + nbc + nra + nrc, 512, sm, s>>>(fa, nba, fc, nbc, partb, done, nra, nrc);
     TC_KCHECK(h);
     return 0;
 }
@@ -1709,7 +1769,7 @@ static int ts_ppo_step(dppo_handle* h, cudaStream_t s, const float* obs, const f
                       + 2 * ws_bytes((size_t)N * g.A, 4) + 2 * ws_bytes(N, 4) + 4 * ws_bytes((size_t)N * 64, 2)
                       + ws_bytes(pf, 4) + ws_bytes((size_t)KP0 * g.H, 4) + ws_bytes((size_t)KP0 * g.Hc, 4) + ws_bytes((size_t)nlb * 5, 8) + ws_bytes(16, 4)
                       + ws_bytes((size_t)nlb * (g.A + 1), 4) + ws_bytes((size_t)nrb * 2 * g.H, 4) + ws_bytes((size_t)nrb * 2 * g.Hc, 4)
-                      + ws_bytes((size_t)(g.H + g.Hc + 2 * KP0) * 32, 4);
+                      + ws_bytes((size_t)(g.H + g.Hc + 2 * KP0) * 32 + g.H + g.Hc, 4);
     DPPO_TRY(ws_reserve(h, need, s));
     TsMlp ma, mc; ts_actor_mlp(h, DPPO_NET_ACTOR_FT, ma); ts_critic_mlp(h, mc);
     ts_mlp_take(h, N, ma, true); ts_mlp_take(h, N, mc, true);
@@ -1722,7 +1782,7 @@ static int ts_ppo_step(dppo_handle* h, cudaStream_t s, const float* obs, const f
     int* ebeg = ws_take<int>(h, 16);
     float* colb3 = ws_take<float>(h, (size_t)nlb * (g.A + 1));
     float* cpa = ws_take<float>(h, (size_t)nrb * 2 * g.H); float* cpc = ws_take<float>(h, (size_t)nrb * 2 * g.Hc);
-    float* gfold = ws_take<float>(h, (size_t)(g.H + g.Hc + 2 * KP0) * 32);       // a1^T dout / h0^T dout of both nets (folded output layer)
+    float* gfold = ws_take<float>(h, (size_t)(g.H + g.Hc + 2 * KP0) * 32 + g.H + g.Hc);       // a1^T dout / h0^T dout of both nets (folded output layer) + scratch
     float* ga1 = gfold; float* ga0 = ga1 + (size_t)g.H * g.A; float* gc1 = ga0 + (size_t)KP0 * g.A; float* gc0 = gc1 + g.Hc;
     const bool fold = !ts_no_fold();
     ma.fold = mc.fold = fold ? 1 : 0;
@@ -1802,19 +1862,15 @@ static int ts_ppo_step(dppo_handle* h, cudaStream_t s, const float* obs, const f
     const int nda = ts_mlp_dw_descs(ma, depsb, N, gr, g.ao.w1, g.ao.w2, g.ao.w3, dw0a, dd, ga1, ga0);
     const int ndc = ts_mlp_dw_descs(mc, dvalb, N, gr + nA, g.co.w1, g.co.w2, g.co.w3, dw0c, dd + nda, gc1, gc0);
     DPPO_TRY(tsp::launch_dw_group(h, s, dd, nda + ndc, N, part, pf, ebeg));
-    // the output layers' weight gradients are assembled next to the merged tail kernel (both only read the reduced dW outputs)
-    if (fold) {
-        DPPO_TRY(fork());
-        DPPO_TRY(ts_dw3_assemble(h, sc, DPPO_NET_ACTOR_FT, ga1, ga0, gr + g.ao.w3, gc1, gc0, gr + nA + g.co.w3));
-    }
+    // everything dv would have fed (dW3, dW2, db2, the residual share of dw0) from the two small products; before the tail, which reads dw0
+    if (fold) DPPO_TRY(ts_dw3_assemble(h, s, DPPO_NET_ACTOR_FT, ga1, ga0, gr, dw0a, gc1, gc0, gr + nA, dw0c));
+    float* b2scr = fold ? gfold + (size_t)(g.H + g.Hc + 2 * KP0) * 32 : nullptr;      // the unwritten slot-0 column sums land here, not in db2
     static int split_tail = -1;     // dev knob DPPO_TS_SPLIT_TAIL=1: the tail's roles as separate launches (to time them one by one)
     if (split_tail < 0) { const char* e = getenv("DPPO_TS_SPLIT_TAIL"); split_tail = (e && atoi(e)) ? 1 : 0; }
     if (loss8 && !split_tail) {
-        DPPO_TRY(tc_launch_tail(h, s, bsum, nlb, hp.inv_nglobal, frac_local, colb3, cpa, nrb, cpc, nrb, dw0a, dw0c));
-        if (fold) DPPO_TRY(join());
+        DPPO_TRY(tc_launch_tail(h, s, bsum, nlb, hp.inv_nglobal, frac_local, colb3, cpa, nrb, cpc, nrb, dw0a, dw0c, b2scr, b2scr ? b2scr + g.H : nullptr));
         return 0;
     }
-    if (fold) DPPO_TRY(join());
     // (unaligned / wide action rows) the same pieces as separate launches
     ppo_metrics_kernel<<<1, 256, 0, s>>>(bsum, nlb, hp.inv_nglobal, frac_local, gr + nA + nC); TC_KCHECK(h);
     if (loss8) {
@@ -1823,8 +1879,8 @@ static int ts_ppo_step(dppo_handle* h, cudaStream_t s, const float* obs, const f
         DPPO_TRY(colsum(h, s, deps, g.A, N, g.A, nullptr, 1, part, gr + g.ao.b3));
         DPPO_TRY(colsum(h, s, dval, 1, N, 1, nullptr, 1, part, gr + nA + g.co.b3));
     }
-    tc_reduce_cols_kernel<<<tc_nblk(2 * g.H, 8), 256, 0, s>>>(cpa, nrb, (size_t)2 * g.H, 2 * g.H, gr + g.ao.b2, g.H, gr + g.ao.b1); TC_KCHECK(h);
-    tc_reduce_cols_kernel<<<tc_nblk(2 * g.Hc, 8), 256, 0, s>>>(cpc, nrb, (size_t)2 * g.Hc, 2 * g.Hc, gr + nA + g.co.b2, g.Hc, gr + nA + g.co.b1); TC_KCHECK(h);
+    tc_reduce_cols_kernel<<<tc_nblk(2 * g.H, 8), 256, 0, s>>>(cpa, nrb, (size_t)2 * g.H, 2 * g.H, b2scr ? b2scr : gr + g.ao.b2, g.H, gr + g.ao.b1); TC_KCHECK(h);
+    tc_reduce_cols_kernel<<<tc_nblk(2 * g.Hc, 8), 256, 0, s>>>(cpc, nrb, (size_t)2 * g.Hc, 2 * g.Hc, b2scr ? b2scr + g.H : gr + nA + g.co.b2, g.Hc, gr + nA + g.co.b1); TC_KCHECK(h);
     const float* w = h->net_w[DPPO_NET_ACTOR_FT]; const ActorDerived& d = h->ad[DPPO_NET_ACTOR_FT];
     const size_t sm = (size_t)(g.T * g.td * 3) * sizeof(float);
     time_backward_kernel<<<1 + (g.H + 127) / 128, 512, sm, s>>>(w, g.ao, g.A, g.td, g.H, g.T, dw0a + (size_t)(g.A + g.Do) * g.H, d.sinemb, d.thpre, d.temb, gr); TC_KCHECK(h);
@@ -1845,11 +1901,11 @@ static int ts_pretrain_grads(dppo_handle* h, cudaStream_t s, const float* action
     const size_t pf = ts_part_floats(h, g.H);
     const size_t need = ts_mlp_ws_bytes(N, g.H, KP0, h->cfg.actor_act == DPPO_ACT_MISH, true) + 4 * ws_bytes(ne, 4) + ws_bytes(N, 4)
                       + 2 * ws_bytes((size_t)N * 64, 2) + ws_bytes(pf, 4) + ws_bytes((size_t)KP0 * g.H, 4) + ws_bytes(nlb, 8) + ws_bytes(16, 4)
-                      + ws_bytes((size_t)nrb * 2 * g.H, 4) + ws_bytes((size_t)(g.H + KP0) * 32, 4);
+                      + ws_bytes((size_t)nrb * 2 * g.H, 4) + ws_bytes((size_t)(g.H + KP0) * 32 + g.H, 4);
     DPPO_TRY(ws_reserve(h, need, s));
     TsMlp ma; ts_actor_mlp(h, DPPO_NET_ACTOR, ma);
     ts_mlp_take(h, N, ma, true);
-    float* ga1 = ws_take<float>(h, (size_t)(g.H + KP0) * 32); float* ga0 = ga1 + (size_t)g.H * g.A;
+    float* ga1 = ws_take<float>(h, (size_t)(g.H + KP0) * 32 + g.H); float* ga0 = ga1 + (size_t)g.H * g.A;     // + scratch for the unwritten slot-0 sums
     if (!ts_no_fold()) { DPPO_TRY(ts_ensure_fold(h, DPPO_NET_ACTOR, s)); ma.fold = 1; }
     float* eps = ws_take<float>(h, ne); float* deps = ws_take<float>(h, ne); float* noise = ws_take<float>(h, ne); float* xn = ws_take<float>(h, ne);
     int* trow = ws_take<int>(h, N);
@@ -1871,8 +1927,8 @@ static int ts_pretrain_grads(dppo_handle* h, cudaStream_t s, const float* action
     tsp::DwDesc dd[5];
     const int nd = ts_mlp_dw_descs(ma, depsb, N, gr, g.ao.w1, g.ao.w2, g.ao.w3, dw0, dd, ga1, ga0);
     DPPO_TRY(tsp::launch_dw_group(h, s, dd, nd, N, part, pf, ebeg));
-    if (ma.fold) DPPO_TRY(ts_dw3_assemble(h, s, DPPO_NET_ACTOR, ga1, ga0, gr + g.ao.w3, nullptr, nullptr, nullptr));
-    tc_reduce_cols_kernel<<<tc_nblk(2 * g.H, 8), 256, 0, s>>>(cpa, nrb, (size_t)2 * g.H, 2 * g.H, gr + g.ao.b2, g.H, gr + g.ao.b1); TC_KCHECK(h);
+    if (ma.fold) DPPO_TRY(ts_dw3_assemble(h, s, DPPO_NET_ACTOR, ga1, ga0, gr, dw0, nullptr, nullptr, nullptr, nullptr));
+    tc_reduce_cols_kernel<<<tc_nblk(2 * g.H, 8), 256, 0, s>>>(cpa, nrb, (size_t)2 * g.H, 2 * g.H, ma.fold ? ga1 + (size_t)(g.H + KP0) * 32 : gr + g.ao.b2, g.H, gr + g.ao.b1); TC_KCHECK(h);
     DPPO_TRY(colsum(h, s, deps, g.A, N, g.A, nullptr, 1, part, gr + g.ao.b3));
     const float* w = h->net_w[DPPO_NET_ACTOR]; const ActorDerived& d = h->ad[DPPO_NET_ACTOR];
     const size_t sm = (size_t)(g.T * g.td * 3) * sizeof(float);
