@@ -1616,8 +1616,8 @@ __device__ __forceinline__ void ts_dw3_assemble_body(const TsDw3Args& f, int bid
 }
 // rows q of [g1 ; g0 ; 1^T dout] times W3^T: a block takes DW3_RB rows, thread j keeps row j of W3 in registers
 constexpr int DW3_RB = 8;
-__device__ __forceinline__ void ts_rank_rows_body(const TsDw3Args& f, int bid, float* sm) {
-    const int H = f.H, NO = f.NO, nrows = H + f.KP0 + 1, q0 = bid * DW3_RB;
+__device__ __forceinline__ void ts_rank_rows_body(const TsDw3Args& f, int bid, float* sm, int row_begin, int row_end) {
+    const int H = f.H, NO = f.NO, nrows = min(H + f.KP0 + 1, row_end), q0 = row_begin + bid * DW3_RB;
     const int ones = f.A + f.Do + f.T;
     for (int i = threadIdx.x; i < DW3_RB * NO; i += blockDim.x) {
         const int q = q0 + i / NO, a = i % NO;
@@ -1645,17 +1645,23 @@ __device__ __forceinline__ void ts_rank_rows_body(const TsDw3Args& f, int bid, f
         }
     }
 }
+// phase 0: the rows that feed dw0 and db2 (q >= H; the tail kernel reads dw0, so these run first, on the main stream); phase 1: dW3 and the
+// dW2 rows (q < H), which nothing but AdamW reads - next to the tail kernel on the second stream
 __global__ void __launch_bounds__(512) ts_dw3_assemble_kernel(const TsDw3Args fa, int blocks_a, const TsDw3Args fc, int blocks_c,
-                                                              float* __restrict__ part, int* __restrict__ done, int rank_a, int rank_c) {
+                                                              float* __restrict__ part, int* __restrict__ done, int rank_a, int rank_c, int phase) {
     extern __shared__ float dw3_sm[];
     int b = blockIdx.x;
-    if (b < blocks_a) { ts_dw3_assemble_body(fa, b, dw3_sm, part, done); return; }
-    b -= blocks_a;
-    if (b < blocks_c) { ts_dw3_assemble_body(fc, b, dw3_sm, part + (size_t)blocks_a * 32 * fa.NO, done + blocks_a / DW3_KS); return; }
-    b -= blocks_c;
-    if (b < rank_a) { ts_rank_rows_body(fa, b, dw3_sm); return; }
+    if (phase == 1) {
+        if (b < blocks_a) { ts_dw3_assemble_body(fa, b, dw3_sm, part, done); return; }
+        b -= blocks_a;
+        if (b < blocks_c) { ts_dw3_assemble_body(fc, b, dw3_sm, part + (size_t)blocks_a * 32 * fa.NO, done + blocks_a / DW3_KS); return; }
+        b -= blocks_c;
+    }
+    const int ra0 = phase == 0 ? fa.H : 0, ra1 = phase == 0 ? fa.H + fa.KP0 + 1 : fa.H;
+    const int rc0 = phase == 0 ? fc.H : 0, rc1 = phase == 0 ? fc.H + fc.KP0 + 1 : fc.H;
+    if (b < rank_a) { ts_rank_rows_body(fa, b, dw3_sm, ra0, ra1); return; }
     b -= rank_a;
-    if (b < rank_c) ts_rank_rows_body(fc, b, dw3_sm);
+    if (b < rank_c) ts_rank_rows_body(fc, b, dw3_sm, rc0, rc1);
 }
 static inline int tsDW3KS() { return DW3_KS; }
 // gnet: this net's slice of the flat gradient; dw0: its [KP0][H] layer-0 staging buffer
@@ -1675,13 +1681,22 @@ static TsDw3Args ts_dw3_args(const dppo_handle* h, int net, const float* g1, con
 }
 // launches the assembly for the actor (and the critic when gc1 != nullptr): dW3, dW2, db2 and the residual share of dw0.  Must run after the
 // grouped weight-gradient launch (g1, g0, dw0) and BEFORE anything that reads dw0 (the tail kernel)
+// phase 0 / 1: see the kernel; phase -1: both, one after the other on s
 static int ts_dw3_assemble(dppo_handle* h, cudaStream_t s, int actor_net, const float* ga1, const float* ga0, float* gneta, float* dw0a,
-                           const float* gc1, const float* gc0, float* gnetc, float* dw0c) {
+                           const float* gc1, const float* gc0, float* gnetc, float* dw0c, int phase = -1) {
+    if (phase < 0) {
+        DPPO_TRY(ts_dw3_assemble(h, s, actor_net, ga1, ga0, gneta, dw0a, gc1, gc0, gnetc, dw0c, 0));
+        return ts_dw3_assemble(h, s, actor_net, ga1, ga0, gneta, dw0a, gc1, gc0, gnetc, dw0c, 1);
+    }
     const Geom& g = h->g;
     const TsDw3Args fa = ts_dw3_args(h, actor_net, ga1, ga0, gneta, dw0a);
     TsDw3Args fc = fa; int nbc = 0, nrc = 0;
-    const int nra = tc_nblk((size_t)(g.H + h->ts->KP0 + 1), DW3_RB);
-    if (gc1) { fc = ts_dw3_args(h, DPPO_NET_CRITIC, gc1, gc0, gnetc, dw0c); nbc = tc_nblk((size_t)g.Hc, 32) * tsDW3KS(); nrc = tc_nblk((size_t)(g.Hc + h->ts->KP0 + 1), DW3_RB); }
+    const int KP0r = h->ts->KP0 + 1;
+    const int nra = phase == 0 ? tc_nblk((size_t)KP0r, DW3_RB) : tc_nblk((size_t)g.H, DW3_RB);
+    if (gc1) {
+        fc = ts_dw3_args(h, DPPO_NET_CRITIC, gc1, gc0, gnetc, dw0c); nbc = tc_nblk((size_t)g.Hc, 32) * tsDW3KS();
+        nrc = phase == 0 ? tc_nblk((size_t)KP0r, DW3_RB) : tc_nblk((size_t)g.Hc, DW3_RB);
+    }
     const int nba = tc_nblk((size_t)g.H, 32) * tsDW3KS();
     auto smf = [&](const TsDw3Args& f) { const int K = f.H + f.A + f.Do + f.T; return (size_t)(((K + DW3_KS - 1) / DW3_KS) * f.NO + 16 * 32 * f.NO) * sizeof(float); };
     auto kper = [&](const TsDw3Args& f) { return (f.H + f.A + f.Do + f.T + DW3_KS - 1) / DW3_KS; };
@@ -1702,7 +1717,7 @@ static int ts_dw3_assemble(dppo_handle* h, cudaStream_t s, int actor_net, const 
     }
     int* done = reinterpret_cast<int*>(st->dw3_buf);
     float* partb = reinterpret_cast<float*>(st->dw3_buf + 1024);
-    ts_dw3_assemble_kernel<<<nba + nbc + nra + nrc, 512, sm, s>>>(fa, nba, fc, nbc, partb, done, nra, nrc);
+    ts_dw3_assemble_kernel<<<(phase == 1 ? nba + nbc : 0) + nra + nrc, 512, sm, s>>>(fa, nba, fc, nbc, partb, done, nra, nrc, phase);
     TC_KCHECK(h);
     return 0;
 }
@@ -1863,14 +1878,21 @@ static int ts_ppo_step(dppo_handle* h, cudaStream_t s, const float* obs, const f
     const int ndc = ts_mlp_dw_descs(mc, dvalb, N, gr + nA, g.co.w1, g.co.w2, g.co.w3, dw0c, dd + nda, gc1, gc0);
     DPPO_TRY(tsp::launch_dw_group(h, s, dd, nda + ndc, N, part, pf, ebeg));
     // everything dv would have fed (dW3, dW2, db2, the residual share of dw0) from the two small products; before the tail, which reads dw0
-    if (fold) DPPO_TRY(ts_dw3_assemble(h, s, DPPO_NET_ACTOR_FT, ga1, ga0, gr, dw0a, gc1, gc0, gr + nA, dw0c));
+    // (the dw0 / db2 rows first, on this stream; dW3 and dW2 - which only AdamW reads - beside the tail kernel on the second stream)
+    if (fold) {
+        DPPO_TRY(ts_dw3_assemble(h, s, DPPO_NET_ACTOR_FT, ga1, ga0, gr, dw0a, gc1, gc0, gr + nA, dw0c, 0));
+        DPPO_TRY(fork());
+        DPPO_TRY(ts_dw3_assemble(h, sc, DPPO_NET_ACTOR_FT, ga1, ga0, gr, dw0a, gc1, gc0, gr + nA, dw0c, 1));
+    }
     float* b2scr = fold ? gfold + (size_t)(g.H + g.Hc + 2 * KP0) * 32 : nullptr;      // the unwritten slot-0 column sums land here, not in db2
     static int split_tail = -1;     // dev knob DPPO_TS_SPLIT_TAIL=1: the tail's roles as separate launches (to time them one by one)
     if (split_tail < 0) { const char* e = getenv("DPPO_TS_SPLIT_TAIL"); split_tail = (e && atoi(e)) ? 1 : 0; }
     if (loss8 && !split_tail) {
         DPPO_TRY(tc_launch_tail(h, s, bsum, nlb, hp.inv_nglobal, frac_local, colb3, cpa, nrb, cpc, nrb, dw0a, dw0c, b2scr, b2scr ? b2scr + g.H : nullptr));
+        if (fold) DPPO_TRY(join());
         return 0;
     }
+    if (fold) DPPO_TRY(join());
     // (unaligned / wide action rows) the same pieces as separate launches
     ppo_metrics_kernel<<<1, 256, 0, s>>>(bsum, nlb, hp.inv_nglobal, frac_local, gr + nA + nC); TC_KCHECK(h);
     if (loss8) {
