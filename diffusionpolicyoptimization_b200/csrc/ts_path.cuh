@@ -1627,11 +1627,28 @@ __device__ __forceinline__ void ts_rank_rows_body(const TsDw3Args& f, int bid, f
         else if (q == H + f.KP0) v = f.g0[(size_t)ones * NO + a];
         sm[i] = v;
     }
+    // W3 through shared memory: coalesced, eight loads in flight per thread (a thread fetching its own row straight from global memory -
+    // 24 strided scalar loads - made the 65-row first phase a 16 us kernel)
+    float* w3s = sm + DW3_RB * NO;              // [H][NO + 1]
+    const int n3 = H * NO;
+    for (int i0 = threadIdx.x; i0 < n3; i0 += blockDim.x * 8) {
+        float t8[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const int i = i0 + u * blockDim.x; t8[u] = i < n3 ? __ldg(f.w3 + i) : 0.f; }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const int i = i0 + u * blockDim.x; if (i < n3) w3s[(i / NO) * (NO + 1) + i % NO] = t8[u]; }
+    }
     __syncthreads();
     for (int j = threadIdx.x; j < H; j += blockDim.x) {
         float w3r[32];
 #pragma unroll
-        for (int a = 0; a < 32; ++a) w3r[a] = a < NO ? __ldg(f.w3 + (size_t)j * NO + a) : 0.f;
+        for (int a = 0; a < 32; ++a) w3r[a] = a < NO ? w3s[j * (NO + 1) + a] : 0.f;
+        float old[DW3_RB];                           // the dw0 entries this thread adds to, all eight loads in flight
+#pragma unroll
+        for (int r = 0; r < DW3_RB; ++r) {
+            const int q = q0 + r;
+            old[r] = (q >= H && q < H + f.KP0 && q < nrows) ? f.dw0[(size_t)(q - H) * H + j] : 0.f;
+        }
 #pragma unroll
         for (int r = 0; r < DW3_RB; ++r) {
             const int q = q0 + r;
@@ -1640,7 +1657,7 @@ __device__ __forceinline__ void ts_rank_rows_body(const TsDw3Args& f, int bid, f
 #pragma unroll
             for (int a = 0; a < 32; ++a) if (a < NO) acc = fmaf(sm[r * NO + a], w3r[a], acc);
             if (q < H) f.dw2[(size_t)q * H + j] = acc;
-            else if (q < H + f.KP0) f.dw0[(size_t)(q - H) * H + j] += acc;
+            else if (q < H + f.KP0) f.dw0[(size_t)(q - H) * H + j] = old[r] + acc;
             else f.db2[j] = acc;
         }
     }
@@ -1698,7 +1715,11 @@ static int ts_dw3_assemble(dppo_handle* h, cudaStream_t s, int actor_net, const 
         nrc = phase == 0 ? tc_nblk((size_t)KP0r, DW3_RB) : tc_nblk((size_t)g.Hc, DW3_RB);
     }
     const int nba = tc_nblk((size_t)g.H, 32) * tsDW3KS();
-    auto smf = [&](const TsDw3Args& f) { const int K = f.H + f.A + f.Do + f.T; return (size_t)(((K + DW3_KS - 1) / DW3_KS) * f.NO + 16 * 32 * f.NO) * sizeof(float); };
+    auto smf = [&](const TsDw3Args& f) {
+        const int K = f.H + f.A + f.Do + f.T;
+        const size_t a = (size_t)(((K + DW3_KS - 1) / DW3_KS) * f.NO + 16 * 32 * f.NO), b = (size_t)(DW3_RB * f.NO + f.H * (f.NO + 1));
+        return (a > b ? a : b) * sizeof(float);
+    };
     auto kper = [&](const TsDw3Args& f) { return (f.H + f.A + f.Do + f.T + DW3_KS - 1) / DW3_KS; };
     const size_t sm = smf(fa) > smf(fc) ? smf(fa) : smf(fc);
     static bool attr_set_dev[64] = {};
